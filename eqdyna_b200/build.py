@@ -1,0 +1,139 @@
+"""Build recipes for the native parts (in-tree, so the .so files travel with the
+gpurun snapshot).
+
+  libeqdyna_host.so  -- stand-in Fortran host (g++, no CUDA)
+  libeqdyna_b200.so  -- the CUDA step library, sm_100a (nvcc)
+  eqdyna_host        -- standalone driver executable (links both)
+  oracle/_build/liboracle.so -- CPU oracle (test infrastructure; g++)
+
+`python -m eqdyna_b200.build [host|cuda|oracle|exe|all]`
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "eqdyna_b200")
+CSRC = os.path.join(PKG, "csrc")
+INC = os.path.join(ROOT, "include")
+LIBDIR = os.path.join(PKG, "lib")
+ORACLE = os.path.join(ROOT, "oracle")
+
+HOST_SRCS = ["eqh_io.cpp", "eqh_mesh.cpp", "eqh_mass.cpp", "eqh_api.cpp"]
+CUDA_SRCS = ["eqd_api.cu", "eqd_kernels.cu"]
+
+# the reference's ubuntu build is -O3 without -march / fast-math: no FMA contraction
+HOST_FLAGS = ["-O2", "-ffp-contract=off", "-fPIC", "-std=c++17", "-Wall", "-Wno-unused-variable"]
+NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources if os.path.exists(s))
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("build failed: %s\n%s" % (" ".join(cmd), r.stdout))
+    return r.stdout
+
+
+def _headers():
+    hs = [os.path.join(INC, f) for f in os.listdir(INC)]
+    for d in ("host", "cuda"):
+        p = os.path.join(CSRC, d)
+        if os.path.isdir(p):
+            hs += [os.path.join(p, f) for f in os.listdir(p) if f.endswith((".h", ".cuh"))]
+    return hs
+
+
+def host_lib_path():
+    return os.path.join(LIBDIR, "libeqdyna_host.so")
+
+
+def cuda_lib_path():
+    return os.path.join(LIBDIR, "libeqdyna_b200.so")
+
+
+def oracle_lib_path():
+    return os.path.join(ORACLE, "_build", "liboracle.so")
+
+
+def build_host(force=False):
+    os.makedirs(LIBDIR, exist_ok=True)
+    srcs = [os.path.join(CSRC, "host", s) for s in HOST_SRCS]
+    out = host_lib_path()
+    if force or _newer(out, srcs + _headers()):
+        _run(["g++"] + HOST_FLAGS + ["-shared", "-I", INC, "-o", out] + srcs)
+    return out
+
+
+def build_oracle(force=False):
+    os.makedirs(os.path.join(ORACLE, "_build"), exist_ok=True)
+    srcs = [os.path.join(ORACLE, "step_oracle.cpp")]
+    out = oracle_lib_path()
+    if force or _newer(out, srcs + _headers()):
+        _run(["g++"] + HOST_FLAGS + ["-fopenmp", "-shared", "-I", INC, "-o", out] + srcs)
+    return out
+
+
+def nccl_flags():
+    """NCCL: headers from the system package, library = the one torch loads
+    (torch-bundled libnccl.so.2) when present, else the system one."""
+    inc, libs = [], []
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        if spec and spec.submodule_search_locations:
+            base = list(spec.submodule_search_locations)[0]
+            if os.path.exists(os.path.join(base, "include", "nccl.h")):
+                inc = ["-I", os.path.join(base, "include")]
+            lib = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(lib):
+                libs = [lib, "-Xlinker", "-rpath", "-Xlinker", os.path.join(base, "lib")]
+    except Exception:
+        pass
+    if not libs:
+        libs = ["-lnccl"]
+    return inc, libs
+
+
+def build_cuda(force=False, extra=()):
+    os.makedirs(LIBDIR, exist_ok=True)
+    srcs = [os.path.join(CSRC, "cuda", s) for s in CUDA_SRCS]
+    out = cuda_lib_path()
+    if force or _newer(out, srcs + _headers()):
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        inc, libs = nccl_flags()
+        cmd = [nvcc, "-O3", "-std=c++17", "-lineinfo"] + NVCC_ARCH + [
+            "-Xcompiler", "-fPIC", "-shared", "-I", INC] + inc + list(extra) + ["-o", out] + srcs + libs
+        _run(cmd)
+    return out
+
+
+def build_exe(force=False):
+    host = build_host(force)
+    cuda = build_cuda(force)
+    src = os.path.join(CSRC, "host", "eqdyna_host_main.cpp")
+    out = os.path.join(PKG, "bin", "eqdyna_host")
+    if not os.path.exists(src):
+        return None
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    if force or _newer(out, [src, host, cuda] + _headers()):
+        _run(["g++"] + HOST_FLAGS + ["-I", INC, "-o", out, src, host, cuda,
+                                      "-Wl,-rpath," + LIBDIR])
+    return out
+
+
+def build_all(force=False):
+    return {"host": build_host(force), "cuda": build_cuda(force), "oracle": build_oracle(force)}
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    fn = {"host": build_host, "cuda": build_cuda, "oracle": build_oracle, "exe": build_exe, "all": build_all}[what]
+    print(fn(force="--force" in sys.argv))

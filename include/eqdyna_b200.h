@@ -1,0 +1,159 @@
+/*
+ * eqdyna_b200.h -- C ABI of libeqdyna_b200.so, the B200 (sm_100a) step library
+ * that replaces the body of EQdyna's `subroutine driver`.
+ *
+ * Reference boundary: src/driver.f90:3-36 (the step loop), called from
+ * src/eqdyna3d.f90:72.  Everything the loop reads is module `globalvar`
+ * (src/globalvar.f90:81-101, shapes from src/eqdyna3d.f90:98-172); every
+ * eqd_set_* argument below is one of those arrays, passed AS ALLOCATED BY THE
+ * FORTRAN HOST: column-major, 1-based indices inside integer arrays.  The
+ * library copies at eqd_set_*; the host keeps ownership.  Results come back
+ * only through eqd_fetch into caller-owned buffers of the original shape.
+ *
+ * All entry points return 0 on success or one of the EQD_ERR_* codes; no C++
+ * exception crosses this boundary.  The matching ISO_C_BINDING interface is
+ * eqdyna_b200/csrc/fortran/eqdyna_cuda_iface.f90; INTEGRATION.md shows the
+ * replacement driver.
+ */
+#ifndef EQDYNA_B200_H
+#define EQDYNA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes (mirror the reference's `stop` sites) ------------------- */
+#define EQD_OK 0
+#define EQD_ERR_NAN 1      /* velocity NaN            (driver.f90:147-152)   */
+#define EQD_ERR_DAMP 2     /* negative PML damping    (comdampv.f90:114-118) */
+#define EQD_ERR_CUDA 3     /* CUDA / NCCL failure                            */
+#define EQD_ERR_ARG 4      /* bad argument / wrong call order                */
+
+/* ---- scalars of module globalvar the step loop reads --------------------- */
+typedef struct eqd_params {
+  /* time stepping (readInputFiles.f90:182-186) */
+  double dt;            /* globalvar dt                                      */
+  int32_t nstep;        /* idnint(totalSimuTime/dt)                          */
+  int32_t me;           /* MPI rank id = mex*npy*npz + mey*npz + mez         */
+  int32_t npx, npy, npz;
+  /* damping / element constants */
+  double rdampk;        /* ALREADY multiplied by dt (readInputFiles.f90:185) */
+  double rdampm;        /* 0 in the reference (globalvar.f90:16)             */
+  double w;             /* 8.0, one-point Gauss weight                       */
+  double grav, roumax, rhow, gamar;
+  double ccosphi, sinphi, tv; /* Drucker-Prager (readInputFiles.f90:182-186) */
+  double kapa_hg;       /* viscous hourglass coefficient (C_hg==2)           */
+  double dx;            /* used by the Q class index only                    */
+  int32_t C_elastic, C_Q, C_hg;
+  /* PML */
+  double PMLb[8];       /* meshgen.f90:532-549                               */
+  int32_t nPML;
+  double R;             /* theoretical reflection coefficient                */
+  double vmaxPML;
+  /* fault */
+  int32_t friclaw, C_nuclea, nucfault, TPV, insertFaultType, ntotft;
+  double nucR, nucT, nucRuptVel, nucdtau0;
+  double xsource, ysource, zsource;
+  double slipRateThres;
+  double tol;           /* 1e-5, hypocentre-pair match (faulting.f90:349)    */
+  double fric_tp_h;     /* global never assigned in the reference => 0       */
+  int32_t outputGroundMotion;
+  int32_t reserved_i[7];
+  double reserved_d[8];
+} eqd_params;
+
+typedef struct eqd_handle eqd_handle;
+
+/* which-codes of eqd_fetch: destination must have the Fortran shape given.  */
+enum {
+  EQD_F_DISP = 1,        /* dispArr(3,Nn)                                    */
+  EQD_F_VEL = 2,         /* velArr(3,Nn)                                     */
+  EQD_F_V1 = 3,          /* v1(Neq)                                          */
+  EQD_F_FORCE = 4,       /* nodalForceArr(Neq)  (= f/m after the last step)  */
+  EQD_F_FRIC = 5,        /* fric(100,nftmx,ntotft)                           */
+  EQD_F_FNFT = 6,        /* fnft(nftmx,ntotft)                               */
+  EQD_F_PSTRAIN = 7,     /* pstrain(Ne)                                      */
+  EQD_F_STRESS = 8,      /* stressArr(sizeStress)                            */
+  EQD_F_ONFAULT_HIST = 9,  /* onFaultQuantHistSCECForm(12,nstep,nOn)         */
+  EQD_F_OFFFAULT_HIST = 10,/* OffFaultStGramSCEC(6*nOff+1,nstep)             */
+  EQD_F_HYPO_LOG = 11,   /* (13,nstep): what showSourceDynamics prints       */
+  EQD_F_GM = 12,         /* (3,nSurf,nGmSamples) output_gm samples           */
+  EQD_F_SRC_EVOL = 13,   /* (nftnd(1),nGmSamples) output_src_evol samples    */
+  EQD_F_TPHIST = 14,     /* onFaultTPHist(2,nftmx,nstep,ntotft), friclaw 5   */
+  EQD_F_MASS = 15,       /* nodalMassArr(Neq) (after eqd_sum_shared)         */
+  EQD_F_FNMS = 16,       /* fnms(Nn)                                         */
+  EQD_F_ARN = 17         /* arn(nftmx,ntotft)                                */
+};
+
+/* timing slots of eqd_get_timing (ms, CUDA events) -- the reference's
+ * compTimeInSeconds(3..6)+MPICommTimeInSeconds (library_output.f90:208-218) */
+enum {
+  EQD_T_TOTAL = 0, EQD_T_NODE = 1, EQD_T_ELEM = 2, EQD_T_ASSEMBLE = 3,
+  EQD_T_HALO = 4, EQD_T_FAULT = 5, EQD_T_NSLOTS = 8
+};
+
+/* -- lifecycle ------------------------------------------------------------- */
+int eqd_create(const eqd_params* p, int device, eqd_handle** out);
+int eqd_destroy(eqd_handle* h);
+int eqd_last_error(const eqd_handle* h, char* buf, int n);
+
+/* -- state upload (each replaces reading the named globalvar arrays) ------- */
+/* mesh: meshgen.f90 outputs.  nodeElemIdRelation(8,Ne), eqNumIndexArr(sizeEq) */
+int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t sizeEq,
+                 const double* meshCoor, const int32_t* nodeElemIdRelation,
+                 const int32_t* elemTypeArr, const int32_t* numOfDofPerNodeArr,
+                 const int32_t* eqNumStartIndexLoc, const int32_t* eqNumIndexArr,
+                 const int32_t* stressCompIndexArr, int32_t sizeStress);
+/* element operators: assembleGlobalMass.f90:283-374 outputs.
+ * eleshp(3,8,Ne) eledet(Ne) elemass(24,Ne) mat(Ne,5) ss(6,Ne) phi(8,4,Ne)    */
+int eqd_set_elem_ops(eqd_handle* h, const double* eleshp, const double* eledet,
+                     const double* elemass, const double* mat, const double* ss,
+                     const double* phi, const double* eleporep,
+                     const double* stressArr, const double* pstrain);
+/* nodal state: nodalMassArr(Neq) fnms(Nn) v1(Neq) velArr(3,Nn) dispArr(3,Nn)
+ * nodalForceArr(Neq) (acceleration left by a previous run; may be NULL = 0) */
+int eqd_set_nodal(eqd_handle* h, const double* nodalMassArr, const double* fnms,
+                  const double* v1, const double* velArr, const double* dispArr,
+                  const double* nodalForceArr);
+/* fault: nsmp(2,nftmx,ntotft) un/us/ud(3,nftmx,ntotft) arn(nftmx,ntotft)
+ * fric(100,nftmx,ntotft) fnft(nftmx,ntotft)                                  */
+int eqd_set_fault(eqd_handle* h, int32_t nftmx, const int32_t* nftnd,
+                  const int32_t* nsmp, const double* un, const double* us,
+                  const double* ud, const double* arn, const double* fric,
+                  const double* fnft);
+/* halo description: numcount(9) fltnum(6) fltMPI(6 as int) and the six face
+ * split-node lists (meshgen.f90:209-254); NULL lists allowed when count==0   */
+int eqd_set_halo(eqd_handle* h, const int32_t* numcount, const int32_t* fltnum,
+                 const int32_t* fltMPI, const int32_t* fltl, const int32_t* fltr,
+                 const int32_t* fltf, const int32_t* fltb, const int32_t* fltd,
+                 const int32_t* fltu);
+/* stations: idhist(3,6*nOff) anonfs(3,nOn) surfaceNodeIdArr(nSurf)           */
+int eqd_set_stations(eqd_handle* h, const int32_t* idhist, int32_t nOff,
+                     const int32_t* anonfs, int32_t nOn,
+                     const int32_t* surfaceNodeIdArr, int32_t nSurf);
+
+/* -- multi-GPU: one process (or thread) per sub-domain ---------------------- */
+/* 128-byte ncclUniqueId made by rank 0 and broadcast by the host (MPI_Bcast) */
+int eqd_get_unique_id(void* id128);
+int eqd_set_comm(eqd_handle* h, const void* id128, int32_t nranks, int32_t rank);
+/* init-time shared-node sums the reference does with MPI before the loop:
+ * nodalMassArr, fnms (assembleGlobalMass.f90:40-41) and arn (meshgen.f90:154).
+ * Call once after eqd_set_* if the host has NOT already summed them.         */
+int eqd_sum_shared(eqd_handle* h);
+
+/* -- run steps nt_begin..nt_end inclusive (1-based like `do nt = 1, nstep`) - */
+int eqd_run(eqd_handle* h, int32_t nt_begin, int32_t nt_end);
+int eqd_fetch(eqd_handle* h, int32_t which, void* dst, int64_t dst_bytes);
+/* algorithmic counters for the benchmark: elements by type, kernel launches */
+int eqd_get_counts(const eqd_handle* h, int64_t* n_regular, int64_t* n_pml,
+                   int64_t* n_pairs, int64_t* launches);
+int eqd_get_timing(const eqd_handle* h, double* ms_slots /*[EQD_T_NSLOTS]*/);
+/* options: key in {"graph","overlap","timing","block"}; see DESIGN.md          */
+int eqd_set_option(eqd_handle* h, const char* key, int32_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
