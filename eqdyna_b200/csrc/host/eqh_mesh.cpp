@@ -302,8 +302,9 @@ void meshgen(const CaseInput& in, RankState& s) {
           double peak = in.rough_geo[0 + 3 * idx];
           pfx = in.rough_geo[1 + 3 * idx];
           pfz = in.rough_geo[2 + 3 * idx];
-          if (nodeCoor[1] > -tol) ycoort = nodeCoor[1] * (in.ymax - peak) / in.ymax + peak;
-          else if (nodeCoor[1] < -tol) ycoort = nodeCoor[1] * (peak - in.ymin) / (-in.ymin) + peak;
+          // ymax / ymin are the globals overwritten with modelBoundCoor at meshgen.f90:33-34
+          if (nodeCoor[1] > -tol) ycoort = nodeCoor[1] * (s.ymaxB - peak) / s.ymaxB + peak;
+          else if (nodeCoor[1] < -tol) ycoort = nodeCoor[1] * (peak - s.yminB) / (-s.yminB) + peak;
           X[1 + 3 * (size_t)(nodeCount - 1)] = ycoort;
         }
         // setNumDof, meshgen.f90:562-572
