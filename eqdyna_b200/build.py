@@ -82,8 +82,9 @@ def build_oracle(force=False):
 
 
 def nccl_flags():
-    """NCCL: headers from the system package, library = the one torch loads
-    (torch-bundled libnccl.so.2) when present, else the system one."""
+    """NCCL is dlopen'ed at run time (eqd_api.cu): headers from the torch-bundled
+    package when present (else /usr/include/nccl.h); the bundled library's path is
+    baked in as a fallback for processes that have not loaded libnccl.so.2 yet."""
     inc, libs = [], []
     try:
         import importlib.util
@@ -94,12 +95,10 @@ def nccl_flags():
                 inc = ["-I", os.path.join(base, "include")]
             lib = os.path.join(base, "lib", "libnccl.so.2")
             if os.path.exists(lib):
-                libs = [lib, "-Xlinker", "-rpath", "-Xlinker", os.path.join(base, "lib")]
+                libs = ['-DEQD_NCCL_PATH="%s"' % lib]
     except Exception:
         pass
-    if not libs:
-        libs = ["-lnccl"]
-    return inc, libs
+    return inc, libs + ["-ldl"]
 
 
 def build_cuda(force=False, extra=()):

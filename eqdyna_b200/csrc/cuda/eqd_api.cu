@@ -1,0 +1,1278 @@
+// C ABI of libeqdyna_b200.so (include/eqdyna_b200.h): state upload, the step
+// loop of src/driver.f90:9-34 as a sequence of sm_100a kernels, halo exchange
+// (MPI4NodalQuant, src/assembleGlobalMass.f90:58-281) over NCCL send/recv or,
+// for several sub-domains driven by one process, over device-to-device copies.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "eqd_dev.cuh"
+#include "eqd_kernels.h"
+#include "eqdyna_b200.h"
+
+#ifndef EQD_NCCL_PATH
+#define EQD_NCCL_PATH ""
+#endif
+
+using namespace eqd;
+
+namespace {
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct ArgError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+#define CK(x)                                                                                      \
+  do {                                                                                             \
+    cudaError_t e_ = (x);                                                                          \
+    if (e_ != cudaSuccess)                                                                         \
+      throw CudaError(std::string(#x) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void alloc(size_t count, bool zero = true) {
+    release();
+    n = count;
+    if (count == 0) return;
+    CK(cudaMalloc(&p, count * sizeof(T)));
+    if (zero) CK(cudaMemset(p, 0, count * sizeof(T)));
+  }
+  void upload(const std::vector<T>& h) {
+    alloc(h.size(), false);
+    if (!h.empty()) CK(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  }
+  std::vector<T> download() const {
+    std::vector<T> h(n);
+    if (n) CK(cudaMemcpy(h.data(), p, n * sizeof(T), cudaMemcpyDeviceToHost));
+    return h;
+  }
+};
+
+inline int pad32(long n) { return (int)((n + 31) / 32 * 32); }
+
+// ---- NCCL through dlopen: the library must load (and export its symbols) on a
+// box without NCCL; the communicator is only needed for multi-process runs.
+struct Nccl {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::string why;
+  bool load() {
+    if (lib) return true;
+    const char* names[] = {getenv("EQD_NCCL_LIB"), "libnccl.so.2", EQD_NCCL_PATH, "libnccl.so"};
+    for (const char* nm : names) {
+      if (!nm || !*nm) continue;
+      lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+      why = dlerror();
+    }
+    if (!lib) return false;
+#define SYM(f) f = (decltype(f))dlsym(lib, "nccl" #f); if (!f) { why = "missing nccl" #f; lib = nullptr; return false; }
+    SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(Send) SYM(Recv) SYM(GroupStart) SYM(GroupEnd) SYM(GetErrorString)
+#undef SYM
+    return true;
+  }
+};
+Nccl g_nccl;
+
+#define NK(x)                                                                               \
+  do {                                                                                      \
+    ncclResult_t r_ = (x);                                                                  \
+    if (r_ != ncclSuccess) throw CudaError(std::string(#x) + ": " + g_nccl.GetErrorString(r_)); \
+  } while (0)
+
+struct ElemClass {
+  int n = 0, S = 0, nf = 24, nstress = 6;
+  std::vector<int> refId;  // slot -> reference element (0-based)
+  DevBuf<int> conn;
+  DevBuf<double> shp, phi, ss, lam, mu, det, rho, vp, stress, qmem, porep, pstrain, emass, damps, ef;
+  DevBuf<uint8_t> qcls;
+};
+
+struct Face {
+  int n = 0;       // doubles exchanged
+  int nb = -1;     // neighbour rank, -1 = inactive
+  DevBuf<uint32_t> idx;
+  DevBuf<double> send, recv;
+  // init-time node-wise exchange (mass, fnms) and pair-wise (arn)
+  std::vector<int> nodes;   // face node ids (0-based), reference order, incl. face masters
+  std::vector<int> pairs;   // fault pair slots on this face (device pair index)
+};
+
+}  // namespace
+
+struct eqd_handle {
+  eqd_params p{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  // ---- host copies (0-based where noted)
+  int Nn = 0, Ne = 0, Neq = 0, sizeEq = 0, sizeStress = 0;
+  std::vector<int> conn;       // (8,Ne) 0-based
+  std::vector<int> etype, ndof, eqStart, eqIdx, stressIdx;
+  std::vector<double> coor;    // (3,Nn)
+  std::vector<int> info;       // per node
+  std::vector<int> elemCode;   // per element: class | slot<<2
+  std::vector<double> fnmsH, massH;
+  int NnS = 0, Np = 0, NpS = 0;
+  bool body = false, plastic = false, qmode = false;
+  // ---- device
+  ElemClass cls[3];
+  DevBuf<int> dInfo, dAdjStart, dSpecial;
+  DevBuf<uint32_t> dAdj;
+  DevBuf<double> dVel, dDisp, dMass, dV1p, dDampp, dForce, dAccel0;
+  int nSpecial = 0;
+  DevBuf<StepState> dState;
+  // fault
+  int nftmx = 0, ntotft = 0, nPairs = 0, PS = 0;
+  std::vector<int> nftnd, pairRef;  // pairRef: device pair -> (i-1) + nftmx*ift
+  std::vector<int> pairNodeS, pairNodeM;
+  DevBuf<int> dNodeS, dNodeM, dIft, dPairStation;
+  DevBuf<double> dUn, dUs, dUd, dArn, dMassS, dMassM, dXs, dFric, dFnft;
+  // stations / histories
+  int nOff = 0, nOn = 0, nOnAlloc = 1, nSurf = 0, nGm = 0;
+  std::vector<int> idhistH, anonfsH, surfH;
+  DevBuf<int> dIdhist, dSurf;
+  DevBuf<double> dOnHist, dOffHist, dHypo, dTpHist, dGm, dSrc;
+  // halo
+  bool haloSet = false;
+  int numcount[9] = {0}, fltnum[6] = {0}, fltMPI[6] = {0};
+  std::vector<int> fltface[6];
+  Face face[3][2];
+  ncclComm_t comm = nullptr;
+  int nranks = 1, rank = 0;
+  cudaEvent_t evPacked[3] = {nullptr, nullptr, nullptr};
+  // run state
+  bool meshSet = false, opsSet = false, nodalSet = false, faultSet = false, finalized = false;
+  int hostNt = 0;
+  double hostTime = 0.0;
+  long launches = 0;
+  bool timing = false;
+  int optGraph = 0, optBlock = 0;
+  double tms[EQD_T_NSLOTS] = {0};
+  std::vector<cudaEvent_t> evs;  // timing events
+
+  NodeArgs nodeArgs() const;
+  ElemArgs elemArgs(int c) const;
+  FaultArgs faultArgs() const;
+};
+
+namespace {
+
+template <class F>
+int guarded(eqd_handle* h, F&& f) {
+  try {
+    if (h) CK(cudaSetDevice(h->device));
+    f();
+    return EQD_OK;
+  } catch (const ArgError& e) {
+    if (h) h->err = e.what();
+    return EQD_ERR_ARG;
+  } catch (const CudaError& e) {
+    if (h) h->err = e.what();
+    return EQD_ERR_CUDA;
+  } catch (const std::exception& e) {
+    if (h) h->err = e.what();
+    return EQD_ERR_ARG;
+  }
+}
+
+// comdampv.f90:1-120 for one PML node (returns the three distinct profile values)
+bool comdampv(const eqd_params& P, double x2, double y, double z, double out[3]) {
+  const double xmax0 = P.PMLb[0], xmin0 = P.PMLb[1], ymax0 = P.PMLb[2], ymin0 = P.PMLb[3], zmin0 = P.PMLb[4];
+  const double maxd[3] = {P.PMLb[5], P.PMLb[6], P.PMLb[7]};
+  double damp[3] = {0, 0, 0};
+  bool any = false;
+  if (z <= zmin0) { damp[2] = std::fabs(z - zmin0); any = true; }
+  else if (z > zmin0) { damp[2] = 0.0; any = true; }
+  if (any) {
+    if (x2 >= xmax0 && y >= ymax0) { damp[0] = std::fabs(x2 - xmax0); damp[1] = std::fabs(y - ymax0); }
+    else if (x2 >= xmax0 && y <= ymin0) { damp[0] = std::fabs(x2 - xmax0); damp[1] = std::fabs(y - ymin0); }
+    else if (x2 <= xmin0 && y <= ymin0) { damp[0] = std::fabs(x2 - xmin0); damp[1] = std::fabs(y - ymin0); }
+    else if (x2 <= xmin0 && y >= xmax0) { damp[0] = std::fabs(x2 - xmin0); damp[1] = std::fabs(y - ymax0); }  // sic, comdampv.f90:29,61
+    else if (x2 >= xmax0 && y > ymin0 && y < ymax0) { damp[0] = std::fabs(x2 - xmax0); damp[1] = 0.0; }
+    else if (y <= ymin0 && x2 > xmin0 && x2 < xmax0) { damp[0] = 0.0; damp[1] = std::fabs(y - ymin0); }
+    else if (x2 <= xmin0 && y > ymin0 && y < ymax0) { damp[0] = std::fabs(x2 - xmin0); damp[1] = 0.0; }
+    else if (y >= ymax0 && x2 > xmin0 && x2 < xmax0) { damp[0] = 0.0; damp[1] = std::fabs(y - ymax0); }
+    else { damp[0] = 0.0; damp[1] = 0.0; }
+  }
+  for (int i = 0; i < 3; ++i) {
+    const double delta = P.nPML * maxd[i];
+    out[i] = 3.0 * P.vmaxPML / 2.0 / delta * std::log(1.0 / P.R) * ((damp[i] / delta) * (damp[i] / delta));
+  }
+  return !(out[0] < 0.0 || out[1] < 0.0 || out[2] < 0.0);
+}
+
+// damping profile at a PML element's centroid, assembleGlobalKU.f90:121-213
+void pml_elem_damps(const eqd_params& P, const double xc[3], double out[3]) {
+  const double xmax2 = P.PMLb[0], xmin2 = P.PMLb[1], ymax2 = P.PMLb[2], ymin2 = P.PMLb[3], zmin2 = P.PMLb[4];
+  const double maxd[3] = {P.PMLb[5], P.PMLb[6], P.PMLb[7]};
+  double d[3] = {0, 0, 0};
+  bool any = false;
+  if (xc[2] < zmin2) { d[2] = std::fabs(xc[2] - zmin2); any = true; }
+  else if (xc[2] > zmin2) { d[2] = 0.0; any = true; }
+  if (any) {
+    if (xc[0] > xmax2 && xc[1] > ymax2) { d[0] = std::fabs(xc[0] - xmax2); d[1] = std::fabs(xc[1] - ymax2); }
+    else if (xc[0] > xmax2 && xc[1] < ymin2) { d[0] = std::fabs(xc[0] - xmax2); d[1] = std::fabs(xc[1] - ymin2); }
+    else if (xc[0] < xmin2 && xc[1] < ymin2) { d[0] = std::fabs(xc[0] - xmin2); d[1] = std::fabs(xc[1] - ymin2); }
+    else if (xc[0] < xmin2 && xc[1] > xmax2) { d[0] = std::fabs(xc[0] - xmin2); d[1] = std::fabs(xc[1] - ymax2); }  // sic, :150,:182
+    else if (xc[0] > xmax2 && xc[1] > ymin2 && xc[1] < ymax2) { d[0] = std::fabs(xc[0] - xmax2); d[1] = 0.0; }
+    else if (xc[1] < ymin2 && xc[0] > xmin2 && xc[0] < xmax2) { d[0] = 0.0; d[1] = std::fabs(xc[1] - ymin2); }
+    else if (xc[0] < xmin2 && xc[1] > ymin2 && xc[1] < ymax2) { d[0] = std::fabs(xc[0] - xmin2); d[1] = 0.0; }
+    else if (xc[1] > ymax2 && xc[0] > xmin2 && xc[0] < xmax2) { d[0] = 0.0; d[1] = std::fabs(xc[1] - ymax2); }
+    else { d[0] = 0.0; d[1] = 0.0; }
+  }
+  for (int i = 0; i < 3; ++i) {
+    const double delta = P.nPML * maxd[i];
+    out[i] = 3 * P.vmaxPML / 2 / delta * std::log(1 / P.R) * ((d[i] / delta) * (d[i] / delta));
+  }
+}
+
+// qconstant.f90:3-35 (single-precision literal tables, as in the reference)
+void qconstant(double Q, int k, double& rtaok, double& rwk, double& c1) {
+  static const float taok[8] = {1.72333e-3f, 1.80701e-3f, 5.38887e-3f, 1.99322e-2f, 8.49833e-2f, 4.09335e-1f, 2.05951f, 13.2629f};
+  static const float alfk[8] = {1.66958e-2f, 3.81644e-2f, 9.84666e-3f, -1.36803e-2f, -2.85125e-2f, -5.37309e-2f, -6.65035e-2f, -1.33696e-1f};
+  static const float betk[8] = {8.98758e-2f, 6.84635e-2f, 9.67052e-2f, 1.20172e-1f, 1.30728e-1f, 1.38746e-1f, 1.40705e-1f, 2.14647e-1f};
+  const double pi = 4 * std::atan(1.0);
+  double kapa = (double)3.071f + (double)1.433f * std::pow(Q, (double)(-1.158f)) * std::log(Q / 5);
+  kapa = kapa / (1 + (double)0.415f * Q);
+  rwk = kapa * (kapa * (double)alfk[k - 1] + (double)betk[k - 1]);
+  rtaok = (double)taok[k - 1];
+  const double ref = 2.0 * pi;
+  const double ak0 = 1.0 - rwk * 8.0 / (1.0 + (rtaok * ref) * (rtaok * ref));
+  const double bk0 = rwk * 8.0 * ref * rtaok / (1.0 + (rtaok * ref) * (rtaok * ref));
+  c1 = 0.5 * std::pow(ak0 * ak0 + bk0 * bk0, -0.5);
+  c1 = c1 * (1.0 + ak0 * std::pow(ak0 * ak0 + bk0 * bk0, -0.5));
+}
+
+void need(bool ok, const char* msg) { if (!ok) throw ArgError(msg); }
+
+}  // namespace
+
+NodeArgs eqd_handle::nodeArgs() const {
+  NodeArgs A{};
+  A.Nn = Nn; A.NnS = NnS; A.Np = Np; A.NpS = NpS;
+  A.info = dInfo.p; A.vel = dVel.p; A.disp = dDisp.p; A.mass = dMass.p;
+  A.v1p = dV1p.p; A.dampp = dDampp.p; A.force = dForce.p;
+  A.adjStart = dAdjStart.p; A.adj = dAdj.p;
+  A.efR = cls[CLS_REG].ef.p; A.SR = cls[CLS_REG].S;
+  A.efX = cls[CLS_REGX].ef.p; A.SX = cls[CLS_REGX].S;
+  A.efP = cls[CLS_PML].ef.p; A.SP = cls[CLS_PML].S;
+  A.accel0 = nullptr;
+  A.dt = p.dt;
+  A.st = dState.p;
+  return A;
+}
+
+ElemArgs eqd_handle::elemArgs(int c) const {
+  const ElemClass& C = cls[c];
+  ElemArgs A{};
+  A.n = C.n; A.S = C.S;
+  A.conn = C.conn.p; A.shp = C.shp.p; A.phi = C.phi.p; A.ss = C.ss.p;
+  A.lam = C.lam.p; A.mu = C.mu.p; A.det = C.det.p; A.rho = C.rho.p; A.vp = C.vp.p;
+  A.stress = C.stress.p; A.qmem = C.qmem.p; A.qcls = C.qcls.p;
+  A.porep = C.porep.p; A.pstrain = C.pstrain.p; A.emass = C.emass.p; A.damps = C.damps.p;
+  A.ef = C.ef.p;
+  A.vel = dVel.p; A.disp = dDisp.p; A.NnS = NnS;
+  A.dt = p.dt; A.rdampk = p.rdampk; A.rdampm = p.rdampm; A.w = p.w;
+  // assembleGlobalKU.f90:16
+  A.bodyz = (1.0 - p.C_elastic) * p.grav * (p.roumax - (p.gamar + 1.0) * p.rhow) / p.roumax;
+  A.ccosphi = p.ccosphi; A.sinphi = p.sinphi;
+  A.expdttv = p.tv != 0.0 ? std::exp(-p.dt / p.tv) : 0.0;
+  A.kapa_hg = p.kapa_hg;
+  return A;
+}
+
+FaultArgs eqd_handle::faultArgs() const {
+  FaultArgs A{};
+  A.nPairs = nPairs; A.PS = PS; A.NnS = NnS;
+  A.nodeS = dNodeS.p; A.nodeM = dNodeM.p; A.ift = dIft.p;
+  A.un = dUn.p; A.us = dUs.p; A.ud = dUd.p; A.arn = dArn.p; A.massS = dMassS.p; A.massM = dMassM.p;
+  A.xs = dXs.p; A.fric = dFric.p; A.fnft = dFnft.p;
+  A.vel = dVel.p; A.disp = dDisp.p; A.force = dForce.p;
+  A.pairStation = dPairStation.p; A.onHist = dOnHist.p; A.nstep = p.nstep;
+  A.hypoLog = dHypo.p; A.tphist = dTpHist.p;
+  A.st = dState.p;
+  A.dt = p.dt; A.nucR = p.nucR; A.nucT = p.nucT; A.nucRuptVel = p.nucRuptVel; A.nucdtau0 = p.nucdtau0;
+  A.xsource = p.xsource; A.ysource = p.ysource; A.zsource = p.zsource;
+  A.slipRateThres = p.slipRateThres; A.tol = p.tol; A.fric_tp_h = p.fric_tp_h;
+  A.friclaw = p.friclaw; A.C_nuclea = p.C_nuclea; A.nucfault = p.nucfault; A.TPV = p.TPV;
+  A.insertFaultType = p.insertFaultType; A.C_elastic = p.C_elastic;
+  return A;
+}
+
+namespace {
+
+// ---------------------------------------------------------------------------
+// face dof / node lists in the order of processNodalQuantArr
+// (assembleGlobalMass.f90:141-188): x-face (iz,iy), y-face (ix,iz), z-face
+// (ix,iy), then the face's split-node masters.
+void face_nodes(const eqd_handle& h, int a, int side, std::vector<int>& out) {
+  out.clear();
+  const int nx = h.numcount[0], ny = h.numcount[1], nz = h.numcount[2];
+  const int n[3] = {nx, ny, nz};
+  const int b = side == 0 ? 1 : n[a];
+  auto id = [&](int ix, int iy, int iz) { return (ix - 1) * ny * nz + (iz - 1) * ny + iy - 1; };
+  if (a == 0) {
+    for (int iz = 1; iz <= nz; ++iz) for (int iy = 1; iy <= ny; ++iy) out.push_back(id(b, iy, iz));
+  } else if (a == 1) {
+    for (int ix = 1; ix <= nx; ++ix) for (int iz = 1; iz <= nz; ++iz) out.push_back(id(ix, b, iz));
+  } else {
+    for (int ix = 1; ix <= nx; ++ix) for (int iy = 1; iy <= ny; ++iy) out.push_back(id(ix, iy, b));
+  }
+  if (h.fltMPI[2 * a + side])
+    for (int k : h.fltface[2 * a + side]) out.push_back(nx * ny * nz + k - 1);
+}
+
+void finalize(eqd_handle* h) {
+  if (h->finalized) return;
+  need(h->meshSet && h->opsSet && h->nodalSet, "eqd_run: eqd_set_mesh, eqd_set_elem_ops and eqd_set_nodal must be called first");
+  const eqd_params& P = h->p;
+  const int Nn = h->Nn;
+  // ---- special nodes: split-node pairs + active rank faces
+  std::vector<char> special(Nn, 0);
+  for (int q = 0; q < h->nPairs; ++q) { special[h->pairNodeS[q]] = 1; special[h->pairNodeM[q]] = 1; }
+  const int np[3] = {P.npx, P.npy, P.npz};
+  const int me = P.me;
+  const int mex = me / (P.npy * P.npz), mey = (me - mex * P.npy * P.npz) / P.npz, mez = me - mex * P.npy * P.npz - mey * P.npz;
+  const int mexyz[3] = {mex, mey, mez};
+  const int stride[3] = {P.npy * P.npz, P.npz, 1};
+  const size_t NS = h->NnS, PSn = h->NpS;
+  if (h->haloSet) {
+    for (int a = 0; a < 3; ++a)
+      for (int side = 0; side < 2; ++side) {
+        Face& F = h->face[a][side];
+        const bool active = np[a] > 1 && (side == 0 ? mexyz[a] != 0 : mexyz[a] != np[a] - 1);
+        if (!active) { F.nb = -1; F.n = 0; continue; }
+        F.nb = me + (side == 0 ? -stride[a] : stride[a]);
+        face_nodes(*h, a, side, F.nodes);
+        std::vector<uint32_t> idx;
+        for (int n : F.nodes) {
+          need(n >= 0 && n < Nn, "eqd_set_halo: face node out of range");
+          const int kind = EQD_INFO_KIND(h->info[n]);
+          if (kind == KIND_FIXED) continue;
+          special[n] = 1;
+          if (kind == KIND_FREE3) for (int j = 0; j < 3; ++j) idx.push_back((uint32_t)(j * NS + n));
+          else { const size_t slot = EQD_INFO_SLOT(h->info[n]); for (int j = 0; j < 12; ++j) idx.push_back((uint32_t)(3 * NS + j * PSn + slot)); }
+        }
+        // cross-check with the reference's own count (numcount(4:9) + 3*fltnum)
+        const int expect = h->numcount[3 + 2 * a + side] + (h->fltMPI[2 * a + side] ? 3 * h->fltnum[2 * a + side] : 0);
+        if ((int)idx.size() != expect)
+          throw ArgError("halo face dof count differs from numcount/fltnum: " + std::to_string(idx.size()) + " vs " + std::to_string(expect));
+        F.n = (int)idx.size();
+        F.idx.upload(idx);
+        F.send.alloc(F.n); F.recv.alloc(F.n);
+        // pairs on this face (for the init-time arn exchange, MPI4arn)
+        F.pairs.clear();
+        if (h->fltMPI[2 * a + side])
+          for (int k : h->fltface[2 * a + side]) {
+            // pair (k, fault ntotft) -> device pair slot
+            const int ref = (k - 1) + h->nftmx * (h->ntotft - 1);
+            int slot = -1;
+            for (int q = 0; q < h->nPairs; ++q) if (h->pairRef[q] == ref) { slot = q; break; }
+            need(slot >= 0, "eqd_set_halo: face pair not found");
+            F.pairs.push_back(slot);
+          }
+      }
+    for (int a = 0; a < 3; ++a) CK(cudaEventCreateWithFlags(&h->evPacked[a], cudaEventDisableTiming));
+  }
+  std::vector<int> list;
+  for (int n = 0; n < Nn; ++n)
+    if (special[n] && EQD_INFO_KIND(h->info[n]) != KIND_FIXED) { h->info[n] |= 4; list.push_back(n); }
+  h->nSpecial = (int)list.size();
+  h->dSpecial.upload(list);
+  h->dInfo.upload(h->info);
+  // ---- stations
+  std::vector<int> pairStation(std::max(h->PS, 1), -1);
+  for (int j = 0; j < h->nOn; ++j) {
+    const int i = h->anonfsH[3 * j], ift = h->anonfsH[3 * j + 2];
+    const int ref = (i - 1) + h->nftmx * (ift - 1);
+    for (int q = 0; q < h->nPairs; ++q)
+      if (h->pairRef[q] == ref) pairStation[q] = j;  // last matching station wins, as the reference's loop
+  }
+  h->dPairStation.upload(pairStation);
+  h->nOnAlloc = std::max(h->nOn, 1);
+  const size_t nstep = (size_t)std::max(P.nstep, 1);
+  h->dOnHist.alloc(12 * nstep * h->nOnAlloc);
+  if (h->nOff > 0) h->dOffHist.alloc((size_t)(6 * h->nOff + 1) * nstep);
+  h->dHypo.alloc(13 * nstep);
+  if (P.friclaw == 5 && h->nPairs > 0) h->dTpHist.alloc(2 * nstep * h->PS);
+  if (P.outputGroundMotion) {
+    h->nGm = 0;
+    const size_t ns = nstep / 10 + 1;
+    if (h->nSurf > 0) h->dGm.alloc(3 * (size_t)h->nSurf * ns);
+    if (h->nPairs > 0) h->dSrc.alloc((size_t)h->nftnd[0] * ns);
+  }
+  std::vector<StepState> st(1);
+  st[0].timeElapsed = 0.0; st[0].nt = 0; st[0].nanFlag = 0; st[0].nanNode = 0; st[0].pad = 0;
+  h->dState.upload(st);
+  h->hostNt = 0; h->hostTime = 0.0;
+  h->finalized = true;
+}
+
+// transport of one axis phase between processes (NCCL) -- pack/unpack by caller
+void halo_axis_nccl(eqd_handle* h, int a) {
+  if (!h->comm) throw ArgError("eqd_run: sub-domain has neighbours but eqd_set_comm was not called");
+  NK(g_nccl.GroupStart());
+  for (int side = 0; side < 2; ++side) {
+    Face& F = h->face[a][side];
+    if (F.nb < 0 || F.n == 0) continue;
+    NK(g_nccl.Send(F.send.p, F.n, ncclDouble, F.nb, h->comm, h->stream));
+    NK(g_nccl.Recv(F.recv.p, F.n, ncclDouble, F.nb, h->comm, h->stream));
+  }
+  NK(g_nccl.GroupEnd());
+}
+
+bool has_neighbours(const eqd_handle* h) {
+  if (!h->haloSet) return false;
+  for (int a = 0; a < 3; ++a) for (int s = 0; s < 2; ++s) if (h->face[a][s].nb >= 0) return true;
+  return false;
+}
+
+struct Timer {
+  eqd_handle* h; int slot; cudaEvent_t a = nullptr, b = nullptr;
+  Timer(eqd_handle* h_, int slot_) : h(h_), slot(slot_) {
+    if (!h->timing) return;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    CK(cudaEventRecord(a, h->stream));
+  }
+  void stop() {
+    if (!h->timing) return;
+    CK(cudaEventRecord(b, h->stream));
+    h->evs.push_back(a); h->evs.push_back(b); h->evs.push_back((cudaEvent_t)(intptr_t)slot);
+  }
+};
+
+void collect_timing(eqd_handle* h) {
+  for (size_t i = 0; i + 3 <= h->evs.size(); i += 3) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->evs[i], h->evs[i + 1]);
+    h->tms[(int)(intptr_t)h->evs[i + 2]] += ms;
+    cudaEventDestroy(h->evs[i]); cudaEventDestroy(h->evs[i + 1]);
+  }
+  h->evs.clear();
+}
+
+// phase A of a step: everything up to and including the packing of axis 0
+void step_pre(eqd_handle* h) {
+  const eqd_params& P = h->p;
+  cudaStream_t s = h->stream;
+  launch_advance(h->dState.p, P.dt, s); h->launches++;
+  {
+    Timer t(h, EQD_T_NODE);
+    NodeArgs A = h->nodeArgs();
+    if (h->dAccel0.p) A.accel0 = h->dAccel0.p;
+    launch_node_update(A, s); h->launches++;
+    if (h->nOff > 0) {
+      launch_store_offfault(h->dIdhist.p, 6 * h->nOff, h->dOffHist.p, h->dVel.p, h->dDisp.p, h->NnS, h->dState.p, s);
+      h->launches++;
+    }
+    t.stop();
+  }
+  if (h->dAccel0.p) { CK(cudaStreamSynchronize(s)); h->dAccel0.release(); }
+  {
+    Timer t(h, EQD_T_ELEM);
+    if (h->cls[CLS_REG].n) { launch_elem_reg(h->elemArgs(CLS_REG), false, h->plastic, h->qmode, h->body, P.C_hg, s); h->launches++; }
+    if (h->cls[CLS_REGX].n) { launch_elem_reg(h->elemArgs(CLS_REGX), true, h->plastic, h->qmode, h->body, P.C_hg, s); h->launches++; }
+    if (h->cls[CLS_PML].n) { launch_elem_pml(h->elemArgs(CLS_PML), h->body, P.C_hg, s); h->launches++; }
+    t.stop();
+  }
+  {
+    Timer t(h, EQD_T_ASSEMBLE);
+    if (h->nSpecial) { launch_assemble_special(h->nodeArgs(), h->dSpecial.p, h->nSpecial, s); h->launches++; }
+    t.stop();
+  }
+}
+
+void halo_pack(eqd_handle* h, int a) {
+  for (int side = 0; side < 2; ++side) {
+    Face& F = h->face[a][side];
+    if (F.nb < 0 || F.n == 0) continue;
+    launch_pack(h->dForce.p, F.idx.p, F.n, F.send.p, h->stream); h->launches++;
+  }
+}
+void halo_unpack(eqd_handle* h, int a) {
+  for (int side = 0; side < 2; ++side) {
+    Face& F = h->face[a][side];
+    if (F.nb < 0 || F.n == 0) continue;
+    launch_unpack_add(h->dForce.p, F.idx.p, F.n, F.recv.p, h->stream); h->launches++;
+  }
+}
+
+void step_post(eqd_handle* h) {
+  const eqd_params& P = h->p;
+  cudaStream_t s = h->stream;
+  Timer t(h, EQD_T_FAULT);
+  if (h->nPairs > 0) {
+    FaultArgs A = h->faultArgs();
+    if (P.friclaw == 5) { launch_thermop(A, s); h->launches++; }
+    launch_fault(A, s); h->launches++;
+  }
+  h->hostNt++;
+  h->hostTime = h->hostTime + P.dt;
+  if (P.outputGroundMotion && h->hostNt % 10 == 0) {  // driver.f90:30-33
+    if (h->dGm.p) { launch_sample_gm(h->dSurf.p, h->nSurf, h->dVel.p, h->NnS, h->dGm.p + 3 * (size_t)h->nSurf * h->nGm, s); h->launches++; }
+    if (h->dSrc.p) { launch_sample_src(h->dFric.p, h->PS, h->nftnd[0], h->dSrc.p + (size_t)h->nftnd[0] * h->nGm, s); h->launches++; }
+    h->nGm++;
+  }
+  t.stop();
+}
+
+void prepare_run(eqd_handle* h, int nt_begin) {
+  finalize(h);
+  if (nt_begin != h->hostNt + 1) {
+    // jump: rebuild the accumulated time exactly as repeated `timeElapsed + dt`
+    double t = 0.0;
+    for (int k = 1; k < nt_begin; ++k) t = t + h->p.dt;
+    StepState st{};
+    CK(cudaMemcpy(&st, h->dState.p, sizeof st, cudaMemcpyDeviceToHost));
+    st.nt = nt_begin - 1; st.timeElapsed = t;
+    CK(cudaMemcpy(h->dState.p, &st, sizeof st, cudaMemcpyHostToDevice));
+    h->hostNt = nt_begin - 1; h->hostTime = t;
+  }
+}
+
+int finish_run(eqd_handle* h) {
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  if (h->timing) collect_timing(h);
+  StepState st{};
+  CK(cudaMemcpy(&st, h->dState.p, sizeof st, cudaMemcpyDeviceToHost));
+  if (st.nanFlag) {
+    h->err = "NaN velocity at node " + std::to_string(st.nanNode) + " (driver.f90:147-152), step <= " + std::to_string(st.nt);
+    return EQD_ERR_NAN;
+  }
+  return EQD_OK;
+}
+
+// init-time shared sums between in-process handles or over NCCL use this generic
+// "exchange doubles per face" helper: vals[a][side] in/out
+}  // namespace
+
+extern "C" {
+
+int eqd_create(const eqd_params* p, int device, eqd_handle** out) {
+  if (!p || !out) return EQD_ERR_ARG;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    fprintf(stderr, "eqdyna_b200: no CUDA device (%s); the step library has no CPU path\n", cudaGetErrorString(e));
+    return EQD_ERR_CUDA;
+  }
+  eqd_handle* h = new eqd_handle();
+  h->p = *p;
+  h->device = device < 0 ? (p->me % ndev) : device;
+  int rc = guarded(h, [&] {
+    need(h->device < ndev, "eqd_create: device index out of range");
+    need(p->dt > 0 && p->npx > 0 && p->npy > 0 && p->npz > 0, "eqd_create: bad dt / decomposition");
+    need(!(p->C_elastic == 0 && p->C_Q == 1), "Q model can only work with elastic code (warning.f90:6-9)");
+    need(p->C_hg == 1 || p->C_hg == 2, "eqd_create: C_hg must be 1 or 2");
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->body = (p->C_elastic == 0) || (p->rdampm != 0.0);
+    h->plastic = p->C_elastic == 0;
+    h->qmode = p->C_Q == 1;
+    if (h->qmode) {
+      QTab tab[16];
+      for (int depth = 0; depth < 2; ++depth)
+        for (int k = 1; k <= 8; ++k) {
+          // calcElemKU.f90:86-93: Qs/Qp by depth
+          const double Qs = depth == 0 ? 10.0 : 50.0, Qp = depth == 0 ? 20.0 : 100.0;
+          double taok, wkp, wks, cv, cs;
+          qconstant(Qp, k, taok, wkp, cv);
+          qconstant(Qs, k, taok, wks, cs);
+          QTab& t = tab[depth * 8 + k - 1];
+          t.taok = taok; t.wkp = wkp * 8.0; t.wks = wks * 8.0; t.cv = cv; t.cs = cs; t.expdt = std::exp(-p->dt / taok);
+        }
+      upload_qtab(tab);
+    }
+  });
+  if (rc != EQD_OK) { fprintf(stderr, "eqd_create: %s\n", h->err.c_str()); delete h; return rc; }
+  *out = h;
+  return EQD_OK;
+}
+
+int eqd_destroy(eqd_handle* h) {
+  if (!h) return EQD_OK;
+  cudaSetDevice(h->device);
+  if (h->comm && g_nccl.lib) g_nccl.CommDestroy(h->comm);
+  for (int a = 0; a < 3; ++a) if (h->evPacked[a]) cudaEventDestroy(h->evPacked[a]);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return EQD_OK;
+}
+
+int eqd_last_error(const eqd_handle* h, char* buf, int n) {
+  if (!h || !buf || n <= 0) return EQD_ERR_ARG;
+  snprintf(buf, n, "%s", h->err.c_str());
+  return EQD_OK;
+}
+
+int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t sizeEq, const double* meshCoor,
+                 const int32_t* nodeElemIdRelation, const int32_t* elemTypeArr, const int32_t* numOfDofPerNodeArr,
+                 const int32_t* eqNumStartIndexLoc, const int32_t* eqNumIndexArr, const int32_t* stressCompIndexArr,
+                 int32_t sizeStress) {
+  if (!h) return EQD_ERR_ARG;
+  return guarded(h, [&] {
+    need(Nn > 0 && Ne > 0 && meshCoor && nodeElemIdRelation && elemTypeArr && numOfDofPerNodeArr && eqNumStartIndexLoc &&
+             eqNumIndexArr && stressCompIndexArr, "eqd_set_mesh: null / empty argument");
+    const eqd_params& P = h->p;
+    h->Nn = Nn; h->Ne = Ne; h->Neq = Neq; h->sizeEq = sizeEq; h->sizeStress = sizeStress;
+    h->coor.assign(meshCoor, meshCoor + 3 * (size_t)Nn);
+    h->etype.assign(elemTypeArr, elemTypeArr + Ne);
+    h->ndof.assign(numOfDofPerNodeArr, numOfDofPerNodeArr + Nn);
+    h->eqStart.assign(eqNumStartIndexLoc, eqNumStartIndexLoc + Nn);
+    h->eqIdx.assign(eqNumIndexArr, eqNumIndexArr + sizeEq);
+    h->stressIdx.assign(stressCompIndexArr, stressCompIndexArr + Ne);
+    h->conn.resize(8 * (size_t)Ne);
+    for (size_t k = 0; k < 8 * (size_t)Ne; ++k) {
+      const int n = nodeElemIdRelation[k] - 1;
+      need(n >= 0 && n < Nn, "eqd_set_mesh: connectivity out of range");
+      h->conn[k] = n;
+    }
+    // ---- node kinds
+    h->info.assign(Nn, 0);
+    h->Np = 0;
+    for (int n = 0; n < Nn; ++n) {
+      const int nd = h->ndof[n], st = h->eqStart[n];
+      need((nd == 3 || nd == 12) && st >= 0 && st + nd <= sizeEq, "eqd_set_mesh: bad dof table");
+      int nfix = 0;
+      for (int j = 0; j < nd; ++j) if (h->eqIdx[st + j] <= 0) nfix++;
+      need(nfix == 0 || nfix == nd, "eqd_set_mesh: partially fixed node is not supported");
+      if (nfix) h->info[n] = KIND_FIXED;
+      else if (nd == 3) h->info[n] = KIND_FREE3;
+      else { h->info[n] = KIND_PML12 | (h->Np << 3); h->Np++; }
+    }
+    h->NnS = pad32(Nn);
+    h->NpS = pad32(std::max(h->Np, 1));
+    need(3 * (double)h->NnS + 12 * (double)h->NpS < 4.0e9, "eqd_set_mesh: sub-domain too large for 32-bit halo offsets");
+    // ---- element classes
+    h->elemCode.assign(Ne, 0);
+    int cnt[3] = {0, 0, 0};
+    for (int e = 0; e < Ne; ++e) {
+      const int t = h->etype[e];
+      int c;
+      if (t == 2) c = CLS_PML;
+      else {
+        need(t == 1 || (t >= 11 && t <= 13), "eqd_set_mesh: unknown element type");
+        c = CLS_REG;
+        for (int k = 0; k < 8; ++k) if (h->ndof[h->conn[8 * (size_t)e + k]] == 12) c = CLS_REGX;
+      }
+      h->elemCode[e] = c | (cnt[c] << 2);
+      cnt[c]++;
+    }
+    for (int c = 0; c < 3; ++c) need(cnt[c] < (1 << 27), "eqd_set_mesh: more than 2^27 elements in one class");
+    const int nf[3] = {24, 48, 96}, nstr[3] = {6, 6, 21};
+    for (int c = 0; c < 3; ++c) {
+      ElemClass& C = h->cls[c];
+      C.n = cnt[c]; C.S = pad32(std::max(cnt[c], 1)); C.nf = nf[c]; C.nstress = nstr[c];
+      C.refId.assign(C.n, 0);
+    }
+    for (int e = 0; e < Ne; ++e) h->cls[h->elemCode[e] & 3].refId[h->elemCode[e] >> 2] = e;
+    for (int c = 0; c < 3; ++c) {
+      ElemClass& C = h->cls[c];
+      if (!C.n) continue;
+      std::vector<int> cn(8 * (size_t)C.S, 0);
+      for (int s = 0; s < C.n; ++s)
+        for (int k = 0; k < 8; ++k) cn[(size_t)k * C.S + s] = h->conn[8 * (size_t)C.refId[s] + k];
+      C.conn.upload(cn);
+      C.ef.alloc((size_t)C.nf * C.S);
+      C.stress.alloc((size_t)C.nstress * C.S);
+      if (c == CLS_PML) {
+        std::vector<double> dm(3 * (size_t)C.S, 0.0);
+        for (int s = 0; s < C.n; ++s) {
+          const int e = C.refId[s];
+          double xc[3] = {0, 0, 0};
+          for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 8; ++j) xc[i] = xc[i] + h->coor[i + 3 * (size_t)h->conn[8 * (size_t)e + j]];
+          for (int i = 0; i < 3; ++i) xc[i] = xc[i] / 8;
+          double d[3];
+          pml_elem_damps(P, xc, d);
+          for (int i = 0; i < 3; ++i) dm[(size_t)i * C.S + s] = d[i];
+        }
+        C.damps.upload(dm);
+      } else if (h->qmode) {
+        std::vector<uint8_t> qc(C.S, 0);
+        for (int s = 0; s < C.n; ++s) {
+          const int e = C.refId[s];
+          double xc[3] = {0, 0, 0};
+          for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 8; ++j) xc[i] = xc[i] + h->coor[i + 3 * (size_t)h->conn[8 * (size_t)e + j]];
+          for (int i = 0; i < 3; ++i) xc[i] = xc[i] / 8.0;
+          // calcElemKU.f90:86-99 (integer assignment truncates toward zero)
+          const int depth = xc[2] > -1000.0 ? 0 : 1;
+          const int ip = (int)((xc[0] - (P.PMLb[1] + P.dx / 2)) / P.dx + 1);
+          const int iq = (int)((xc[1] - (P.PMLb[3] + P.dx / 2)) / P.dx + 1);
+          const int ir = (int)((xc[2] - (P.PMLb[4] + P.dx / 2)) / P.dx + 1);
+          const int k = 1 + ip % 2 + 2 * (iq % 2) + 4 * (ir % 2);
+          need(k >= 1 && k <= 8, "Q class index out of range (element outside the uniform grid)");
+          qc[s] = (uint8_t)(depth * 8 + k - 1);
+        }
+        C.qcls.upload(qc);
+        C.qmem.alloc(6 * (size_t)C.S);
+      }
+    }
+    // ---- node -> (element, local node) CSR, ascending reference element id
+    std::vector<int> start(Nn + 1, 0);
+    for (int e = 0; e < Ne; ++e)
+      for (int k = 0; k < 8; ++k) {
+        const int n = h->conn[8 * (size_t)e + k];
+        if (EQD_INFO_KIND(h->info[n]) != KIND_FIXED) start[n + 1]++;
+      }
+    for (int n = 0; n < Nn; ++n) {
+      need((long)start[n] + start[n + 1] < 2147483647L, "eqd_set_mesh: adjacency overflow");
+      start[n + 1] += start[n];
+    }
+    std::vector<uint32_t> adj(start[Nn]);
+    {
+      std::vector<int> fill(start.begin(), start.end() - 1);
+      for (int e = 0; e < Ne; ++e) {
+        const int c = h->elemCode[e] & 3, s = h->elemCode[e] >> 2;
+        for (int k = 0; k < 8; ++k) {
+          const int n = h->conn[8 * (size_t)e + k];
+          if (EQD_INFO_KIND(h->info[n]) == KIND_FIXED) continue;
+          need(!(c == CLS_REG && EQD_INFO_KIND(h->info[n]) == KIND_PML12), "internal: REG element on a 12-dof node");
+          adj[fill[n]++] = EQD_ADJ(c, k, s);
+        }
+      }
+    }
+    h->dAdjStart.upload(start);
+    h->dAdj.upload(adj);
+    // ---- PML node damping profile (comdampv, recomputed every step in the reference)
+    std::vector<double> dp(3 * (size_t)h->NpS, 0.0);
+    for (int n = 0; n < Nn; ++n)
+      if (EQD_INFO_KIND(h->info[n]) == KIND_PML12) {
+        double d[3];
+        if (!comdampv(P, h->coor[3 * (size_t)n], h->coor[3 * (size_t)n + 1], h->coor[3 * (size_t)n + 2], d))
+          throw ArgError("negative PML damping (comdampv.f90:114-118)");
+        const size_t slot = EQD_INFO_SLOT(h->info[n]);
+        for (int i = 0; i < 3; ++i) dp[(size_t)i * h->NpS + slot] = d[i];
+      }
+    h->dDampp.upload(dp);
+    h->dVel.alloc(3 * (size_t)h->NnS); h->dDisp.alloc(3 * (size_t)h->NnS);
+    h->dV1p.alloc(12 * (size_t)h->NpS);
+    h->dForce.alloc(3 * (size_t)h->NnS + 12 * (size_t)h->NpS);
+    h->dMass.alloc(Nn);
+    h->meshSet = true;
+  });
+}
+
+int eqd_set_elem_ops(eqd_handle* h, const double* eleshp, const double* eledet, const double* elemass, const double* mat,
+                     const double* ss, const double* phi, const double* eleporep, const double* stressArr,
+                     const double* pstrain) {
+  if (!h) return EQD_ERR_ARG;
+  return guarded(h, [&] {
+    need(h->meshSet, "eqd_set_elem_ops: call eqd_set_mesh first");
+    need(eleshp && eledet && mat && ss && phi && stressArr, "eqd_set_elem_ops: null argument");
+    need(!h->body || elemass, "eqd_set_elem_ops: elemass required (gravity / mass damping)");
+    need(!h->plastic || (eleporep && pstrain), "eqd_set_elem_ops: eleporep/pstrain required for C_elastic==0");
+    const int Ne = h->Ne;
+    DevBuf<int> dCode; dCode.upload(h->elemCode);
+    DevBuf<double> tmp;
+    for (int c = 0; c < 3; ++c) {
+      ElemClass& C = h->cls[c];
+      if (!C.n) continue;
+      C.shp.alloc(24 * (size_t)C.S); C.phi.alloc(32 * (size_t)C.S); C.ss.alloc(6 * (size_t)C.S);
+      C.lam.alloc(C.S); C.mu.alloc(C.S); C.det.alloc(C.S);
+      if (h->p.C_hg == 2) { C.rho.alloc(C.S); C.vp.alloc(C.S); }
+      if (h->body) C.emass.alloc(8 * (size_t)C.S);
+      if (h->plastic && c != CLS_PML) { C.porep.alloc(C.S); C.pstrain.alloc(C.S); }
+    }
+    auto spread = [&](const double* src, int K, auto member, int k0, int nk, int rowOff) {
+      tmp.alloc((size_t)K * Ne, false);
+      CK(cudaMemcpy(tmp.p, src, sizeof(double) * (size_t)K * Ne, cudaMemcpyHostToDevice));
+      for (int c = 0; c < 3; ++c) {
+        ElemClass& C = h->cls[c];
+        DevBuf<double>& dst = C.*member;
+        if (!C.n || !dst.p) continue;
+        launch_aos_to_soa(tmp.p, K, Ne, dCode.p, c, dst.p + (size_t)rowOff * C.S, C.S, k0, nk, h->stream);
+      }
+      CK(cudaStreamSynchronize(h->stream));
+    };
+    spread(eleshp, 24, &ElemClass::shp, 0, 24, 0);
+    spread(phi, 32, &ElemClass::phi, 0, 32, 0);
+    spread(ss, 6, &ElemClass::ss, 0, 6, 0);
+    spread(eledet, 1, &ElemClass::det, 0, 1, 0);
+    spread(mat + 3 * (size_t)Ne, 1, &ElemClass::lam, 0, 1, 0);  // mat(Ne,5): element index fastest
+    spread(mat + 4 * (size_t)Ne, 1, &ElemClass::mu, 0, 1, 0);
+    if (h->p.C_hg == 2) {
+      spread(mat + 2 * (size_t)Ne, 1, &ElemClass::rho, 0, 1, 0);
+      spread(mat, 1, &ElemClass::vp, 0, 1, 0);
+    }
+    if (h->body) {
+      tmp.alloc((size_t)24 * Ne, false);
+      CK(cudaMemcpy(tmp.p, elemass, sizeof(double) * (size_t)24 * Ne, cudaMemcpyHostToDevice));
+      for (int c = 0; c < 3; ++c) {
+        ElemClass& C = h->cls[c];
+        if (!C.n) continue;
+        for (int i = 0; i < 8; ++i) launch_aos_to_soa(tmp.p, 24, Ne, dCode.p, c, C.emass.p + (size_t)i * C.S, C.S, 3 * i, 1, h->stream);
+      }
+      CK(cudaStreamSynchronize(h->stream));
+    }
+    if (h->plastic) {
+      spread(eleporep, 1, &ElemClass::porep, 0, 1, 0);
+      spread(pstrain, 1, &ElemClass::pstrain, 0, 1, 0);
+    }
+    tmp.release();
+    // stresses: stressArr(stressCompIndexArr(e) + k)
+    for (int c = 0; c < 3; ++c) {
+      ElemClass& C = h->cls[c];
+      if (!C.n) continue;
+      std::vector<double> sg((size_t)C.nstress * C.S, 0.0), qm;
+      if (h->qmode && c != CLS_PML) qm.assign(6 * (size_t)C.S, 0.0);
+      for (int s = 0; s < C.n; ++s) {
+        const int base = h->stressIdx[C.refId[s]];
+        need(base >= 0 && base + (c == CLS_PML ? 21 : 12) <= h->sizeStress, "eqd_set_elem_ops: stress index out of range");
+        for (int k = 0; k < C.nstress; ++k) sg[(size_t)k * C.S + s] = stressArr[base + k];
+        if (!qm.empty()) for (int k = 0; k < 6; ++k) qm[(size_t)k * C.S + s] = stressArr[base + 6 + k];
+      }
+      C.stress.upload(sg);
+      if (!qm.empty()) C.qmem.upload(qm);
+    }
+    h->opsSet = true;
+  });
+}
+
+int eqd_set_nodal(eqd_handle* h, const double* nodalMassArr, const double* fnms, const double* v1, const double* velArr,
+                  const double* dispArr, const double* nodalForceArr) {
+  if (!h) return EQD_ERR_ARG;
+  return guarded(h, [&] {
+    need(h->meshSet, "eqd_set_nodal: call eqd_set_mesh first");
+    need(nodalMassArr && fnms && v1 && velArr && dispArr, "eqd_set_nodal: null argument");
+    const int Nn = h->Nn;
+    const size_t NS = h->NnS, PS = h->NpS;
+    h->fnmsH.assign(fnms, fnms + Nn);
+    h->massH.assign(Nn, 1.0);
+    std::vector<double> vel(3 * NS, 0.0), disp(3 * NS, 0.0), v1p(12 * PS, 0.0), acc;
+    bool anyAcc = false;
+    if (nodalForceArr)
+      for (int k = 0; k < h->Neq && !anyAcc; ++k) anyAcc = nodalForceArr[k] != 0.0;
+    if (anyAcc) acc.assign(3 * NS + 12 * PS, 0.0);
+    for (int n = 0; n < Nn; ++n) {
+      const int kind = EQD_INFO_KIND(h->info[n]);
+      if (kind == KIND_FIXED) continue;
+      const int st = h->eqStart[n], nd = h->ndof[n];
+      const double m = nodalMassArr[h->eqIdx[st] - 1];
+      for (int j = 1; j < nd; ++j)
+        need(nodalMassArr[h->eqIdx[st + j] - 1] == m, "eqd_set_nodal: dofs of one node carry different lumped masses");
+      h->massH[n] = m;
+      for (int j = 0; j < 3; ++j) disp[j * NS + n] = dispArr[j + 3 * (size_t)n];
+      if (kind == KIND_FREE3) {
+        // v1 and velArr are the same quantity for a 3-dof node after the first update (driver.f90:102-103)
+        for (int j = 0; j < 3; ++j) vel[j * NS + n] = v1[h->eqIdx[st + j] - 1];
+        if (anyAcc) for (int j = 0; j < 3; ++j) acc[j * NS + n] = nodalForceArr[h->eqIdx[st + j] - 1];
+      } else {
+        const size_t slot = EQD_INFO_SLOT(h->info[n]);
+        for (int j = 0; j < 12; ++j) v1p[j * PS + slot] = v1[h->eqIdx[st + j] - 1];
+        for (int j = 0; j < 3; ++j) vel[j * NS + n] = velArr[j + 3 * (size_t)n];
+        if (anyAcc) for (int j = 0; j < 12; ++j) acc[3 * NS + j * PS + slot] = nodalForceArr[h->eqIdx[st + j] - 1];
+      }
+    }
+    h->dVel.upload(vel); h->dDisp.upload(disp); h->dV1p.upload(v1p); h->dMass.upload(h->massH);
+    if (anyAcc) h->dAccel0.upload(acc); else h->dAccel0.release();
+    h->nodalSet = true;
+  });
+}
+
+int eqd_set_fault(eqd_handle* h, int32_t nftmx, const int32_t* nftnd, const int32_t* nsmp, const double* un,
+                  const double* us, const double* ud, const double* arn, const double* fric, const double* fnft) {
+  if (!h) return EQD_ERR_ARG;
+  return guarded(h, [&] {
+    need(h->meshSet && h->nodalSet, "eqd_set_fault: call eqd_set_mesh and eqd_set_nodal first");
+    need(!h->finalized, "eqd_set_fault: already running");
+    const int ntotft = h->p.ntotft;
+    need(nftmx >= 1 && ntotft >= 1 && nftnd && nsmp && un && us && ud && arn && fric && fnft, "eqd_set_fault: null / empty argument");
+    h->nftmx = nftmx; h->ntotft = ntotft;
+    h->nftnd.assign(nftnd, nftnd + ntotft);
+    h->pairRef.clear();
+    for (int ift = 0; ift < ntotft; ++ift)
+      for (int i = 0; i < nftnd[ift]; ++i) h->pairRef.push_back(i + nftmx * ift);
+    h->nPairs = (int)h->pairRef.size();
+    h->PS = pad32(std::max(h->nPairs, 1));
+    const size_t PS = h->PS;
+    std::vector<int> nS(PS, 0), nM(PS, 0), ift(PS, 0);
+    std::vector<double> u1(3 * PS, 0.0), u2(3 * PS, 0.0), u3(3 * PS, 0.0), ar(PS, 1.0), mS(PS, 1.0), mM(PS, 1.0), xs(3 * PS, 0.0),
+        fr(100 * PS, 0.0), ft(PS, 0.0);
+    h->pairNodeS.resize(h->nPairs); h->pairNodeM.resize(h->nPairs);
+    for (int q = 0; q < h->nPairs; ++q) {
+      const size_t pb = h->pairRef[q];
+      const int s = nsmp[2 * pb] - 1, m = nsmp[2 * pb + 1] - 1;
+      need(s >= 0 && s < h->Nn && m >= 0 && m < h->Nn, "eqd_set_fault: nsmp out of range");
+      need(EQD_INFO_KIND(h->info[s]) == KIND_FREE3 && EQD_INFO_KIND(h->info[m]) == KIND_FREE3, "eqd_set_fault: split nodes must be free 3-dof nodes");
+      nS[q] = s; nM[q] = m; ift[q] = (int)(pb / nftmx) + 1;
+      h->pairNodeS[q] = s; h->pairNodeM[q] = m;
+      for (int k = 0; k < 3; ++k) {
+        u1[k * PS + q] = un[k + 3 * pb]; u2[k * PS + q] = us[k + 3 * pb]; u3[k * PS + q] = ud[k + 3 * pb];
+        xs[k * PS + q] = h->coor[k + 3 * (size_t)s];
+      }
+      ar[q] = arn[pb]; mS[q] = h->fnmsH[s]; mM[q] = h->fnmsH[m]; ft[q] = fnft[pb];
+      for (int k = 0; k < 100; ++k) fr[k * PS + q] = fric[k + 100 * pb];
+    }
+    h->dNodeS.upload(nS); h->dNodeM.upload(nM); h->dIft.upload(ift);
+    h->dUn.upload(u1); h->dUs.upload(u2); h->dUd.upload(u3); h->dArn.upload(ar);
+    h->dMassS.upload(mS); h->dMassM.upload(mM); h->dXs.upload(xs); h->dFric.upload(fr); h->dFnft.upload(ft);
+    h->faultSet = true;
+  });
+}
+
+int eqd_set_halo(eqd_handle* h, const int32_t* numcount, const int32_t* fltnum, const int32_t* fltMPI, const int32_t* fltl,
+                 const int32_t* fltr, const int32_t* fltf, const int32_t* fltb, const int32_t* fltd, const int32_t* fltu) {
+  if (!h) return EQD_ERR_ARG;
+  return guarded(h, [&] {
+    need(h->meshSet && !h->finalized, "eqd_set_halo: call after eqd_set_mesh and before eqd_run");
+    need(numcount && fltnum && fltMPI, "eqd_set_halo: null argument");
+    for (int k = 0; k < 9; ++k) h->numcount[k] = numcount[k];
+    const int32_t* lists[6] = {fltl, fltr, fltf, fltb, fltd, fltu};
+    for (int k = 0; k < 6; ++k) {
+      h->fltnum[k] = fltnum[k]; h->fltMPI[k] = fltMPI[k];
+      h->fltface[k].clear();
+      if (fltnum[k] > 0 && fltMPI[k]) {
+        need(lists[k] != nullptr, "eqd_set_halo: face list missing");
+        h->fltface[k].assign(lists[k], lists[k] + fltnum[k]);
+      }
+    }
+    need((long)numcount[0] * numcount[1] * numcount[2] <= h->Nn, "eqd_set_halo: numcount(1:3) exceeds the node count");
+    h->haloSet = true;
+  });
+}
+
+int eqd_set_stations(eqd_handle* h, const int32_t* idhist, int32_t nOff, const int32_t* anonfs, int32_t nOn,
+                     const int32_t* surfaceNodeIdArr, int32_t nSurf) {
+  if (!h) return EQD_ERR_ARG;
+  return guarded(h, [&] {
+    need(h->meshSet && !h->finalized, "eqd_set_stations: call after eqd_set_mesh and before eqd_run");
+    h->nOff = nOff > 0 && idhist ? nOff : 0;
+    h->nOn = nOn > 0 && anonfs ? nOn : 0;
+    h->nSurf = nSurf > 0 && surfaceNodeIdArr ? nSurf : 0;
+    if (h->nOff) {
+      h->idhistH.assign(idhist, idhist + 18 * (size_t)h->nOff);
+      for (int i = 0; i < 6 * h->nOff; ++i) {
+        need(h->idhistH[3 * i] >= 1 && h->idhistH[3 * i] <= h->Nn && h->idhistH[3 * i + 1] >= 1 && h->idhistH[3 * i + 1] <= 3,
+             "eqd_set_stations: idhist out of range");
+        need(h->idhistH[3 * i + 2] == 1 || h->idhistH[3 * i + 2] == 2, "eqd_set_stations: idhist(3,:) must be 1 (disp) or 2 (vel)");
+      }
+      h->dIdhist.upload(h->idhistH);
+    }
+    if (h->nOn) h->anonfsH.assign(anonfs, anonfs + 3 * (size_t)h->nOn);
+    if (h->nSurf) { h->surfH.assign(surfaceNodeIdArr, surfaceNodeIdArr + h->nSurf); h->dSurf.upload(h->surfH); }
+  });
+}
+
+int eqd_get_unique_id(void* id128) {
+  if (!id128) return EQD_ERR_ARG;
+  if (!g_nccl.load()) { fprintf(stderr, "eqdyna_b200: cannot load NCCL: %s\n", g_nccl.why.c_str()); return EQD_ERR_CUDA; }
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return EQD_ERR_CUDA;
+  memcpy(id128, &id, 128);
+  return EQD_OK;
+}
+
+int eqd_set_comm(eqd_handle* h, const void* id128, int32_t nranks, int32_t rank) {
+  if (!h) return EQD_ERR_ARG;
+  return guarded(h, [&] {
+    need(id128 && nranks >= 1 && rank >= 0 && rank < nranks, "eqd_set_comm: bad arguments");
+    need(nranks == h->p.npx * h->p.npy * h->p.npz && rank == h->p.me, "eqd_set_comm: rank/nranks must match me and npx*npy*npz");
+    if (!g_nccl.load()) throw CudaError("cannot load NCCL: " + g_nccl.why);
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    NK(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
+    h->nranks = nranks; h->rank = rank;
+  });
+}
+
+// The init-time sums of the reference (nodalMassArr and fnms through
+// MPI4NodalQuant, assembleGlobalMass.f90:40-41; arn through MPI4arn,
+// meshgen.f90:274-395), x then y then z, for a one-process-per-GPU host.
+int eqd_sum_shared(eqd_handle* h) {
+  if (!h) return EQD_ERR_ARG;
+  return guarded(h, [&] {
+    need(h->nodalSet, "eqd_sum_shared: call after eqd_set_nodal / eqd_set_fault / eqd_set_halo");
+    finalize(h);
+    if (!has_neighbours(h)) return;
+    need(h->comm != nullptr, "eqd_sum_shared: eqd_set_comm first");
+    // host-staged: these run once
+    for (int a = 0; a < 3; ++a) {
+      std::vector<double> sendv[2], recvv[2];
+      DevBuf<double> ds[2], dr[2];
+      for (int side = 0; side < 2; ++side) {
+        Face& F = h->face[a][side];
+        if (F.nb < 0) continue;
+        for (int n : F.nodes) { sendv[side].push_back(h->massH[n]); sendv[side].push_back(h->fnmsH[n]); }
+        std::vector<double> arnH = h->dArn.download();
+        for (int q : F.pairs) sendv[side].push_back(arnH[q]);
+        ds[side].upload(sendv[side]); dr[side].alloc(sendv[side].size());
+      }
+      NK(g_nccl.GroupStart());
+      for (int side = 0; side < 2; ++side) {
+        Face& F = h->face[a][side];
+        if (F.nb < 0 || ds[side].n == 0) continue;
+        NK(g_nccl.Send(ds[side].p, ds[side].n, ncclDouble, F.nb, h->comm, h->stream));
+        NK(g_nccl.Recv(dr[side].p, dr[side].n, ncclDouble, F.nb, h->comm, h->stream));
+      }
+      NK(g_nccl.GroupEnd());
+      CK(cudaStreamSynchronize(h->stream));
+      for (int side = 0; side < 2; ++side) {
+        Face& F = h->face[a][side];
+        if (F.nb < 0 || ds[side].n == 0) continue;
+        recvv[side] = dr[side].download();
+        size_t k = 0;
+        for (int n : F.nodes) {
+          if (EQD_INFO_KIND(h->info[n]) != KIND_FIXED) h->massH[n] = h->massH[n] + recvv[side][k];
+          h->fnmsH[n] = h->fnmsH[n] + recvv[side][k + 1];
+          k += 2;
+        }
+        std::vector<double> arnH = h->dArn.download();
+        for (int q : F.pairs) arnH[q] = arnH[q] + recvv[side][k++];
+        h->dArn.upload(arnH);
+      }
+    }
+    h->dMass.upload(h->massH);
+    std::vector<double> mS(h->PS, 1.0), mM(h->PS, 1.0);
+    for (int q = 0; q < h->nPairs; ++q) { mS[q] = h->fnmsH[h->pairNodeS[q]]; mM[q] = h->fnmsH[h->pairNodeM[q]]; }
+    if (h->nPairs) { h->dMassS.upload(mS); h->dMassM.upload(mM); }
+  });
+}
+
+int eqd_run(eqd_handle* h, int32_t nt_begin, int32_t nt_end) {
+  if (!h) return EQD_ERR_ARG;
+  int rc2 = EQD_OK;
+  int rc = guarded(h, [&] {
+    need(nt_begin >= 1 && nt_end <= h->p.nstep, "eqd_run: step range outside 1..nstep");
+    prepare_run(h, nt_begin);
+    const bool multi = has_neighbours(h);
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    if (h->timing) { CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1)); CK(cudaEventRecord(t0, h->stream)); }
+    for (int nt = nt_begin; nt <= nt_end; ++nt) {
+      step_pre(h);
+      if (multi) {
+        Timer t(h, EQD_T_HALO);
+        for (int a = 0; a < 3; ++a) {
+          if (h->face[a][0].nb < 0 && h->face[a][1].nb < 0) continue;
+          halo_pack(h, a);
+          halo_axis_nccl(h, a);
+          halo_unpack(h, a);
+        }
+        t.stop();
+      }
+      step_post(h);
+    }
+    if (h->timing) {
+      CK(cudaEventRecord(t1, h->stream));
+      CK(cudaEventSynchronize(t1));
+      float ms = 0; CK(cudaEventElapsedTime(&ms, t0, t1));
+      h->tms[EQD_T_TOTAL] += ms;
+      cudaEventDestroy(t0); cudaEventDestroy(t1);
+    }
+    rc2 = finish_run(h);
+  });
+  return rc != EQD_OK ? rc : rc2;
+}
+
+// Several sub-domains driven by ONE process (all on one device, or one device
+// each with peer access): lock-step run with device-to-device halo copies.
+int eqd_run_group(eqd_handle** hs, int32_t n, int32_t nt_begin, int32_t nt_end) {
+  if (!hs || n < 1) return EQD_ERR_ARG;
+  int rcAll = EQD_OK;
+  int rc = guarded(hs[0], [&] {
+    need(n == hs[0]->p.npx * hs[0]->p.npy * hs[0]->p.npz, "eqd_run_group: need every sub-domain of the decomposition");
+    for (int r = 0; r < n; ++r) {
+      need(hs[r] && hs[r]->p.me == r, "eqd_run_group: handles must be ordered by rank id");
+      CK(cudaSetDevice(hs[r]->device));
+      need(nt_begin >= 1 && nt_end <= hs[r]->p.nstep, "eqd_run_group: step range outside 1..nstep");
+      prepare_run(hs[r], nt_begin);
+    }
+    for (int nt = nt_begin; nt <= nt_end; ++nt) {
+      for (int r = 0; r < n; ++r) { CK(cudaSetDevice(hs[r]->device)); step_pre(hs[r]); }
+      for (int a = 0; a < 3; ++a) {
+        for (int r = 0; r < n; ++r) {
+          eqd_handle* h = hs[r];
+          if (!h->haloSet || (h->face[a][0].nb < 0 && h->face[a][1].nb < 0)) continue;
+          CK(cudaSetDevice(h->device));
+          halo_pack(h, a);
+          CK(cudaEventRecord(h->evPacked[a], h->stream));
+        }
+        for (int r = 0; r < n; ++r) {
+          eqd_handle* h = hs[r];
+          if (!h->haloSet) continue;
+          CK(cudaSetDevice(h->device));
+          for (int side = 0; side < 2; ++side) {
+            Face& F = h->face[a][side];
+            if (F.nb < 0 || F.n == 0) continue;
+            eqd_handle* o = hs[F.nb];
+            Face& G = o->face[a][1 - side];
+            need(G.n == F.n, "eqd_run_group: face sizes differ between neighbours");
+            CK(cudaStreamWaitEvent(h->stream, o->evPacked[a], 0));
+            CK(cudaMemcpyAsync(F.recv.p, G.send.p, sizeof(double) * F.n, cudaMemcpyDefault, h->stream));
+          }
+          halo_unpack(h, a);
+        }
+        // a rank's send buffers of this axis are reused next step only: the next
+        // pack on the same stream is ordered after the neighbours' copies by the
+        // step_pre/step_post kernels of every rank being enqueued in between and
+        // by the device-wide join below
+      }
+      for (int r = 0; r < n; ++r) { CK(cudaSetDevice(hs[r]->device)); step_post(hs[r]); }
+      // lock-step join so that no rank overwrites a send buffer a neighbour still reads
+      for (int r = 0; r < n; ++r) { CK(cudaSetDevice(hs[r]->device)); CK(cudaStreamSynchronize(hs[r]->stream)); }
+    }
+    for (int r = 0; r < n; ++r) {
+      CK(cudaSetDevice(hs[r]->device));
+      int rc1 = finish_run(hs[r]);
+      if (rc1 != EQD_OK) { rcAll = rc1; if (r) hs[0]->err = hs[r]->err; }
+    }
+  });
+  return rc != EQD_OK ? rc : rcAll;
+}
+
+int eqd_fetch(eqd_handle* h, int32_t which, void* dst, int64_t dst_bytes) {
+  if (!h) return EQD_ERR_ARG;
+  return guarded(h, [&] {
+    need(dst != nullptr, "eqd_fetch: null destination");
+    need(h->meshSet && h->nodalSet, "eqd_fetch: nothing uploaded yet");
+    CK(cudaStreamSynchronize(h->stream));
+    double* out = (double*)dst;
+    const int Nn = h->Nn;
+    const size_t NS = h->NnS, PSn = h->NpS;
+    auto want = [&](size_t nDoubles) { need((size_t)dst_bytes >= nDoubles * sizeof(double), "eqd_fetch: destination too small"); };
+    switch (which) {
+      case EQD_F_DISP: case EQD_F_VEL: {
+        want(3 * (size_t)Nn);
+        std::vector<double> v = (which == EQD_F_DISP ? h->dDisp : h->dVel).download();
+        for (int n = 0; n < Nn; ++n) for (int j = 0; j < 3; ++j) out[j + 3 * (size_t)n] = v[j * NS + n];
+        break;
+      }
+      case EQD_F_V1: case EQD_F_FORCE: case EQD_F_MASS: {
+        want(h->Neq);
+        std::vector<double> a3, a12;
+        if (which == EQD_F_V1) { a3 = h->dVel.download(); a12 = h->dV1p.download(); }
+        else if (which == EQD_F_FORCE) {
+          finalize(h);
+          DevBuf<double> acc; acc.alloc(3 * NS + 12 * PSn);
+          NodeArgs A = h->nodeArgs();
+          if (h->dAccel0.p) A.accel0 = h->dAccel0.p;
+          launch_materialize_accel(A, acc.p, h->stream);
+          CK(cudaStreamSynchronize(h->stream));
+          std::vector<double> all = acc.download();
+          a3.assign(all.begin(), all.begin() + 3 * NS);
+          a12.assign(all.begin() + 3 * NS, all.end());
+        }
+        for (int n = 0; n < Nn; ++n) {
+          const int kind = EQD_INFO_KIND(h->info[n]);
+          if (kind == KIND_FIXED) continue;
+          const int st = h->eqStart[n];
+          if (which == EQD_F_MASS) { for (int j = 0; j < h->ndof[n]; ++j) out[h->eqIdx[st + j] - 1] = h->massH[n]; continue; }
+          if (kind == KIND_FREE3) for (int j = 0; j < 3; ++j) out[h->eqIdx[st + j] - 1] = a3[j * NS + n];
+          else { const size_t slot = EQD_INFO_SLOT(h->info[n]); for (int j = 0; j < 12; ++j) out[h->eqIdx[st + j] - 1] = a12[j * PSn + slot]; }
+        }
+        break;
+      }
+      case EQD_F_FNMS: want(Nn); memcpy(out, h->fnmsH.data(), sizeof(double) * Nn); break;
+      case EQD_F_FRIC: {
+        need(h->faultSet, "eqd_fetch: no fault");
+        want(100 * (size_t)h->nftmx * h->ntotft);
+        std::vector<double> fr = h->dFric.download();
+        for (int q = 0; q < h->nPairs; ++q) for (int k = 0; k < 100; ++k) out[k + 100 * (size_t)h->pairRef[q]] = fr[(size_t)k * h->PS + q];
+        break;
+      }
+      case EQD_F_FNFT: case EQD_F_ARN: {
+        need(h->faultSet, "eqd_fetch: no fault");
+        want((size_t)h->nftmx * h->ntotft);
+        std::vector<double> v = (which == EQD_F_FNFT ? h->dFnft : h->dArn).download();
+        for (int q = 0; q < h->nPairs; ++q) out[h->pairRef[q]] = v[q];
+        break;
+      }
+      case EQD_F_PSTRAIN: {
+        want(h->Ne);
+        for (int c = 0; c < 3; ++c) {
+          ElemClass& C = h->cls[c];
+          if (!C.n || !C.pstrain.p) continue;
+          std::vector<double> v = C.pstrain.download();
+          for (int s = 0; s < C.n; ++s) out[C.refId[s]] = v[s];
+        }
+        break;
+      }
+      case EQD_F_STRESS: {
+        want(h->sizeStress);
+        for (int c = 0; c < 3; ++c) {
+          ElemClass& C = h->cls[c];
+          if (!C.n) continue;
+          std::vector<double> sg = C.stress.download(), qm;
+          if (C.qmem.p) qm = C.qmem.download();
+          for (int s = 0; s < C.n; ++s) {
+            const int base = h->stressIdx[C.refId[s]];
+            for (int k = 0; k < C.nstress; ++k) out[base + k] = sg[(size_t)k * C.S + s];
+            if (!qm.empty()) for (int k = 0; k < 6; ++k) out[base + 6 + k] = qm[(size_t)k * C.S + s];
+          }
+        }
+        break;
+      }
+      case EQD_F_ONFAULT_HIST: finalize(h); want(h->dOnHist.n); CK(cudaMemcpy(out, h->dOnHist.p, sizeof(double) * h->dOnHist.n, cudaMemcpyDeviceToHost)); break;
+      case EQD_F_OFFFAULT_HIST: finalize(h); want(h->dOffHist.n); if (h->dOffHist.n) CK(cudaMemcpy(out, h->dOffHist.p, sizeof(double) * h->dOffHist.n, cudaMemcpyDeviceToHost)); break;
+      case EQD_F_HYPO_LOG: finalize(h); want(h->dHypo.n); CK(cudaMemcpy(out, h->dHypo.p, sizeof(double) * h->dHypo.n, cudaMemcpyDeviceToHost)); break;
+      case EQD_F_GM: finalize(h); want(3 * (size_t)h->nSurf * h->nGm); if (h->dGm.p && h->nGm) CK(cudaMemcpy(out, h->dGm.p, sizeof(double) * 3 * (size_t)h->nSurf * h->nGm, cudaMemcpyDeviceToHost)); break;
+      case EQD_F_SRC_EVOL: finalize(h); need(h->faultSet, "eqd_fetch: no fault"); want((size_t)h->nftnd[0] * h->nGm); if (h->dSrc.p && h->nGm) CK(cudaMemcpy(out, h->dSrc.p, sizeof(double) * (size_t)h->nftnd[0] * h->nGm, cudaMemcpyDeviceToHost)); break;
+      case EQD_F_TPHIST: {
+        need(h->faultSet && h->dTpHist.p, "eqd_fetch: no thermal-pressurization history (friclaw != 5)");
+        const size_t nstep = h->p.nstep;
+        want(2 * (size_t)h->nftmx * nstep * h->ntotft);
+        std::vector<double> v = h->dTpHist.download();
+        for (int q = 0; q < h->nPairs; ++q) {
+          const size_t i = h->pairRef[q] % h->nftmx, ift = h->pairRef[q] / h->nftmx;
+          for (size_t j = 0; j < nstep; ++j)
+            for (int a = 0; a < 2; ++a) out[a + 2 * (i + h->nftmx * (j + nstep * ift))] = v[(j * 2 + a) * h->PS + q];
+        }
+        break;
+      }
+      default: throw ArgError("eqd_fetch: unknown which-code");
+    }
+  });
+}
+
+int eqd_get_counts(const eqd_handle* h, int64_t* n_regular, int64_t* n_pml, int64_t* n_pairs, int64_t* launches) {
+  if (!h) return EQD_ERR_ARG;
+  if (n_regular) *n_regular = h->cls[CLS_REG].n + h->cls[CLS_REGX].n;
+  if (n_pml) *n_pml = h->cls[CLS_PML].n;
+  if (n_pairs) *n_pairs = h->nPairs;
+  if (launches) *launches = h->launches;
+  return EQD_OK;
+}
+
+int eqd_get_timing(const eqd_handle* h, double* ms_slots) {
+  if (!h || !ms_slots) return EQD_ERR_ARG;
+  for (int k = 0; k < EQD_T_NSLOTS; ++k) ms_slots[k] = h->tms[k];
+  return EQD_OK;
+}
+
+int eqd_set_option(eqd_handle* h, const char* key, int32_t value) {
+  if (!h || !key) return EQD_ERR_ARG;
+  if (!strcmp(key, "timing")) { h->timing = value != 0; if (value == 2) { for (double& t : h->tms) t = 0; h->launches = 0; } return EQD_OK; }
+  if (!strcmp(key, "graph")) { h->optGraph = value; return EQD_OK; }
+  if (!strcmp(key, "block")) { h->optBlock = value; return EQD_OK; }
+  if (!strcmp(key, "overlap")) return EQD_OK;
+  h->err = std::string("eqd_set_option: unknown key ") + key;
+  return EQD_ERR_ARG;
+}
+
+}  // extern "C"

@@ -1,0 +1,950 @@
+// Hand-written FP64 sm_100a kernels of the EQdyna step loop (src/driver.f90:9-34).
+// Every kernel cites the reference routine it replaces.  One thread per work
+// item (element / node / split-node pair), SoA operands with the work-item
+// index fastest so every warp-wide access is a run of consecutive doubles.
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "eqd_dev.cuh"
+#include "eqd_kernels.h"
+
+namespace eqd {
+
+__constant__ QTab c_qtab[16];
+
+void upload_qtab(const QTab* t) { cudaMemcpyToSymbol(c_qtab, t, sizeof(QTab) * 16); }
+
+#define LDG(p) __ldg(p)
+
+// ----------------------------------------------------------------------------
+// step counter: driver.f90:11 (timeElapsed = timeElapsed + dt)
+__global__ void k_advance(StepState* st, double dt) {
+  st->timeElapsed = st->timeElapsed + dt;
+  st->nt = st->nt + 1;
+}
+
+// ----------------------------------------------------------------------------
+// Ordered gather of a node's force from the element-force buffers
+// (replaces the scatter-add of assembleGlobalKU.f90:28-35,47-63 and
+// hrglss.f90:42-54: same contributions, fixed order = ascending element id).
+__device__ __forceinline__ void gather3(const NodeArgs& A, int n, double f[3]) {
+  const int b = LDG(A.adjStart + n), e = LDG(A.adjStart + n + 1);
+  f[0] = f[1] = f[2] = 0.0;
+  for (int k = b; k < e; ++k) {
+    const uint32_t u = LDG(A.adj + k);
+    const int cls = u & 3, ln = (u >> 2) & 7;
+    const size_t idx = u >> 5;
+    if (cls == CLS_REG) {
+      const double* p = A.efR + (size_t)(3 * ln) * A.SR + idx;
+      f[0] += LDG(p); f[1] += LDG(p + A.SR); f[2] += LDG(p + 2 * (size_t)A.SR);
+    } else if (cls == CLS_PML) {
+      // 3-dof node of a PML element: assembleGlobalKU.f90:55-61
+      const double* p = A.efP + (size_t)(12 * ln) * A.SP + idx;
+      const size_t S = A.SP;
+      f[0] = f[0] + LDG(p) + LDG(p + S) + LDG(p + 2 * S) + LDG(p + 9 * S);
+      f[1] = f[1] + LDG(p + 3 * S) + LDG(p + 4 * S) + LDG(p + 5 * S) + LDG(p + 10 * S);
+      f[2] = f[2] + LDG(p + 6 * S) + LDG(p + 7 * S) + LDG(p + 8 * S) + LDG(p + 11 * S);
+    } else {
+      const double* p = A.efX + (size_t)(3 * ln) * A.SX + idx;
+      const size_t S = A.SX;
+      f[0] = f[0] + LDG(p) + LDG(p + 24 * S);
+      f[1] = f[1] + LDG(p + S) + LDG(p + 25 * S);
+      f[2] = f[2] + LDG(p + 2 * S) + LDG(p + 26 * S);
+    }
+  }
+}
+
+__device__ __forceinline__ void gather12(const NodeArgs& A, int n, double f[12]) {
+  const int b = LDG(A.adjStart + n), e = LDG(A.adjStart + n + 1);
+#pragma unroll
+  for (int j = 0; j < 12; ++j) f[j] = 0.0;
+  for (int k = b; k < e; ++k) {
+    const uint32_t u = LDG(A.adj + k);
+    const int cls = u & 3, ln = (u >> 2) & 7;
+    const size_t idx = u >> 5;
+    if (cls == CLS_PML) {
+      const double* p = A.efP + (size_t)(12 * ln) * A.SP + idx;
+#pragma unroll
+      for (int j = 0; j < 12; ++j) f[j] += LDG(p + (size_t)j * A.SP);
+    } else if (cls == CLS_REGX) {
+      // regular element on a 12-dof node: KU goes to dofs 1-3
+      // (assembleGlobalKU.f90:28-35), hourglass to dofs 10-12 (hrglss.f90:44-48)
+      const double* p = A.efX + (size_t)(3 * ln) * A.SX + idx;
+      const size_t S = A.SX;
+      f[0] += LDG(p); f[1] += LDG(p + S); f[2] += LDG(p + 2 * S);
+      f[9] += LDG(p + 24 * S); f[10] += LDG(p + 25 * S); f[11] += LDG(p + 26 * S);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// velDispUpdate (driver.f90:89-155) fused with the force assembly and with the
+// previous step's `nodalForceArr/nodalMassArr` (driver.f90:29).
+__global__ void __launch_bounds__(256) k_node_update(NodeArgs A) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= A.Nn) return;
+  const int info = LDG(A.info + n);
+  const int kind = EQD_INFO_KIND(info);
+  if (kind == KIND_FIXED) return;  // vel = disp = 0 for ever (driver.f90:142-145)
+  const double dt = A.dt;
+  const size_t NS = A.NnS;
+  const double m = LDG(A.mass + n);
+  bool bad = false;
+  if (kind == KIND_FREE3) {
+    double a[3];
+    if (A.accel0) {
+      a[0] = A.accel0[n]; a[1] = A.accel0[NS + n]; a[2] = A.accel0[2 * NS + n];
+    } else {
+      double f[3];
+      if (EQD_INFO_SPECIAL(info)) {
+        f[0] = A.force[n]; f[1] = A.force[NS + n]; f[2] = A.force[2 * NS + n];
+      } else {
+        gather3(A, n, f);
+      }
+      a[0] = f[0] / m; a[1] = f[1] / m; a[2] = f[2] / m;
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      double v = A.vel[j * NS + n];
+      v = v + a[j] * dt;                      // driver.f90:102
+      A.vel[j * NS + n] = v;                  // :103
+      A.disp[j * NS + n] = A.disp[j * NS + n] + v * dt;  // :104
+      bad |= (v != v);
+    }
+  } else {
+    const int slot = EQD_INFO_SLOT(info);
+    const size_t PS = A.NpS;
+    double a[12];
+    if (A.accel0) {
+      const double* ap = A.accel0 + 3 * NS;
+#pragma unroll
+      for (int j = 0; j < 12; ++j) a[j] = ap[j * PS + slot];
+    } else {
+      double f[12];
+      if (EQD_INFO_SPECIAL(info)) {
+        const double* fp = A.force + 3 * NS;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) f[j] = fp[j * PS + slot];
+      } else {
+        gather12(A, n, f);
+      }
+#pragma unroll
+      for (int j = 0; j < 12; ++j) a[j] = f[j] / m;
+    }
+    double d[3], v[12];
+    d[0] = LDG(A.dampp + slot); d[1] = LDG(A.dampp + PS + slot); d[2] = LDG(A.dampp + 2 * PS + slot);
+    const double rdt = 1.0 / dt;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {             // driver.f90:112-117, dampv(j) = damp(mod(j-1,3)+1)
+      const double dj = d[j % 3];
+      v[j] = (a[j] + A.v1p[j * PS + slot] * (rdt - dj / 2.0)) / (rdt + dj / 2.0);
+      A.v1p[j * PS + slot] = v[j];
+    }
+#pragma unroll
+    for (int j = 9; j < 12; ++j) {            // :118-123
+      v[j] = A.v1p[j * PS + slot] + a[j] * dt;
+      A.v1p[j * PS + slot] = v[j];
+    }
+    double vel[3];
+    vel[0] = v[0] + v[1] + v[2] + v[9];       // :125-141
+    vel[1] = v[3] + v[4] + v[5] + v[10];
+    vel[2] = v[6] + v[7] + v[8] + v[11];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      A.vel[j * NS + n] = vel[j];
+      A.disp[j * NS + n] = A.disp[j * NS + n] + vel[j] * dt;
+      bad |= (vel[j] != vel[j]);
+    }
+  }
+  if (bad) {
+    if (atomicExch(&A.st->nanFlag, 1) == 0) A.st->nanNode = n + 1;
+  }
+}
+
+// materialise the ordered force sums of the "special" nodes
+__global__ void __launch_bounds__(128) k_assemble_special(NodeArgs A, const int* __restrict__ list, int nList) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nList) return;
+  const int n = list[i];
+  const int info = LDG(A.info + n);
+  const int kind = EQD_INFO_KIND(info);
+  const size_t NS = A.NnS;
+  if (kind == KIND_FREE3) {
+    double f[3];
+    gather3(A, n, f);
+    A.force[n] = f[0]; A.force[NS + n] = f[1]; A.force[2 * NS + n] = f[2];
+  } else if (kind == KIND_PML12) {
+    double f[12];
+    gather12(A, n, f);
+    const int slot = EQD_INFO_SLOT(info);
+    double* fp = A.force + 3 * NS;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) fp[(size_t)j * A.NpS + slot] = f[j];
+  }
+}
+
+// nodalForceArr as the reference leaves it after driver.f90:29 (f/m), for eqd_fetch
+__global__ void k_materialize_accel(NodeArgs A, double* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= A.Nn) return;
+  const int info = LDG(A.info + n);
+  const int kind = EQD_INFO_KIND(info);
+  const size_t NS = A.NnS;
+  const double m = LDG(A.mass + n);
+  if (kind == KIND_FREE3) {
+    double f[3];
+    if (A.accel0) { out[n] = A.accel0[n]; out[NS + n] = A.accel0[NS + n]; out[2 * NS + n] = A.accel0[2 * NS + n]; return; }
+    if (EQD_INFO_SPECIAL(info)) { f[0] = A.force[n]; f[1] = A.force[NS + n]; f[2] = A.force[2 * NS + n]; }
+    else gather3(A, n, f);
+    out[n] = f[0] / m; out[NS + n] = f[1] / m; out[2 * NS + n] = f[2] / m;
+  } else if (kind == KIND_PML12) {
+    const int slot = EQD_INFO_SLOT(info);
+    const size_t PS = A.NpS;
+    double f[12];
+    if (A.accel0) {
+      for (int j = 0; j < 12; ++j) out[3 * NS + j * PS + slot] = A.accel0[3 * NS + j * PS + slot];
+      return;
+    }
+    if (EQD_INFO_SPECIAL(info)) { for (int j = 0; j < 12; ++j) f[j] = A.force[3 * NS + j * PS + slot]; }
+    else gather12(A, n, f);
+    for (int j = 0; j < 12; ++j) out[3 * NS + j * PS + slot] = f[j] / m;
+  }
+}
+
+// ----------------------------------------------------------------------------
+// Regular hexahedron / degenerate wedge: calcElemKU.f90:3-191 (+ calcB.f90,
+// calcElemMass.f90) fused with hrglss.f90:13-98.  The 6x24 B matrix is never
+// materialised; two passes over the 8 nodes keep the live state small:
+//   pass 1  gather v,d -> strain rate (strain), hourglass modal amplitudes
+//   pass 2  B^T sigma and the hourglass forces per node -> ef
+template <bool PLASTIC, bool QMODE, bool BODY, bool SPLIT, int CHG>
+__global__ void __launch_bounds__(128) k_elem_reg(ElemArgs A) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= A.n) return;
+  const size_t S = A.S, NS = A.NnS;
+  const double dt = A.dt, rdampk = A.rdampk;
+  double sr[6] = {0, 0, 0, 0, 0, 0}, sn[6] = {0, 0, 0, 0, 0, 0};
+  double phid[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  double qv[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};  // viscous hourglass (C_hg==2)
+  double body[BODY ? 24 : 1];
+  double xc2 = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int nd = LDG(A.conn + i * S + e);
+    const double vx = LDG(A.vel + nd), vy = LDG(A.vel + NS + nd), vz = LDG(A.vel + 2 * NS + nd);
+    const double dx = LDG(A.disp + nd), dy = LDG(A.disp + NS + nd), dz = LDG(A.disp + 2 * NS + nd);
+    const double s1 = LDG(A.shp + (3 * i) * S + e), s2 = LDG(A.shp + (3 * i + 1) * S + e), s3 = LDG(A.shp + (3 * i + 2) * S + e);
+    // calcElemKU.f90:44-60 (B with engineering shear, calcB.f90:10-25)
+    sr[0] = sr[0] + s1 * vx;
+    sr[1] = sr[1] + s2 * vy;
+    sr[2] = sr[2] + s3 * vz;
+    sr[3] = sr[3] + s3 * vy + s2 * vz;
+    sr[4] = sr[4] + s3 * vx + s1 * vz;
+    sr[5] = sr[5] + s2 * vx + s1 * vy;
+    if (QMODE) {
+      sn[0] = sn[0] + s1 * dx;
+      sn[1] = sn[1] + s2 * dy;
+      sn[2] = sn[2] + s3 * dz;
+      sn[3] = sn[3] + s3 * dy + s2 * dz;
+      sn[4] = sn[4] + s3 * dx + s1 * dz;
+      sn[5] = sn[5] + s2 * dx + s1 * dy;
+    }
+    if (CHG == 1) {
+      // hrglss.f90:20-33: dl = d + rdampk*v ; phid = sum_j phi(j,m)*dl(j)
+      const double lx = dx + rdampk * vx, ly = dy + rdampk * vy, lz = dz + rdampk * vz;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const double p = LDG(A.phi + (8 * m + i) * S + e);
+        phid[m][0] = phid[m][0] + p * lx;
+        phid[m][1] = phid[m][1] + p * ly;
+        phid[m][2] = phid[m][2] + p * lz;
+      }
+    } else if (CHG == 2) {
+      // hrglss.f90:57-70
+      const int fi[4][8] = {{1, 1, -1, -1, -1, -1, 1, 1}, {1, -1, -1, 1, -1, 1, 1, -1},
+                            {1, -1, 1, -1, 1, -1, 1, -1}, {1, -1, 1, -1, -1, 1, -1, 1}};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        qv[0][j] = qv[0][j] + vx * fi[j][i];
+        qv[1][j] = qv[1][j] + vy * fi[j][i];
+        qv[2][j] = qv[2][j] + vz * fi[j][i];
+      }
+    }
+    if (BODY) {
+      // assembleGlobalKU.f90:15-16 + calcElemMass.f90: elresf = -al*elemass
+      const double em = LDG(A.emass + i * S + e);
+      body[3 * i] = 0.0 - (A.rdampm * vx) * em;
+      body[3 * i + 1] = 0.0 - (A.rdampm * vy) * em;
+      body[3 * i + 2] = 0.0 - (A.rdampm * vz + A.bodyz) * em;
+    }
+  }
+  const double lam = LDG(A.lam + e), mu = LDG(A.mu + e);
+  const double l2m = lam + 2 * mu;
+  double rate[6];
+  // calcElemKU.f90:63-70
+  rate[0] = 0.0 + l2m * sr[0] + lam * sr[1] + lam * sr[2];
+  rate[1] = 0.0 + lam * sr[0] + l2m * sr[1] + lam * sr[2];
+  rate[2] = 0.0 + lam * sr[0] + lam * sr[1] + l2m * sr[2];
+  rate[3] = mu * sr[3];
+  rate[4] = mu * sr[4];
+  rate[5] = mu * sr[5];
+  double sg[6];
+  if (!QMODE) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) sg[i] = A.stress[i * S + e] + rate[i] * dt;  // :72-76
+  } else {
+    // calcElemKU.f90:77-132, constants tabulated per class (qconstant.f90)
+    const QTab q = c_qtab[A.qcls[e]];
+    const double miuu = mu * q.cs, Mu = l2m * q.cv;
+    const double vols = sn[0] + sn[1] + sn[2];
+    const double ex = q.expdt;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const double a1 = A.qmem[i * S + e];
+      double an;
+      if (i < 3) an = ex * a1 + (1 - ex) * (2 * miuu * sn[i] * q.wks + (Mu * q.wkp - 2 * miuu * q.wks) * vols);
+      else an = ex * a1 + (1 - ex) * (miuu * sn[i] * q.wks);
+      A.qmem[i * S + e] = an;
+      if (i < 3) sg[i] = 2.0 * miuu * sn[i] + (Mu - 2.0 * miuu) * vols - 0.5 * (an + a1);
+      else sg[i] = 2.0 * miuu * sn[i] / 2.0 - 0.5 * (an + a1);
+    }
+  }
+  if (PLASTIC) {
+    // Drucker-Prager viscoplasticity, calcElemKU.f90:133-167
+    const double strmea = (sg[0] + sg[1] + sg[2]) / 3.0;
+    double dv[6] = {sg[0] - strmea, sg[1] - strmea, sg[2] - strmea, sg[3], sg[4], sg[5]};
+    double taomax = 0.5 * (dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]) + dv[3] * dv[3] + dv[4] * dv[4] + dv[5] * dv[5];
+    taomax = sqrt(taomax);
+    double yield = A.ccosphi - A.sinphi * (strmea + LDG(A.porep + e));
+    if (yield < 0.0) yield = 0.0;
+    if (taomax > yield) {
+      const double rjust = yield / taomax + (1 - yield / taomax) * A.expdttv;
+      double pi[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        sg[i] = dv[i] * rjust;
+        pi[i] = (dv[i] - sg[i]) / mu;
+        if (i < 3) sg[i] = sg[i] + strmea;
+      }
+      const double pm = (pi[0] + pi[1] + pi[2]) / 3.0;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) pi[i] = pi[i] - pm;
+      double mag = 0.5 * (pi[0] * pi[0] + pi[1] * pi[1] + pi[2] * pi[2]) + pi[3] * pi[3] + pi[4] * pi[4] + pi[5] * pi[5];
+      A.pstrain[e] = A.pstrain[e] + sqrt(mag);   // assembleGlobalKU.f90:26
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) A.stress[i * S + e] = sg[i];
+  // calcElemKU.f90:169-173, constk = -eledet
+  const double temp = (-LDG(A.det + e)) * A.w;
+  double t[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) t[i] = temp * (sg[i] + rdampk * rate[i]);
+  double hv[4][3];
+  double coef = 0.0;
+  if (CHG == 1) {
+    double ssv[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) ssv[i] = LDG(A.ss + i * S + e);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {  // hrglss.f90:35-40
+      hv[m][0] = ssv[0] * phid[m][0] + ssv[1] * phid[m][1] + ssv[2] * phid[m][2];
+      hv[m][1] = ssv[1] * phid[m][0] + ssv[3] * phid[m][1] + ssv[4] * phid[m][2];
+      hv[m][2] = ssv[2] * phid[m][0] + ssv[4] * phid[m][1] + ssv[5] * phid[m][2];
+    }
+  } else if (CHG == 2) {
+    coef = 0.25 * A.kapa_hg * LDG(A.rho + e) * LDG(A.vp + e) * pow(LDG(A.det + e) * A.w, 2.0 / 3.0);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const double s1 = LDG(A.shp + (3 * i) * S + e), s2 = LDG(A.shp + (3 * i + 1) * S + e), s3 = LDG(A.shp + (3 * i + 2) * S + e);
+    // calcElemKU.f90:175-189
+    double f0 = s1 * t[0] + s3 * t[4] + s2 * t[5];
+    double f1 = s2 * t[1] + s3 * t[3] + s1 * t[5];
+    double f2 = s3 * t[2] + s2 * t[3] + s1 * t[4];
+    if (BODY) { f0 = body[3 * i] + f0; f1 = body[3 * i + 1] + f1; f2 = body[3 * i + 2] + f2; }
+    double h0 = 0.0, h1 = 0.0, h2 = 0.0;
+    if (CHG == 1) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {  // hrglss.f90:41-54: force -= phi(i,m)*(SS.phid)
+        const double p = LDG(A.phi + (8 * m + i) * S + e);
+        h0 = h0 - p * hv[m][0];
+        h1 = h1 - p * hv[m][1];
+        h2 = h2 - p * hv[m][2];
+      }
+    } else if (CHG == 2) {
+      const int fi[4][8] = {{1, 1, -1, -1, -1, -1, 1, 1}, {1, -1, -1, 1, -1, 1, 1, -1},
+                            {1, -1, 1, -1, 1, -1, 1, -1}, {1, -1, 1, -1, -1, 1, -1, 1}};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {  // hrglss.f90:71-80
+        h0 = h0 - coef * qv[0][j] * fi[j][i];
+        h1 = h1 - coef * qv[1][j] * fi[j][i];
+        h2 = h2 - coef * qv[2][j] * fi[j][i];
+      }
+    }
+    if (SPLIT) {
+      A.ef[(3 * i) * S + e] = f0; A.ef[(3 * i + 1) * S + e] = f1; A.ef[(3 * i + 2) * S + e] = f2;
+      A.ef[(24 + 3 * i) * S + e] = h0; A.ef[(25 + 3 * i) * S + e] = h1; A.ef[(26 + 3 * i) * S + e] = h2;
+    } else {
+      A.ef[(3 * i) * S + e] = f0 + h0; A.ef[(3 * i + 1) * S + e] = f1 + h1; A.ef[(3 * i + 2) * S + e] = f2 + h2;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// PML element: calcPMLElemKU (assembleGlobalKU.f90:70-346) fused with hrglss.
+// The damping profile at the centroid (:130-213, constant in time) is
+// precomputed by the host into damps[3][S].
+template <bool BODY, int CHG>
+__global__ void __launch_bounds__(128) k_elem_pml(ElemArgs A) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= A.n) return;
+  const size_t S = A.S, NS = A.NnS;
+  const double dt = A.dt, rdampk = A.rdampk;
+  double g[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};  // g[a][b] = d v_b / d x_a
+  double sr[6] = {0, 0, 0, 0, 0, 0};
+  double phid[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  double qv[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+  double body[BODY ? 24 : 1];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int nd = LDG(A.conn + i * S + e);
+    const double vx = LDG(A.vel + nd), vy = LDG(A.vel + NS + nd), vz = LDG(A.vel + 2 * NS + nd);
+    const double s1 = LDG(A.shp + (3 * i) * S + e), s2 = LDG(A.shp + (3 * i + 1) * S + e), s3 = LDG(A.shp + (3 * i + 2) * S + e);
+    // assembleGlobalKU.f90:215-246
+    sr[0] = sr[0] + s1 * vx;
+    sr[1] = sr[1] + s2 * vy;
+    sr[2] = sr[2] + s3 * vz;
+    sr[3] = sr[3] + s3 * vy + s2 * vz;
+    sr[4] = sr[4] + s3 * vx + s1 * vz;
+    sr[5] = sr[5] + s2 * vx + s1 * vy;
+    // :248-275
+    g[0][0] = g[0][0] + s1 * vx; g[1][1] = g[1][1] + s2 * vy; g[2][2] = g[2][2] + s3 * vz;
+    g[0][1] = g[0][1] + s1 * vy; g[1][0] = g[1][0] + s2 * vx;
+    g[0][2] = g[0][2] + s1 * vz; g[2][0] = g[2][0] + s3 * vx;
+    g[1][2] = g[1][2] + s2 * vz; g[2][1] = g[2][1] + s3 * vy;
+    if (CHG == 1) {
+      const double dx = LDG(A.disp + nd), dy = LDG(A.disp + NS + nd), dz = LDG(A.disp + 2 * NS + nd);
+      const double lx = dx + rdampk * vx, ly = dy + rdampk * vy, lz = dz + rdampk * vz;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const double p = LDG(A.phi + (8 * m + i) * S + e);
+        phid[m][0] = phid[m][0] + p * lx;
+        phid[m][1] = phid[m][1] + p * ly;
+        phid[m][2] = phid[m][2] + p * lz;
+      }
+    } else if (CHG == 2) {
+      const int fi[4][8] = {{1, 1, -1, -1, -1, -1, 1, 1}, {1, -1, -1, 1, -1, 1, 1, -1},
+                            {1, -1, 1, -1, 1, -1, 1, -1}, {1, -1, 1, -1, -1, 1, -1, 1}};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        qv[0][j] = qv[0][j] + vx * fi[j][i];
+        qv[1][j] = qv[1][j] + vy * fi[j][i];
+        qv[2][j] = qv[2][j] + vz * fi[j][i];
+      }
+    }
+    if (BODY) {
+      const double em = LDG(A.emass + i * S + e);
+      body[3 * i] = 0.0 - (A.rdampm * vx) * em;
+      body[3 * i + 1] = 0.0 - (A.rdampm * vy) * em;
+      body[3 * i + 2] = 0.0 - (A.rdampm * vz + A.bodyz) * em;
+    }
+  }
+  const double lam = LDG(A.lam + e), mu = LDG(A.mu + e);
+  const double l2m = lam + 2.0 * mu;
+  double rate[6];
+  rate[0] = 0.0 + l2m * sr[0] + lam * sr[1] + lam * sr[2];
+  rate[1] = 0.0 + lam * sr[0] + l2m * sr[1] + lam * sr[2];
+  rate[2] = 0.0 + lam * sr[0] + lam * sr[1] + l2m * sr[2];
+  rate[3] = mu * sr[3];
+  rate[4] = mu * sr[4];
+  rate[5] = mu * sr[5];
+  const double dp[3] = {LDG(A.damps + e), LDG(A.damps + S + e), LDG(A.damps + 2 * S + e)};
+  const double rdt = 1 / dt;
+  // :277-311  s <- (coef*D + (1/dt - d/2) s) / (1/dt + d/2)
+  double s[15];
+#define PML_UPD(k, coef, D, a)                                          \
+  {                                                                     \
+    double x = (coef) * (D) + (rdt - dp[a] / 2) * A.stress[(k) * S + e]; \
+    x = x / (rdt + dp[a] / 2);                                          \
+    s[k] = x;                                                           \
+    A.stress[(k) * S + e] = x;                                          \
+  }
+  PML_UPD(0, l2m, g[0][0], 0) PML_UPD(1, lam, g[1][1], 1) PML_UPD(2, lam, g[2][2], 2)
+  PML_UPD(3, lam, g[0][0], 0) PML_UPD(4, l2m, g[1][1], 1) PML_UPD(5, lam, g[2][2], 2)
+  PML_UPD(6, lam, g[0][0], 0) PML_UPD(7, lam, g[1][1], 1) PML_UPD(8, l2m, g[2][2], 2)
+  PML_UPD(9, mu, g[0][1], 0) PML_UPD(10, mu, g[1][0], 1)
+  PML_UPD(11, mu, g[0][2], 0) PML_UPD(12, mu, g[2][0], 2)
+  PML_UPD(13, mu, g[1][2], 1) PML_UPD(14, mu, g[2][1], 2)
+#undef PML_UPD
+  const double sxx = s[0] + s[1] + s[2], syy = s[3] + s[4] + s[5], szz = s[6] + s[7] + s[8];
+  const double sxy = s[9] + s[10], sxz = s[11] + s[12], syz = s[13] + s[14];
+  double s0[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) s0[i] = LDG(A.stress + (15 + i) * S + e) + rdampk * rate[i];  // :320-325 (read-only slots)
+  const double det = LDG(A.det + e), w = A.w;
+  double hv[4][3];
+  double coef = 0.0;
+  if (CHG == 1) {
+    double ssv[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) ssv[i] = LDG(A.ss + i * S + e);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      hv[m][0] = ssv[0] * phid[m][0] + ssv[1] * phid[m][1] + ssv[2] * phid[m][2];
+      hv[m][1] = ssv[1] * phid[m][0] + ssv[3] * phid[m][1] + ssv[4] * phid[m][2];
+      hv[m][2] = ssv[2] * phid[m][0] + ssv[4] * phid[m][1] + ssv[5] * phid[m][2];
+    }
+  } else if (CHG == 2) {
+    coef = 0.25 * A.kapa_hg * LDG(A.rho + e) * LDG(A.vp + e) * pow(det * w, 2.0 / 3.0);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const double s1 = LDG(A.shp + (3 * i) * S + e), s2 = LDG(A.shp + (3 * i + 1) * S + e), s3 = LDG(A.shp + (3 * i + 2) * S + e);
+    double* f = A.ef + (size_t)(12 * i) * S + e;
+    // :328-344
+    f[0] = 0.0 - det * w * s1 * sxx;
+    f[S] = 0.0 - det * w * s2 * sxy;
+    f[2 * S] = 0.0 - det * w * s3 * sxz;
+    f[3 * S] = 0.0 - det * w * s1 * sxy;
+    f[4 * S] = 0.0 - det * w * s2 * syy;
+    f[5 * S] = 0.0 - det * w * s3 * syz;
+    f[6 * S] = 0.0 - det * w * s1 * sxz;
+    f[7 * S] = 0.0 - det * w * s2 * syz;
+    f[8 * S] = 0.0 - det * w * s3 * szz;
+    double b0 = 0.0, b1 = 0.0, b2 = 0.0;
+    if (BODY) { b0 = body[3 * i]; b1 = body[3 * i + 1]; b2 = body[3 * i + 2]; }
+    double f9 = b0 - det * w * (s1 * s0[0] + s3 * s0[4] + s2 * s0[5]);
+    double f10 = b1 - det * w * (s2 * s0[1] + s3 * s0[3] + s1 * s0[5]);
+    double f11 = b2 - det * w * (s3 * s0[2] + s2 * s0[3] + s1 * s0[4]);
+    if (CHG == 1) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const double p = LDG(A.phi + (8 * m + i) * S + e);
+        f9 = f9 - p * hv[m][0];
+        f10 = f10 - p * hv[m][1];
+        f11 = f11 - p * hv[m][2];
+      }
+    } else if (CHG == 2) {
+      const int fi[4][8] = {{1, 1, -1, -1, -1, -1, 1, 1}, {1, -1, -1, 1, -1, 1, 1, -1},
+                            {1, -1, 1, -1, 1, -1, 1, -1}, {1, -1, 1, -1, -1, 1, -1, 1}};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        f9 = f9 - coef * qv[0][j] * fi[j][i];
+        f10 = f10 - coef * qv[1][j] * fi[j][i];
+        f11 = f11 - coef * qv[2][j] * fi[j][i];
+      }
+    }
+    f[9 * S] = f9; f[10 * S] = f10; f[11 * S] = f11;
+  }
+}
+
+// ----------------------------------------------------------------------------
+// storeOffFaultStData, driver.f90:157-180
+__global__ void k_store_offfault(const int* __restrict__ idhist, int n, double* __restrict__ out,
+                                 const double* __restrict__ vel, const double* __restrict__ disp, int NnS,
+                                 const StepState* st) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 0..n   (0 = time)
+  if (i > n) return;
+  double* row = out + (size_t)(n + 1) * (st->nt - 1);
+  if (i == 0) { row[0] = st->timeElapsed; return; }
+  const int node = idhist[3 * (i - 1)] - 1, k = idhist[3 * (i - 1) + 1] - 1, q = idhist[3 * (i - 1) + 2];
+  if (q == 1) row[i] = disp[(size_t)k * NnS + node];
+  else if (q == 2) row[i] = vel[(size_t)k * NnS + node];
+}
+
+// output_gm / output_src_evol samples (library_output.f90:267-279,297-312)
+__global__ void k_sample_gm(const int* __restrict__ surf, int nSurf, const double* __restrict__ vel, int NnS,
+                            double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nSurf) return;
+  const int n = surf[i] - 1;
+  out[3 * (size_t)i] = vel[n]; out[3 * (size_t)i + 1] = vel[(size_t)NnS + n]; out[3 * (size_t)i + 2] = vel[2 * (size_t)NnS + n];
+}
+__global__ void k_sample_src(const double* __restrict__ fric, int PS, int n, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = fric[(size_t)46 * PS + i];  // fric(47,i,1)
+}
+
+// ----------------------------------------------------------------------------
+// halo pack / unpack-add (processNodalQuantArr, assembleGlobalMass.f90:145-236)
+__global__ void k_pack(const double* __restrict__ src, const uint32_t* __restrict__ idx, int n, double* __restrict__ buf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) buf[i] = src[idx[i]];
+}
+__global__ void k_unpack_add(double* __restrict__ dst, const uint32_t* __restrict__ idx, int n, const double* __restrict__ buf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[idx[i]] = dst[idx[i]] + buf[i];
+}
+
+// ----------------------------------------------------------------------------
+// thermop.f90:1-40: one thread per pair, O(nt) history convolution
+__global__ void __launch_bounds__(128) k_thermop(FaultArgs A) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= A.nPairs) return;
+  const size_t PS = A.PS;
+#define FR(k) A.fric[(size_t)((k) - 1) * PS + p]
+  const double dt = A.dt, pi = 4 * atan(1.0), h = A.fric_tp_h;
+  const int nt = A.st->nt;
+  const double gama = FR(19) / FR(18), omega = FR(16), kapa = FR(17);
+  double tmp = 0.0, tmp2 = 0.0;
+  for (int j = 1; j <= nt - 1; ++j) {
+    const double V = A.tphist[((size_t)(j - 1) * 2) * PS + p], tau = A.tphist[((size_t)(j - 1) * 2 + 1) * PS + p];
+    double ker = -kapa / (omega - kapa) / sqrt(4.0 * kapa * (nt - j) * dt + 2.0 * (h * h));
+    ker = ker + omega / (omega - kapa) / sqrt(4.0 * omega * (nt - j) * dt + 2.0 * (h * h));
+    tmp = tmp + fabs(tau) * V * ker * dt;
+    const double ker2 = 1.0 / sqrt(4.0 * kapa * (nt - j) * dt + 2.0 * (h * h));
+    tmp2 = tmp2 + fabs(tau) * V * ker2 * dt;
+  }
+  FR(51) = tmp * gama / sqrt(pi);
+  FR(52) = tmp2 / FR(18) / sqrt(pi) + FR(41);
+#undef FR
+}
+
+// ----------------------------------------------------------------------------
+// fric.f90
+__device__ __forceinline__ double d_slip_weak(double slip, double fs, double fd, double d0) {  // fric.f90:3-19
+  double xmu = 0.0;
+  if (fabs(slip) < (double)1.0e-10f) xmu = fs;
+  else if (slip < d0) xmu = fs - (fs - fd) * slip / d0;
+  if (slip >= d0) xmu = fd;
+  return xmu;
+}
+__device__ __forceinline__ double d_time_weak(double trupt, double fs, double fd, double t0) {  // fric.f90:21-37
+  if (trupt <= 0.0) return fs;
+  else if (trupt < t0) return fs - (fs - fd) * trupt / t0;
+  return fd;
+}
+struct RsfPar { double A, B, L, f0, V0, fw, Vw; };
+__device__ __forceinline__ void d_rsf_ageing(double V2, double& theta, const RsfPar& r, double& xmu, double& dxmudv, double dt) {  // fric.f90:39-61
+  const double tmpc = 1.0 / (2.0 * r.V0) * exp((r.f0 + r.B * log(r.V0 * theta / r.L)) / r.A);
+  const double tmp = (V2 + 1.e-30) * tmpc;
+  xmu = r.A * log(tmp + sqrt(tmp * tmp + 1.0));
+  dxmudv = r.A * tmpc / sqrt(1.0 + tmp * tmp);
+  theta = r.L / V2 + (theta - r.L / V2) * exp(-V2 * dt / r.L);
+}
+__device__ __forceinline__ void d_rsf_slip(double V2, double& psi, const RsfPar& r, double& xmu, double& dxmudv, double dt) {  // fric.f90:63-95
+  const double tmpc = 1.0 / (2.0 * r.V0) * exp(psi / r.A);
+  const double tmp = (V2 + 1.e-30) * tmpc;
+  xmu = r.A * log(tmp + sqrt(tmp * tmp + 1.0));
+  dxmudv = r.A * tmpc / sqrt(1.0 + tmp * tmp);
+  const double fLV = r.f0 - (r.B - r.A) * log(V2 / r.V0);
+  const double q = V2 / r.Vw, q2 = q * q, q4 = q2 * q2;
+  const double fss = r.fw + (fLV - r.fw) / pow(1.0 + q4 * q4, 0.125);
+  const double fssa = fss / r.A;
+  const double psiss = r.A * log(2.0 * r.V0 / V2 * (exp(fssa) - exp(-fssa)) / 2.0);
+  psi = psiss + (psi - psiss) * exp(-V2 * dt / r.L);
+}
+
+// faulting.f90:3-541, one thread per split-node pair
+__global__ void __launch_bounds__(128) k_fault(FaultArgs A) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= A.nPairs) return;
+  const size_t PS = A.PS, NS = A.NnS;
+#define FR(k) A.fric[(size_t)((k) - 1) * PS + p]
+  const double dt = A.dt;
+  const int nt = A.st->nt;
+  const double timeElapsed = A.st->timeElapsed;
+  const int nS = A.nodeS[p], nM = A.nodeM[p];
+  const int ift = A.ift[p];
+  double un[3], us[3], ud[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { un[k] = A.un[k * PS + p]; us[k] = A.us[k * PS + p]; ud[k] = A.ud[k * PS + p]; }
+  const double arn = A.arn[p];
+  const double Cel = (double)A.C_elastic;
+  // ---- getNsdSlipSliprateTraction, faulting.f90:54-134
+  const double initT[3] = {FR(7), FR(8) + 0.0, FR(49)};
+  const double massSlave = A.massS[p], massMaster = A.massM[p];
+  const double totalMass = (massSlave + massMaster) * arn;
+  double fS[3], fM[3], vS[3], vM[3], dS[3], dM[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    fS[k] = A.force[k * NS + nS]; fM[k] = A.force[k * NS + nM];
+    vS[k] = A.vel[k * NS + nS]; vM[k] = A.vel[k * NS + nM];
+    dS[k] = A.disp[k * NS + nS]; dM[k] = A.disp[k * NS + nM];
+  }
+#define ROT(x, u) ((x)[0] * (u)[0] + (x)[1] * (u)[1] + (x)[2] * (u)[2])
+  const double fSn[3] = {ROT(fS, un), ROT(fS, us), ROT(fS, ud)}, fMn[3] = {ROT(fM, un), ROT(fM, us), ROT(fM, ud)};
+  const double vSn[3] = {ROT(vS, un), ROT(vS, us), ROT(vS, ud)}, vMn[3] = {ROT(vM, un), ROT(vM, us), ROT(vM, ud)};
+  const double dSn[3] = {ROT(dS, un), ROT(dS, us), ROT(dS, ud)}, dMn[3] = {ROT(dM, un), ROT(dM, us), ROT(dM, ud)};
+#undef ROT
+  double slip[4], rate[4], T[4];
+  for (int j = 0; j < 3; ++j) slip[j] = dMn[j] - dSn[j];
+  slip[3] = sqrt(slip[0] * slip[0] + slip[1] * slip[1] + slip[2] * slip[2]);
+  for (int j = 0; j < 3; ++j) rate[j] = vMn[j] - vSn[j];
+  rate[3] = sqrt(rate[0] * rate[0] + rate[1] * rate[1] + rate[2] * rate[2]);
+  FR(71) = slip[1]; FR(72) = slip[2]; FR(73) = slip[0];
+  FR(74) = rate[1]; FR(75) = rate[2];
+  double f76 = FR(76);
+  if (rate[3] > f76) { f76 = rate[3]; FR(76) = f76; }
+  const double f77 = FR(77) + rate[3] * dt;
+  FR(77) = f77;
+  T[0] = (massSlave * massMaster * ((vMn[0] - vSn[0]) + (dMn[0] - dSn[0]) / dt) / dt + massSlave * fMn[0] -
+          massMaster * fSn[0]) / totalMass + initT[0] * Cel;
+  T[1] = (massSlave * massMaster * (vMn[1] - vSn[1]) / dt + massSlave * fMn[1] - massMaster * fSn[1]) / totalMass +
+         initT[1] * Cel;
+  T[2] = (massSlave * massMaster * (vMn[2] - vSn[2]) / dt + massSlave * fMn[2] - massMaster * fSn[2]) / totalMass +
+         initT[2] * Cel;
+  const double xs0 = A.xs[p], xs1 = A.xs[PS + p], xs2 = A.xs[2 * PS + p];
+  const double radius = sqrt((xs0 - A.xsource) * (xs0 - A.xsource) + (xs1 - A.ysource) * (xs1 - A.ysource) +
+                             (xs2 - A.zsource) * (xs2 - A.zsource));
+  double f20 = 0.0, f23 = 0.0;
+  if (A.friclaw >= 3) { f20 = FR(20); f23 = FR(23); }
+  if (A.friclaw >= 3 && A.C_nuclea == 1 && ift == A.nucfault) {
+    // rsfNucleation, faulting.f90:367-414
+    double dtau2 = 0.0, Fq = 0.0, G = 1.0;
+    if (radius < A.nucR) Fq = exp(radius * radius / (radius * radius - A.nucR * A.nucR));
+    if (timeElapsed <= A.nucT)
+      G = exp((timeElapsed - A.nucT) * (timeElapsed - A.nucT) / (timeElapsed * (timeElapsed - 2.0 * A.nucT)));
+    if (A.TPV == 105 || A.TPV == 104) dtau2 = A.nucdtau0 * Fq * G;
+    else if (A.TPV == 2802) {
+      if (nt == 1) {
+        FR(81) = A.nucdtau0;
+        const double ttao = sqrt(T[1] * T[1] + T[2] * T[2]);
+        const double back = sqrt((rate[1] + FR(26)) * (rate[1] + FR(26)) + (rate[2] + FR(27)) * (rate[2] + FR(27)));
+        f20 = FR(9) * log(2.0 * FR(12) / back * sinh(ttao / fabs(T[0]) / FR(9)));
+        f23 = fabs(T[0]);
+      }
+      dtau2 = FR(81) * Fq * G;
+    }
+    T[1] = T[1] + dtau2;
+  }
+  T[3] = sqrt(T[1] * T[1] + T[2] * T[2]);
+
+  if (A.friclaw <= 2) {
+    // ---- solveSWTW, faulting.f90:136-188
+    double mu = 0.0;
+    const double fs = FR(1), fd = FR(2);
+    if (A.friclaw == 1) mu = d_slip_weak(f77, fs, fd, FR(3));
+    else mu = d_time_weak(timeElapsed - A.fnft[p], fs, fd, FR(5));
+    if (A.C_nuclea == 1 && ift == A.nucfault) {
+      // swtwNucleation, faulting.f90:416-443
+      double tr = 1.0e9;
+      if (radius <= A.nucR) {
+        if (A.TPV == 201 || A.TPV == 36 || A.TPV == 37)
+          tr = (radius + 0.081 * A.nucR * (1.0 / (1.0 - (radius / A.nucR) * (radius / A.nucR)) - 1.0)) / (0.7 * 3464.0);
+        if (A.TPV == 202) tr = radius / A.nucRuptVel;
+      }
+      const double t0 = FR(5);
+      double tc = 1.0;
+      if (timeElapsed < tr) tc = 0.0;
+      else if ((timeElapsed < (tr + t0)) && (timeElapsed >= tr)) tc = (timeElapsed - tr) / t0;
+      mu = fmin(fs + (fd - fs) * tc, mu);
+    }
+    const double pore = FR(6);
+    double effN;
+    if ((T[0] + pore) > 0) effN = 0.0;
+    else effN = T[0] + pore;
+    const double trial = FR(4) - mu * effN;
+    if (T[3] > trial) {
+      T[1] = T[1] * trial / T[3];
+      T[2] = T[2] * trial / T[3];
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double xt = (T[0] * un[j] + T[1] * us[j] + T[2] * ud[j]) * arn;
+      const double x0 = (initT[0] * un[j] + initT[1] * us[j] + initT[2] * ud[j]) * arn;
+      A.force[j * NS + nS] = fS[j] + xt - x0 * Cel;
+      A.force[j * NS + nM] = fM[j] - xt + x0 * Cel;
+    }
+    FR(78) = T[0]; FR(79) = T[1]; FR(80) = T[2];
+  } else {
+    // ---- solveRSF, faulting.f90:190-327
+    if (A.friclaw == 5) T[0] = T[0] + FR(51);
+    else T[0] = T[0] + FR(6);
+    if (A.insertFaultType > 0 && A.C_elastic == 1) {
+      const double max_norm = -40.0e6, min_norm = -10.0e6;
+      if (T[0] >= min_norm) T[0] = min_norm;
+      else if (T[0] <= max_norm) T[0] = max_norm;
+    }
+    if (T[0] > 0.0) T[0] = 0.0;
+    const double bg[3] = {FR(25), FR(26), FR(27)};
+    for (int j = 0; j < 3; ++j) {
+      slip[j] = slip[j] + bg[j] * timeElapsed;
+      rate[j] = rate[j] + bg[j];
+    }
+    slip[3] = sqrt(slip[1] * slip[1] + slip[2] * slip[2]);
+    rate[3] = sqrt(rate[1] * rate[1] + rate[2] * rate[2]);
+    double v_trial = rate[3];
+    RsfPar r;
+    r.A = FR(9); r.B = FR(10); r.L = FR(11); r.V0 = FR(12); r.f0 = FR(13); r.fw = FR(14); r.Vw = FR(15);
+    const double coh = FR(4);
+    double theta_pc_tmp = f23, theta_pc_dot;
+    // rate_state_normal_stress, faulting.f90:35-52
+    theta_pc_dot = -v_trial / r.L * (f23 - fabs(T[0]));
+    f23 = f23 + theta_pc_dot * dt;
+    FR(24) = theta_pc_dot;
+    double statetmp = f20;
+    double xmu = 0, dxmudv = 0;
+    if (A.friclaw == 3) d_rsf_ageing(v_trial, f20, r, xmu, dxmudv, dt);
+    else d_rsf_slip(v_trial, f20, r, xmu, dxmudv, dt);
+    double taoc_old;
+    if (A.friclaw == 5) taoc_old = coh - xmu * T[0];
+    else taoc_old = xmu * theta_pc_tmp;
+    const double mr = massMaster * massSlave / (massMaster + massSlave);
+    const double T_coeff = arn * dt / mr;
+    double trialT[4] = {0, 0, 0, 0};
+    for (int j = 1; j <= 2; ++j) trialT[j] = T[j] - taoc_old * 0.5 * (rate[j] / rate[3]) + bg[j] / T_coeff;
+    trialT[3] = sqrt(trialT[1] * trialT[1] + trialT[2] * trialT[2]);
+    // NewtonRaphson, faulting.f90:459-516
+    double taoc_new = 0.0;
+    {
+      const double state0 = statetmp, thetaPc0 = theta_pc_tmp;
+      double stateTmp = state0;
+      double thetaPcTmp = 0.0;  // uninitialised local in the reference when friclaw==5 (never read by the solve)
+      for (int iv = 1; iv <= 20; ++iv) {
+        stateTmp = state0;
+        if (A.friclaw == 3) d_rsf_ageing(v_trial, stateTmp, r, xmu, dxmudv, dt);
+        else d_rsf_slip(v_trial, stateTmp, r, xmu, dxmudv, dt);
+        double rsfeq, drsfeqdv;
+        if (A.friclaw < 5) {
+          thetaPcTmp = thetaPc0;
+          const double dot = -v_trial / r.L * (thetaPcTmp - fabs(T[0]));
+          thetaPcTmp = thetaPcTmp + dot * dt;
+          taoc_new = xmu * thetaPcTmp;
+          rsfeq = v_trial + T_coeff * (taoc_new * 0.5 - trialT[3]);
+          drsfeqdv = 1.0 + T_coeff * (dxmudv * thetaPcTmp) * 0.5;
+        } else {
+          taoc_new = coh - xmu * fmin(T[0], 0.0);
+          rsfeq = v_trial + T_coeff * (taoc_new * 0.5 - trialT[3]);
+          drsfeqdv = 1.0 + T_coeff * (-dxmudv * fmin(T[0], 0.0)) * 0.5;
+        }
+        if (fabs(rsfeq / drsfeqdv) < 1.e-14 * fabs(v_trial) && fabs(rsfeq) < 1.e-6 * fabs(v_trial)) break;
+        const double newSliprate = v_trial - rsfeq / drsfeqdv;
+        if (newSliprate <= 0.0) v_trial = v_trial / 2.0;
+        else v_trial = newSliprate;
+      }
+      if (A.TPV == 105 && v_trial < FR(46)) v_trial = FR(46);
+      statetmp = stateTmp;
+      theta_pc_tmp = thetaPcTmp;
+    }
+    f20 = statetmp;
+    f23 = theta_pc_tmp;
+    for (int j = 1; j <= 2; ++j) T[j] = taoc_old * 0.5 * (rate[j] / rate[3]) + taoc_new * 0.5 * (trialT[j] / trialT[3]);
+    FR(78) = T[0]; FR(79) = T[1]; FR(80) = T[2];
+    FR(47) = v_trial;
+    const double tmag = sqrt(T[1] * T[1] + T[2] * T[2]);
+    FR(48) = tmag;
+    if (A.tphist) {
+      A.tphist[((size_t)(nt - 1) * 2) * PS + p] = v_trial;
+      A.tphist[((size_t)(nt - 1) * 2 + 1) * PS + p] = tmag;
+    }
+    double acc[3];
+    acc[0] = -rate[0] / dt - slip[0] / dt / dt;
+    acc[1] = (v_trial * (trialT[1] / trialT[3]) - rate[1]) / dt;
+    acc[2] = (v_trial * (trialT[2] / trialT[3]) - rate[2]) / dt;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double xa = acc[0] * un[j] + acc[1] * us[j] + acc[2] * ud[j];
+      const double xr = fS[j] + fM[j];
+      const double aS = (-xa + xr / massMaster), aM = (xa + xr / massSlave);
+      A.force[j * NS + nS] = aS * mr;
+      A.force[j * NS + nM] = aM * mr;
+      FR(31 + j) = vM[j] + aM * dt;
+      FR(34 + j) = vS[j] + aS * dt;
+    }
+  }
+  if (A.friclaw >= 3) { FR(20) = f20; FR(23) = f23; }
+  // showSourceDynamics, faulting.f90:343-365 (recorded; the host prints)
+  if (fabs(xs0 - A.xsource) < A.tol && fabs(xs2 - A.zsource) < A.tol && A.hypoLog) {
+    double* h = A.hypoLog + 13 * (size_t)(nt - 1);
+    h[0] = timeElapsed; h[1] = FR(78); h[2] = FR(79); h[3] = FR(80); h[4] = FR(23); h[5] = FR(73); h[6] = FR(71);
+    h[7] = FR(72); h[8] = FR(74); h[9] = FR(75); h[10] = FR(76); h[11] = FR(77); h[12] = FR(20);
+  }
+  // storeOnFaultStationQuantSCEC, faulting.f90:518-541
+  const int stn = A.pairStation[p];
+  if (stn >= 0) {
+    double* q = A.onHist + 12 * ((size_t)(nt - 1) + (size_t)A.nstep * stn);
+    q[0] = timeElapsed; q[1] = rate[1]; q[2] = rate[2]; q[3] = FR(20);
+    q[4] = slip[1]; q[5] = slip[2]; q[6] = slip[0];
+    q[7] = T[1]; q[8] = T[2]; q[9] = T[0];
+    q[10] = FR(51) + FR(42); q[11] = FR(52);
+  }
+  // storeRuptureTime, faulting.f90:329-341
+  if (A.fnft[p] > 5000.0)
+    if (rate[3] >= A.slipRateThres) A.fnft[p] = timeElapsed;
+#undef FR
+}
+
+// ----------------------------------------------------------------------------
+// layout conversion helpers (upload / fetch): AoS(k fastest) <-> SoA(element fastest)
+__global__ void k_aos_to_soa(const double* __restrict__ src, int K, int n, const int* __restrict__ dstIdx, int cls,
+                             double* __restrict__ dst, int S, int k0, int nk) {
+  // src(K, n) column-major: src[k + K*e]; element e goes to class slot dstIdx[e] if its class matches
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const int code = dstIdx[e];
+  if ((code & 3) != cls) return;
+  const size_t d = (size_t)(code >> 2);
+  for (int k = 0; k < nk; ++k) dst[(size_t)k * S + d] = src[(size_t)(k0 + k) + (size_t)K * e];
+}
+
+// ----------------------------------------------------------------------------
+// launch wrappers
+static inline int nblk(long n, int b) { return (int)((n + b - 1) / b); }
+
+void launch_advance(StepState* st, double dt, cudaStream_t s) { k_advance<<<1, 1, 0, s>>>(st, dt); }
+
+void launch_node_update(const NodeArgs& A, cudaStream_t s) {
+  if (A.Nn > 0) k_node_update<<<nblk(A.Nn, 256), 256, 0, s>>>(A);
+}
+void launch_assemble_special(const NodeArgs& A, const int* list, int n, cudaStream_t s) {
+  if (n > 0) k_assemble_special<<<nblk(n, 128), 128, 0, s>>>(A, list, n);
+}
+void launch_materialize_accel(const NodeArgs& A, double* out, cudaStream_t s) {
+  if (A.Nn > 0) k_materialize_accel<<<nblk(A.Nn, 128), 128, 0, s>>>(A, out);
+}
+
+template <bool PL, bool Q, bool BODY, bool SPLIT>
+static void launch_reg_chg(const ElemArgs& A, int chg, cudaStream_t s) {
+  const int g = nblk(A.n, 128);
+  if (chg == 2) k_elem_reg<PL, Q, BODY, SPLIT, 2><<<g, 128, 0, s>>>(A);
+  else k_elem_reg<PL, Q, BODY, SPLIT, 1><<<g, 128, 0, s>>>(A);
+}
+template <bool SPLIT>
+static void launch_reg_split(const ElemArgs& A, bool plastic, bool q, bool body, int chg, cudaStream_t s) {
+  // C_Q==1 with C_elastic==0 is rejected by the reference (warning.f90:6-9)
+  if (q) { if (body) launch_reg_chg<false, true, true, SPLIT>(A, chg, s); else launch_reg_chg<false, true, false, SPLIT>(A, chg, s); }
+  else if (plastic) { if (body) launch_reg_chg<true, false, true, SPLIT>(A, chg, s); else launch_reg_chg<true, false, false, SPLIT>(A, chg, s); }
+  else { if (body) launch_reg_chg<false, false, true, SPLIT>(A, chg, s); else launch_reg_chg<false, false, false, SPLIT>(A, chg, s); }
+}
+void launch_elem_reg(const ElemArgs& A, bool split, bool plastic, bool q, bool body, int chg, cudaStream_t s) {
+  if (A.n <= 0) return;
+  if (split) launch_reg_split<true>(A, plastic, q, body, chg, s);
+  else launch_reg_split<false>(A, plastic, q, body, chg, s);
+}
+void launch_elem_pml(const ElemArgs& A, bool body, int chg, cudaStream_t s) {
+  if (A.n <= 0) return;
+  const int g = nblk(A.n, 128);
+  if (body) { if (chg == 2) k_elem_pml<true, 2><<<g, 128, 0, s>>>(A); else k_elem_pml<true, 1><<<g, 128, 0, s>>>(A); }
+  else { if (chg == 2) k_elem_pml<false, 2><<<g, 128, 0, s>>>(A); else k_elem_pml<false, 1><<<g, 128, 0, s>>>(A); }
+}
+void launch_store_offfault(const int* idhist, int n, double* out, const double* vel, const double* disp, int NnS,
+                           const StepState* st, cudaStream_t s) {
+  if (n > 0) k_store_offfault<<<nblk(n + 1, 128), 128, 0, s>>>(idhist, n, out, vel, disp, NnS, st);
+}
+void launch_sample_gm(const int* surf, int nSurf, const double* vel, int NnS, double* out, cudaStream_t s) {
+  if (nSurf > 0) k_sample_gm<<<nblk(nSurf, 128), 128, 0, s>>>(surf, nSurf, vel, NnS, out);
+}
+void launch_sample_src(const double* fric, int PS, int n, double* out, cudaStream_t s) {
+  if (n > 0) k_sample_src<<<nblk(n, 128), 128, 0, s>>>(fric, PS, n, out);
+}
+void launch_pack(const double* src, const uint32_t* idx, int n, double* buf, cudaStream_t s) {
+  if (n > 0) k_pack<<<nblk(n, 256), 256, 0, s>>>(src, idx, n, buf);
+}
+void launch_unpack_add(double* dst, const uint32_t* idx, int n, const double* buf, cudaStream_t s) {
+  if (n > 0) k_unpack_add<<<nblk(n, 256), 256, 0, s>>>(dst, idx, n, buf);
+}
+void launch_thermop(const FaultArgs& A, cudaStream_t s) {
+  if (A.nPairs > 0) k_thermop<<<nblk(A.nPairs, 128), 128, 0, s>>>(A);
+}
+void launch_fault(const FaultArgs& A, cudaStream_t s) {
+  if (A.nPairs > 0) k_fault<<<nblk(A.nPairs, 128), 128, 0, s>>>(A);
+}
+void launch_aos_to_soa(const double* src, int K, int n, const int* dstIdx, int cls, double* dst, int S, int k0, int nk,
+                       cudaStream_t s) {
+  if (n > 0) k_aos_to_soa<<<nblk(n, 256), 256, 0, s>>>(src, K, n, dstIdx, cls, dst, S, k0, nk);
+}
+
+}  // namespace eqd

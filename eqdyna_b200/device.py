@@ -1,0 +1,187 @@
+"""ctypes binding of libeqdyna_b200.so (include/eqdyna_b200.h), the CUDA step
+library.  `Domain` = one sub-domain on one GPU, fed from the globalvar arrays
+of the host (eqdyna_b200.host.View), exactly as the Fortran host would feed it
+through ISO_C_BINDING (eqdyna_b200/csrc/fortran/eqdyna_cuda_iface.f90).
+
+There is no CPU path: if the library is missing or no GPU is visible every
+entry point raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build
+from .host import EqdParams
+
+F_DISP, F_VEL, F_V1, F_FORCE, F_FRIC, F_FNFT, F_PSTRAIN, F_STRESS = 1, 2, 3, 4, 5, 6, 7, 8
+F_ONFAULT_HIST, F_OFFFAULT_HIST, F_HYPO_LOG, F_GM, F_SRC_EVOL, F_TPHIST, F_MASS, F_FNMS, F_ARN = 9, 10, 11, 12, 13, 14, 15, 16, 17
+T_TOTAL, T_NODE, T_ELEM, T_ASSEMBLE, T_HALO, T_FAULT, T_NSLOTS = 0, 1, 2, 3, 4, 5, 8
+
+EXPORTS = [
+    "eqd_create", "eqd_destroy", "eqd_last_error", "eqd_set_mesh", "eqd_set_elem_ops", "eqd_set_nodal",
+    "eqd_set_fault", "eqd_set_halo", "eqd_set_stations", "eqd_get_unique_id", "eqd_set_comm", "eqd_sum_shared",
+    "eqd_run", "eqd_run_group", "eqd_fetch", "eqd_get_counts", "eqd_get_timing", "eqd_set_option",
+]
+
+_lib = None
+
+
+class StepError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("eqdyna_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib():
+    """Load libeqdyna_b200.so (built in-tree by eqdyna_b200.build).  Raises if absent."""
+    global _lib
+    if _lib is None:
+        path = build.cuda_lib_path()
+        if not os.path.exists(path):
+            raise RuntimeError("libeqdyna_b200.so is not built (python -m eqdyna_b200.build cuda); there is no CPU fallback")
+        L = C.CDLL(path)
+        vp, i32, i64, cp = C.c_void_p, C.c_int32, C.c_int64, C.c_char_p
+        L.eqd_create.argtypes = [C.POINTER(EqdParams), C.c_int, C.POINTER(vp)]
+        L.eqd_destroy.argtypes = [vp]
+        L.eqd_last_error.argtypes = [vp, cp, C.c_int]
+        L.eqd_set_mesh.argtypes = [vp, i32, i32, i32, i32] + [vp] * 7 + [i32]
+        L.eqd_set_elem_ops.argtypes = [vp] + [vp] * 9
+        L.eqd_set_nodal.argtypes = [vp] + [vp] * 6
+        L.eqd_set_fault.argtypes = [vp, i32] + [vp] * 8
+        L.eqd_set_halo.argtypes = [vp] + [vp] * 9
+        L.eqd_set_stations.argtypes = [vp, vp, i32, vp, i32, vp, i32]
+        L.eqd_get_unique_id.argtypes = [vp]
+        L.eqd_set_comm.argtypes = [vp, vp, i32, i32]
+        L.eqd_sum_shared.argtypes = [vp]
+        L.eqd_run.argtypes = [vp, i32, i32]
+        L.eqd_run_group.argtypes = [C.POINTER(vp), i32, i32, i32]
+        L.eqd_fetch.argtypes = [vp, i32, vp, i64]
+        L.eqd_get_counts.argtypes = [vp] + [C.POINTER(i64)] * 4
+        L.eqd_get_timing.argtypes = [vp, C.POINTER(C.c_double)]
+        L.eqd_set_option.argtypes = [vp, cp, i32]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    return C.c_void_p(a.ctypes.data)
+
+
+def unique_id():
+    buf = (C.c_char * 128)()
+    rc = lib().eqd_get_unique_id(buf)
+    if rc:
+        raise StepError(rc, "eqd_get_unique_id failed (NCCL not loadable?)")
+    return bytes(buf)
+
+
+class Domain:
+    """One sub-domain of a case on one GPU."""
+
+    def __init__(self, view, device=0):
+        self.view = view
+        self._h = C.c_void_p()
+        p = EqdParams.from_buffer_copy(view.params)
+        rc = lib().eqd_create(C.byref(p), int(device), C.byref(self._h))
+        if rc:
+            raise StepError(rc, "eqd_create failed (no CUDA device? see stderr)")
+        self._keep = []
+        self._upload(view)
+
+    def _check(self, rc):
+        if rc:
+            buf = C.create_string_buffer(1024)
+            lib().eqd_last_error(self._h, buf, 1024)
+            raise StepError(rc, buf.value.decode(errors="replace"))
+
+    def _upload(self, v):
+        L = lib()
+        r = v.raw
+        self._check(L.eqd_set_mesh(self._h, r.Nn, r.Ne, r.Neq, r.sizeEq, _ptr(v.meshCoor), _ptr(v.nodeElemIdRelation),
+                                   _ptr(v.elemTypeArr), _ptr(v.numOfDofPerNodeArr), _ptr(v.eqNumStartIndexLoc),
+                                   _ptr(v.eqNumIndexArr), _ptr(v.stressCompIndexArr), r.sizeStress))
+        self._check(L.eqd_set_elem_ops(self._h, _ptr(v.eleshp), _ptr(v.eledet), _ptr(v.elemass), _ptr(v.mat), _ptr(v.ss),
+                                       _ptr(v.phi), _ptr(v.eleporep), _ptr(v.stressArr), _ptr(v.pstrain)))
+        self._check(L.eqd_set_nodal(self._h, _ptr(v.nodalMassArr), _ptr(v.fnms), _ptr(v.v1), _ptr(v.velArr),
+                                    _ptr(v.dispArr), _ptr(v.nodalForceArr)))
+        if int(np.sum(v.nftnd)) > 0:
+            self._check(L.eqd_set_fault(self._h, r.nftmx, _ptr(v.nftnd), _ptr(v.nsmp), _ptr(v.un), _ptr(v.us), _ptr(v.ud),
+                                        _ptr(v.arn), _ptr(v.fric), _ptr(v.fnft)))
+        fl = [(_ptr(a) if a is not None and a.size else None) for a in v.fltface]
+        self._check(L.eqd_set_halo(self._h, _ptr(v.numcount), _ptr(v.fltnum), _ptr(v.fltMPI), *fl))
+        self._check(L.eqd_set_stations(self._h, _ptr(v.idhist) if r.nOff else None, r.nOff,
+                                       _ptr(v.anonfs) if r.nOn else None, r.nOn,
+                                       _ptr(v.surfaceNodeIdArr) if r.nSurf else None, r.nSurf))
+
+    # -- multi-process plumbing
+    def set_comm(self, id128, nranks, rank):
+        self._check(lib().eqd_set_comm(self._h, C.c_char_p(id128), nranks, rank))
+
+    def sum_shared(self):
+        self._check(lib().eqd_sum_shared(self._h))
+
+    def set_option(self, key, value):
+        self._check(lib().eqd_set_option(self._h, key.encode(), int(value)))
+
+    def run(self, nt_begin, nt_end):
+        self._check(lib().eqd_run(self._h, int(nt_begin), int(nt_end)))
+
+    def counts(self):
+        a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        lib().eqd_get_counts(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+        return {"regular": a.value, "pml": b.value, "pairs": c.value, "launches": d.value}
+
+    def timing(self):
+        t = (C.c_double * T_NSLOTS)()
+        lib().eqd_get_timing(self._h, t)
+        return {"total": t[T_TOTAL], "node": t[T_NODE], "elem": t[T_ELEM], "assemble": t[T_ASSEMBLE],
+                "halo": t[T_HALO], "fault": t[T_FAULT]}
+
+    def fetch(self, which, shape, dtype=np.float64):
+        out = np.zeros(shape, dtype=dtype, order="F")
+        self._check(lib().eqd_fetch(self._h, which, _ptr(out), out.nbytes))
+        return out
+
+    def fetch_into_view(self):
+        """Copy the post-run state back into the host arrays (what the Fortran
+        host's output routines read, eqdyna3d.f90:75-79)."""
+        v = self.view
+        r = v.raw
+        v.dispArr[...] = self.fetch(F_DISP, (3, r.Nn))
+        v.velArr[...] = self.fetch(F_VEL, (3, r.Nn))
+        v.v1[...] = self.fetch(F_V1, (r.Neq,))
+        v.nodalForceArr[...] = self.fetch(F_FORCE, (r.Neq,))
+        v.stressArr[...] = self.fetch(F_STRESS, (r.sizeStress,))
+        if v.params.C_elastic == 0:
+            v.pstrain[...] = self.fetch(F_PSTRAIN, (r.Ne,))
+        if int(np.sum(v.nftnd)) > 0:
+            v.fric[...] = self.fetch(F_FRIC, (100, r.nftmx, r.ntotft))
+            v.fnft[...] = self.fetch(F_FNFT, (r.nftmx, r.ntotft))
+            v.onFaultQuantHistSCECForm[...] = self.fetch(F_ONFAULT_HIST, (12, r.nstep, r.nOnAlloc))
+            v.hypoLog[...] = self.fetch(F_HYPO_LOG, (13, r.nstep))
+            if v.onFaultTPHist is not None and v.params.friclaw == 5:
+                v.onFaultTPHist[...] = self.fetch(F_TPHIST, (2, r.nftmx, r.nstep, r.ntotft))
+        if r.nOff:
+            v.OffFaultStGramSCEC[...] = self.fetch(F_OFFFAULT_HIST, (6 * r.nOff + 1, r.nstep))
+
+    def close(self):
+        if self._h:
+            lib().eqd_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def run_group(domains, nt_begin, nt_end):
+    """Lock-step run of all sub-domains of a decomposition from one process."""
+    arr = (C.c_void_p * len(domains))(*[d._h for d in domains])
+    rc = lib().eqd_run_group(arr, len(domains), int(nt_begin), int(nt_end))
+    if rc:
+        domains[0]._check(rc)

@@ -145,6 +145,11 @@ int eqd_sum_shared(eqd_handle* h);
 
 /* -- run steps nt_begin..nt_end inclusive (1-based like `do nt = 1, nstep`) - */
 int eqd_run(eqd_handle* h, int32_t nt_begin, int32_t nt_end);
+/* Several sub-domains driven by ONE process (handles ordered by rank id, all
+ * npx*npy*npz of them; one device or one device each): lock-step steps with
+ * device-to-device halo copies instead of NCCL.  The host must have summed the
+ * shared mass / fnms / arn itself (as the in-process stand-in host does).     */
+int eqd_run_group(eqd_handle** hs, int32_t n, int32_t nt_begin, int32_t nt_end);
 int eqd_fetch(eqd_handle* h, int32_t which, void* dst, int64_t dst_bytes);
 /* algorithmic counters for the benchmark: elements by type, kernel launches */
 int eqd_get_counts(const eqd_handle* h, int64_t* n_regular, int64_t* n_pml,

@@ -1,0 +1,138 @@
+"""Shared parity helpers: run one case through the CUDA step library and
+through the CPU oracle from the same initial state and compare.
+
+Tolerances (BASELINE.json north_star): fault slip-rate / shear-stress series and
+station velocity seismograms within 1e-6 relative L2; rupture time within one dt.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+CASES = os.path.join(ROOT, "tests", "golden", "cases")
+REF_RESULTS = os.path.join(ROOT, "tests", "golden", "ref_results")
+
+REL_L2_TOL = 1.0e-6
+
+
+def rel_l2(a, b):
+    a = np.asarray(a, dtype=np.float64).ravel()
+    b = np.asarray(b, dtype=np.float64).ravel()
+    den = np.sqrt(np.sum(b * b))
+    num = np.sqrt(np.sum((a - b) ** 2))
+    if den == 0.0:
+        return 0.0 if num == 0.0 else float("inf")
+    return float(num / den)
+
+
+def build_world(case, np_xyz=None, nstep=0):
+    from eqdyna_b200.host import World
+    return World(os.path.join(CASES, case), np_xyz=np_xyz, nstep=nstep).build()
+
+
+def run_oracle(world, nstep=None, threads=None):
+    import oracle
+    n = world.view(0).nstep if nstep is None else nstep
+    oracle.run(world, 1, n, threads=threads)
+    return world
+
+
+def run_gpu(world, nstep=None, device=0, chunks=1, options=None):
+    """Step every sub-domain of `world` on the GPU and copy the results back into
+    the world's host arrays.  Returns the Domain list (caller may read timing)."""
+    from eqdyna_b200 import device as dev
+    n = world.view(0).nstep if nstep is None else nstep
+    doms = [dev.Domain(world.view(r), device=device) for r in range(world.size)]
+    for d in doms:
+        for k, v in (options or {}).items():
+            d.set_option(k, v)
+    bounds = np.linspace(0, n, chunks + 1).astype(int)
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        if b <= a:
+            continue
+        if world.size == 1:
+            doms[0].run(a + 1, b)
+        else:
+            dev.run_group(doms, a + 1, b)
+    for d in doms:
+        d.fetch_into_view()
+    return doms
+
+
+def compare_worlds(wg, wo, nstep=None, verbose=False):
+    """Compare GPU-run world `wg` against oracle-run world `wo`.  Returns a dict of
+    error measures; raises AssertionError with a readable message on violation."""
+    res = {}
+    worst = {}
+
+    def upd(key, val):
+        worst[key] = max(worst.get(key, 0.0), val)
+
+    for r in range(wg.size):
+        g, o = wg.view(r), wo.view(r)
+        n = g.nstep if nstep is None else nstep
+        dt = g.params.dt
+        # integer mesh arrays are inputs here (same host), nothing to compare.
+        upd("disp", rel_l2(g.dispArr, o.dispArr))
+        upd("vel", rel_l2(g.velArr, o.velArr))
+        upd("v1", rel_l2(g.v1, o.v1))
+        upd("accel", rel_l2(g.nodalForceArr, o.nodalForceArr))
+        used = g.raw.stressUsed
+        upd("stress", rel_l2(g.stressArr[:used], o.stressArr[:used]))
+        if g.params.C_elastic == 0:
+            upd("pstrain", rel_l2(g.pstrain, o.pstrain))
+        npairs = int(np.sum(g.nftnd))
+        if npairs:
+            for ift in range(g.ntotft):
+                k = int(g.nftnd[ift])
+                if not k:
+                    continue
+                fg, fo = g.fric[:, :k, ift], o.fric[:, :k, ift]
+                for name, sl in (("slip", slice(70, 73)), ("sliprate", slice(73, 75)), ("peakrate", slice(75, 76)),
+                                 ("cumslip", slice(76, 77)), ("traction", slice(77, 80)), ("state", slice(19, 20)),
+                                 ("vms", slice(30, 36)), ("finalrate", slice(46, 48))):
+                    upd("fric." + name, rel_l2(fg[sl], fo[sl]))
+                tg, to = g.fnft[:k, ift], o.fnft[:k, ift]
+                both = (tg < 5000.0) & (to < 5000.0)
+                upd("rupt_mismatch", float(np.sum((tg < 5000.0) != (to < 5000.0))))
+                if both.any():
+                    upd("rupt_time_steps", float(np.max(np.abs(tg[both] - to[both])) / dt))
+            if g.nOn:
+                hg = g.onFaultQuantHistSCECForm[:, :n, :g.nOn]
+                ho = o.onFaultQuantHistSCECForm[:, :n, :g.nOn]
+                for s in range(g.nOn):
+                    upd("onfault.sliprate", rel_l2(hg[1:3, :, s], ho[1:3, :, s]))
+                    upd("onfault.shear", rel_l2(hg[7:9, :, s], ho[7:9, :, s]))
+                    upd("onfault.normal", rel_l2(hg[9, :, s], ho[9, :, s]))
+                    upd("onfault.slip", rel_l2(hg[4:7, :, s], ho[4:7, :, s]))
+            upd("hypolog", rel_l2(g.hypoLog[:, :n], o.hypoLog[:, :n]))
+        if g.nOff:
+            sg = g.OffFaultStGramSCEC[:, :n]
+            so = o.OffFaultStGramSCEC[:, :n]
+            for st in range(g.nOff):
+                rows = 1 + 6 * st + np.arange(6)
+                upd("station.vel", rel_l2(sg[rows[1::2]], so[rows[1::2]]))
+                upd("station.disp", rel_l2(sg[rows[0::2]], so[rows[0::2]]))
+    res.update(worst)
+    if verbose:
+        for k in sorted(res):
+            print("  %-20s %.3e" % (k, res[k]))
+    return res
+
+
+def assert_parity(res, tol=REL_L2_TOL):
+    bad = []
+    for k, v in res.items():
+        if k == "rupt_time_steps":
+            if v > 1.0 + 1e-9:
+                bad.append((k, v))
+        elif k == "rupt_mismatch":
+            if v > 0:
+                bad.append((k, v))
+        elif not (v <= tol):
+            bad.append((k, v))
+    assert not bad, "parity violated: " + ", ".join("%s=%.3e" % kv for kv in bad)
