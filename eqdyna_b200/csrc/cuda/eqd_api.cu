@@ -429,6 +429,9 @@ void finalize(eqd_handle* h) {
   st[0].timeElapsed = 0.0; st[0].nt = 0; st[0].nanFlag = 0; st[0].nanNode = 0; st[0].pad = 0;
   h->dState.upload(st);
   h->hostNt = 0; h->hostTime = 0.0;
+  // cudaMemset / cudaMemcpy above ran on the legacy stream, which does not order
+  // against the non-blocking step stream
+  CK(cudaDeviceSynchronize());
   h->finalized = true;
 }
 
@@ -589,7 +592,10 @@ int eqd_create(const eqd_params* p, int device, eqd_handle** out) {
     need(p->dt > 0 && p->npx > 0 && p->npy > 0 && p->npz > 0, "eqd_create: bad dt / decomposition");
     need(!(p->C_elastic == 0 && p->C_Q == 1), "Q model can only work with elastic code (warning.f90:6-9)");
     need(p->C_hg == 1 || p->C_hg == 2, "eqd_create: C_hg must be 1 or 2");
-    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    // A *blocking* stream on purpose: the setup path uses plain cudaMemcpy /
+    // cudaMemset on the legacy stream (a pageable H2D copy may return before its
+    // DMA has landed), and a blocking stream is ordered after those.
+    CK(cudaStreamCreate(&h->stream));
     h->body = (p->C_elastic == 0) || (p->rdampm != 0.0);
     h->plastic = p->C_elastic == 0;
     h->qmode = p->C_Q == 1;
