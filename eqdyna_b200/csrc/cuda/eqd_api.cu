@@ -495,11 +495,19 @@ void step_pre(eqd_handle* h) {
     t.stop();
   }
   if (h->dAccel0.p) { CK(cudaStreamSynchronize(s)); h->dAccel0.release(); }
-  {
+  if (h->cls[CLS_REG].n) {
     Timer t(h, EQD_T_ELEM);
-    if (h->cls[CLS_REG].n) { launch_elem_reg(h->elemArgs(CLS_REG), false, h->plastic, h->qmode, h->body, P.C_hg, s); h->launches++; }
-    if (h->cls[CLS_REGX].n) { launch_elem_reg(h->elemArgs(CLS_REGX), true, h->plastic, h->qmode, h->body, P.C_hg, s); h->launches++; }
-    if (h->cls[CLS_PML].n) { launch_elem_pml(h->elemArgs(CLS_PML), h->body, P.C_hg, s); h->launches++; }
+    launch_elem_reg(h->elemArgs(CLS_REG), false, h->plastic, h->qmode, h->body, P.C_hg, s); h->launches++;
+    t.stop();
+  }
+  if (h->cls[CLS_REGX].n) {
+    Timer t(h, EQD_T_ELEM_REGX);
+    launch_elem_reg(h->elemArgs(CLS_REGX), true, h->plastic, h->qmode, h->body, P.C_hg, s); h->launches++;
+    t.stop();
+  }
+  if (h->cls[CLS_PML].n) {
+    Timer t(h, EQD_T_ELEM_PML);
+    launch_elem_pml(h->elemArgs(CLS_PML), h->body, P.C_hg, s); h->launches++;
     t.stop();
   }
   {

@@ -90,8 +90,8 @@ enum {
 /* timing slots of eqd_get_timing (ms, CUDA events) -- the reference's
  * compTimeInSeconds(3..6)+MPICommTimeInSeconds (library_output.f90:208-218) */
 enum {
-  EQD_T_TOTAL = 0, EQD_T_NODE = 1, EQD_T_ELEM = 2, EQD_T_ASSEMBLE = 3,
-  EQD_T_HALO = 4, EQD_T_FAULT = 5, EQD_T_NSLOTS = 8
+  EQD_T_TOTAL = 0, EQD_T_NODE = 1, EQD_T_ELEM = 2 /* regular hex/wedge kernel */, EQD_T_ASSEMBLE = 3,
+  EQD_T_HALO = 4, EQD_T_FAULT = 5, EQD_T_ELEM_PML = 6, EQD_T_ELEM_REGX = 7, EQD_T_NSLOTS = 8
 };
 
 /* -- lifecycle ------------------------------------------------------------- */
@@ -155,7 +155,9 @@ int eqd_fetch(eqd_handle* h, int32_t which, void* dst, int64_t dst_bytes);
 int eqd_get_counts(const eqd_handle* h, int64_t* n_regular, int64_t* n_pml,
                    int64_t* n_pairs, int64_t* launches);
 int eqd_get_timing(const eqd_handle* h, double* ms_slots /*[EQD_T_NSLOTS]*/);
-/* options: key in {"graph","overlap","timing","block"}; see DESIGN.md          */
+/* options: "timing" 1 = CUDA-event timing of every phase (2 = also reset the
+ * accumulated slots and the launch counter), "graph", "overlap", "block": see
+ * DESIGN.md                                                                   */
 int eqd_set_option(eqd_handle* h, const char* key, int32_t value);
 
 #ifdef __cplusplus

@@ -105,10 +105,12 @@ def _install_stubs():
     sys.modules["matplotlib.animation"] = anim
 
 
-def gen_case(case, out_root=OUT_ROOT, overrides=None):
-    """Run the reference workflow for `case`; `overrides` is an optional
-    python snippet appended to user_defined_params.py BEFORE `par` is used
-    (not used for the committed fixtures)."""
+def gen_case(case, out_root=OUT_ROOT, subst=None, out_name=None, gz=False):
+    """Run the reference workflow for `case`.  `subst` is an optional list of
+    (old, new) text replacements applied to the scratch copy of
+    user_defined_params.py (used for the benchmark-resolution variants, e.g.
+    TPV104 at dx = 100 m: README.md:87 / misc/model_path_initial.m:5-8);
+    `out_name` names the fixture directory; gz compresses the on-fault dump."""
     _install_stubs()
     work = tempfile.mkdtemp(prefix="eqd_case_")
     try:
@@ -117,6 +119,14 @@ def gen_case(case, out_root=OUT_ROOT, overrides=None):
         for f in ("defaultParameters.py", "lib.py", "case.setup",
                   "generateFaultInterface"):
             shutil.copy(os.path.join(REF, "scripts", f), work)
+        if subst:
+            up = os.path.join(work, "user_defined_params.py")
+            txt = open(up).read()
+            for old, new in subst:
+                if old not in txt:
+                    raise RuntimeError("substitution source %r not found in %s" % (old, case))
+                txt = txt.replace(old, new)
+            open(up, "w").write(txt)
         cwd = os.getcwd()
         os.chdir(work)
         sys.path.insert(0, work)
@@ -137,7 +147,7 @@ def gen_case(case, out_root=OUT_ROOT, overrides=None):
         finally:
             os.chdir(cwd)
             sys.path.remove(work)
-        out = os.path.join(out_root, case)
+        out = os.path.join(out_root, out_name or case)
         os.makedirs(out, exist_ok=True)
         names = ["bGlobal.txt", "bModelGeometry.txt", "bFaultGeometry.txt",
                  "bMaterial.txt", "bStations.txt"]
@@ -146,7 +156,9 @@ def gen_case(case, out_root=OUT_ROOT, overrides=None):
         for n in names:
             shutil.copy(os.path.join(work, n), os.path.join(out, n))
         nfz, nfx = fields["sw_fs"].shape
-        with open(os.path.join(out, "on_fault_vars_input.bin"), "wb") as f:
+        import gzip
+        opener = (lambda p: gzip.open(p + ".gz", "wb", compresslevel=9)) if gz else (lambda p: open(p, "wb"))
+        with opener(os.path.join(out, "on_fault_vars_input.bin")) as f:
             f.write(b"EQDOFV1\0")
             f.write(struct.pack("<iii", nfx, nfz, len(NC_NAMES)))
             f.write(struct.pack("<i", 0))
@@ -159,8 +171,22 @@ def gen_case(case, out_root=OUT_ROOT, overrides=None):
         shutil.rmtree(work, ignore_errors=True)
 
 
+# benchmark-resolution variants (BASELINE.json configs)
+VARIANTS = {
+    "bench.tpv104_100m": ("test.tpv104", [("par.term = 5.", "par.term = 15."), ("par.dx = 500.", "par.dx = 100."),
+                                          ("par.dt = 0.5*par.dx/par.vp", "par.dt = 0.008")]),
+    "bench.tpv104_200m": ("test.tpv104", [("par.term = 5.", "par.term = 15."), ("par.dx = 500.", "par.dx = 200."),
+                                          ("par.dt = 0.5*par.dx/par.vp", "par.dt = 0.016")]),
+}
+
 if __name__ == "__main__":
     cases = sys.argv[1:] or CASES
+    for c in list(cases):
+        if c in VARIANTS:
+            base, subst = VARIANTS[c]
+            par = gen_case(base, subst=subst, out_name=c, gz=True)
+            print("fixture written:", c, "nfx,nfz =", par.nfx, par.nfz, "dx =", par.dx, "dt =", par.dt, "term =", par.term)
+            cases.remove(c)
     for c in cases:
         par = gen_case(c)
         print("fixture written:", c, "nfx,nfz =", par.nfx, par.nfz,
