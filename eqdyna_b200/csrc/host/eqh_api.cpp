@@ -49,6 +49,22 @@ int eqh_world_create(const char* case_dir, int npx, int npy, int npz, int nstep,
   });
 }
 
+// The reference's compile-time switches (globalvar.f90:16,59-77) are plain
+// initialisers there; a host build with other values is emulated by setting
+// them before eqh_get_view.
+int eqh_world_set_switch(eqh_world* w, const char* name, double value) {
+  return guarded([&] {
+    std::string n = name ? name : "";
+    if (n == "C_Q") w->in.C_Q = (int)value;
+    else if (n == "C_hg") w->in.C_hg = (int)value;
+    else if (n == "kapa_hg") w->in.kapa_hg = value;
+    else if (n == "rdampm") w->in.rdampm = value;
+    else if (n == "outputGroundMotion") w->in.outputGroundMotion = (int)value;
+    else throw std::runtime_error("eqh_world_set_switch: unknown switch " + n);
+    if (w->in.C_elastic == 0 && w->in.C_Q == 1) throw std::runtime_error("Q model can only work with elastic code (stop 1001)");
+  });
+}
+
 int eqh_world_destroy(eqh_world* w) {
   delete w;
   return 0;

@@ -70,6 +70,7 @@ def lib():
         L.eqh_last_error.restype = C.c_char_p
         L.eqh_world_create.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.eqh_world_destroy.argtypes = [C.c_void_p]
+        L.eqh_world_set_switch.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
         L.eqh_world_size.argtypes = [C.c_void_p]
         L.eqh_world_build.argtypes = [C.c_void_p, C.c_int]
         L.eqh_world_sum_shared.argtypes = [C.c_void_p]
@@ -164,6 +165,13 @@ class World:
             raise RuntimeError("eqh_world_build: " + lib().eqh_last_error().decode())
         if rank < 0 and sum_shared:
             self.sum_shared()
+        return self
+
+    def set_switch(self, name, value):
+        """Emulate another setting of a compile-time switch of globalvar.f90 (C_Q, C_hg, ...)."""
+        rc = lib().eqh_world_set_switch(self._h, name.encode(), float(value))
+        if rc:
+            raise RuntimeError("eqh_world_set_switch: " + lib().eqh_last_error().decode())
         return self
 
     def sum_shared(self):

@@ -78,6 +78,9 @@ typedef struct eqh_view {
  * the number of time steps (term/dt).                                          */
 int eqh_world_create(const char* case_dir, int npx, int npy, int npz, int nstep, eqh_world** out);
 int eqh_world_destroy(eqh_world* w);
+/* emulate a host built with other compile-time switches of globalvar.f90:
+ * "C_Q", "C_hg", "kapa_hg", "rdampm", "outputGroundMotion"                    */
+int eqh_world_set_switch(eqh_world* w, const char* name, double value);
 const char* eqh_last_error(void);
 int eqh_world_size(const eqh_world* w);
 /* Build sub-domain `rank` (mesh4num, meshgen, on-fault load, mass/operators,

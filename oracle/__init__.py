@@ -47,3 +47,37 @@ def run(world, nt_begin, nt_end, time_elapsed=0.0, ranks=None, threads=None):
     if rc:
         raise RuntimeError("oracle run failed with code %d" % rc)
     return t.value
+
+
+class RankStepper:
+    """One sub-domain stepped by this process; the caller moves the face buffers
+    (tests/test_multiproc_gloo.py does it over torch.distributed/gloo)."""
+
+    def __init__(self, world, rank):
+        self.v = world.raw_view(rank)
+        self.t = C.c_double(0.0)
+        self.L = lib()
+        self.L.orc_face_pack.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        self.L.orc_face_add.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        self.L.orc_step_pre.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+        self.L.orc_step_post.argtypes = [C.c_void_p, C.c_int, C.c_double]
+
+    def pre(self, nt):
+        rc = self.L.orc_step_pre(C.byref(self.v), nt, C.byref(self.t))
+        if rc:
+            raise RuntimeError("orc_step_pre failed: %d" % rc)
+
+    def pack(self, axis, side):
+        import numpy as np
+        n = self.L.orc_face_pack(C.byref(self.v), axis, side, None)
+        buf = np.zeros(n)
+        self.L.orc_face_pack(C.byref(self.v), axis, side, buf.ctypes.data)
+        return buf
+
+    def add(self, axis, side, buf):
+        rc = self.L.orc_face_add(C.byref(self.v), axis, side, buf.ctypes.data, int(buf.size))
+        if rc:
+            raise RuntimeError("orc_face_add: face size mismatch")
+
+    def post(self, nt):
+        self.L.orc_step_post(C.byref(self.v), nt, self.t)

@@ -896,4 +896,45 @@ int orc_run(eqh_view* views, int nranks, int nt_begin, int nt_end, double* time_
   return 0;
 }
 
+// ---- phase-split entry points for a one-sub-domain-per-process host (tests of
+// the N>1 host logic over torch.distributed/gloo): the same step, with the
+// MPI4NodalQuant exchange left to the caller.
+int orc_step_pre(eqh_view* v, int nt, double* time_elapsed) {
+  Ctx c{v, nt, *time_elapsed + v->params.dt};
+  int rc = vel_disp_update(c);
+  if (rc) return rc;
+  store_off_fault(c);
+  std::memset(v->nodalForceArr, 0, sizeof(double) * (size_t)v->Neq);
+  assemble_global_ku(c);
+  hrglss(c);
+  *time_elapsed = c.timeElapsed;
+  return 0;
+}
+
+// number of doubles on face (axis a, side 0/1); buf != NULL: pack them in
+// processNodalQuantArr order (assembleGlobalMass.f90:141-188)
+int orc_face_pack(eqh_view* v, int a, int side, double* buf) {
+  std::vector<double*> slots;
+  face_slots(*v, a, side, slots);
+  if (buf)
+    for (size_t k = 0; k < slots.size(); ++k) buf[k] = *slots[k];
+  return (int)slots.size();
+}
+
+int orc_face_add(eqh_view* v, int a, int side, const double* buf, int n) {
+  std::vector<double*> slots;
+  face_slots(*v, a, side, slots);
+  if ((int)slots.size() != n) return EQD_ERR_ARG;
+  for (int k = 0; k < n; ++k) *slots[k] = *slots[k] + buf[k];
+  return 0;
+}
+
+int orc_step_post(eqh_view* v, int nt, double time_elapsed) {
+  Ctx c{v, nt, time_elapsed};
+  if (v->params.friclaw == 5) thermop(c);
+  faulting(c);
+  for (int k = 0; k < v->Neq; ++k) v->nodalForceArr[k] = v->nodalForceArr[k] / v->nodalMassArr[k];
+  return 0;
+}
+
 }  // extern "C"
