@@ -543,7 +543,7 @@ void step_post(eqd_handle* h) {
   }
   h->hostNt++;
   h->hostTime = h->hostTime + P.dt;
-  if (P.outputGroundMotion && h->hostNt % 10 == 0) {  // driver.f90:30-33
+  if (P.outputGroundMotion && h->hostNt % 10 == 1) {  // driver.f90:30-33: mod(nt,10) == 1
     if (h->dGm.p) { launch_sample_gm(h->dSurf.p, h->nSurf, h->dVel.p, h->NnS, h->dGm.p + 3 * (size_t)h->nSurf * h->nGm, s); h->launches++; }
     if (h->dSrc.p) { launch_sample_src(h->dFric.p, h->PS, h->nftnd[0], h->dSrc.p + (size_t)h->nftnd[0] * h->nGm, s); h->launches++; }
     h->nGm++;

@@ -132,3 +132,29 @@ def test_bench_fixture_matches_readme_benchmark():
     g = open(os.path.join(d, "bGlobal.txt")).read().split()
     assert "15.0" in g and "0.008" in g and "104" in g
     assert os.path.getsize(os.path.join(d, "on_fault_vars_input.bin")) == 24 + 24 * 361 * 181 * 8
+
+
+def test_fortran_interface_covers_the_abi():
+    """eqdyna_cuda_iface.f90 binds every function of include/eqdyna_b200.h, and the bind(C)
+    struct lists the fields of eqd_params in the header's order."""
+    f90 = open(os.path.join(ROOT, "eqdyna_b200", "csrc", "fortran", "eqdyna_cuda_iface.f90")).read()
+    bound = sorted(set(re.findall(r"bind\(C,\s*name='(eqd_\w+)'\)", f90)))
+    assert bound == header_functions(os.path.join(ROOT, "include", "eqdyna_b200.h"), "eqd_")
+    hdr = open(os.path.join(ROOT, "include", "eqdyna_b200.h")).read()
+    body = re.sub(r"/\*.*?\*/", "", hdr[hdr.index("typedef struct eqd_params"):hdr.index("} eqd_params;")], flags=re.S)
+    cfields = []
+    for decl in body.split(";"):
+        decl = decl.replace("typedef struct eqd_params {", "").strip()
+        if not decl:
+            continue
+        names = decl.split(None, 1)[1] if decl.split()[0] in ("double", "int32_t") else ""
+        cfields += [re.sub(r"\[.*\]", "", n).strip() for n in names.split(",") if n.strip()]
+    tbody = f90[f90.index("type, bind(C) :: eqd_params"):f90.index("end type eqd_params")]
+    ffields = []
+    for line in tbody.splitlines()[1:]:
+        if "::" in line:
+            ffields += [re.sub(r"\(.*\)", "", n).strip() for n in line.split("::")[1].split(",") if n.strip()]
+    assert [c.lower() for c in cfields] == [f.lower() for f in ffields]
+    # the ctypes mirror used by the tests has the same order too
+    from eqdyna_b200.host import EqdParams
+    assert [n for n, _ in EqdParams._fields_] == cfields
