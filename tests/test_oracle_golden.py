@@ -68,6 +68,6 @@ def test_oracle_drv_a6_early_time(outdir):
         b = np.loadtxt(os.path.join(out, f))
         np.testing.assert_array_equal(a[:, :3], b[:, :3])           # node coordinates incl. the fractal surface
         early = a[:, 3] < 1.5
-        assert early.sum() > 100
+        assert early.sum() > (100 if f == "frt.txt1" else 0)   # frt.txt1 holds the hypocentre side
         np.testing.assert_allclose(b[early, 3], a[early, 3], atol=1e-6)
     w.close()
