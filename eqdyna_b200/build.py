@@ -21,7 +21,7 @@ LIBDIR = os.path.join(PKG, "lib")
 ORACLE = os.path.join(ROOT, "oracle")
 
 HOST_SRCS = ["eqh_io.cpp", "eqh_mesh.cpp", "eqh_mass.cpp", "eqh_api.cpp"]
-CUDA_SRCS = ["eqd_api.cu", "eqd_kernels.cu"]
+CUDA_SRCS = ["eqd_api.cu", "eqd_kernels.cu", "eqd_tiles.cu"]
 
 # the reference's ubuntu build is -O3 without -march / fast-math: no FMA contraction
 HOST_FLAGS = ["-O2", "-ffp-contract=off", "-fPIC", "-std=c++17", "-Wall", "-Wno-unused-variable"]

@@ -17,6 +17,7 @@
 
 #include "eqd_dev.cuh"
 #include "eqd_kernels.h"
+#include "eqd_tiles.h"
 #include "eqdyna_b200.h"
 
 #ifndef EQD_NCCL_PATH
@@ -104,10 +105,15 @@ Nccl g_nccl;
   } while (0)
 
 struct ElemClass {
-  int n = 0, S = 0, nf = 24, nstress = 6;
-  std::vector<int> refId;  // slot -> reference element (0-based)
-  DevBuf<int> conn;
-  DevBuf<double> shp, phi, ss, lam, mu, det, rho, vp, stress, qmem, porep, pstrain, emass, damps, ef;
+  int n = 0, S = 0, nf = 3, nstress = 6;
+  // tiles (eqd_tiles.h): launch order = rank-face tiles first, then interior
+  int nTiles = 0, nFaceTiles = 0, LS = 1, PFS = 4;
+  std::vector<int> refId;  // [S] slot -> reference element (0-based), -1 = padding
+  std::vector<int> tileNodeH, tnodeH;
+  DevBuf<int> tileOrder, tileElem, tileCnt, tileNode, tnode;
+  DevBuf<uint8_t> tileColours;
+  DevBuf<uint16_t> lconn;
+  DevBuf<double> shp, phi, ss, lam, mu, det, rho, vp, stress, qmem, porep, pstrain, emass, damps, pf;
   DevBuf<uint8_t> qcls;
 };
 
@@ -140,8 +146,8 @@ struct eqd_handle {
   bool body = false, plastic = false, qmode = false;
   // ---- device
   ElemClass cls[3];
-  DevBuf<int> dInfo, dAdjStart, dSpecial;
-  DevBuf<uint32_t> dAdj;
+  DevBuf<int> dInfo, dSlotStart, dSpecial;
+  DevBuf<uint32_t> dSlots;
   DevBuf<double> dVel, dDisp, dMass, dV1p, dDampp, dForce, dAccel0;
   int nSpecial = 0;
   DevBuf<StepState> dState;
@@ -276,10 +282,10 @@ NodeArgs eqd_handle::nodeArgs() const {
   A.Nn = Nn; A.NnS = NnS; A.Np = Np; A.NpS = NpS;
   A.info = dInfo.p; A.vel = dVel.p; A.disp = dDisp.p; A.mass = dMass.p;
   A.v1p = dV1p.p; A.dampp = dDampp.p; A.force = dForce.p;
-  A.adjStart = dAdjStart.p; A.adj = dAdj.p;
-  A.efR = cls[CLS_REG].ef.p; A.SR = cls[CLS_REG].S;
-  A.efX = cls[CLS_REGX].ef.p; A.SX = cls[CLS_REGX].S;
-  A.efP = cls[CLS_PML].ef.p; A.SP = cls[CLS_PML].S;
+  A.slotStart = dSlotStart.p; A.slots = dSlots.p;
+  A.pfR = cls[CLS_REG].pf.p; A.SR = cls[CLS_REG].PFS;
+  A.pfX = cls[CLS_REGX].pf.p; A.SX = cls[CLS_REGX].PFS;
+  A.pfP = cls[CLS_PML].pf.p; A.SP = cls[CLS_PML].PFS;
   A.accel0 = nullptr;
   A.dt = p.dt;
   A.st = dState.p;
@@ -290,11 +296,13 @@ ElemArgs eqd_handle::elemArgs(int c) const {
   const ElemClass& C = cls[c];
   ElemArgs A{};
   A.n = C.n; A.S = C.S;
-  A.conn = C.conn.p; A.shp = C.shp.p; A.phi = C.phi.p; A.ss = C.ss.p;
+  A.tileOrder = C.tileOrder.p; A.tile0 = 0;
+  A.tileElem = C.tileElem.p; A.tileCnt = C.tileCnt.p; A.tileNode = C.tileNode.p; A.tileColours = C.tileColours.p;
+  A.tnode = C.tnode.p; A.lconn = C.lconn.p; A.LS = C.LS; A.pf = C.pf.p; A.PFS = C.PFS;
+  A.shp = C.shp.p; A.phi = C.phi.p; A.ss = C.ss.p;
   A.lam = C.lam.p; A.mu = C.mu.p; A.det = C.det.p; A.rho = C.rho.p; A.vp = C.vp.p;
   A.stress = C.stress.p; A.qmem = C.qmem.p; A.qcls = C.qcls.p;
   A.porep = C.porep.p; A.pstrain = C.pstrain.p; A.emass = C.emass.p; A.damps = C.damps.p;
-  A.ef = C.ef.p;
   A.vel = dVel.p; A.disp = dDisp.p; A.NnS = NnS;
   A.dt = p.dt; A.rdampk = p.rdampk; A.rdampm = p.rdampm; A.w = p.w;
   // assembleGlobalKU.f90:16
@@ -497,17 +505,17 @@ void step_pre(eqd_handle* h) {
   if (h->dAccel0.p) { CK(cudaStreamSynchronize(s)); h->dAccel0.release(); }
   if (h->cls[CLS_REG].n) {
     Timer t(h, EQD_T_ELEM);
-    launch_elem_reg(h->elemArgs(CLS_REG), false, h->plastic, h->qmode, h->body, P.C_hg, s); h->launches++;
+    launch_elem_reg(h->elemArgs(CLS_REG), h->cls[CLS_REG].nTiles, false, h->plastic, h->qmode, h->body, P.C_hg, s); h->launches++;
     t.stop();
   }
   if (h->cls[CLS_REGX].n) {
     Timer t(h, EQD_T_ELEM_REGX);
-    launch_elem_reg(h->elemArgs(CLS_REGX), true, h->plastic, h->qmode, h->body, P.C_hg, s); h->launches++;
+    launch_elem_reg(h->elemArgs(CLS_REGX), h->cls[CLS_REGX].nTiles, true, h->plastic, h->qmode, h->body, P.C_hg, s); h->launches++;
     t.stop();
   }
   if (h->cls[CLS_PML].n) {
     Timer t(h, EQD_T_ELEM_PML);
-    launch_elem_pml(h->elemArgs(CLS_PML), h->body, P.C_hg, s); h->launches++;
+    launch_elem_pml(h->elemArgs(CLS_PML), h->cls[CLS_PML].nTiles, h->body, P.C_hg, s); h->launches++;
     t.stop();
   }
   {
@@ -681,9 +689,8 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
     h->NnS = pad32(Nn);
     h->NpS = pad32(std::max(h->Np, 1));
     need(3 * (double)h->NnS + 12 * (double)h->NpS < 4.0e9, "eqd_set_mesh: sub-domain too large for 32-bit halo offsets");
-    // ---- element classes
-    h->elemCode.assign(Ne, 0);
-    int cnt[3] = {0, 0, 0};
+    // ---- element classes, cut into tiles (eqd_tiles.h)
+    std::vector<int> members[3];
     for (int e = 0; e < Ne; ++e) {
       const int t = h->etype[e];
       int c;
@@ -693,30 +700,37 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
         c = CLS_REG;
         for (int k = 0; k < 8; ++k) if (h->ndof[h->conn[8 * (size_t)e + k]] == 12) c = CLS_REGX;
       }
-      h->elemCode[e] = c | (cnt[c] << 2);
-      cnt[c]++;
+      members[c].push_back(e);
     }
-    for (int c = 0; c < 3; ++c) need(cnt[c] < (1 << 27), "eqd_set_mesh: more than 2^27 elements in one class");
-    const int nf[3] = {24, 48, 96}, nstr[3] = {6, 6, 21};
+    int gny = 0, gnz = 0;
+    const bool gridOk = infer_grid(h->conn.data(), h->etype.data(), Ne, Nn, gny, gnz);
+    h->elemCode.assign(Ne, 0);
+    const int nf[3] = {3, 6, 12}, nstr[3] = {6, 6, 21};
     for (int c = 0; c < 3; ++c) {
       ElemClass& C = h->cls[c];
-      C.n = cnt[c]; C.S = pad32(std::max(cnt[c], 1)); C.nf = nf[c]; C.nstress = nstr[c];
-      C.refId.assign(C.n, 0);
-    }
-    for (int e = 0; e < Ne; ++e) h->cls[h->elemCode[e] & 3].refId[h->elemCode[e] >> 2] = e;
-    for (int c = 0; c < 3; ++c) {
-      ElemClass& C = h->cls[c];
+      TileShape sh;
+      if (c == CLS_PML) { sh.bx = 3; sh.bz = 3; sh.by = 32; sh.capE = 384; sh.capN = 800; }
+      TilePlan T;
+      plan_tiles(h->conn.data(), members[c], Nn, gny, gnz, gridOk, sh, EQD_TILE_THREADS, T);
+      C.n = T.n; C.S = T.S; C.nf = nf[c]; C.nstress = nstr[c];
+      C.nTiles = T.nTiles; C.nFaceTiles = 0; C.LS = T.LS; C.PFS = T.PFS;
+      need((size_t)tile_rows(c, h->qmode) * C.LS * sizeof(double) <= 227 * 1024 - 1024, "eqd_set_mesh: tile does not fit shared memory");
+      C.refId = T.refId;
+      for (int s = 0; s < C.S; ++s) if (C.refId[s] >= 0) h->elemCode[C.refId[s]] = c | (s << 2);
+      C.tileNodeH = T.tileNode; C.tnodeH = T.tnode;
       if (!C.n) continue;
-      std::vector<int> cn(8 * (size_t)C.S, 0);
-      for (int s = 0; s < C.n; ++s)
-        for (int k = 0; k < 8; ++k) cn[(size_t)k * C.S + s] = h->conn[8 * (size_t)C.refId[s] + k];
-      C.conn.upload(cn);
-      C.ef.alloc((size_t)C.nf * C.S);
+      std::vector<int> ord(C.nTiles);
+      for (int t = 0; t < C.nTiles; ++t) ord[t] = t;
+      C.tileOrder.upload(ord);
+      C.tileElem.upload(T.tileElem); C.tileCnt.upload(T.tileCnt); C.tileNode.upload(T.tileNode);
+      C.tileColours.upload(T.tileColours); C.tnode.upload(T.tnode); C.lconn.upload(T.lconn);
+      C.pf.alloc((size_t)C.nf * C.PFS);
       C.stress.alloc((size_t)C.nstress * C.S);
       if (c == CLS_PML) {
         std::vector<double> dm(3 * (size_t)C.S, 0.0);
-        for (int s = 0; s < C.n; ++s) {
+        for (int s = 0; s < C.S; ++s) {
           const int e = C.refId[s];
+          if (e < 0) continue;
           double xc[3] = {0, 0, 0};
           for (int i = 0; i < 3; ++i)
             for (int j = 0; j < 8; ++j) xc[i] = xc[i] + h->coor[i + 3 * (size_t)h->conn[8 * (size_t)e + j]];
@@ -728,8 +742,9 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
         C.damps.upload(dm);
       } else if (h->qmode) {
         std::vector<uint8_t> qc(C.S, 0);
-        for (int s = 0; s < C.n; ++s) {
+        for (int s = 0; s < C.S; ++s) {
           const int e = C.refId[s];
+          if (e < 0) continue;
           double xc[3] = {0, 0, 0};
           for (int i = 0; i < 3; ++i)
             for (int j = 0; j < 8; ++j) xc[i] = xc[i] + h->coor[i + 3 * (size_t)h->conn[8 * (size_t)e + j]];
@@ -747,32 +762,31 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
         C.qmem.alloc(6 * (size_t)C.S);
       }
     }
-    // ---- node -> (element, local node) CSR, ascending reference element id
+    // ---- node -> tile-node slots CSR, by class then ascending tile id
     std::vector<int> start(Nn + 1, 0);
-    for (int e = 0; e < Ne; ++e)
-      for (int k = 0; k < 8; ++k) {
-        const int n = h->conn[8 * (size_t)e + k];
-        if (EQD_INFO_KIND(h->info[n]) != KIND_FIXED) start[n + 1]++;
-      }
+    for (int c = 0; c < 3; ++c)
+      for (int nd : h->cls[c].tnodeH) if (nd >= 0 && EQD_INFO_KIND(h->info[nd]) != KIND_FIXED) start[nd + 1]++;
     for (int n = 0; n < Nn; ++n) {
-      need((long)start[n] + start[n + 1] < 2147483647L, "eqd_set_mesh: adjacency overflow");
+      need((long)start[n] + start[n + 1] < 2147483647L, "eqd_set_mesh: slot table overflow");
       start[n + 1] += start[n];
     }
-    std::vector<uint32_t> adj(start[Nn]);
+    std::vector<uint32_t> slots(start[Nn]);
     {
       std::vector<int> fill(start.begin(), start.end() - 1);
-      for (int e = 0; e < Ne; ++e) {
-        const int c = h->elemCode[e] & 3, s = h->elemCode[e] >> 2;
-        for (int k = 0; k < 8; ++k) {
-          const int n = h->conn[8 * (size_t)e + k];
-          if (EQD_INFO_KIND(h->info[n]) == KIND_FIXED) continue;
-          need(!(c == CLS_REG && EQD_INFO_KIND(h->info[n]) == KIND_PML12), "internal: REG element on a 12-dof node");
-          adj[fill[n]++] = EQD_ADJ(c, k, s);
+      for (int c = 0; c < 3; ++c) {
+        const std::vector<int>& tn = h->cls[c].tnodeH;
+        for (size_t s = 0; s < tn.size(); ++s) {
+          const int nd = tn[s];
+          if (nd < 0) continue;
+          const int kind = EQD_INFO_KIND(h->info[nd]);
+          if (kind == KIND_FIXED) continue;
+          need(!(c == CLS_REG && kind == KIND_PML12), "internal: REG element on a 12-dof node");
+          slots[fill[nd]++] = EQD_SLOT(c, s);
         }
       }
     }
-    h->dAdjStart.upload(start);
-    h->dAdj.upload(adj);
+    h->dSlotStart.upload(start);
+    h->dSlots.upload(slots);
     // ---- PML node damping profile (comdampv, recomputed every step in the reference)
     std::vector<double> dp(3 * (size_t)h->NpS, 0.0);
     for (int n = 0; n < Nn; ++n)
@@ -855,7 +869,8 @@ int eqd_set_elem_ops(eqd_handle* h, const double* eleshp, const double* eledet, 
       if (!C.n) continue;
       std::vector<double> sg((size_t)C.nstress * C.S, 0.0), qm;
       if (h->qmode && c != CLS_PML) qm.assign(6 * (size_t)C.S, 0.0);
-      for (int s = 0; s < C.n; ++s) {
+      for (int s = 0; s < C.S; ++s) {
+        if (C.refId[s] < 0) continue;
         const int base = h->stressIdx[C.refId[s]];
         need(base >= 0 && base + (c == CLS_PML ? 21 : 12) <= h->sizeStress, "eqd_set_elem_ops: stress index out of range");
         for (int k = 0; k < C.nstress; ++k) sg[(size_t)k * C.S + s] = stressArr[base + k];
@@ -1223,7 +1238,7 @@ int eqd_fetch(eqd_handle* h, int32_t which, void* dst, int64_t dst_bytes) {
           ElemClass& C = h->cls[c];
           if (!C.n || !C.pstrain.p) continue;
           std::vector<double> v = C.pstrain.download();
-          for (int s = 0; s < C.n; ++s) out[C.refId[s]] = v[s];
+          for (int s = 0; s < C.S; ++s) if (C.refId[s] >= 0) out[C.refId[s]] = v[s];
         }
         break;
       }
@@ -1234,7 +1249,8 @@ int eqd_fetch(eqd_handle* h, int32_t which, void* dst, int64_t dst_bytes) {
           if (!C.n) continue;
           std::vector<double> sg = C.stress.download(), qm;
           if (C.qmem.p) qm = C.qmem.download();
-          for (int s = 0; s < C.n; ++s) {
+          for (int s = 0; s < C.S; ++s) {
+            if (C.refId[s] < 0) continue;
             const int base = h->stressIdx[C.refId[s]];
             for (int k = 0; k < C.nstress; ++k) out[base + k] = sg[(size_t)k * C.S + s];
             if (!qm.empty()) for (int k = 0; k < 6; ++k) out[base + 6 + k] = qm[(size_t)k * C.S + s];

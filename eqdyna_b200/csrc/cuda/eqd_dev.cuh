@@ -7,12 +7,19 @@
 //   nodes     vel[3][NnS] disp[3][NnS] mass[Nn]            (3-dof nodes: v1 == vel)
 //   PML nodes v1p[12][NpS] dampp[3][NpS]                   (12-dof split field, comdampv precomputed)
 //   elements  three classes, each SoA with the element index fastest:
-//             REG  (types 1,11,12,13 touching only 3-dof nodes)  ef[24]
-//             REGX (regular element touching a 12-dof node)      ef[48] = KU | hourglass
-//             PML  (type 2)                                      ef[96]
-//   assembly  node -> (element, local node) CSR in ascending reference element
-//             id; a node's force is the ordered sum of its elements' `ef`
-//             entries (no atomics => fixed summation order)
+//             REG  (types 1,11,12,13 touching only 3-dof nodes)  3 force rows / node
+//             REGX (regular element touching a 12-dof node)      6 rows = KU | hourglass
+//             PML  (type 2)                                      12 rows
+//   tiles     every class is cut into bricks of ~4x4x32 (PML 3x3x32) elements
+//             stored contiguously; one CTA owns one tile: it stages the tile's
+//             nodes (v, d + rdampk v) in shared memory, sweeps the tile's
+//             elements and accumulates their nodal forces in shared memory in a
+//             FIXED order (8 local-node phases, host-coloured where two elements
+//             of one phase share a node: no atomics), then writes ONE partial
+//             force row per tile node: pf[rows][slot]
+//   assembly  node -> tile-node slots CSR (class, tile ascending); a node's
+//             force is the ordered sum of its 1..8 tile partials, fused into
+//             the next node update
 //   special   nodes whose force is needed between the element sweep and the
 //             next node update (split-node pairs, rank-face halo nodes): their
 //             sums are materialised in force[3][NnS] / forcep[12][NpS]
@@ -26,8 +33,12 @@ enum { CLS_REG = 0, CLS_REGX = 1, CLS_PML = 2 };
 #define EQD_INFO_KIND(i) ((i) & 3)
 #define EQD_INFO_SPECIAL(i) (((i) >> 2) & 1)
 #define EQD_INFO_SLOT(i) ((i) >> 3)
-// adjacency entry: class (2 bits) | local node (3 bits) | element index in class (27 bits)
-#define EQD_ADJ(cls, ln, idx) ((uint32_t)(cls) | ((uint32_t)(ln) << 2) | ((uint32_t)(idx) << 5))
+// node -> tile-node slot entry: class (2 bits) | slot in the class's partial buffer (30 bits)
+#define EQD_SLOT(cls, slot) ((uint32_t)(cls) | ((uint32_t)(slot) << 2))
+// local connectivity entry: tile-local node index (12 bits) | colour of the phase (4 bits)
+#define EQD_LN_BITS 12
+#define EQD_LN_MASK 0x0fffu
+#define EQD_TILE_THREADS 128
 
 struct StepState {
   double timeElapsed;  // driver.f90:11
@@ -46,11 +57,11 @@ struct NodeArgs {
   double* v1p;           // [12][NpS]
   const double* dampp;   // [3][NpS]
   double* force;         // [3][NnS] + [12][NpS] (forcep = force + 3*NnS)
-  const int* adjStart;   // [Nn+1]
-  const uint32_t* adj;
-  const double* efR; int SR;
-  const double* efX; int SX;
-  const double* efP; int SP;
+  const int* slotStart;  // [Nn+1]
+  const uint32_t* slots; // EQD_SLOT entries
+  const double* pfR; int SR;   // [3][SR]  tile partials, REG
+  const double* pfX; int SX;   // [6][SX]  REGX: KU | hourglass
+  const double* pfP; int SP;   // [12][SP] PML
   const double* accel0;  // optional uploaded acceleration, same layout as force; first step only
   double dt;
   StepState* st;
@@ -58,7 +69,16 @@ struct NodeArgs {
 
 struct ElemArgs {
   int n, S;
-  const int* conn;       // [8][S] 0-based node ids
+  // tiles: elements of tile t are slots tileElem[t] .. tileElem[t]+tileCnt[t]-1,
+  // its nodes are tnode[tileNode[t] .. tileNode[t+1]-1] (-1 = padding)
+  const int* tileOrder;  // launch order -> tile id (rank-face tiles first)
+  int tile0;             // first entry of tileOrder this launch covers
+  const int* tileElem; const int* tileCnt; const int* tileNode;
+  const uint8_t* tileColours;  // colours per phase in this tile (1 = conflict free)
+  const int* tnode;
+  const uint16_t* lconn; // [8][S] local node | colour << 12
+  int LS;                // shared-memory row stride (max tile nodes of the class)
+  double* pf; int PFS;   // [3|6|12][PFS] partial nodal forces, one row per tile node
   const double* shp;     // [24][S]  eleshp(3,8,e): row 3*i+j
   const double* phi;     // [32][S]  phi(8,4,e):    row 8*m+i
   const double* ss;      // [6][S]
@@ -70,7 +90,6 @@ struct ElemArgs {
   const double* porep; double* pstrain;  // plastic
   const double* emass;   // [8][S] nodal lumped element mass (body force / Rayleigh mass damping)
   const double* damps;   // [3][S] PML damping profile at the centroid
-  double* ef;            // [24|48|96][S]
   const double* vel; const double* disp; int NnS;
   double dt, rdampk, rdampm, w, bodyz, ccosphi, sinphi, expdttv, kapa_hg;
 };

@@ -1,9 +1,15 @@
 // Hand-written FP64 sm_100a kernels of the EQdyna step loop (src/driver.f90:9-34).
 // Every kernel cites the reference routine it replaces.  One thread per work
 // item (element / node / split-node pair), SoA operands with the work-item
-// index fastest so every warp-wide access is a run of consecutive doubles.
+// index fastest so every warp-wide access is a run of consecutive doubles;
+// element kernels work tile by tile (one CTA = one brick of elements) and
+// assemble nodal forces in shared memory in a fixed order.
 #include <cuda_runtime.h>
 #include <math.h>
+
+#include <mutex>
+#include <set>
+#include <utility>
 
 #include "eqd_dev.cuh"
 #include "eqd_kernels.h"
@@ -24,55 +30,56 @@ __global__ void k_advance(StepState* st, double dt) {
 }
 
 // ----------------------------------------------------------------------------
-// Ordered gather of a node's force from the element-force buffers
-// (replaces the scatter-add of assembleGlobalKU.f90:28-35,47-63 and
-// hrglss.f90:42-54: same contributions, fixed order = ascending element id).
+// Ordered gather of a node's force from the tile partials (replaces the
+// scatter-add of assembleGlobalKU.f90:28-35,47-63 and hrglss.f90:42-54: same
+// contributions; fixed order = 8 local-node phases inside a tile, then the
+// node's tiles by class and ascending tile id).
 __device__ __forceinline__ void gather3(const NodeArgs& A, int n, double f[3]) {
-  const int b = LDG(A.adjStart + n), e = LDG(A.adjStart + n + 1);
+  const int b = LDG(A.slotStart + n), e = LDG(A.slotStart + n + 1);
   f[0] = f[1] = f[2] = 0.0;
   for (int k = b; k < e; ++k) {
-    const uint32_t u = LDG(A.adj + k);
-    const int cls = u & 3, ln = (u >> 2) & 7;
-    const size_t idx = u >> 5;
+    const uint32_t u = LDG(A.slots + k);
+    const int cls = u & 3;
+    const size_t idx = u >> 2;
     if (cls == CLS_REG) {
-      const double* p = A.efR + (size_t)(3 * ln) * A.SR + idx;
-      f[0] += LDG(p); f[1] += LDG(p + A.SR); f[2] += LDG(p + 2 * (size_t)A.SR);
+      const double* p = A.pfR + idx;
+      f[0] += p[0]; f[1] += p[A.SR]; f[2] += p[2 * (size_t)A.SR];
     } else if (cls == CLS_PML) {
       // 3-dof node of a PML element: assembleGlobalKU.f90:55-61
-      const double* p = A.efP + (size_t)(12 * ln) * A.SP + idx;
+      const double* p = A.pfP + idx;
       const size_t S = A.SP;
-      f[0] = f[0] + LDG(p) + LDG(p + S) + LDG(p + 2 * S) + LDG(p + 9 * S);
-      f[1] = f[1] + LDG(p + 3 * S) + LDG(p + 4 * S) + LDG(p + 5 * S) + LDG(p + 10 * S);
-      f[2] = f[2] + LDG(p + 6 * S) + LDG(p + 7 * S) + LDG(p + 8 * S) + LDG(p + 11 * S);
+      f[0] = f[0] + p[0] + p[S] + p[2 * S] + p[9 * S];
+      f[1] = f[1] + p[3 * S] + p[4 * S] + p[5 * S] + p[10 * S];
+      f[2] = f[2] + p[6 * S] + p[7 * S] + p[8 * S] + p[11 * S];
     } else {
-      const double* p = A.efX + (size_t)(3 * ln) * A.SX + idx;
+      const double* p = A.pfX + idx;
       const size_t S = A.SX;
-      f[0] = f[0] + LDG(p) + LDG(p + 24 * S);
-      f[1] = f[1] + LDG(p + S) + LDG(p + 25 * S);
-      f[2] = f[2] + LDG(p + 2 * S) + LDG(p + 26 * S);
+      f[0] = f[0] + p[0] + p[3 * S];
+      f[1] = f[1] + p[S] + p[4 * S];
+      f[2] = f[2] + p[2 * S] + p[5 * S];
     }
   }
 }
 
 __device__ __forceinline__ void gather12(const NodeArgs& A, int n, double f[12]) {
-  const int b = LDG(A.adjStart + n), e = LDG(A.adjStart + n + 1);
+  const int b = LDG(A.slotStart + n), e = LDG(A.slotStart + n + 1);
 #pragma unroll
   for (int j = 0; j < 12; ++j) f[j] = 0.0;
   for (int k = b; k < e; ++k) {
-    const uint32_t u = LDG(A.adj + k);
-    const int cls = u & 3, ln = (u >> 2) & 7;
-    const size_t idx = u >> 5;
+    const uint32_t u = LDG(A.slots + k);
+    const int cls = u & 3;
+    const size_t idx = u >> 2;
     if (cls == CLS_PML) {
-      const double* p = A.efP + (size_t)(12 * ln) * A.SP + idx;
+      const double* p = A.pfP + idx;
 #pragma unroll
-      for (int j = 0; j < 12; ++j) f[j] += LDG(p + (size_t)j * A.SP);
+      for (int j = 0; j < 12; ++j) f[j] += p[(size_t)j * A.SP];
     } else if (cls == CLS_REGX) {
       // regular element on a 12-dof node: KU goes to dofs 1-3
       // (assembleGlobalKU.f90:28-35), hourglass to dofs 10-12 (hrglss.f90:44-48)
-      const double* p = A.efX + (size_t)(3 * ln) * A.SX + idx;
+      const double* p = A.pfX + idx;
       const size_t S = A.SX;
-      f[0] += LDG(p); f[1] += LDG(p + S); f[2] += LDG(p + 2 * S);
-      f[9] += LDG(p + 24 * S); f[10] += LDG(p + 25 * S); f[11] += LDG(p + 26 * S);
+      f[0] += p[0]; f[1] += p[S]; f[2] += p[2 * S];
+      f[9] += p[3 * S]; f[10] += p[4 * S]; f[11] += p[5 * S];
     }
   }
 }
@@ -212,330 +219,466 @@ __global__ void k_materialize_accel(NodeArgs A, double* __restrict__ out) {
 }
 
 // ----------------------------------------------------------------------------
+// Tile kernels.  One CTA owns one tile (a brick of a few hundred elements of one
+// class, contiguous in the class's SoA):
+//   stage    the tile's nodes: v and d + rdampk*v (hrglss.f90:20-27) -> shared
+//   sweep    one thread per element (EQD_TILE_THREADS at a time): operators
+//            stream from HBM straight into registers, nodal values come from
+//            shared memory
+//   assemble 8 local-node phases; in phase i every element adds its force on
+//            local node i to the tile's shared force rows.  Two elements of one
+//            phase never touch the same node in a structured hexahedral brick;
+//            where they do (wedge pairs) the host gave them different colours
+//            and the phase is split.  Plain read-modify-write, no atomics: the
+//            summation order is fixed.
+//   flush    one partial force row per tile node -> pf (coalesced)
+struct TileCtx {
+  int e0, ne, nb, LN, NC;
+};
+__device__ __forceinline__ TileCtx tile_ctx(const ElemArgs& A) {
+  TileCtx T;
+  const int t = LDG(A.tileOrder + A.tile0 + blockIdx.x);
+  T.e0 = LDG(A.tileElem + t);
+  T.ne = LDG(A.tileCnt + t);
+  T.nb = LDG(A.tileNode + t);
+  T.LN = LDG(A.tileNode + t + 1) - T.nb;
+  T.NC = LDG(A.tileColours + t);
+  return T;
+}
+
 // Regular hexahedron / degenerate wedge: calcElemKU.f90:3-191 (+ calcB.f90,
 // calcElemMass.f90) fused with hrglss.f90:13-98.  The 6x24 B matrix is never
-// materialised; two passes over the 8 nodes keep the live state small:
-//   pass 1  gather v,d -> strain rate (strain), hourglass modal amplitudes
-//   pass 2  B^T sigma and the hourglass forces per node -> ef
+// materialised.
 template <bool PLASTIC, bool QMODE, bool BODY, bool SPLIT, int CHG>
-__global__ void __launch_bounds__(128) k_elem_reg(ElemArgs A) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= A.n) return;
+__global__ void __launch_bounds__(EQD_TILE_THREADS, 2) k_tile_reg(ElemArgs A) {
+  extern __shared__ double sm[];
+  constexpr int NT = EQD_TILE_THREADS;
+  constexpr int NF = SPLIT ? 6 : 3;
+  const int tid = threadIdx.x;
+  const TileCtx T = tile_ctx(A);
+  const int LS = A.LS;
   const size_t S = A.S, NS = A.NnS;
   const double dt = A.dt, rdampk = A.rdampk;
-  double sr[6] = {0, 0, 0, 0, 0, 0}, sn[6] = {0, 0, 0, 0, 0, 0};
-  double phid[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-  double qv[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};  // viscous hourglass (C_hg==2)
-  double body[BODY ? 24 : 1];
-  double xc2 = 0.0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int nd = LDG(A.conn + i * S + e);
-    const double vx = LDG(A.vel + nd), vy = LDG(A.vel + NS + nd), vz = LDG(A.vel + 2 * NS + nd);
-    const double dx = LDG(A.disp + nd), dy = LDG(A.disp + NS + nd), dz = LDG(A.disp + 2 * NS + nd);
-    const double s1 = LDG(A.shp + (3 * i) * S + e), s2 = LDG(A.shp + (3 * i + 1) * S + e), s3 = LDG(A.shp + (3 * i + 2) * S + e);
-    // calcElemKU.f90:44-60 (B with engineering shear, calcB.f90:10-25)
-    sr[0] = sr[0] + s1 * vx;
-    sr[1] = sr[1] + s2 * vy;
-    sr[2] = sr[2] + s3 * vz;
-    sr[3] = sr[3] + s3 * vy + s2 * vz;
-    sr[4] = sr[4] + s3 * vx + s1 * vz;
-    sr[5] = sr[5] + s2 * vx + s1 * vy;
-    if (QMODE) {
-      sn[0] = sn[0] + s1 * dx;
-      sn[1] = sn[1] + s2 * dy;
-      sn[2] = sn[2] + s3 * dz;
-      sn[3] = sn[3] + s3 * dy + s2 * dz;
-      sn[4] = sn[4] + s3 * dx + s1 * dz;
-      sn[5] = sn[5] + s2 * dx + s1 * dy;
+  double* sv = sm;                          // [3][LS] velocity
+  double* sl = sm + 3 * LS;                 // [3][LS] d + rdampk*v
+  double* sd = sm + 6 * LS;                 // [3][LS] displacement (Q only)
+  double* sf = sm + (QMODE ? 9 : 6) * LS;   // [NF][LS] force accumulators
+  for (int i = tid; i < T.LN; i += NT) {
+    const int nd = LDG(A.tnode + T.nb + i);
+    double vx = 0, vy = 0, vz = 0, dx = 0, dy = 0, dz = 0;
+    if (nd >= 0) {
+      vx = LDG(A.vel + nd); vy = LDG(A.vel + NS + nd); vz = LDG(A.vel + 2 * NS + nd);
+      dx = LDG(A.disp + nd); dy = LDG(A.disp + NS + nd); dz = LDG(A.disp + 2 * NS + nd);
     }
-    if (CHG == 1) {
-      // hrglss.f90:20-33: dl = d + rdampk*v ; phid = sum_j phi(j,m)*dl(j)
-      const double lx = dx + rdampk * vx, ly = dy + rdampk * vy, lz = dz + rdampk * vz;
+    sv[i] = vx; sv[LS + i] = vy; sv[2 * LS + i] = vz;
+    sl[i] = dx + rdampk * vx; sl[LS + i] = dy + rdampk * vy; sl[2 * LS + i] = dz + rdampk * vz;
+    if (QMODE) { sd[i] = dx; sd[LS + i] = dy; sd[2 * LS + i] = dz; }
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const double p = LDG(A.phi + (8 * m + i) * S + e);
-        phid[m][0] = phid[m][0] + p * lx;
-        phid[m][1] = phid[m][1] + p * ly;
-        phid[m][2] = phid[m][2] + p * lz;
+    for (int j = 0; j < NF; ++j) sf[j * LS + i] = 0.0;
+  }
+  __syncthreads();
+  for (int base = 0; base < T.ne; base += NT) {
+    const int le = base + tid;
+    const bool act = le < T.ne;
+    const size_t e = (size_t)T.e0 + (act ? le : 0);
+    unsigned lc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double f[8][3];
+    double hf[SPLIT ? 8 : 1][3];
+    if (act) {
+      double sr[6] = {0, 0, 0, 0, 0, 0}, sn[6] = {0, 0, 0, 0, 0, 0};
+      double phid[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+      double qv[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};  // viscous hourglass (C_hg==2)
+      double shp[8][3];
+      double ph[CHG == 1 ? 4 : 1][8];
+      double body[BODY ? 24 : 1];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        lc[i] = LDG(A.lconn + i * S + e);
+        shp[i][0] = LDG(A.shp + (3 * i) * S + e); shp[i][1] = LDG(A.shp + (3 * i + 1) * S + e); shp[i][2] = LDG(A.shp + (3 * i + 2) * S + e);
+        if (CHG == 1) {
+#pragma unroll
+          for (int m = 0; m < 4; ++m) ph[m][i] = LDG(A.phi + (8 * m + i) * S + e);
+        }
       }
-    } else if (CHG == 2) {
-      // hrglss.f90:57-70
-      const int fi[4][8] = {{1, 1, -1, -1, -1, -1, 1, 1}, {1, -1, -1, 1, -1, 1, 1, -1},
-                            {1, -1, 1, -1, 1, -1, 1, -1}, {1, -1, 1, -1, -1, 1, -1, 1}};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        qv[0][j] = qv[0][j] + vx * fi[j][i];
-        qv[1][j] = qv[1][j] + vy * fi[j][i];
-        qv[2][j] = qv[2][j] + vz * fi[j][i];
+      for (int i = 0; i < 8; ++i) {
+        const int li = lc[i] & EQD_LN_MASK;
+        const double vx = sv[li], vy = sv[LS + li], vz = sv[2 * LS + li];
+        const double s1 = shp[i][0], s2 = shp[i][1], s3 = shp[i][2];
+        // calcElemKU.f90:44-60 (B with engineering shear, calcB.f90:10-25)
+        sr[0] = sr[0] + s1 * vx;
+        sr[1] = sr[1] + s2 * vy;
+        sr[2] = sr[2] + s3 * vz;
+        sr[3] = sr[3] + s3 * vy + s2 * vz;
+        sr[4] = sr[4] + s3 * vx + s1 * vz;
+        sr[5] = sr[5] + s2 * vx + s1 * vy;
+        if (QMODE) {
+          const double dx = sd[li], dy = sd[LS + li], dz = sd[2 * LS + li];
+          sn[0] = sn[0] + s1 * dx;
+          sn[1] = sn[1] + s2 * dy;
+          sn[2] = sn[2] + s3 * dz;
+          sn[3] = sn[3] + s3 * dy + s2 * dz;
+          sn[4] = sn[4] + s3 * dx + s1 * dz;
+          sn[5] = sn[5] + s2 * dx + s1 * dy;
+        }
+        if (CHG == 1) {
+          // hrglss.f90:20-33: dl = d + rdampk*v ; phid = sum_j phi(j,m)*dl(j)
+          const double lx = sl[li], ly = sl[LS + li], lz = sl[2 * LS + li];
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const double p = ph[m][i];
+            phid[m][0] = phid[m][0] + p * lx;
+            phid[m][1] = phid[m][1] + p * ly;
+            phid[m][2] = phid[m][2] + p * lz;
+          }
+        } else if (CHG == 2) {
+          // hrglss.f90:57-70
+          const int fi[4][8] = {{1, 1, -1, -1, -1, -1, 1, 1}, {1, -1, -1, 1, -1, 1, 1, -1},
+                                {1, -1, 1, -1, 1, -1, 1, -1}, {1, -1, 1, -1, -1, 1, -1, 1}};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            qv[0][j] = qv[0][j] + vx * fi[j][i];
+            qv[1][j] = qv[1][j] + vy * fi[j][i];
+            qv[2][j] = qv[2][j] + vz * fi[j][i];
+          }
+        }
+        if (BODY) {
+          // assembleGlobalKU.f90:15-16 + calcElemMass.f90: elresf = -al*elemass
+          const double em = LDG(A.emass + i * S + e);
+          body[3 * i] = 0.0 - (A.rdampm * vx) * em;
+          body[3 * i + 1] = 0.0 - (A.rdampm * vy) * em;
+          body[3 * i + 2] = 0.0 - (A.rdampm * vz + A.bodyz) * em;
+        }
+      }
+      const double lam = LDG(A.lam + e), mu = LDG(A.mu + e);
+      const double l2m = lam + 2 * mu;
+      double rate[6];
+      // calcElemKU.f90:63-70
+      rate[0] = 0.0 + l2m * sr[0] + lam * sr[1] + lam * sr[2];
+      rate[1] = 0.0 + lam * sr[0] + l2m * sr[1] + lam * sr[2];
+      rate[2] = 0.0 + lam * sr[0] + lam * sr[1] + l2m * sr[2];
+      rate[3] = mu * sr[3];
+      rate[4] = mu * sr[4];
+      rate[5] = mu * sr[5];
+      double sg[6];
+      if (!QMODE) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) sg[i] = A.stress[i * S + e] + rate[i] * dt;  // :72-76
+      } else {
+        // calcElemKU.f90:77-132, constants tabulated per class (qconstant.f90)
+        const QTab q = c_qtab[A.qcls[e]];
+        const double miuu = mu * q.cs, Mu = l2m * q.cv;
+        const double vols = sn[0] + sn[1] + sn[2];
+        const double ex = q.expdt;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const double a1 = A.qmem[i * S + e];
+          double an;
+          if (i < 3) an = ex * a1 + (1 - ex) * (2 * miuu * sn[i] * q.wks + (Mu * q.wkp - 2 * miuu * q.wks) * vols);
+          else an = ex * a1 + (1 - ex) * (miuu * sn[i] * q.wks);
+          A.qmem[i * S + e] = an;
+          if (i < 3) sg[i] = 2.0 * miuu * sn[i] + (Mu - 2.0 * miuu) * vols - 0.5 * (an + a1);
+          else sg[i] = 2.0 * miuu * sn[i] / 2.0 - 0.5 * (an + a1);
+        }
+      }
+      if (PLASTIC) {
+        // Drucker-Prager viscoplasticity, calcElemKU.f90:133-167
+        const double strmea = (sg[0] + sg[1] + sg[2]) / 3.0;
+        double dv[6] = {sg[0] - strmea, sg[1] - strmea, sg[2] - strmea, sg[3], sg[4], sg[5]};
+        double taomax = 0.5 * (dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]) + dv[3] * dv[3] + dv[4] * dv[4] + dv[5] * dv[5];
+        taomax = sqrt(taomax);
+        double yield = A.ccosphi - A.sinphi * (strmea + LDG(A.porep + e));
+        if (yield < 0.0) yield = 0.0;
+        if (taomax > yield) {
+          const double rjust = yield / taomax + (1 - yield / taomax) * A.expdttv;
+          double pi[6];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            sg[i] = dv[i] * rjust;
+            pi[i] = (dv[i] - sg[i]) / mu;
+            if (i < 3) sg[i] = sg[i] + strmea;
+          }
+          const double pm = (pi[0] + pi[1] + pi[2]) / 3.0;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) pi[i] = pi[i] - pm;
+          double mag = 0.5 * (pi[0] * pi[0] + pi[1] * pi[1] + pi[2] * pi[2]) + pi[3] * pi[3] + pi[4] * pi[4] + pi[5] * pi[5];
+          A.pstrain[e] = A.pstrain[e] + sqrt(mag);   // assembleGlobalKU.f90:26
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) A.stress[i * S + e] = sg[i];
+      // calcElemKU.f90:169-173, constk = -eledet
+      const double det = LDG(A.det + e);
+      const double temp = (-det) * A.w;
+      double t[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) t[i] = temp * (sg[i] + rdampk * rate[i]);
+      double hv[4][3];
+      double coef = 0.0;
+      if (CHG == 1) {
+        double ssv[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) ssv[i] = LDG(A.ss + i * S + e);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {  // hrglss.f90:35-40
+          hv[m][0] = ssv[0] * phid[m][0] + ssv[1] * phid[m][1] + ssv[2] * phid[m][2];
+          hv[m][1] = ssv[1] * phid[m][0] + ssv[3] * phid[m][1] + ssv[4] * phid[m][2];
+          hv[m][2] = ssv[2] * phid[m][0] + ssv[4] * phid[m][1] + ssv[5] * phid[m][2];
+        }
+      } else if (CHG == 2) {
+        coef = 0.25 * A.kapa_hg * LDG(A.rho + e) * LDG(A.vp + e) * pow(det * A.w, 2.0 / 3.0);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const double s1 = shp[i][0], s2 = shp[i][1], s3 = shp[i][2];
+        // calcElemKU.f90:175-189
+        double f0 = s1 * t[0] + s3 * t[4] + s2 * t[5];
+        double f1 = s2 * t[1] + s3 * t[3] + s1 * t[5];
+        double f2 = s3 * t[2] + s2 * t[3] + s1 * t[4];
+        if (BODY) { f0 = body[3 * i] + f0; f1 = body[3 * i + 1] + f1; f2 = body[3 * i + 2] + f2; }
+        double h0 = 0.0, h1 = 0.0, h2 = 0.0;
+        if (CHG == 1) {
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {  // hrglss.f90:41-54: force -= phi(i,m)*(SS.phid)
+            const double p = ph[m][i];
+            h0 = h0 - p * hv[m][0];
+            h1 = h1 - p * hv[m][1];
+            h2 = h2 - p * hv[m][2];
+          }
+        } else if (CHG == 2) {
+          const int fi[4][8] = {{1, 1, -1, -1, -1, -1, 1, 1}, {1, -1, -1, 1, -1, 1, 1, -1},
+                                {1, -1, 1, -1, 1, -1, 1, -1}, {1, -1, 1, -1, -1, 1, -1, 1}};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {  // hrglss.f90:71-80
+            h0 = h0 - coef * qv[0][j] * fi[j][i];
+            h1 = h1 - coef * qv[1][j] * fi[j][i];
+            h2 = h2 - coef * qv[2][j] * fi[j][i];
+          }
+        }
+        if (SPLIT) {
+          f[i][0] = f0; f[i][1] = f1; f[i][2] = f2;
+          hf[i][0] = h0; hf[i][1] = h1; hf[i][2] = h2;
+        } else {
+          f[i][0] = f0 + h0; f[i][1] = f1 + h1; f[i][2] = f2 + h2;
+        }
       }
     }
-    if (BODY) {
-      // assembleGlobalKU.f90:15-16 + calcElemMass.f90: elresf = -al*elemass
-      const double em = LDG(A.emass + i * S + e);
-      body[3 * i] = 0.0 - (A.rdampm * vx) * em;
-      body[3 * i + 1] = 0.0 - (A.rdampm * vy) * em;
-      body[3 * i + 2] = 0.0 - (A.rdampm * vz + A.bodyz) * em;
+    // ---- ordered assembly into the tile's shared force rows
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int li = lc[i] & EQD_LN_MASK, col = lc[i] >> EQD_LN_BITS;
+      for (int c = 0; c < T.NC; ++c) {
+        if (act && col == c) {
+          sf[li] += f[i][0]; sf[LS + li] += f[i][1]; sf[2 * LS + li] += f[i][2];
+          if (SPLIT) { sf[3 * LS + li] += hf[i][0]; sf[4 * LS + li] += hf[i][1]; sf[5 * LS + li] += hf[i][2]; }
+        }
+        __syncthreads();
+      }
     }
   }
-  const double lam = LDG(A.lam + e), mu = LDG(A.mu + e);
-  const double l2m = lam + 2 * mu;
-  double rate[6];
-  // calcElemKU.f90:63-70
-  rate[0] = 0.0 + l2m * sr[0] + lam * sr[1] + lam * sr[2];
-  rate[1] = 0.0 + lam * sr[0] + l2m * sr[1] + lam * sr[2];
-  rate[2] = 0.0 + lam * sr[0] + lam * sr[1] + l2m * sr[2];
-  rate[3] = mu * sr[3];
-  rate[4] = mu * sr[4];
-  rate[5] = mu * sr[5];
-  double sg[6];
-  if (!QMODE) {
+  for (int i = tid; i < T.LN; i += NT) {
 #pragma unroll
-    for (int i = 0; i < 6; ++i) sg[i] = A.stress[i * S + e] + rate[i] * dt;  // :72-76
-  } else {
-    // calcElemKU.f90:77-132, constants tabulated per class (qconstant.f90)
-    const QTab q = c_qtab[A.qcls[e]];
-    const double miuu = mu * q.cs, Mu = l2m * q.cv;
-    const double vols = sn[0] + sn[1] + sn[2];
-    const double ex = q.expdt;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const double a1 = A.qmem[i * S + e];
-      double an;
-      if (i < 3) an = ex * a1 + (1 - ex) * (2 * miuu * sn[i] * q.wks + (Mu * q.wkp - 2 * miuu * q.wks) * vols);
-      else an = ex * a1 + (1 - ex) * (miuu * sn[i] * q.wks);
-      A.qmem[i * S + e] = an;
-      if (i < 3) sg[i] = 2.0 * miuu * sn[i] + (Mu - 2.0 * miuu) * vols - 0.5 * (an + a1);
-      else sg[i] = 2.0 * miuu * sn[i] / 2.0 - 0.5 * (an + a1);
-    }
-  }
-  if (PLASTIC) {
-    // Drucker-Prager viscoplasticity, calcElemKU.f90:133-167
-    const double strmea = (sg[0] + sg[1] + sg[2]) / 3.0;
-    double dv[6] = {sg[0] - strmea, sg[1] - strmea, sg[2] - strmea, sg[3], sg[4], sg[5]};
-    double taomax = 0.5 * (dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]) + dv[3] * dv[3] + dv[4] * dv[4] + dv[5] * dv[5];
-    taomax = sqrt(taomax);
-    double yield = A.ccosphi - A.sinphi * (strmea + LDG(A.porep + e));
-    if (yield < 0.0) yield = 0.0;
-    if (taomax > yield) {
-      const double rjust = yield / taomax + (1 - yield / taomax) * A.expdttv;
-      double pi[6];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        sg[i] = dv[i] * rjust;
-        pi[i] = (dv[i] - sg[i]) / mu;
-        if (i < 3) sg[i] = sg[i] + strmea;
-      }
-      const double pm = (pi[0] + pi[1] + pi[2]) / 3.0;
-#pragma unroll
-      for (int i = 0; i < 6; ++i) pi[i] = pi[i] - pm;
-      double mag = 0.5 * (pi[0] * pi[0] + pi[1] * pi[1] + pi[2] * pi[2]) + pi[3] * pi[3] + pi[4] * pi[4] + pi[5] * pi[5];
-      A.pstrain[e] = A.pstrain[e] + sqrt(mag);   // assembleGlobalKU.f90:26
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 6; ++i) A.stress[i * S + e] = sg[i];
-  // calcElemKU.f90:169-173, constk = -eledet
-  const double temp = (-LDG(A.det + e)) * A.w;
-  double t[6];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) t[i] = temp * (sg[i] + rdampk * rate[i]);
-  double hv[4][3];
-  double coef = 0.0;
-  if (CHG == 1) {
-    double ssv[6];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) ssv[i] = LDG(A.ss + i * S + e);
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {  // hrglss.f90:35-40
-      hv[m][0] = ssv[0] * phid[m][0] + ssv[1] * phid[m][1] + ssv[2] * phid[m][2];
-      hv[m][1] = ssv[1] * phid[m][0] + ssv[3] * phid[m][1] + ssv[4] * phid[m][2];
-      hv[m][2] = ssv[2] * phid[m][0] + ssv[4] * phid[m][1] + ssv[5] * phid[m][2];
-    }
-  } else if (CHG == 2) {
-    coef = 0.25 * A.kapa_hg * LDG(A.rho + e) * LDG(A.vp + e) * pow(LDG(A.det + e) * A.w, 2.0 / 3.0);
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const double s1 = LDG(A.shp + (3 * i) * S + e), s2 = LDG(A.shp + (3 * i + 1) * S + e), s3 = LDG(A.shp + (3 * i + 2) * S + e);
-    // calcElemKU.f90:175-189
-    double f0 = s1 * t[0] + s3 * t[4] + s2 * t[5];
-    double f1 = s2 * t[1] + s3 * t[3] + s1 * t[5];
-    double f2 = s3 * t[2] + s2 * t[3] + s1 * t[4];
-    if (BODY) { f0 = body[3 * i] + f0; f1 = body[3 * i + 1] + f1; f2 = body[3 * i + 2] + f2; }
-    double h0 = 0.0, h1 = 0.0, h2 = 0.0;
-    if (CHG == 1) {
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {  // hrglss.f90:41-54: force -= phi(i,m)*(SS.phid)
-        const double p = LDG(A.phi + (8 * m + i) * S + e);
-        h0 = h0 - p * hv[m][0];
-        h1 = h1 - p * hv[m][1];
-        h2 = h2 - p * hv[m][2];
-      }
-    } else if (CHG == 2) {
-      const int fi[4][8] = {{1, 1, -1, -1, -1, -1, 1, 1}, {1, -1, -1, 1, -1, 1, 1, -1},
-                            {1, -1, 1, -1, 1, -1, 1, -1}, {1, -1, 1, -1, -1, 1, -1, 1}};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {  // hrglss.f90:71-80
-        h0 = h0 - coef * qv[0][j] * fi[j][i];
-        h1 = h1 - coef * qv[1][j] * fi[j][i];
-        h2 = h2 - coef * qv[2][j] * fi[j][i];
-      }
-    }
-    if (SPLIT) {
-      A.ef[(3 * i) * S + e] = f0; A.ef[(3 * i + 1) * S + e] = f1; A.ef[(3 * i + 2) * S + e] = f2;
-      A.ef[(24 + 3 * i) * S + e] = h0; A.ef[(25 + 3 * i) * S + e] = h1; A.ef[(26 + 3 * i) * S + e] = h2;
-    } else {
-      A.ef[(3 * i) * S + e] = f0 + h0; A.ef[(3 * i + 1) * S + e] = f1 + h1; A.ef[(3 * i + 2) * S + e] = f2 + h2;
-    }
+    for (int j = 0; j < NF; ++j) A.pf[(size_t)j * A.PFS + T.nb + i] = sf[j * LS + i];
   }
 }
 
 // ----------------------------------------------------------------------------
 // PML element: calcPMLElemKU (assembleGlobalKU.f90:70-346) fused with hrglss.
 // The damping profile at the centroid (:130-213, constant in time) is
-// precomputed by the host into damps[3][S].
+// precomputed by the host into damps[3][S].  Same tile scheme, 12 force rows.
 template <bool BODY, int CHG>
-__global__ void __launch_bounds__(128) k_elem_pml(ElemArgs A) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= A.n) return;
+__global__ void __launch_bounds__(EQD_TILE_THREADS, 2) k_tile_pml(ElemArgs A) {
+  extern __shared__ double sm[];
+  constexpr int NT = EQD_TILE_THREADS;
+  const int tid = threadIdx.x;
+  const TileCtx T = tile_ctx(A);
+  const int LS = A.LS;
   const size_t S = A.S, NS = A.NnS;
   const double dt = A.dt, rdampk = A.rdampk;
-  double g[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};  // g[a][b] = d v_b / d x_a
-  double sr[6] = {0, 0, 0, 0, 0, 0};
-  double phid[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-  double qv[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
-  double body[BODY ? 24 : 1];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int nd = LDG(A.conn + i * S + e);
-    const double vx = LDG(A.vel + nd), vy = LDG(A.vel + NS + nd), vz = LDG(A.vel + 2 * NS + nd);
-    const double s1 = LDG(A.shp + (3 * i) * S + e), s2 = LDG(A.shp + (3 * i + 1) * S + e), s3 = LDG(A.shp + (3 * i + 2) * S + e);
-    // assembleGlobalKU.f90:215-246
-    sr[0] = sr[0] + s1 * vx;
-    sr[1] = sr[1] + s2 * vy;
-    sr[2] = sr[2] + s3 * vz;
-    sr[3] = sr[3] + s3 * vy + s2 * vz;
-    sr[4] = sr[4] + s3 * vx + s1 * vz;
-    sr[5] = sr[5] + s2 * vx + s1 * vy;
-    // :248-275
-    g[0][0] = g[0][0] + s1 * vx; g[1][1] = g[1][1] + s2 * vy; g[2][2] = g[2][2] + s3 * vz;
-    g[0][1] = g[0][1] + s1 * vy; g[1][0] = g[1][0] + s2 * vx;
-    g[0][2] = g[0][2] + s1 * vz; g[2][0] = g[2][0] + s3 * vx;
-    g[1][2] = g[1][2] + s2 * vz; g[2][1] = g[2][1] + s3 * vy;
-    if (CHG == 1) {
-      const double dx = LDG(A.disp + nd), dy = LDG(A.disp + NS + nd), dz = LDG(A.disp + 2 * NS + nd);
-      const double lx = dx + rdampk * vx, ly = dy + rdampk * vy, lz = dz + rdampk * vz;
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const double p = LDG(A.phi + (8 * m + i) * S + e);
-        phid[m][0] = phid[m][0] + p * lx;
-        phid[m][1] = phid[m][1] + p * ly;
-        phid[m][2] = phid[m][2] + p * lz;
-      }
-    } else if (CHG == 2) {
-      const int fi[4][8] = {{1, 1, -1, -1, -1, -1, 1, 1}, {1, -1, -1, 1, -1, 1, 1, -1},
-                            {1, -1, 1, -1, 1, -1, 1, -1}, {1, -1, 1, -1, -1, 1, -1, 1}};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        qv[0][j] = qv[0][j] + vx * fi[j][i];
-        qv[1][j] = qv[1][j] + vy * fi[j][i];
-        qv[2][j] = qv[2][j] + vz * fi[j][i];
-      }
+  double* sv = sm;            // [3][LS]
+  double* sl = sm + 3 * LS;   // [3][LS]
+  double* sf = sm + 6 * LS;   // [12][LS]
+  for (int i = tid; i < T.LN; i += NT) {
+    const int nd = LDG(A.tnode + T.nb + i);
+    double vx = 0, vy = 0, vz = 0, dx = 0, dy = 0, dz = 0;
+    if (nd >= 0) {
+      vx = LDG(A.vel + nd); vy = LDG(A.vel + NS + nd); vz = LDG(A.vel + 2 * NS + nd);
+      if (CHG == 1) { dx = LDG(A.disp + nd); dy = LDG(A.disp + NS + nd); dz = LDG(A.disp + 2 * NS + nd); }
     }
-    if (BODY) {
-      const double em = LDG(A.emass + i * S + e);
-      body[3 * i] = 0.0 - (A.rdampm * vx) * em;
-      body[3 * i + 1] = 0.0 - (A.rdampm * vy) * em;
-      body[3 * i + 2] = 0.0 - (A.rdampm * vz + A.bodyz) * em;
-    }
+    sv[i] = vx; sv[LS + i] = vy; sv[2 * LS + i] = vz;
+    sl[i] = dx + rdampk * vx; sl[LS + i] = dy + rdampk * vy; sl[2 * LS + i] = dz + rdampk * vz;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) sf[j * LS + i] = 0.0;
   }
-  const double lam = LDG(A.lam + e), mu = LDG(A.mu + e);
-  const double l2m = lam + 2.0 * mu;
-  double rate[6];
-  rate[0] = 0.0 + l2m * sr[0] + lam * sr[1] + lam * sr[2];
-  rate[1] = 0.0 + lam * sr[0] + l2m * sr[1] + lam * sr[2];
-  rate[2] = 0.0 + lam * sr[0] + lam * sr[1] + l2m * sr[2];
-  rate[3] = mu * sr[3];
-  rate[4] = mu * sr[4];
-  rate[5] = mu * sr[5];
-  const double dp[3] = {LDG(A.damps + e), LDG(A.damps + S + e), LDG(A.damps + 2 * S + e)};
-  const double rdt = 1 / dt;
-  // :277-311  s <- (coef*D + (1/dt - d/2) s) / (1/dt + d/2)
-  double s[15];
-#define PML_UPD(k, coef, D, a)                                          \
-  {                                                                     \
-    double x = (coef) * (D) + (rdt - dp[a] / 2) * A.stress[(k) * S + e]; \
-    x = x / (rdt + dp[a] / 2);                                          \
-    s[k] = x;                                                           \
-    A.stress[(k) * S + e] = x;                                          \
+  __syncthreads();
+  for (int base = 0; base < T.ne; base += NT) {
+    const int le = base + tid;
+    const bool act = le < T.ne;
+    const size_t e = (size_t)T.e0 + (act ? le : 0);
+    unsigned lc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double shp[8][3];
+    double ph[CHG == 1 ? 4 : 1][8];
+    double body[BODY ? 24 : 1];
+    double qv[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+    double hv[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    double s0[6] = {0, 0, 0, 0, 0, 0};
+    double sxx = 0, syy = 0, szz = 0, sxy = 0, sxz = 0, syz = 0, detw = 0, coef = 0;
+    if (act) {
+      double g[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};  // g[a][b] = d v_b / d x_a
+      double sr[6] = {0, 0, 0, 0, 0, 0};
+      double phid[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        lc[i] = LDG(A.lconn + i * S + e);
+        shp[i][0] = LDG(A.shp + (3 * i) * S + e); shp[i][1] = LDG(A.shp + (3 * i + 1) * S + e); shp[i][2] = LDG(A.shp + (3 * i + 2) * S + e);
+        if (CHG == 1) {
+#pragma unroll
+          for (int m = 0; m < 4; ++m) ph[m][i] = LDG(A.phi + (8 * m + i) * S + e);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int li = lc[i] & EQD_LN_MASK;
+        const double vx = sv[li], vy = sv[LS + li], vz = sv[2 * LS + li];
+        const double s1 = shp[i][0], s2 = shp[i][1], s3 = shp[i][2];
+        // assembleGlobalKU.f90:215-246
+        sr[0] = sr[0] + s1 * vx;
+        sr[1] = sr[1] + s2 * vy;
+        sr[2] = sr[2] + s3 * vz;
+        sr[3] = sr[3] + s3 * vy + s2 * vz;
+        sr[4] = sr[4] + s3 * vx + s1 * vz;
+        sr[5] = sr[5] + s2 * vx + s1 * vy;
+        // :248-275
+        g[0][0] = g[0][0] + s1 * vx; g[1][1] = g[1][1] + s2 * vy; g[2][2] = g[2][2] + s3 * vz;
+        g[0][1] = g[0][1] + s1 * vy; g[1][0] = g[1][0] + s2 * vx;
+        g[0][2] = g[0][2] + s1 * vz; g[2][0] = g[2][0] + s3 * vx;
+        g[1][2] = g[1][2] + s2 * vz; g[2][1] = g[2][1] + s3 * vy;
+        if (CHG == 1) {
+          const double lx = sl[li], ly = sl[LS + li], lz = sl[2 * LS + li];
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const double p = ph[m][i];
+            phid[m][0] = phid[m][0] + p * lx;
+            phid[m][1] = phid[m][1] + p * ly;
+            phid[m][2] = phid[m][2] + p * lz;
+          }
+        } else if (CHG == 2) {
+          const int fi[4][8] = {{1, 1, -1, -1, -1, -1, 1, 1}, {1, -1, -1, 1, -1, 1, 1, -1},
+                                {1, -1, 1, -1, 1, -1, 1, -1}, {1, -1, 1, -1, -1, 1, -1, 1}};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            qv[0][j] = qv[0][j] + vx * fi[j][i];
+            qv[1][j] = qv[1][j] + vy * fi[j][i];
+            qv[2][j] = qv[2][j] + vz * fi[j][i];
+          }
+        }
+        if (BODY) {
+          const double em = LDG(A.emass + i * S + e);
+          body[3 * i] = 0.0 - (A.rdampm * vx) * em;
+          body[3 * i + 1] = 0.0 - (A.rdampm * vy) * em;
+          body[3 * i + 2] = 0.0 - (A.rdampm * vz + A.bodyz) * em;
+        }
+      }
+      const double lam = LDG(A.lam + e), mu = LDG(A.mu + e);
+      const double l2m = lam + 2.0 * mu;
+      double rate[6];
+      rate[0] = 0.0 + l2m * sr[0] + lam * sr[1] + lam * sr[2];
+      rate[1] = 0.0 + lam * sr[0] + l2m * sr[1] + lam * sr[2];
+      rate[2] = 0.0 + lam * sr[0] + lam * sr[1] + l2m * sr[2];
+      rate[3] = mu * sr[3];
+      rate[4] = mu * sr[4];
+      rate[5] = mu * sr[5];
+      const double dp[3] = {LDG(A.damps + e), LDG(A.damps + S + e), LDG(A.damps + 2 * S + e)};
+      const double rdt = 1 / dt;
+      // :277-311  s <- (coef*D + (1/dt - d/2) s) / (1/dt + d/2)
+      double s[15];
+#define PML_UPD(k, cf, D, a)                                           \
+  {                                                                    \
+    double x = (cf) * (D) + (rdt - dp[a] / 2) * A.stress[(k) * S + e]; \
+    x = x / (rdt + dp[a] / 2);                                         \
+    s[k] = x;                                                          \
+    A.stress[(k) * S + e] = x;                                         \
   }
-  PML_UPD(0, l2m, g[0][0], 0) PML_UPD(1, lam, g[1][1], 1) PML_UPD(2, lam, g[2][2], 2)
-  PML_UPD(3, lam, g[0][0], 0) PML_UPD(4, l2m, g[1][1], 1) PML_UPD(5, lam, g[2][2], 2)
-  PML_UPD(6, lam, g[0][0], 0) PML_UPD(7, lam, g[1][1], 1) PML_UPD(8, l2m, g[2][2], 2)
-  PML_UPD(9, mu, g[0][1], 0) PML_UPD(10, mu, g[1][0], 1)
-  PML_UPD(11, mu, g[0][2], 0) PML_UPD(12, mu, g[2][0], 2)
-  PML_UPD(13, mu, g[1][2], 1) PML_UPD(14, mu, g[2][1], 2)
+      PML_UPD(0, l2m, g[0][0], 0) PML_UPD(1, lam, g[1][1], 1) PML_UPD(2, lam, g[2][2], 2)
+      PML_UPD(3, lam, g[0][0], 0) PML_UPD(4, l2m, g[1][1], 1) PML_UPD(5, lam, g[2][2], 2)
+      PML_UPD(6, lam, g[0][0], 0) PML_UPD(7, lam, g[1][1], 1) PML_UPD(8, l2m, g[2][2], 2)
+      PML_UPD(9, mu, g[0][1], 0) PML_UPD(10, mu, g[1][0], 1)
+      PML_UPD(11, mu, g[0][2], 0) PML_UPD(12, mu, g[2][0], 2)
+      PML_UPD(13, mu, g[1][2], 1) PML_UPD(14, mu, g[2][1], 2)
 #undef PML_UPD
-  const double sxx = s[0] + s[1] + s[2], syy = s[3] + s[4] + s[5], szz = s[6] + s[7] + s[8];
-  const double sxy = s[9] + s[10], sxz = s[11] + s[12], syz = s[13] + s[14];
-  double s0[6];
+      sxx = s[0] + s[1] + s[2]; syy = s[3] + s[4] + s[5]; szz = s[6] + s[7] + s[8];
+      sxy = s[9] + s[10]; sxz = s[11] + s[12]; syz = s[13] + s[14];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) s0[i] = LDG(A.stress + (15 + i) * S + e) + rdampk * rate[i];  // :320-325 (read-only slots)
-  const double det = LDG(A.det + e), w = A.w;
-  double hv[4][3];
-  double coef = 0.0;
-  if (CHG == 1) {
-    double ssv[6];
+      for (int i = 0; i < 6; ++i) s0[i] = LDG(A.stress + (15 + i) * S + e) + rdampk * rate[i];  // :320-325 (read-only slots)
+      const double det = LDG(A.det + e);
+      detw = det * A.w;
+      if (CHG == 1) {
+        double ssv[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) ssv[i] = LDG(A.ss + i * S + e);
+        for (int i = 0; i < 6; ++i) ssv[i] = LDG(A.ss + i * S + e);
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      hv[m][0] = ssv[0] * phid[m][0] + ssv[1] * phid[m][1] + ssv[2] * phid[m][2];
-      hv[m][1] = ssv[1] * phid[m][0] + ssv[3] * phid[m][1] + ssv[4] * phid[m][2];
-      hv[m][2] = ssv[2] * phid[m][0] + ssv[4] * phid[m][1] + ssv[5] * phid[m][2];
+        for (int m = 0; m < 4; ++m) {
+          hv[m][0] = ssv[0] * phid[m][0] + ssv[1] * phid[m][1] + ssv[2] * phid[m][2];
+          hv[m][1] = ssv[1] * phid[m][0] + ssv[3] * phid[m][1] + ssv[4] * phid[m][2];
+          hv[m][2] = ssv[2] * phid[m][0] + ssv[4] * phid[m][1] + ssv[5] * phid[m][2];
+        }
+      } else if (CHG == 2) {
+        coef = 0.25 * A.kapa_hg * LDG(A.rho + e) * LDG(A.vp + e) * pow(det * A.w, 2.0 / 3.0);
+      }
     }
-  } else if (CHG == 2) {
-    coef = 0.25 * A.kapa_hg * LDG(A.rho + e) * LDG(A.vp + e) * pow(det * w, 2.0 / 3.0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      double fo[12];
+      if (act) {
+        const double s1 = shp[i][0], s2 = shp[i][1], s3 = shp[i][2];
+        // :328-344
+        fo[0] = 0.0 - detw * s1 * sxx;
+        fo[1] = 0.0 - detw * s2 * sxy;
+        fo[2] = 0.0 - detw * s3 * sxz;
+        fo[3] = 0.0 - detw * s1 * sxy;
+        fo[4] = 0.0 - detw * s2 * syy;
+        fo[5] = 0.0 - detw * s3 * syz;
+        fo[6] = 0.0 - detw * s1 * sxz;
+        fo[7] = 0.0 - detw * s2 * syz;
+        fo[8] = 0.0 - detw * s3 * szz;
+        double b0 = 0.0, b1 = 0.0, b2 = 0.0;
+        if (BODY) { b0 = body[3 * i]; b1 = body[3 * i + 1]; b2 = body[3 * i + 2]; }
+        double f9 = b0 - detw * (s1 * s0[0] + s3 * s0[4] + s2 * s0[5]);
+        double f10 = b1 - detw * (s2 * s0[1] + s3 * s0[3] + s1 * s0[5]);
+        double f11 = b2 - detw * (s3 * s0[2] + s2 * s0[3] + s1 * s0[4]);
+        if (CHG == 1) {
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const double p = ph[m][i];
+            f9 = f9 - p * hv[m][0];
+            f10 = f10 - p * hv[m][1];
+            f11 = f11 - p * hv[m][2];
+          }
+        } else if (CHG == 2) {
+          const int fi[4][8] = {{1, 1, -1, -1, -1, -1, 1, 1}, {1, -1, -1, 1, -1, 1, 1, -1},
+                                {1, -1, 1, -1, 1, -1, 1, -1}, {1, -1, 1, -1, -1, 1, -1, 1}};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            f9 = f9 - coef * qv[0][j] * fi[j][i];
+            f10 = f10 - coef * qv[1][j] * fi[j][i];
+            f11 = f11 - coef * qv[2][j] * fi[j][i];
+          }
+        }
+        fo[9] = f9; fo[10] = f10; fo[11] = f11;
+      }
+      const int li = lc[i] & EQD_LN_MASK, col = lc[i] >> EQD_LN_BITS;
+      for (int c = 0; c < T.NC; ++c) {
+        if (act && col == c) {
+#pragma unroll
+          for (int j = 0; j < 12; ++j) sf[j * LS + li] += fo[j];
+        }
+        __syncthreads();
+      }
+    }
   }
+  for (int i = tid; i < T.LN; i += NT) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const double s1 = LDG(A.shp + (3 * i) * S + e), s2 = LDG(A.shp + (3 * i + 1) * S + e), s3 = LDG(A.shp + (3 * i + 2) * S + e);
-    double* f = A.ef + (size_t)(12 * i) * S + e;
-    // :328-344
-    f[0] = 0.0 - det * w * s1 * sxx;
-    f[S] = 0.0 - det * w * s2 * sxy;
-    f[2 * S] = 0.0 - det * w * s3 * sxz;
-    f[3 * S] = 0.0 - det * w * s1 * sxy;
-    f[4 * S] = 0.0 - det * w * s2 * syy;
-    f[5 * S] = 0.0 - det * w * s3 * syz;
-    f[6 * S] = 0.0 - det * w * s1 * sxz;
-    f[7 * S] = 0.0 - det * w * s2 * syz;
-    f[8 * S] = 0.0 - det * w * s3 * szz;
-    double b0 = 0.0, b1 = 0.0, b2 = 0.0;
-    if (BODY) { b0 = body[3 * i]; b1 = body[3 * i + 1]; b2 = body[3 * i + 2]; }
-    double f9 = b0 - det * w * (s1 * s0[0] + s3 * s0[4] + s2 * s0[5]);
-    double f10 = b1 - det * w * (s2 * s0[1] + s3 * s0[3] + s1 * s0[5]);
-    double f11 = b2 - det * w * (s3 * s0[2] + s2 * s0[3] + s1 * s0[4]);
-    if (CHG == 1) {
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const double p = LDG(A.phi + (8 * m + i) * S + e);
-        f9 = f9 - p * hv[m][0];
-        f10 = f10 - p * hv[m][1];
-        f11 = f11 - p * hv[m][2];
-      }
-    } else if (CHG == 2) {
-      const int fi[4][8] = {{1, 1, -1, -1, -1, -1, 1, 1}, {1, -1, -1, 1, -1, 1, 1, -1},
-                            {1, -1, 1, -1, 1, -1, 1, -1}, {1, -1, 1, -1, -1, 1, -1, 1}};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        f9 = f9 - coef * qv[0][j] * fi[j][i];
-        f10 = f10 - coef * qv[1][j] * fi[j][i];
-        f11 = f11 - coef * qv[2][j] * fi[j][i];
-      }
-    }
-    f[9 * S] = f9; f[10 * S] = f10; f[11 * S] = f11;
+    for (int j = 0; j < 12; ++j) A.pf[(size_t)j * A.PFS + T.nb + i] = sf[j * LS + i];
   }
 }
 
@@ -896,30 +1039,46 @@ void launch_materialize_accel(const NodeArgs& A, double* out, cudaStream_t s) {
   if (A.Nn > 0) k_materialize_accel<<<nblk(A.Nn, 128), 128, 0, s>>>(A, out);
 }
 
+// dynamic shared memory of a tile kernel: staged rows + force rows, LS doubles each
+static size_t tile_smem(const ElemArgs& A, int rows) { return (size_t)rows * A.LS * sizeof(double); }
+static void tile_launch(void (*kern)(ElemArgs), const ElemArgs& A, int ntiles, int rows, cudaStream_t s) {
+  const size_t sm = tile_smem(A, rows);
+  // opt in to the large dynamic shared memory once per (device, kernel)
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*>> done;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (done.insert({dev, (const void*)kern}).second)
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+  }
+  kern<<<ntiles, EQD_TILE_THREADS, sm, s>>>(A);
+}
 template <bool PL, bool Q, bool BODY, bool SPLIT>
-static void launch_reg_chg(const ElemArgs& A, int chg, cudaStream_t s) {
-  const int g = nblk(A.n, 128);
-  if (chg == 2) k_elem_reg<PL, Q, BODY, SPLIT, 2><<<g, 128, 0, s>>>(A);
-  else k_elem_reg<PL, Q, BODY, SPLIT, 1><<<g, 128, 0, s>>>(A);
+static void launch_reg_chg(const ElemArgs& A, int ntiles, int chg, cudaStream_t s) {
+  const int rows = (Q ? 9 : 6) + (SPLIT ? 6 : 3);
+  if (chg == 2) tile_launch(k_tile_reg<PL, Q, BODY, SPLIT, 2>, A, ntiles, rows, s);
+  else tile_launch(k_tile_reg<PL, Q, BODY, SPLIT, 1>, A, ntiles, rows, s);
 }
 template <bool SPLIT>
-static void launch_reg_split(const ElemArgs& A, bool plastic, bool q, bool body, int chg, cudaStream_t s) {
+static void launch_reg_split(const ElemArgs& A, int ntiles, bool plastic, bool q, bool body, int chg, cudaStream_t s) {
   // C_Q==1 with C_elastic==0 is rejected by the reference (warning.f90:6-9)
-  if (q) { if (body) launch_reg_chg<false, true, true, SPLIT>(A, chg, s); else launch_reg_chg<false, true, false, SPLIT>(A, chg, s); }
-  else if (plastic) { if (body) launch_reg_chg<true, false, true, SPLIT>(A, chg, s); else launch_reg_chg<true, false, false, SPLIT>(A, chg, s); }
-  else { if (body) launch_reg_chg<false, false, true, SPLIT>(A, chg, s); else launch_reg_chg<false, false, false, SPLIT>(A, chg, s); }
+  if (q) { if (body) launch_reg_chg<false, true, true, SPLIT>(A, ntiles, chg, s); else launch_reg_chg<false, true, false, SPLIT>(A, ntiles, chg, s); }
+  else if (plastic) { if (body) launch_reg_chg<true, false, true, SPLIT>(A, ntiles, chg, s); else launch_reg_chg<true, false, false, SPLIT>(A, ntiles, chg, s); }
+  else { if (body) launch_reg_chg<false, false, true, SPLIT>(A, ntiles, chg, s); else launch_reg_chg<false, false, false, SPLIT>(A, ntiles, chg, s); }
 }
-void launch_elem_reg(const ElemArgs& A, bool split, bool plastic, bool q, bool body, int chg, cudaStream_t s) {
-  if (A.n <= 0) return;
-  if (split) launch_reg_split<true>(A, plastic, q, body, chg, s);
-  else launch_reg_split<false>(A, plastic, q, body, chg, s);
+void launch_elem_reg(const ElemArgs& A, int ntiles, bool split, bool plastic, bool q, bool body, int chg, cudaStream_t s) {
+  if (ntiles <= 0) return;
+  if (split) launch_reg_split<true>(A, ntiles, plastic, q, body, chg, s);
+  else launch_reg_split<false>(A, ntiles, plastic, q, body, chg, s);
 }
-void launch_elem_pml(const ElemArgs& A, bool body, int chg, cudaStream_t s) {
-  if (A.n <= 0) return;
-  const int g = nblk(A.n, 128);
-  if (body) { if (chg == 2) k_elem_pml<true, 2><<<g, 128, 0, s>>>(A); else k_elem_pml<true, 1><<<g, 128, 0, s>>>(A); }
-  else { if (chg == 2) k_elem_pml<false, 2><<<g, 128, 0, s>>>(A); else k_elem_pml<false, 1><<<g, 128, 0, s>>>(A); }
+void launch_elem_pml(const ElemArgs& A, int ntiles, bool body, int chg, cudaStream_t s) {
+  if (ntiles <= 0) return;
+  if (body) { if (chg == 2) tile_launch(k_tile_pml<true, 2>, A, ntiles, 18, s); else tile_launch(k_tile_pml<true, 1>, A, ntiles, 18, s); }
+  else { if (chg == 2) tile_launch(k_tile_pml<false, 2>, A, ntiles, 18, s); else tile_launch(k_tile_pml<false, 1>, A, ntiles, 18, s); }
 }
+int tile_rows(int cls, bool q) { return cls == CLS_PML ? 18 : (q ? 9 : 6) + (cls == CLS_REGX ? 6 : 3); }
 void launch_store_offfault(const int* idhist, int n, double* out, const double* vel, const double* disp, int NnS,
                            const StepState* st, cudaStream_t s) {
   if (n > 0) k_store_offfault<<<nblk(n + 1, 128), 128, 0, s>>>(idhist, n, out, vel, disp, NnS, st);

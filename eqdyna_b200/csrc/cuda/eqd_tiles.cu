@@ -1,0 +1,283 @@
+// Tile planner (host): see eqd_tiles.h.  No reference code path corresponds to
+// this file: the reference sweeps elements in storage order and scatter-adds
+// (assembleGlobalKU.f90:11-66); the tiles only re-group that same sweep so that
+// one CTA can assemble a brick's nodal forces on chip.
+#include "eqd_tiles.h"
+
+#include <algorithm>
+#include <stdexcept>
+#include <thread>
+
+#include "eqd_dev.cuh"
+
+namespace eqd {
+
+namespace {
+
+template <class F>
+void parallel_for(int n, F&& fn) {
+  int nt = (int)std::thread::hardware_concurrency();
+  nt = std::max(1, std::min(nt, 16));
+  if (n < 64 || nt == 1) { fn(0, n); return; }
+  std::vector<std::thread> th;
+  const int chunk = (n + nt - 1) / nt;
+  for (int t = 0; t < nt; ++t) {
+    const int b = t * chunk, e = std::min(n, b + chunk);
+    if (b >= e) break;
+    th.emplace_back([=, &fn] { fn(b, e); });
+  }
+  for (auto& x : th) x.join();
+}
+
+inline int balanced(int extent, int target, int& nblocks) {
+  nblocks = std::max(1, (extent + target - 1) / target);
+  return std::max(1, (extent + nblocks - 1) / nblocks);
+}
+
+struct Tile {
+  int b, e;                 // range in the sorted element order
+  std::vector<int> nodes;   // ascending unique node ids
+};
+
+void unique_nodes(const int* conn, const std::vector<int>& elems, const std::vector<int>& order, int b, int e,
+                  std::vector<int>& out) {
+  out.clear();
+  out.reserve(8 * (size_t)(e - b));
+  for (int k = b; k < e; ++k) {
+    const int* c = conn + 8 * (size_t)elems[order[k]];
+    for (int j = 0; j < 8; ++j) out.push_back(c[j]);
+  }
+  std::sort(out.begin(), out.end());
+  out.erase(std::unique(out.begin(), out.end()), out.end());
+}
+
+void split_group(const int* conn, const std::vector<int>& elems, const std::vector<int>& order, int b, int e,
+                 const TileShape& sh, std::vector<Tile>& out) {
+  if (b >= e) return;
+  Tile t;
+  t.b = b; t.e = e;
+  if (e - b <= sh.capE) {
+    unique_nodes(conn, elems, order, b, e, t.nodes);
+    if ((int)t.nodes.size() <= sh.capN || e - b == 1) { out.push_back(std::move(t)); return; }
+  }
+  const int m = b + (e - b) / 2;
+  split_group(conn, elems, order, b, m, sh, out);
+  split_group(conn, elems, order, m, e, sh, out);
+}
+
+}  // namespace
+
+bool infer_grid(const int* conn, const int* etype, int Ne, int Nn, int& ny, int& nz) {
+  for (int e = 0; e < Ne; ++e) {
+    if (etype[e] != 1 && etype[e] != 2) continue;
+    int a[8];
+    for (int k = 0; k < 8; ++k) a[k] = conn[8 * (size_t)e + k];
+    std::sort(a, a + 8);
+    const int p = a[2] - a[0], q = a[4] - a[0];
+    if (a[1] - a[0] != 1 || p <= 1 || q <= p + 1 || q % p != 0) continue;
+    if (a[3] != a[0] + p + 1 || a[5] != a[0] + q + 1 || a[6] != a[0] + q + p || a[7] != a[0] + q + p + 1) continue;
+    ny = p; nz = q / p;
+    (void)Nn;
+    return true;
+  }
+  return false;
+}
+
+void plan_tiles(const int* conn, const std::vector<int>& elems, int Nn, int ny, int nz, bool gridOk,
+                const TileShape& sh, int NT, TilePlan& P) {
+  const int n = (int)elems.size();
+  P = TilePlan();
+  P.n = n;
+  if (n == 0) { P.S = 32; P.PFS = 4; P.LS = 1; P.refId.assign(P.S, -1); P.tileNode.assign(1, 0); P.tnode.assign(P.PFS, -1); P.lconn.assign(8 * (size_t)P.S, 0); return; }
+  if (sh.capN > (int)EQD_LN_MASK) throw std::runtime_error("tile node cap exceeds the 12-bit local index");
+  // ---- brick key per element
+  std::vector<int> key(n);
+  int nKeys = 1;
+  if (gridOk) {
+    const long nynz = (long)ny * nz;
+    std::vector<int> cx(n), cy(n), cz(n);
+    parallel_for(n, [&](int b, int e) {
+      for (int j = b; j < e; ++j) {
+        const int* c = conn + 8 * (size_t)elems[j];
+        int n0 = c[0];
+        for (int k = 1; k < 8; ++k) n0 = std::min(n0, c[k]);
+        cx[j] = (int)(n0 / nynz); cz[j] = (int)((n0 % nynz) / ny); cy[j] = (int)(n0 % ny);
+      }
+    });
+    int mn[3] = {cx[0], cz[0], cy[0]}, mx[3] = {cx[0], cz[0], cy[0]};
+    for (int j = 0; j < n; ++j) {
+      mn[0] = std::min(mn[0], cx[j]); mx[0] = std::max(mx[0], cx[j]);
+      mn[1] = std::min(mn[1], cz[j]); mx[1] = std::max(mx[1], cz[j]);
+      mn[2] = std::min(mn[2], cy[j]); mx[2] = std::max(mx[2], cy[j]);
+    }
+    int nb[3];
+    const int bxe = balanced(mx[0] - mn[0] + 1, sh.bx, nb[0]);
+    const int bze = balanced(mx[1] - mn[1] + 1, sh.bz, nb[1]);
+    const int bye = balanced(mx[2] - mn[2] + 1, sh.by, nb[2]);
+    const double tot = (double)nb[0] * nb[1] * nb[2];
+    if (tot > 1.0e9) throw std::runtime_error("tile planner: brick grid too large");
+    nKeys = nb[0] * nb[1] * nb[2];
+    parallel_for(n, [&](int b, int e) {
+      for (int j = b; j < e; ++j)
+        key[j] = (((cx[j] - mn[0]) / bxe) * nb[1] + (cz[j] - mn[1]) / bze) * nb[2] + (cy[j] - mn[2]) / bye;
+    });
+  } else {
+    const int per = std::max(32, std::min(sh.capE, sh.bx * sh.bz * sh.by));
+    nKeys = (n + per - 1) / per;
+    for (int j = 0; j < n; ++j) key[j] = j / per;
+  }
+  // ---- stable counting sort by key (elements keep ascending reference order inside a brick)
+  std::vector<int> start(nKeys + 1, 0);
+  for (int j = 0; j < n; ++j) start[key[j] + 1]++;
+  for (int k = 0; k < nKeys; ++k) start[k + 1] += start[k];
+  std::vector<int> order(n);
+  {
+    std::vector<int> fill(start.begin(), start.end() - 1);
+    for (int j = 0; j < n; ++j) order[fill[key[j]]++] = j;
+  }
+  // ---- non-empty groups -> tiles
+  std::vector<int> groups;
+  for (int k = 0; k < nKeys; ++k) if (start[k + 1] > start[k]) groups.push_back(k);
+  const int nG = (int)groups.size();
+  std::vector<std::vector<Tile>> gt(nG);
+  parallel_for(nG, [&](int b, int e) {
+    for (int g = b; g < e; ++g) split_group(conn, elems, order, start[groups[g]], start[groups[g] + 1], sh, gt[g]);
+  });
+  std::vector<Tile*> tiles;
+  for (auto& v : gt) for (auto& t : v) tiles.push_back(&t);
+  const int nT = (int)tiles.size();
+  P.nTiles = nT;
+  P.tileElem.resize(nT); P.tileCnt.resize(nT); P.tileNode.resize(nT + 1); P.tileColours.assign(nT, 1);
+  long slot = 0, nslot = 0;
+  int LS = 1;
+  for (int t = 0; t < nT; ++t) {
+    P.tileElem[t] = (int)slot; P.tileCnt[t] = tiles[t]->e - tiles[t]->b;
+    slot += (P.tileCnt[t] + 31) / 32 * 32;
+    P.tileNode[t] = (int)nslot;
+    const int ln = (int)tiles[t]->nodes.size();
+    if (ln > (int)EQD_LN_MASK) throw std::runtime_error("tile planner: one element brick touches more than 4095 nodes");
+    LS = std::max(LS, (ln + 3) / 4 * 4);
+    nslot += (ln + 3) / 4 * 4;
+    if (slot > (1L << 29) || nslot > (1L << 30)) throw std::runtime_error("tile planner: class too large for 32-bit slots");
+  }
+  P.tileNode[nT] = (int)nslot;
+  P.S = (int)std::max(slot, 32L);
+  P.PFS = (int)std::max(nslot, 4L);
+  P.LS = LS;
+  P.refId.assign(P.S, -1);
+  P.tnode.assign(P.PFS, -1);
+  P.lconn.assign(8 * (size_t)P.S, 0);
+  const size_t S = P.S;
+  std::vector<int> bad(1, 0);
+  parallel_for(nT, [&](int tb, int te) {
+    std::vector<int> stamp, cnt;
+    for (int t = tb; t < te; ++t) {
+      const Tile& T = *tiles[t];
+      const int ln = (int)T.nodes.size();
+      std::copy(T.nodes.begin(), T.nodes.end(), P.tnode.begin() + P.tileNode[t]);
+      stamp.assign(8 * (size_t)ln, -1); cnt.assign(8 * (size_t)ln, 0);
+      int maxc = 1;
+      for (int k = T.b; k < T.e; ++k) {
+        const int le = k - T.b;
+        const size_t s = (size_t)P.tileElem[t] + le;
+        const int e = elems[order[k]];
+        P.refId[s] = e;
+        const int pass = le / NT;
+        for (int i = 0; i < 8; ++i) {
+          const int nd = conn[8 * (size_t)e + i];
+          const int li = (int)(std::lower_bound(T.nodes.begin(), T.nodes.end(), nd) - T.nodes.begin());
+          // colour = how many earlier elements of this (pass, phase) hit the same node
+          const size_t q = 8 * (size_t)li + i;
+          if (stamp[q] != pass) { stamp[q] = pass; cnt[q] = 0; }
+          const int col = cnt[q]++;
+          if (col > 15) { bad[0] = 1; continue; }
+          maxc = std::max(maxc, col + 1);
+          P.lconn[(size_t)i * S + s] = (uint16_t)(li | (col << EQD_LN_BITS));
+        }
+      }
+      P.tileColours[t] = (uint8_t)maxc;
+    }
+  });
+  if (bad[0]) throw std::runtime_error("tile planner: more than 16 elements of one phase share a node");
+  (void)Nn;
+}
+
+}  // namespace eqd
+
+// ----------------------------------------------------------------------------
+// Host-only self-check of the planner on a sub-domain's connectivity (needs no
+// GPU; used by the CPU test-suite and by `eqd_set_option(h, "check_tiles", 1)`).
+// stats[0..7] = tiles, elements, padded slots, tile-node slots, max tile nodes,
+// max colours, tiles with more than one colour, grid inferred (0/1), per class
+// c at stats[8*c ..].  Returns 0 when every invariant holds, else a line number.
+extern "C" int eqd_plan_check(int32_t Nn, int32_t Ne, const int32_t* nodeElemIdRelation, const int32_t* elemTypeArr,
+                              const int32_t* numOfDofPerNodeArr, int64_t* stats) {
+  using namespace eqd;
+  if (Nn <= 0 || Ne <= 0 || !nodeElemIdRelation || !elemTypeArr || !numOfDofPerNodeArr || !stats) return __LINE__;
+  try {
+    std::vector<int> conn(8 * (size_t)Ne);
+    for (size_t k = 0; k < conn.size(); ++k) {
+      conn[k] = nodeElemIdRelation[k] - 1;
+      if (conn[k] < 0 || conn[k] >= Nn) return __LINE__;
+    }
+    std::vector<int> members[3];
+    for (int e = 0; e < Ne; ++e) {
+      int c = CLS_PML;
+      if (elemTypeArr[e] != 2) {
+        c = CLS_REG;
+        for (int k = 0; k < 8; ++k) if (numOfDofPerNodeArr[conn[8 * (size_t)e + k]] == 12) c = CLS_REGX;
+      }
+      members[c].push_back(e);
+    }
+    int ny = 0, nz = 0;
+    const bool ok = infer_grid(conn.data(), elemTypeArr, Ne, Nn, ny, nz);
+    std::vector<char> seen(Ne, 0);
+    for (int c = 0; c < 3; ++c) {
+      TileShape sh;
+      if (c == CLS_PML) { sh.bx = 3; sh.bz = 3; sh.by = 32; sh.capE = 384; sh.capN = 800; }
+      TilePlan P;
+      plan_tiles(conn.data(), members[c], Nn, ny, nz, ok, sh, EQD_TILE_THREADS, P);
+      int64_t* st = stats + 8 * c;
+      st[0] = P.nTiles; st[1] = P.n; st[2] = P.S; st[3] = P.PFS; st[4] = P.LS; st[5] = 0; st[6] = 0; st[7] = ok;
+      if (P.n == 0) continue;
+      for (int t = 0; t < P.nTiles; ++t) {
+        const int nb = P.tileNode[t], ln = P.tileNode[t + 1] - nb;
+        if (P.tileElem[t] % 32 || nb % 4 || ln > P.LS || P.tileCnt[t] > sh.capE) return __LINE__;
+        for (int i = 1; i < ln; ++i)
+          if (P.tnode[nb + i] >= 0 && P.tnode[nb + i] <= P.tnode[nb + i - 1]) return __LINE__;
+        st[5] = std::max<int64_t>(st[5], P.tileColours[t]);
+        st[6] += P.tileColours[t] > 1;
+        // replay the kernel's assembly schedule and look for write conflicts
+        std::vector<int> owner(ln);
+        for (int base = 0; base < P.tileCnt[t]; base += EQD_TILE_THREADS)
+          for (int i = 0; i < 8; ++i)
+            for (int col = 0; col < P.tileColours[t]; ++col) {
+              std::fill(owner.begin(), owner.end(), -1);
+              for (int le = base; le < std::min(P.tileCnt[t], base + EQD_TILE_THREADS); ++le) {
+                const size_t s = (size_t)P.tileElem[t] + le;
+                const unsigned u = P.lconn[(size_t)i * P.S + s];
+                if ((int)(u >> EQD_LN_BITS) != col) continue;
+                const int li = u & EQD_LN_MASK;
+                if (li >= ln || owner[li] >= 0) return __LINE__;
+                owner[li] = le;
+              }
+            }
+        for (int le = 0; le < P.tileCnt[t]; ++le) {
+          const size_t s = (size_t)P.tileElem[t] + le;
+          const int e = P.refId[s];
+          if (e < 0 || e >= Ne || seen[e]) return __LINE__;
+          seen[e] = 1;
+          for (int i = 0; i < 8; ++i) {
+            const unsigned u = P.lconn[(size_t)i * P.S + s];
+            if (P.tnode[nb + (u & EQD_LN_MASK)] != conn[8 * (size_t)e + i]) return __LINE__;
+            if ((int)(u >> EQD_LN_BITS) >= P.tileColours[t]) return __LINE__;
+          }
+        }
+      }
+    }
+    for (int e = 0; e < Ne; ++e) if (!seen[e]) return __LINE__;
+  } catch (const std::exception&) {
+    return __LINE__;
+  }
+  return 0;
+}

@@ -1,0 +1,42 @@
+// Host-side tile planner of the step library: cuts one element class into
+// bricks ("tiles") that one CTA sweeps and assembles in shared memory
+// (eqd_kernels.cu: k_tile_reg / k_tile_pml).  Pure index work on the
+// reference's connectivity (nodeElemIdRelation, meshgen.f90:702-741); it never
+// changes which nodes an element touches, only where the element is stored.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace eqd {
+
+struct TilePlan {
+  int n = 0;        // elements of the class
+  int S = 0;        // padded slot count (SoA row length)
+  int nTiles = 0;
+  int LS = 0;       // max nodes of a tile (shared-memory row stride)
+  int PFS = 0;      // padded total of tile-node slots (row length of the partial buffer)
+  std::vector<int> refId;          // [S] slot -> reference element id (0-based), -1 = padding
+  std::vector<int> tileElem;       // [nTiles] first slot (multiple of 32)
+  std::vector<int> tileCnt;        // [nTiles] elements
+  std::vector<int> tileNode;       // [nTiles+1] first tile-node slot (multiple of 4)
+  std::vector<uint8_t> tileColours;  // [nTiles] colours per assembly phase (1 = conflict free)
+  std::vector<int> tnode;          // [PFS] node id per tile-node slot, ascending inside a tile, -1 = padding
+  std::vector<uint16_t> lconn;     // [8][S] tile-local node | colour << 12
+};
+
+struct TileShape {
+  int bx = 4, bz = 4, by = 32;  // target brick, in elements, along the x / z / y grid axes
+  int capE = 640;               // hard cap on elements per tile
+  int capN = 1280;              // hard cap on nodes per tile (< 4096: 12-bit local ids)
+};
+
+// Node-grid strides of the structured part of the mesh, inferred from a plain
+// brick's connectivity: node id = ix*ny*nz + iz*ny + iy (meshgen.f90:64-107).
+// Returns false when no brick reveals them (tiles then follow storage order).
+bool infer_grid(const int* conn, const int* etype, int Ne, int Nn, int& ny, int& nz);
+
+// elems: the class's reference element ids, ascending.  conn: (8,Ne) 0-based.
+void plan_tiles(const int* conn, const std::vector<int>& elems, int Nn, int ny, int nz, bool gridOk,
+                const TileShape& shape, int threadsPerTile, TilePlan& out);
+
+}  // namespace eqd

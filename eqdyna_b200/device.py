@@ -21,10 +21,11 @@ T_TOTAL, T_NODE, T_ELEM, T_ASSEMBLE, T_HALO, T_FAULT, T_ELEM_PML, T_ELEM_REGX, T
 EXPORTS = [
     "eqd_create", "eqd_destroy", "eqd_last_error", "eqd_set_mesh", "eqd_set_elem_ops", "eqd_set_nodal",
     "eqd_set_fault", "eqd_set_halo", "eqd_set_stations", "eqd_get_unique_id", "eqd_set_comm", "eqd_sum_shared",
-    "eqd_run", "eqd_run_group", "eqd_fetch", "eqd_get_counts", "eqd_get_timing", "eqd_set_option",
+    "eqd_run", "eqd_run_group", "eqd_fetch", "eqd_get_counts", "eqd_get_timing", "eqd_set_option", "eqd_plan_check",
 ]
 
 _lib = None
+EQD_ERR_ARG = 4
 
 
 class StepError(RuntimeError):
@@ -60,6 +61,7 @@ def lib():
         L.eqd_get_counts.argtypes = [vp] + [C.POINTER(i64)] * 4
         L.eqd_get_timing.argtypes = [vp, C.POINTER(C.c_double)]
         L.eqd_set_option.argtypes = [vp, cp, i32]
+        L.eqd_plan_check.argtypes = [i32, i32, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -76,6 +78,19 @@ def unique_id():
     if rc:
         raise StepError(rc, "eqd_get_unique_id failed (NCCL not loadable?)")
     return bytes(buf)
+
+
+def plan_check(view):
+    """Run the tile planner on a sub-domain's connectivity on the host (no GPU) and
+    verify its invariants; returns per-class statistics."""
+    r = view.raw
+    st = np.zeros(24, dtype=np.int64)
+    rc = lib().eqd_plan_check(r.Nn, r.Ne, _ptr(view.nodeElemIdRelation), _ptr(view.elemTypeArr),
+                              _ptr(view.numOfDofPerNodeArr), _ptr(st))
+    if rc:
+        raise StepError(EQD_ERR_ARG, "tile planner invariant violated (eqd_tiles.cu:%d)" % rc)
+    keys = ("tiles", "elements", "slots", "node_slots", "max_tile_nodes", "max_colours", "multi_colour_tiles", "grid")
+    return {name: dict(zip(keys, (int(x) for x in st[8 * c:8 * c + 8]))) for c, name in enumerate(("reg", "regx", "pml"))}
 
 
 class Domain:

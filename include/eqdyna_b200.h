@@ -160,6 +160,16 @@ int eqd_get_timing(const eqd_handle* h, double* ms_slots /*[EQD_T_NSLOTS]*/);
  * DESIGN.md                                                                   */
 int eqd_set_option(eqd_handle* h, const char* key, int32_t value);
 
+/* Host-only self-check of the tile planner (no GPU needed): cuts the given
+ * connectivity (nodeElemIdRelation(8,Ne), 1-based, meshgen.f90:702-741) into the
+ * tiles the element kernels sweep and replays their shared-memory assembly
+ * schedule looking for write conflicts.  stats[24]: per class (regular,
+ * regular-on-PML-node, PML) tiles, elements, padded slots, tile-node slots,
+ * max tile nodes, max colours, multi-colour tiles, grid inferred.  0 = ok.    */
+int eqd_plan_check(int32_t Nn, int32_t Ne, const int32_t* nodeElemIdRelation,
+                   const int32_t* elemTypeArr, const int32_t* numOfDofPerNodeArr,
+                   int64_t* stats);
+
 #ifdef __cplusplus
 }
 #endif
