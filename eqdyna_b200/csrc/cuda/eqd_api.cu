@@ -110,8 +110,9 @@ struct ElemClass {
   int nTiles = 0, nFaceTiles = 0, LS = 1, PFS = 4;
   std::vector<int> refId;  // [S] slot -> reference element (0-based), -1 = padding
   std::vector<int> tileNodeH, tnodeH;
-  DevBuf<int> tileOrder, tileElem, tileCnt, tileNode, tnode;
-  DevBuf<uint8_t> tileColours;
+  std::vector<int4> tileRecH;  // planner order
+  DevBuf<int4> tileRec;        // launch order
+  DevBuf<int> tnode;
   DevBuf<uint16_t> lconn;
   DevBuf<double> shp, phi, ss, lam, mu, det, rho, vp, stress, qmem, porep, pstrain, emass, damps, pf;
   DevBuf<uint8_t> qcls;
@@ -296,8 +297,7 @@ ElemArgs eqd_handle::elemArgs(int c) const {
   const ElemClass& C = cls[c];
   ElemArgs A{};
   A.n = C.n; A.S = C.S;
-  A.tileOrder = C.tileOrder.p; A.tile0 = 0;
-  A.tileElem = C.tileElem.p; A.tileCnt = C.tileCnt.p; A.tileNode = C.tileNode.p; A.tileColours = C.tileColours.p;
+  A.tileRec = C.tileRec.p; A.tile0 = 0; A.ntiles = C.nTiles;
   A.tnode = C.tnode.p; A.lconn = C.lconn.p; A.LS = C.LS; A.pf = C.pf.p; A.PFS = C.PFS;
   A.shp = C.shp.p; A.phi = C.phi.p; A.ss = C.ss.p;
   A.lam = C.lam.p; A.mu = C.mu.p; A.det = C.det.p; A.rho = C.rho.p; A.vp = C.vp.p;
@@ -505,17 +505,17 @@ void step_pre(eqd_handle* h) {
   if (h->dAccel0.p) { CK(cudaStreamSynchronize(s)); h->dAccel0.release(); }
   if (h->cls[CLS_REG].n) {
     Timer t(h, EQD_T_ELEM);
-    launch_elem_reg(h->elemArgs(CLS_REG), h->cls[CLS_REG].nTiles, false, h->plastic, h->qmode, h->body, P.C_hg, s); h->launches++;
+    launch_elem_reg(h->elemArgs(CLS_REG), false, h->plastic, h->qmode, h->body, P.C_hg, s); h->launches++;
     t.stop();
   }
   if (h->cls[CLS_REGX].n) {
     Timer t(h, EQD_T_ELEM_REGX);
-    launch_elem_reg(h->elemArgs(CLS_REGX), h->cls[CLS_REGX].nTiles, true, h->plastic, h->qmode, h->body, P.C_hg, s); h->launches++;
+    launch_elem_reg(h->elemArgs(CLS_REGX), true, h->plastic, h->qmode, h->body, P.C_hg, s); h->launches++;
     t.stop();
   }
   if (h->cls[CLS_PML].n) {
     Timer t(h, EQD_T_ELEM_PML);
-    launch_elem_pml(h->elemArgs(CLS_PML), h->cls[CLS_PML].nTiles, h->body, P.C_hg, s); h->launches++;
+    launch_elem_pml(h->elemArgs(CLS_PML), h->body, P.C_hg, s); h->launches++;
     t.stop();
   }
   {
@@ -710,20 +710,22 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
       ElemClass& C = h->cls[c];
       TileShape sh;
       if (c == CLS_PML) { sh.bx = 3; sh.bz = 3; sh.by = 32; sh.capE = 384; sh.capN = 800; }
+      else { sh.bx = 4; sh.bz = 4; sh.by = 16; sh.capE = 384; sh.capN = h->qmode ? 336 : 420; }  // two CTAs per SM
       TilePlan T;
       plan_tiles(h->conn.data(), members[c], Nn, gny, gnz, gridOk, sh, EQD_TILE_THREADS, T);
       C.n = T.n; C.S = T.S; C.nf = nf[c]; C.nstress = nstr[c];
       C.nTiles = T.nTiles; C.nFaceTiles = 0; C.LS = T.LS; C.PFS = T.PFS;
-      need((size_t)tile_rows(c, h->qmode) * C.LS * sizeof(double) <= 227 * 1024 - 1024, "eqd_set_mesh: tile does not fit shared memory");
+      need(tile_smem_bytes(c, h->qmode, C.LS) <= 227 * 1024, "eqd_set_mesh: tile does not fit shared memory");
       C.refId = T.refId;
       for (int s = 0; s < C.S; ++s) if (C.refId[s] >= 0) h->elemCode[C.refId[s]] = c | (s << 2);
       C.tileNodeH = T.tileNode; C.tnodeH = T.tnode;
       if (!C.n) continue;
-      std::vector<int> ord(C.nTiles);
-      for (int t = 0; t < C.nTiles; ++t) ord[t] = t;
-      C.tileOrder.upload(ord);
-      C.tileElem.upload(T.tileElem); C.tileCnt.upload(T.tileCnt); C.tileNode.upload(T.tileNode);
-      C.tileColours.upload(T.tileColours); C.tnode.upload(T.tnode); C.lconn.upload(T.lconn);
+      need(c == CLS_PML || C.LS <= EQD_REG_NPT * 2 * EQD_STAGE, "eqd_set_mesh: regular tile has too many nodes");
+      C.tileRecH.resize(C.nTiles);
+      for (int t = 0; t < C.nTiles; ++t)
+        C.tileRecH[t] = make_int4(T.tileElem[t], T.tileCnt[t] | ((int)T.tileColours[t] << 16), T.tileNode[t], T.tileNode[t + 1] - T.tileNode[t]);
+      C.tileRec.upload(C.tileRecH);
+      C.tnode.upload(T.tnode); C.lconn.upload(T.lconn);
       C.pf.alloc((size_t)C.nf * C.PFS);
       C.stress.alloc((size_t)C.nstress * C.S);
       if (c == CLS_PML) {

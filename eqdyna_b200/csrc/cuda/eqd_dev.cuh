@@ -26,6 +26,8 @@
 #pragma once
 #include <cstdint>
 
+#include <vector_types.h>
+
 namespace eqd {
 
 enum { KIND_FREE3 = 0, KIND_PML12 = 1, KIND_FIXED = 2 };
@@ -38,7 +40,9 @@ enum { CLS_REG = 0, CLS_REGX = 1, CLS_PML = 2 };
 // local connectivity entry: tile-local node index (12 bits) | colour of the phase (4 bits)
 #define EQD_LN_BITS 12
 #define EQD_LN_MASK 0x0fffu
-#define EQD_TILE_THREADS 128
+#define EQD_TILE_THREADS 128   // PML tile kernel: one thread per element of a pass
+#define EQD_STAGE 128          // regular tile kernel: elements per streamed stage (two threads each)
+#define EQD_REG_NPT 2          // regular tile kernel: tile nodes handled per thread (LS <= 2 * 256)
 
 struct StepState {
   double timeElapsed;  // driver.f90:11
@@ -71,10 +75,9 @@ struct ElemArgs {
   int n, S;
   // tiles: elements of tile t are slots tileElem[t] .. tileElem[t]+tileCnt[t]-1,
   // its nodes are tnode[tileNode[t] .. tileNode[t+1]-1] (-1 = padding)
-  const int* tileOrder;  // launch order -> tile id (rank-face tiles first)
-  int tile0;             // first entry of tileOrder this launch covers
-  const int* tileElem; const int* tileCnt; const int* tileNode;
-  const uint8_t* tileColours;  // colours per phase in this tile (1 = conflict free)
+  const int4* tileRec;   // per tile in LAUNCH order (rank-face tiles first):
+                         // {first slot, elements | colours << 16, first tile-node slot, tile nodes}
+  int tile0, ntiles;     // tiles [tile0, tile0+ntiles) of tileRec belong to this launch
   const int* tnode;
   const uint16_t* lconn; // [8][S] local node | colour << 12
   int LS;                // shared-memory row stride (max tile nodes of the class)

@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#include <algorithm>
+#include <map>
 #include <mutex>
 #include <set>
 #include <utility>
@@ -219,266 +221,391 @@ __global__ void k_materialize_accel(NodeArgs A, double* __restrict__ out) {
 }
 
 // ----------------------------------------------------------------------------
+// ---- async-proxy helpers (sm_90+): 1-D bulk copies global -> shared that
+// signal an mbarrier with their byte count (SASS: UBLKCP / SYNCS)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ----------------------------------------------------------------------------
 // Tile kernels.  One CTA owns one tile (a brick of a few hundred elements of one
-// class, contiguous in the class's SoA):
+// class, contiguous in the class's SoA) and walks it in stages of EQD_STAGE
+// elements:
+//   stream   the stage's operator rows (shape derivatives, hourglass vectors
+//            and stiffness, moduli, stresses, local connectivity) arrive in
+//            shared memory through bulk asynchronous copies signalling an
+//            mbarrier; the next stage is requested as soon as the current one
+//            has been consumed, so HBM latency hides behind the assembly phases
+//            and the second CTA of the SM
 //   stage    the tile's nodes: v and d + rdampk*v (hrglss.f90:20-27) -> shared
-//   sweep    one thread per element (EQD_TILE_THREADS at a time): operators
-//            stream from HBM straight into registers, nodal values come from
-//            shared memory
+//   sweep    two threads per element: warps 0-3 do the constitutive part
+//            (calcElemKU), warps 4-7 the hourglass part (hrglss) of the same
+//            EQD_STAGE elements
 //   assemble 8 local-node phases; in phase i every element adds its force on
-//            local node i to the tile's shared force rows.  Two elements of one
-//            phase never touch the same node in a structured hexahedral brick;
-//            where they do (wedge pairs) the host gave them different colours
-//            and the phase is split.  Plain read-modify-write, no atomics: the
-//            summation order is fixed.
+//            local node i to the tile's shared force rows (one set per role).
+//            Two elements of one phase never touch the same node in a
+//            structured hexahedral brick; where they do (wedge pairs) the host
+//            gave them different colours and the phase is split.  Plain
+//            read-modify-write, no atomics: the summation order is fixed.
 //   flush    one partial force row per tile node -> pf (coalesced)
-struct TileCtx {
-  int e0, ne, nb, LN, NC;
-};
-__device__ __forceinline__ TileCtx tile_ctx(const ElemArgs& A) {
-  TileCtx T;
-  const int t = LDG(A.tileOrder + A.tile0 + blockIdx.x);
-  T.e0 = LDG(A.tileElem + t);
-  T.ne = LDG(A.tileCnt + t);
-  T.nb = LDG(A.tileNode + t);
-  T.LN = LDG(A.tileNode + t + 1) - T.nb;
-  T.NC = LDG(A.tileColours + t);
-  return T;
+// tile record (int4): first element slot, elements | colours << 16, first tile-node slot, tile nodes
+#define TR_E0(r) ((r).x)
+#define TR_NE(r) ((r).y & 0xffff)
+#define TR_NC(r) ((r).y >> 16)
+#define TR_NB(r) ((r).z)
+#define TR_LN(r) ((r).w)
+
+// operator rows of one regular-element stage, in shared-memory order
+enum { RR_SHP = 0, RR_PHI = 24, RR_SS = 56, RR_LAM = 62, RR_MU = 63, RR_DET = 64, RR_STRESS = 65, RR_ROWS = 71 };
+__device__ __forceinline__ const double* reg_row_src(const ElemArgs& A, int r) {
+  const size_t S = A.S;
+  if (r < RR_PHI) return A.shp + (size_t)r * S;
+  if (r < RR_SS) return A.phi + (size_t)(r - RR_PHI) * S;
+  if (r < RR_LAM) return A.ss + (size_t)(r - RR_SS) * S;
+  if (r == RR_LAM) return A.lam;
+  if (r == RR_MU) return A.mu;
+  if (r == RR_DET) return A.det;
+  return A.stress + (size_t)(r - RR_STRESS) * S;
 }
 
 // Regular hexahedron / degenerate wedge: calcElemKU.f90:3-191 (+ calcB.f90,
-// calcElemMass.f90) fused with hrglss.f90:13-98.  The 6x24 B matrix is never
+// calcElemMass.f90) and hrglss.f90:13-98.  The 6x24 B matrix is never
 // materialised.
 template <bool PLASTIC, bool QMODE, bool BODY, bool SPLIT, int CHG>
-__global__ void __launch_bounds__(EQD_TILE_THREADS, 2) k_tile_reg(ElemArgs A) {
-  extern __shared__ double sm[];
-  constexpr int NT = EQD_TILE_THREADS;
-  constexpr int NF = SPLIT ? 6 : 3;
+__global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  constexpr int SE = EQD_STAGE;
+  constexpr int NT = 2 * SE;
+  constexpr int NPT = EQD_REG_NPT;  // tile nodes per thread (LS <= NPT * NT, checked by the host)
   const int tid = threadIdx.x;
-  const TileCtx T = tile_ctx(A);
+  const int role = tid / SE;        // 0: constitutive (KU), 1: hourglass; warp-uniform
+  const int lane = tid - role * SE; // element of the stage
+  const int tEnd = A.tile0 + A.ntiles;
+  int tnext = A.tile0 + blockIdx.x;
+  if (tnext >= tEnd) return;
   const int LS = A.LS;
   const size_t S = A.S, NS = A.NnS;
   const double dt = A.dt, rdampk = A.rdampk;
-  double* sv = sm;                          // [3][LS] velocity
-  double* sl = sm + 3 * LS;                 // [3][LS] d + rdampk*v
-  double* sd = sm + 6 * LS;                 // [3][LS] displacement (Q only)
-  double* sf = sm + (QMODE ? 9 : 6) * LS;   // [NF][LS] force accumulators
-  for (int i = tid; i < T.LN; i += NT) {
-    const int nd = LDG(A.tnode + T.nb + i);
-    double vx = 0, vy = 0, vz = 0, dx = 0, dy = 0, dz = 0;
-    if (nd >= 0) {
-      vx = LDG(A.vel + nd); vy = LDG(A.vel + NS + nd); vz = LDG(A.vel + 2 * NS + nd);
-      dx = LDG(A.disp + nd); dy = LDG(A.disp + NS + nd); dz = LDG(A.disp + 2 * NS + nd);
-    }
+  uint64_t* bar = (uint64_t*)smraw;
+  double* ops = (double*)(smraw + 128);                         // [RR_ROWS][SE]
+  uint16_t* slc = (uint16_t*)(ops + RR_ROWS * SE);              // [8][SE]
+  double* sv = (double*)(slc + 8 * SE);                         // [3][LS] velocity
+  double* sl = sv + 3 * LS;                                     // [3][LS] d + rdampk*v
+  double* sd = sl + 3 * LS;                                     // [3][LS] displacement (Q only)
+  double* sf = sl + (QMODE ? 6 : 3) * LS;                       // [2][3][LS] force accumulators: KU | hourglass
+  auto request = [&](const int4& rec, int base) {
+    // one thread per row; sizes are whole 32-element groups (the class SoA is padded)
+    const int cnt = min(SE, (TR_NE(rec) - base + 31) & ~31);
+    if (tid == 0) mbar_expect_tx(bar, (uint32_t)(cnt * (RR_ROWS * 8 + 8 * 2)));
+    __syncwarp();
+    if (tid < RR_ROWS) bulk_g2s(ops + tid * SE, reg_row_src(A, tid) + TR_E0(rec) + base, cnt * 8, bar);
+    else if (tid < RR_ROWS + 8) bulk_g2s(slc + (tid - RR_ROWS) * SE, A.lconn + (size_t)(tid - RR_ROWS) * S + TR_E0(rec) + base, cnt * 2, bar);
+  };
+  auto put_node = [&](int i, double vx, double vy, double vz, double dx, double dy, double dz) {
     sv[i] = vx; sv[LS + i] = vy; sv[2 * LS + i] = vz;
     sl[i] = dx + rdampk * vx; sl[LS + i] = dy + rdampk * vy; sl[2 * LS + i] = dz + rdampk * vz;
     if (QMODE) { sd[i] = dx; sd[LS + i] = dy; sd[2 * LS + i] = dz; }
+  };
+  const int4 zero4 = make_int4(0, 0, 0, 0);
+  // software pipeline over this CTA's tiles: rc = tile being swept, rn = the next
+  // one (its operators and nodes are requested while rc's forces are assembled)
+  int4 rc = __ldg(A.tileRec + tnext);
+  tnext += gridDim.x;
+  int4 rn = tnext < tEnd ? __ldg(A.tileRec + tnext) : zero4;
+  if (tid == 0) mbar_init(bar, 1);
+  __syncthreads();
+  request(rc, 0);
 #pragma unroll
-    for (int j = 0; j < NF; ++j) sf[j * LS + i] = 0.0;
+  for (int k = 0; k < NPT; ++k) {
+    const int i = tid + k * NT;
+    if (i < LS) {
+      const int nd = i < TR_LN(rc) ? LDG(A.tnode + TR_NB(rc) + i) : -1;
+      double vx = 0, vy = 0, vz = 0, dx = 0, dy = 0, dz = 0;
+      if (nd >= 0) {
+        vx = LDG(A.vel + nd); vy = LDG(A.vel + NS + nd); vz = LDG(A.vel + 2 * NS + nd);
+        dx = LDG(A.disp + nd); dy = LDG(A.disp + NS + nd); dz = LDG(A.disp + 2 * NS + nd);
+      }
+      put_node(i, vx, vy, vz, dx, dy, dz);
+#pragma unroll
+      for (int j = 0; j < 6; ++j) sf[j * LS + i] = 0.0;
+    }
   }
   __syncthreads();
-  for (int base = 0; base < T.ne; base += NT) {
-    const int le = base + tid;
-    const bool act = le < T.ne;
-    const size_t e = (size_t)T.e0 + (act ? le : 0);
+  double* acc = sf + role * 3 * LS;
+  uint32_t parity = 0;
+  while (true) {
+  const bool more = tnext < tEnd;
+  // node ids of the next tile (used when rc's last stage has been consumed) and the record after it
+  int nn[NPT];
+#pragma unroll
+  for (int k = 0; k < NPT; ++k) {
+    const int i = tid + k * NT;
+    nn[k] = (more && i < TR_LN(rn)) ? LDG(A.tnode + TR_NB(rn) + i) : -1;
+  }
+  const int4 rnn = (tnext + (int)gridDim.x < tEnd) ? __ldg(A.tileRec + tnext + gridDim.x) : zero4;
+  double pv[NPT][6];
+  const int ne = TR_NE(rc), NC = TR_NC(rc);
+  for (int base = 0; base < ne; base += SE) {
+    const int le = base + lane;
+    const bool act = le < ne;
+    const size_t e = (size_t)TR_E0(rc) + (act ? le : 0);
     unsigned lc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double f[8][3];
-    double hf[SPLIT ? 8 : 1][3];
+    mbar_wait(bar, parity);
+    parity ^= 1;
     if (act) {
-      double sr[6] = {0, 0, 0, 0, 0, 0}, sn[6] = {0, 0, 0, 0, 0, 0};
-      double phid[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-      double qv[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};  // viscous hourglass (C_hg==2)
-      double shp[8][3];
-      double ph[CHG == 1 ? 4 : 1][8];
-      double body[BODY ? 24 : 1];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        lc[i] = LDG(A.lconn + i * S + e);
-        shp[i][0] = LDG(A.shp + (3 * i) * S + e); shp[i][1] = LDG(A.shp + (3 * i + 1) * S + e); shp[i][2] = LDG(A.shp + (3 * i + 2) * S + e);
-        if (CHG == 1) {
+      for (int i = 0; i < 8; ++i) lc[i] = slc[i * SE + lane];
+#define OP(r) ops[(r) * SE + lane]
+      if (role == 0) {
+        // ---------------- constitutive part: calcElemKU.f90
+        double sr[6] = {0, 0, 0, 0, 0, 0}, sn[6] = {0, 0, 0, 0, 0, 0};
+        double body[BODY ? 24 : 1];
 #pragma unroll
-          for (int m = 0; m < 4; ++m) ph[m][i] = LDG(A.phi + (8 * m + i) * S + e);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int li = lc[i] & EQD_LN_MASK;
-        const double vx = sv[li], vy = sv[LS + li], vz = sv[2 * LS + li];
-        const double s1 = shp[i][0], s2 = shp[i][1], s3 = shp[i][2];
-        // calcElemKU.f90:44-60 (B with engineering shear, calcB.f90:10-25)
-        sr[0] = sr[0] + s1 * vx;
-        sr[1] = sr[1] + s2 * vy;
-        sr[2] = sr[2] + s3 * vz;
-        sr[3] = sr[3] + s3 * vy + s2 * vz;
-        sr[4] = sr[4] + s3 * vx + s1 * vz;
-        sr[5] = sr[5] + s2 * vx + s1 * vy;
-        if (QMODE) {
-          const double dx = sd[li], dy = sd[LS + li], dz = sd[2 * LS + li];
-          sn[0] = sn[0] + s1 * dx;
-          sn[1] = sn[1] + s2 * dy;
-          sn[2] = sn[2] + s3 * dz;
-          sn[3] = sn[3] + s3 * dy + s2 * dz;
-          sn[4] = sn[4] + s3 * dx + s1 * dz;
-          sn[5] = sn[5] + s2 * dx + s1 * dy;
-        }
-        if (CHG == 1) {
-          // hrglss.f90:20-33: dl = d + rdampk*v ; phid = sum_j phi(j,m)*dl(j)
-          const double lx = sl[li], ly = sl[LS + li], lz = sl[2 * LS + li];
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            const double p = ph[m][i];
-            phid[m][0] = phid[m][0] + p * lx;
-            phid[m][1] = phid[m][1] + p * ly;
-            phid[m][2] = phid[m][2] + p * lz;
+        for (int i = 0; i < 8; ++i) {
+          const int li = lc[i] & EQD_LN_MASK;
+          const double vx = sv[li], vy = sv[LS + li], vz = sv[2 * LS + li];
+          const double s1 = OP(RR_SHP + 3 * i), s2 = OP(RR_SHP + 3 * i + 1), s3 = OP(RR_SHP + 3 * i + 2);
+          // calcElemKU.f90:44-60 (B with engineering shear, calcB.f90:10-25)
+          sr[0] = sr[0] + s1 * vx;
+          sr[1] = sr[1] + s2 * vy;
+          sr[2] = sr[2] + s3 * vz;
+          sr[3] = sr[3] + s3 * vy + s2 * vz;
+          sr[4] = sr[4] + s3 * vx + s1 * vz;
+          sr[5] = sr[5] + s2 * vx + s1 * vy;
+          if (QMODE) {
+            const double dx = sd[li], dy = sd[LS + li], dz = sd[2 * LS + li];
+            sn[0] = sn[0] + s1 * dx;
+            sn[1] = sn[1] + s2 * dy;
+            sn[2] = sn[2] + s3 * dz;
+            sn[3] = sn[3] + s3 * dy + s2 * dz;
+            sn[4] = sn[4] + s3 * dx + s1 * dz;
+            sn[5] = sn[5] + s2 * dx + s1 * dy;
           }
-        } else if (CHG == 2) {
-          // hrglss.f90:57-70
-          const int fi[4][8] = {{1, 1, -1, -1, -1, -1, 1, 1}, {1, -1, -1, 1, -1, 1, 1, -1},
-                                {1, -1, 1, -1, 1, -1, 1, -1}, {1, -1, 1, -1, -1, 1, -1, 1}};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            qv[0][j] = qv[0][j] + vx * fi[j][i];
-            qv[1][j] = qv[1][j] + vy * fi[j][i];
-            qv[2][j] = qv[2][j] + vz * fi[j][i];
+          if (BODY) {
+            // assembleGlobalKU.f90:15-16 + calcElemMass.f90: elresf = -al*elemass
+            const double em = LDG(A.emass + i * S + e);
+            body[3 * i] = 0.0 - (A.rdampm * vx) * em;
+            body[3 * i + 1] = 0.0 - (A.rdampm * vy) * em;
+            body[3 * i + 2] = 0.0 - (A.rdampm * vz + A.bodyz) * em;
           }
         }
-        if (BODY) {
-          // assembleGlobalKU.f90:15-16 + calcElemMass.f90: elresf = -al*elemass
-          const double em = LDG(A.emass + i * S + e);
-          body[3 * i] = 0.0 - (A.rdampm * vx) * em;
-          body[3 * i + 1] = 0.0 - (A.rdampm * vy) * em;
-          body[3 * i + 2] = 0.0 - (A.rdampm * vz + A.bodyz) * em;
-        }
-      }
-      const double lam = LDG(A.lam + e), mu = LDG(A.mu + e);
-      const double l2m = lam + 2 * mu;
-      double rate[6];
-      // calcElemKU.f90:63-70
-      rate[0] = 0.0 + l2m * sr[0] + lam * sr[1] + lam * sr[2];
-      rate[1] = 0.0 + lam * sr[0] + l2m * sr[1] + lam * sr[2];
-      rate[2] = 0.0 + lam * sr[0] + lam * sr[1] + l2m * sr[2];
-      rate[3] = mu * sr[3];
-      rate[4] = mu * sr[4];
-      rate[5] = mu * sr[5];
-      double sg[6];
-      if (!QMODE) {
+        const double lam = OP(RR_LAM), mu = OP(RR_MU);
+        const double l2m = lam + 2 * mu;
+        double rate[6];
+        // calcElemKU.f90:63-70
+        rate[0] = 0.0 + l2m * sr[0] + lam * sr[1] + lam * sr[2];
+        rate[1] = 0.0 + lam * sr[0] + l2m * sr[1] + lam * sr[2];
+        rate[2] = 0.0 + lam * sr[0] + lam * sr[1] + l2m * sr[2];
+        rate[3] = mu * sr[3];
+        rate[4] = mu * sr[4];
+        rate[5] = mu * sr[5];
+        double sg[6];
+        if (!QMODE) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) sg[i] = A.stress[i * S + e] + rate[i] * dt;  // :72-76
-      } else {
-        // calcElemKU.f90:77-132, constants tabulated per class (qconstant.f90)
-        const QTab q = c_qtab[A.qcls[e]];
-        const double miuu = mu * q.cs, Mu = l2m * q.cv;
-        const double vols = sn[0] + sn[1] + sn[2];
-        const double ex = q.expdt;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          const double a1 = A.qmem[i * S + e];
-          double an;
-          if (i < 3) an = ex * a1 + (1 - ex) * (2 * miuu * sn[i] * q.wks + (Mu * q.wkp - 2 * miuu * q.wks) * vols);
-          else an = ex * a1 + (1 - ex) * (miuu * sn[i] * q.wks);
-          A.qmem[i * S + e] = an;
-          if (i < 3) sg[i] = 2.0 * miuu * sn[i] + (Mu - 2.0 * miuu) * vols - 0.5 * (an + a1);
-          else sg[i] = 2.0 * miuu * sn[i] / 2.0 - 0.5 * (an + a1);
-        }
-      }
-      if (PLASTIC) {
-        // Drucker-Prager viscoplasticity, calcElemKU.f90:133-167
-        const double strmea = (sg[0] + sg[1] + sg[2]) / 3.0;
-        double dv[6] = {sg[0] - strmea, sg[1] - strmea, sg[2] - strmea, sg[3], sg[4], sg[5]};
-        double taomax = 0.5 * (dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]) + dv[3] * dv[3] + dv[4] * dv[4] + dv[5] * dv[5];
-        taomax = sqrt(taomax);
-        double yield = A.ccosphi - A.sinphi * (strmea + LDG(A.porep + e));
-        if (yield < 0.0) yield = 0.0;
-        if (taomax > yield) {
-          const double rjust = yield / taomax + (1 - yield / taomax) * A.expdttv;
-          double pi[6];
+          for (int i = 0; i < 6; ++i) sg[i] = OP(RR_STRESS + i) + rate[i] * dt;  // :72-76
+        } else {
+          // calcElemKU.f90:77-132, constants tabulated per class (qconstant.f90)
+          const QTab q = c_qtab[A.qcls[e]];
+          const double miuu = mu * q.cs, Mu = l2m * q.cv;
+          const double vols = sn[0] + sn[1] + sn[2];
+          const double ex = q.expdt;
 #pragma unroll
           for (int i = 0; i < 6; ++i) {
-            sg[i] = dv[i] * rjust;
-            pi[i] = (dv[i] - sg[i]) / mu;
-            if (i < 3) sg[i] = sg[i] + strmea;
+            const double a1 = A.qmem[i * S + e];
+            double an;
+            if (i < 3) an = ex * a1 + (1 - ex) * (2 * miuu * sn[i] * q.wks + (Mu * q.wkp - 2 * miuu * q.wks) * vols);
+            else an = ex * a1 + (1 - ex) * (miuu * sn[i] * q.wks);
+            A.qmem[i * S + e] = an;
+            if (i < 3) sg[i] = 2.0 * miuu * sn[i] + (Mu - 2.0 * miuu) * vols - 0.5 * (an + a1);
+            else sg[i] = 2.0 * miuu * sn[i] / 2.0 - 0.5 * (an + a1);
           }
-          const double pm = (pi[0] + pi[1] + pi[2]) / 3.0;
-#pragma unroll
-          for (int i = 0; i < 6; ++i) pi[i] = pi[i] - pm;
-          double mag = 0.5 * (pi[0] * pi[0] + pi[1] * pi[1] + pi[2] * pi[2]) + pi[3] * pi[3] + pi[4] * pi[4] + pi[5] * pi[5];
-          A.pstrain[e] = A.pstrain[e] + sqrt(mag);   // assembleGlobalKU.f90:26
         }
-      }
+        if (PLASTIC) {
+          // Drucker-Prager viscoplasticity, calcElemKU.f90:133-167
+          const double strmea = (sg[0] + sg[1] + sg[2]) / 3.0;
+          double dv[6] = {sg[0] - strmea, sg[1] - strmea, sg[2] - strmea, sg[3], sg[4], sg[5]};
+          double taomax = 0.5 * (dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2]) + dv[3] * dv[3] + dv[4] * dv[4] + dv[5] * dv[5];
+          taomax = sqrt(taomax);
+          double yield = A.ccosphi - A.sinphi * (strmea + LDG(A.porep + e));
+          if (yield < 0.0) yield = 0.0;
+          if (taomax > yield) {
+            const double rjust = yield / taomax + (1 - yield / taomax) * A.expdttv;
+            double pi[6];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) A.stress[i * S + e] = sg[i];
-      // calcElemKU.f90:169-173, constk = -eledet
-      const double det = LDG(A.det + e);
-      const double temp = (-det) * A.w;
-      double t[6];
+            for (int i = 0; i < 6; ++i) {
+              sg[i] = dv[i] * rjust;
+              pi[i] = (dv[i] - sg[i]) / mu;
+              if (i < 3) sg[i] = sg[i] + strmea;
+            }
+            const double pm = (pi[0] + pi[1] + pi[2]) / 3.0;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) t[i] = temp * (sg[i] + rdampk * rate[i]);
-      double hv[4][3];
-      double coef = 0.0;
-      if (CHG == 1) {
-        double ssv[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) ssv[i] = LDG(A.ss + i * S + e);
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {  // hrglss.f90:35-40
-          hv[m][0] = ssv[0] * phid[m][0] + ssv[1] * phid[m][1] + ssv[2] * phid[m][2];
-          hv[m][1] = ssv[1] * phid[m][0] + ssv[3] * phid[m][1] + ssv[4] * phid[m][2];
-          hv[m][2] = ssv[2] * phid[m][0] + ssv[4] * phid[m][1] + ssv[5] * phid[m][2];
+            for (int i = 0; i < 6; ++i) pi[i] = pi[i] - pm;
+            double mag = 0.5 * (pi[0] * pi[0] + pi[1] * pi[1] + pi[2] * pi[2]) + pi[3] * pi[3] + pi[4] * pi[4] + pi[5] * pi[5];
+            A.pstrain[e] = A.pstrain[e] + sqrt(mag);   // assembleGlobalKU.f90:26
+          }
         }
-      } else if (CHG == 2) {
-        coef = 0.25 * A.kapa_hg * LDG(A.rho + e) * LDG(A.vp + e) * pow(det * A.w, 2.0 / 3.0);
-      }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const double s1 = shp[i][0], s2 = shp[i][1], s3 = shp[i][2];
-        // calcElemKU.f90:175-189
-        double f0 = s1 * t[0] + s3 * t[4] + s2 * t[5];
-        double f1 = s2 * t[1] + s3 * t[3] + s1 * t[5];
-        double f2 = s3 * t[2] + s2 * t[3] + s1 * t[4];
-        if (BODY) { f0 = body[3 * i] + f0; f1 = body[3 * i + 1] + f1; f2 = body[3 * i + 2] + f2; }
-        double h0 = 0.0, h1 = 0.0, h2 = 0.0;
+        for (int i = 0; i < 6; ++i) A.stress[i * S + e] = sg[i];
+        // calcElemKU.f90:169-173, constk = -eledet
+        const double temp = (-OP(RR_DET)) * A.w;
+        double t[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) t[i] = temp * (sg[i] + rdampk * rate[i]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const double s1 = OP(RR_SHP + 3 * i), s2 = OP(RR_SHP + 3 * i + 1), s3 = OP(RR_SHP + 3 * i + 2);
+          // calcElemKU.f90:175-189
+          double f0 = s1 * t[0] + s3 * t[4] + s2 * t[5];
+          double f1 = s2 * t[1] + s3 * t[3] + s1 * t[5];
+          double f2 = s3 * t[2] + s2 * t[3] + s1 * t[4];
+          if (BODY) { f0 = body[3 * i] + f0; f1 = body[3 * i + 1] + f1; f2 = body[3 * i + 2] + f2; }
+          f[i][0] = f0; f[i][1] = f1; f[i][2] = f2;
+        }
+      } else {
+        // ---------------- hourglass part: hrglss.f90
         if (CHG == 1) {
+          double phid[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
 #pragma unroll
-          for (int m = 0; m < 4; ++m) {  // hrglss.f90:41-54: force -= phi(i,m)*(SS.phid)
-            const double p = ph[m][i];
-            h0 = h0 - p * hv[m][0];
-            h1 = h1 - p * hv[m][1];
-            h2 = h2 - p * hv[m][2];
+          for (int i = 0; i < 8; ++i) {
+            const int li = lc[i] & EQD_LN_MASK;
+            // hrglss.f90:20-33: dl = d + rdampk*v ; phid = sum_j phi(j,m)*dl(j)
+            const double lx = sl[li], ly = sl[LS + li], lz = sl[2 * LS + li];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const double p = OP(RR_PHI + 8 * m + i);
+              phid[m][0] = phid[m][0] + p * lx;
+              phid[m][1] = phid[m][1] + p * ly;
+              phid[m][2] = phid[m][2] + p * lz;
+            }
           }
-        } else if (CHG == 2) {
+          double ssv[6], hv[4][3];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) ssv[i] = OP(RR_SS + i);
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {  // hrglss.f90:35-40
+            hv[m][0] = ssv[0] * phid[m][0] + ssv[1] * phid[m][1] + ssv[2] * phid[m][2];
+            hv[m][1] = ssv[1] * phid[m][0] + ssv[3] * phid[m][1] + ssv[4] * phid[m][2];
+            hv[m][2] = ssv[2] * phid[m][0] + ssv[4] * phid[m][1] + ssv[5] * phid[m][2];
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            double h0 = 0.0, h1 = 0.0, h2 = 0.0;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {  // hrglss.f90:41-54: force -= phi(i,m)*(SS.phid)
+              const double p = OP(RR_PHI + 8 * m + i);
+              h0 = h0 - p * hv[m][0];
+              h1 = h1 - p * hv[m][1];
+              h2 = h2 - p * hv[m][2];
+            }
+            f[i][0] = h0; f[i][1] = h1; f[i][2] = h2;
+          }
+        } else {
+          // viscous hourglass, hrglss.f90:57-80
           const int fi[4][8] = {{1, 1, -1, -1, -1, -1, 1, 1}, {1, -1, -1, 1, -1, 1, 1, -1},
                                 {1, -1, 1, -1, 1, -1, 1, -1}, {1, -1, 1, -1, -1, 1, -1, 1}};
+          double qv[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {  // hrglss.f90:71-80
-            h0 = h0 - coef * qv[0][j] * fi[j][i];
-            h1 = h1 - coef * qv[1][j] * fi[j][i];
-            h2 = h2 - coef * qv[2][j] * fi[j][i];
+          for (int i = 0; i < 8; ++i) {
+            const int li = lc[i] & EQD_LN_MASK;
+            const double vx = sv[li], vy = sv[LS + li], vz = sv[2 * LS + li];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              qv[0][j] = qv[0][j] + vx * fi[j][i];
+              qv[1][j] = qv[1][j] + vy * fi[j][i];
+              qv[2][j] = qv[2][j] + vz * fi[j][i];
+            }
+          }
+          const double coef = 0.25 * A.kapa_hg * LDG(A.rho + e) * LDG(A.vp + e) * pow(OP(RR_DET) * A.w, 2.0 / 3.0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            double h0 = 0.0, h1 = 0.0, h2 = 0.0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              h0 = h0 - coef * qv[0][j] * fi[j][i];
+              h1 = h1 - coef * qv[1][j] * fi[j][i];
+              h2 = h2 - coef * qv[2][j] * fi[j][i];
+            }
+            f[i][0] = h0; f[i][1] = h1; f[i][2] = h2;
           }
         }
-        if (SPLIT) {
-          f[i][0] = f0; f[i][1] = f1; f[i][2] = f2;
-          hf[i][0] = h0; hf[i][1] = h1; hf[i][2] = h2;
-        } else {
-          f[i][0] = f0 + h0; f[i][1] = f1 + h1; f[i][2] = f2 + h2;
+      }
+#undef OP
+    }
+    // the stage buffer is consumed: request the next stage (or the next tile's first
+    // one, and its nodal values into registers); they land while the forces are assembled
+    __syncthreads();
+    const bool last = base + SE >= ne;
+    if (!last) request(rc, base + SE);
+    else if (more) {
+      request(rn, 0);
+#pragma unroll
+      for (int k = 0; k < NPT; ++k) {
+        const int nd = nn[k];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) pv[k][j] = 0.0;
+        if (nd >= 0) {
+          pv[k][0] = LDG(A.vel + nd); pv[k][1] = LDG(A.vel + NS + nd); pv[k][2] = LDG(A.vel + 2 * NS + nd);
+          pv[k][3] = LDG(A.disp + nd); pv[k][4] = LDG(A.disp + NS + nd); pv[k][5] = LDG(A.disp + 2 * NS + nd);
         }
       }
     }
-    // ---- ordered assembly into the tile's shared force rows
+    // ---- ordered assembly into the tile's shared force rows (one set per role)
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int li = lc[i] & EQD_LN_MASK, col = lc[i] >> EQD_LN_BITS;
-      for (int c = 0; c < T.NC; ++c) {
-        if (act && col == c) {
-          sf[li] += f[i][0]; sf[LS + li] += f[i][1]; sf[2 * LS + li] += f[i][2];
-          if (SPLIT) { sf[3 * LS + li] += hf[i][0]; sf[4 * LS + li] += hf[i][1]; sf[5 * LS + li] += hf[i][2]; }
-        }
+      for (int c = 0; c < NC; ++c) {
+        if (act && col == c) { acc[li] += f[i][0]; acc[LS + li] += f[i][1]; acc[2 * LS + li] += f[i][2]; }
         __syncthreads();
       }
     }
   }
-  for (int i = tid; i < T.LN; i += NT) {
+  // ---- flush the tile's partial forces; hand the node rows over to the next tile
 #pragma unroll
-    for (int j = 0; j < NF; ++j) A.pf[(size_t)j * A.PFS + T.nb + i] = sf[j * LS + i];
+  for (int k = 0; k < NPT; ++k) {
+    const int i = tid + k * NT;
+    if (i < LS) {
+      if (i < TR_LN(rc)) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          if (SPLIT) {
+            A.pf[(size_t)j * A.PFS + TR_NB(rc) + i] = sf[j * LS + i];
+            A.pf[(size_t)(3 + j) * A.PFS + TR_NB(rc) + i] = sf[(3 + j) * LS + i];
+          } else {
+            A.pf[(size_t)j * A.PFS + TR_NB(rc) + i] = sf[j * LS + i] + sf[(3 + j) * LS + i];
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 6; ++j) sf[j * LS + i] = 0.0;
+      if (more) put_node(i, pv[k][0], pv[k][1], pv[k][2], pv[k][3], pv[k][4], pv[k][5]);
+    }
+  }
+  if (!more) break;
+  __syncthreads();
+  rc = rn; rn = rnn; tnext += gridDim.x;
   }
 }
 
@@ -491,7 +618,11 @@ __global__ void __launch_bounds__(EQD_TILE_THREADS, 2) k_tile_pml(ElemArgs A) {
   extern __shared__ double sm[];
   constexpr int NT = EQD_TILE_THREADS;
   const int tid = threadIdx.x;
-  const TileCtx T = tile_ctx(A);
+  struct { int e0, ne, nb, LN, NC; } T;
+  {
+    const int4 r = __ldg(A.tileRec + A.tile0 + blockIdx.x);
+    T.e0 = TR_E0(r); T.ne = TR_NE(r); T.nb = TR_NB(r); T.LN = TR_LN(r); T.NC = TR_NC(r);
+  }
   const int LS = A.LS;
   const size_t S = A.S, NS = A.NnS;
   const double dt = A.dt, rdampk = A.rdampk;
@@ -1039,10 +1170,25 @@ void launch_materialize_accel(const NodeArgs& A, double* out, cudaStream_t s) {
   if (A.Nn > 0) k_materialize_accel<<<nblk(A.Nn, 128), 128, 0, s>>>(A, out);
 }
 
-// dynamic shared memory of a tile kernel: staged rows + force rows, LS doubles each
-static size_t tile_smem(const ElemArgs& A, int rows) { return (size_t)rows * A.LS * sizeof(double); }
-static void tile_launch(void (*kern)(ElemArgs), const ElemArgs& A, int ntiles, int rows, cudaStream_t s) {
-  const size_t sm = tile_smem(A, rows);
+// dynamic shared memory of a tile kernel of class `cls` whose largest tile has LS nodes
+size_t tile_smem_bytes(int cls, bool q, int LS) {
+  if (cls == CLS_PML) return (size_t)18 * LS * sizeof(double);
+  return 128 + (size_t)RR_ROWS * EQD_STAGE * sizeof(double) + 8 * EQD_STAGE * sizeof(uint16_t) + (size_t)(q ? 15 : 12) * LS * sizeof(double);
+}
+static int sm_count() {
+  static std::mutex mu;
+  static std::map<int, int> cache;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> g(mu);
+  auto it = cache.find(dev);
+  if (it != cache.end()) return it->second;
+  int n = 148;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  cache[dev] = n;
+  return n;
+}
+static void tile_launch(void (*kern)(ElemArgs), const ElemArgs& A, int ntiles, int threads, size_t sm, cudaStream_t s) {
   // opt in to the large dynamic shared memory once per (device, kernel)
   static std::mutex mu;
   static std::set<std::pair<int, const void*>> done;
@@ -1053,32 +1199,37 @@ static void tile_launch(void (*kern)(ElemArgs), const ElemArgs& A, int ntiles, i
     if (done.insert({dev, (const void*)kern}).second)
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
   }
-  kern<<<ntiles, EQD_TILE_THREADS, sm, s>>>(A);
+  kern<<<ntiles, threads, sm, s>>>(A);
 }
 template <bool PL, bool Q, bool BODY, bool SPLIT>
-static void launch_reg_chg(const ElemArgs& A, int ntiles, int chg, cudaStream_t s) {
-  const int rows = (Q ? 9 : 6) + (SPLIT ? 6 : 3);
-  if (chg == 2) tile_launch(k_tile_reg<PL, Q, BODY, SPLIT, 2>, A, ntiles, rows, s);
-  else tile_launch(k_tile_reg<PL, Q, BODY, SPLIT, 1>, A, ntiles, rows, s);
+static void launch_reg_chg(const ElemArgs& A, int chg, cudaStream_t s) {
+  const int ntiles = A.ntiles;
+  const size_t sm = tile_smem_bytes(CLS_REG, Q, A.LS);
+  // persistent CTAs, two per SM, each walking tiles blockIdx.x, +gridDim.x, ...
+  const int grid = std::min(ntiles, 2 * sm_count());
+  if (chg == 2) tile_launch(k_tile_reg<PL, Q, BODY, SPLIT, 2>, A, grid, 2 * EQD_STAGE, sm, s);
+  else tile_launch(k_tile_reg<PL, Q, BODY, SPLIT, 1>, A, grid, 2 * EQD_STAGE, sm, s);
 }
 template <bool SPLIT>
-static void launch_reg_split(const ElemArgs& A, int ntiles, bool plastic, bool q, bool body, int chg, cudaStream_t s) {
+static void launch_reg_split(const ElemArgs& A, bool plastic, bool q, bool body, int chg, cudaStream_t s) {
   // C_Q==1 with C_elastic==0 is rejected by the reference (warning.f90:6-9)
-  if (q) { if (body) launch_reg_chg<false, true, true, SPLIT>(A, ntiles, chg, s); else launch_reg_chg<false, true, false, SPLIT>(A, ntiles, chg, s); }
-  else if (plastic) { if (body) launch_reg_chg<true, false, true, SPLIT>(A, ntiles, chg, s); else launch_reg_chg<true, false, false, SPLIT>(A, ntiles, chg, s); }
-  else { if (body) launch_reg_chg<false, false, true, SPLIT>(A, ntiles, chg, s); else launch_reg_chg<false, false, false, SPLIT>(A, ntiles, chg, s); }
+  if (q) { if (body) launch_reg_chg<false, true, true, SPLIT>(A, chg, s); else launch_reg_chg<false, true, false, SPLIT>(A, chg, s); }
+  else if (plastic) { if (body) launch_reg_chg<true, false, true, SPLIT>(A, chg, s); else launch_reg_chg<true, false, false, SPLIT>(A, chg, s); }
+  else { if (body) launch_reg_chg<false, false, true, SPLIT>(A, chg, s); else launch_reg_chg<false, false, false, SPLIT>(A, chg, s); }
 }
-void launch_elem_reg(const ElemArgs& A, int ntiles, bool split, bool plastic, bool q, bool body, int chg, cudaStream_t s) {
+void launch_elem_reg(const ElemArgs& A, bool split, bool plastic, bool q, bool body, int chg, cudaStream_t s) {
+  if (A.ntiles <= 0) return;
+  if (split) launch_reg_split<true>(A, plastic, q, body, chg, s);
+  else launch_reg_split<false>(A, plastic, q, body, chg, s);
+}
+void launch_elem_pml(const ElemArgs& A, bool body, int chg, cudaStream_t s) {
+  const int ntiles = A.ntiles;
   if (ntiles <= 0) return;
-  if (split) launch_reg_split<true>(A, ntiles, plastic, q, body, chg, s);
-  else launch_reg_split<false>(A, ntiles, plastic, q, body, chg, s);
+  const size_t sm = tile_smem_bytes(CLS_PML, false, A.LS);
+  const int nt = EQD_TILE_THREADS;
+  if (body) { if (chg == 2) tile_launch(k_tile_pml<true, 2>, A, ntiles, nt, sm, s); else tile_launch(k_tile_pml<true, 1>, A, ntiles, nt, sm, s); }
+  else { if (chg == 2) tile_launch(k_tile_pml<false, 2>, A, ntiles, nt, sm, s); else tile_launch(k_tile_pml<false, 1>, A, ntiles, nt, sm, s); }
 }
-void launch_elem_pml(const ElemArgs& A, int ntiles, bool body, int chg, cudaStream_t s) {
-  if (ntiles <= 0) return;
-  if (body) { if (chg == 2) tile_launch(k_tile_pml<true, 2>, A, ntiles, 18, s); else tile_launch(k_tile_pml<true, 1>, A, ntiles, 18, s); }
-  else { if (chg == 2) tile_launch(k_tile_pml<false, 2>, A, ntiles, 18, s); else tile_launch(k_tile_pml<false, 1>, A, ntiles, 18, s); }
-}
-int tile_rows(int cls, bool q) { return cls == CLS_PML ? 18 : (q ? 9 : 6) + (cls == CLS_REGX ? 6 : 3); }
 void launch_store_offfault(const int* idhist, int n, double* out, const double* vel, const double* disp, int NnS,
                            const StepState* st, cudaStream_t s) {
   if (n > 0) k_store_offfault<<<nblk(n + 1, 128), 128, 0, s>>>(idhist, n, out, vel, disp, NnS, st);

@@ -10,10 +10,10 @@ void launch_advance(StepState* st, double dt, cudaStream_t s);
 void launch_node_update(const NodeArgs& A, cudaStream_t s);
 void launch_assemble_special(const NodeArgs& A, const int* list, int n, cudaStream_t s);
 void launch_materialize_accel(const NodeArgs& A, double* out, cudaStream_t s);
-// ntiles CTAs starting at A.tile0 of the class's launch order
-void launch_elem_reg(const ElemArgs& A, int ntiles, bool split, bool plastic, bool q, bool body, int chg, cudaStream_t s);
-void launch_elem_pml(const ElemArgs& A, int ntiles, bool body, int chg, cudaStream_t s);
-int tile_rows(int cls, bool q);  // shared-memory rows (of LS doubles) a tile kernel of this class needs
+// sweep tiles [A.tile0, A.tile0 + A.ntiles) of the class's launch order
+void launch_elem_reg(const ElemArgs& A, bool split, bool plastic, bool q, bool body, int chg, cudaStream_t s);
+void launch_elem_pml(const ElemArgs& A, bool body, int chg, cudaStream_t s);
+size_t tile_smem_bytes(int cls, bool q, int LS);  // dynamic shared memory of the class's tile kernel
 void launch_store_offfault(const int* idhist, int n, double* out, const double* vel, const double* disp, int NnS,
                            const StepState* st, cudaStream_t s);
 void launch_sample_gm(const int* surf, int nSurf, const double* vel, int NnS, double* out, cudaStream_t s);
