@@ -710,7 +710,7 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
       ElemClass& C = h->cls[c];
       TileShape sh;
       if (c == CLS_PML) { sh.bx = 3; sh.bz = 3; sh.by = 32; sh.capE = 384; sh.capN = 800; }
-      else { sh.bx = 4; sh.bz = 4; sh.by = 16; sh.capE = 384; sh.capN = h->qmode ? 336 : 420; }  // two CTAs per SM
+      else { sh.bx = 4; sh.bz = 4; sh.by = 16; sh.capE = 384; sh.capN = EQD_REG_LS; }  // two CTAs per SM
       TilePlan T;
       plan_tiles(h->conn.data(), members[c], Nn, gny, gnz, gridOk, sh, EQD_TILE_THREADS, T);
       C.n = T.n; C.S = T.S; C.nf = nf[c]; C.nstress = nstr[c];
@@ -720,7 +720,7 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
       for (int s = 0; s < C.S; ++s) if (C.refId[s] >= 0) h->elemCode[C.refId[s]] = c | (s << 2);
       C.tileNodeH = T.tileNode; C.tnodeH = T.tnode;
       if (!C.n) continue;
-      need(c == CLS_PML || C.LS <= EQD_REG_NPT * 2 * EQD_STAGE, "eqd_set_mesh: regular tile has too many nodes");
+      need(c == CLS_PML || C.LS <= EQD_REG_LS, "eqd_set_mesh: regular tile has too many nodes");
       C.tileRecH.resize(C.nTiles);
       for (int t = 0; t < C.nTiles; ++t)
         C.tileRecH[t] = make_int4(T.tileElem[t], T.tileCnt[t] | ((int)T.tileColours[t] << 16), T.tileNode[t], T.tileNode[t + 1] - T.tileNode[t]);

@@ -42,7 +42,7 @@ enum { CLS_REG = 0, CLS_REGX = 1, CLS_PML = 2 };
 #define EQD_LN_MASK 0x0fffu
 #define EQD_TILE_THREADS 128   // PML tile kernel: one thread per element of a pass
 #define EQD_STAGE 128          // regular tile kernel: elements per streamed stage (two threads each)
-#define EQD_REG_NPT 2          // regular tile kernel: tile nodes handled per thread (LS <= 2 * 256)
+#define EQD_REG_LS 400         // regular tile kernel: node cap of a tile = shared-memory row stride (two CTAs per SM)
 
 struct StepState {
   double timeElapsed;  // driver.f90:11

@@ -249,6 +249,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+// per-thread asynchronous 8-byte copy global -> shared (LDGSTS): gathers that need no register staging
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------
 // Tile kernels.  One CTA owns one tile (a brick of a few hundred elements of one
 // class, contiguous in the class's SoA) and walks it in stages of EQD_STAGE
@@ -298,22 +305,24 @@ __global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
   extern __shared__ __align__(128) unsigned char smraw[];
   constexpr int SE = EQD_STAGE;
   constexpr int NT = 2 * SE;
-  constexpr int NPT = EQD_REG_NPT;  // tile nodes per thread (LS <= NPT * NT, checked by the host)
+  constexpr int LS = EQD_REG_LS;    // shared-memory row stride = node cap of a regular tile
+  constexpr int NPT = (LS + NT - 1) / NT;
   const int tid = threadIdx.x;
   const int role = tid / SE;        // 0: constitutive (KU), 1: hourglass; warp-uniform
   const int lane = tid - role * SE; // element of the stage
   const int tEnd = A.tile0 + A.ntiles;
   int tnext = A.tile0 + blockIdx.x;
   if (tnext >= tEnd) return;
-  const int LS = A.LS;
   const size_t S = A.S, NS = A.NnS;
   const double dt = A.dt, rdampk = A.rdampk;
-  uint64_t* bar = (uint64_t*)smraw;
+  uint64_t* bar = (uint64_t*)smraw;                             // operator stage landed
+  uint64_t* barN = bar + 1;                                     // node-id list of the next tile landed
   double* ops = (double*)(smraw + 128);                         // [RR_ROWS][SE]
   uint16_t* slc = (uint16_t*)(ops + RR_ROWS * SE);              // [8][SE]
-  double* sv = (double*)(slc + 8 * SE);                         // [3][LS] velocity
+  int* tnS = (int*)(slc + 8 * SE);                              // [LS] node ids of the tile whose nodes are gathered next
+  double* sv = (double*)(tnS + LS);                             // [3][LS] velocity
   double* sl = sv + 3 * LS;                                     // [3][LS] d + rdampk*v
-  double* sd = sl + 3 * LS;                                     // [3][LS] displacement (Q only)
+  double* sd = QMODE ? sl + 3 * LS : sl;                        // [3][LS] displacement: gather target (kept for Q)
   double* sf = sl + (QMODE ? 6 : 3) * LS;                       // [2][3][LS] force accumulators: KU | hourglass
   auto request = [&](const int4& rec, int base) {
     // one thread per row; sizes are whole 32-element groups (the class SoA is padded)
@@ -323,10 +332,44 @@ __global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
     if (tid < RR_ROWS) bulk_g2s(ops + tid * SE, reg_row_src(A, tid) + TR_E0(rec) + base, cnt * 8, bar);
     else if (tid < RR_ROWS + 8) bulk_g2s(slc + (tid - RR_ROWS) * SE, A.lconn + (size_t)(tid - RR_ROWS) * S + TR_E0(rec) + base, cnt * 2, bar);
   };
-  auto put_node = [&](int i, double vx, double vy, double vz, double dx, double dy, double dz) {
-    sv[i] = vx; sv[LS + i] = vy; sv[2 * LS + i] = vz;
-    sl[i] = dx + rdampk * vx; sl[LS + i] = dy + rdampk * vy; sl[2 * LS + i] = dz + rdampk * vz;
-    if (QMODE) { sd[i] = dx; sd[LS + i] = dy; sd[2 * LS + i] = dz; }
+  auto request_ids = [&](const int4& rec) {
+    if (tid == 0) {
+      mbar_expect_tx(barN, (uint32_t)(TR_LN(rec) * 4));
+      bulk_g2s(tnS, A.tnode + TR_NB(rec), TR_LN(rec) * 4, barN);
+    }
+  };
+  // gather the nodal values of tile `rec` (ids in tnS) straight into shared memory
+  auto gather_nodes = [&](const int4& rec) {
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) {
+      const int i = tid + k * NT;
+      if (i < LS) {
+        const int nd = i < TR_LN(rec) ? tnS[i] : -1;
+        if (nd >= 0) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            cp_async8(sv + j * LS + i, A.vel + j * NS + nd);
+            cp_async8(sd + j * LS + i, A.disp + j * NS + nd);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) { sv[j * LS + i] = 0.0; sd[j * LS + i] = 0.0; }
+        }
+      }
+    }
+    cp_async_commit();
+  };
+  // own nodes have landed: d -> d + rdampk*v (hrglss.f90:20-27)
+  auto finish_nodes = [&]() {
+    cp_async_wait_all();
+#pragma unroll
+    for (int k = 0; k < NPT; ++k) {
+      const int i = tid + k * NT;
+      if (i < LS) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) sl[j * LS + i] = sd[j * LS + i] + rdampk * sv[j * LS + i];
+      }
+    }
   };
   const int4 zero4 = make_int4(0, 0, 0, 0);
   // software pipeline over this CTA's tiles: rc = tile being swept, rn = the next
@@ -334,38 +377,29 @@ __global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
   int4 rc = __ldg(A.tileRec + tnext);
   tnext += gridDim.x;
   int4 rn = tnext < tEnd ? __ldg(A.tileRec + tnext) : zero4;
-  if (tid == 0) mbar_init(bar, 1);
+  if (tid == 0) { mbar_init(bar, 1); mbar_init(barN, 1); }
   __syncthreads();
   request(rc, 0);
+  request_ids(rc);
 #pragma unroll
   for (int k = 0; k < NPT; ++k) {
     const int i = tid + k * NT;
     if (i < LS) {
-      const int nd = i < TR_LN(rc) ? LDG(A.tnode + TR_NB(rc) + i) : -1;
-      double vx = 0, vy = 0, vz = 0, dx = 0, dy = 0, dz = 0;
-      if (nd >= 0) {
-        vx = LDG(A.vel + nd); vy = LDG(A.vel + NS + nd); vz = LDG(A.vel + 2 * NS + nd);
-        dx = LDG(A.disp + nd); dy = LDG(A.disp + NS + nd); dz = LDG(A.disp + 2 * NS + nd);
-      }
-      put_node(i, vx, vy, vz, dx, dy, dz);
 #pragma unroll
       for (int j = 0; j < 6; ++j) sf[j * LS + i] = 0.0;
     }
   }
+  uint32_t parity = 0, parityN = 0;
+  mbar_wait(barN, parityN);
+  parityN ^= 1;
+  gather_nodes(rc);
+  finish_nodes();
   __syncthreads();
   double* acc = sf + role * 3 * LS;
-  uint32_t parity = 0;
   while (true) {
   const bool more = tnext < tEnd;
-  // node ids of the next tile (used when rc's last stage has been consumed) and the record after it
-  int nn[NPT];
-#pragma unroll
-  for (int k = 0; k < NPT; ++k) {
-    const int i = tid + k * NT;
-    nn[k] = (more && i < TR_LN(rn)) ? LDG(A.tnode + TR_NB(rn) + i) : -1;
-  }
   const int4 rnn = (tnext + (int)gridDim.x < tEnd) ? __ldg(A.tileRec + tnext + gridDim.x) : zero4;
-  double pv[NPT][6];
+  if (more) request_ids(rn);   // tnS is free: rc's nodes are already in sv/sl
   const int ne = TR_NE(rc), NC = TR_NC(rc);
   for (int base = 0; base < ne; base += SE) {
     const int le = base + lane;
@@ -554,23 +588,16 @@ __global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
       }
 #undef OP
     }
-    // the stage buffer is consumed: request the next stage (or the next tile's first
-    // one, and its nodal values into registers); they land while the forces are assembled
+    // the stage buffer is consumed: request the next stage, or the next tile's first
+    // stage and its nodal values; they land while the forces are assembled
     __syncthreads();
     const bool last = base + SE >= ne;
     if (!last) request(rc, base + SE);
     else if (more) {
       request(rn, 0);
-#pragma unroll
-      for (int k = 0; k < NPT; ++k) {
-        const int nd = nn[k];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) pv[k][j] = 0.0;
-        if (nd >= 0) {
-          pv[k][0] = LDG(A.vel + nd); pv[k][1] = LDG(A.vel + NS + nd); pv[k][2] = LDG(A.vel + 2 * NS + nd);
-          pv[k][3] = LDG(A.disp + nd); pv[k][4] = LDG(A.disp + NS + nd); pv[k][5] = LDG(A.disp + 2 * NS + nd);
-        }
-      }
+      mbar_wait(barN, parityN);
+      parityN ^= 1;
+      gather_nodes(rn);   // sv / sd are dead once the last stage has been consumed
     }
     // ---- ordered assembly into the tile's shared force rows (one set per role)
 #pragma unroll
@@ -582,7 +609,7 @@ __global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
       }
     }
   }
-  // ---- flush the tile's partial forces; hand the node rows over to the next tile
+  // ---- flush the tile's partial forces
 #pragma unroll
   for (int k = 0; k < NPT; ++k) {
     const int i = tid + k * NT;
@@ -600,10 +627,10 @@ __global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
       }
 #pragma unroll
       for (int j = 0; j < 6; ++j) sf[j * LS + i] = 0.0;
-      if (more) put_node(i, pv[k][0], pv[k][1], pv[k][2], pv[k][3], pv[k][4], pv[k][5]);
     }
   }
   if (!more) break;
+  finish_nodes();
   __syncthreads();
   rc = rn; rn = rnn; tnext += gridDim.x;
   }
@@ -1173,7 +1200,9 @@ void launch_materialize_accel(const NodeArgs& A, double* out, cudaStream_t s) {
 // dynamic shared memory of a tile kernel of class `cls` whose largest tile has LS nodes
 size_t tile_smem_bytes(int cls, bool q, int LS) {
   if (cls == CLS_PML) return (size_t)18 * LS * sizeof(double);
-  return 128 + (size_t)RR_ROWS * EQD_STAGE * sizeof(double) + 8 * EQD_STAGE * sizeof(uint16_t) + (size_t)(q ? 15 : 12) * LS * sizeof(double);
+  (void)LS;
+  return 128 + (size_t)RR_ROWS * EQD_STAGE * sizeof(double) + 8 * EQD_STAGE * sizeof(uint16_t) + (size_t)EQD_REG_LS * sizeof(int) +
+         (size_t)(q ? 15 : 12) * EQD_REG_LS * sizeof(double);
 }
 static int sm_count() {
   static std::mutex mu;

@@ -235,7 +235,7 @@ extern "C" int eqd_plan_check(int32_t Nn, int32_t Ne, const int32_t* nodeElemIdR
     for (int c = 0; c < 3; ++c) {
       TileShape sh;
       if (c == CLS_PML) { sh.bx = 3; sh.bz = 3; sh.by = 32; sh.capE = 384; sh.capN = 800; }
-      else { sh.bx = 4; sh.bz = 4; sh.by = 16; sh.capE = 384; sh.capN = 420; }
+      else { sh.bx = 4; sh.bz = 4; sh.by = 16; sh.capE = 384; sh.capN = EQD_REG_LS; }
       TilePlan P;
       plan_tiles(conn.data(), members[c], Nn, ny, nz, ok, sh, EQD_TILE_THREADS, P);
       int64_t* st = stats + 8 * c;
