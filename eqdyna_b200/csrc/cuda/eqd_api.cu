@@ -147,7 +147,7 @@ struct eqd_handle {
   bool body = false, plastic = false, qmode = false;
   // ---- device
   ElemClass cls[3];
-  DevBuf<int> dInfo, dSlotStart, dSpecial;
+  DevBuf<int> dInfo, dPmlNode, dSlotStart, dSpecial;
   DevBuf<uint32_t> dSlots;
   DevBuf<double> dVel, dDisp, dMass, dV1p, dDampp, dForce, dAccel0;
   int nSpecial = 0;
@@ -281,7 +281,7 @@ void need(bool ok, const char* msg) { if (!ok) throw ArgError(msg); }
 NodeArgs eqd_handle::nodeArgs() const {
   NodeArgs A{};
   A.Nn = Nn; A.NnS = NnS; A.Np = Np; A.NpS = NpS;
-  A.info = dInfo.p; A.vel = dVel.p; A.disp = dDisp.p; A.mass = dMass.p;
+  A.info = dInfo.p; A.pmlNode = dPmlNode.p; A.vel = dVel.p; A.disp = dDisp.p; A.mass = dMass.p;
   A.v1p = dV1p.p; A.dampp = dDampp.p; A.force = dForce.p;
   A.slotStart = dSlotStart.p; A.slots = dSlots.p;
   A.pfR = cls[CLS_REG].pf.p; A.SR = cls[CLS_REG].PFS;
@@ -495,7 +495,7 @@ void step_pre(eqd_handle* h) {
     Timer t(h, EQD_T_NODE);
     NodeArgs A = h->nodeArgs();
     if (h->dAccel0.p) A.accel0 = h->dAccel0.p;
-    launch_node_update(A, s); h->launches++;
+    launch_node_update(A, s); h->launches += h->Np > 0 ? 2 : 1;
     if (h->nOff > 0) {
       launch_store_offfault(h->dIdhist.p, 6 * h->nOff, h->dOffHist.p, h->dVel.p, h->dDisp.p, h->NnS, h->dState.p, s);
       h->launches++;
@@ -688,6 +688,11 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
     }
     h->NnS = pad32(Nn);
     h->NpS = pad32(std::max(h->Np, 1));
+    {
+      std::vector<int> pn(std::max(h->Np, 1), 0);
+      for (int n = 0; n < Nn; ++n) if (EQD_INFO_KIND(h->info[n]) == KIND_PML12) pn[EQD_INFO_SLOT(h->info[n])] = n;
+      h->dPmlNode.upload(pn);
+    }
     need(3 * (double)h->NnS + 12 * (double)h->NpS < 4.0e9, "eqd_set_mesh: sub-domain too large for 32-bit halo offsets");
     // ---- element classes, cut into tiles (eqd_tiles.h)
     std::vector<int> members[3];
@@ -709,10 +714,10 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
     for (int c = 0; c < 3; ++c) {
       ElemClass& C = h->cls[c];
       TileShape sh;
-      if (c == CLS_PML) { sh.bx = 3; sh.bz = 3; sh.by = 32; sh.capE = 384; sh.capN = 800; }
+      if (c == CLS_PML) { sh.bx = 3; sh.bz = 3; sh.by = 24; sh.capE = 320; sh.capN = EQD_PML_LS; }
       else { sh.bx = 4; sh.bz = 4; sh.by = 16; sh.capE = 384; sh.capN = EQD_REG_LS; }  // two CTAs per SM
       TilePlan T;
-      plan_tiles(h->conn.data(), members[c], Nn, gny, gnz, gridOk, sh, EQD_TILE_THREADS, T);
+      plan_tiles(h->conn.data(), members[c], Nn, gny, gnz, gridOk, sh, c == CLS_PML ? EQD_STAGE_PML : EQD_STAGE, T);
       C.n = T.n; C.S = T.S; C.nf = nf[c]; C.nstress = nstr[c];
       C.nTiles = T.nTiles; C.nFaceTiles = 0; C.LS = T.LS; C.PFS = T.PFS;
       need(tile_smem_bytes(c, h->qmode, C.LS) <= 227 * 1024, "eqd_set_mesh: tile does not fit shared memory");
@@ -720,7 +725,7 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
       for (int s = 0; s < C.S; ++s) if (C.refId[s] >= 0) h->elemCode[C.refId[s]] = c | (s << 2);
       C.tileNodeH = T.tileNode; C.tnodeH = T.tnode;
       if (!C.n) continue;
-      need(c == CLS_PML || C.LS <= EQD_REG_LS, "eqd_set_mesh: regular tile has too many nodes");
+      need(C.LS <= (c == CLS_PML ? EQD_PML_LS : EQD_REG_LS), "eqd_set_mesh: tile has too many nodes");
       C.tileRecH.resize(C.nTiles);
       for (int t = 0; t < C.nTiles; ++t)
         C.tileRecH[t] = make_int4(T.tileElem[t], T.tileCnt[t] | ((int)T.tileColours[t] << 16), T.tileNode[t], T.tileNode[t + 1] - T.tileNode[t]);

@@ -40,8 +40,9 @@ enum { CLS_REG = 0, CLS_REGX = 1, CLS_PML = 2 };
 // local connectivity entry: tile-local node index (12 bits) | colour of the phase (4 bits)
 #define EQD_LN_BITS 12
 #define EQD_LN_MASK 0x0fffu
-#define EQD_TILE_THREADS 128   // PML tile kernel: one thread per element of a pass
 #define EQD_STAGE 128          // regular tile kernel: elements per streamed stage (two threads each)
+#define EQD_STAGE_PML 64       // PML tile kernel: elements per streamed stage (four threads each)
+#define EQD_PML_LS 400         // PML tile kernel: node cap of a tile
 #define EQD_REG_LS 400         // regular tile kernel: node cap of a tile = shared-memory row stride (two CTAs per SM)
 
 struct StepState {
@@ -55,6 +56,7 @@ struct StepState {
 struct NodeArgs {
   int Nn, NnS, Np, NpS;
   const int* info;       // [Nn] kind | special<<2 | pmlSlot<<3
+  const int* pmlNode;    // [Np] PML slot -> node
   double* vel;           // [3][NnS]
   double* disp;          // [3][NnS]
   const double* mass;    // [Nn]

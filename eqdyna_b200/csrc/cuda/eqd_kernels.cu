@@ -88,82 +88,93 @@ __device__ __forceinline__ void gather12(const NodeArgs& A, int n, double f[12])
 
 // ----------------------------------------------------------------------------
 // velDispUpdate (driver.f90:89-155) fused with the force assembly and with the
-// previous step's `nodalForceArr/nodalMassArr` (driver.f90:29).
-__global__ void __launch_bounds__(256) k_node_update(NodeArgs A) {
+// previous step's `nodalForceArr/nodalMassArr` (driver.f90:29).  Two kernels so
+// that the 3-dof one (almost every node) stays light enough for full occupancy:
+// its gather is a chain of dependent loads that only parallelism hides.
+__global__ void __launch_bounds__(256, 6) k_node_update3(NodeArgs A) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= A.Nn) return;
   const int info = LDG(A.info + n);
-  const int kind = EQD_INFO_KIND(info);
-  if (kind == KIND_FIXED) return;  // vel = disp = 0 for ever (driver.f90:142-145)
+  if (EQD_INFO_KIND(info) != KIND_FREE3) return;  // fixed: vel = disp = 0 for ever (driver.f90:142-145)
   const double dt = A.dt;
   const size_t NS = A.NnS;
-  const double m = LDG(A.mass + n);
-  bool bad = false;
-  if (kind == KIND_FREE3) {
-    double a[3];
-    if (A.accel0) {
-      a[0] = A.accel0[n]; a[1] = A.accel0[NS + n]; a[2] = A.accel0[2 * NS + n];
-    } else {
-      double f[3];
-      if (EQD_INFO_SPECIAL(info)) {
-        f[0] = A.force[n]; f[1] = A.force[NS + n]; f[2] = A.force[2 * NS + n];
-      } else {
-        gather3(A, n, f);
-      }
-      a[0] = f[0] / m; a[1] = f[1] / m; a[2] = f[2] / m;
-    }
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      double v = A.vel[j * NS + n];
-      v = v + a[j] * dt;                      // driver.f90:102
-      A.vel[j * NS + n] = v;                  // :103
-      A.disp[j * NS + n] = A.disp[j * NS + n] + v * dt;  // :104
-      bad |= (v != v);
-    }
+  double a[3];
+  if (A.accel0) {
+    a[0] = A.accel0[n]; a[1] = A.accel0[NS + n]; a[2] = A.accel0[2 * NS + n];
   } else {
-    const int slot = EQD_INFO_SLOT(info);
-    const size_t PS = A.NpS;
-    double a[12];
-    if (A.accel0) {
-      const double* ap = A.accel0 + 3 * NS;
-#pragma unroll
-      for (int j = 0; j < 12; ++j) a[j] = ap[j * PS + slot];
+    const double m = LDG(A.mass + n);
+    double f[3];
+    if (EQD_INFO_SPECIAL(info)) {
+      f[0] = A.force[n]; f[1] = A.force[NS + n]; f[2] = A.force[2 * NS + n];
     } else {
-      double f[12];
-      if (EQD_INFO_SPECIAL(info)) {
-        const double* fp = A.force + 3 * NS;
-#pragma unroll
-        for (int j = 0; j < 12; ++j) f[j] = fp[j * PS + slot];
-      } else {
-        gather12(A, n, f);
-      }
-#pragma unroll
-      for (int j = 0; j < 12; ++j) a[j] = f[j] / m;
+      gather3(A, n, f);
     }
-    double d[3], v[12];
-    d[0] = LDG(A.dampp + slot); d[1] = LDG(A.dampp + PS + slot); d[2] = LDG(A.dampp + 2 * PS + slot);
-    const double rdt = 1.0 / dt;
+    a[0] = f[0] / m; a[1] = f[1] / m; a[2] = f[2] / m;
+  }
+  bool bad = false;
 #pragma unroll
-    for (int j = 0; j < 9; ++j) {             // driver.f90:112-117, dampv(j) = damp(mod(j-1,3)+1)
-      const double dj = d[j % 3];
-      v[j] = (a[j] + A.v1p[j * PS + slot] * (rdt - dj / 2.0)) / (rdt + dj / 2.0);
-      A.v1p[j * PS + slot] = v[j];
+  for (int j = 0; j < 3; ++j) {
+    double v = A.vel[j * NS + n];
+    v = v + a[j] * dt;                      // driver.f90:102
+    A.vel[j * NS + n] = v;                  // :103
+    A.disp[j * NS + n] = A.disp[j * NS + n] + v * dt;  // :104
+    bad |= (v != v);
+  }
+  if (bad) {
+    if (atomicExch(&A.st->nanFlag, 1) == 0) A.st->nanNode = n + 1;
+  }
+}
+
+// 12-dof PML nodes: split-field velocities with damping (driver.f90:105-141), one thread per PML slot
+__global__ void __launch_bounds__(128) k_node_update12(NodeArgs A) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= A.Np) return;
+  const int n = LDG(A.pmlNode + slot);
+  const int info = LDG(A.info + n);
+  const double dt = A.dt;
+  const size_t NS = A.NnS, PS = A.NpS;
+  const double m = LDG(A.mass + n);
+  double a[12];
+  if (A.accel0) {
+    const double* ap = A.accel0 + 3 * NS;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) a[j] = ap[j * PS + slot];
+  } else {
+    double f[12];
+    if (EQD_INFO_SPECIAL(info)) {
+      const double* fp = A.force + 3 * NS;
+#pragma unroll
+      for (int j = 0; j < 12; ++j) f[j] = fp[j * PS + slot];
+    } else {
+      gather12(A, n, f);
     }
 #pragma unroll
-    for (int j = 9; j < 12; ++j) {            // :118-123
-      v[j] = A.v1p[j * PS + slot] + a[j] * dt;
-      A.v1p[j * PS + slot] = v[j];
-    }
-    double vel[3];
-    vel[0] = v[0] + v[1] + v[2] + v[9];       // :125-141
-    vel[1] = v[3] + v[4] + v[5] + v[10];
-    vel[2] = v[6] + v[7] + v[8] + v[11];
+    for (int j = 0; j < 12; ++j) a[j] = f[j] / m;
+  }
+  double d[3], v[12];
+  d[0] = LDG(A.dampp + slot); d[1] = LDG(A.dampp + PS + slot); d[2] = LDG(A.dampp + 2 * PS + slot);
+  const double rdt = 1.0 / dt;
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      A.vel[j * NS + n] = vel[j];
-      A.disp[j * NS + n] = A.disp[j * NS + n] + vel[j] * dt;
-      bad |= (vel[j] != vel[j]);
-    }
+  for (int j = 0; j < 9; ++j) {             // driver.f90:112-117, dampv(j) = damp(mod(j-1,3)+1)
+    const double dj = d[j % 3];
+    v[j] = (a[j] + A.v1p[j * PS + slot] * (rdt - dj / 2.0)) / (rdt + dj / 2.0);
+    A.v1p[j * PS + slot] = v[j];
+  }
+#pragma unroll
+  for (int j = 9; j < 12; ++j) {            // :118-123
+    v[j] = A.v1p[j * PS + slot] + a[j] * dt;
+    A.v1p[j * PS + slot] = v[j];
+  }
+  double vel[3];
+  vel[0] = v[0] + v[1] + v[2] + v[9];       // :125-141
+  vel[1] = v[3] + v[4] + v[5] + v[10];
+  vel[2] = v[6] + v[7] + v[8] + v[11];
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    A.vel[j * NS + n] = vel[j];
+    A.disp[j * NS + n] = A.disp[j * NS + n] + vel[j] * dt;
+    bad |= (vel[j] != vel[j]);
   }
   if (bad) {
     if (atomicExch(&A.st->nanFlag, 1) == 0) A.st->nanNode = n + 1;
@@ -637,206 +648,348 @@ __global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
 }
 
 // ----------------------------------------------------------------------------
-// PML element: calcPMLElemKU (assembleGlobalKU.f90:70-346) fused with hrglss.
-// The damping profile at the centroid (:130-213, constant in time) is
-// precomputed by the host into damps[3][S].  Same tile scheme, 12 force rows.
+// PML element: calcPMLElemKU (assembleGlobalKU.f90:70-346) and hrglss.  The
+// damping profile at the centroid (:130-213, constant in time) is precomputed by
+// the host into damps[3][S].  Same streamed-tile scheme as the regular kernel,
+// stages of EQD_STAGE_PML elements and FOUR threads per element:
+//   warps 0-1  normal split stresses  s(1:9)   -> force dofs 1,5,9
+//   warps 2-3  shear split stresses   s(10:15) -> force dofs 2,3,4,6,7,8
+//   warps 4-5  regular stress part    s(16:21) + rdampk*rate -> dofs 10-12
+//   warps 6-7  hourglass              (hrglss.f90)           -> dofs 10-12 (own rows, merged at the flush)
+enum { PR_SHP = 0, PR_PHI = 24, PR_SS = 56, PR_LAM = 62, PR_MU = 63, PR_DET = 64, PR_DAMP = 65, PR_STRESS = 68, PR_ROWS = 89 };
+__device__ __forceinline__ const double* pml_row_src(const ElemArgs& A, int r) {
+  const size_t S = A.S;
+  if (r < PR_PHI) return A.shp + (size_t)r * S;
+  if (r < PR_SS) return A.phi + (size_t)(r - PR_PHI) * S;
+  if (r < PR_LAM) return A.ss + (size_t)(r - PR_SS) * S;
+  if (r == PR_LAM) return A.lam;
+  if (r == PR_MU) return A.mu;
+  if (r == PR_DET) return A.det;
+  if (r < PR_STRESS) return A.damps + (size_t)(r - PR_DAMP) * S;
+  return A.stress + (size_t)(r - PR_STRESS) * S;
+}
+
 template <bool BODY, int CHG>
-__global__ void __launch_bounds__(EQD_TILE_THREADS, 2) k_tile_pml(ElemArgs A) {
-  extern __shared__ double sm[];
-  constexpr int NT = EQD_TILE_THREADS;
+__global__ void __launch_bounds__(4 * EQD_STAGE_PML, 2) k_tile_pml(ElemArgs A) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  constexpr int SE = EQD_STAGE_PML;
+  constexpr int NT = 4 * SE;
+  constexpr int LS = EQD_PML_LS;
+  constexpr int NPT = (LS + NT - 1) / NT;
+  constexpr int NROW = 15;          // force rows: 12 dofs + 3 hourglass rows
   const int tid = threadIdx.x;
-  struct { int e0, ne, nb, LN, NC; } T;
-  {
-    const int4 r = __ldg(A.tileRec + A.tile0 + blockIdx.x);
-    T.e0 = TR_E0(r); T.ne = TR_NE(r); T.nb = TR_NB(r); T.LN = TR_LN(r); T.NC = TR_NC(r);
-  }
-  const int LS = A.LS;
+  const int role = tid / SE;        // warp-uniform
+  const int lane = tid - role * SE;
+  const int tEnd = A.tile0 + A.ntiles;
+  int tnext = A.tile0 + blockIdx.x;
+  if (tnext >= tEnd) return;
   const size_t S = A.S, NS = A.NnS;
   const double dt = A.dt, rdampk = A.rdampk;
-  double* sv = sm;            // [3][LS]
-  double* sl = sm + 3 * LS;   // [3][LS]
-  double* sf = sm + 6 * LS;   // [12][LS]
-  for (int i = tid; i < T.LN; i += NT) {
-    const int nd = LDG(A.tnode + T.nb + i);
-    double vx = 0, vy = 0, vz = 0, dx = 0, dy = 0, dz = 0;
-    if (nd >= 0) {
-      vx = LDG(A.vel + nd); vy = LDG(A.vel + NS + nd); vz = LDG(A.vel + 2 * NS + nd);
-      if (CHG == 1) { dx = LDG(A.disp + nd); dy = LDG(A.disp + NS + nd); dz = LDG(A.disp + 2 * NS + nd); }
+  uint64_t* bar = (uint64_t*)smraw;
+  uint64_t* barN = bar + 1;
+  double* ops = (double*)(smraw + 128);                         // [PR_ROWS][SE]
+  uint16_t* slc = (uint16_t*)(ops + PR_ROWS * SE);              // [8][SE]
+  int* tnS = (int*)(slc + 8 * SE);                              // [LS]
+  double* sv = (double*)(tnS + LS);                             // [3][LS] velocity
+  double* sl = sv + 3 * LS;                                     // [3][LS] d + rdampk*v
+  double* sf = sl + 3 * LS;                                     // [NROW][LS]
+  auto request = [&](const int4& rec, int base) {
+    const int cnt = min(SE, (TR_NE(rec) - base + 31) & ~31);
+    if (tid == 0) mbar_expect_tx(bar, (uint32_t)(cnt * (PR_ROWS * 8 + 8 * 2)));
+    __syncwarp();
+    if (tid < PR_ROWS) bulk_g2s(ops + tid * SE, pml_row_src(A, tid) + TR_E0(rec) + base, cnt * 8, bar);
+    else if (tid < PR_ROWS + 8) bulk_g2s(slc + (tid - PR_ROWS) * SE, A.lconn + (size_t)(tid - PR_ROWS) * S + TR_E0(rec) + base, cnt * 2, bar);
+  };
+  auto request_ids = [&](const int4& rec) {
+    if (tid == 0) {
+      mbar_expect_tx(barN, (uint32_t)(TR_LN(rec) * 4));
+      bulk_g2s(tnS, A.tnode + TR_NB(rec), TR_LN(rec) * 4, barN);
     }
-    sv[i] = vx; sv[LS + i] = vy; sv[2 * LS + i] = vz;
-    sl[i] = dx + rdampk * vx; sl[LS + i] = dy + rdampk * vy; sl[2 * LS + i] = dz + rdampk * vz;
+  };
+  auto gather_nodes = [&](const int4& rec) {
 #pragma unroll
-    for (int j = 0; j < 12; ++j) sf[j * LS + i] = 0.0;
-  }
+    for (int k = 0; k < NPT; ++k) {
+      const int i = tid + k * NT;
+      if (i < LS) {
+        const int nd = i < TR_LN(rec) ? tnS[i] : -1;
+        if (nd >= 0) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            cp_async8(sv + j * LS + i, A.vel + j * NS + nd);
+            if (CHG == 1) cp_async8(sl + j * LS + i, A.disp + j * NS + nd);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) { sv[j * LS + i] = 0.0; sl[j * LS + i] = 0.0; }
+        }
+      }
+    }
+    cp_async_commit();
+  };
+  auto finish_nodes = [&]() {
+    cp_async_wait_all();
+    if (CHG == 1) {
+#pragma unroll
+      for (int k = 0; k < NPT; ++k) {
+        const int i = tid + k * NT;
+        if (i < LS) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) sl[j * LS + i] = sl[j * LS + i] + rdampk * sv[j * LS + i];
+        }
+      }
+    }
+  };
+  const int4 zero4 = make_int4(0, 0, 0, 0);
+  int4 rc = __ldg(A.tileRec + tnext);
+  tnext += gridDim.x;
+  int4 rn = tnext < tEnd ? __ldg(A.tileRec + tnext) : zero4;
+  if (tid == 0) { mbar_init(bar, 1); mbar_init(barN, 1); }
   __syncthreads();
-  for (int base = 0; base < T.ne; base += NT) {
-    const int le = base + tid;
-    const bool act = le < T.ne;
-    const size_t e = (size_t)T.e0 + (act ? le : 0);
-    unsigned lc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    double shp[8][3];
-    double ph[CHG == 1 ? 4 : 1][8];
-    double body[BODY ? 24 : 1];
-    double qv[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
-    double hv[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    double s0[6] = {0, 0, 0, 0, 0, 0};
-    double sxx = 0, syy = 0, szz = 0, sxy = 0, sxz = 0, syz = 0, detw = 0, coef = 0;
-    if (act) {
-      double g[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};  // g[a][b] = d v_b / d x_a
-      double sr[6] = {0, 0, 0, 0, 0, 0};
-      double phid[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  request(rc, 0);
+  request_ids(rc);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        lc[i] = LDG(A.lconn + i * S + e);
-        shp[i][0] = LDG(A.shp + (3 * i) * S + e); shp[i][1] = LDG(A.shp + (3 * i + 1) * S + e); shp[i][2] = LDG(A.shp + (3 * i + 2) * S + e);
-        if (CHG == 1) {
+  for (int k = 0; k < NPT; ++k) {
+    const int i = tid + k * NT;
+    if (i < LS) {
 #pragma unroll
-          for (int m = 0; m < 4; ++m) ph[m][i] = LDG(A.phi + (8 * m + i) * S + e);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int li = lc[i] & EQD_LN_MASK;
-        const double vx = sv[li], vy = sv[LS + li], vz = sv[2 * LS + li];
-        const double s1 = shp[i][0], s2 = shp[i][1], s3 = shp[i][2];
-        // assembleGlobalKU.f90:215-246
-        sr[0] = sr[0] + s1 * vx;
-        sr[1] = sr[1] + s2 * vy;
-        sr[2] = sr[2] + s3 * vz;
-        sr[3] = sr[3] + s3 * vy + s2 * vz;
-        sr[4] = sr[4] + s3 * vx + s1 * vz;
-        sr[5] = sr[5] + s2 * vx + s1 * vy;
-        // :248-275
-        g[0][0] = g[0][0] + s1 * vx; g[1][1] = g[1][1] + s2 * vy; g[2][2] = g[2][2] + s3 * vz;
-        g[0][1] = g[0][1] + s1 * vy; g[1][0] = g[1][0] + s2 * vx;
-        g[0][2] = g[0][2] + s1 * vz; g[2][0] = g[2][0] + s3 * vx;
-        g[1][2] = g[1][2] + s2 * vz; g[2][1] = g[2][1] + s3 * vy;
-        if (CHG == 1) {
-          const double lx = sl[li], ly = sl[LS + li], lz = sl[2 * LS + li];
-#pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            const double p = ph[m][i];
-            phid[m][0] = phid[m][0] + p * lx;
-            phid[m][1] = phid[m][1] + p * ly;
-            phid[m][2] = phid[m][2] + p * lz;
-          }
-        } else if (CHG == 2) {
-          const int fi[4][8] = {{1, 1, -1, -1, -1, -1, 1, 1}, {1, -1, -1, 1, -1, 1, 1, -1},
-                                {1, -1, 1, -1, 1, -1, 1, -1}, {1, -1, 1, -1, -1, 1, -1, 1}};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            qv[0][j] = qv[0][j] + vx * fi[j][i];
-            qv[1][j] = qv[1][j] + vy * fi[j][i];
-            qv[2][j] = qv[2][j] + vz * fi[j][i];
-          }
-        }
-        if (BODY) {
-          const double em = LDG(A.emass + i * S + e);
-          body[3 * i] = 0.0 - (A.rdampm * vx) * em;
-          body[3 * i + 1] = 0.0 - (A.rdampm * vy) * em;
-          body[3 * i + 2] = 0.0 - (A.rdampm * vz + A.bodyz) * em;
-        }
-      }
-      const double lam = LDG(A.lam + e), mu = LDG(A.mu + e);
-      const double l2m = lam + 2.0 * mu;
-      double rate[6];
-      rate[0] = 0.0 + l2m * sr[0] + lam * sr[1] + lam * sr[2];
-      rate[1] = 0.0 + lam * sr[0] + l2m * sr[1] + lam * sr[2];
-      rate[2] = 0.0 + lam * sr[0] + lam * sr[1] + l2m * sr[2];
-      rate[3] = mu * sr[3];
-      rate[4] = mu * sr[4];
-      rate[5] = mu * sr[5];
-      const double dp[3] = {LDG(A.damps + e), LDG(A.damps + S + e), LDG(A.damps + 2 * S + e)};
-      const double rdt = 1 / dt;
-      // :277-311  s <- (coef*D + (1/dt - d/2) s) / (1/dt + d/2)
-      double s[15];
-#define PML_UPD(k, cf, D, a)                                           \
-  {                                                                    \
-    double x = (cf) * (D) + (rdt - dp[a] / 2) * A.stress[(k) * S + e]; \
-    x = x / (rdt + dp[a] / 2);                                         \
-    s[k] = x;                                                          \
-    A.stress[(k) * S + e] = x;                                         \
-  }
-      PML_UPD(0, l2m, g[0][0], 0) PML_UPD(1, lam, g[1][1], 1) PML_UPD(2, lam, g[2][2], 2)
-      PML_UPD(3, lam, g[0][0], 0) PML_UPD(4, l2m, g[1][1], 1) PML_UPD(5, lam, g[2][2], 2)
-      PML_UPD(6, lam, g[0][0], 0) PML_UPD(7, lam, g[1][1], 1) PML_UPD(8, l2m, g[2][2], 2)
-      PML_UPD(9, mu, g[0][1], 0) PML_UPD(10, mu, g[1][0], 1)
-      PML_UPD(11, mu, g[0][2], 0) PML_UPD(12, mu, g[2][0], 2)
-      PML_UPD(13, mu, g[1][2], 1) PML_UPD(14, mu, g[2][1], 2)
-#undef PML_UPD
-      sxx = s[0] + s[1] + s[2]; syy = s[3] + s[4] + s[5]; szz = s[6] + s[7] + s[8];
-      sxy = s[9] + s[10]; sxz = s[11] + s[12]; syz = s[13] + s[14];
-#pragma unroll
-      for (int i = 0; i < 6; ++i) s0[i] = LDG(A.stress + (15 + i) * S + e) + rdampk * rate[i];  // :320-325 (read-only slots)
-      const double det = LDG(A.det + e);
-      detw = det * A.w;
-      if (CHG == 1) {
-        double ssv[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) ssv[i] = LDG(A.ss + i * S + e);
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          hv[m][0] = ssv[0] * phid[m][0] + ssv[1] * phid[m][1] + ssv[2] * phid[m][2];
-          hv[m][1] = ssv[1] * phid[m][0] + ssv[3] * phid[m][1] + ssv[4] * phid[m][2];
-          hv[m][2] = ssv[2] * phid[m][0] + ssv[4] * phid[m][1] + ssv[5] * phid[m][2];
-        }
-      } else if (CHG == 2) {
-        coef = 0.25 * A.kapa_hg * LDG(A.rho + e) * LDG(A.vp + e) * pow(det * A.w, 2.0 / 3.0);
-      }
+      for (int j = 0; j < NROW; ++j) sf[j * LS + i] = 0.0;
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      double fo[12];
+  }
+  uint32_t parity = 0, parityN = 0;
+  mbar_wait(barN, parityN);
+  parityN ^= 1;
+  gather_nodes(rc);
+  finish_nodes();
+  __syncthreads();
+  while (true) {
+    const bool more = tnext < tEnd;
+    const int4 rnn = (tnext + (int)gridDim.x < tEnd) ? __ldg(A.tileRec + tnext + gridDim.x) : zero4;
+    if (more) request_ids(rn);
+    const int ne = TR_NE(rc), NC = TR_NC(rc);
+    for (int base = 0; base < ne; base += SE) {
+      const int le = base + lane;
+      const bool act = le < ne;
+      const size_t e = (size_t)TR_E0(rc) + (act ? le : 0);
+      unsigned lc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      // per role: up to 6 force rows per node, kept as coefficients so that few registers stay live
+      // role 0: c[0..2] = detw*(sxx, syy, szz)      force(i) = 0 - c * shp
+      // role 1: c[0..2] = detw*(sxy, sxz, syz)
+      // role 2: s0[6], body                          role 3: hv[4][3]
+      double c0 = 0, c1 = 0, c2 = 0, detw = 0;
+      double s0[6] = {0, 0, 0, 0, 0, 0};
+      double hv[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+      double body[BODY ? 24 : 1];
+      double qcoef = 0.0;
+      double qv[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+      mbar_wait(bar, parity);
+      parity ^= 1;
+#define OP(r) ops[(r) * SE + lane]
       if (act) {
-        const double s1 = shp[i][0], s2 = shp[i][1], s3 = shp[i][2];
-        // :328-344
-        fo[0] = 0.0 - detw * s1 * sxx;
-        fo[1] = 0.0 - detw * s2 * sxy;
-        fo[2] = 0.0 - detw * s3 * sxz;
-        fo[3] = 0.0 - detw * s1 * sxy;
-        fo[4] = 0.0 - detw * s2 * syy;
-        fo[5] = 0.0 - detw * s3 * syz;
-        fo[6] = 0.0 - detw * s1 * sxz;
-        fo[7] = 0.0 - detw * s2 * syz;
-        fo[8] = 0.0 - detw * s3 * szz;
-        double b0 = 0.0, b1 = 0.0, b2 = 0.0;
-        if (BODY) { b0 = body[3 * i]; b1 = body[3 * i + 1]; b2 = body[3 * i + 2]; }
-        double f9 = b0 - detw * (s1 * s0[0] + s3 * s0[4] + s2 * s0[5]);
-        double f10 = b1 - detw * (s2 * s0[1] + s3 * s0[3] + s1 * s0[5]);
-        double f11 = b2 - detw * (s3 * s0[2] + s2 * s0[3] + s1 * s0[4]);
-        if (CHG == 1) {
 #pragma unroll
-          for (int m = 0; m < 4; ++m) {
-            const double p = ph[m][i];
-            f9 = f9 - p * hv[m][0];
-            f10 = f10 - p * hv[m][1];
-            f11 = f11 - p * hv[m][2];
+        for (int i = 0; i < 8; ++i) lc[i] = slc[i * SE + lane];
+        const double lam = OP(PR_LAM), mu = OP(PR_MU);
+        const double l2m = lam + 2.0 * mu;
+        const double rdt = 1 / dt;
+        detw = OP(PR_DET) * A.w;
+        // :277-311  s <- (coef*D + (1/dt - d/2) s) / (1/dt + d/2)
+#define PML_UPD(k, cf, D, a, out)                                    \
+  {                                                                  \
+    const double dpa = OP(PR_DAMP + (a));                            \
+    double x = (cf) * (D) + (rdt - dpa / 2) * OP(PR_STRESS + (k));   \
+    x = x / (rdt + dpa / 2);                                         \
+    out = x;                                                         \
+    A.stress[(size_t)(k) * S + e] = x;                               \
+  }
+        if (role == 0) {
+          double g00 = 0, g11 = 0, g22 = 0;  // assembleGlobalKU.f90:248-275
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int li = lc[i] & EQD_LN_MASK;
+            g00 = g00 + OP(PR_SHP + 3 * i) * sv[li];
+            g11 = g11 + OP(PR_SHP + 3 * i + 1) * sv[LS + li];
+            g22 = g22 + OP(PR_SHP + 3 * i + 2) * sv[2 * LS + li];
           }
-        } else if (CHG == 2) {
-          const int fi[4][8] = {{1, 1, -1, -1, -1, -1, 1, 1}, {1, -1, -1, 1, -1, 1, 1, -1},
-                                {1, -1, 1, -1, 1, -1, 1, -1}, {1, -1, 1, -1, -1, 1, -1, 1}};
+          double s[9];
+          PML_UPD(0, l2m, g00, 0, s[0]) PML_UPD(1, lam, g11, 1, s[1]) PML_UPD(2, lam, g22, 2, s[2])
+          PML_UPD(3, lam, g00, 0, s[3]) PML_UPD(4, l2m, g11, 1, s[4]) PML_UPD(5, lam, g22, 2, s[5])
+          PML_UPD(6, lam, g00, 0, s[6]) PML_UPD(7, lam, g11, 1, s[7]) PML_UPD(8, l2m, g22, 2, s[8])
+          c0 = s[0] + s[1] + s[2]; c1 = s[3] + s[4] + s[5]; c2 = s[6] + s[7] + s[8];  // sxx, syy, szz
+        } else if (role == 1) {
+          double g01 = 0, g10 = 0, g02 = 0, g20 = 0, g12 = 0, g21 = 0;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            f9 = f9 - coef * qv[0][j] * fi[j][i];
-            f10 = f10 - coef * qv[1][j] * fi[j][i];
-            f11 = f11 - coef * qv[2][j] * fi[j][i];
+          for (int i = 0; i < 8; ++i) {
+            const int li = lc[i] & EQD_LN_MASK;
+            const double vx = sv[li], vy = sv[LS + li], vz = sv[2 * LS + li];
+            const double s1 = OP(PR_SHP + 3 * i), s2 = OP(PR_SHP + 3 * i + 1), s3 = OP(PR_SHP + 3 * i + 2);
+            g01 = g01 + s1 * vy; g10 = g10 + s2 * vx;
+            g02 = g02 + s1 * vz; g20 = g20 + s3 * vx;
+            g12 = g12 + s2 * vz; g21 = g21 + s3 * vy;
+          }
+          double s[6];
+          PML_UPD(9, mu, g01, 0, s[0]) PML_UPD(10, mu, g10, 1, s[1])
+          PML_UPD(11, mu, g02, 0, s[2]) PML_UPD(12, mu, g20, 2, s[3])
+          PML_UPD(13, mu, g12, 1, s[4]) PML_UPD(14, mu, g21, 2, s[5])
+          c0 = s[0] + s[1]; c1 = s[2] + s[3]; c2 = s[4] + s[5];  // sxy, sxz, syz
+        } else if (role == 2) {
+          double sr[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int li = lc[i] & EQD_LN_MASK;
+            const double vx = sv[li], vy = sv[LS + li], vz = sv[2 * LS + li];
+            const double s1 = OP(PR_SHP + 3 * i), s2 = OP(PR_SHP + 3 * i + 1), s3 = OP(PR_SHP + 3 * i + 2);
+            // assembleGlobalKU.f90:215-246
+            sr[0] = sr[0] + s1 * vx;
+            sr[1] = sr[1] + s2 * vy;
+            sr[2] = sr[2] + s3 * vz;
+            sr[3] = sr[3] + s3 * vy + s2 * vz;
+            sr[4] = sr[4] + s3 * vx + s1 * vz;
+            sr[5] = sr[5] + s2 * vx + s1 * vy;
+            if (BODY) {
+              const double em = LDG(A.emass + i * S + e);
+              body[3 * i] = 0.0 - (A.rdampm * vx) * em;
+              body[3 * i + 1] = 0.0 - (A.rdampm * vy) * em;
+              body[3 * i + 2] = 0.0 - (A.rdampm * vz + A.bodyz) * em;
+            }
+          }
+          double rate[6];
+          rate[0] = 0.0 + l2m * sr[0] + lam * sr[1] + lam * sr[2];
+          rate[1] = 0.0 + lam * sr[0] + l2m * sr[1] + lam * sr[2];
+          rate[2] = 0.0 + lam * sr[0] + lam * sr[1] + l2m * sr[2];
+          rate[3] = mu * sr[3];
+          rate[4] = mu * sr[4];
+          rate[5] = mu * sr[5];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) s0[i] = OP(PR_STRESS + 15 + i) + rdampk * rate[i];  // :320-325 (read-only slots)
+        } else {
+          if (CHG == 1) {
+            double phid[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int li = lc[i] & EQD_LN_MASK;
+              const double lx = sl[li], ly = sl[LS + li], lz = sl[2 * LS + li];
+#pragma unroll
+              for (int m = 0; m < 4; ++m) {
+                const double p = OP(PR_PHI + 8 * m + i);
+                phid[m][0] = phid[m][0] + p * lx;
+                phid[m][1] = phid[m][1] + p * ly;
+                phid[m][2] = phid[m][2] + p * lz;
+              }
+            }
+            double ssv[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) ssv[i] = OP(PR_SS + i);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              hv[m][0] = ssv[0] * phid[m][0] + ssv[1] * phid[m][1] + ssv[2] * phid[m][2];
+              hv[m][1] = ssv[1] * phid[m][0] + ssv[3] * phid[m][1] + ssv[4] * phid[m][2];
+              hv[m][2] = ssv[2] * phid[m][0] + ssv[4] * phid[m][1] + ssv[5] * phid[m][2];
+            }
+          } else {
+            const int fi[4][8] = {{1, 1, -1, -1, -1, -1, 1, 1}, {1, -1, -1, 1, -1, 1, 1, -1},
+                                  {1, -1, 1, -1, 1, -1, 1, -1}, {1, -1, 1, -1, -1, 1, -1, 1}};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int li = lc[i] & EQD_LN_MASK;
+              const double vx = sv[li], vy = sv[LS + li], vz = sv[2 * LS + li];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                qv[0][j] = qv[0][j] + vx * fi[j][i];
+                qv[1][j] = qv[1][j] + vy * fi[j][i];
+                qv[2][j] = qv[2][j] + vz * fi[j][i];
+              }
+            }
+            qcoef = 0.25 * A.kapa_hg * LDG(A.rho + e) * LDG(A.vp + e) * pow(OP(PR_DET) * A.w, 2.0 / 3.0);
           }
         }
-        fo[9] = f9; fo[10] = f10; fo[11] = f11;
+#undef PML_UPD
       }
-      const int li = lc[i] & EQD_LN_MASK, col = lc[i] >> EQD_LN_BITS;
-      for (int c = 0; c < T.NC; ++c) {
-        if (act && col == c) {
+      // shp / phi of the stage are still needed by the assembly phases below, so the
+      // next stage is requested only after them; the second CTA of the SM covers the gap
 #pragma unroll
-          for (int j = 0; j < 12; ++j) sf[j * LS + li] += fo[j];
+      for (int i = 0; i < 8; ++i) {
+        const int li = lc[i] & EQD_LN_MASK, col = lc[i] >> EQD_LN_BITS;
+        double fo[6] = {0, 0, 0, 0, 0, 0};
+        if (act) {
+          const double s1 = OP(PR_SHP + 3 * i), s2 = OP(PR_SHP + 3 * i + 1), s3 = OP(PR_SHP + 3 * i + 2);
+          if (role == 0) {         // :328-344, dofs 1,5,9
+            fo[0] = 0.0 - detw * s1 * c0;
+            fo[1] = 0.0 - detw * s2 * c1;
+            fo[2] = 0.0 - detw * s3 * c2;
+          } else if (role == 1) {  // dofs 2,3,4,6,7,8
+            fo[0] = 0.0 - detw * s2 * c0;
+            fo[1] = 0.0 - detw * s3 * c1;
+            fo[2] = 0.0 - detw * s1 * c0;
+            fo[3] = 0.0 - detw * s3 * c2;
+            fo[4] = 0.0 - detw * s1 * c1;
+            fo[5] = 0.0 - detw * s2 * c2;
+          } else if (role == 2) {  // dofs 10-12
+            double b0 = 0.0, b1 = 0.0, b2 = 0.0;
+            if (BODY) { b0 = body[3 * i]; b1 = body[3 * i + 1]; b2 = body[3 * i + 2]; }
+            fo[0] = b0 - detw * (s1 * s0[0] + s3 * s0[4] + s2 * s0[5]);
+            fo[1] = b1 - detw * (s2 * s0[1] + s3 * s0[3] + s1 * s0[5]);
+            fo[2] = b2 - detw * (s3 * s0[2] + s2 * s0[3] + s1 * s0[4]);
+          } else {                 // hourglass, own rows 13-15
+            if (CHG == 1) {
+#pragma unroll
+              for (int m = 0; m < 4; ++m) {
+                const double p = OP(PR_PHI + 8 * m + i);
+                fo[0] = fo[0] - p * hv[m][0];
+                fo[1] = fo[1] - p * hv[m][1];
+                fo[2] = fo[2] - p * hv[m][2];
+              }
+            } else {
+              const int fi[4][8] = {{1, 1, -1, -1, -1, -1, 1, 1}, {1, -1, -1, 1, -1, 1, 1, -1},
+                                    {1, -1, 1, -1, 1, -1, 1, -1}, {1, -1, 1, -1, -1, 1, -1, 1}};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                fo[0] = fo[0] - qcoef * qv[0][j] * fi[j][i];
+                fo[1] = fo[1] - qcoef * qv[1][j] * fi[j][i];
+                fo[2] = fo[2] - qcoef * qv[2][j] * fi[j][i];
+              }
+            }
+          }
         }
-        __syncthreads();
+        for (int c = 0; c < NC; ++c) {
+          if (act && col == c) {
+            if (role == 0) { sf[0 * LS + li] += fo[0]; sf[4 * LS + li] += fo[1]; sf[8 * LS + li] += fo[2]; }
+            else if (role == 1) {
+              sf[1 * LS + li] += fo[0]; sf[2 * LS + li] += fo[1]; sf[3 * LS + li] += fo[2];
+              sf[5 * LS + li] += fo[3]; sf[6 * LS + li] += fo[4]; sf[7 * LS + li] += fo[5];
+            } else if (role == 2) { sf[9 * LS + li] += fo[0]; sf[10 * LS + li] += fo[1]; sf[11 * LS + li] += fo[2]; }
+            else { sf[12 * LS + li] += fo[0]; sf[13 * LS + li] += fo[1]; sf[14 * LS + li] += fo[2]; }
+          }
+          __syncthreads();
+        }
+      }
+#undef OP
+      const bool last = base + SE >= ne;
+      if (!last) request(rc, base + SE);
+      else if (more) {
+        request(rn, 0);
+        mbar_wait(barN, parityN);
+        parityN ^= 1;
+        gather_nodes(rn);
       }
     }
-  }
-  for (int i = tid; i < T.LN; i += NT) {
+    // ---- flush
 #pragma unroll
-    for (int j = 0; j < 12; ++j) A.pf[(size_t)j * A.PFS + T.nb + i] = sf[j * LS + i];
+    for (int k = 0; k < NPT; ++k) {
+      const int i = tid + k * NT;
+      if (i < LS) {
+        if (i < TR_LN(rc)) {
+#pragma unroll
+          for (int j = 0; j < 9; ++j) A.pf[(size_t)j * A.PFS + TR_NB(rc) + i] = sf[j * LS + i];
+#pragma unroll
+          for (int j = 9; j < 12; ++j) A.pf[(size_t)j * A.PFS + TR_NB(rc) + i] = sf[j * LS + i] + sf[(j + 3) * LS + i];
+        }
+#pragma unroll
+        for (int j = 0; j < NROW; ++j) sf[j * LS + i] = 0.0;
+      }
+    }
+    if (!more) break;
+    finish_nodes();
+    __syncthreads();
+    rc = rn; rn = rnn; tnext += gridDim.x;
   }
 }
 
@@ -1188,7 +1341,8 @@ static inline int nblk(long n, int b) { return (int)((n + b - 1) / b); }
 void launch_advance(StepState* st, double dt, cudaStream_t s) { k_advance<<<1, 1, 0, s>>>(st, dt); }
 
 void launch_node_update(const NodeArgs& A, cudaStream_t s) {
-  if (A.Nn > 0) k_node_update<<<nblk(A.Nn, 256), 256, 0, s>>>(A);
+  if (A.Nn > 0) k_node_update3<<<nblk(A.Nn, 256), 256, 0, s>>>(A);
+  if (A.Np > 0) k_node_update12<<<nblk(A.Np, 128), 128, 0, s>>>(A);
 }
 void launch_assemble_special(const NodeArgs& A, const int* list, int n, cudaStream_t s) {
   if (n > 0) k_assemble_special<<<nblk(n, 128), 128, 0, s>>>(A, list, n);
@@ -1199,7 +1353,9 @@ void launch_materialize_accel(const NodeArgs& A, double* out, cudaStream_t s) {
 
 // dynamic shared memory of a tile kernel of class `cls` whose largest tile has LS nodes
 size_t tile_smem_bytes(int cls, bool q, int LS) {
-  if (cls == CLS_PML) return (size_t)18 * LS * sizeof(double);
+  if (cls == CLS_PML)
+    return 128 + (size_t)PR_ROWS * EQD_STAGE_PML * sizeof(double) + 8 * EQD_STAGE_PML * sizeof(uint16_t) + (size_t)EQD_PML_LS * sizeof(int) +
+           (size_t)21 * EQD_PML_LS * sizeof(double);
   (void)LS;
   return 128 + (size_t)RR_ROWS * EQD_STAGE * sizeof(double) + 8 * EQD_STAGE * sizeof(uint16_t) + (size_t)EQD_REG_LS * sizeof(int) +
          (size_t)(q ? 15 : 12) * EQD_REG_LS * sizeof(double);
@@ -1252,10 +1408,11 @@ void launch_elem_reg(const ElemArgs& A, bool split, bool plastic, bool q, bool b
   else launch_reg_split<false>(A, plastic, q, body, chg, s);
 }
 void launch_elem_pml(const ElemArgs& A, bool body, int chg, cudaStream_t s) {
-  const int ntiles = A.ntiles;
+  int ntiles = A.ntiles;
   if (ntiles <= 0) return;
   const size_t sm = tile_smem_bytes(CLS_PML, false, A.LS);
-  const int nt = EQD_TILE_THREADS;
+  const int nt = 4 * EQD_STAGE_PML;
+  ntiles = std::min(ntiles, 2 * sm_count());
   if (body) { if (chg == 2) tile_launch(k_tile_pml<true, 2>, A, ntiles, nt, sm, s); else tile_launch(k_tile_pml<true, 1>, A, ntiles, nt, sm, s); }
   else { if (chg == 2) tile_launch(k_tile_pml<false, 2>, A, ntiles, nt, sm, s); else tile_launch(k_tile_pml<false, 1>, A, ntiles, nt, sm, s); }
 }

@@ -234,10 +234,11 @@ extern "C" int eqd_plan_check(int32_t Nn, int32_t Ne, const int32_t* nodeElemIdR
     std::vector<char> seen(Ne, 0);
     for (int c = 0; c < 3; ++c) {
       TileShape sh;
-      if (c == CLS_PML) { sh.bx = 3; sh.bz = 3; sh.by = 32; sh.capE = 384; sh.capN = 800; }
+      if (c == CLS_PML) { sh.bx = 3; sh.bz = 3; sh.by = 24; sh.capE = 320; sh.capN = EQD_PML_LS; }
       else { sh.bx = 4; sh.bz = 4; sh.by = 16; sh.capE = 384; sh.capN = EQD_REG_LS; }
+      const int NTP = c == CLS_PML ? EQD_STAGE_PML : EQD_STAGE;
       TilePlan P;
-      plan_tiles(conn.data(), members[c], Nn, ny, nz, ok, sh, EQD_TILE_THREADS, P);
+      plan_tiles(conn.data(), members[c], Nn, ny, nz, ok, sh, NTP, P);
       int64_t* st = stats + 8 * c;
       st[0] = P.nTiles; st[1] = P.n; st[2] = P.S; st[3] = P.PFS; st[4] = P.LS; st[5] = 0; st[6] = 0; st[7] = ok;
       if (P.n == 0) continue;
@@ -250,11 +251,11 @@ extern "C" int eqd_plan_check(int32_t Nn, int32_t Ne, const int32_t* nodeElemIdR
         st[6] += P.tileColours[t] > 1;
         // replay the kernel's assembly schedule and look for write conflicts
         std::vector<int> owner(ln);
-        for (int base = 0; base < P.tileCnt[t]; base += EQD_TILE_THREADS)
+        for (int base = 0; base < P.tileCnt[t]; base += NTP)
           for (int i = 0; i < 8; ++i)
             for (int col = 0; col < P.tileColours[t]; ++col) {
               std::fill(owner.begin(), owner.end(), -1);
-              for (int le = base; le < std::min(P.tileCnt[t], base + EQD_TILE_THREADS); ++le) {
+              for (int le = base; le < std::min(P.tileCnt[t], base + NTP); ++le) {
                 const size_t s = (size_t)P.tileElem[t] + le;
                 const unsigned u = P.lconn[(size_t)i * P.S + s];
                 if ((int)(u >> EQD_LN_BITS) != col) continue;
