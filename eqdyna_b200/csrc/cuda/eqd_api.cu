@@ -147,8 +147,9 @@ struct eqd_handle {
   bool body = false, plastic = false, qmode = false;
   // ---- device
   ElemClass cls[3];
-  DevBuf<int> dInfo, dPmlNode, dSlotStart, dSpecial;
-  DevBuf<uint32_t> dSlots;
+  DevBuf<int> dInfo, dPmlNode, dSpecial;
+  DevBuf<uint8_t> dSlotCnt;
+  DevBuf<uint32_t> dSlotTab;
   DevBuf<double> dVel, dDisp, dMass, dV1p, dDampp, dForce, dAccel0;
   int nSpecial = 0;
   DevBuf<StepState> dState;
@@ -283,7 +284,7 @@ NodeArgs eqd_handle::nodeArgs() const {
   A.Nn = Nn; A.NnS = NnS; A.Np = Np; A.NpS = NpS;
   A.info = dInfo.p; A.pmlNode = dPmlNode.p; A.vel = dVel.p; A.disp = dDisp.p; A.mass = dMass.p;
   A.v1p = dV1p.p; A.dampp = dDampp.p; A.force = dForce.p;
-  A.slotStart = dSlotStart.p; A.slots = dSlots.p;
+  A.slotCnt = dSlotCnt.p; A.slotTab = dSlotTab.p;
   A.pfR = cls[CLS_REG].pf.p; A.SR = cls[CLS_REG].PFS;
   A.pfX = cls[CLS_REGX].pf.p; A.SX = cls[CLS_REGX].PFS;
   A.pfP = cls[CLS_PML].pf.p; A.SP = cls[CLS_PML].PFS;
@@ -769,17 +770,19 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
         C.qmem.alloc(6 * (size_t)C.S);
       }
     }
-    // ---- node -> tile-node slots CSR, by class then ascending tile id
-    std::vector<int> start(Nn + 1, 0);
-    for (int c = 0; c < 3; ++c)
-      for (int nd : h->cls[c].tnodeH) if (nd >= 0 && EQD_INFO_KIND(h->info[nd]) != KIND_FIXED) start[nd + 1]++;
-    for (int n = 0; n < Nn; ++n) {
-      need((long)start[n] + start[n + 1] < 2147483647L, "eqd_set_mesh: slot table overflow");
-      start[n + 1] += start[n];
-    }
-    std::vector<uint32_t> slots(start[Nn]);
+    // ---- node -> tile-node slots by rank, class then ascending tile id
     {
-      std::vector<int> fill(start.begin(), start.end() - 1);
+      std::vector<uint8_t> cnt(Nn, 0);
+      int maxCnt = 2;
+      for (int c = 0; c < 3; ++c)
+        for (int nd : h->cls[c].tnodeH)
+          if (nd >= 0 && EQD_INFO_KIND(h->info[nd]) != KIND_FIXED) {
+            need(cnt[nd] < 255, "eqd_set_mesh: a node belongs to more than 255 tiles");
+            maxCnt = std::max(maxCnt, (int)++cnt[nd]);
+          }
+      const size_t NS = h->NnS;
+      std::vector<uint32_t> tab((size_t)maxCnt * NS, 0);
+      std::fill(cnt.begin(), cnt.end(), 0);
       for (int c = 0; c < 3; ++c) {
         const std::vector<int>& tn = h->cls[c].tnodeH;
         for (size_t s = 0; s < tn.size(); ++s) {
@@ -788,12 +791,12 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
           const int kind = EQD_INFO_KIND(h->info[nd]);
           if (kind == KIND_FIXED) continue;
           need(!(c == CLS_REG && kind == KIND_PML12), "internal: REG element on a 12-dof node");
-          slots[fill[nd]++] = EQD_SLOT(c, s);
+          tab[(size_t)cnt[nd]++ * NS + nd] = EQD_SLOT(c, s);
         }
       }
+      h->dSlotCnt.upload(cnt);
+      h->dSlotTab.upload(tab);
     }
-    h->dSlotStart.upload(start);
-    h->dSlots.upload(slots);
     // ---- PML node damping profile (comdampv, recomputed every step in the reference)
     std::vector<double> dp(3 * (size_t)h->NpS, 0.0);
     for (int n = 0; n < Nn; ++n)

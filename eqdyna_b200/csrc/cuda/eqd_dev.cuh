@@ -17,7 +17,7 @@
 //             FIXED order (8 local-node phases, host-coloured where two elements
 //             of one phase share a node: no atomics), then writes ONE partial
 //             force row per tile node: pf[rows][slot]
-//   assembly  node -> tile-node slots CSR (class, tile ascending); a node's
+//   assembly  node -> tile-node slots, stored by rank (class, tile ascending); a node's
 //             force is the ordered sum of its 1..8 tile partials, fused into
 //             the next node update
 //   special   nodes whose force is needed between the element sweep and the
@@ -63,8 +63,8 @@ struct NodeArgs {
   double* v1p;           // [12][NpS]
   const double* dampp;   // [3][NpS]
   double* force;         // [3][NnS] + [12][NpS] (forcep = force + 3*NnS)
-  const int* slotStart;  // [Nn+1]
-  const uint32_t* slots; // EQD_SLOT entries
+  const uint8_t* slotCnt;   // [Nn] tile-node slots of the node (0 for fixed nodes)
+  const uint32_t* slotTab;  // [maxCnt][NnS] EQD_SLOT entries by rank (class, then ascending tile id)
   const double* pfR; int SR;   // [3][SR]  tile partials, REG
   const double* pfX; int SX;   // [6][SX]  REGX: KU | hourglass
   const double* pfP; int SP;   // [12][SP] PML

@@ -24,6 +24,14 @@ void upload_qtab(const QTab* t) { cudaMemcpyToSymbol(c_qtab, t, sizeof(QTab) * 1
 
 #define LDG(p) __ldg(p)
 
+// loads the compiler must issue where they are written (it otherwise sinks them
+// below early exits and branches, which turns independent DRAM round trips into a chain)
+__device__ __forceinline__ double ld_now(const double* p) { double v; asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; }
+__device__ __forceinline__ double ldc_now(const double* p) { double v; asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; }
+__device__ __forceinline__ uint32_t ldc_now(const uint32_t* p) { uint32_t v; asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ int ldc_now(const int* p) { int v; asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ int ldc_now(const uint8_t* p) { uint32_t v; asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p)); return (int)v; }
+
 // ----------------------------------------------------------------------------
 // step counter: driver.f90:11 (timeElapsed = timeElapsed + dt)
 __global__ void k_advance(StepState* st, double dt) {
@@ -36,39 +44,46 @@ __global__ void k_advance(StepState* st, double dt) {
 // scatter-add of assembleGlobalKU.f90:28-35,47-63 and hrglss.f90:42-54: same
 // contributions; fixed order = 8 local-node phases inside a tile, then the
 // node's tiles by class and ascending tile id).
-__device__ __forceinline__ void gather3(const NodeArgs& A, int n, double f[3]) {
-  const int b = LDG(A.slotStart + n), e = LDG(A.slotStart + n + 1);
-  f[0] = f[1] = f[2] = 0.0;
-  for (int k = b; k < e; ++k) {
-    const uint32_t u = LDG(A.slots + k);
-    const int cls = u & 3;
-    const size_t idx = u >> 2;
-    if (cls == CLS_REG) {
-      const double* p = A.pfR + idx;
-      f[0] += p[0]; f[1] += p[A.SR]; f[2] += p[2 * (size_t)A.SR];
-    } else if (cls == CLS_PML) {
-      // 3-dof node of a PML element: assembleGlobalKU.f90:55-61
-      const double* p = A.pfP + idx;
-      const size_t S = A.SP;
-      f[0] = f[0] + p[0] + p[S] + p[2 * S] + p[9 * S];
-      f[1] = f[1] + p[3 * S] + p[4 * S] + p[5 * S] + p[10 * S];
-      f[2] = f[2] + p[6 * S] + p[7 * S] + p[8 * S] + p[11 * S];
-    } else {
-      const double* p = A.pfX + idx;
-      const size_t S = A.SX;
-      f[0] = f[0] + p[0] + p[3 * S];
-      f[1] = f[1] + p[S] + p[4 * S];
-      f[2] = f[2] + p[2 * S] + p[5 * S];
-    }
+__device__ __forceinline__ void add3(const NodeArgs& A, uint32_t u, double f[3]) {
+  const int cls = u & 3;
+  const size_t idx = u >> 2;
+  if (cls == CLS_REG) {
+    const double* p = A.pfR + idx;
+    f[0] += p[0]; f[1] += p[A.SR]; f[2] += p[2 * (size_t)A.SR];
+  } else if (cls == CLS_PML) {
+    // 3-dof node of a PML element: assembleGlobalKU.f90:55-61
+    const double* p = A.pfP + idx;
+    const size_t S = A.SP;
+    f[0] = f[0] + p[0] + p[S] + p[2 * S] + p[9 * S];
+    f[1] = f[1] + p[3 * S] + p[4 * S] + p[5 * S] + p[10 * S];
+    f[2] = f[2] + p[6 * S] + p[7 * S] + p[8 * S] + p[11 * S];
+  } else {
+    const double* p = A.pfX + idx;
+    const size_t S = A.SX;
+    f[0] = f[0] + p[0] + p[3 * S];
+    f[1] = f[1] + p[S] + p[4 * S];
+    f[2] = f[2] + p[2 * S] + p[5 * S];
   }
 }
+// The slot table is stored by rank: slotTab[k][n] = k-th tile-node slot of node n,
+// so a warp of consecutive nodes reads consecutive words and the first two ranks
+// can be fetched together with `info` (one level of the dependent-load chain less).
+__device__ __forceinline__ void gather3(const NodeArgs& A, int n, int cnt, uint32_t u0, uint32_t u1, double f[3]) {
+  f[0] = f[1] = f[2] = 0.0;
+  if (cnt > 0) add3(A, u0, f);
+  if (cnt > 1) add3(A, u1, f);
+  for (int k = 2; k < cnt; ++k) add3(A, LDG(A.slotTab + (size_t)k * A.NnS + n), f);
+}
+__device__ __forceinline__ void gather3(const NodeArgs& A, int n, int cnt, double f[3]) {
+  f[0] = f[1] = f[2] = 0.0;
+  for (int k = 0; k < cnt; ++k) add3(A, LDG(A.slotTab + (size_t)k * A.NnS + n), f);
+}
 
-__device__ __forceinline__ void gather12(const NodeArgs& A, int n, double f[12]) {
-  const int b = LDG(A.slotStart + n), e = LDG(A.slotStart + n + 1);
+__device__ __forceinline__ void gather12(const NodeArgs& A, int n, int cnt, double f[12]) {
 #pragma unroll
   for (int j = 0; j < 12; ++j) f[j] = 0.0;
-  for (int k = b; k < e; ++k) {
-    const uint32_t u = LDG(A.slots + k);
+  for (int k = 0; k < cnt; ++k) {
+    const uint32_t u = LDG(A.slotTab + (size_t)k * A.NnS + n);
     const int cls = u & 3;
     const size_t idx = u >> 2;
     if (cls == CLS_PML) {
@@ -91,37 +106,49 @@ __device__ __forceinline__ void gather12(const NodeArgs& A, int n, double f[12])
 // previous step's `nodalForceArr/nodalMassArr` (driver.f90:29).  Two kernels so
 // that the 3-dof one (almost every node) stays light enough for full occupancy:
 // its gather is a chain of dependent loads that only parallelism hides.
-__global__ void __launch_bounds__(256, 6) k_node_update3(NodeArgs A) {
+__global__ void __launch_bounds__(256, 4) k_node_update3(NodeArgs A) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= A.Nn) return;
-  const int info = LDG(A.info + n);
-  if (EQD_INFO_KIND(info) != KIND_FREE3) return;  // fixed: vel = disp = 0 for ever (driver.f90:142-145)
-  const double dt = A.dt;
   const size_t NS = A.NnS;
-  double a[3];
+  // every independent load first: the stores below may alias them for the compiler,
+  // which would otherwise serialise six DRAM round trips per node
+  const int info = ldc_now(A.info + n);
+  const uint32_t u0 = ldc_now(A.slotTab + n), u1 = ldc_now(A.slotTab + NS + n);
+  const int cnt0 = ldc_now(A.slotCnt + n);
+  const double m = ldc_now(A.mass + n);
+  double v[3], d[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { v[j] = ld_now(A.vel + j * NS + n); d[j] = ld_now(A.disp + j * NS + n); }
+  // no early exit: fixed and PML nodes run through with an empty gather and skip the
+  // stores (vel = disp = 0 for ever for fixed nodes, driver.f90:142-145)
+  const bool mine = EQD_INFO_KIND(info) == KIND_FREE3;
+  const int cnt = mine ? cnt0 : 0;
+  const double dt = A.dt;
+  double a[3] = {0.0, 0.0, 0.0};
   if (A.accel0) {
-    a[0] = A.accel0[n]; a[1] = A.accel0[NS + n]; a[2] = A.accel0[2 * NS + n];
+    if (mine) { a[0] = A.accel0[n]; a[1] = A.accel0[NS + n]; a[2] = A.accel0[2 * NS + n]; }
   } else {
-    const double m = LDG(A.mass + n);
     double f[3];
-    if (EQD_INFO_SPECIAL(info)) {
+    if (mine && EQD_INFO_SPECIAL(info)) {
       f[0] = A.force[n]; f[1] = A.force[NS + n]; f[2] = A.force[2 * NS + n];
     } else {
-      gather3(A, n, f);
+      gather3(A, n, cnt, u0, u1, f);
     }
     a[0] = f[0] / m; a[1] = f[1] / m; a[2] = f[2] / m;
   }
   bool bad = false;
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    double v = A.vel[j * NS + n];
-    v = v + a[j] * dt;                      // driver.f90:102
-    A.vel[j * NS + n] = v;                  // :103
-    A.disp[j * NS + n] = A.disp[j * NS + n] + v * dt;  // :104
-    bad |= (v != v);
+    v[j] = v[j] + a[j] * dt;                // driver.f90:102
+    d[j] = d[j] + v[j] * dt;                // :104
+    bad |= (v[j] != v[j]);
   }
-  if (bad) {
-    if (atomicExch(&A.st->nanFlag, 1) == 0) A.st->nanNode = n + 1;
+  if (mine) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { A.vel[j * NS + n] = v[j]; A.disp[j * NS + n] = d[j]; }  // :103
+    if (bad) {
+      if (atomicExch(&A.st->nanFlag, 1) == 0) A.st->nanNode = n + 1;
+    }
   }
 }
 
@@ -129,11 +156,19 @@ __global__ void __launch_bounds__(256, 6) k_node_update3(NodeArgs A) {
 __global__ void __launch_bounds__(128) k_node_update12(NodeArgs A) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= A.Np) return;
-  const int n = LDG(A.pmlNode + slot);
-  const int info = LDG(A.info + n);
-  const double dt = A.dt;
   const size_t NS = A.NnS, PS = A.NpS;
-  const double m = LDG(A.mass + n);
+  const int n = ldc_now(A.pmlNode + slot);
+  double v1[12], d[3];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) v1[j] = ld_now(A.v1p + j * PS + slot);
+  d[0] = ldc_now(A.dampp + slot); d[1] = ldc_now(A.dampp + PS + slot); d[2] = ldc_now(A.dampp + 2 * PS + slot);
+  const int info = ldc_now(A.info + n);
+  const int cnt = ldc_now(A.slotCnt + n);
+  const double m = ldc_now(A.mass + n);
+  double dis[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) dis[j] = ld_now(A.disp + j * NS + n);
+  const double dt = A.dt;
   double a[12];
   if (A.accel0) {
     const double* ap = A.accel0 + 3 * NS;
@@ -146,25 +181,22 @@ __global__ void __launch_bounds__(128) k_node_update12(NodeArgs A) {
 #pragma unroll
       for (int j = 0; j < 12; ++j) f[j] = fp[j * PS + slot];
     } else {
-      gather12(A, n, f);
+      gather12(A, n, cnt, f);
     }
 #pragma unroll
     for (int j = 0; j < 12; ++j) a[j] = f[j] / m;
   }
-  double d[3], v[12];
-  d[0] = LDG(A.dampp + slot); d[1] = LDG(A.dampp + PS + slot); d[2] = LDG(A.dampp + 2 * PS + slot);
+  double v[12];
   const double rdt = 1.0 / dt;
 #pragma unroll
   for (int j = 0; j < 9; ++j) {             // driver.f90:112-117, dampv(j) = damp(mod(j-1,3)+1)
     const double dj = d[j % 3];
-    v[j] = (a[j] + A.v1p[j * PS + slot] * (rdt - dj / 2.0)) / (rdt + dj / 2.0);
-    A.v1p[j * PS + slot] = v[j];
+    v[j] = (a[j] + v1[j] * (rdt - dj / 2.0)) / (rdt + dj / 2.0);
   }
 #pragma unroll
-  for (int j = 9; j < 12; ++j) {            // :118-123
-    v[j] = A.v1p[j * PS + slot] + a[j] * dt;
-    A.v1p[j * PS + slot] = v[j];
-  }
+  for (int j = 9; j < 12; ++j) v[j] = v1[j] + a[j] * dt;   // :118-123
+#pragma unroll
+  for (int j = 0; j < 12; ++j) A.v1p[j * PS + slot] = v[j];
   double vel[3];
   vel[0] = v[0] + v[1] + v[2] + v[9];       // :125-141
   vel[1] = v[3] + v[4] + v[5] + v[10];
@@ -173,7 +205,7 @@ __global__ void __launch_bounds__(128) k_node_update12(NodeArgs A) {
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     A.vel[j * NS + n] = vel[j];
-    A.disp[j * NS + n] = A.disp[j * NS + n] + vel[j] * dt;
+    A.disp[j * NS + n] = dis[j] + vel[j] * dt;
     bad |= (vel[j] != vel[j]);
   }
   if (bad) {
@@ -191,11 +223,11 @@ __global__ void __launch_bounds__(128) k_assemble_special(NodeArgs A, const int*
   const size_t NS = A.NnS;
   if (kind == KIND_FREE3) {
     double f[3];
-    gather3(A, n, f);
+    gather3(A, n, LDG(A.slotCnt + n), f);
     A.force[n] = f[0]; A.force[NS + n] = f[1]; A.force[2 * NS + n] = f[2];
   } else if (kind == KIND_PML12) {
     double f[12];
-    gather12(A, n, f);
+    gather12(A, n, LDG(A.slotCnt + n), f);
     const int slot = EQD_INFO_SLOT(info);
     double* fp = A.force + 3 * NS;
 #pragma unroll
@@ -215,7 +247,7 @@ __global__ void k_materialize_accel(NodeArgs A, double* __restrict__ out) {
     double f[3];
     if (A.accel0) { out[n] = A.accel0[n]; out[NS + n] = A.accel0[NS + n]; out[2 * NS + n] = A.accel0[2 * NS + n]; return; }
     if (EQD_INFO_SPECIAL(info)) { f[0] = A.force[n]; f[1] = A.force[NS + n]; f[2] = A.force[2 * NS + n]; }
-    else gather3(A, n, f);
+    else gather3(A, n, LDG(A.slotCnt + n), f);
     out[n] = f[0] / m; out[NS + n] = f[1] / m; out[2 * NS + n] = f[2] / m;
   } else if (kind == KIND_PML12) {
     const int slot = EQD_INFO_SLOT(info);
@@ -226,7 +258,7 @@ __global__ void k_materialize_accel(NodeArgs A, double* __restrict__ out) {
       return;
     }
     if (EQD_INFO_SPECIAL(info)) { for (int j = 0; j < 12; ++j) f[j] = A.force[3 * NS + j * PS + slot]; }
-    else gather12(A, n, f);
+    else gather12(A, n, LDG(A.slotCnt + n), f);
     for (int j = 0; j < 12; ++j) out[3 * NS + j * PS + slot] = f[j] / m;
   }
 }
@@ -792,13 +824,15 @@ __global__ void __launch_bounds__(4 * EQD_STAGE_PML, 2) k_tile_pml(ElemArgs A) {
         const double rdt = 1 / dt;
         detw = OP(PR_DET) * A.w;
         // :277-311  s <- (coef*D + (1/dt - d/2) s) / (1/dt + d/2)
-#define PML_UPD(k, cf, D, a, out)                                    \
-  {                                                                  \
-    const double dpa = OP(PR_DAMP + (a));                            \
-    double x = (cf) * (D) + (rdt - dpa / 2) * OP(PR_STRESS + (k));   \
-    x = x / (rdt + dpa / 2);                                         \
-    out = x;                                                         \
-    A.stress[(size_t)(k) * S + e] = x;                               \
+        // the three denominators are formed once per element and applied as reciprocals
+        // (15 divisions -> 3; differs from the reference's `/` by at most one rounding)
+        const double dh[3] = {OP(PR_DAMP) / 2, OP(PR_DAMP + 1) / 2, OP(PR_DAMP + 2) / 2};
+        const double rden[3] = {1.0 / (rdt + dh[0]), 1.0 / (rdt + dh[1]), 1.0 / (rdt + dh[2])};
+#define PML_UPD(k, cf, D, a, out)                                         \
+  {                                                                       \
+    const double x = ((cf) * (D) + (rdt - dh[a]) * OP(PR_STRESS + (k))) * rden[a]; \
+    out = x;                                                              \
+    A.stress[(size_t)(k) * S + e] = x;                                    \
   }
         if (role == 0) {
           double g00 = 0, g11 = 0, g22 = 0;  // assembleGlobalKU.f90:248-275
@@ -905,10 +939,10 @@ __global__ void __launch_bounds__(4 * EQD_STAGE_PML, 2) k_tile_pml(ElemArgs A) {
       }
       // shp / phi of the stage are still needed by the assembly phases below, so the
       // next stage is requested only after them; the second CTA of the SM covers the gap
+      // force of local node i (registers + the stage's shp / phi rows)
+      auto node_force = [&](int i, double fo[6]) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int li = lc[i] & EQD_LN_MASK, col = lc[i] >> EQD_LN_BITS;
-        double fo[6] = {0, 0, 0, 0, 0, 0};
+        for (int j = 0; j < 6; ++j) fo[j] = 0.0;
         if (act) {
           const double s1 = OP(PR_SHP + 3 * i), s2 = OP(PR_SHP + 3 * i + 1), s3 = OP(PR_SHP + 3 * i + 2);
           if (role == 0) {         // :328-344, dofs 1,5,9
@@ -949,6 +983,13 @@ __global__ void __launch_bounds__(4 * EQD_STAGE_PML, 2) k_tile_pml(ElemArgs A) {
             }
           }
         }
+      };
+      double fo[6];
+      node_force(0, fo);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int li = lc[i] & EQD_LN_MASK, col = lc[i] >> EQD_LN_BITS;
+        double fn[6] = {0, 0, 0, 0, 0, 0};
         for (int c = 0; c < NC; ++c) {
           if (act && col == c) {
             if (role == 0) { sf[0 * LS + li] += fo[0]; sf[4 * LS + li] += fo[1]; sf[8 * LS + li] += fo[2]; }
@@ -958,8 +999,12 @@ __global__ void __launch_bounds__(4 * EQD_STAGE_PML, 2) k_tile_pml(ElemArgs A) {
             } else if (role == 2) { sf[9 * LS + li] += fo[0]; sf[10 * LS + li] += fo[1]; sf[11 * LS + li] += fo[2]; }
             else { sf[12 * LS + li] += fo[0]; sf[13 * LS + li] += fo[1]; sf[14 * LS + li] += fo[2]; }
           }
+          // the next node's force is formed while the CTA drains into the barrier
+          if (c == NC - 1 && i < 7) node_force(i + 1, fn);
           __syncthreads();
         }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) fo[j] = fn[j];
       }
 #undef OP
       const bool last = base + SE >= ne;
