@@ -1,0 +1,75 @@
+"""Multi-process / multi-GPU parity (-m gpu, needs >= 2 devices; skipped on a
+single-GPU box): one process per sub-domain, nodal-force halos over
+ncclSend/ncclRecv exactly as `bench.py --gpus N` runs them, compared with the
+CPU oracle of the same decomposition at the contract tolerance."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+import parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world_size, port, case, decomp, nstep, out):
+    sys.path.insert(0, parity.ROOT)
+    sys.path.insert(0, os.path.join(parity.ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    from eqdyna_b200 import device as dev
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    w = parity.build_world(case, decomp, nstep)   # whole world on the host: init-time shared sums done
+    v = w.view(rank)
+    d = dev.Domain(v, device=rank % torch.cuda.device_count())
+    ids = [dev.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    d.set_comm(ids[0], world_size, rank)
+    n = v.nstep
+    d.run(1, n // 2)          # two chunks: the halo state must survive a return to the host
+    d.run(n // 2 + 1, n)
+    d.fetch_into_view()
+    np.savez(os.path.join(out, "rank%d.npz" % rank), disp=v.dispArr, vel=v.velArr, fric=v.fric, fnft=v.fnft,
+             hist=v.onFaultQuantHistSCECForm)
+    dist.barrier()
+    d.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("case,decomp,nstep", [("test.tpv8", (2, 1, 1), 0), ("test.tpv104", (1, 2, 1), 60)],
+                         ids=["tpv8-2x1x1", "tpv104-1x2x1-fault-on-rank-face"])
+def test_nccl_processes_match_oracle(tmp_path, case, decomp, nstep):
+    import torch
+    import torch.multiprocessing as mp
+    n = decomp[0] * decomp[1] * decomp[2]
+    if torch.cuda.device_count() < n:
+        pytest.skip("needs %d GPUs" % n)
+    port = _free_port()
+    mp.spawn(_worker, args=(n, port, case, decomp, nstep, str(tmp_path)), nprocs=n, join=True)
+    wo = parity.build_world(case, decomp, nstep)
+    parity.run_oracle(wo)
+    for r in range(n):
+        got = np.load(os.path.join(str(tmp_path), "rank%d.npz" % r))
+        o = wo.view(r)
+        assert parity.rel_l2(got["disp"], o.dispArr) <= parity.REL_L2_TOL
+        assert parity.rel_l2(got["vel"], o.velArr) <= parity.REL_L2_TOL
+        k = int(o.nftnd[0])
+        if k:
+            assert parity.rel_l2(got["fric"][70:80, :k, 0], o.fric[70:80, :k, 0]) <= parity.REL_L2_TOL
+            both = (got["fnft"][:k, 0] < 5000.0) & (o.fnft[:k, 0] < 5000.0)
+            assert np.array_equal(got["fnft"][:k, 0] < 5000.0, o.fnft[:k, 0] < 5000.0)
+            if both.any():
+                assert np.max(np.abs(got["fnft"][:k, 0][both] - o.fnft[:k, 0][both])) <= o.params.dt * (1 + 1e-9)
+    wo.close()
