@@ -131,5 +131,12 @@ module eqdyna_cuda_iface
             character(kind=c_char) :: key(*)
             integer(c_int32_t), value :: val
         end function
+        integer(c_int) function eqd_plan_check(Nn, Ne, nodeElemIdRelation, elemTypeArr, numOfDofPerNodeArr, stats) &
+                bind(C, name='eqd_plan_check')
+            import :: c_int, c_int32_t, c_int64_t
+            integer(c_int32_t), value :: Nn, Ne
+            integer(c_int32_t) :: nodeElemIdRelation(8,*), elemTypeArr(*), numOfDofPerNodeArr(*)
+            integer(c_int64_t), intent(out) :: stats(24)
+        end function
     end interface
 end module eqdyna_cuda_iface
