@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Turn ncu outputs into the tracked summaries under profiles/.
 
-  summarize_profiles.py TAG LAUNCHES.csv FULL_RAW.csv [N_REGULAR N_PML N_NODES]
+  summarize_profiles.py TAG LAUNCHES.csv FULL_RAW.csv [N_REGULAR N_PML N_NODES [N_PML_NODES]]
 
 LAUNCHES.csv: `ncu --metrics gpu__time_duration.sum --clock-control none --csv` launch list.
 FULL_RAW.csv: `ncu -i prof.ncu-rep --page raw --csv` of a `--set full` capture.
@@ -90,7 +90,9 @@ def main():
     tag, lpath, fpath = sys.argv[1:4]
     counts = {}
     if len(sys.argv) >= 7:
-        counts = {"k_elem_reg": int(sys.argv[4]), "k_elem_pml": int(sys.argv[5]), "k_node_update": int(sys.argv[6])}
+        counts = {"k_tile_reg": int(sys.argv[4]), "k_tile_pml": int(sys.argv[5]), "k_node_update3": int(sys.argv[6])}
+        if len(sys.argv) >= 8:
+            counts["k_node_update12"] = int(sys.argv[7])
     s = {"tag": tag, "launch_list": launches(lpath), **full(fpath, counts)}
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     for name in ("ncu_summary_%s.json" % tag, "ncu_summary.json"):
