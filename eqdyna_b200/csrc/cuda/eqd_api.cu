@@ -7,6 +7,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -62,6 +63,19 @@ struct DevBuf {
     std::vector<T> h(n);
     if (n) CK(cudaMemcpy(h.data(), p, n * sizeof(T), cudaMemcpyDeviceToHost));
     return h;
+  }
+};
+
+// EQD_VERBOSE=1: wall-clock laps of the set-up phases on stderr
+struct Lap {
+  bool on; const char* what; std::chrono::steady_clock::time_point t;
+  explicit Lap(const char* w) : on(getenv("EQD_VERBOSE") != nullptr), what(w), t(std::chrono::steady_clock::now()) {}
+  void lap(const char* label) {
+    if (!on) return;
+    cudaDeviceSynchronize();
+    auto n = std::chrono::steady_clock::now();
+    fprintf(stderr, "[eqd] %s: %s %.3f s\n", what, label, std::chrono::duration<double>(n - t).count());
+    t = n;
   }
 };
 
@@ -172,6 +186,14 @@ struct eqd_handle {
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;
   cudaEvent_t evPacked[3] = {nullptr, nullptr, nullptr};
+  // overlap of the halo with the interior element sweep: tiles that
+  // touch a rank-face node are swept first, their face sums are exchanged on
+  // commStream while the main stream sweeps the interior tiles
+  cudaStream_t commStream = nullptr;
+  cudaEvent_t evFace = nullptr, evHalo = nullptr;
+  DevBuf<int> dSpecialA, dSpecialB;  // special nodes on active rank faces | the others (split-node pairs)
+  int nSpecialA = 0, nSpecialB = 0;
+  int optOverlap = 1, optReserve = 8, smCount = 148;
   // run state
   bool meshSet = false, opsSet = false, nodalSet = false, faultSet = false, finalized = false;
   int hostNt = 0;
@@ -298,7 +320,7 @@ ElemArgs eqd_handle::elemArgs(int c) const {
   const ElemClass& C = cls[c];
   ElemArgs A{};
   A.n = C.n; A.S = C.S;
-  A.tileRec = C.tileRec.p; A.tile0 = 0; A.ntiles = C.nTiles;
+  A.tileRec = C.tileRec.p; A.tile0 = 0; A.ntiles = C.nTiles; A.maxGrid = 0;
   A.tnode = C.tnode.p; A.lconn = C.lconn.p; A.LS = C.LS; A.pf = C.pf.p; A.PFS = C.PFS;
   A.shp = C.shp.p; A.phi = C.phi.p; A.ss = C.ss.p;
   A.lam = C.lam.p; A.mu = C.mu.p; A.det = C.det.p; A.rho = C.rho.p; A.vp = C.vp.p;
@@ -407,11 +429,46 @@ void finalize(eqd_handle* h) {
       }
     for (int a = 0; a < 3; ++a) CK(cudaEventCreateWithFlags(&h->evPacked[a], cudaEventDisableTiming));
   }
-  std::vector<int> list;
+  // ---- launch order of the tiles: those touching an active rank face first
+  std::vector<char> onFace(Nn, 0);
+  bool anyFace = false;
+  if (h->haloSet)
+    for (int a = 0; a < 3; ++a)
+      for (int side = 0; side < 2; ++side)
+        if (h->face[a][side].nb >= 0)
+          for (int n : h->face[a][side].nodes) { onFace[n] = 1; anyFace = true; }
+  if (anyFace) {
+    for (int c = 0; c < 3; ++c) {
+      ElemClass& C = h->cls[c];
+      if (!C.n) continue;
+      std::vector<int4> first, rest;
+      for (int t = 0; t < C.nTiles; ++t) {
+        bool f = false;
+        for (int k = C.tileNodeH[t]; k < C.tileNodeH[t + 1] && !f; ++k) f = C.tnodeH[k] >= 0 && onFace[C.tnodeH[k]];
+        (f ? first : rest).push_back(C.tileRecH[t]);
+      }
+      C.nFaceTiles = (int)first.size();
+      first.insert(first.end(), rest.begin(), rest.end());
+      C.tileRec.upload(first);
+    }
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&h->commStream, cudaStreamDefault, hi));
+    CK(cudaEventCreateWithFlags(&h->evFace, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&h->evHalo, cudaEventDisableTiming));
+    CK(cudaDeviceGetAttribute(&h->smCount, cudaDevAttrMultiProcessorCount, h->device));
+  }
+  std::vector<int> list, listA, listB;
   for (int n = 0; n < Nn; ++n)
-    if (special[n] && EQD_INFO_KIND(h->info[n]) != KIND_FIXED) { h->info[n] |= 4; list.push_back(n); }
+    if (special[n] && EQD_INFO_KIND(h->info[n]) != KIND_FIXED) {
+      h->info[n] |= 4;
+      list.push_back(n);
+      (onFace[n] ? listA : listB).push_back(n);
+    }
   h->nSpecial = (int)list.size();
   h->dSpecial.upload(list);
+  h->nSpecialA = (int)listA.size(); h->nSpecialB = (int)listB.size();
+  h->dSpecialA.upload(listA); h->dSpecialB.upload(listB);
   h->dInfo.upload(h->info);
   // ---- stations
   std::vector<int> pairStation(std::max(h->PS, 1), -1);
@@ -445,14 +502,14 @@ void finalize(eqd_handle* h) {
 }
 
 // transport of one axis phase between processes (NCCL) -- pack/unpack by caller
-void halo_axis_nccl(eqd_handle* h, int a) {
+void halo_axis_nccl(eqd_handle* h, int a, cudaStream_t st) {
   if (!h->comm) throw ArgError("eqd_run: sub-domain has neighbours but eqd_set_comm was not called");
   NK(g_nccl.GroupStart());
   for (int side = 0; side < 2; ++side) {
     Face& F = h->face[a][side];
     if (F.nb < 0 || F.n == 0) continue;
-    NK(g_nccl.Send(F.send.p, F.n, ncclDouble, F.nb, h->comm, h->stream));
-    NK(g_nccl.Recv(F.recv.p, F.n, ncclDouble, F.nb, h->comm, h->stream));
+    NK(g_nccl.Send(F.send.p, F.n, ncclDouble, F.nb, h->comm, st));
+    NK(g_nccl.Recv(F.recv.p, F.n, ncclDouble, F.nb, h->comm, st));
   }
   NK(g_nccl.GroupEnd());
 }
@@ -464,15 +521,15 @@ bool has_neighbours(const eqd_handle* h) {
 }
 
 struct Timer {
-  eqd_handle* h; int slot; cudaEvent_t a = nullptr, b = nullptr;
-  Timer(eqd_handle* h_, int slot_) : h(h_), slot(slot_) {
+  eqd_handle* h; int slot; cudaEvent_t a = nullptr, b = nullptr; cudaStream_t s;
+  Timer(eqd_handle* h_, int slot_, cudaStream_t s_ = nullptr) : h(h_), slot(slot_), s(s_ ? s_ : h_->stream) {
     if (!h->timing) return;
     CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
-    CK(cudaEventRecord(a, h->stream));
+    CK(cudaEventRecord(a, s));
   }
   void stop() {
     if (!h->timing) return;
-    CK(cudaEventRecord(b, h->stream));
+    CK(cudaEventRecord(b, s));
     h->evs.push_back(a); h->evs.push_back(b); h->evs.push_back((cudaEvent_t)(intptr_t)slot);
   }
 };
@@ -488,7 +545,11 @@ void collect_timing(eqd_handle* h) {
 }
 
 // phase A of a step: everything up to and including the packing of axis 0
-void step_pre(eqd_handle* h) {
+void halo_all_nccl(eqd_handle* h, cudaStream_t st);
+
+// mode 0: one sweep over all tiles; 1: face tiles, halo over NCCL on commStream overlapped with the
+// interior tiles; 2: face / interior split on one stream (in-process groups: the caller does the halo)
+void step_pre(eqd_handle* h, int mode = 0) {
   const eqd_params& P = h->p;
   cudaStream_t s = h->stream;
   launch_advance(h->dState.p, P.dt, s); h->launches++;
@@ -504,41 +565,79 @@ void step_pre(eqd_handle* h) {
     t.stop();
   }
   if (h->dAccel0.p) { CK(cudaStreamSynchronize(s)); h->dAccel0.release(); }
-  if (h->cls[CLS_REG].n) {
-    Timer t(h, EQD_T_ELEM);
-    launch_elem_reg(h->elemArgs(CLS_REG), false, h->plastic, h->qmode, h->body, P.C_hg, s); h->launches++;
-    t.stop();
-  }
-  if (h->cls[CLS_REGX].n) {
-    Timer t(h, EQD_T_ELEM_REGX);
-    launch_elem_reg(h->elemArgs(CLS_REGX), true, h->plastic, h->qmode, h->body, P.C_hg, s); h->launches++;
-    t.stop();
-  }
-  if (h->cls[CLS_PML].n) {
-    Timer t(h, EQD_T_ELEM_PML);
-    launch_elem_pml(h->elemArgs(CLS_PML), h->body, P.C_hg, s); h->launches++;
-    t.stop();
-  }
-  {
+  if (!(h->commStream && h->optOverlap)) mode = 0;
+  // sweep tiles [first, first+count) of every class
+  auto sweep = [&](int part) {   // 0: all tiles, 1: rank-face tiles, 2: interior tiles
+    for (int c = 0; c < 3; ++c) {
+      ElemClass& C = h->cls[c];
+      if (!C.n) continue;
+      ElemArgs A = h->elemArgs(c);
+      if (part == 1) { A.tile0 = 0; A.ntiles = C.nFaceTiles; }
+      if (part == 2) { A.tile0 = C.nFaceTiles; A.ntiles = C.nTiles - C.nFaceTiles; A.maxGrid = std::max(2 * h->smCount - h->optReserve, 2); }
+      if (A.ntiles <= 0) continue;
+      Timer t(h, c == CLS_REG ? EQD_T_ELEM : c == CLS_REGX ? EQD_T_ELEM_REGX : EQD_T_ELEM_PML);
+      if (c == CLS_PML) launch_elem_pml(A, h->body, P.C_hg, s);
+      else launch_elem_reg(A, c == CLS_REGX, h->plastic, h->qmode, h->body, P.C_hg, s);
+      h->launches++;
+      t.stop();
+    }
+  };
+  auto assemble = [&](const DevBuf<int>& list, int n) {
     Timer t(h, EQD_T_ASSEMBLE);
-    if (h->nSpecial) { launch_assemble_special(h->nodeArgs(), h->dSpecial.p, h->nSpecial, s); h->launches++; }
+    if (n) { launch_assemble_special(h->nodeArgs(), list.p, n, s); h->launches++; }
     t.stop();
+  };
+  if (mode == 0) {
+    sweep(0);
+    assemble(h->dSpecial, h->nSpecial);
+    return;
   }
+  if (mode == 2) {
+    sweep(1);
+    assemble(h->dSpecialA, h->nSpecialA);
+    sweep(2);
+    assemble(h->dSpecialB, h->nSpecialB);
+    return;
+  }
+  // rank-face tiles -> face sums -> halo on the communication stream, concurrently
+  // with the interior tiles on the main stream; joined before the fault solver
+  sweep(1);
+  assemble(h->dSpecialA, h->nSpecialA);
+  CK(cudaEventRecord(h->evFace, s));
+  CK(cudaStreamWaitEvent(h->commStream, h->evFace, 0));
+  halo_all_nccl(h, h->commStream);
+  CK(cudaEventRecord(h->evHalo, h->commStream));
+  sweep(2);
+  assemble(h->dSpecialB, h->nSpecialB);
+  CK(cudaStreamWaitEvent(s, h->evHalo, 0));
 }
 
-void halo_pack(eqd_handle* h, int a) {
+void halo_pack(eqd_handle* h, int a, cudaStream_t st = nullptr) {
+  if (!st) st = h->stream;
   for (int side = 0; side < 2; ++side) {
     Face& F = h->face[a][side];
     if (F.nb < 0 || F.n == 0) continue;
-    launch_pack(h->dForce.p, F.idx.p, F.n, F.send.p, h->stream); h->launches++;
+    launch_pack(h->dForce.p, F.idx.p, F.n, F.send.p, st); h->launches++;
   }
 }
-void halo_unpack(eqd_handle* h, int a) {
+void halo_unpack(eqd_handle* h, int a, cudaStream_t st = nullptr) {
+  if (!st) st = h->stream;
   for (int side = 0; side < 2; ++side) {
     Face& F = h->face[a][side];
     if (F.nb < 0 || F.n == 0) continue;
-    launch_unpack_add(h->dForce.p, F.idx.p, F.n, F.recv.p, h->stream); h->launches++;
+    launch_unpack_add(h->dForce.p, F.idx.p, F.n, F.recv.p, st); h->launches++;
   }
+}
+// the three axis phases of MPI4NodalQuant between processes, in order, on stream st
+void halo_all_nccl(eqd_handle* h, cudaStream_t st) {
+  Timer t(h, EQD_T_HALO, st);
+  for (int a = 0; a < 3; ++a) {
+    if (h->face[a][0].nb < 0 && h->face[a][1].nb < 0) continue;
+    halo_pack(h, a, st);
+    halo_axis_nccl(h, a, st);
+    halo_unpack(h, a, st);
+  }
+  t.stop();
 }
 
 void step_post(eqd_handle* h) {
@@ -641,6 +740,9 @@ int eqd_destroy(eqd_handle* h) {
   cudaSetDevice(h->device);
   if (h->comm && g_nccl.lib) g_nccl.CommDestroy(h->comm);
   for (int a = 0; a < 3; ++a) if (h->evPacked[a]) cudaEventDestroy(h->evPacked[a]);
+  if (h->evFace) cudaEventDestroy(h->evFace);
+  if (h->evHalo) cudaEventDestroy(h->evHalo);
+  if (h->commStream) cudaStreamDestroy(h->commStream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return EQD_OK;
@@ -661,6 +763,7 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
     need(Nn > 0 && Ne > 0 && meshCoor && nodeElemIdRelation && elemTypeArr && numOfDofPerNodeArr && eqNumStartIndexLoc &&
              eqNumIndexArr && stressCompIndexArr, "eqd_set_mesh: null / empty argument");
     const eqd_params& P = h->p;
+    Lap lap("eqd_set_mesh");
     h->Nn = Nn; h->Ne = Ne; h->Neq = Neq; h->sizeEq = sizeEq; h->sizeStress = sizeStress;
     h->coor.assign(meshCoor, meshCoor + 3 * (size_t)Nn);
     h->etype.assign(elemTypeArr, elemTypeArr + Ne);
@@ -674,6 +777,7 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
       need(n >= 0 && n < Nn, "eqd_set_mesh: connectivity out of range");
       h->conn[k] = n;
     }
+    lap.lap("host copies");
     // ---- node kinds
     h->info.assign(Nn, 0);
     h->Np = 0;
@@ -708,6 +812,7 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
       }
       members[c].push_back(e);
     }
+    lap.lap("node kinds + classes");
     int gny = 0, gnz = 0;
     const bool gridOk = infer_grid(h->conn.data(), h->etype.data(), Ne, Nn, gny, gnz);
     h->elemCode.assign(Ne, 0);
@@ -770,6 +875,7 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
         C.qmem.alloc(6 * (size_t)C.S);
       }
     }
+    lap.lap("tile plan + uploads");
     // ---- node -> tile-node slots by rank, class then ascending tile id
     {
       std::vector<uint8_t> cnt(Nn, 0);
@@ -797,6 +903,7 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
       h->dSlotCnt.upload(cnt);
       h->dSlotTab.upload(tab);
     }
+    lap.lap("slot table");
     // ---- PML node damping profile (comdampv, recomputed every step in the reference)
     std::vector<double> dp(3 * (size_t)h->NpS, 0.0);
     for (int n = 0; n < Nn; ++n)
@@ -812,6 +919,7 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
     h->dV1p.alloc(12 * (size_t)h->NpS);
     h->dForce.alloc(3 * (size_t)h->NnS + 12 * (size_t)h->NpS);
     h->dMass.alloc(Nn);
+    lap.lap("comdampv + nodal allocs");
     h->meshSet = true;
   });
 }
@@ -826,6 +934,7 @@ int eqd_set_elem_ops(eqd_handle* h, const double* eleshp, const double* eledet, 
     need(!h->body || elemass, "eqd_set_elem_ops: elemass required (gravity / mass damping)");
     need(!h->plastic || (eleporep && pstrain), "eqd_set_elem_ops: eleporep/pstrain required for C_elastic==0");
     const int Ne = h->Ne;
+    Lap lap("eqd_set_elem_ops");
     DevBuf<int> dCode; dCode.upload(h->elemCode);
     DevBuf<double> tmp;
     for (int c = 0; c < 3; ++c) {
@@ -873,6 +982,7 @@ int eqd_set_elem_ops(eqd_handle* h, const double* eleshp, const double* eledet, 
       spread(pstrain, 1, &ElemClass::pstrain, 0, 1, 0);
     }
     tmp.release();
+    lap.lap("operator rows");
     // stresses: stressArr(stressCompIndexArr(e) + k)
     for (int c = 0; c < 3; ++c) {
       ElemClass& C = h->cls[c];
@@ -889,6 +999,7 @@ int eqd_set_elem_ops(eqd_handle* h, const double* eleshp, const double* eledet, 
       C.stress.upload(sg);
       if (!qm.empty()) C.qmem.upload(qm);
     }
+    lap.lap("stresses");
     h->opsSet = true;
   });
 }
@@ -901,6 +1012,7 @@ int eqd_set_nodal(eqd_handle* h, const double* nodalMassArr, const double* fnms,
     need(nodalMassArr && fnms && v1 && velArr && dispArr, "eqd_set_nodal: null argument");
     const int Nn = h->Nn;
     const size_t NS = h->NnS, PS = h->NpS;
+    Lap lap("eqd_set_nodal");
     h->fnmsH.assign(fnms, fnms + Nn);
     h->massH.assign(Nn, 1.0);
     std::vector<double> vel(3 * NS, 0.0), disp(3 * NS, 0.0), v1p(12 * PS, 0.0), acc;
@@ -930,6 +1042,7 @@ int eqd_set_nodal(eqd_handle* h, const double* nodalMassArr, const double* fnms,
     }
     h->dVel.upload(vel); h->dDisp.upload(disp); h->dV1p.upload(v1p); h->dMass.upload(h->massH);
     if (anyAcc) h->dAccel0.upload(acc); else h->dAccel0.release();
+    lap.lap("all");
     h->nodalSet = true;
   });
 }
@@ -1104,17 +1217,9 @@ int eqd_run(eqd_handle* h, int32_t nt_begin, int32_t nt_end) {
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     if (h->timing) { CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1)); CK(cudaEventRecord(t0, h->stream)); }
     for (int nt = nt_begin; nt <= nt_end; ++nt) {
-      step_pre(h);
-      if (multi) {
-        Timer t(h, EQD_T_HALO);
-        for (int a = 0; a < 3; ++a) {
-          if (h->face[a][0].nb < 0 && h->face[a][1].nb < 0) continue;
-          halo_pack(h, a);
-          halo_axis_nccl(h, a);
-          halo_unpack(h, a);
-        }
-        t.stop();
-      }
+      const bool overlap = multi && h->commStream && h->optOverlap;
+      step_pre(h, overlap ? 1 : 0);
+      if (multi && !overlap) halo_all_nccl(h, h->stream);
       step_post(h);
     }
     if (h->timing) {
@@ -1143,7 +1248,7 @@ int eqd_run_group(eqd_handle** hs, int32_t n, int32_t nt_begin, int32_t nt_end) 
       prepare_run(hs[r], nt_begin);
     }
     for (int nt = nt_begin; nt <= nt_end; ++nt) {
-      for (int r = 0; r < n; ++r) { CK(cudaSetDevice(hs[r]->device)); step_pre(hs[r]); }
+      for (int r = 0; r < n; ++r) { CK(cudaSetDevice(hs[r]->device)); step_pre(hs[r], 2); }
       for (int a = 0; a < 3; ++a) {
         for (int r = 0; r < n; ++r) {
           eqd_handle* h = hs[r];
@@ -1310,7 +1415,8 @@ int eqd_set_option(eqd_handle* h, const char* key, int32_t value) {
   if (!strcmp(key, "timing")) { h->timing = value != 0; if (value == 2) { for (double& t : h->tms) t = 0; h->launches = 0; } return EQD_OK; }
   if (!strcmp(key, "graph")) { h->optGraph = value; return EQD_OK; }
   if (!strcmp(key, "block")) { h->optBlock = value; return EQD_OK; }
-  if (!strcmp(key, "overlap")) return EQD_OK;
+  if (!strcmp(key, "overlap")) { h->optOverlap = value; return EQD_OK; }
+  if (!strcmp(key, "reserve")) { h->optReserve = value; return EQD_OK; }
   h->err = std::string("eqd_set_option: unknown key ") + key;
   return EQD_ERR_ARG;
 }

@@ -80,6 +80,7 @@ struct ElemArgs {
   const int4* tileRec;   // per tile in LAUNCH order (rank-face tiles first):
                          // {first slot, elements | colours << 16, first tile-node slot, tile nodes}
   int tile0, ntiles;     // tiles [tile0, tile0+ntiles) of tileRec belong to this launch
+  int maxGrid;           // cap on the persistent grid (0 = two CTAs per SM); the overlapped interior sweep leaves room for the halo kernels
   const int* tnode;
   const uint16_t* lconn; // [8][S] local node | colour << 12
   int LS;                // shared-memory row stride (max tile nodes of the class)

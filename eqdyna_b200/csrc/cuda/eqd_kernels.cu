@@ -1436,7 +1436,7 @@ static void launch_reg_chg(const ElemArgs& A, int chg, cudaStream_t s) {
   const int ntiles = A.ntiles;
   const size_t sm = tile_smem_bytes(CLS_REG, Q, A.LS);
   // persistent CTAs, two per SM, each walking tiles blockIdx.x, +gridDim.x, ...
-  const int grid = std::min(ntiles, 2 * sm_count());
+  const int grid = std::min(ntiles, A.maxGrid > 0 ? A.maxGrid : 2 * sm_count());
   if (chg == 2) tile_launch(k_tile_reg<PL, Q, BODY, SPLIT, 2>, A, grid, 2 * EQD_STAGE, sm, s);
   else tile_launch(k_tile_reg<PL, Q, BODY, SPLIT, 1>, A, grid, 2 * EQD_STAGE, sm, s);
 }
@@ -1457,7 +1457,7 @@ void launch_elem_pml(const ElemArgs& A, bool body, int chg, cudaStream_t s) {
   if (ntiles <= 0) return;
   const size_t sm = tile_smem_bytes(CLS_PML, false, A.LS);
   const int nt = 4 * EQD_STAGE_PML;
-  ntiles = std::min(ntiles, 2 * sm_count());
+  ntiles = std::min(ntiles, A.maxGrid > 0 ? A.maxGrid : 2 * sm_count());
   if (body) { if (chg == 2) tile_launch(k_tile_pml<true, 2>, A, ntiles, nt, sm, s); else tile_launch(k_tile_pml<true, 1>, A, ntiles, nt, sm, s); }
   else { if (chg == 2) tile_launch(k_tile_pml<false, 2>, A, ntiles, nt, sm, s); else tile_launch(k_tile_pml<false, 1>, A, ntiles, nt, sm, s); }
 }

@@ -22,7 +22,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world_size, port, case, decomp, nstep, out):
+def _worker(rank, world_size, port, case, decomp, nstep, overlap, out):
     sys.path.insert(0, parity.ROOT)
     sys.path.insert(0, os.path.join(parity.ROOT, "tests"))
     import torch
@@ -37,6 +37,7 @@ def _worker(rank, world_size, port, case, decomp, nstep, out):
     ids = [dev.unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     d.set_comm(ids[0], world_size, rank)
+    d.set_option("overlap", overlap)   # 1: halo on the communication stream under the interior tiles
     n = v.nstep
     d.run(1, n // 2)          # two chunks: the halo state must survive a return to the host
     d.run(n // 2 + 1, n)
@@ -48,16 +49,18 @@ def _worker(rank, world_size, port, case, decomp, nstep, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case,decomp,nstep", [("test.tpv8", (2, 1, 1), 0), ("test.tpv104", (1, 2, 1), 60)],
-                         ids=["tpv8-2x1x1", "tpv104-1x2x1-fault-on-rank-face"])
-def test_nccl_processes_match_oracle(tmp_path, case, decomp, nstep):
+@pytest.mark.parametrize("case,decomp,nstep,overlap",
+                         [("test.tpv8", (2, 1, 1), 0, 1), ("test.tpv104", (1, 2, 1), 60, 1), ("test.tpv8", (2, 1, 1), 40, 0),
+                          ("test.tpv10", (2, 1, 2), 60, 1)],
+                         ids=["tpv8-2x1x1", "tpv104-1x2x1-fault-on-rank-face", "tpv8-2x1x1-no-overlap", "tpv10-2x1x2"])
+def test_nccl_processes_match_oracle(tmp_path, case, decomp, nstep, overlap):
     import torch
     import torch.multiprocessing as mp
     n = decomp[0] * decomp[1] * decomp[2]
     if torch.cuda.device_count() < n:
         pytest.skip("needs %d GPUs" % n)
     port = _free_port()
-    mp.spawn(_worker, args=(n, port, case, decomp, nstep, str(tmp_path)), nprocs=n, join=True)
+    mp.spawn(_worker, args=(n, port, case, decomp, nstep, overlap, str(tmp_path)), nprocs=n, join=True)
     wo = parity.build_world(case, decomp, nstep)
     parity.run_oracle(wo)
     for r in range(n):
