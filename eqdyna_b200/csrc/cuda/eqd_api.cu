@@ -14,10 +14,12 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "eqd_dev.cuh"
 #include "eqd_kernels.h"
+#include "eqd_par.h"
 #include "eqd_tiles.h"
 #include "eqdyna_b200.h"
 
@@ -39,6 +41,19 @@ struct ArgError : std::runtime_error { using std::runtime_error::runtime_error; 
       throw CudaError(std::string(#x) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
   } while (0)
 
+// the calling handle's pinned staging buffers while a set-up call is running (else pageable copies)
+thread_local StagedCopy* t_stage = nullptr;
+thread_local cudaStream_t t_stageStream = nullptr;
+
+inline void h2d(void* dst, const void* src, size_t bytes) {
+  if (t_stage && bytes >= (8u << 20)) {
+    cudaError_t e_ = t_stage->h2d(dst, src, bytes, t_stageStream);
+    if (e_ != cudaSuccess) throw CudaError(std::string("staged host->device copy: ") + cudaGetErrorString(e_));
+  } else {
+    CK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+  }
+}
+
 template <class T>
 struct DevBuf {
   T* p = nullptr;
@@ -55,9 +70,10 @@ struct DevBuf {
     CK(cudaMalloc(&p, count * sizeof(T)));
     if (zero) CK(cudaMemset(p, 0, count * sizeof(T)));
   }
-  void upload(const std::vector<T>& h) {
+  template <class A>
+  void upload(const std::vector<T, A>& h) {
     alloc(h.size(), false);
-    if (!h.empty()) CK(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    if (!h.empty()) h2d(p, h.data(), h.size() * sizeof(T));
   }
   std::vector<T> download() const {
     std::vector<T> h(n);
@@ -122,8 +138,9 @@ struct ElemClass {
   int n = 0, S = 0, nf = 3, nstress = 6;
   // tiles (eqd_tiles.h): launch order = rank-face tiles first, then interior
   int nTiles = 0, nFaceTiles = 0, LS = 1, PFS = 4;
-  std::vector<int> refId;  // [S] slot -> reference element (0-based), -1 = padding
-  std::vector<int> tileNodeH, tnodeH;
+  raw_vector<int> refId;  // [S] slot -> reference element (0-based), -1 = padding
+  std::vector<int> tileNodeH;
+  raw_vector<int> tnodeH;
   std::vector<int4> tileRecH;  // planner order
   DevBuf<int4> tileRec;        // launch order
   DevBuf<int> tnode;
@@ -151,9 +168,9 @@ struct eqd_handle {
   std::string err;
   // ---- host copies (0-based where noted)
   int Nn = 0, Ne = 0, Neq = 0, sizeEq = 0, sizeStress = 0;
-  std::vector<int> conn;       // (8,Ne) 0-based
-  std::vector<int> etype, ndof, eqStart, eqIdx, stressIdx;
-  std::vector<double> coor;    // (3,Nn)
+  raw_vector<int> conn;        // (8,Ne) 0-based
+  raw_vector<int> etype, ndof, eqStart, eqIdx, stressIdx;
+  raw_vector<double> coor;     // (3,Nn)
   std::vector<int> info;       // per node
   std::vector<int> elemCode;   // per element: class | slot<<2
   std::vector<double> fnmsH, massH;
@@ -190,10 +207,12 @@ struct eqd_handle {
   // touch a rank-face node are swept first, their face sums are exchanged on
   // commStream while the main stream sweeps the interior tiles
   cudaStream_t commStream = nullptr;
-  cudaEvent_t evFace = nullptr, evHalo = nullptr;
+  cudaEvent_t evFace = nullptr, evElem = nullptr, evComm = nullptr;
+  bool anyFace = false;
   DevBuf<int> dSpecialA, dSpecialB;  // special nodes on active rank faces | the others (split-node pairs)
   int nSpecialA = 0, nSpecialB = 0;
-  int optOverlap = 1, optReserve = 8, smCount = 148;
+  int optOverlap = -1, optReserve = 8, smCount = 148;  // overlap -1 = auto: 1 with rank neighbours, else 0
+  std::unique_ptr<StagedCopy> stage;  // pinned staging of the set-up uploads, dropped once the run starts
   // run state
   bool meshSet = false, opsSet = false, nodalSet = false, faultSet = false, finalized = false;
   int hostNt = 0;
@@ -213,6 +232,10 @@ namespace {
 
 template <class F>
 int guarded(eqd_handle* h, F&& f) {
+  struct StageScope {
+    StageScope(eqd_handle* h) { if (h && h->stage) { t_stage = h->stage.get(); t_stageStream = h->stream; } }
+    ~StageScope() { t_stage = nullptr; t_stageStream = nullptr; }
+  } scope(h);
   try {
     if (h) CK(cudaSetDevice(h->device));
     f();
@@ -310,7 +333,7 @@ NodeArgs eqd_handle::nodeArgs() const {
   A.pfR = cls[CLS_REG].pf.p; A.SR = cls[CLS_REG].PFS;
   A.pfX = cls[CLS_REGX].pf.p; A.SX = cls[CLS_REGX].PFS;
   A.pfP = cls[CLS_PML].pf.p; A.SP = cls[CLS_PML].PFS;
-  A.accel0 = nullptr;
+  A.accel0 = nullptr; A.skipSpecial = 0;
   A.dt = p.dt;
   A.st = dState.p;
   return A;
@@ -431,7 +454,8 @@ void finalize(eqd_handle* h) {
   }
   // ---- launch order of the tiles: those touching an active rank face first
   std::vector<char> onFace(Nn, 0);
-  bool anyFace = false;
+  bool& anyFace = h->anyFace;
+  anyFace = false;
   if (h->haloSet)
     for (int a = 0; a < 3; ++a)
       for (int side = 0; side < 2; ++side)
@@ -451,11 +475,13 @@ void finalize(eqd_handle* h) {
       first.insert(first.end(), rest.begin(), rest.end());
       C.tileRec.upload(first);
     }
+  }
+  {
+    // communication stream (halo + fault solver); a blocking stream like the main one
     int lo = 0, hi = 0;
     CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     CK(cudaStreamCreateWithPriority(&h->commStream, cudaStreamDefault, hi));
-    CK(cudaEventCreateWithFlags(&h->evFace, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&h->evHalo, cudaEventDisableTiming));
+    for (cudaEvent_t* e : {&h->evFace, &h->evElem, &h->evComm}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     CK(cudaDeviceGetAttribute(&h->smCount, cudaDevAttrMultiProcessorCount, h->device));
   }
   std::vector<int> list, listA, listB;
@@ -498,6 +524,7 @@ void finalize(eqd_handle* h) {
   // cudaMemset / cudaMemcpy above ran on the legacy stream, which does not order
   // against the non-blocking step stream
   CK(cudaDeviceSynchronize());
+  h->stage.reset();
   h->finalized = true;
 }
 
@@ -544,74 +571,6 @@ void collect_timing(eqd_handle* h) {
   h->evs.clear();
 }
 
-// phase A of a step: everything up to and including the packing of axis 0
-void halo_all_nccl(eqd_handle* h, cudaStream_t st);
-
-// mode 0: one sweep over all tiles; 1: face tiles, halo over NCCL on commStream overlapped with the
-// interior tiles; 2: face / interior split on one stream (in-process groups: the caller does the halo)
-void step_pre(eqd_handle* h, int mode = 0) {
-  const eqd_params& P = h->p;
-  cudaStream_t s = h->stream;
-  launch_advance(h->dState.p, P.dt, s); h->launches++;
-  {
-    Timer t(h, EQD_T_NODE);
-    NodeArgs A = h->nodeArgs();
-    if (h->dAccel0.p) A.accel0 = h->dAccel0.p;
-    launch_node_update(A, s); h->launches += h->Np > 0 ? 2 : 1;
-    if (h->nOff > 0) {
-      launch_store_offfault(h->dIdhist.p, 6 * h->nOff, h->dOffHist.p, h->dVel.p, h->dDisp.p, h->NnS, h->dState.p, s);
-      h->launches++;
-    }
-    t.stop();
-  }
-  if (h->dAccel0.p) { CK(cudaStreamSynchronize(s)); h->dAccel0.release(); }
-  if (!(h->commStream && h->optOverlap)) mode = 0;
-  // sweep tiles [first, first+count) of every class
-  auto sweep = [&](int part) {   // 0: all tiles, 1: rank-face tiles, 2: interior tiles
-    for (int c = 0; c < 3; ++c) {
-      ElemClass& C = h->cls[c];
-      if (!C.n) continue;
-      ElemArgs A = h->elemArgs(c);
-      if (part == 1) { A.tile0 = 0; A.ntiles = C.nFaceTiles; }
-      if (part == 2) { A.tile0 = C.nFaceTiles; A.ntiles = C.nTiles - C.nFaceTiles; A.maxGrid = std::max(2 * h->smCount - h->optReserve, 2); }
-      if (A.ntiles <= 0) continue;
-      Timer t(h, c == CLS_REG ? EQD_T_ELEM : c == CLS_REGX ? EQD_T_ELEM_REGX : EQD_T_ELEM_PML);
-      if (c == CLS_PML) launch_elem_pml(A, h->body, P.C_hg, s);
-      else launch_elem_reg(A, c == CLS_REGX, h->plastic, h->qmode, h->body, P.C_hg, s);
-      h->launches++;
-      t.stop();
-    }
-  };
-  auto assemble = [&](const DevBuf<int>& list, int n) {
-    Timer t(h, EQD_T_ASSEMBLE);
-    if (n) { launch_assemble_special(h->nodeArgs(), list.p, n, s); h->launches++; }
-    t.stop();
-  };
-  if (mode == 0) {
-    sweep(0);
-    assemble(h->dSpecial, h->nSpecial);
-    return;
-  }
-  if (mode == 2) {
-    sweep(1);
-    assemble(h->dSpecialA, h->nSpecialA);
-    sweep(2);
-    assemble(h->dSpecialB, h->nSpecialB);
-    return;
-  }
-  // rank-face tiles -> face sums -> halo on the communication stream, concurrently
-  // with the interior tiles on the main stream; joined before the fault solver
-  sweep(1);
-  assemble(h->dSpecialA, h->nSpecialA);
-  CK(cudaEventRecord(h->evFace, s));
-  CK(cudaStreamWaitEvent(h->commStream, h->evFace, 0));
-  halo_all_nccl(h, h->commStream);
-  CK(cudaEventRecord(h->evHalo, h->commStream));
-  sweep(2);
-  assemble(h->dSpecialB, h->nSpecialB);
-  CK(cudaStreamWaitEvent(s, h->evHalo, 0));
-}
-
 void halo_pack(eqd_handle* h, int a, cudaStream_t st = nullptr) {
   if (!st) st = h->stream;
   for (int side = 0; side < 2; ++side) {
@@ -640,23 +599,108 @@ void halo_all_nccl(eqd_handle* h, cudaStream_t st) {
   t.stop();
 }
 
-void step_post(eqd_handle* h) {
+// Everything of a step that follows the element sweep and needs the summed
+// face forces: thermop + faulting (driver.f90:23-28) and the source-evolution
+// sample (driver.f90:30-33), on stream st.
+void launch_fault_phase(eqd_handle* h, cudaStream_t st) {
   const eqd_params& P = h->p;
-  cudaStream_t s = h->stream;
-  Timer t(h, EQD_T_FAULT);
+  Timer t(h, EQD_T_FAULT, st);
   if (h->nPairs > 0) {
     FaultArgs A = h->faultArgs();
-    if (P.friclaw == 5) { launch_thermop(A, s); h->launches++; }
-    launch_fault(A, s); h->launches++;
+    if (P.friclaw == 5) { launch_thermop(A, st); h->launches++; }
+    launch_fault(A, st); h->launches++;
   }
-  h->hostNt++;
-  h->hostTime = h->hostTime + P.dt;
-  if (P.outputGroundMotion && h->hostNt % 10 == 1) {  // driver.f90:30-33: mod(nt,10) == 1
-    if (h->dGm.p) { launch_sample_gm(h->dSurf.p, h->nSurf, h->dVel.p, h->NnS, h->dGm.p + 3 * (size_t)h->nSurf * h->nGm, s); h->launches++; }
-    if (h->dSrc.p) { launch_sample_src(h->dFric.p, h->PS, h->nftnd[0], h->dSrc.p + (size_t)h->nftnd[0] * h->nGm, s); h->launches++; }
-    h->nGm++;
+  if (P.outputGroundMotion && (h->hostNt + 1) % 10 == 1 && h->dSrc.p) {  // driver.f90:30-33: mod(nt,10) == 1
+    launch_sample_src(h->dFric.p, h->PS, h->nftnd[0], h->dSrc.p + (size_t)h->nftnd[0] * h->nGm, st); h->launches++;
   }
   t.stop();
+}
+
+// One time step (driver.f90:9-34) as a launch sequence.
+//   ov == 0  serial: everything on the main stream.  `external` = the caller does
+//            the halo between step_pre and step_post (in-process groups).
+//   ov >= 1  the halo and the fault solver run on commStream and are joined only
+//            by the special-node update of the NEXT step: they hide under that
+//            step's bulk node update, which touches no split-node or rank-face
+//            node (those are updated by k_node_update_special after the join).
+//   ov == 2  additionally the tiles touching a rank face are swept first and the
+//            halo starts while the interior tiles are still being swept.
+void step_pre(eqd_handle* h, int ov, bool multi) {
+  const eqd_params& P = h->p;
+  cudaStream_t s = h->stream, c = h->commStream;
+  {
+    Timer t(h, EQD_T_NODE);
+    NodeArgs A = h->nodeArgs();
+    if (h->dAccel0.p) A.accel0 = h->dAccel0.p;
+    A.skipSpecial = ov ? 1 : 0;
+    launch_node_update(A, s); h->launches += h->Np > 0 ? 2 : 1;
+    t.stop();
+    if (ov) {
+      // join: halo + fault solver of the previous step
+      CK(cudaStreamWaitEvent(s, h->evComm, 0));
+    }
+    launch_advance(h->dState.p, P.dt, s); h->launches++;
+    Timer t2(h, EQD_T_NODE);
+    if (ov && h->nSpecial) { launch_node_update_special(A, h->dSpecial.p, h->nSpecial, s); h->launches++; }
+    if (h->nOff > 0) {
+      launch_store_offfault(h->dIdhist.p, 6 * h->nOff, h->dOffHist.p, h->dVel.p, h->dDisp.p, h->NnS, h->dState.p, s);
+      h->launches++;
+    }
+    t2.stop();
+  }
+  if (h->dAccel0.p) { CK(cudaStreamSynchronize(s)); h->dAccel0.release(); }
+  auto sweep = [&](int part) {   // 0: all tiles, 1: rank-face tiles, 2: interior tiles
+    for (int k = 0; k < 3; ++k) {
+      ElemClass& C = h->cls[k];
+      if (!C.n) continue;
+      ElemArgs A = h->elemArgs(k);
+      if (part == 1) { A.tile0 = 0; A.ntiles = C.nFaceTiles; }
+      if (part == 2) { A.tile0 = C.nFaceTiles; A.ntiles = C.nTiles - C.nFaceTiles; A.maxGrid = std::max(2 * h->smCount - h->optReserve, 2); }
+      if (A.ntiles <= 0) continue;
+      Timer t(h, k == CLS_REG ? EQD_T_ELEM : k == CLS_REGX ? EQD_T_ELEM_REGX : EQD_T_ELEM_PML);
+      if (k == CLS_PML) launch_elem_pml(A, h->body, P.C_hg, s);
+      else launch_elem_reg(A, k == CLS_REGX, h->plastic, h->qmode, h->body, P.C_hg, s);
+      h->launches++;
+      t.stop();
+    }
+  };
+  auto assemble = [&](const DevBuf<int>& list, int n) {
+    Timer t(h, EQD_T_ASSEMBLE);
+    if (n) { launch_assemble_special(h->nodeArgs(), list.p, n, s); h->launches++; }
+    t.stop();
+  };
+  const bool split = ov == 2 && multi && h->anyFace;
+  if (!split) {
+    sweep(0);
+    assemble(h->dSpecial, h->nSpecial);
+  } else {
+    sweep(1);
+    assemble(h->dSpecialA, h->nSpecialA);
+    CK(cudaEventRecord(h->evFace, s));
+    CK(cudaStreamWaitEvent(c, h->evFace, 0));
+    halo_all_nccl(h, c);
+    sweep(2);
+    assemble(h->dSpecialB, h->nSpecialB);
+  }
+  if (ov) {
+    CK(cudaEventRecord(h->evElem, s));
+    CK(cudaStreamWaitEvent(c, h->evElem, 0));
+    if (multi && !split) halo_all_nccl(h, c);
+  }
+}
+
+void step_post(eqd_handle* h, int ov) {
+  const eqd_params& P = h->p;
+  cudaStream_t s = h->stream;
+  launch_fault_phase(h, ov ? h->commStream : s);
+  if (ov) CK(cudaEventRecord(h->evComm, h->commStream));
+  h->hostNt++;
+  h->hostTime = h->hostTime + P.dt;
+  if (P.outputGroundMotion && h->hostNt % 10 == 1) {
+    // velArr of this step: written by the node updates on the main stream
+    if (h->dGm.p) { launch_sample_gm(h->dSurf.p, h->nSurf, h->dVel.p, h->NnS, h->dGm.p + 3 * (size_t)h->nSurf * h->nGm, s); h->launches++; }
+    h->nGm++;
+  }
 }
 
 void prepare_run(eqd_handle* h, int nt_begin) {
@@ -674,6 +718,7 @@ void prepare_run(eqd_handle* h, int nt_begin) {
 }
 
 int finish_run(eqd_handle* h) {
+  if (h->commStream) CK(cudaStreamSynchronize(h->commStream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
   if (h->timing) collect_timing(h);
@@ -712,6 +757,7 @@ int eqd_create(const eqd_params* p, int device, eqd_handle** out) {
     // cudaMemset on the legacy stream (a pageable H2D copy may return before its
     // DMA has landed), and a blocking stream is ordered after those.
     CK(cudaStreamCreate(&h->stream));
+    h->stage.reset(new StagedCopy());
     h->body = (p->C_elastic == 0) || (p->rdampm != 0.0);
     h->plastic = p->C_elastic == 0;
     h->qmode = p->C_Q == 1;
@@ -740,8 +786,7 @@ int eqd_destroy(eqd_handle* h) {
   cudaSetDevice(h->device);
   if (h->comm && g_nccl.lib) g_nccl.CommDestroy(h->comm);
   for (int a = 0; a < 3; ++a) if (h->evPacked[a]) cudaEventDestroy(h->evPacked[a]);
-  if (h->evFace) cudaEventDestroy(h->evFace);
-  if (h->evHalo) cudaEventDestroy(h->evHalo);
+  for (cudaEvent_t e : {h->evFace, h->evElem, h->evComm}) if (e) cudaEventDestroy(e);
   if (h->commStream) cudaStreamDestroy(h->commStream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -765,31 +810,47 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
     const eqd_params& P = h->p;
     Lap lap("eqd_set_mesh");
     h->Nn = Nn; h->Ne = Ne; h->Neq = Neq; h->sizeEq = sizeEq; h->sizeStress = sizeStress;
-    h->coor.assign(meshCoor, meshCoor + 3 * (size_t)Nn);
-    h->etype.assign(elemTypeArr, elemTypeArr + Ne);
-    h->ndof.assign(numOfDofPerNodeArr, numOfDofPerNodeArr + Nn);
-    h->eqStart.assign(eqNumStartIndexLoc, eqNumStartIndexLoc + Nn);
-    h->eqIdx.assign(eqNumIndexArr, eqNumIndexArr + sizeEq);
-    h->stressIdx.assign(stressCompIndexArr, stressCompIndexArr + Ne);
-    h->conn.resize(8 * (size_t)Ne);
-    for (size_t k = 0; k < 8 * (size_t)Ne; ++k) {
-      const int n = nodeElemIdRelation[k] - 1;
-      need(n >= 0 && n < Nn, "eqd_set_mesh: connectivity out of range");
-      h->conn[k] = n;
+    h->coor.resize(3 * (size_t)Nn); h->etype.resize(Ne); h->ndof.resize(Nn); h->eqStart.resize(Nn);
+    h->eqIdx.resize(sizeEq); h->stressIdx.resize(Ne); h->conn.resize(8 * (size_t)Ne);
+    parallel_memcpy(h->coor.data(), meshCoor, sizeof(double) * 3 * (size_t)Nn);
+    parallel_memcpy(h->etype.data(), elemTypeArr, sizeof(int) * (size_t)Ne);
+    parallel_memcpy(h->ndof.data(), numOfDofPerNodeArr, sizeof(int) * (size_t)Nn);
+    parallel_memcpy(h->eqStart.data(), eqNumStartIndexLoc, sizeof(int) * (size_t)Nn);
+    parallel_memcpy(h->eqIdx.data(), eqNumIndexArr, sizeof(int) * (size_t)sizeEq);
+    parallel_memcpy(h->stressIdx.data(), stressCompIndexArr, sizeof(int) * (size_t)Ne);
+    {
+      std::vector<char> badv(host_threads() + 1, 0);
+      parallel_range(8 * (size_t)Ne, [&](size_t b, size_t e) {
+        bool bad = false;
+        for (size_t k = b; k < e; ++k) {
+          const int n = nodeElemIdRelation[k] - 1;
+          bad |= (n < 0 || n >= Nn);
+          h->conn[k] = n;
+        }
+        if (bad) badv[0] = 1;
+      });
+      need(!badv[0], "eqd_set_mesh: connectivity out of range");
     }
     lap.lap("host copies");
     // ---- node kinds
     h->info.assign(Nn, 0);
     h->Np = 0;
-    for (int n = 0; n < Nn; ++n) {
-      const int nd = h->ndof[n], st = h->eqStart[n];
-      need((nd == 3 || nd == 12) && st >= 0 && st + nd <= sizeEq, "eqd_set_mesh: bad dof table");
-      int nfix = 0;
-      for (int j = 0; j < nd; ++j) if (h->eqIdx[st + j] <= 0) nfix++;
-      need(nfix == 0 || nfix == nd, "eqd_set_mesh: partially fixed node is not supported");
-      if (nfix) h->info[n] = KIND_FIXED;
-      else if (nd == 3) h->info[n] = KIND_FREE3;
-      else { h->info[n] = KIND_PML12 | (h->Np << 3); h->Np++; }
+    {
+      std::vector<char> badv(2, 0);
+      parallel_range((size_t)Nn, [&](size_t b, size_t e) {
+        for (size_t n = b; n < e; ++n) {
+          const int nd = h->ndof[n], st = h->eqStart[n];
+          if (!((nd == 3 || nd == 12) && st >= 0 && st + nd <= sizeEq)) { badv[0] = 1; continue; }
+          int nfix = 0;
+          for (int j = 0; j < nd; ++j) if (h->eqIdx[st + j] <= 0) nfix++;
+          if (!(nfix == 0 || nfix == nd)) { badv[1] = 1; continue; }
+          h->info[n] = nfix ? KIND_FIXED : (nd == 3 ? KIND_FREE3 : KIND_PML12);
+        }
+      });
+      need(!badv[0], "eqd_set_mesh: bad dof table");
+      need(!badv[1], "eqd_set_mesh: partially fixed node is not supported");
+      for (int n = 0; n < Nn; ++n)
+        if (h->info[n] == KIND_PML12) { h->info[n] = KIND_PML12 | (h->Np << 3); h->Np++; }
     }
     h->NnS = pad32(Nn);
     h->NpS = pad32(std::max(h->Np, 1));
@@ -801,16 +862,24 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
     need(3 * (double)h->NnS + 12 * (double)h->NpS < 4.0e9, "eqd_set_mesh: sub-domain too large for 32-bit halo offsets");
     // ---- element classes, cut into tiles (eqd_tiles.h)
     std::vector<int> members[3];
-    for (int e = 0; e < Ne; ++e) {
-      const int t = h->etype[e];
-      int c;
-      if (t == 2) c = CLS_PML;
-      else {
-        need(t == 1 || (t >= 11 && t <= 13), "eqd_set_mesh: unknown element type");
-        c = CLS_REG;
-        for (int k = 0; k < 8; ++k) if (h->ndof[h->conn[8 * (size_t)e + k]] == 12) c = CLS_REGX;
-      }
-      members[c].push_back(e);
+    {
+      std::vector<signed char> ccode(Ne);
+      parallel_range((size_t)Ne, [&](size_t b, size_t e) {
+        for (size_t el = b; el < e; ++el) {
+          const int t = h->etype[el];
+          int c;
+          if (t == 2) c = CLS_PML;
+          else if (t == 1 || (t >= 11 && t <= 13)) {
+            c = CLS_REG;
+            for (int k = 0; k < 8; ++k) if (h->ndof[h->conn[8 * el + k]] == 12) c = CLS_REGX;
+          } else c = -1;
+          ccode[el] = (signed char)c;
+        }
+      });
+      size_t cntc[3] = {0, 0, 0};
+      for (int e = 0; e < Ne; ++e) { need(ccode[e] >= 0, "eqd_set_mesh: unknown element type"); cntc[ccode[e]]++; }
+      for (int c = 0; c < 3; ++c) members[c].reserve(cntc[c]);
+      for (int e = 0; e < Ne; ++e) members[ccode[e]].push_back(e);
     }
     lap.lap("node kinds + classes");
     int gny = 0, gnz = 0;
@@ -827,31 +896,36 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
       C.n = T.n; C.S = T.S; C.nf = nf[c]; C.nstress = nstr[c];
       C.nTiles = T.nTiles; C.nFaceTiles = 0; C.LS = T.LS; C.PFS = T.PFS;
       need(tile_smem_bytes(c, h->qmode, C.LS) <= 227 * 1024, "eqd_set_mesh: tile does not fit shared memory");
-      C.refId = T.refId;
-      for (int s = 0; s < C.S; ++s) if (C.refId[s] >= 0) h->elemCode[C.refId[s]] = c | (s << 2);
-      C.tileNodeH = T.tileNode; C.tnodeH = T.tnode;
-      if (!C.n) continue;
+      C.refId = std::move(T.refId);
+      parallel_range((size_t)C.S, [&](size_t sb, size_t se) {
+        for (size_t s = sb; s < se; ++s) if (C.refId[s] >= 0) h->elemCode[C.refId[s]] = c | ((int)s << 2);
+      });
+      C.tileNodeH = T.tileNode;
+      if (!C.n) { C.tnodeH = std::move(T.tnode); continue; }
       need(C.LS <= (c == CLS_PML ? EQD_PML_LS : EQD_REG_LS), "eqd_set_mesh: tile has too many nodes");
       C.tileRecH.resize(C.nTiles);
       for (int t = 0; t < C.nTiles; ++t)
         C.tileRecH[t] = make_int4(T.tileElem[t], T.tileCnt[t] | ((int)T.tileColours[t] << 16), T.tileNode[t], T.tileNode[t + 1] - T.tileNode[t]);
       C.tileRec.upload(C.tileRecH);
       C.tnode.upload(T.tnode); C.lconn.upload(T.lconn);
+      C.tnodeH = std::move(T.tnode);
       C.pf.alloc((size_t)C.nf * C.PFS);
       C.stress.alloc((size_t)C.nstress * C.S);
       if (c == CLS_PML) {
         std::vector<double> dm(3 * (size_t)C.S, 0.0);
-        for (int s = 0; s < C.S; ++s) {
-          const int e = C.refId[s];
-          if (e < 0) continue;
-          double xc[3] = {0, 0, 0};
-          for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 8; ++j) xc[i] = xc[i] + h->coor[i + 3 * (size_t)h->conn[8 * (size_t)e + j]];
-          for (int i = 0; i < 3; ++i) xc[i] = xc[i] / 8;
-          double d[3];
-          pml_elem_damps(P, xc, d);
-          for (int i = 0; i < 3; ++i) dm[(size_t)i * C.S + s] = d[i];
-        }
+        parallel_range((size_t)C.S, [&](size_t sb, size_t se) {
+          for (size_t s = sb; s < se; ++s) {
+            const int e = C.refId[s];
+            if (e < 0) continue;
+            double xc[3] = {0, 0, 0};
+            for (int i = 0; i < 3; ++i)
+              for (int j = 0; j < 8; ++j) xc[i] = xc[i] + h->coor[i + 3 * (size_t)h->conn[8 * (size_t)e + j]];
+            for (int i = 0; i < 3; ++i) xc[i] = xc[i] / 8;
+            double d[3];
+            pml_elem_damps(P, xc, d);
+            for (int i = 0; i < 3; ++i) dm[(size_t)i * C.S + s] = d[i];
+          }
+        });
         C.damps.upload(dm);
       } else if (h->qmode) {
         std::vector<uint8_t> qc(C.S, 0);
@@ -878,42 +952,64 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
     lap.lap("tile plan + uploads");
     // ---- node -> tile-node slots by rank, class then ascending tile id
     {
+      // every thread owns a contiguous range of nodes and scans all tile-node lists for them,
+      // so each node's slots are still visited in (class, ascending slot) order
       std::vector<uint8_t> cnt(Nn, 0);
-      int maxCnt = 2;
-      for (int c = 0; c < 3; ++c)
-        for (int nd : h->cls[c].tnodeH)
-          if (nd >= 0 && EQD_INFO_KIND(h->info[nd]) != KIND_FIXED) {
-            need(cnt[nd] < 255, "eqd_set_mesh: a node belongs to more than 255 tiles");
-            maxCnt = std::max(maxCnt, (int)++cnt[nd]);
-          }
+      const int nth = host_threads();
+      std::vector<int> maxv(nth + 1, 2), badv(nth + 1, 0);
       const size_t NS = h->NnS;
+      const size_t per = ((size_t)Nn + nth - 1) / nth;
+      auto scan = [&](std::vector<uint32_t>* tab) {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nth; ++t)
+          th.emplace_back([&, t] {
+            const int lo = (int)std::min((size_t)Nn, t * per), hi = (int)std::min((size_t)Nn, (t + 1) * per);
+            if (lo >= hi) return;
+            for (int c = 0; c < 3; ++c) {
+              const raw_vector<int>& tn = h->cls[c].tnodeH;
+              for (size_t sl = 0; sl < tn.size(); ++sl) {
+                const int nd = tn[sl];
+                if (nd < lo || nd >= hi) continue;
+                const int kind = EQD_INFO_KIND(h->info[nd]);
+                if (kind == KIND_FIXED) continue;
+                if (!tab) {
+                  if (cnt[nd] == 255) { badv[t] = 1; continue; }
+                  maxv[t] = std::max(maxv[t], (int)++cnt[nd]);
+                } else {
+                  if (c == CLS_REG && kind == KIND_PML12) { badv[t] = 2; continue; }
+                  (*tab)[(size_t)cnt[nd]++ * NS + nd] = EQD_SLOT(c, sl);
+                }
+              }
+            }
+          });
+        for (auto& x : th) x.join();
+      };
+      scan(nullptr);
+      int maxCnt = 2;
+      for (int t = 0; t < nth; ++t) { maxCnt = std::max(maxCnt, maxv[t]); need(!badv[t], "eqd_set_mesh: a node belongs to more than 255 tiles"); }
       std::vector<uint32_t> tab((size_t)maxCnt * NS, 0);
-      std::fill(cnt.begin(), cnt.end(), 0);
-      for (int c = 0; c < 3; ++c) {
-        const std::vector<int>& tn = h->cls[c].tnodeH;
-        for (size_t s = 0; s < tn.size(); ++s) {
-          const int nd = tn[s];
-          if (nd < 0) continue;
-          const int kind = EQD_INFO_KIND(h->info[nd]);
-          if (kind == KIND_FIXED) continue;
-          need(!(c == CLS_REG && kind == KIND_PML12), "internal: REG element on a 12-dof node");
-          tab[(size_t)cnt[nd]++ * NS + nd] = EQD_SLOT(c, s);
-        }
-      }
+      parallel_range((size_t)Nn, [&](size_t b, size_t e) { std::fill(cnt.begin() + b, cnt.begin() + e, (uint8_t)0); });
+      scan(&tab);
+      for (int t = 0; t < nth; ++t) need(!badv[t], "internal: REG element on a 12-dof node");
       h->dSlotCnt.upload(cnt);
       h->dSlotTab.upload(tab);
     }
     lap.lap("slot table");
     // ---- PML node damping profile (comdampv, recomputed every step in the reference)
     std::vector<double> dp(3 * (size_t)h->NpS, 0.0);
-    for (int n = 0; n < Nn; ++n)
-      if (EQD_INFO_KIND(h->info[n]) == KIND_PML12) {
-        double d[3];
-        if (!comdampv(P, h->coor[3 * (size_t)n], h->coor[3 * (size_t)n + 1], h->coor[3 * (size_t)n + 2], d))
-          throw ArgError("negative PML damping (comdampv.f90:114-118)");
-        const size_t slot = EQD_INFO_SLOT(h->info[n]);
-        for (int i = 0; i < 3; ++i) dp[(size_t)i * h->NpS + slot] = d[i];
-      }
+    {
+      std::vector<char> neg(1, 0);
+      parallel_range((size_t)Nn, [&](size_t b, size_t e) {
+        for (size_t n = b; n < e; ++n)
+          if (EQD_INFO_KIND(h->info[n]) == KIND_PML12) {
+            double d[3];
+            if (!comdampv(P, h->coor[3 * n], h->coor[3 * n + 1], h->coor[3 * n + 2], d)) { neg[0] = 1; continue; }
+            const size_t slot = EQD_INFO_SLOT(h->info[n]);
+            for (int i = 0; i < 3; ++i) dp[(size_t)i * h->NpS + slot] = d[i];
+          }
+      });
+      if (neg[0]) throw ArgError("negative PML damping (comdampv.f90:114-118)");
+    }
     h->dDampp.upload(dp);
     h->dVel.alloc(3 * (size_t)h->NnS); h->dDisp.alloc(3 * (size_t)h->NnS);
     h->dV1p.alloc(12 * (size_t)h->NpS);
@@ -948,7 +1044,7 @@ int eqd_set_elem_ops(eqd_handle* h, const double* eleshp, const double* eledet, 
     }
     auto spread = [&](const double* src, int K, auto member, int k0, int nk, int rowOff) {
       tmp.alloc((size_t)K * Ne, false);
-      CK(cudaMemcpy(tmp.p, src, sizeof(double) * (size_t)K * Ne, cudaMemcpyHostToDevice));
+      h2d(tmp.p, src, sizeof(double) * (size_t)K * Ne);
       for (int c = 0; c < 3; ++c) {
         ElemClass& C = h->cls[c];
         DevBuf<double>& dst = C.*member;
@@ -969,7 +1065,7 @@ int eqd_set_elem_ops(eqd_handle* h, const double* eleshp, const double* eledet, 
     }
     if (h->body) {
       tmp.alloc((size_t)24 * Ne, false);
-      CK(cudaMemcpy(tmp.p, elemass, sizeof(double) * (size_t)24 * Ne, cudaMemcpyHostToDevice));
+      h2d(tmp.p, elemass, sizeof(double) * (size_t)24 * Ne);
       for (int c = 0; c < 3; ++c) {
         ElemClass& C = h->cls[c];
         if (!C.n) continue;
@@ -989,13 +1085,17 @@ int eqd_set_elem_ops(eqd_handle* h, const double* eleshp, const double* eledet, 
       if (!C.n) continue;
       std::vector<double> sg((size_t)C.nstress * C.S, 0.0), qm;
       if (h->qmode && c != CLS_PML) qm.assign(6 * (size_t)C.S, 0.0);
-      for (int s = 0; s < C.S; ++s) {
-        if (C.refId[s] < 0) continue;
-        const int base = h->stressIdx[C.refId[s]];
-        need(base >= 0 && base + (c == CLS_PML ? 21 : 12) <= h->sizeStress, "eqd_set_elem_ops: stress index out of range");
-        for (int k = 0; k < C.nstress; ++k) sg[(size_t)k * C.S + s] = stressArr[base + k];
-        if (!qm.empty()) for (int k = 0; k < 6; ++k) qm[(size_t)k * C.S + s] = stressArr[base + 6 + k];
-      }
+      std::vector<char> badv(1, 0);
+      parallel_range((size_t)C.S, [&](size_t sb, size_t se) {
+        for (size_t s = sb; s < se; ++s) {
+          if (C.refId[s] < 0) continue;
+          const int base = h->stressIdx[C.refId[s]];
+          if (!(base >= 0 && base + (c == CLS_PML ? 21 : 12) <= h->sizeStress)) { badv[0] = 1; continue; }
+          for (int k = 0; k < C.nstress; ++k) sg[(size_t)k * C.S + s] = stressArr[base + k];
+          if (!qm.empty()) for (int k = 0; k < 6; ++k) qm[(size_t)k * C.S + s] = stressArr[base + 6 + k];
+        }
+      });
+      need(!badv[0], "eqd_set_elem_ops: stress index out of range");
       C.stress.upload(sg);
       if (!qm.empty()) C.qmem.upload(qm);
     }
@@ -1017,29 +1117,38 @@ int eqd_set_nodal(eqd_handle* h, const double* nodalMassArr, const double* fnms,
     h->massH.assign(Nn, 1.0);
     std::vector<double> vel(3 * NS, 0.0), disp(3 * NS, 0.0), v1p(12 * PS, 0.0), acc;
     bool anyAcc = false;
-    if (nodalForceArr)
-      for (int k = 0; k < h->Neq && !anyAcc; ++k) anyAcc = nodalForceArr[k] != 0.0;
-    if (anyAcc) acc.assign(3 * NS + 12 * PS, 0.0);
-    for (int n = 0; n < Nn; ++n) {
-      const int kind = EQD_INFO_KIND(h->info[n]);
-      if (kind == KIND_FIXED) continue;
-      const int st = h->eqStart[n], nd = h->ndof[n];
-      const double m = nodalMassArr[h->eqIdx[st] - 1];
-      for (int j = 1; j < nd; ++j)
-        need(nodalMassArr[h->eqIdx[st + j] - 1] == m, "eqd_set_nodal: dofs of one node carry different lumped masses");
-      h->massH[n] = m;
-      for (int j = 0; j < 3; ++j) disp[j * NS + n] = dispArr[j + 3 * (size_t)n];
-      if (kind == KIND_FREE3) {
-        // v1 and velArr are the same quantity for a 3-dof node after the first update (driver.f90:102-103)
-        for (int j = 0; j < 3; ++j) vel[j * NS + n] = v1[h->eqIdx[st + j] - 1];
-        if (anyAcc) for (int j = 0; j < 3; ++j) acc[j * NS + n] = nodalForceArr[h->eqIdx[st + j] - 1];
-      } else {
-        const size_t slot = EQD_INFO_SLOT(h->info[n]);
-        for (int j = 0; j < 12; ++j) v1p[j * PS + slot] = v1[h->eqIdx[st + j] - 1];
-        for (int j = 0; j < 3; ++j) vel[j * NS + n] = velArr[j + 3 * (size_t)n];
-        if (anyAcc) for (int j = 0; j < 12; ++j) acc[3 * NS + j * PS + slot] = nodalForceArr[h->eqIdx[st + j] - 1];
-      }
+    if (nodalForceArr) {
+      std::vector<char> any(1, 0);
+      parallel_range((size_t)h->Neq, [&](size_t b, size_t e) {
+        for (size_t k = b; k < e && !any[0]; ++k) if (nodalForceArr[k] != 0.0) any[0] = 1;
+      });
+      anyAcc = any[0] != 0;
     }
+    if (anyAcc) acc.assign(3 * NS + 12 * PS, 0.0);
+    std::vector<char> badv(1, 0);
+    parallel_range((size_t)Nn, [&](size_t nb, size_t ne) {
+      for (size_t n = nb; n < ne; ++n) {
+        const int kind = EQD_INFO_KIND(h->info[n]);
+        if (kind == KIND_FIXED) continue;
+        const int st = h->eqStart[n], nd = h->ndof[n];
+        const double m = nodalMassArr[h->eqIdx[st] - 1];
+        for (int j = 1; j < nd; ++j)
+          if (nodalMassArr[h->eqIdx[st + j] - 1] != m) badv[0] = 1;
+        h->massH[n] = m;
+        for (int j = 0; j < 3; ++j) disp[j * NS + n] = dispArr[j + 3 * n];
+        if (kind == KIND_FREE3) {
+          // v1 and velArr are the same quantity for a 3-dof node after the first update (driver.f90:102-103)
+          for (int j = 0; j < 3; ++j) vel[j * NS + n] = v1[h->eqIdx[st + j] - 1];
+          if (anyAcc) for (int j = 0; j < 3; ++j) acc[j * NS + n] = nodalForceArr[h->eqIdx[st + j] - 1];
+        } else {
+          const size_t slot = EQD_INFO_SLOT(h->info[n]);
+          for (int j = 0; j < 12; ++j) v1p[j * PS + slot] = v1[h->eqIdx[st + j] - 1];
+          for (int j = 0; j < 3; ++j) vel[j * NS + n] = velArr[j + 3 * n];
+          if (anyAcc) for (int j = 0; j < 12; ++j) acc[3 * NS + j * PS + slot] = nodalForceArr[h->eqIdx[st + j] - 1];
+        }
+      }
+    });
+    need(!badv[0], "eqd_set_nodal: dofs of one node carry different lumped masses");
     h->dVel.upload(vel); h->dDisp.upload(disp); h->dV1p.upload(v1p); h->dMass.upload(h->massH);
     if (anyAcc) h->dAccel0.upload(acc); else h->dAccel0.release();
     lap.lap("all");
@@ -1217,11 +1326,13 @@ int eqd_run(eqd_handle* h, int32_t nt_begin, int32_t nt_end) {
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     if (h->timing) { CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1)); CK(cudaEventRecord(t0, h->stream)); }
     for (int nt = nt_begin; nt <= nt_end; ++nt) {
-      const bool overlap = multi && h->commStream && h->optOverlap;
-      step_pre(h, overlap ? 1 : 0);
-      if (multi && !overlap) halo_all_nccl(h, h->stream);
-      step_post(h);
+      const int ov = !h->commStream ? 0 : h->optOverlap < 0 ? (multi ? 1 : 0) : h->optOverlap;
+      step_pre(h, ov, multi);
+      if (multi && !ov) halo_all_nccl(h, h->stream);
+      step_post(h, ov);
     }
+    // the last step's fault solver ran on the communication stream
+    if (h->commStream && nt_end >= nt_begin) CK(cudaStreamWaitEvent(h->stream, h->evComm, 0));
     if (h->timing) {
       CK(cudaEventRecord(t1, h->stream));
       CK(cudaEventSynchronize(t1));
@@ -1248,7 +1359,7 @@ int eqd_run_group(eqd_handle** hs, int32_t n, int32_t nt_begin, int32_t nt_end) 
       prepare_run(hs[r], nt_begin);
     }
     for (int nt = nt_begin; nt <= nt_end; ++nt) {
-      for (int r = 0; r < n; ++r) { CK(cudaSetDevice(hs[r]->device)); step_pre(hs[r], 2); }
+      for (int r = 0; r < n; ++r) { CK(cudaSetDevice(hs[r]->device)); step_pre(hs[r], 0, false); }
       for (int a = 0; a < 3; ++a) {
         for (int r = 0; r < n; ++r) {
           eqd_handle* h = hs[r];
@@ -1277,7 +1388,7 @@ int eqd_run_group(eqd_handle** hs, int32_t n, int32_t nt_begin, int32_t nt_end) 
         // step_pre/step_post kernels of every rank being enqueued in between and
         // by the device-wide join below
       }
-      for (int r = 0; r < n; ++r) { CK(cudaSetDevice(hs[r]->device)); step_post(hs[r]); }
+      for (int r = 0; r < n; ++r) { CK(cudaSetDevice(hs[r]->device)); step_post(hs[r], 0); }
       // lock-step join so that no rank overwrites a send buffer a neighbour still reads
       for (int r = 0; r < n; ++r) { CK(cudaSetDevice(hs[r]->device)); CK(cudaStreamSynchronize(hs[r]->stream)); }
     }
@@ -1304,7 +1415,9 @@ int eqd_fetch(eqd_handle* h, int32_t which, void* dst, int64_t dst_bytes) {
       case EQD_F_DISP: case EQD_F_VEL: {
         want(3 * (size_t)Nn);
         std::vector<double> v = (which == EQD_F_DISP ? h->dDisp : h->dVel).download();
-        for (int n = 0; n < Nn; ++n) for (int j = 0; j < 3; ++j) out[j + 3 * (size_t)n] = v[j * NS + n];
+        parallel_range((size_t)Nn, [&](size_t b, size_t e) {
+          for (size_t n = b; n < e; ++n) for (int j = 0; j < 3; ++j) out[j + 3 * n] = v[j * NS + n];
+        });
         break;
       }
       case EQD_F_V1: case EQD_F_FORCE: case EQD_F_MASS: {

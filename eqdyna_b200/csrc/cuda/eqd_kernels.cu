@@ -106,6 +106,7 @@ __device__ __forceinline__ void gather12(const NodeArgs& A, int n, int cnt, doub
 // previous step's `nodalForceArr/nodalMassArr` (driver.f90:29).  Two kernels so
 // that the 3-dof one (almost every node) stays light enough for full occupancy:
 // its gather is a chain of dependent loads that only parallelism hides.
+template <bool SKIP>
 __global__ void __launch_bounds__(256, 4) k_node_update3(NodeArgs A) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= A.Nn) return;
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(256, 4) k_node_update3(NodeArgs A) {
   for (int j = 0; j < 3; ++j) { v[j] = ld_now(A.vel + j * NS + n); d[j] = ld_now(A.disp + j * NS + n); }
   // no early exit: fixed and PML nodes run through with an empty gather and skip the
   // stores (vel = disp = 0 for ever for fixed nodes, driver.f90:142-145)
-  const bool mine = EQD_INFO_KIND(info) == KIND_FREE3;
+  const bool mine = EQD_INFO_KIND(info) == KIND_FREE3 && !(SKIP && EQD_INFO_SPECIAL(info));
   const int cnt = mine ? cnt0 : 0;
   const double dt = A.dt;
   double a[3] = {0.0, 0.0, 0.0};
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(256, 4) k_node_update3(NodeArgs A) {
     if (mine) { a[0] = A.accel0[n]; a[1] = A.accel0[NS + n]; a[2] = A.accel0[2 * NS + n]; }
   } else {
     double f[3];
-    if (mine && EQD_INFO_SPECIAL(info)) {
+    if (!SKIP && mine && EQD_INFO_SPECIAL(info)) {
       f[0] = A.force[n]; f[1] = A.force[NS + n]; f[2] = A.force[2 * NS + n];
     } else {
       gather3(A, n, cnt, u0, u1, f);
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(256, 4) k_node_update3(NodeArgs A) {
 }
 
 // 12-dof PML nodes: split-field velocities with damping (driver.f90:105-141), one thread per PML slot
+template <bool SKIP>
 __global__ void __launch_bounds__(128) k_node_update12(NodeArgs A) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= A.Np) return;
@@ -165,6 +167,7 @@ __global__ void __launch_bounds__(128) k_node_update12(NodeArgs A) {
   const int info = ldc_now(A.info + n);
   const int cnt = ldc_now(A.slotCnt + n);
   const double m = ldc_now(A.mass + n);
+  if (SKIP && EQD_INFO_SPECIAL(info)) return;
   double dis[3];
 #pragma unroll
   for (int j = 0; j < 3; ++j) dis[j] = ld_now(A.disp + j * NS + n);
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(128) k_node_update12(NodeArgs A) {
     for (int j = 0; j < 12; ++j) a[j] = ap[j * PS + slot];
   } else {
     double f[12];
-    if (EQD_INFO_SPECIAL(info)) {
+    if (!SKIP && EQD_INFO_SPECIAL(info)) {
       const double* fp = A.force + 3 * NS;
 #pragma unroll
       for (int j = 0; j < 12; ++j) f[j] = fp[j * PS + slot];
@@ -207,6 +210,64 @@ __global__ void __launch_bounds__(128) k_node_update12(NodeArgs A) {
     A.vel[j * NS + n] = vel[j];
     A.disp[j * NS + n] = dis[j] + vel[j] * dt;
     bad |= (vel[j] != vel[j]);
+  }
+  if (bad) {
+    if (atomicExch(&A.st->nanFlag, 1) == 0) A.st->nanNode = n + 1;
+  }
+}
+
+// The special nodes (split-node pairs, rank-face nodes) of the same update: their
+// force comes from force[] / forcep[], which the halo and the fault solver of the
+// previous step finish on the communication stream.  Same arithmetic as above.
+__global__ void __launch_bounds__(128) k_node_update_special(NodeArgs A, const int* __restrict__ list, int nList) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nList) return;
+  const int n = list[i];
+  const int info = LDG(A.info + n);
+  const int kind = EQD_INFO_KIND(info);
+  const size_t NS = A.NnS, PS = A.NpS;
+  const double dt = A.dt;
+  const double m = LDG(A.mass + n);
+  bool bad = false;
+  if (kind == KIND_FREE3) {
+    double a[3];
+    if (A.accel0) { a[0] = A.accel0[n]; a[1] = A.accel0[NS + n]; a[2] = A.accel0[2 * NS + n]; }
+    else { a[0] = A.force[n] / m; a[1] = A.force[NS + n] / m; a[2] = A.force[2 * NS + n] / m; }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      double v = A.vel[j * NS + n], d = A.disp[j * NS + n];
+      v = v + a[j] * dt;                      // driver.f90:102
+      d = d + v * dt;                         // :104
+      bad |= (v != v);
+      A.vel[j * NS + n] = v; A.disp[j * NS + n] = d;
+    }
+  } else if (kind == KIND_PML12) {
+    const int slot = EQD_INFO_SLOT(info);
+    double a[12], v[12];
+    const double* src = (A.accel0 ? A.accel0 : A.force) + 3 * NS;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) a[j] = A.accel0 ? src[j * PS + slot] : src[j * PS + slot] / m;
+    const double dmp[3] = {LDG(A.dampp + slot), LDG(A.dampp + PS + slot), LDG(A.dampp + 2 * PS + slot)};
+    const double rdt = 1.0 / dt;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {             // driver.f90:112-117
+      const double dj = dmp[j % 3];
+      v[j] = (a[j] + A.v1p[j * PS + slot] * (rdt - dj / 2.0)) / (rdt + dj / 2.0);
+    }
+#pragma unroll
+    for (int j = 9; j < 12; ++j) v[j] = A.v1p[j * PS + slot] + a[j] * dt;   // :118-123
+#pragma unroll
+    for (int j = 0; j < 12; ++j) A.v1p[j * PS + slot] = v[j];
+    double vel[3];
+    vel[0] = v[0] + v[1] + v[2] + v[9];       // :125-141
+    vel[1] = v[3] + v[4] + v[5] + v[10];
+    vel[2] = v[6] + v[7] + v[8] + v[11];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      A.vel[j * NS + n] = vel[j];
+      A.disp[j * NS + n] = A.disp[j * NS + n] + vel[j] * dt;
+      bad |= (vel[j] != vel[j]);
+    }
   }
   if (bad) {
     if (atomicExch(&A.st->nanFlag, 1) == 0) A.st->nanNode = n + 1;
@@ -290,6 +351,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+
+// named barrier over the `nthreads` threads of one role (ids 1..4; 0 is __syncthreads): the roles of a
+// tile kernel accumulate into disjoint force rows, so an assembly phase only has to order the warps
+// of its own role
+__device__ __forceinline__ void role_sync(int role, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(role + 1), "r"(nthreads) : "memory");
 }
 
 // per-thread asynchronous 8-byte copy global -> shared (LDGSTS): gathers that need no register staging
@@ -648,11 +716,12 @@ __global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
       const int li = lc[i] & EQD_LN_MASK, col = lc[i] >> EQD_LN_BITS;
       for (int c = 0; c < NC; ++c) {
         if (act && col == c) { acc[li] += f[i][0]; acc[LS + li] += f[i][1]; acc[2 * LS + li] += f[i][2]; }
-        __syncthreads();
+        role_sync(role, SE);
       }
     }
   }
-  // ---- flush the tile's partial forces
+  // ---- flush the tile's partial forces (both roles' rows)
+  __syncthreads();
 #pragma unroll
   for (int k = 0; k < NPT; ++k) {
     const int i = tid + k * NT;
@@ -809,10 +878,12 @@ __global__ void __launch_bounds__(4 * EQD_STAGE_PML, 2) k_tile_pml(ElemArgs A) {
       // role 2: s0[6], body                          role 3: hv[4][3]
       double c0 = 0, c1 = 0, c2 = 0, detw = 0;
       double s0[6] = {0, 0, 0, 0, 0, 0};
-      double hv[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
       double body[BODY ? 24 : 1];
-      double qcoef = 0.0;
-      double qv[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+      // roles 0-2: the element's shape derivatives; role 3: its 8x3 hourglass forces.  Held in
+      // registers so that the stage buffer is free (and the next stage in flight) during assembly.
+      double r24[24];
+#pragma unroll
+      for (int k = 0; k < 24; ++k) r24[k] = 0.0;
       mbar_wait(bar, parity);
       parity ^= 1;
 #define OP(r) ops[(r) * SE + lane]
@@ -834,14 +905,18 @@ __global__ void __launch_bounds__(4 * EQD_STAGE_PML, 2) k_tile_pml(ElemArgs A) {
     out = x;                                                              \
     A.stress[(size_t)(k) * S + e] = x;                                    \
   }
+        if (role < 3) {
+#pragma unroll
+          for (int k = 0; k < 24; ++k) r24[k] = OP(PR_SHP + k);
+        }
         if (role == 0) {
           double g00 = 0, g11 = 0, g22 = 0;  // assembleGlobalKU.f90:248-275
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int li = lc[i] & EQD_LN_MASK;
-            g00 = g00 + OP(PR_SHP + 3 * i) * sv[li];
-            g11 = g11 + OP(PR_SHP + 3 * i + 1) * sv[LS + li];
-            g22 = g22 + OP(PR_SHP + 3 * i + 2) * sv[2 * LS + li];
+            g00 = g00 + r24[3 * i] * sv[li];
+            g11 = g11 + r24[3 * i + 1] * sv[LS + li];
+            g22 = g22 + r24[3 * i + 2] * sv[2 * LS + li];
           }
           double s[9];
           PML_UPD(0, l2m, g00, 0, s[0]) PML_UPD(1, lam, g11, 1, s[1]) PML_UPD(2, lam, g22, 2, s[2])
@@ -854,7 +929,7 @@ __global__ void __launch_bounds__(4 * EQD_STAGE_PML, 2) k_tile_pml(ElemArgs A) {
           for (int i = 0; i < 8; ++i) {
             const int li = lc[i] & EQD_LN_MASK;
             const double vx = sv[li], vy = sv[LS + li], vz = sv[2 * LS + li];
-            const double s1 = OP(PR_SHP + 3 * i), s2 = OP(PR_SHP + 3 * i + 1), s3 = OP(PR_SHP + 3 * i + 2);
+            const double s1 = r24[3 * i], s2 = r24[3 * i + 1], s3 = r24[3 * i + 2];
             g01 = g01 + s1 * vy; g10 = g10 + s2 * vx;
             g02 = g02 + s1 * vz; g20 = g20 + s3 * vx;
             g12 = g12 + s2 * vz; g21 = g21 + s3 * vy;
@@ -870,7 +945,7 @@ __global__ void __launch_bounds__(4 * EQD_STAGE_PML, 2) k_tile_pml(ElemArgs A) {
           for (int i = 0; i < 8; ++i) {
             const int li = lc[i] & EQD_LN_MASK;
             const double vx = sv[li], vy = sv[LS + li], vz = sv[2 * LS + li];
-            const double s1 = OP(PR_SHP + 3 * i), s2 = OP(PR_SHP + 3 * i + 1), s3 = OP(PR_SHP + 3 * i + 2);
+            const double s1 = r24[3 * i], s2 = r24[3 * i + 1], s3 = r24[3 * i + 2];
             // assembleGlobalKU.f90:215-246
             sr[0] = sr[0] + s1 * vx;
             sr[1] = sr[1] + s2 * vy;
@@ -909,7 +984,7 @@ __global__ void __launch_bounds__(4 * EQD_STAGE_PML, 2) k_tile_pml(ElemArgs A) {
                 phid[m][2] = phid[m][2] + p * lz;
               }
             }
-            double ssv[6];
+            double ssv[6], hv[4][3];
 #pragma unroll
             for (int i = 0; i < 6; ++i) ssv[i] = OP(PR_SS + i);
 #pragma unroll
@@ -918,9 +993,22 @@ __global__ void __launch_bounds__(4 * EQD_STAGE_PML, 2) k_tile_pml(ElemArgs A) {
               hv[m][1] = ssv[1] * phid[m][0] + ssv[3] * phid[m][1] + ssv[4] * phid[m][2];
               hv[m][2] = ssv[2] * phid[m][0] + ssv[4] * phid[m][1] + ssv[5] * phid[m][2];
             }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              double h0 = 0.0, h1 = 0.0, h2 = 0.0;
+#pragma unroll
+              for (int m = 0; m < 4; ++m) {   // hrglss.f90:41-54
+                const double p = OP(PR_PHI + 8 * m + i);
+                h0 = h0 - p * hv[m][0];
+                h1 = h1 - p * hv[m][1];
+                h2 = h2 - p * hv[m][2];
+              }
+              r24[3 * i] = h0; r24[3 * i + 1] = h1; r24[3 * i + 2] = h2;
+            }
           } else {
             const int fi[4][8] = {{1, 1, -1, -1, -1, -1, 1, 1}, {1, -1, -1, 1, -1, 1, 1, -1},
                                   {1, -1, 1, -1, 1, -1, 1, -1}, {1, -1, 1, -1, -1, 1, -1, 1}};
+            double qv[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int li = lc[i] & EQD_LN_MASK;
@@ -932,81 +1020,26 @@ __global__ void __launch_bounds__(4 * EQD_STAGE_PML, 2) k_tile_pml(ElemArgs A) {
                 qv[2][j] = qv[2][j] + vz * fi[j][i];
               }
             }
-            qcoef = 0.25 * A.kapa_hg * LDG(A.rho + e) * LDG(A.vp + e) * pow(OP(PR_DET) * A.w, 2.0 / 3.0);
+            const double qcoef = 0.25 * A.kapa_hg * LDG(A.rho + e) * LDG(A.vp + e) * pow(OP(PR_DET) * A.w, 2.0 / 3.0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              double h0 = 0.0, h1 = 0.0, h2 = 0.0;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                h0 = h0 - qcoef * qv[0][j] * fi[j][i];
+                h1 = h1 - qcoef * qv[1][j] * fi[j][i];
+                h2 = h2 - qcoef * qv[2][j] * fi[j][i];
+              }
+              r24[3 * i] = h0; r24[3 * i + 1] = h1; r24[3 * i + 2] = h2;
+            }
           }
         }
 #undef PML_UPD
       }
-      // shp / phi of the stage are still needed by the assembly phases below, so the
-      // next stage is requested only after them; the second CTA of the SM covers the gap
-      // force of local node i (registers + the stage's shp / phi rows)
-      auto node_force = [&](int i, double fo[6]) {
-#pragma unroll
-        for (int j = 0; j < 6; ++j) fo[j] = 0.0;
-        if (act) {
-          const double s1 = OP(PR_SHP + 3 * i), s2 = OP(PR_SHP + 3 * i + 1), s3 = OP(PR_SHP + 3 * i + 2);
-          if (role == 0) {         // :328-344, dofs 1,5,9
-            fo[0] = 0.0 - detw * s1 * c0;
-            fo[1] = 0.0 - detw * s2 * c1;
-            fo[2] = 0.0 - detw * s3 * c2;
-          } else if (role == 1) {  // dofs 2,3,4,6,7,8
-            fo[0] = 0.0 - detw * s2 * c0;
-            fo[1] = 0.0 - detw * s3 * c1;
-            fo[2] = 0.0 - detw * s1 * c0;
-            fo[3] = 0.0 - detw * s3 * c2;
-            fo[4] = 0.0 - detw * s1 * c1;
-            fo[5] = 0.0 - detw * s2 * c2;
-          } else if (role == 2) {  // dofs 10-12
-            double b0 = 0.0, b1 = 0.0, b2 = 0.0;
-            if (BODY) { b0 = body[3 * i]; b1 = body[3 * i + 1]; b2 = body[3 * i + 2]; }
-            fo[0] = b0 - detw * (s1 * s0[0] + s3 * s0[4] + s2 * s0[5]);
-            fo[1] = b1 - detw * (s2 * s0[1] + s3 * s0[3] + s1 * s0[5]);
-            fo[2] = b2 - detw * (s3 * s0[2] + s2 * s0[3] + s1 * s0[4]);
-          } else {                 // hourglass, own rows 13-15
-            if (CHG == 1) {
-#pragma unroll
-              for (int m = 0; m < 4; ++m) {
-                const double p = OP(PR_PHI + 8 * m + i);
-                fo[0] = fo[0] - p * hv[m][0];
-                fo[1] = fo[1] - p * hv[m][1];
-                fo[2] = fo[2] - p * hv[m][2];
-              }
-            } else {
-              const int fi[4][8] = {{1, 1, -1, -1, -1, -1, 1, 1}, {1, -1, -1, 1, -1, 1, 1, -1},
-                                    {1, -1, 1, -1, 1, -1, 1, -1}, {1, -1, 1, -1, -1, 1, -1, 1}};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                fo[0] = fo[0] - qcoef * qv[0][j] * fi[j][i];
-                fo[1] = fo[1] - qcoef * qv[1][j] * fi[j][i];
-                fo[2] = fo[2] - qcoef * qv[2][j] * fi[j][i];
-              }
-            }
-          }
-        }
-      };
-      double fo[6];
-      node_force(0, fo);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int li = lc[i] & EQD_LN_MASK, col = lc[i] >> EQD_LN_BITS;
-        double fn[6] = {0, 0, 0, 0, 0, 0};
-        for (int c = 0; c < NC; ++c) {
-          if (act && col == c) {
-            if (role == 0) { sf[0 * LS + li] += fo[0]; sf[4 * LS + li] += fo[1]; sf[8 * LS + li] += fo[2]; }
-            else if (role == 1) {
-              sf[1 * LS + li] += fo[0]; sf[2 * LS + li] += fo[1]; sf[3 * LS + li] += fo[2];
-              sf[5 * LS + li] += fo[3]; sf[6 * LS + li] += fo[4]; sf[7 * LS + li] += fo[5];
-            } else if (role == 2) { sf[9 * LS + li] += fo[0]; sf[10 * LS + li] += fo[1]; sf[11 * LS + li] += fo[2]; }
-            else { sf[12 * LS + li] += fo[0]; sf[13 * LS + li] += fo[1]; sf[14 * LS + li] += fo[2]; }
-          }
-          // the next node's force is formed while the CTA drains into the barrier
-          if (c == NC - 1 && i < 7) node_force(i + 1, fn);
-          __syncthreads();
-        }
-#pragma unroll
-        for (int j = 0; j < 6; ++j) fo[j] = fn[j];
-      }
 #undef OP
+      // the stage buffer and the nodal values are consumed: request the next stage, or the
+      // next tile's first stage and its nodes; they land while the forces are assembled
+      __syncthreads();
       const bool last = base + SE >= ne;
       if (!last) request(rc, base + SE);
       else if (more) {
@@ -1015,7 +1048,39 @@ __global__ void __launch_bounds__(4 * EQD_STAGE_PML, 2) k_tile_pml(ElemArgs A) {
         parityN ^= 1;
         gather_nodes(rn);
       }
+      // ---- ordered assembly (assembleGlobalKU.f90:328-344): 8 local-node phases
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int li = lc[i] & EQD_LN_MASK, col = lc[i] >> EQD_LN_BITS;
+        const double s1 = r24[3 * i], s2 = r24[3 * i + 1], s3 = r24[3 * i + 2];
+        for (int c = 0; c < NC; ++c) {
+          if (act && col == c) {
+            if (role == 0) {         // dofs 1,5,9
+              sf[0 * LS + li] += 0.0 - detw * s1 * c0;
+              sf[4 * LS + li] += 0.0 - detw * s2 * c1;
+              sf[8 * LS + li] += 0.0 - detw * s3 * c2;
+            } else if (role == 1) {  // dofs 2,3,4,6,7,8
+              sf[1 * LS + li] += 0.0 - detw * s2 * c0;
+              sf[2 * LS + li] += 0.0 - detw * s3 * c1;
+              sf[3 * LS + li] += 0.0 - detw * s1 * c0;
+              sf[5 * LS + li] += 0.0 - detw * s3 * c2;
+              sf[6 * LS + li] += 0.0 - detw * s1 * c1;
+              sf[7 * LS + li] += 0.0 - detw * s2 * c2;
+            } else if (role == 2) {  // dofs 10-12
+              double b0 = 0.0, b1 = 0.0, b2 = 0.0;
+              if (BODY) { b0 = body[3 * i]; b1 = body[3 * i + 1]; b2 = body[3 * i + 2]; }
+              sf[9 * LS + li] += b0 - detw * (s1 * s0[0] + s3 * s0[4] + s2 * s0[5]);
+              sf[10 * LS + li] += b1 - detw * (s2 * s0[1] + s3 * s0[3] + s1 * s0[5]);
+              sf[11 * LS + li] += b2 - detw * (s3 * s0[2] + s2 * s0[3] + s1 * s0[4]);
+            } else {                 // hourglass, own rows 13-15
+              sf[12 * LS + li] += s1; sf[13 * LS + li] += s2; sf[14 * LS + li] += s3;
+            }
+          }
+          role_sync(role, SE);   // the four roles own disjoint force rows
+        }
+      }
     }
+    __syncthreads();
     // ---- flush
 #pragma unroll
     for (int k = 0; k < NPT; ++k) {
@@ -1386,8 +1451,16 @@ static inline int nblk(long n, int b) { return (int)((n + b - 1) / b); }
 void launch_advance(StepState* st, double dt, cudaStream_t s) { k_advance<<<1, 1, 0, s>>>(st, dt); }
 
 void launch_node_update(const NodeArgs& A, cudaStream_t s) {
-  if (A.Nn > 0) k_node_update3<<<nblk(A.Nn, 256), 256, 0, s>>>(A);
-  if (A.Np > 0) k_node_update12<<<nblk(A.Np, 128), 128, 0, s>>>(A);
+  if (A.skipSpecial) {
+    if (A.Nn > 0) k_node_update3<true><<<nblk(A.Nn, 256), 256, 0, s>>>(A);
+    if (A.Np > 0) k_node_update12<true><<<nblk(A.Np, 128), 128, 0, s>>>(A);
+  } else {
+    if (A.Nn > 0) k_node_update3<false><<<nblk(A.Nn, 256), 256, 0, s>>>(A);
+    if (A.Np > 0) k_node_update12<false><<<nblk(A.Np, 128), 128, 0, s>>>(A);
+  }
+}
+void launch_node_update_special(const NodeArgs& A, const int* list, int n, cudaStream_t s) {
+  if (n > 0) k_node_update_special<<<nblk(n, 128), 128, 0, s>>>(A, list, n);
 }
 void launch_assemble_special(const NodeArgs& A, const int* list, int n, cudaStream_t s) {
   if (n > 0) k_assemble_special<<<nblk(n, 128), 128, 0, s>>>(A, list, n);
@@ -1481,7 +1554,8 @@ void launch_thermop(const FaultArgs& A, cudaStream_t s) {
   if (A.nPairs > 0) k_thermop<<<nblk(A.nPairs, 128), 128, 0, s>>>(A);
 }
 void launch_fault(const FaultArgs& A, cudaStream_t s) {
-  if (A.nPairs > 0) k_fault<<<nblk(A.nPairs, 128), 128, 0, s>>>(A);
+  // 178 registers per thread: 64-thread CTAs pack five to an SM where 128-thread ones pack two
+  if (A.nPairs > 0) k_fault<<<nblk(A.nPairs, 64), 64, 0, s>>>(A);
 }
 void launch_aos_to_soa(const double* src, int K, int n, const int* dstIdx, int cls, double* dst, int S, int k0, int nk,
                        cudaStream_t s) {

@@ -8,6 +8,7 @@ namespace eqd {
 void upload_qtab(const QTab* t16);
 void launch_advance(StepState* st, double dt, cudaStream_t s);
 void launch_node_update(const NodeArgs& A, cudaStream_t s);
+void launch_node_update_special(const NodeArgs& A, const int* list, int n, cudaStream_t s);
 void launch_assemble_special(const NodeArgs& A, const int* list, int n, cudaStream_t s);
 void launch_materialize_accel(const NodeArgs& A, double* out, cudaStream_t s);
 // sweep tiles [A.tile0, A.tile0 + A.ntiles) of the class's launch order

@@ -5,10 +5,12 @@
 #include "eqd_tiles.h"
 
 #include <algorithm>
+#include <mutex>
 #include <stdexcept>
 #include <thread>
 
 #include "eqd_dev.cuh"
+#include "eqd_par.h"
 
 namespace eqd {
 
@@ -39,7 +41,7 @@ struct Tile {
   std::vector<int> nodes;   // ascending unique node ids
 };
 
-void unique_nodes(const int* conn, const std::vector<int>& elems, const std::vector<int>& order, int b, int e,
+void unique_nodes(const int* conn, const std::vector<int>& elems, const raw_vector<int>& order, int b, int e,
                   std::vector<int>& out) {
   out.clear();
   out.reserve(8 * (size_t)(e - b));
@@ -51,7 +53,7 @@ void unique_nodes(const int* conn, const std::vector<int>& elems, const std::vec
   out.erase(std::unique(out.begin(), out.end()), out.end());
 }
 
-void split_group(const int* conn, const std::vector<int>& elems, const std::vector<int>& order, int b, int e,
+void split_group(const int* conn, const std::vector<int>& elems, const raw_vector<int>& order, int b, int e,
                  const TileShape& sh, std::vector<Tile>& out) {
   if (b >= e) return;
   Tile t;
@@ -91,11 +93,11 @@ void plan_tiles(const int* conn, const std::vector<int>& elems, int Nn, int ny, 
   if (n == 0) { P.S = 32; P.PFS = 4; P.LS = 1; P.refId.assign(P.S, -1); P.tileNode.assign(1, 0); P.tnode.assign(P.PFS, -1); P.lconn.assign(8 * (size_t)P.S, 0); return; }
   if (sh.capN > (int)EQD_LN_MASK) throw std::runtime_error("tile node cap exceeds the 12-bit local index");
   // ---- brick key per element
-  std::vector<int> key(n);
+  raw_vector<int> key(n);
   int nKeys = 1;
   if (gridOk) {
     const long nynz = (long)ny * nz;
-    std::vector<int> cx(n), cy(n), cz(n);
+    raw_vector<int> cx(n), cy(n), cz(n);
     parallel_for(n, [&](int b, int e) {
       for (int j = b; j < e; ++j) {
         const int* c = conn + 8 * (size_t)elems[j];
@@ -105,10 +107,18 @@ void plan_tiles(const int* conn, const std::vector<int>& elems, int Nn, int ny, 
       }
     });
     int mn[3] = {cx[0], cz[0], cy[0]}, mx[3] = {cx[0], cz[0], cy[0]};
-    for (int j = 0; j < n; ++j) {
-      mn[0] = std::min(mn[0], cx[j]); mx[0] = std::max(mx[0], cx[j]);
-      mn[1] = std::min(mn[1], cz[j]); mx[1] = std::max(mx[1], cz[j]);
-      mn[2] = std::min(mn[2], cy[j]); mx[2] = std::max(mx[2], cy[j]);
+    {
+      std::mutex mu;
+      parallel_for(n, [&](int b, int e) {
+        int lmn[3] = {cx[b], cz[b], cy[b]}, lmx[3] = {cx[b], cz[b], cy[b]};
+        for (int j = b; j < e; ++j) {
+          lmn[0] = std::min(lmn[0], cx[j]); lmx[0] = std::max(lmx[0], cx[j]);
+          lmn[1] = std::min(lmn[1], cz[j]); lmx[1] = std::max(lmx[1], cz[j]);
+          lmn[2] = std::min(lmn[2], cy[j]); lmx[2] = std::max(lmx[2], cy[j]);
+        }
+        std::lock_guard<std::mutex> g(mu);
+        for (int k = 0; k < 3; ++k) { mn[k] = std::min(mn[k], lmn[k]); mx[k] = std::max(mx[k], lmx[k]); }
+      });
     }
     int nb[3];
     const int bxe = balanced(mx[0] - mn[0] + 1, sh.bx, nb[0]);
@@ -130,7 +140,7 @@ void plan_tiles(const int* conn, const std::vector<int>& elems, int Nn, int ny, 
   std::vector<int> start(nKeys + 1, 0);
   for (int j = 0; j < n; ++j) start[key[j] + 1]++;
   for (int k = 0; k < nKeys; ++k) start[k + 1] += start[k];
-  std::vector<int> order(n);
+  raw_vector<int> order(n);
   {
     std::vector<int> fill(start.begin(), start.end() - 1);
     for (int j = 0; j < n; ++j) order[fill[key[j]]++] = j;
@@ -164,9 +174,10 @@ void plan_tiles(const int* conn, const std::vector<int>& elems, int Nn, int ny, 
   P.S = (int)std::max(slot, 32L);
   P.PFS = (int)std::max(nslot, 4L);
   P.LS = LS;
-  P.refId.assign(P.S, -1);
-  P.tnode.assign(P.PFS, -1);
-  P.lconn.assign(8 * (size_t)P.S, 0);
+  P.refId.resize(P.S); P.tnode.resize(P.PFS); P.lconn.resize(8 * (size_t)P.S);
+  parallel_range((size_t)P.S, [&](size_t b, size_t e) { std::fill(P.refId.begin() + b, P.refId.begin() + e, -1); });
+  parallel_range((size_t)P.PFS, [&](size_t b, size_t e) { std::fill(P.tnode.begin() + b, P.tnode.begin() + e, -1); });
+  parallel_range(8 * (size_t)P.S, [&](size_t b, size_t e) { std::fill(P.lconn.begin() + b, P.lconn.begin() + e, (uint16_t)0); });
   const size_t S = P.S;
   std::vector<int> bad(1, 0);
   parallel_for(nT, [&](int tb, int te) {

@@ -7,6 +7,8 @@
 #include <cstdint>
 #include <vector>
 
+#include "eqd_par.h"
+
 namespace eqd {
 
 struct TilePlan {
@@ -15,13 +17,13 @@ struct TilePlan {
   int nTiles = 0;
   int LS = 0;       // max nodes of a tile (shared-memory row stride)
   int PFS = 0;      // padded total of tile-node slots (row length of the partial buffer)
-  std::vector<int> refId;          // [S] slot -> reference element id (0-based), -1 = padding
+  raw_vector<int> refId;          // [S] slot -> reference element id (0-based), -1 = padding
   std::vector<int> tileElem;       // [nTiles] first slot (multiple of 32)
   std::vector<int> tileCnt;        // [nTiles] elements
   std::vector<int> tileNode;       // [nTiles+1] first tile-node slot (multiple of 4)
   std::vector<uint8_t> tileColours;  // [nTiles] colours per assembly phase (1 = conflict free)
-  std::vector<int> tnode;          // [PFS] node id per tile-node slot, ascending inside a tile, -1 = padding
-  std::vector<uint16_t> lconn;     // [8][S] tile-local node | colour << 12
+  raw_vector<int> tnode;          // [PFS] node id per tile-node slot, ascending inside a tile, -1 = padding
+  raw_vector<uint16_t> lconn;     // [8][S] tile-local node | colour << 12
 };
 
 struct TileShape {
