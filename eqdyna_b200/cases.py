@@ -35,5 +35,11 @@ def materialize(name, scratch=None):
                     shutil.copyfileobj(a, b)
                 os.replace(tmp, dst)
         else:
-            shutil.copy(os.path.join(d, f), os.path.join(out, f))
+            # several ranks may materialise the same case at once: only ever publish whole files
+            src, dst = os.path.join(d, f), os.path.join(out, f)
+            if os.path.exists(dst) and os.path.getsize(dst) == os.path.getsize(src):
+                continue
+            tmp = dst + ".tmp%d" % os.getpid()
+            shutil.copy(src, tmp)
+            os.replace(tmp, dst)
     return out

@@ -524,6 +524,7 @@ void finalize(eqd_handle* h) {
   // cudaMemset / cudaMemcpy above ran on the legacy stream, which does not order
   // against the non-blocking step stream
   CK(cudaDeviceSynchronize());
+  if (t_stage == h->stage.get()) { t_stage = nullptr; t_stageStream = nullptr; }  // finalize may run inside a guarded call
   h->stage.reset();
   h->finalized = true;
 }
