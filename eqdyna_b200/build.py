@@ -21,7 +21,9 @@ LIBDIR = os.path.join(PKG, "lib")
 ORACLE = os.path.join(ROOT, "oracle")
 
 HOST_SRCS = ["eqh_io.cpp", "eqh_mesh.cpp", "eqh_mass.cpp", "eqh_api.cpp"]
-CUDA_SRCS = ["eqd_api.cu", "eqd_kernels.cu", "eqd_tiles.cu"]
+CUDA_SRCS = ["eqd_api.cu", "eqd_kernels.cu", "eqd_tiles.cu", "eqd_ops.cu"]
+# the operator precompute must round like the reference build (no FMA contraction)
+CUDA_FILE_FLAGS = {"eqd_ops.cu": ["--fmad=false"]}
 
 # the reference's ubuntu build is -O3 without -march / fast-math: no FMA contraction
 HOST_FLAGS = ["-O2", "-ffp-contract=off", "-fPIC", "-std=c++17", "-Wall", "-Wno-unused-variable"]
@@ -105,12 +107,26 @@ def build_cuda(force=False, extra=()):
     os.makedirs(LIBDIR, exist_ok=True)
     srcs = [os.path.join(CSRC, "cuda", s) for s in CUDA_SRCS]
     out = cuda_lib_path()
-    if force or _newer(out, srcs + _headers()):
-        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-        inc, libs = nccl_flags()
-        cmd = [nvcc, "-O3", "-std=c++17", "-lineinfo"] + NVCC_ARCH + [
-            "-Xcompiler", "-fPIC", "-shared", "-I", INC] + inc + list(extra) + ["-o", out] + srcs + libs
-        _run(cmd)
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    inc, libs = nccl_flags()
+    objdir = os.path.join(LIBDIR, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    hdrs = _headers()
+    objs, jobs = [], []
+    for src in srcs:
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or _newer(obj, [src] + hdrs):
+            cmd = [nvcc, "-O3", "-std=c++17", "-lineinfo"] + NVCC_ARCH + ["-Xcompiler", "-fPIC", "-I", INC] + inc + [
+                f for f in libs if f.startswith("-D")] + CUDA_FILE_FLAGS.get(os.path.basename(src), []) + list(extra) + ["-c", src, "-o", obj]
+            jobs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+            jobs[-1].cmdline = cmd
+    for j in jobs:   # the translation units compile side by side
+        o, _ = j.communicate()
+        if j.returncode != 0:
+            raise RuntimeError("build failed: %s\n%s" % (" ".join(j.cmdline), o))
+    if force or jobs or _newer(out, objs):
+        _run([nvcc, "-shared"] + NVCC_ARCH + ["-o", out] + objs + [f for f in libs if not f.startswith("-D")])
     return out
 
 

@@ -174,6 +174,7 @@ struct eqd_handle {
   std::vector<int> info;       // per node
   std::vector<int> elemCode;   // per element: class | slot<<2
   std::vector<double> fnmsH, massH;
+  bool massFromDevice = false;  // eqd_compute_elem_ops filled massH / fnmsH / dMass
   int NnS = 0, Np = 0, NpS = 0;
   bool body = false, plastic = false, qmode = false;
   // ---- device
@@ -1021,6 +1022,129 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
   });
 }
 
+}  // extern "C"
+
+namespace {
+// porep / pstrain / stresses of eqd_set_elem_ops and eqd_compute_elem_ops
+void upload_elem_state(eqd_handle* h, DevBuf<int>& dCode, const double* eleporep, const double* stressArr, const double* pstrain) {
+  const int Ne = h->Ne;
+  DevBuf<double> tmp;
+  auto spread = [&](const double* src, int K, auto member, int k0, int nk, int rowOff) {
+    tmp.alloc((size_t)K * Ne, false);
+    h2d(tmp.p, src, sizeof(double) * (size_t)K * Ne);
+    for (int c = 0; c < 3; ++c) {
+      ElemClass& C = h->cls[c];
+      DevBuf<double>& dst = C.*member;
+      if (!C.n || !dst.p) continue;
+      launch_aos_to_soa(tmp.p, K, Ne, dCode.p, c, dst.p + (size_t)rowOff * C.S, C.S, k0, nk, h->stream);
+    }
+    CK(cudaStreamSynchronize(h->stream));
+  };
+  if (h->plastic) {
+    spread(eleporep, 1, &ElemClass::porep, 0, 1, 0);
+    spread(pstrain, 1, &ElemClass::pstrain, 0, 1, 0);
+  }
+  tmp.release();
+  // stresses: stressArr(stressCompIndexArr(e) + k)
+  for (int c = 0; c < 3; ++c) {
+    ElemClass& C = h->cls[c];
+    if (!C.n) continue;
+    std::vector<double> sg((size_t)C.nstress * C.S, 0.0), qm;
+    if (h->qmode && c != CLS_PML) qm.assign(6 * (size_t)C.S, 0.0);
+    std::vector<char> badv(1, 0);
+    parallel_range((size_t)C.S, [&](size_t sb, size_t se) {
+      for (size_t s = sb; s < se; ++s) {
+        if (C.refId[s] < 0) continue;
+        const int base = h->stressIdx[C.refId[s]];
+        if (!(base >= 0 && base + (c == CLS_PML ? 21 : 12) <= h->sizeStress)) { badv[0] = 1; continue; }
+        for (int k = 0; k < C.nstress; ++k) sg[(size_t)k * C.S + s] = stressArr[base + k];
+        if (!qm.empty()) for (int k = 0; k < 6; ++k) qm[(size_t)k * C.S + s] = stressArr[base + 6 + k];
+      }
+    });
+    need(!badv[0], "eqd_set_elem_ops: stress index out of range");
+    C.stress.upload(sg);
+    if (!qm.empty()) C.qmem.upload(qm);
+  }
+}
+void alloc_elem_ops(eqd_handle* h) {
+  for (int c = 0; c < 3; ++c) {
+    ElemClass& C = h->cls[c];
+    if (!C.n) continue;
+    C.shp.alloc(24 * (size_t)C.S); C.phi.alloc(32 * (size_t)C.S); C.ss.alloc(6 * (size_t)C.S);
+    C.lam.alloc(C.S); C.mu.alloc(C.S); C.det.alloc(C.S);
+    if (h->p.C_hg == 2) { C.rho.alloc(C.S); C.vp.alloc(C.S); }
+    if (h->body) C.emass.alloc(8 * (size_t)C.S);
+    if (h->plastic && c != CLS_PML) { C.porep.alloc(C.S); C.pstrain.alloc(C.S); }
+  }
+}
+}  // namespace
+
+extern "C" {
+
+// Operators computed on the device from the mesh of eqd_set_mesh (eqd_ops.cu); see the header.
+int eqd_compute_elem_ops(eqd_handle* h, const double* mat, const double* eleporep, const double* stressArr,
+                         const double* pstrain) {
+  if (!h) return EQD_ERR_ARG;
+  return guarded(h, [&] {
+    need(h->meshSet, "eqd_compute_elem_ops: call eqd_set_mesh first");
+    need(mat && stressArr, "eqd_compute_elem_ops: null argument");
+    need(!h->plastic || (eleporep && pstrain), "eqd_compute_elem_ops: eleporep/pstrain required for C_elastic==0");
+    const int Ne = h->Ne, Nn = h->Nn;
+    Lap lap("eqd_compute_elem_ops");
+    alloc_elem_ops(h);
+    DevBuf<int> dConn, dEtype, dBad;
+    DevBuf<double> dCoor, dMat;
+    dConn.upload(h->conn); dEtype.upload(h->etype); dCoor.upload(h->coor);
+    dMat.alloc(5 * (size_t)Ne, false);
+    h2d(dMat.p, mat, sizeof(double) * 5 * (size_t)Ne);
+    std::vector<int> big(1, 0x7fffffff);
+    dBad.upload(big);
+    lap.lap("mesh upload");
+    DevBuf<double> emTmp[3], pm[3];
+    for (int c = 0; c < 3; ++c) {
+      ElemClass& C = h->cls[c];
+      if (!C.n) continue;
+      DevBuf<int> dRef; dRef.upload(C.refId);
+      if (!h->body) emTmp[c].alloc(8 * (size_t)C.S);
+      OpsArgs A{};
+      A.S = C.S; A.Ne = Ne; A.refId = dRef.p; A.conn = dConn.p; A.etype = dEtype.p; A.coor = dCoor.p; A.mat = dMat.p;
+      A.w = h->p.w;
+      A.shp = C.shp.p; A.phi = C.phi.p; A.ss = C.ss.p; A.det = C.det.p; A.lam = C.lam.p; A.mu = C.mu.p;
+      A.rho = C.rho.p; A.vp = C.vp.p;
+      A.em = h->body ? C.emass.p : emTmp[c].p;
+      A.badElem = dBad.p;
+      launch_elem_ops(A, h->stream);
+      // lumped mass partial per tile node, fixed order
+      pm[c].alloc(C.PFS);
+      TileMassArgs T{};
+      T.tileRec = C.tileRec.p; T.em = A.em; T.lconn = C.lconn.p; T.S = C.S; T.capE = 384; T.pm = pm[c].p;
+      launch_tile_mass(T, C.nTiles, h->stream);
+      CK(cudaStreamSynchronize(h->stream));
+    }
+    CK(cudaGetLastError());
+    const int bad = dBad.download()[0];
+    if (bad != 0x7fffffff) throw ArgError("Non-positive determinant; element " + std::to_string(bad + 1) + " (calcGlobalShapeFunc.f90:57-61)");
+    NodeMassArgs M{};
+    M.Nn = Nn; M.NnS = h->NnS; M.slotCnt = h->dSlotCnt.p; M.slotTab = h->dSlotTab.p;
+    for (int c = 0; c < 3; ++c) M.pm[c] = pm[c].p;
+    M.mass = h->dMass.p;
+    launch_node_mass(M, h->stream);
+    CK(cudaStreamSynchronize(h->stream));
+    h->massH = h->dMass.download();
+    h->fnmsH = h->massH;                       // fnms adds the same element masses (assembleGlobalMass.f90:322)
+    parallel_range((size_t)Nn, [&](size_t b, size_t e) {
+      for (size_t n = b; n < e; ++n) if (EQD_INFO_KIND(h->info[n]) == KIND_FIXED) h->massH[n] = 1.0;
+    });
+    h->dMass.upload(h->massH);
+    h->massFromDevice = true;
+    lap.lap("operators + mass");
+    DevBuf<int> dCode; dCode.upload(h->elemCode);
+    upload_elem_state(h, dCode, eleporep, stressArr, pstrain);
+    lap.lap("stresses");
+    h->opsSet = true;
+  });
+}
+
 int eqd_set_elem_ops(eqd_handle* h, const double* eleshp, const double* eledet, const double* elemass, const double* mat,
                      const double* ss, const double* phi, const double* eleporep, const double* stressArr,
                      const double* pstrain) {
@@ -1034,15 +1158,7 @@ int eqd_set_elem_ops(eqd_handle* h, const double* eleshp, const double* eledet, 
     Lap lap("eqd_set_elem_ops");
     DevBuf<int> dCode; dCode.upload(h->elemCode);
     DevBuf<double> tmp;
-    for (int c = 0; c < 3; ++c) {
-      ElemClass& C = h->cls[c];
-      if (!C.n) continue;
-      C.shp.alloc(24 * (size_t)C.S); C.phi.alloc(32 * (size_t)C.S); C.ss.alloc(6 * (size_t)C.S);
-      C.lam.alloc(C.S); C.mu.alloc(C.S); C.det.alloc(C.S);
-      if (h->p.C_hg == 2) { C.rho.alloc(C.S); C.vp.alloc(C.S); }
-      if (h->body) C.emass.alloc(8 * (size_t)C.S);
-      if (h->plastic && c != CLS_PML) { C.porep.alloc(C.S); C.pstrain.alloc(C.S); }
-    }
+    alloc_elem_ops(h);
     auto spread = [&](const double* src, int K, auto member, int k0, int nk, int rowOff) {
       tmp.alloc((size_t)K * Ne, false);
       h2d(tmp.p, src, sizeof(double) * (size_t)K * Ne);
@@ -1074,32 +1190,9 @@ int eqd_set_elem_ops(eqd_handle* h, const double* eleshp, const double* eledet, 
       }
       CK(cudaStreamSynchronize(h->stream));
     }
-    if (h->plastic) {
-      spread(eleporep, 1, &ElemClass::porep, 0, 1, 0);
-      spread(pstrain, 1, &ElemClass::pstrain, 0, 1, 0);
-    }
     tmp.release();
     lap.lap("operator rows");
-    // stresses: stressArr(stressCompIndexArr(e) + k)
-    for (int c = 0; c < 3; ++c) {
-      ElemClass& C = h->cls[c];
-      if (!C.n) continue;
-      std::vector<double> sg((size_t)C.nstress * C.S, 0.0), qm;
-      if (h->qmode && c != CLS_PML) qm.assign(6 * (size_t)C.S, 0.0);
-      std::vector<char> badv(1, 0);
-      parallel_range((size_t)C.S, [&](size_t sb, size_t se) {
-        for (size_t s = sb; s < se; ++s) {
-          if (C.refId[s] < 0) continue;
-          const int base = h->stressIdx[C.refId[s]];
-          if (!(base >= 0 && base + (c == CLS_PML ? 21 : 12) <= h->sizeStress)) { badv[0] = 1; continue; }
-          for (int k = 0; k < C.nstress; ++k) sg[(size_t)k * C.S + s] = stressArr[base + k];
-          if (!qm.empty()) for (int k = 0; k < 6; ++k) qm[(size_t)k * C.S + s] = stressArr[base + 6 + k];
-        }
-      });
-      need(!badv[0], "eqd_set_elem_ops: stress index out of range");
-      C.stress.upload(sg);
-      if (!qm.empty()) C.qmem.upload(qm);
-    }
+    upload_elem_state(h, dCode, eleporep, stressArr, pstrain);
     lap.lap("stresses");
     h->opsSet = true;
   });
@@ -1110,12 +1203,18 @@ int eqd_set_nodal(eqd_handle* h, const double* nodalMassArr, const double* fnms,
   if (!h) return EQD_ERR_ARG;
   return guarded(h, [&] {
     need(h->meshSet, "eqd_set_nodal: call eqd_set_mesh first");
-    need(nodalMassArr && fnms && v1 && velArr && dispArr, "eqd_set_nodal: null argument");
+    need(v1 && velArr && dispArr, "eqd_set_nodal: null argument");
+    // NULL mass arrays = keep the lumped mass eqd_compute_elem_ops assembled on the device
+    const bool devMass = !nodalMassArr && !fnms && h->massFromDevice;
+    need(devMass || (nodalMassArr && fnms), "eqd_set_nodal: nodalMassArr / fnms missing (and no eqd_compute_elem_ops before)");
     const int Nn = h->Nn;
     const size_t NS = h->NnS, PS = h->NpS;
     Lap lap("eqd_set_nodal");
-    h->fnmsH.assign(fnms, fnms + Nn);
-    h->massH.assign(Nn, 1.0);
+    if (!devMass) {
+      h->fnmsH.assign(fnms, fnms + Nn);
+      h->massH.assign(Nn, 1.0);
+      h->massFromDevice = false;
+    }
     std::vector<double> vel(3 * NS, 0.0), disp(3 * NS, 0.0), v1p(12 * PS, 0.0), acc;
     bool anyAcc = false;
     if (nodalForceArr) {
@@ -1132,10 +1231,12 @@ int eqd_set_nodal(eqd_handle* h, const double* nodalMassArr, const double* fnms,
         const int kind = EQD_INFO_KIND(h->info[n]);
         if (kind == KIND_FIXED) continue;
         const int st = h->eqStart[n], nd = h->ndof[n];
-        const double m = nodalMassArr[h->eqIdx[st] - 1];
-        for (int j = 1; j < nd; ++j)
-          if (nodalMassArr[h->eqIdx[st + j] - 1] != m) badv[0] = 1;
-        h->massH[n] = m;
+        if (!devMass) {
+          const double m = nodalMassArr[h->eqIdx[st] - 1];
+          for (int j = 1; j < nd; ++j)
+            if (nodalMassArr[h->eqIdx[st + j] - 1] != m) badv[0] = 1;
+          h->massH[n] = m;
+        }
         for (int j = 0; j < 3; ++j) disp[j * NS + n] = dispArr[j + 3 * n];
         if (kind == KIND_FREE3) {
           // v1 and velArr are the same quantity for a 3-dof node after the first update (driver.f90:102-103)
@@ -1443,6 +1544,24 @@ int eqd_fetch(eqd_handle* h, int32_t which, void* dst, int64_t dst_bytes) {
           if (which == EQD_F_MASS) { for (int j = 0; j < h->ndof[n]; ++j) out[h->eqIdx[st + j] - 1] = h->massH[n]; continue; }
           if (kind == KIND_FREE3) for (int j = 0; j < 3; ++j) out[h->eqIdx[st + j] - 1] = a3[j * NS + n];
           else { const size_t slot = EQD_INFO_SLOT(h->info[n]); for (int j = 0; j < 12; ++j) out[h->eqIdx[st + j] - 1] = a12[j * PSn + slot]; }
+        }
+        break;
+      }
+      case EQD_F_ELEDET: case EQD_F_ELESHP: case EQD_F_SS: case EQD_F_PHI: {
+        need(h->opsSet, "eqd_fetch: no element operators yet");
+        const int K = which == EQD_F_ELEDET ? 1 : which == EQD_F_ELESHP ? 24 : which == EQD_F_SS ? 6 : 32;
+        want((size_t)K * h->Ne);
+        for (int c = 0; c < 3; ++c) {
+          ElemClass& C = h->cls[c];
+          if (!C.n) continue;
+          const DevBuf<double>& src = which == EQD_F_ELEDET ? C.det : which == EQD_F_ELESHP ? C.shp : which == EQD_F_SS ? C.ss : C.phi;
+          std::vector<double> v = src.download();
+          parallel_range((size_t)C.S, [&](size_t sb, size_t se) {
+            for (size_t s = sb; s < se; ++s) {
+              if (C.refId[s] < 0) continue;
+              for (int k = 0; k < K; ++k) out[k + (size_t)K * C.refId[s]] = v[(size_t)k * C.S + s];
+            }
+          });
         }
         break;
       }

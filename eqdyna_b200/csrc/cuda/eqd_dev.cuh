@@ -121,6 +121,31 @@ struct FaultArgs {
   int friclaw, C_nuclea, nucfault, TPV, insertFaultType, C_elastic;
 };
 
+// operator precompute on the device (eqd_ops.cu)
+struct OpsArgs {
+  int S, Ne;
+  const int* refId;      // [S] class slot -> reference element (0-based), -1 = padding
+  const int* conn;       // (8,Ne) 0-based
+  const int* etype;      // [Ne]
+  const double* coor;    // (3,Nn)
+  const double* mat;     // (Ne,5), element index fastest
+  double w;
+  double* shp; double* phi; double* ss; double* det; double* lam; double* mu;
+  double* rho; double* vp;   // optional (C_hg == 2)
+  double* em;            // [8][S] lumped element mass per local node
+  int* badElem;          // smallest element id with a non-positive determinant
+};
+struct TileMassArgs {
+  const int4* tileRec; const double* em; const uint16_t* lconn; int S, capE;
+  double* pm;            // [PFS] lumped-mass partial per tile-node slot
+};
+struct NodeMassArgs {
+  int Nn, NnS;
+  const uint8_t* slotCnt; const uint32_t* slotTab;
+  const double* pm[3];
+  double* mass;
+};
+
 // Q constants per class (qconstant.f90), filled by the host at create time
 struct QTab { double taok, wkp, wks, cv, cs, expdt; };
 

@@ -1202,7 +1202,7 @@ __device__ __forceinline__ void d_rsf_slip(double V2, double& psi, const RsfPar&
 }
 
 // faulting.f90:3-541, one thread per split-node pair
-__global__ void __launch_bounds__(128) k_fault(FaultArgs A) {
+__global__ void __launch_bounds__(64, 8) k_fault(FaultArgs A) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= A.nPairs) return;
   const size_t PS = A.PS, NS = A.NnS;

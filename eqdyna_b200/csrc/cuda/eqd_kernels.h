@@ -25,4 +25,8 @@ void launch_thermop(const FaultArgs& A, cudaStream_t s);
 void launch_fault(const FaultArgs& A, cudaStream_t s);
 void launch_aos_to_soa(const double* src, int K, int n, const int* dstIdx, int cls, double* dst, int S, int k0, int nk,
                        cudaStream_t s);
+// eqd_ops.cu
+void launch_elem_ops(const OpsArgs& A, cudaStream_t s);
+void launch_tile_mass(const TileMassArgs& A, int ntiles, cudaStream_t s);
+void launch_node_mass(const NodeMassArgs& A, cudaStream_t s);
 }  // namespace eqd

@@ -131,6 +131,11 @@ module eqdyna_cuda_iface
             character(kind=c_char) :: key(*)
             integer(c_int32_t), value :: val
         end function
+        integer(c_int) function eqd_compute_elem_ops(handle, mat, eleporep, stressArr, pstrain) &
+                bind(C, name='eqd_compute_elem_ops')
+            import :: c_int, c_ptr
+            type(c_ptr), value :: handle, mat, eleporep, stressArr, pstrain
+        end function
         integer(c_int) function eqd_plan_check(Nn, Ne, nodeElemIdRelation, elemTypeArr, numOfDofPerNodeArr, stats) &
                 bind(C, name='eqd_plan_check')
             import :: c_int, c_int32_t, c_int64_t

@@ -16,10 +16,11 @@ from .host import EqdParams
 
 F_DISP, F_VEL, F_V1, F_FORCE, F_FRIC, F_FNFT, F_PSTRAIN, F_STRESS = 1, 2, 3, 4, 5, 6, 7, 8
 F_ONFAULT_HIST, F_OFFFAULT_HIST, F_HYPO_LOG, F_GM, F_SRC_EVOL, F_TPHIST, F_MASS, F_FNMS, F_ARN = 9, 10, 11, 12, 13, 14, 15, 16, 17
+F_ELEDET, F_ELESHP, F_SS, F_PHI = 18, 19, 20, 21
 T_TOTAL, T_NODE, T_ELEM, T_ASSEMBLE, T_HALO, T_FAULT, T_ELEM_PML, T_ELEM_REGX, T_NSLOTS = 0, 1, 2, 3, 4, 5, 6, 7, 8
 
 EXPORTS = [
-    "eqd_create", "eqd_destroy", "eqd_last_error", "eqd_set_mesh", "eqd_set_elem_ops", "eqd_set_nodal",
+    "eqd_create", "eqd_destroy", "eqd_last_error", "eqd_set_mesh", "eqd_set_elem_ops", "eqd_compute_elem_ops", "eqd_set_nodal",
     "eqd_set_fault", "eqd_set_halo", "eqd_set_stations", "eqd_get_unique_id", "eqd_set_comm", "eqd_sum_shared",
     "eqd_run", "eqd_run_group", "eqd_fetch", "eqd_get_counts", "eqd_get_timing", "eqd_set_option", "eqd_plan_check",
 ]
@@ -48,6 +49,7 @@ def lib():
         L.eqd_last_error.argtypes = [vp, cp, C.c_int]
         L.eqd_set_mesh.argtypes = [vp, i32, i32, i32, i32] + [vp] * 7 + [i32]
         L.eqd_set_elem_ops.argtypes = [vp] + [vp] * 9
+        L.eqd_compute_elem_ops.argtypes = [vp] + [vp] * 4
         L.eqd_set_nodal.argtypes = [vp] + [vp] * 6
         L.eqd_set_fault.argtypes = [vp, i32] + [vp] * 8
         L.eqd_set_halo.argtypes = [vp] + [vp] * 9
@@ -96,8 +98,11 @@ def plan_check(view):
 class Domain:
     """One sub-domain of a case on one GPU."""
 
-    def __init__(self, view, device=0):
+    def __init__(self, view, device=0, compute_ops=False):
+        """compute_ops: let the device compute the element operators and the lumped mass from the
+        mesh (eqd_compute_elem_ops) instead of uploading the host's (eqd_set_elem_ops)."""
         self.view = view
+        self.compute_ops = compute_ops
         self._h = C.c_void_p()
         p = EqdParams.from_buffer_copy(view.params)
         rc = lib().eqd_create(C.byref(p), int(device), C.byref(self._h))
@@ -118,10 +123,14 @@ class Domain:
         self._check(L.eqd_set_mesh(self._h, r.Nn, r.Ne, r.Neq, r.sizeEq, _ptr(v.meshCoor), _ptr(v.nodeElemIdRelation),
                                    _ptr(v.elemTypeArr), _ptr(v.numOfDofPerNodeArr), _ptr(v.eqNumStartIndexLoc),
                                    _ptr(v.eqNumIndexArr), _ptr(v.stressCompIndexArr), r.sizeStress))
-        self._check(L.eqd_set_elem_ops(self._h, _ptr(v.eleshp), _ptr(v.eledet), _ptr(v.elemass), _ptr(v.mat), _ptr(v.ss),
-                                       _ptr(v.phi), _ptr(v.eleporep), _ptr(v.stressArr), _ptr(v.pstrain)))
-        self._check(L.eqd_set_nodal(self._h, _ptr(v.nodalMassArr), _ptr(v.fnms), _ptr(v.v1), _ptr(v.velArr),
-                                    _ptr(v.dispArr), _ptr(v.nodalForceArr)))
+        if self.compute_ops:
+            self._check(L.eqd_compute_elem_ops(self._h, _ptr(v.mat), _ptr(v.eleporep), _ptr(v.stressArr), _ptr(v.pstrain)))
+            self._check(L.eqd_set_nodal(self._h, None, None, _ptr(v.v1), _ptr(v.velArr), _ptr(v.dispArr), _ptr(v.nodalForceArr)))
+        else:
+            self._check(L.eqd_set_elem_ops(self._h, _ptr(v.eleshp), _ptr(v.eledet), _ptr(v.elemass), _ptr(v.mat), _ptr(v.ss),
+                                           _ptr(v.phi), _ptr(v.eleporep), _ptr(v.stressArr), _ptr(v.pstrain)))
+            self._check(L.eqd_set_nodal(self._h, _ptr(v.nodalMassArr), _ptr(v.fnms), _ptr(v.v1), _ptr(v.velArr),
+                                        _ptr(v.dispArr), _ptr(v.nodalForceArr)))
         if int(np.sum(v.nftnd)) > 0:
             self._check(L.eqd_set_fault(self._h, r.nftmx, _ptr(v.nftnd), _ptr(v.nsmp), _ptr(v.un), _ptr(v.us), _ptr(v.ud),
                                         _ptr(v.arn), _ptr(v.fric), _ptr(v.fnft)))

@@ -84,7 +84,11 @@ enum {
   EQD_F_TPHIST = 14,     /* onFaultTPHist(2,nftmx,nstep,ntotft), friclaw 5   */
   EQD_F_MASS = 15,       /* nodalMassArr(Neq) (after eqd_sum_shared)         */
   EQD_F_FNMS = 16,       /* fnms(Nn)                                         */
-  EQD_F_ARN = 17         /* arn(nftmx,ntotft)                                */
+  EQD_F_ARN = 17,        /* arn(nftmx,ntotft)                                */
+  EQD_F_ELEDET = 18,     /* eledet(Ne)       | element operators as the device  */
+  EQD_F_ELESHP = 19,     /* eleshp(3,8,Ne)   | holds them (uploaded by          */
+  EQD_F_SS = 20,         /* ss(6,Ne)         | eqd_set_elem_ops or computed by  */
+  EQD_F_PHI = 21         /* phi(8,4,Ne)      | eqd_compute_elem_ops)            */
 };
 
 /* timing slots of eqd_get_timing (ms, CUDA events) -- the reference's
@@ -112,6 +116,18 @@ int eqd_set_elem_ops(eqd_handle* h, const double* eleshp, const double* eledet,
                      const double* elemass, const double* mat, const double* ss,
                      const double* phi, const double* eleporep,
                      const double* stressArr, const double* pstrain);
+/* Alternative to eqd_set_elem_ops: compute eleshp, eledet, elemass, ss, phi and the
+ * lumped nodal mass ON THE DEVICE from the mesh given to eqd_set_mesh, i.e. the
+ * work of assembleGlobalMass (assembleGlobalMass.f90:3-56,283-406),
+ * calcGlobalShapeFunc.f90:19-75 and vlm (library.f90:60-93); the host then neither
+ * computes nor uploads the ~600 B of operators per element.  Per-element values are
+ * bit-identical to the Fortran ones (no FMA contraction, same operation order); the
+ * nodal mass is summed in tile order (last-bit differences).  Follow with
+ * eqd_set_nodal(h, NULL, NULL, v1, velArr, dispArr, ...) to keep that mass, and
+ * with eqd_sum_shared when sub-domains share nodes.  Error 4 with the element
+ * number on a non-positive determinant (calcGlobalShapeFunc.f90:57-61).          */
+int eqd_compute_elem_ops(eqd_handle* h, const double* mat, const double* eleporep,
+                         const double* stressArr, const double* pstrain);
 /* nodal state: nodalMassArr(Neq) fnms(Nn) v1(Neq) velArr(3,Nn) dispArr(3,Nn)
  * nodalForceArr(Neq) (acceleration left by a previous run; may be NULL = 0) */
 int eqd_set_nodal(eqd_handle* h, const double* nodalMassArr, const double* fnms,

@@ -73,12 +73,12 @@ def run_oracle(world, nstep=None, threads=None):
     return world
 
 
-def run_gpu(world, nstep=None, device=0, chunks=1, options=None):
+def run_gpu(world, nstep=None, device=0, chunks=1, options=None, compute_ops=False):
     """Step every sub-domain of `world` on the GPU and copy the results back into
     the world's host arrays.  Returns the Domain list (caller may read timing)."""
     from eqdyna_b200 import device as dev
     n = world.view(0).nstep if nstep is None else nstep
-    doms = [dev.Domain(world.view(r), device=device) for r in range(world.size)]
+    doms = [dev.Domain(world.view(r), device=device, compute_ops=compute_ops) for r in range(world.size)]
     for d in doms:
         for k, v in (options or {}).items():
             d.set_option(k, v)

@@ -34,6 +34,7 @@ CASES = [
     ("test.meng2023a", (2, 2, 1), 0, "time-weakening (friclaw 2)"),
     ("test.tpv36", (2, 2, 2), 250, "15-degree thrust: degenerate wedges (types 11,12,13), forced nucleation"),
     ("test.tpv37", (1, 1, 1), 40, "wedges, single sub-domain"),
+    ("test.tpv104", (4, 1, 2), 60, "the benchmark's 8-GPU decomposition: sub-domains with neighbours on both x sides"),
 ]
 
 
