@@ -220,7 +220,8 @@ struct eqd_handle {
   double hostTime = 0.0;
   long launches = 0;
   bool timing = false;
-  int optGraph = 0, optBlock = 0;
+  int optGraph = 0, optBlock = 0, optNodeVariant = 4;
+  int optTile[2][3] = {{kRegBrick[0], kRegBrick[1], kRegBrick[2]}, {kPmlBrick[0], kPmlBrick[1], kPmlBrick[2]}};  // brick of a regular / PML tile in elements along x, z, y (before eqd_set_mesh)
   double tms[EQD_T_NSLOTS] = {0};
   std::vector<cudaEvent_t> evs;  // timing events
 
@@ -334,7 +335,7 @@ NodeArgs eqd_handle::nodeArgs() const {
   A.pfR = cls[CLS_REG].pf.p; A.SR = cls[CLS_REG].PFS;
   A.pfX = cls[CLS_REGX].pf.p; A.SX = cls[CLS_REGX].PFS;
   A.pfP = cls[CLS_PML].pf.p; A.SP = cls[CLS_PML].PFS;
-  A.accel0 = nullptr; A.skipSpecial = 0;
+  A.accel0 = nullptr; A.skipSpecial = 0; A.variant = optNodeVariant;
   A.dt = p.dt;
   A.st = dState.p;
   return A;
@@ -891,8 +892,10 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
     for (int c = 0; c < 3; ++c) {
       ElemClass& C = h->cls[c];
       TileShape sh;
-      if (c == CLS_PML) { sh.bx = 3; sh.bz = 3; sh.by = 24; sh.capE = 320; sh.capN = EQD_PML_LS; }
-      else { sh.bx = 4; sh.bz = 4; sh.by = 16; sh.capE = 384; sh.capN = EQD_REG_LS; }  // two CTAs per SM
+      const int* ts = h->optTile[c == CLS_PML ? 1 : 0];
+      sh.bx = ts[0]; sh.bz = ts[1]; sh.by = ts[2];
+      if (c == CLS_PML) { sh.capE = 320; sh.capN = EQD_PML_LS; }
+      else { sh.capE = 384; sh.capN = EQD_REG_LS; }  // two CTAs per SM
       TilePlan T;
       plan_tiles(h->conn.data(), members[c], Nn, gny, gnz, gridOk, sh, c == CLS_PML ? EQD_STAGE_PML : EQD_STAGE, T);
       C.n = T.n; C.S = T.S; C.nf = nf[c]; C.nstress = nstr[c];
@@ -1649,6 +1652,16 @@ int eqd_set_option(eqd_handle* h, const char* key, int32_t value) {
   if (!strcmp(key, "graph")) { h->optGraph = value; return EQD_OK; }
   if (!strcmp(key, "block")) { h->optBlock = value; return EQD_OK; }
   if (!strcmp(key, "overlap")) { h->optOverlap = value; return EQD_OK; }
+  {
+    const char* names[6] = {"reg_bx", "reg_bz", "reg_by", "pml_bx", "pml_bz", "pml_by"};
+    for (int k = 0; k < 6; ++k)
+      if (!strcmp(key, names[k])) {
+        if (value < 1 || value > 64 || h->meshSet) return EQD_ERR_ARG;
+        h->optTile[k / 3][k % 3] = value;
+        return EQD_OK;
+      }
+  }
+  if (!strcmp(key, "node_variant")) { h->optNodeVariant = value; return EQD_OK; }
   if (!strcmp(key, "reserve")) { h->optReserve = value; return EQD_OK; }
   h->err = std::string("eqd_set_option: unknown key ") + key;
   return EQD_ERR_ARG;

@@ -69,6 +69,7 @@ struct NodeArgs {
   const double* pfX; int SX;   // [6][SX]  REGX: KU | hourglass
   const double* pfP; int SP;   // [12][SP] PML
   const double* accel0;  // optional uploaded acceleration, same layout as force; first step only
+  int variant;           // launch-bounds variant of k_node_update3 (tuning)
   int skipSpecial;       // 1: k_node_update3/12 leave the special nodes to k_node_update_special
   double dt;
   StepState* st;

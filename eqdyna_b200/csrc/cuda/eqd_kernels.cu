@@ -106,8 +106,8 @@ __device__ __forceinline__ void gather12(const NodeArgs& A, int n, int cnt, doub
 // previous step's `nodalForceArr/nodalMassArr` (driver.f90:29).  Two kernels so
 // that the 3-dof one (almost every node) stays light enough for full occupancy:
 // its gather is a chain of dependent loads that only parallelism hides.
-template <bool SKIP>
-__global__ void __launch_bounds__(256, 4) k_node_update3(NodeArgs A) {
+template <bool SKIP, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_node_update3(NodeArgs A) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= A.Nn) return;
   const size_t NS = A.NnS;
@@ -154,8 +154,8 @@ __global__ void __launch_bounds__(256, 4) k_node_update3(NodeArgs A) {
 }
 
 // 12-dof PML nodes: split-field velocities with damping (driver.f90:105-141), one thread per PML slot
-template <bool SKIP>
-__global__ void __launch_bounds__(128) k_node_update12(NodeArgs A) {
+template <bool SKIP, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_node_update12(NodeArgs A) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot >= A.Np) return;
   const size_t NS = A.NnS, PS = A.NpS;
@@ -1450,13 +1450,33 @@ static inline int nblk(long n, int b) { return (int)((n + b - 1) / b); }
 
 void launch_advance(StepState* st, double dt, cudaStream_t s) { k_advance<<<1, 1, 0, s>>>(st, dt); }
 
+template <bool SKIP>
+static void launch_node3(const NodeArgs& A, cudaStream_t s) {
+  // occupancy variants of the same kernel (eqd_set_option "node_variant"); the gather is latency bound
+  switch (A.variant % 10) {
+    case 1: k_node_update3<SKIP, 256, 5><<<nblk(A.Nn, 256), 256, 0, s>>>(A); break;
+    case 2: k_node_update3<SKIP, 256, 6><<<nblk(A.Nn, 256), 256, 0, s>>>(A); break;
+    case 3: k_node_update3<SKIP, 128, 8><<<nblk(A.Nn, 128), 128, 0, s>>>(A); break;
+    case 4: k_node_update3<SKIP, 128, 10><<<nblk(A.Nn, 128), 128, 0, s>>>(A); break;
+    case 5: k_node_update3<SKIP, 128, 12><<<nblk(A.Nn, 128), 128, 0, s>>>(A); break;
+    default: k_node_update3<SKIP, 256, 4><<<nblk(A.Nn, 256), 256, 0, s>>>(A); break;
+  }
+}
+template <bool SKIP>
+static void launch_node12(const NodeArgs& A, cudaStream_t s) {
+  switch (A.variant / 10) {
+    case 1: k_node_update12<SKIP, 6><<<nblk(A.Np, 128), 128, 0, s>>>(A); break;
+    case 2: k_node_update12<SKIP, 8><<<nblk(A.Np, 128), 128, 0, s>>>(A); break;
+    default: k_node_update12<SKIP, 5><<<nblk(A.Np, 128), 128, 0, s>>>(A); break;
+  }
+}
 void launch_node_update(const NodeArgs& A, cudaStream_t s) {
   if (A.skipSpecial) {
-    if (A.Nn > 0) k_node_update3<true><<<nblk(A.Nn, 256), 256, 0, s>>>(A);
-    if (A.Np > 0) k_node_update12<true><<<nblk(A.Np, 128), 128, 0, s>>>(A);
+    if (A.Nn > 0) launch_node3<true>(A, s);
+    if (A.Np > 0) launch_node12<true>(A, s);
   } else {
-    if (A.Nn > 0) k_node_update3<false><<<nblk(A.Nn, 256), 256, 0, s>>>(A);
-    if (A.Np > 0) k_node_update12<false><<<nblk(A.Np, 128), 128, 0, s>>>(A);
+    if (A.Nn > 0) launch_node3<false>(A, s);
+    if (A.Np > 0) launch_node12<false>(A, s);
   }
 }
 void launch_node_update_special(const NodeArgs& A, const int* list, int n, cudaStream_t s) {

@@ -245,8 +245,8 @@ extern "C" int eqd_plan_check(int32_t Nn, int32_t Ne, const int32_t* nodeElemIdR
     std::vector<char> seen(Ne, 0);
     for (int c = 0; c < 3; ++c) {
       TileShape sh;
-      if (c == CLS_PML) { sh.bx = 3; sh.bz = 3; sh.by = 24; sh.capE = 320; sh.capN = EQD_PML_LS; }
-      else { sh.bx = 4; sh.bz = 4; sh.by = 16; sh.capE = 384; sh.capN = EQD_REG_LS; }
+      if (c == CLS_PML) { sh.bx = kPmlBrick[0]; sh.bz = kPmlBrick[1]; sh.by = kPmlBrick[2]; sh.capE = 320; sh.capN = EQD_PML_LS; }
+      else { sh.bx = kRegBrick[0]; sh.bz = kRegBrick[1]; sh.by = kRegBrick[2]; sh.capE = 384; sh.capN = EQD_REG_LS; }
       const int NTP = c == CLS_PML ? EQD_STAGE_PML : EQD_STAGE;
       TilePlan P;
       plan_tiles(conn.data(), members[c], Nn, ny, nz, ok, sh, NTP, P);

@@ -26,6 +26,13 @@ struct TilePlan {
   raw_vector<uint16_t> lconn;     // [8][S] tile-local node | colour << 12
 };
 
+// default bricks (elements along x, z, y), measured on TPV104 @ 100 m (tools/tune_tiles.py): a regular
+// brick of 4x4x16 is halved by the 400-node cap into two 2x4x16 tiles = exactly one 128-element stage
+// with 16-element y runs (bank-conflict free in shared memory); PML slabs are 6 elements thick in any
+// direction, 6x7x6 fills four 64-element stages whatever the slab's orientation
+constexpr int kRegBrick[3] = {4, 4, 16};
+constexpr int kPmlBrick[3] = {6, 7, 6};
+
 struct TileShape {
   int bx = 4, bz = 4, by = 32;  // target brick, in elements, along the x / z / y grid axes
   int capE = 640;               // hard cap on elements per tile

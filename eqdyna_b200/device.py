@@ -98,7 +98,7 @@ def plan_check(view):
 class Domain:
     """One sub-domain of a case on one GPU."""
 
-    def __init__(self, view, device=0, compute_ops=False):
+    def __init__(self, view, device=0, compute_ops=False, options=None):
         """compute_ops: let the device compute the element operators and the lumped mass from the
         mesh (eqd_compute_elem_ops) instead of uploading the host's (eqd_set_elem_ops)."""
         self.view = view
@@ -109,6 +109,8 @@ class Domain:
         if rc:
             raise StepError(rc, "eqd_create failed (no CUDA device? see stderr)")
         self._keep = []
+        for k, val in (options or {}).items():   # options that shape the upload (tile bricks)
+            self.set_option(k, val)
         self._upload(view)
 
     def _check(self, rc):

@@ -1,0 +1,35 @@
+#!/usr/bin/env python3
+"""Time tile-brick shapes of the element kernels on the benchmark mesh (run on a GPU box).
+usage: tune_tiles.py [CASE]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from eqdyna_b200 import cases, device as dev  # noqa: E402
+from eqdyna_b200.host import World  # noqa: E402
+
+case = sys.argv[1] if len(sys.argv) > 1 else "bench.tpv104_100m"
+w = World(cases.materialize(case), np_xyz=(1, 1, 1), nstep=100)
+w.build(rank=0, sum_shared=False)
+CONFIGS = [
+    ((4, 4, 16), (6, 3, 12)),
+    ((4, 4, 16), (3, 6, 12)),
+    ((4, 4, 16), (6, 4, 9)),
+    ((4, 4, 16), (6, 2, 16)),
+    ((4, 4, 16), (3, 4, 16)),
+    ((4, 4, 16), (6, 8, 5)),
+    ((2, 4, 21), (6, 7, 6)),
+    ((3, 3, 14), (6, 7, 6)),
+]
+for reg, pml in CONFIGS:
+    opts = dict(zip(("reg_bx", "reg_bz", "reg_by", "pml_bx", "pml_bz", "pml_by"), reg + pml))
+    d = dev.Domain(w.view(0), device=0, compute_ops=True, options=opts)
+    d.set_option("timing", 1)
+    d.run(1, 10)
+    d.set_option("timing", 2)
+    d.run(11, 40)
+    t = d.timing()
+    print("reg %s pml %s: elem %.4f pml %.4f node %.4f total %.4f ms/step" % (
+        reg, pml, t["elem"] / 30, t["elem_pml"] / 30, t["node"] / 30, t["total"] / 30), flush=True)
+    d.close()
+w.close()
