@@ -22,7 +22,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world_size, port, case, decomp, nstep, overlap, out):
+def _worker(rank, world_size, port, case, decomp, nstep, overlap, own_rank_only, out):
     sys.path.insert(0, parity.ROOT)
     sys.path.insert(0, os.path.join(parity.ROOT, "tests"))
     import torch
@@ -31,12 +31,22 @@ def _worker(rank, world_size, port, case, decomp, nstep, overlap, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world_size)
-    w = parity.build_world(case, decomp, nstep)   # whole world on the host: init-time shared sums done
+    if own_rank_only:
+        # what bench.py --gpus N does: every process builds only its own sub-domain, the operators and
+        # the lumped mass are computed on the device and the init-time shared sums go over NCCL
+        from eqdyna_b200 import cases
+        from eqdyna_b200.host import World
+        w = World(cases.materialize(case), np_xyz=decomp, nstep=nstep)
+        w.build(rank=rank, sum_shared=False)
+    else:
+        w = parity.build_world(case, decomp, nstep)   # whole world on the host: init-time shared sums done
     v = w.view(rank)
-    d = dev.Domain(v, device=rank % torch.cuda.device_count())
+    d = dev.Domain(v, device=rank % torch.cuda.device_count(), compute_ops=bool(own_rank_only))
     ids = [dev.unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     d.set_comm(ids[0], world_size, rank)
+    if own_rank_only:
+        d.sum_shared()
     d.set_option("overlap", overlap)   # 1: halo on the communication stream under the interior tiles
     n = v.nstep
     d.run(1, n // 2)          # two chunks: the halo state must survive a return to the host
@@ -49,18 +59,19 @@ def _worker(rank, world_size, port, case, decomp, nstep, overlap, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case,decomp,nstep,overlap",
-                         [("test.tpv8", (2, 1, 1), 0, 1), ("test.tpv104", (1, 2, 1), 60, 1), ("test.tpv8", (2, 1, 1), 40, 0),
-                          ("test.tpv10", (2, 1, 2), 60, 1)],
-                         ids=["tpv8-2x1x1", "tpv104-1x2x1-fault-on-rank-face", "tpv8-2x1x1-no-overlap", "tpv10-2x1x2"])
-def test_nccl_processes_match_oracle(tmp_path, case, decomp, nstep, overlap):
+@pytest.mark.parametrize("case,decomp,nstep,overlap,own_rank_only",
+                         [("test.tpv8", (2, 1, 1), 0, 1, 0), ("test.tpv104", (1, 2, 1), 60, 1, 0), ("test.tpv8", (2, 1, 1), 40, 0, 0),
+                          ("test.tpv104", (1, 2, 1), 60, 1, 1), ("test.tpv10", (2, 1, 2), 60, 2, 0)],
+                         ids=["tpv8-2x1x1", "tpv104-1x2x1-fault-on-rank-face", "tpv8-2x1x1-no-overlap",
+                              "tpv104-1x2x1-own-rank-device-ops-sum-shared", "tpv10-2x1x2-face-tiles-first"])
+def test_nccl_processes_match_oracle(tmp_path, case, decomp, nstep, overlap, own_rank_only):
     import torch
     import torch.multiprocessing as mp
     n = decomp[0] * decomp[1] * decomp[2]
     if torch.cuda.device_count() < n:
         pytest.skip("needs %d GPUs" % n)
     port = _free_port()
-    mp.spawn(_worker, args=(n, port, case, decomp, nstep, overlap, str(tmp_path)), nprocs=n, join=True)
+    mp.spawn(_worker, args=(n, port, case, decomp, nstep, overlap, own_rank_only, str(tmp_path)), nprocs=n, join=True)
     wo = parity.build_world(case, decomp, nstep)
     parity.run_oracle(wo)
     for r in range(n):
