@@ -1181,24 +1181,38 @@ __device__ __forceinline__ double d_time_weak(double trupt, double fs, double fd
   return fd;
 }
 struct RsfPar { double A, B, L, f0, V0, fw, Vw; };
-__device__ __forceinline__ void d_rsf_ageing(double V2, double& theta, const RsfPar& r, double& xmu, double& dxmudv, double dt) {  // fric.f90:39-61
-  const double tmpc = 1.0 / (2.0 * r.V0) * exp((r.f0 + r.B * log(r.V0 * theta / r.L)) / r.A);
-  const double tmp = (V2 + 1.e-30) * tmpc;
-  xmu = r.A * log(tmp + sqrt(tmp * tmp + 1.0));
-  dxmudv = r.A * tmpc / sqrt(1.0 + tmp * tmp);
-  theta = r.L / V2 + (theta - r.L / V2) * exp(-V2 * dt / r.L);
+// fric.f90:39-95 split into its two halves: the friction coefficient and its slip-rate derivative
+// (all the Newton solve needs, with the state-dependent factor tmpc hoisted: the state is reset to
+// state0 at the top of every iteration, faulting.f90:471), and the state evolution (only the LAST
+// iteration's value survives, faulting.f90:511, so it is evaluated once after the loop).  Same
+// expressions on the same inputs: bit-identical to evaluating both halves in every iteration.
+__device__ __forceinline__ double d_rsf_tmpc_ageing(double theta, const RsfPar& r) {
+  return 1.0 / (2.0 * r.V0) * exp((r.f0 + r.B * log(r.V0 * theta / r.L)) / r.A);
 }
-__device__ __forceinline__ void d_rsf_slip(double V2, double& psi, const RsfPar& r, double& xmu, double& dxmudv, double dt) {  // fric.f90:63-95
-  const double tmpc = 1.0 / (2.0 * r.V0) * exp(psi / r.A);
+__device__ __forceinline__ double d_rsf_tmpc_slip(double psi, const RsfPar& r) { return 1.0 / (2.0 * r.V0) * exp(psi / r.A); }
+__device__ __forceinline__ void d_rsf_mu(double V2, double tmpc, const RsfPar& r, double& xmu, double& dxmudv) {
   const double tmp = (V2 + 1.e-30) * tmpc;
   xmu = r.A * log(tmp + sqrt(tmp * tmp + 1.0));
   dxmudv = r.A * tmpc / sqrt(1.0 + tmp * tmp);
+}
+__device__ __forceinline__ double d_rsf_state_ageing(double V2, double theta, const RsfPar& r, double dt) {
+  return r.L / V2 + (theta - r.L / V2) * exp(-V2 * dt / r.L);
+}
+__device__ __forceinline__ double d_rsf_state_slip(double V2, double psi, const RsfPar& r, double dt) {
   const double fLV = r.f0 - (r.B - r.A) * log(V2 / r.V0);
   const double q = V2 / r.Vw, q2 = q * q, q4 = q2 * q2;
   const double fss = r.fw + (fLV - r.fw) / pow(1.0 + q4 * q4, 0.125);
   const double fssa = fss / r.A;
   const double psiss = r.A * log(2.0 * r.V0 / V2 * (exp(fssa) - exp(-fssa)) / 2.0);
-  psi = psiss + (psi - psiss) * exp(-V2 * dt / r.L);
+  return psiss + (psi - psiss) * exp(-V2 * dt / r.L);
+}
+__device__ __forceinline__ void d_rsf_ageing(double V2, double& theta, const RsfPar& r, double& xmu, double& dxmudv, double dt) {  // fric.f90:39-61
+  d_rsf_mu(V2, d_rsf_tmpc_ageing(theta, r), r, xmu, dxmudv);
+  theta = d_rsf_state_ageing(V2, theta, r, dt);
+}
+__device__ __forceinline__ void d_rsf_slip(double V2, double& psi, const RsfPar& r, double& xmu, double& dxmudv, double dt) {  // fric.f90:63-95
+  d_rsf_mu(V2, d_rsf_tmpc_slip(psi, r), r, xmu, dxmudv);
+  psi = d_rsf_state_slip(V2, psi, r, dt);
 }
 
 // faulting.f90:3-541, one thread per split-node pair
@@ -1357,10 +1371,11 @@ __global__ void __launch_bounds__(64, 8) k_fault(FaultArgs A) {
       const double state0 = statetmp, thetaPc0 = theta_pc_tmp;
       double stateTmp = state0;
       double thetaPcTmp = 0.0;  // uninitialised local in the reference when friclaw==5 (never read by the solve)
+      const double tmpc0 = A.friclaw == 3 ? d_rsf_tmpc_ageing(state0, r) : d_rsf_tmpc_slip(state0, r);
+      double v_state = v_trial;   // slip rate the surviving state evolution is evaluated at
       for (int iv = 1; iv <= 20; ++iv) {
-        stateTmp = state0;
-        if (A.friclaw == 3) d_rsf_ageing(v_trial, stateTmp, r, xmu, dxmudv, dt);
-        else d_rsf_slip(v_trial, stateTmp, r, xmu, dxmudv, dt);
+        v_state = v_trial;
+        d_rsf_mu(v_trial, tmpc0, r, xmu, dxmudv);
         double rsfeq, drsfeqdv;
         if (A.friclaw < 5) {
           thetaPcTmp = thetaPc0;
@@ -1379,6 +1394,7 @@ __global__ void __launch_bounds__(64, 8) k_fault(FaultArgs A) {
         if (newSliprate <= 0.0) v_trial = v_trial / 2.0;
         else v_trial = newSliprate;
       }
+      stateTmp = A.friclaw == 3 ? d_rsf_state_ageing(v_state, state0, r, dt) : d_rsf_state_slip(v_state, state0, r, dt);
       if (A.TPV == 105 && v_trial < FR(46)) v_trial = FR(46);
       statetmp = stateTmp;
       theta_pc_tmp = thetaPcTmp;
