@@ -220,7 +220,7 @@ struct eqd_handle {
   double hostTime = 0.0;
   long launches = 0;
   bool timing = false;
-  int optGraph = 0, optBlock = 0, optNodeVariant = 4;
+  int optNodeVariant = 4;
   int optTile[2][3] = {{kRegBrick[0], kRegBrick[1], kRegBrick[2]}, {kPmlBrick[0], kPmlBrick[1], kPmlBrick[2]}};  // brick of a regular / PML tile in elements along x, z, y (before eqd_set_mesh)
   double tms[EQD_T_NSLOTS] = {0};
   std::vector<cudaEvent_t> evs;  // timing events
@@ -1649,8 +1649,6 @@ int eqd_get_timing(const eqd_handle* h, double* ms_slots) {
 int eqd_set_option(eqd_handle* h, const char* key, int32_t value) {
   if (!h || !key) return EQD_ERR_ARG;
   if (!strcmp(key, "timing")) { h->timing = value != 0; if (value == 2) { for (double& t : h->tms) t = 0; h->launches = 0; } return EQD_OK; }
-  if (!strcmp(key, "graph")) { h->optGraph = value; return EQD_OK; }
-  if (!strcmp(key, "block")) { h->optBlock = value; return EQD_OK; }
   if (!strcmp(key, "overlap")) { h->optOverlap = value; return EQD_OK; }
   {
     const char* names[6] = {"reg_bx", "reg_bz", "reg_by", "pml_bx", "pml_bz", "pml_by"};

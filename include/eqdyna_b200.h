@@ -172,8 +172,12 @@ int eqd_get_counts(const eqd_handle* h, int64_t* n_regular, int64_t* n_pml,
                    int64_t* n_pairs, int64_t* launches);
 int eqd_get_timing(const eqd_handle* h, double* ms_slots /*[EQD_T_NSLOTS]*/);
 /* options: "timing" 1 = CUDA-event timing of every phase (2 = also reset the
- * accumulated slots and the launch counter), "graph", "overlap", "block": see
- * DESIGN.md                                                                   */
+ * accumulated slots and the launch counter); "overlap" -1 auto (default) / 0 serial
+ * step / 1 halo + fault solver on a second stream under the next bulk node update /
+ * 2 also rank-face tiles first; "reserve" CTAs left free by the overlapped interior
+ * sweep (mode 2); "node_variant" launch-bounds variant of the node update; and,
+ * before eqd_set_mesh only, the tile bricks "reg_bx/bz/by", "pml_bx/bz/by".
+ * Unknown keys return 4.  See DESIGN.md sections 3-4.                          */
 int eqd_set_option(eqd_handle* h, const char* key, int32_t value);
 
 /* Host-only self-check of the tile planner (no GPU needed): cuts the given
