@@ -17,6 +17,7 @@
 #include <thread>
 #include <vector>
 
+#include "eqd_box.h"
 #include "eqd_dev.cuh"
 #include "eqd_kernels.h"
 #include "eqd_par.h"
@@ -143,6 +144,9 @@ struct ElemClass {
   raw_vector<int> tnodeH;
   std::vector<int4> tileRecH;  // planner order
   DevBuf<int4> tileRec;        // launch order
+  std::vector<uint8_t> tileBoxH;  // planner order: 1 = all elements of the tile are axis-aligned hexahedra (option "box")
+  DevBuf<uint8_t> tileBox;        // launch order; empty = closed-form box operators off
+  long nBoxElems = 0;
   DevBuf<int> tnode;
   DevBuf<uint16_t> lconn;
   DevBuf<double> shp, phi, ss, lam, mu, det, rho, vp, stress, qmem, porep, pstrain, emass, damps, pf;
@@ -221,6 +225,7 @@ struct eqd_handle {
   long launches = 0;
   bool timing = false;
   int optNodeVariant = 4;
+  int optBox = 0;   // closed-form operators on all-box tiles (eqd_box.h): 1 = regular classes, 2 = also PML; set before the first eqd_run
   int optTile[2][3] = {{kRegBrick[0], kRegBrick[1], kRegBrick[2]}, {kPmlBrick[0], kPmlBrick[1], kPmlBrick[2]}};  // brick of a regular / PML tile in elements along x, z, y (before eqd_set_mesh)
   double tms[EQD_T_NSLOTS] = {0};
   std::vector<cudaEvent_t> evs;  // timing events
@@ -358,6 +363,7 @@ ElemArgs eqd_handle::elemArgs(int c) const {
   A.ccosphi = p.ccosphi; A.sinphi = p.sinphi;
   A.expdttv = p.tv != 0.0 ? std::exp(-p.dt / p.tv) : 0.0;
   A.kapa_hg = p.kapa_hg;
+  A.tileBox = C.tileBox.n ? C.tileBox.p : nullptr;
   return A;
 }
 
@@ -463,19 +469,45 @@ void finalize(eqd_handle* h) {
       for (int side = 0; side < 2; ++side)
         if (h->face[a][side].nb >= 0)
           for (int n : h->face[a][side].nodes) { onFace[n] = 1; anyFace = true; }
+  // ---- option "box": flag the tiles (1: regular classes, 2: also PML) whose elements are all
+  // axis-aligned hexahedra (exact test on the reference's coordinates, eqd_box.h)
+  if (h->optBox)
+    for (int c = 0; c < 3; ++c) {
+      ElemClass& C = h->cls[c];
+      C.nBoxElems = 0;
+      if (!C.n || (c == CLS_PML && h->optBox < 2)) continue;
+      C.tileBoxH.assign(C.nTiles, 0);
+      parallel_range((size_t)C.nTiles, [&](size_t tb, size_t te) {
+        for (size_t t = tb; t < te; ++t) {
+          const int e0 = C.tileRecH[t].x, ne = C.tileRecH[t].y & 0xffff;
+          bool all = true;
+          for (int k = 0; k < ne && all; ++k) {
+            const int e = C.refId[(size_t)e0 + k];
+            all = e >= 0 && h->etype[e] != 11 && h->etype[e] != 12 && box_element(&h->conn[8 * (size_t)e], h->coor.data());
+          }
+          C.tileBoxH[t] = all ? 1 : 0;
+        }
+      });
+      for (int t = 0; t < C.nTiles; ++t) if (C.tileBoxH[t]) C.nBoxElems += C.tileRecH[t].y & 0xffff;
+      if (!anyFace) C.tileBox.upload(C.tileBoxH);
+    }
   if (anyFace) {
     for (int c = 0; c < 3; ++c) {
       ElemClass& C = h->cls[c];
       if (!C.n) continue;
       std::vector<int4> first, rest;
+      std::vector<uint8_t> firstB, restB;
+      const bool boxed = !C.tileBoxH.empty();
       for (int t = 0; t < C.nTiles; ++t) {
         bool f = false;
         for (int k = C.tileNodeH[t]; k < C.tileNodeH[t + 1] && !f; ++k) f = C.tnodeH[k] >= 0 && onFace[C.tnodeH[k]];
         (f ? first : rest).push_back(C.tileRecH[t]);
+        if (boxed) (f ? firstB : restB).push_back(C.tileBoxH[t]);
       }
       C.nFaceTiles = (int)first.size();
       first.insert(first.end(), rest.begin(), rest.end());
       C.tileRec.upload(first);
+      if (boxed) { firstB.insert(firstB.end(), restB.begin(), restB.end()); C.tileBox.upload(firstB); }
     }
   }
   {
@@ -1640,6 +1672,13 @@ int eqd_get_counts(const eqd_handle* h, int64_t* n_regular, int64_t* n_pml, int6
   return EQD_OK;
 }
 
+int eqd_get_box_counts(const eqd_handle* h, int64_t* n_regular_box, int64_t* n_pml_box) {
+  if (!h) return EQD_ERR_ARG;
+  if (n_regular_box) *n_regular_box = h->cls[CLS_REG].nBoxElems + h->cls[CLS_REGX].nBoxElems;
+  if (n_pml_box) *n_pml_box = h->cls[CLS_PML].nBoxElems;
+  return EQD_OK;
+}
+
 int eqd_get_timing(const eqd_handle* h, double* ms_slots) {
   if (!h || !ms_slots) return EQD_ERR_ARG;
   for (int k = 0; k < EQD_T_NSLOTS; ++k) ms_slots[k] = h->tms[k];
@@ -1660,6 +1699,11 @@ int eqd_set_option(eqd_handle* h, const char* key, int32_t value) {
       }
   }
   if (!strcmp(key, "node_variant")) { h->optNodeVariant = value; return EQD_OK; }
+  if (!strcmp(key, "box")) {
+    if (h->finalized) { h->err = "eqd_set_option: box must be set before the first eqd_run / eqd_sum_shared"; return EQD_ERR_ARG; }
+    h->optBox = value < 0 ? 0 : value > 2 ? 2 : value;
+    return EQD_OK;
+  }
   if (!strcmp(key, "reserve")) { h->optReserve = value; return EQD_OK; }
   h->err = std::string("eqd_set_option: unknown key ") + key;
   return EQD_ERR_ARG;

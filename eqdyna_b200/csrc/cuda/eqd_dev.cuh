@@ -100,6 +100,7 @@ struct ElemArgs {
   const double* damps;   // [3][S] PML damping profile at the centroid
   const double* vel; const double* disp; int NnS;
   double dt, rdampk, rdampm, w, bodyz, ccosphi, sinphi, expdttv, kapa_hg;
+  const uint8_t* tileBox;  // per tile in launch order: 1 = every element is an axis-aligned hexahedron (eqd_box.h); null = off
 };
 
 struct FaultArgs {

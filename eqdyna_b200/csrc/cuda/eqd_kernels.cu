@@ -13,6 +13,7 @@
 #include <set>
 #include <utility>
 
+#include "eqd_box.h"
 #include "eqd_dev.cuh"
 #include "eqd_kernels.h"
 
@@ -411,7 +412,10 @@ __device__ __forceinline__ const double* reg_row_src(const ElemArgs& A, int r) {
 // Regular hexahedron / degenerate wedge: calcElemKU.f90:3-191 (+ calcB.f90,
 // calcElemMass.f90) and hrglss.f90:13-98.  The 6x24 B matrix is never
 // materialised.
-template <bool PLASTIC, bool QMODE, bool BODY, bool SPLIT, int CHG>
+// BOX: tiles flagged in A.tileBox hold only axis-aligned hexahedra; their shape
+// derivatives, hourglass vectors and hourglass stiffness are used in closed form
+// (eqd_box.h) and only BOX_ROWS of the RR_ROWS operator rows are streamed.
+template <bool PLASTIC, bool QMODE, bool BODY, bool SPLIT, int CHG, bool BOX>
 __global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
   extern __shared__ __align__(128) unsigned char smraw[];
   constexpr int SE = EQD_STAGE;
@@ -435,12 +439,12 @@ __global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
   double* sl = sv + 3 * LS;                                     // [3][LS] d + rdampk*v
   double* sd = QMODE ? sl + 3 * LS : sl;                        // [3][LS] displacement: gather target (kept for Q)
   double* sf = sl + (QMODE ? 6 : 3) * LS;                       // [2][3][LS] force accumulators: KU | hourglass
-  auto request = [&](const int4& rec, int base) {
+  auto request = [&](const int4& rec, int base, bool bx) {
     // one thread per row; sizes are whole 32-element groups (the class SoA is padded)
     const int cnt = min(SE, (TR_NE(rec) - base + 31) & ~31);
-    if (tid == 0) mbar_expect_tx(bar, (uint32_t)(cnt * (RR_ROWS * 8 + 8 * 2)));
+    if (tid == 0) mbar_expect_tx(bar, (uint32_t)(cnt * ((BOX && bx ? (int)BOX_ROWS : (int)RR_ROWS) * 8 + 8 * 2)));
     __syncwarp();
-    if (tid < RR_ROWS) bulk_g2s(ops + tid * SE, reg_row_src(A, tid) + TR_E0(rec) + base, cnt * 8, bar);
+    if (tid < RR_ROWS) { if (!(BOX && bx) || box_row(tid)) bulk_g2s(ops + tid * SE, reg_row_src(A, tid) + TR_E0(rec) + base, cnt * 8, bar); }
     else if (tid < RR_ROWS + 8) bulk_g2s(slc + (tid - RR_ROWS) * SE, A.lconn + (size_t)(tid - RR_ROWS) * S + TR_E0(rec) + base, cnt * 2, bar);
   };
   auto request_ids = [&](const int4& rec) {
@@ -486,11 +490,13 @@ __global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
   // software pipeline over this CTA's tiles: rc = tile being swept, rn = the next
   // one (its operators and nodes are requested while rc's forces are assembled)
   int4 rc = __ldg(A.tileRec + tnext);
+  bool bc = BOX && __ldg(A.tileBox + tnext) != 0;   // CTA-uniform
   tnext += gridDim.x;
   int4 rn = tnext < tEnd ? __ldg(A.tileRec + tnext) : zero4;
+  bool bn = BOX && tnext < tEnd && __ldg(A.tileBox + tnext) != 0;
   if (tid == 0) { mbar_init(bar, 1); mbar_init(barN, 1); }
   __syncthreads();
-  request(rc, 0);
+  request(rc, 0, bc);
   request_ids(rc);
 #pragma unroll
   for (int k = 0; k < NPT; ++k) {
@@ -510,6 +516,7 @@ __global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
   while (true) {
   const bool more = tnext < tEnd;
   const int4 rnn = (tnext + (int)gridDim.x < tEnd) ? __ldg(A.tileRec + tnext + gridDim.x) : zero4;
+  const bool bnn = BOX && (tnext + (int)gridDim.x < tEnd) && __ldg(A.tileBox + tnext + gridDim.x) != 0;
   if (more) request_ids(rn);   // tnS is free: rc's nodes are already in sv/sl
   const int ne = TR_NE(rc), NC = TR_NC(rc);
   for (int base = 0; base < ne; base += SE) {
@@ -528,6 +535,32 @@ __global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
         // ---------------- constitutive part: calcElemKU.f90
         double sr[6] = {0, 0, 0, 0, 0, 0}, sn[6] = {0, 0, 0, 0, 0, 0};
         double body[BODY ? 24 : 1];
+        if (BOX && bc) {
+          // axis-aligned hexahedra: eleshp(d,i) = sign_d(i)*a_d (eqd_box.h)
+          double u[8][3], g[3][3];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int li = lc[i] & EQD_LN_MASK;
+            u[i][0] = sv[li]; u[i][1] = sv[LS + li]; u[i][2] = sv[2 * LS + li];
+            if (BODY) {
+              const double em = LDG(A.emass + i * S + e);
+              body[3 * i] = 0.0 - (A.rdampm * u[i][0]) * em;
+              body[3 * i + 1] = 0.0 - (A.rdampm * u[i][1]) * em;
+              body[3 * i + 2] = 0.0 - (A.rdampm * u[i][2] + A.bodyz) * em;
+            }
+          }
+          box_grad(u, g);
+          box_strain(g, OP(BOX_AX), OP(BOX_AY), OP(BOX_AZ), sr);
+          if (QMODE) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int li = lc[i] & EQD_LN_MASK;
+              u[i][0] = sd[li]; u[i][1] = sd[LS + li]; u[i][2] = sd[2 * LS + li];
+            }
+            box_grad(u, g);
+            box_strain(g, OP(BOX_AX), OP(BOX_AY), OP(BOX_AZ), sn);
+          }
+        } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int li = lc[i] & EQD_LN_MASK;
@@ -556,6 +589,7 @@ __global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
             body[3 * i + 1] = 0.0 - (A.rdampm * vy) * em;
             body[3 * i + 2] = 0.0 - (A.rdampm * vz + A.bodyz) * em;
           }
+        }
         }
         const double lam = OP(RR_LAM), mu = OP(RR_MU);
         const double l2m = lam + 2 * mu;
@@ -619,6 +653,13 @@ __global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
         double t[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) t[i] = temp * (sg[i] + rdampk * rate[i]);
+        if (BOX && bc) {
+          box_force(t, OP(BOX_AX), OP(BOX_AY), OP(BOX_AZ), f);
+          if (BODY) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { f[i][0] = body[3 * i] + f[i][0]; f[i][1] = body[3 * i + 1] + f[i][1]; f[i][2] = body[3 * i + 2] + f[i][2]; }
+          }
+        } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const double s1 = OP(RR_SHP + 3 * i), s2 = OP(RR_SHP + 3 * i + 1), s3 = OP(RR_SHP + 3 * i + 2);
@@ -629,9 +670,20 @@ __global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
           if (BODY) { f0 = body[3 * i] + f0; f1 = body[3 * i + 1] + f1; f2 = body[3 * i + 2] + f2; }
           f[i][0] = f0; f[i][1] = f1; f[i][2] = f2;
         }
+        }
       } else {
         // ---------------- hourglass part: hrglss.f90
         if (CHG == 1) {
+          if (BOX && bc) {
+            // phi = ha, ss diagonal (eqd_box.h)
+            double l[8][3];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int li = lc[i] & EQD_LN_MASK;
+              l[i][0] = sl[li]; l[i][1] = sl[LS + li]; l[i][2] = sl[2 * LS + li];
+            }
+            box_hourglass(l, OP(BOX_SS0), OP(BOX_SS3), OP(BOX_SS5), f);
+          } else {
           double phid[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -666,6 +718,7 @@ __global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
               h2 = h2 - p * hv[m][2];
             }
             f[i][0] = h0; f[i][1] = h1; f[i][2] = h2;
+          }
           }
         } else {
           // viscous hourglass, hrglss.f90:57-80
@@ -703,9 +756,9 @@ __global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
     // stage and its nodal values; they land while the forces are assembled
     __syncthreads();
     const bool last = base + SE >= ne;
-    if (!last) request(rc, base + SE);
+    if (!last) request(rc, base + SE, bc);
     else if (more) {
-      request(rn, 0);
+      request(rn, 0, bn);
       mbar_wait(barN, parityN);
       parityN ^= 1;
       gather_nodes(rn);   // sv / sd are dead once the last stage has been consumed
@@ -745,6 +798,7 @@ __global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
   finish_nodes();
   __syncthreads();
   rc = rn; rn = rnn; tnext += gridDim.x;
+  bc = bn; bn = bnn;
   }
 }
 
@@ -770,7 +824,10 @@ __device__ __forceinline__ const double* pml_row_src(const ElemArgs& A, int r) {
   return A.stress + (size_t)(r - PR_STRESS) * S;
 }
 
-template <bool BODY, int CHG>
+// BOX: as in k_tile_reg -- tiles flagged in A.tileBox stream 33 of the 89 rows and
+// rebuild eleshp = sign*a_d, phi = ha, ss = diag in registers (eqd_box.h).
+constexpr int PR_BOX_ROWS = BOX_ROWS + (PR_ROWS - RR_ROWS);
+template <bool BODY, int CHG, bool BOX>
 __global__ void __launch_bounds__(4 * EQD_STAGE_PML, 2) k_tile_pml(ElemArgs A) {
   extern __shared__ __align__(128) unsigned char smraw[];
   constexpr int SE = EQD_STAGE_PML;
@@ -794,11 +851,11 @@ __global__ void __launch_bounds__(4 * EQD_STAGE_PML, 2) k_tile_pml(ElemArgs A) {
   double* sv = (double*)(tnS + LS);                             // [3][LS] velocity
   double* sl = sv + 3 * LS;                                     // [3][LS] d + rdampk*v
   double* sf = sl + 3 * LS;                                     // [NROW][LS]
-  auto request = [&](const int4& rec, int base) {
+  auto request = [&](const int4& rec, int base, bool bx) {
     const int cnt = min(SE, (TR_NE(rec) - base + 31) & ~31);
-    if (tid == 0) mbar_expect_tx(bar, (uint32_t)(cnt * (PR_ROWS * 8 + 8 * 2)));
+    if (tid == 0) mbar_expect_tx(bar, (uint32_t)(cnt * ((BOX && bx ? (int)PR_BOX_ROWS : (int)PR_ROWS) * 8 + 8 * 2)));
     __syncwarp();
-    if (tid < PR_ROWS) bulk_g2s(ops + tid * SE, pml_row_src(A, tid) + TR_E0(rec) + base, cnt * 8, bar);
+    if (tid < PR_ROWS) { if (!(BOX && bx) || box_row(tid)) bulk_g2s(ops + tid * SE, pml_row_src(A, tid) + TR_E0(rec) + base, cnt * 8, bar); }
     else if (tid < PR_ROWS + 8) bulk_g2s(slc + (tid - PR_ROWS) * SE, A.lconn + (size_t)(tid - PR_ROWS) * S + TR_E0(rec) + base, cnt * 2, bar);
   };
   auto request_ids = [&](const int4& rec) {
@@ -842,11 +899,13 @@ __global__ void __launch_bounds__(4 * EQD_STAGE_PML, 2) k_tile_pml(ElemArgs A) {
   };
   const int4 zero4 = make_int4(0, 0, 0, 0);
   int4 rc = __ldg(A.tileRec + tnext);
+  bool bc = BOX && __ldg(A.tileBox + tnext) != 0;   // CTA-uniform
   tnext += gridDim.x;
   int4 rn = tnext < tEnd ? __ldg(A.tileRec + tnext) : zero4;
+  bool bn = BOX && tnext < tEnd && __ldg(A.tileBox + tnext) != 0;
   if (tid == 0) { mbar_init(bar, 1); mbar_init(barN, 1); }
   __syncthreads();
-  request(rc, 0);
+  request(rc, 0, bc);
   request_ids(rc);
 #pragma unroll
   for (int k = 0; k < NPT; ++k) {
@@ -865,6 +924,7 @@ __global__ void __launch_bounds__(4 * EQD_STAGE_PML, 2) k_tile_pml(ElemArgs A) {
   while (true) {
     const bool more = tnext < tEnd;
     const int4 rnn = (tnext + (int)gridDim.x < tEnd) ? __ldg(A.tileRec + tnext + gridDim.x) : zero4;
+    const bool bnn = BOX && (tnext + (int)gridDim.x < tEnd) && __ldg(A.tileBox + tnext + gridDim.x) != 0;
     if (more) request_ids(rn);
     const int ne = TR_NE(rc), NC = TR_NC(rc);
     for (int base = 0; base < ne; base += SE) {
@@ -906,8 +966,18 @@ __global__ void __launch_bounds__(4 * EQD_STAGE_PML, 2) k_tile_pml(ElemArgs A) {
     A.stress[(size_t)(k) * S + e] = x;                                    \
   }
         if (role < 3) {
+          if (BOX && bc) {
+            const double ax = OP(BOX_AX), ay = OP(BOX_AY), az = OP(BOX_AZ);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              r24[3 * i] = box_px(i) ? ax : -ax;
+              r24[3 * i + 1] = box_py(i) ? ay : -ay;
+              r24[3 * i + 2] = box_pz(i) ? az : -az;
+            }
+          } else {
 #pragma unroll
           for (int k = 0; k < 24; ++k) r24[k] = OP(PR_SHP + k);
+          }
         }
         if (role == 0) {
           double g00 = 0, g11 = 0, g22 = 0;  // assembleGlobalKU.f90:248-275
@@ -971,6 +1041,17 @@ __global__ void __launch_bounds__(4 * EQD_STAGE_PML, 2) k_tile_pml(ElemArgs A) {
           for (int i = 0; i < 6; ++i) s0[i] = OP(PR_STRESS + 15 + i) + rdampk * rate[i];  // :320-325 (read-only slots)
         } else {
           if (CHG == 1) {
+            if (BOX && bc) {
+              double l[8][3], fh[8][3];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int li = lc[i] & EQD_LN_MASK;
+                l[i][0] = sl[li]; l[i][1] = sl[LS + li]; l[i][2] = sl[2 * LS + li];
+              }
+              box_hourglass(l, OP(BOX_SS0), OP(BOX_SS3), OP(BOX_SS5), fh);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { r24[3 * i] = fh[i][0]; r24[3 * i + 1] = fh[i][1]; r24[3 * i + 2] = fh[i][2]; }
+            } else {
             double phid[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -1004,6 +1085,7 @@ __global__ void __launch_bounds__(4 * EQD_STAGE_PML, 2) k_tile_pml(ElemArgs A) {
                 h2 = h2 - p * hv[m][2];
               }
               r24[3 * i] = h0; r24[3 * i + 1] = h1; r24[3 * i + 2] = h2;
+            }
             }
           } else {
             const int fi[4][8] = {{1, 1, -1, -1, -1, -1, 1, 1}, {1, -1, -1, 1, -1, 1, 1, -1},
@@ -1041,9 +1123,9 @@ __global__ void __launch_bounds__(4 * EQD_STAGE_PML, 2) k_tile_pml(ElemArgs A) {
       // next tile's first stage and its nodes; they land while the forces are assembled
       __syncthreads();
       const bool last = base + SE >= ne;
-      if (!last) request(rc, base + SE);
+      if (!last) request(rc, base + SE, bc);
       else if (more) {
-        request(rn, 0);
+        request(rn, 0, bn);
         mbar_wait(barN, parityN);
         parityN ^= 1;
         gather_nodes(rn);
@@ -1100,6 +1182,7 @@ __global__ void __launch_bounds__(4 * EQD_STAGE_PML, 2) k_tile_pml(ElemArgs A) {
     finish_nodes();
     __syncthreads();
     rc = rn; rn = rnn; tnext += gridDim.x;
+    bc = bn; bn = bnn;
   }
 }
 
@@ -1546,8 +1629,14 @@ static void launch_reg_chg(const ElemArgs& A, int chg, cudaStream_t s) {
   const size_t sm = tile_smem_bytes(CLS_REG, Q, A.LS);
   // persistent CTAs, two per SM, each walking tiles blockIdx.x, +gridDim.x, ...
   const int grid = std::min(ntiles, A.maxGrid > 0 ? A.maxGrid : 2 * sm_count());
-  if (chg == 2) tile_launch(k_tile_reg<PL, Q, BODY, SPLIT, 2>, A, grid, 2 * EQD_STAGE, sm, s);
-  else tile_launch(k_tile_reg<PL, Q, BODY, SPLIT, 1>, A, grid, 2 * EQD_STAGE, sm, s);
+  if (A.tileBox) {
+    // closed-form operators on the tiles flagged as all-box (eqd_set_option "box")
+    if (chg == 2) tile_launch(k_tile_reg<PL, Q, BODY, SPLIT, 2, true>, A, grid, 2 * EQD_STAGE, sm, s);
+    else tile_launch(k_tile_reg<PL, Q, BODY, SPLIT, 1, true>, A, grid, 2 * EQD_STAGE, sm, s);
+    return;
+  }
+  if (chg == 2) tile_launch(k_tile_reg<PL, Q, BODY, SPLIT, 2, false>, A, grid, 2 * EQD_STAGE, sm, s);
+  else tile_launch(k_tile_reg<PL, Q, BODY, SPLIT, 1, false>, A, grid, 2 * EQD_STAGE, sm, s);
 }
 template <bool SPLIT>
 static void launch_reg_split(const ElemArgs& A, bool plastic, bool q, bool body, int chg, cudaStream_t s) {
@@ -1567,8 +1656,13 @@ void launch_elem_pml(const ElemArgs& A, bool body, int chg, cudaStream_t s) {
   const size_t sm = tile_smem_bytes(CLS_PML, false, A.LS);
   const int nt = 4 * EQD_STAGE_PML;
   ntiles = std::min(ntiles, A.maxGrid > 0 ? A.maxGrid : 2 * sm_count());
-  if (body) { if (chg == 2) tile_launch(k_tile_pml<true, 2>, A, ntiles, nt, sm, s); else tile_launch(k_tile_pml<true, 1>, A, ntiles, nt, sm, s); }
-  else { if (chg == 2) tile_launch(k_tile_pml<false, 2>, A, ntiles, nt, sm, s); else tile_launch(k_tile_pml<false, 1>, A, ntiles, nt, sm, s); }
+  if (A.tileBox) {
+    if (body) { if (chg == 2) tile_launch(k_tile_pml<true, 2, true>, A, ntiles, nt, sm, s); else tile_launch(k_tile_pml<true, 1, true>, A, ntiles, nt, sm, s); }
+    else { if (chg == 2) tile_launch(k_tile_pml<false, 2, true>, A, ntiles, nt, sm, s); else tile_launch(k_tile_pml<false, 1, true>, A, ntiles, nt, sm, s); }
+    return;
+  }
+  if (body) { if (chg == 2) tile_launch(k_tile_pml<true, 2, false>, A, ntiles, nt, sm, s); else tile_launch(k_tile_pml<true, 1, false>, A, ntiles, nt, sm, s); }
+  else { if (chg == 2) tile_launch(k_tile_pml<false, 2, false>, A, ntiles, nt, sm, s); else tile_launch(k_tile_pml<false, 1, false>, A, ntiles, nt, sm, s); }
 }
 void launch_store_offfault(const int* idhist, int n, double* out, const double* vel, const double* disp, int NnS,
                            const StepState* st, cudaStream_t s) {

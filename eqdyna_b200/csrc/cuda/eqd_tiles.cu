@@ -5,10 +5,12 @@
 #include "eqd_tiles.h"
 
 #include <algorithm>
+#include <cmath>
 #include <mutex>
 #include <stdexcept>
 #include <thread>
 
+#include "eqd_box.h"
 #include "eqd_dev.cuh"
 #include "eqd_par.h"
 
@@ -292,5 +294,85 @@ extern "C" int eqd_plan_check(int32_t Nn, int32_t Ne, const int32_t* nodeElemIdR
   } catch (const std::exception&) {
     return __LINE__;
   }
+  return 0;
+}
+
+// ----------------------------------------------------------------------------
+// Host-only check of the closed-form box operators (eqd_box.h) against the
+// reference's precomputed ones (needs no GPU; CPU test-suite).  For every element
+// that passes the geometric box test, the strain, the B^T t nodal forces
+// (calcElemKU.f90:44-60,175-189) and the hourglass forces (hrglss.f90:20-54) of a
+// pseudo-random nodal field are evaluated both ways.  dev[0..2] = the largest
+// deviation of the three, relative to the element's largest component;
+// *nBox = elements that passed the test.  Returns 0, or a line number on bad input.
+extern "C" int eqd_box_check(int32_t Nn, int32_t Ne, const double* meshCoor, const int32_t* nodeElemIdRelation,
+                             const int32_t* elemTypeArr, const double* eleshp, const double* phi, const double* ss,
+                             int64_t* nBox, double* dev) {
+  using namespace eqd;
+  if (Nn <= 0 || Ne <= 0 || !meshCoor || !nodeElemIdRelation || !elemTypeArr || !eleshp || !phi || !ss || !nBox || !dev) return __LINE__;
+  auto field = [](int node, int c) {   // deterministic values in (-1, 1), no pattern along the grid
+    uint32_t x = (uint32_t)node * 2654435761u + (uint32_t)c * 40503u + 12345u;
+    x ^= x >> 15; x *= 2246822519u; x ^= x >> 13; x *= 3266489917u; x ^= x >> 16;
+    return (double)x / 2147483648.0 - 1.0;
+  };
+  int64_t count = 0;
+  double d[3] = {0, 0, 0};
+  for (int e = 0; e < Ne; ++e) {
+    int c[8];
+    for (int k = 0; k < 8; ++k) { c[k] = nodeElemIdRelation[8 * (size_t)e + k] - 1; if (c[k] < 0 || c[k] >= Nn) return __LINE__; }
+    if (elemTypeArr[e] == 11 || elemTypeArr[e] == 12 || !box_element(c, meshCoor)) continue;
+    ++count;
+    const double* shp = eleshp + 24 * (size_t)e;   // eleshp(3,8,e)
+    const double* ph = phi + 32 * (size_t)e;       // phi(8,4,e)
+    const double* s6 = ss + 6 * (size_t)e;
+    double u[8][3];
+    for (int i = 0; i < 8; ++i) for (int k = 0; k < 3; ++k) u[i][k] = field(c[i], k);
+    // general forms
+    double sr[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 8; ++i) {
+      const double s1 = shp[3 * i], s2 = shp[3 * i + 1], s3 = shp[3 * i + 2];
+      sr[0] += s1 * u[i][0]; sr[1] += s2 * u[i][1]; sr[2] += s3 * u[i][2];
+      sr[3] += s3 * u[i][1] + s2 * u[i][2]; sr[4] += s3 * u[i][0] + s1 * u[i][2]; sr[5] += s2 * u[i][0] + s1 * u[i][1];
+    }
+    double t[6];
+    for (int k = 0; k < 6; ++k) t[k] = field(c[0] + 7 * k, 3 + k);
+    double fg[8][3], hg[8][3];
+    for (int i = 0; i < 8; ++i) {
+      const double s1 = shp[3 * i], s2 = shp[3 * i + 1], s3 = shp[3 * i + 2];
+      fg[i][0] = s1 * t[0] + s3 * t[4] + s2 * t[5];
+      fg[i][1] = s2 * t[1] + s3 * t[3] + s1 * t[5];
+      fg[i][2] = s3 * t[2] + s2 * t[3] + s1 * t[4];
+    }
+    double phid[4][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, hv[4][3];
+    for (int i = 0; i < 8; ++i) for (int m = 0; m < 4; ++m) for (int k = 0; k < 3; ++k) phid[m][k] += ph[8 * m + i] * u[i][k];
+    for (int m = 0; m < 4; ++m) {
+      hv[m][0] = s6[0] * phid[m][0] + s6[1] * phid[m][1] + s6[2] * phid[m][2];
+      hv[m][1] = s6[1] * phid[m][0] + s6[3] * phid[m][1] + s6[4] * phid[m][2];
+      hv[m][2] = s6[2] * phid[m][0] + s6[4] * phid[m][1] + s6[5] * phid[m][2];
+    }
+    for (int i = 0; i < 8; ++i) for (int k = 0; k < 3; ++k) {
+      double h = 0.0;
+      for (int m = 0; m < 4; ++m) h -= ph[8 * m + i] * hv[m][k];
+      hg[i][k] = h;
+    }
+    // closed forms
+    const double ax = shp[BOX_AX], ay = shp[BOX_AY], az = shp[BOX_AZ];
+    double g[3][3], sb[6], fb[8][3], hb[8][3];
+    box_grad(u, g);
+    box_strain(g, ax, ay, az, sb);
+    box_force(t, ax, ay, az, fb);
+    box_hourglass(u, s6[0], s6[3], s6[5], hb);
+    double sc = 0, df = 0;
+    for (int k = 0; k < 6; ++k) { sc = std::max(sc, std::fabs(sr[k])); df = std::max(df, std::fabs(sr[k] - sb[k])); }
+    if (sc > 0) d[0] = std::max(d[0], df / sc);
+    sc = 0; df = 0;
+    for (int i = 0; i < 8; ++i) for (int k = 0; k < 3; ++k) { sc = std::max(sc, std::fabs(fg[i][k])); df = std::max(df, std::fabs(fg[i][k] - fb[i][k])); }
+    if (sc > 0) d[1] = std::max(d[1], df / sc);
+    sc = 0; df = 0;
+    for (int i = 0; i < 8; ++i) for (int k = 0; k < 3; ++k) { sc = std::max(sc, std::fabs(hg[i][k])); df = std::max(df, std::fabs(hg[i][k] - hb[i][k])); }
+    if (sc > 0) d[2] = std::max(d[2], df / sc);
+  }
+  *nBox = count;
+  for (int k = 0; k < 3; ++k) dev[k] = d[k];
   return 0;
 }

@@ -120,6 +120,11 @@ module eqdyna_cuda_iface
             type(c_ptr), value :: handle
             integer(c_int64_t), intent(out) :: n_regular, n_pml, n_pairs, launches
         end function
+        integer(c_int) function eqd_get_box_counts(handle, n_regular_box, n_pml_box) bind(C, name='eqd_get_box_counts')
+            import :: c_int, c_ptr, c_int64_t
+            type(c_ptr), value :: handle
+            integer(c_int64_t), intent(out) :: n_regular_box, n_pml_box
+        end function
         integer(c_int) function eqd_get_timing(handle, ms_slots) bind(C, name='eqd_get_timing')
             import :: c_int, c_ptr, c_double
             type(c_ptr), value :: handle
@@ -142,6 +147,15 @@ module eqdyna_cuda_iface
             integer(c_int32_t), value :: Nn, Ne
             integer(c_int32_t) :: nodeElemIdRelation(8,*), elemTypeArr(*), numOfDofPerNodeArr(*)
             integer(c_int64_t), intent(out) :: stats(24)
+        end function
+        integer(c_int) function eqd_box_check(Nn, Ne, meshCoor, nodeElemIdRelation, elemTypeArr, eleshp, phi, ss, nBox, dev) &
+                bind(C, name='eqd_box_check')
+            import :: c_int, c_int32_t, c_int64_t, c_double
+            integer(c_int32_t), value :: Nn, Ne
+            real(c_double) :: meshCoor(3,*), eleshp(3,8,*), phi(8,4,*), ss(6,*)
+            integer(c_int32_t) :: nodeElemIdRelation(8,*), elemTypeArr(*)
+            integer(c_int64_t), intent(out) :: nBox
+            real(c_double), intent(out) :: dev(3)
         end function
     end interface
 end module eqdyna_cuda_iface

@@ -23,6 +23,7 @@ EXPORTS = [
     "eqd_create", "eqd_destroy", "eqd_last_error", "eqd_set_mesh", "eqd_set_elem_ops", "eqd_compute_elem_ops", "eqd_set_nodal",
     "eqd_set_fault", "eqd_set_halo", "eqd_set_stations", "eqd_get_unique_id", "eqd_set_comm", "eqd_sum_shared",
     "eqd_run", "eqd_run_group", "eqd_fetch", "eqd_get_counts", "eqd_get_timing", "eqd_set_option", "eqd_plan_check",
+    "eqd_box_check", "eqd_get_box_counts",
 ]
 
 _lib = None
@@ -62,8 +63,10 @@ def lib():
         L.eqd_fetch.argtypes = [vp, i32, vp, i64]
         L.eqd_get_counts.argtypes = [vp] + [C.POINTER(i64)] * 4
         L.eqd_get_timing.argtypes = [vp, C.POINTER(C.c_double)]
+        L.eqd_get_box_counts.argtypes = [vp] + [C.POINTER(i64)] * 2
         L.eqd_set_option.argtypes = [vp, cp, i32]
         L.eqd_plan_check.argtypes = [i32, i32, vp, vp, vp, vp]
+        L.eqd_box_check.argtypes = [i32, i32] + [vp] * 8
         _lib = L
     return _lib
 
@@ -93,6 +96,20 @@ def plan_check(view):
         raise StepError(EQD_ERR_ARG, "tile planner invariant violated (eqd_tiles.cu:%d)" % rc)
     keys = ("tiles", "elements", "slots", "node_slots", "max_tile_nodes", "max_colours", "multi_colour_tiles", "grid")
     return {name: dict(zip(keys, (int(x) for x in st[8 * c:8 * c + 8]))) for c, name in enumerate(("reg", "regx", "pml"))}
+
+
+def box_check(view):
+    """Compare the closed-form operators of axis-aligned hexahedra (option "box", eqd_box.h)
+    with the host's precomputed eleshp / phi / ss on every box element of a sub-domain
+    (host only, no GPU).  Returns (box elements, [strain, force, hourglass] relative deviation)."""
+    r = view.raw
+    n = C.c_int64()
+    dev = np.zeros(3)
+    rc = lib().eqd_box_check(r.Nn, r.Ne, _ptr(view.meshCoor), _ptr(view.nodeElemIdRelation), _ptr(view.elemTypeArr),
+                             _ptr(view.eleshp), _ptr(view.phi), _ptr(view.ss), C.byref(n), _ptr(dev))
+    if rc:
+        raise StepError(EQD_ERR_ARG, "eqd_box_check: bad input (eqd_tiles.cu:%d)" % rc)
+    return n.value, dev
 
 
 class Domain:
@@ -159,6 +176,12 @@ class Domain:
         a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
         lib().eqd_get_counts(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
         return {"regular": a.value, "pml": b.value, "pairs": c.value, "launches": d.value}
+
+    def box_counts(self):
+        """Elements swept with closed-form box operators (option "box"), after the first run."""
+        a, b = C.c_int64(), C.c_int64()
+        lib().eqd_get_box_counts(self._h, C.byref(a), C.byref(b))
+        return {"regular": a.value, "pml": b.value}
 
     def timing(self):
         t = (C.c_double * T_NSLOTS)()

@@ -170,13 +170,19 @@ int eqd_fetch(eqd_handle* h, int32_t which, void* dst, int64_t dst_bytes);
 /* algorithmic counters for the benchmark: elements by type, kernel launches */
 int eqd_get_counts(const eqd_handle* h, int64_t* n_regular, int64_t* n_pml,
                    int64_t* n_pairs, int64_t* launches);
+/* elements swept with closed-form box operators (option "box"); valid after the first run */
+int eqd_get_box_counts(const eqd_handle* h, int64_t* n_regular_box, int64_t* n_pml_box);
 int eqd_get_timing(const eqd_handle* h, double* ms_slots /*[EQD_T_NSLOTS]*/);
 /* options: "timing" 1 = CUDA-event timing of every phase (2 = also reset the
  * accumulated slots and the launch counter); "overlap" -1 auto (default) / 0 serial
  * step / 1 halo + fault solver on a second stream under the next bulk node update /
  * 2 also rank-face tiles first; "reserve" CTAs left free by the overlapped interior
  * sweep (mode 2); "node_variant" launch-bounds variant of the node update; and,
- * before eqd_set_mesh only, the tile bricks "reg_bx/bz/by", "pml_bx/bz/by".
+ * before eqd_set_mesh only, the tile bricks "reg_bx/bz/by", "pml_bx/bz/by";
+ * "box" (before the first eqd_run / eqd_sum_shared) 0 off (default) / 1 regular
+ * classes / 2 also PML: tiles whose elements are all axis-aligned hexahedra
+ * (exact test on meshCoor) use eleshp = sign*a_d, phi = ha, ss = diag in closed
+ * form and stream 15 instead of 71 (PML: 33 instead of 89) operator rows.
  * Unknown keys return 4.  See DESIGN.md sections 3-4.                          */
 int eqd_set_option(eqd_handle* h, const char* key, int32_t value);
 
@@ -189,6 +195,16 @@ int eqd_set_option(eqd_handle* h, const char* key, int32_t value);
 int eqd_plan_check(int32_t Nn, int32_t Ne, const int32_t* nodeElemIdRelation,
                    const int32_t* elemTypeArr, const int32_t* numOfDofPerNodeArr,
                    int64_t* stats);
+
+/* Host-only check of the closed-form operators the regular tile kernel uses on
+ * axis-aligned hexahedra under eqd_set_option("box", 1) (no GPU needed): for every
+ * element whose eight nodes form an exact box in meshCoor, the strain, B^T t
+ * forces (calcElemKU.f90:44-60,175-189) and hourglass forces (hrglss.f90:20-54)
+ * of a pseudo-random field are computed from eleshp / phi / ss and in closed
+ * form.  dev[3] = largest relative deviations, *nBox = box elements.  0 = ok. */
+int eqd_box_check(int32_t Nn, int32_t Ne, const double* meshCoor, const int32_t* nodeElemIdRelation,
+                  const int32_t* elemTypeArr, const double* eleshp, const double* phi, const double* ss,
+                  int64_t* nBox, double* dev);
 
 #ifdef __cplusplus
 }

@@ -158,3 +158,22 @@ def test_fortran_interface_covers_the_abi():
     # the ctypes mirror used by the tests has the same order too
     from eqdyna_b200.host import EqdParams
     assert [n for n, _ in EqdParams._fields_] == cfields
+
+
+@pytest.mark.parametrize("case,frac", [("test.tpv104", 1.0), ("test.tpv10", 0.5), ("test.tpv36", 0.99), ("test.drv.a6", 0.1)])
+def test_box_operators(case, frac):
+    """Closed-form operators of axis-aligned hexahedra (eqd_box.h, option "box" of the tile
+    kernels) against the host's eleshp / phi / ss: strain, B^T t forces and hourglass forces of
+    a pseudo-random field agree to rounding on every element that passes the exact box test."""
+    from eqdyna_b200 import device
+    w = parity.build_world(case, (1, 1, 1), 2)
+    v = w.view(0)
+    n, dev = device.box_check(v)
+    assert n >= frac * v.Ne and n <= v.Ne
+    if case == "test.tpv104":
+        assert n == v.Ne                                   # planar vertical fault: the whole mesh is rectilinear
+    assert np.all(dev < 1e-12), dev
+    # wedges never pass
+    wed = np.isin(v.elemTypeArr, (11, 12))
+    assert n <= v.Ne - int(wed.sum())
+    w.close()
