@@ -225,6 +225,7 @@ struct eqd_handle {
   long launches = 0;
   bool timing = false;
   int optNodeVariant = 4;
+  int optBoxCompact = 0;   // 1: classes whose tiles are ALL box tiles use the compact stage buffer (three CTAs per SM)
   int optBox = 0;   // closed-form operators on all-box tiles (eqd_box.h): 1 = regular classes, 2 = also PML; set before the first eqd_run
   int optTile[2][3] = {{kRegBrick[0], kRegBrick[1], kRegBrick[2]}, {kPmlBrick[0], kPmlBrick[1], kPmlBrick[2]}};  // brick of a regular / PML tile in elements along x, z, y (before eqd_set_mesh)
   double tms[EQD_T_NSLOTS] = {0};
@@ -364,6 +365,7 @@ ElemArgs eqd_handle::elemArgs(int c) const {
   A.expdttv = p.tv != 0.0 ? std::exp(-p.dt / p.tv) : 0.0;
   A.kapa_hg = p.kapa_hg;
   A.tileBox = C.tileBox.n ? C.tileBox.p : nullptr;
+  A.allBox = (optBoxCompact && C.tileBox.n && C.nBoxElems == C.n) ? 1 : 0;
   return A;
 }
 
@@ -1699,6 +1701,7 @@ int eqd_set_option(eqd_handle* h, const char* key, int32_t value) {
       }
   }
   if (!strcmp(key, "node_variant")) { h->optNodeVariant = value; return EQD_OK; }
+  if (!strcmp(key, "box_compact")) { h->optBoxCompact = value != 0; return EQD_OK; }
   if (!strcmp(key, "box")) {
     if (h->finalized) { h->err = "eqd_set_option: box must be set before the first eqd_run / eqd_sum_shared"; return EQD_ERR_ARG; }
     h->optBox = value < 0 ? 0 : value > 2 ? 2 : value;

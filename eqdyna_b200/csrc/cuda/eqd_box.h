@@ -31,6 +31,11 @@ EQD_HD constexpr bool box_row(int r) {
   return r == BOX_AX || r == BOX_AY || r == BOX_AZ || r == BOX_SS0 || r == BOX_SS3 || r == BOX_SS5 || r >= BOX_FIRST_SCALAR;
 }
 
+// slot of row r in a stage buffer that holds only the box rows
+EQD_HD constexpr int box_slot(int r) {
+  return r == BOX_AX ? 0 : r == BOX_AY ? 1 : r == BOX_AZ ? 2 : r == BOX_SS0 ? 3 : r == BOX_SS3 ? 4 : r == BOX_SS5 ? 5 : r - BOX_FIRST_SCALAR + 6;
+}
+
 // corner signs of calcLocalShapeFunc.f90:19-25: true = +1
 EQD_HD constexpr bool box_px(int i) { return ((i ^ (i >> 1)) & 1) != 0; }  // - + + - - + + -
 EQD_HD constexpr bool box_py(int i) { return ((i >> 1) & 1) != 0; }        // - - + + - - + +

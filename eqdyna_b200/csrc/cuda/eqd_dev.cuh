@@ -101,6 +101,7 @@ struct ElemArgs {
   const double* vel; const double* disp; int NnS;
   double dt, rdampk, rdampm, w, bodyz, ccosphi, sinphi, expdttv, kapa_hg;
   const uint8_t* tileBox;  // per tile in launch order: 1 = every element is an axis-aligned hexahedron (eqd_box.h); null = off
+  int allBox;              // 1: every tile of the class is a box tile and the compact stage buffer was asked for ("box_compact")
 };
 
 struct FaultArgs {

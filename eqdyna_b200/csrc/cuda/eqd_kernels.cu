@@ -415,8 +415,11 @@ __device__ __forceinline__ const double* reg_row_src(const ElemArgs& A, int r) {
 // BOX: tiles flagged in A.tileBox hold only axis-aligned hexahedra; their shape
 // derivatives, hourglass vectors and hourglass stiffness are used in closed form
 // (eqd_box.h) and only BOX_ROWS of the RR_ROWS operator rows are streamed.
-template <bool PLASTIC, bool QMODE, bool BODY, bool SPLIT, int CHG, bool BOX>
-__global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
+// BOX == 1: per-tile flag (meshes with warped regions); BOX == 2: every tile of the
+// launch is a box tile -- the stage buffer holds only the BOX_ROWS rows, so three
+// CTAs fit an SM (A.allBox, option "box_compact").
+template <bool PLASTIC, bool QMODE, bool BODY, bool SPLIT, int CHG, int BOX>
+__global__ void __launch_bounds__(2 * EQD_STAGE, BOX == 2 ? 3 : 2) k_tile_reg(ElemArgs A) {
   extern __shared__ __align__(128) unsigned char smraw[];
   constexpr int SE = EQD_STAGE;
   constexpr int NT = 2 * SE;
@@ -432,8 +435,10 @@ __global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
   const double dt = A.dt, rdampk = A.rdampk;
   uint64_t* bar = (uint64_t*)smraw;                             // operator stage landed
   uint64_t* barN = bar + 1;                                     // node-id list of the next tile landed
-  double* ops = (double*)(smraw + 128);                         // [RR_ROWS][SE]
-  uint16_t* slc = (uint16_t*)(ops + RR_ROWS * SE);              // [8][SE]
+  constexpr int NROWS = BOX == 2 ? (int)BOX_ROWS : (int)RR_ROWS;
+#define ISBOX(flag) (BOX == 2 || (BOX == 1 && (flag)))
+  double* ops = (double*)(smraw + 128);                         // [NROWS][SE]
+  uint16_t* slc = (uint16_t*)(ops + NROWS * SE);                // [8][SE]
   int* tnS = (int*)(slc + 8 * SE);                              // [LS] node ids of the tile whose nodes are gathered next
   double* sv = (double*)(tnS + LS);                             // [3][LS] velocity
   double* sl = sv + 3 * LS;                                     // [3][LS] d + rdampk*v
@@ -442,9 +447,9 @@ __global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
   auto request = [&](const int4& rec, int base, bool bx) {
     // one thread per row; sizes are whole 32-element groups (the class SoA is padded)
     const int cnt = min(SE, (TR_NE(rec) - base + 31) & ~31);
-    if (tid == 0) mbar_expect_tx(bar, (uint32_t)(cnt * ((BOX && bx ? (int)BOX_ROWS : (int)RR_ROWS) * 8 + 8 * 2)));
+    if (tid == 0) mbar_expect_tx(bar, (uint32_t)(cnt * ((ISBOX(bx) ? (int)BOX_ROWS : (int)RR_ROWS) * 8 + 8 * 2)));
     __syncwarp();
-    if (tid < RR_ROWS) { if (!(BOX && bx) || box_row(tid)) bulk_g2s(ops + tid * SE, reg_row_src(A, tid) + TR_E0(rec) + base, cnt * 8, bar); }
+    if (tid < RR_ROWS) { if (!ISBOX(bx) || box_row(tid)) bulk_g2s(ops + (BOX == 2 ? box_slot(tid) : tid) * SE, reg_row_src(A, tid) + TR_E0(rec) + base, cnt * 8, bar); }
     else if (tid < RR_ROWS + 8) bulk_g2s(slc + (tid - RR_ROWS) * SE, A.lconn + (size_t)(tid - RR_ROWS) * S + TR_E0(rec) + base, cnt * 2, bar);
   };
   auto request_ids = [&](const int4& rec) {
@@ -490,10 +495,10 @@ __global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
   // software pipeline over this CTA's tiles: rc = tile being swept, rn = the next
   // one (its operators and nodes are requested while rc's forces are assembled)
   int4 rc = __ldg(A.tileRec + tnext);
-  bool bc = BOX && __ldg(A.tileBox + tnext) != 0;   // CTA-uniform
+  bool bc = BOX == 1 && __ldg(A.tileBox + tnext) != 0;   // CTA-uniform
   tnext += gridDim.x;
   int4 rn = tnext < tEnd ? __ldg(A.tileRec + tnext) : zero4;
-  bool bn = BOX && tnext < tEnd && __ldg(A.tileBox + tnext) != 0;
+  bool bn = BOX == 1 && tnext < tEnd && __ldg(A.tileBox + tnext) != 0;
   if (tid == 0) { mbar_init(bar, 1); mbar_init(barN, 1); }
   __syncthreads();
   request(rc, 0, bc);
@@ -516,7 +521,7 @@ __global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
   while (true) {
   const bool more = tnext < tEnd;
   const int4 rnn = (tnext + (int)gridDim.x < tEnd) ? __ldg(A.tileRec + tnext + gridDim.x) : zero4;
-  const bool bnn = BOX && (tnext + (int)gridDim.x < tEnd) && __ldg(A.tileBox + tnext + gridDim.x) != 0;
+  const bool bnn = BOX == 1 && (tnext + (int)gridDim.x < tEnd) && __ldg(A.tileBox + tnext + gridDim.x) != 0;
   if (more) request_ids(rn);   // tnS is free: rc's nodes are already in sv/sl
   const int ne = TR_NE(rc), NC = TR_NC(rc);
   for (int base = 0; base < ne; base += SE) {
@@ -530,12 +535,12 @@ __global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
     if (act) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) lc[i] = slc[i * SE + lane];
-#define OP(r) ops[(r) * SE + lane]
+#define OP(r) ops[(BOX == 2 ? box_slot(r) : (r)) * SE + lane]
       if (role == 0) {
         // ---------------- constitutive part: calcElemKU.f90
         double sr[6] = {0, 0, 0, 0, 0, 0}, sn[6] = {0, 0, 0, 0, 0, 0};
         double body[BODY ? 24 : 1];
-        if (BOX && bc) {
+        if (ISBOX(bc)) {
           // axis-aligned hexahedra: eleshp(d,i) = sign_d(i)*a_d (eqd_box.h)
           double u[8][3], g[3][3];
 #pragma unroll
@@ -653,7 +658,7 @@ __global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
         double t[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) t[i] = temp * (sg[i] + rdampk * rate[i]);
-        if (BOX && bc) {
+        if (ISBOX(bc)) {
           box_force(t, OP(BOX_AX), OP(BOX_AY), OP(BOX_AZ), f);
           if (BODY) {
 #pragma unroll
@@ -674,7 +679,7 @@ __global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
       } else {
         // ---------------- hourglass part: hrglss.f90
         if (CHG == 1) {
-          if (BOX && bc) {
+          if (ISBOX(bc)) {
             // phi = ha, ss diagonal (eqd_box.h)
             double l[8][3];
 #pragma unroll
@@ -800,6 +805,7 @@ __global__ void __launch_bounds__(2 * EQD_STAGE, 2) k_tile_reg(ElemArgs A) {
   rc = rn; rn = rnn; tnext += gridDim.x;
   bc = bn; bn = bnn;
   }
+#undef ISBOX
 }
 
 // ----------------------------------------------------------------------------
@@ -1629,14 +1635,22 @@ static void launch_reg_chg(const ElemArgs& A, int chg, cudaStream_t s) {
   const size_t sm = tile_smem_bytes(CLS_REG, Q, A.LS);
   // persistent CTAs, two per SM, each walking tiles blockIdx.x, +gridDim.x, ...
   const int grid = std::min(ntiles, A.maxGrid > 0 ? A.maxGrid : 2 * sm_count());
-  if (A.tileBox) {
-    // closed-form operators on the tiles flagged as all-box (eqd_set_option "box")
-    if (chg == 2) tile_launch(k_tile_reg<PL, Q, BODY, SPLIT, 2, true>, A, grid, 2 * EQD_STAGE, sm, s);
-    else tile_launch(k_tile_reg<PL, Q, BODY, SPLIT, 1, true>, A, grid, 2 * EQD_STAGE, sm, s);
+  if (A.tileBox && A.allBox) {
+    // every tile is a box tile: compact stage buffer, three CTAs per SM (option "box_compact")
+    const size_t smc = sm - (size_t)(RR_ROWS - BOX_ROWS) * EQD_STAGE * sizeof(double);
+    const int gridc = std::min(ntiles, A.maxGrid > 0 ? A.maxGrid : 3 * sm_count());
+    if (chg == 2) tile_launch(k_tile_reg<PL, Q, BODY, SPLIT, 2, 2>, A, gridc, 2 * EQD_STAGE, smc, s);
+    else tile_launch(k_tile_reg<PL, Q, BODY, SPLIT, 1, 2>, A, gridc, 2 * EQD_STAGE, smc, s);
     return;
   }
-  if (chg == 2) tile_launch(k_tile_reg<PL, Q, BODY, SPLIT, 2, false>, A, grid, 2 * EQD_STAGE, sm, s);
-  else tile_launch(k_tile_reg<PL, Q, BODY, SPLIT, 1, false>, A, grid, 2 * EQD_STAGE, sm, s);
+  if (A.tileBox) {
+    // closed-form operators on the tiles flagged as all-box (eqd_set_option "box")
+    if (chg == 2) tile_launch(k_tile_reg<PL, Q, BODY, SPLIT, 2, 1>, A, grid, 2 * EQD_STAGE, sm, s);
+    else tile_launch(k_tile_reg<PL, Q, BODY, SPLIT, 1, 1>, A, grid, 2 * EQD_STAGE, sm, s);
+    return;
+  }
+  if (chg == 2) tile_launch(k_tile_reg<PL, Q, BODY, SPLIT, 2, 0>, A, grid, 2 * EQD_STAGE, sm, s);
+  else tile_launch(k_tile_reg<PL, Q, BODY, SPLIT, 1, 0>, A, grid, 2 * EQD_STAGE, sm, s);
 }
 template <bool SPLIT>
 static void launch_reg_split(const ElemArgs& A, bool plastic, bool q, bool body, int chg, cudaStream_t s) {
