@@ -59,7 +59,9 @@ int eqh_world_set_switch(eqh_world* w, const char* name, double value) {
     else if (n == "C_hg") w->in.C_hg = (int)value;
     else if (n == "kapa_hg") w->in.kapa_hg = value;
     else if (n == "rdampm") w->in.rdampm = value;
-    else if (n == "outputGroundMotion") w->in.outputGroundMotion = (int)value;
+    else if (n == "outputGroundMotion") w->in.outputGroundMotion = (int)value;   // before eqh_world_build: it sizes the sample arrays
+    else if (n == "outputFinalSurfDisp") w->in.outputFinalSurfDisp = (int)value;
+    else if (n == "output_plastic") w->in.output_plastic = (int)value;
     else throw std::runtime_error("eqh_world_set_switch: unknown switch " + n);
     if (w->in.C_elastic == 0 && w->in.C_Q == 1) throw std::runtime_error("Q model can only work with elastic code (stop 1001)");
   });
@@ -140,6 +142,10 @@ int eqh_get_view(eqh_world* w, int rank, eqh_view* v) {
     v->OffFaultStGramSCEC = s.OffFaultStGramSCEC.empty() ? nullptr : s.OffFaultStGramSCEC.data();
     v->hypoLog = s.hypoLog.data();
     v->onFaultTPHist = s.onFaultTPHist.empty() ? nullptr : s.onFaultTPHist.data();
+    v->gmHist = s.gmHist.empty() ? nullptr : s.gmHist.data();
+    v->srcEvolHist = s.srcEvolHist.empty() ? nullptr : s.srcEvolHist.data();
+    v->nGmSamples = &s.nGmSamples;
+    v->nGmAlloc = s.nGmAlloc;
   });
 }
 
@@ -151,6 +157,21 @@ int eqh_write_outputs(eqh_world* w, int rank, const char* out_dir) {
     eqh::write_onfault_stations(s, out_dir);
     eqh::write_offfault_stations(s, out_dir);
     eqh::write_frt(s, out_dir);
+    if (w->in.output_plastic == 1) eqh::write_plastic_strain(s, out_dir);
+    if (w->in.outputFinalSurfDisp == 1) eqh::write_final_surf_disp(s, out_dir);
+    // written while stepping / before it in the reference (driver.f90:30-33, eqdyna3d.f90:61)
+    eqh::write_surface_coor(s, out_dir);
+    eqh::write_gm(s, out_dir);
+    eqh::write_src_evol(s, out_dir);
+    if (s.compTimeSet) eqh::write_comp_time(s, out_dir);
+  });
+}
+
+int eqh_set_comp_time(eqh_world* w, int rank, const double* t10) {
+  return guarded([&] {
+    if (rank < 0 || rank >= (int)w->ranks.size() || !w->ranks[rank] || !t10) throw std::runtime_error("rank not built");
+    for (int k = 0; k < 10; ++k) w->ranks[rank]->compTime[k] = t10[k];
+    w->ranks[rank]->compTimeSet = true;
   });
 }
 

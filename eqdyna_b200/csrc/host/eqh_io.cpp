@@ -409,4 +409,93 @@ void write_offfault_stations(const RankState& s, const std::string& dir) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// The remaining writers of library_output.f90.  The reference opens most of these
+// with position='append' while it steps; here each file is written once, whole.
+namespace {
+FILE* open_rank_file(const RankState& s, const std::string& dir, const char* stem, const char* mode) {
+  std::string p = dir + "/" + stem + std::to_string(s.me);   // 'name'//mm, mm = trimmed rank id (eqdyna3d.f90:95-96)
+  FILE* f = std::fopen(p.c_str(), mode);
+  if (!f) throw std::runtime_error("cannot write " + p);
+  return f;
+}
+}  // namespace
+
+// find_surfaceNodeIdArr, library_output.f90:247-264: (1x,3e18.7e4) per surface node
+void write_surface_coor(const RankState& s, const std::string& dir) {
+  const CaseInput& in = *s.in;
+  if (!(in.outputGroundMotion == 1 || in.outputFinalSurfDisp == 1) || s.surface_nnode <= 0) return;
+  FILE* f = open_rank_file(s, dir, "surface_coor.txt", "w");
+  for (int i = 0; i < s.surface_nnode; ++i) {
+    const double* c = &s.meshCoor[3 * (size_t)(s.surfaceNodeIdArr[i] - 1)];
+    std::string line = " ";
+    for (int j = 0; j < 3; ++j) line += fortran_e(c[j], 18, 7, 4);
+    std::fprintf(f, "%s\n", line.c_str());
+  }
+  std::fclose(f);
+}
+
+// output_gm, library_output.f90:267-279: unformatted stream, velArr(1:3,node) of every
+// surface node, one block per sampled step
+void write_gm(const RankState& s, const std::string& dir) {
+  if (s.in->outputGroundMotion != 1 || s.surface_nnode <= 0) return;
+  FILE* f = open_rank_file(s, dir, "gm", "wb");
+  const size_t n = (size_t)3 * s.surface_nnode * s.nGmSamples;
+  if (n && std::fwrite(s.gmHist.data(), sizeof(double), n, f) != n) { std::fclose(f); throw std::runtime_error("short write: gm"); }
+  std::fclose(f);
+}
+
+// output_src_evol, library_output.f90:297-312: fric(47,i,1), i = 1..nftnd(1), per sampled step
+void write_src_evol(const RankState& s, const std::string& dir) {
+  if (s.in->outputGroundMotion != 1 || s.nftnd.empty() || s.nftnd[0] <= 0) return;
+  FILE* f = open_rank_file(s, dir, "src_evol", "wb");
+  const size_t n = (size_t)s.nftnd[0] * s.nGmSamples;
+  if (n && std::fwrite(s.srcEvolHist.data(), sizeof(double), n, f) != n) { std::fclose(f); throw std::runtime_error("short write: src_evol"); }
+  std::fclose(f);
+}
+
+// output_finalSurfDisp, library_output.f90:282-295
+void write_final_surf_disp(const RankState& s, const std::string& dir) {
+  if (s.in->outputFinalSurfDisp != 1 || s.surface_nnode <= 0) return;
+  FILE* f = open_rank_file(s, dir, "finalSurfDisp.txt", "w");
+  for (int i = 0; i < s.surface_nnode; ++i) {
+    const double* d = &s.dispArr[3 * (size_t)(s.surfaceNodeIdArr[i] - 1)];
+    std::string line = " ";
+    for (int j = 0; j < 3; ++j) line += fortran_e(d[j], 18, 7, 4);
+    std::fprintf(f, "%s\n", line.c_str());
+  }
+  std::fclose(f);
+}
+
+// output_plastic_strain, library_output.f90:221-244: elements with pstrain > 1e-4 whose
+// first node lies within |x| < 5 km, |y| < 2 km, |z| < 8 km: centroid, pstrain, 12 stress slots
+void write_plastic_strain(const RankState& s, const std::string& dir) {
+  if (s.in->output_plastic != 1) return;
+  FILE* f = nullptr;
+  for (int i = 0; i < s.totalNumOfElements; ++i) {
+    const int* c = &s.nodeElemIdRelation[8 * (size_t)i];
+    const double* x1 = &s.meshCoor[3 * (size_t)(c[0] - 1)];
+    if (!(s.pstrain[i] > 1.0e-4 && std::fabs(x1[0]) < 5.0e3 && std::fabs(x1[1]) < 2.0e3 && std::fabs(x1[2]) < 8.0e3)) continue;
+    if (!f) f = open_rank_file(s, dir, "pstr.txt", "w");   // the reference creates the file at the first hit
+    double sc[3] = {0.0, 0.0, 0.0};
+    for (int j = 0; j < 8; ++j)
+      for (int k = 0; k < 3; ++k) sc[k] = sc[k] + s.meshCoor[k + 3 * (size_t)(c[j] - 1)];
+    std::string line = " ";
+    for (int k = 0; k < 3; ++k) line += fortran_e(sc[k] / 8.0, 18, 7, 4);
+    line += fortran_e(s.pstrain[i], 18, 7, 4);
+    for (int j = 1; j <= 12; ++j) line += fortran_e(s.stressArr[(size_t)s.stressCompIndexArr[i] + j - 1], 18, 7, 4);
+    std::fprintf(f, "%s\n", line.c_str());
+  }
+  if (f) std::fclose(f);
+}
+
+// output_timeanalysis, library_output.f90:208-218: (1x,10e18.7e4,2i10)
+void write_comp_time(const RankState& s, const std::string& dir) {
+  FILE* f = open_rank_file(s, dir, "compTime", "w");
+  std::string line = " ";
+  for (int k = 0; k < 10; ++k) line += fortran_e(s.compTime[k], 18, 7, 4);
+  std::fprintf(f, "%s%10d%10d\n", line.c_str(), s.totalNumOfElements, s.totalNumOfEquations);
+  std::fclose(f);
+}
+
 }  // namespace eqh

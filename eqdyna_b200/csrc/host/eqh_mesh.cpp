@@ -696,6 +696,13 @@ void alloc_after_meshgen(const CaseInput& in, RankState& s) {
   s.dispArr.assign((size_t)3 * s.totalNumOfNodes, 0.0);
   s.hypoLog.assign((size_t)13 * in.nstep, 0.0);
   if (in.friclaw == 5) s.onFaultTPHist.assign((size_t)2 * s.nftmx * in.nstep * in.ntotft, 0.0);
+  s.nGmAlloc = 0; s.nGmSamples = 0;
+  s.gmHist.clear(); s.srcEvolHist.clear();
+  if (in.outputGroundMotion == 1) {   // one sample at every nt with mod(nt,10) == 1 (driver.f90:30)
+    s.nGmAlloc = in.nstep / 10 + 1;
+    s.gmHist.assign((size_t)3 * s.surface_nnode * s.nGmAlloc, 0.0);
+    s.srcEvolHist.assign((size_t)(s.nftnd.empty() ? 0 : s.nftnd[0]) * s.nGmAlloc, 0.0);
+  }
   s.idhist.clear();
   s.OffFaultStGramSCEC.clear();
   if (s.numOfOffFaultStCount > 0) {

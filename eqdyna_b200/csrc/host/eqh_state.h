@@ -112,6 +112,13 @@ struct RankState {
   std::vector<double> OffFaultStGramSCEC;        // (6*nOff+1,nstep)
   std::vector<double> hypoLog;   // (13,nstep)
   std::vector<double> onFaultTPHist;  // (2,nftmx,nstep,ntotft) only friclaw==5
+  // what output_gm / output_src_evol append to gm<me> / src_evol<me> every 10th step
+  // (driver.f90:30-33), kept in memory until eqh_write_outputs
+  std::vector<double> gmHist;       // (3,surface_nnode,nGmAlloc)
+  std::vector<double> srcEvolHist;  // (nftnd(1),nGmAlloc)
+  int nGmAlloc = 0, nGmSamples = 0;
+  double compTime[10] = {0};        // compTimeInSeconds(1:9), MPICommTimeInSeconds (library_output.f90:208-218)
+  bool compTimeSet = false;
   eqd_params params() const;
   const CaseInput* in = nullptr;
 };
@@ -121,6 +128,12 @@ void read_case(const std::string& dir, CaseInput& in);
 void write_frt(const RankState& s, const std::string& dir);
 void write_onfault_stations(const RankState& s, const std::string& dir);
 void write_offfault_stations(const RankState& s, const std::string& dir);
+void write_surface_coor(const RankState& s, const std::string& dir);
+void write_gm(const RankState& s, const std::string& dir);
+void write_src_evol(const RankState& s, const std::string& dir);
+void write_final_surf_disp(const RankState& s, const std::string& dir);
+void write_plastic_strain(const RankState& s, const std::string& dir);
+void write_comp_time(const RankState& s, const std::string& dir);
 // eqh_mesh.cpp
 void mesh4num(const CaseInput& in, RankState& s);
 void meshgen(const CaseInput& in, RankState& s);

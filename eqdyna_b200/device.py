@@ -126,6 +126,7 @@ class Domain:
         if rc:
             raise StepError(rc, "eqd_create failed (no CUDA device? see stderr)")
         self._keep = []
+        self._nt_done = 0
         for k, val in (options or {}).items():   # options that shape the upload (tile bricks)
             self.set_option(k, val)
         self._upload(view)
@@ -171,6 +172,7 @@ class Domain:
 
     def run(self, nt_begin, nt_end):
         self._check(lib().eqd_run(self._h, int(nt_begin), int(nt_end)))
+        self._nt_done = max(self._nt_done, int(nt_end))
 
     def counts(self):
         a, b, c, d = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
@@ -215,6 +217,14 @@ class Domain:
                 v.onFaultTPHist[...] = self.fetch(F_TPHIST, (2, r.nftmx, r.nstep, r.ntotft))
         if r.nOff:
             v.OffFaultStGramSCEC[...] = self.fetch(F_OFFFAULT_HIST, (6 * r.nOff + 1, r.nstep))
+        if v.params.outputGroundMotion == 1 and self._nt_done > 0:
+            # output_gm / output_src_evol samples: one per step with mod(nt,10) == 1 (driver.f90:30-33)
+            k = (self._nt_done - 1) // 10 + 1
+            if v.gmHist is not None and k <= v.nGmAlloc:
+                v.gmHist[:, :, :k] = self.fetch(F_GM, (3, r.nSurf, k))
+            if v.srcEvolHist is not None and k <= v.nGmAlloc:
+                v.srcEvolHist[:, :k] = self.fetch(F_SRC_EVOL, (int(v.nftnd[0]), k))
+            v.nGmSamples[0] = k
 
     def close(self):
         if self._h:
@@ -234,3 +244,5 @@ def run_group(domains, nt_begin, nt_end):
     rc = lib().eqd_run_group(arr, len(domains), int(nt_begin), int(nt_end))
     if rc:
         domains[0]._check(rc)
+    for d in domains:
+        d._nt_done = max(d._nt_done, int(nt_end))

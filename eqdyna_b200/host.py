@@ -54,6 +54,7 @@ class EqhView(C.Structure):
         ("idhist", c_i32p), ("anonfs", c_i32p), ("surfaceNodeIdArr", c_i32p),
         ("onFaultQuantHistSCECForm", c_f64p), ("OffFaultStGramSCEC", c_f64p), ("hypoLog", c_f64p),
         ("onFaultTPHist", c_f64p),
+        ("gmHist", c_f64p), ("srcEvolHist", c_f64p), ("nGmSamples", c_i32p), ("nGmAlloc", C.c_int32), ("pad2_", C.c_int32),
     ]
 
 
@@ -77,6 +78,7 @@ def lib():
         L.eqh_get_view.argtypes = [C.c_void_p, C.c_int, C.POINTER(EqhView)]
         L.eqh_write_outputs.argtypes = [C.c_void_p, C.c_int, C.c_char_p]
         L.eqh_release_operators.argtypes = [C.c_void_p, C.c_int]
+        L.eqh_set_comp_time.argtypes = [C.c_void_p, C.c_int, c_f64p]
         _lib = L
     return _lib
 
@@ -145,6 +147,11 @@ class View:
         self.OffFaultStGramSCEC = _np(v.OffFaultStGramSCEC, (6 * v.nOff + 1, v.nstep), f64)
         self.hypoLog = _np(v.hypoLog, (13, v.nstep), f64)
         self.onFaultTPHist = _np(v.onFaultTPHist, (2, v.nftmx, v.nstep, v.ntotft), f64)
+        # samples of output_gm / output_src_evol (every step with mod(nt,10) == 1)
+        self.nGmAlloc = v.nGmAlloc
+        self.gmHist = _np(v.gmHist, (3, v.nSurf, v.nGmAlloc), f64) if v.nGmAlloc and v.nSurf else None
+        self.srcEvolHist = _np(v.srcEvolHist, (int(self.nftnd[0]), v.nGmAlloc), f64) if v.nGmAlloc and int(self.nftnd[0]) else None
+        self.nGmSamples = _np(v.nGmSamples, (1,), i32)
 
 
 class World:
@@ -194,6 +201,13 @@ class World:
         rc = lib().eqh_write_outputs(self._h, rank, os.fsencode(out_dir))
         if rc:
             raise RuntimeError("eqh_write_outputs: " + lib().eqh_last_error().decode())
+
+    def set_comp_time(self, rank, t10):
+        """compTimeInSeconds(1:9) + MPICommTimeInSeconds for compTime<me> (library_output.f90:208-218)."""
+        a = (C.c_double * 10)(*[float(x) for x in t10])
+        rc = lib().eqh_set_comp_time(self._h, rank, a)
+        if rc:
+            raise RuntimeError("eqh_set_comp_time: " + lib().eqh_last_error().decode())
 
     def release_operators(self, rank):
         lib().eqh_release_operators(self._h, rank)

@@ -71,6 +71,13 @@ typedef struct eqh_view {
   double* OffFaultStGramSCEC;
   double* hypoLog;
   double* onFaultTPHist;
+  /* samples of output_gm / output_src_evol (driver.f90:30-33): velArr of the surface
+   * nodes and fric(47,:,1) at every step with mod(nt,10) == 1, in file order      */
+  double* gmHist;        /* (3,nSurf,nGmAlloc)     */
+  double* srcEvolHist;   /* (nftnd(1),nGmAlloc)    */
+  int32_t* nGmSamples;   /* samples taken so far   */
+  int32_t nGmAlloc;      /* nstep/10 + 1, 0 = outputGroundMotion off */
+  int32_t pad2_;
 } eqh_view;
 
 /* Read the case directory (b*.txt + on_fault_vars_input.bin [+ rough geometry]).
@@ -90,8 +97,14 @@ int eqh_world_size(const eqh_world* w);
 int eqh_world_build(eqh_world* w, int rank);
 int eqh_world_sum_shared(eqh_world* w);
 int eqh_get_view(eqh_world* w, int rank, eqh_view* out);
-/* replace arrays the device summed at init (one-rank-per-process path) */
+/* What eqdyna3d.f90:75-84 and driver.f90:30-33 write for one rank, in the reference's
+ * formats (library_output.f90): faultst*.txt, body*.txt, frt.txt<me>; with
+ * outputGroundMotion gm<me>, src_evol<me> (raw float64 streams) and surface_coor.txt<me>;
+ * with outputFinalSurfDisp finalSurfDisp.txt<me>; with output_plastic pstr.txt<me>;
+ * compTime<me> once eqh_set_comp_time supplied the ten timings.                      */
 int eqh_write_outputs(eqh_world* w, int rank, const char* out_dir);
+/* compTimeInSeconds(1:9) and MPICommTimeInSeconds of output_timeanalysis (library_output.f90:208-218) */
+int eqh_set_comp_time(eqh_world* w, int rank, const double* t10);
 /* free the big element-operator arrays of a rank once they live on the device */
 int eqh_release_operators(eqh_world* w, int rank);
 

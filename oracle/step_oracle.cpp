@@ -852,6 +852,24 @@ void faulting(Ctx& c) {
     for (int i = 1; i <= v.nftnd[ift]; ++i) fault_pair(c, ift, i, &garbage);
 }
 
+// driver.f90:30-33 -> output_gm, output_src_evol (library_output.f90:267-279,297-312): what the
+// reference appends to gm<me> / src_evol<me> at every step with mod(nt,10) == 1, kept in the
+// host's sample arrays (the host writes the files, eqh_write_outputs)
+void sample_gm(Ctx& c) {
+  eqh_view& v = *c.v;
+  if (v.params.outputGroundMotion != 1 || c.nt % 10 != 1 || !v.nGmSamples) return;
+  const int k = *v.nGmSamples;
+  if (k >= v.nGmAlloc) return;
+  if (v.gmHist)
+    for (int i = 0; i < v.nSurf; ++i) {
+      const int node = v.surfaceNodeIdArr[i];
+      for (int j = 0; j < 3; ++j) v.gmHist[j + 3 * ((size_t)i + (size_t)v.nSurf * k)] = v.velArr[j + 3 * (size_t)(node - 1)];
+    }
+  if (v.srcEvolHist && v.nftnd[0] > 0)
+    for (int i = 0; i < v.nftnd[0]; ++i) v.srcEvolHist[(size_t)i + (size_t)v.nftnd[0] * k] = v.fric[46 + 100 * (size_t)i];
+  *v.nGmSamples = k + 1;
+}
+
 }  // namespace
 
 extern "C" {
@@ -889,7 +907,7 @@ int orc_run(eqh_view* views, int nranks, int nt_begin, int nt_end, double* time_
       faulting(c);
       eqh_view& v = *c.v;
       for (int k = 0; k < v.Neq; ++k) v.nodalForceArr[k] = v.nodalForceArr[k] / v.nodalMassArr[k];
-      // output_gm / output_src_evol (driver.f90:30-33) are host file appends; not part of the oracle state
+      sample_gm(c);
     }
   }
   *time_elapsed = ctx[0].timeElapsed;
@@ -934,6 +952,7 @@ int orc_step_post(eqh_view* v, int nt, double time_elapsed) {
   if (v->params.friclaw == 5) thermop(c);
   faulting(c);
   for (int k = 0; k < v->Neq; ++k) v->nodalForceArr[k] = v->nodalForceArr[k] / v->nodalMassArr[k];
+  sample_gm(c);
   return 0;
 }
 
