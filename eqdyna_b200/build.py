@@ -145,7 +145,11 @@ def build_exe(force=False):
 
 
 def build_all(force=False):
-    return {"host": build_host(force), "cuda": build_cuda(force), "oracle": build_oracle(force)}
+    out = {"host": build_host(force), "cuda": build_cuda(force), "oracle": build_oracle(force)}
+    exe = build_exe(force)   # standalone driver (eqdyna_host <case_dir>): links the two libraries above
+    if exe:
+        out["exe"] = exe
+    return out
 
 
 if __name__ == "__main__":

@@ -177,3 +177,24 @@ def test_box_operators(case, frac):
     wed = np.isin(v.elemTypeArr, (11, 12))
     assert n <= v.Ne - int(wed.sum())
     w.close()
+
+
+def test_standalone_driver_fails_loudly_without_a_gpu(tmp_path):
+    """eqdyna_host (eqdyna_b200/csrc/host/eqdyna_host_main.cpp), the compiled counterpart of
+    driver_cuda.f90: builds the sub-domains, then must stop with the CUDA error code -- not
+    fall back to any CPU path -- when no device is visible."""
+    import subprocess
+    import torch
+    from eqdyna_b200 import build, cases
+    exe = build.build_exe()
+    assert exe and os.path.exists(exe)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([exe, cases.materialize("test.tpv8"), "-nstep", "2", "-o", str(tmp_path / "out")],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    assert r.returncode == 3, (r.returncode, r.stderr)
+    assert "no CPU path" in r.stderr
+    assert "4 sub-domain(s), 235008 elements" in r.stdout
+    assert not any(f.startswith("frt") for f in os.listdir(str(tmp_path / "out")))
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 4 and "usage" in r.stderr
