@@ -217,7 +217,7 @@ struct eqd_handle {
   DevBuf<int> dSpecialA, dSpecialB;  // special nodes on active rank faces | the others (split-node pairs)
   int nSpecialA = 0, nSpecialB = 0;
   int optOverlap = -1, optReserve = 8, smCount = 148;  // overlap -1 = auto: 1 with rank neighbours, else 0
-  std::unique_ptr<StagedCopy> stage;  // pinned staging of the set-up uploads, dropped once the run starts
+  std::unique_ptr<StagedCopy> stage;  // pinned staging of the set-up uploads (and of large eqd_fetch reads); small sub-domains drop it once the run starts
   // run state
   bool meshSet = false, opsSet = false, nodalSet = false, faultSet = false, finalized = false;
   int hostNt = 0;
@@ -560,8 +560,12 @@ void finalize(eqd_handle* h) {
   // cudaMemset / cudaMemcpy above ran on the legacy stream, which does not order
   // against the non-blocking step stream
   CK(cudaDeviceSynchronize());
-  if (t_stage == h->stage.get()) { t_stage = nullptr; t_stageStream = nullptr; }  // finalize may run inside a guarded call
-  h->stage.reset();
+  // small sub-domains give their pinned staging buffers back; large ones keep them for the staged
+  // reads of eqd_fetch (re-pinning 256 MB costs more than the reads)
+  if ((size_t)h->Nn * 3 * sizeof(double) < (64u << 20)) {
+    if (t_stage == h->stage.get()) { t_stage = nullptr; t_stageStream = nullptr; }  // finalize may run inside a guarded call
+    h->stage.reset();
+  }
   h->finalized = true;
 }
 
@@ -1086,16 +1090,17 @@ void upload_elem_state(eqd_handle* h, DevBuf<int>& dCode, const double* eleporep
   for (int c = 0; c < 3; ++c) {
     ElemClass& C = h->cls[c];
     if (!C.n) continue;
-    std::vector<double> sg((size_t)C.nstress * C.S, 0.0), qm;
-    if (h->qmode && c != CLS_PML) qm.assign(6 * (size_t)C.S, 0.0);
+    // first touched inside the parallel loop (no serial zero fill of ~1 GB); padding slots get zeros there
+    raw_vector<double> sg((size_t)C.nstress * C.S), qm;
+    if (h->qmode && c != CLS_PML) qm.resize(6 * (size_t)C.S);
     std::vector<char> badv(1, 0);
     parallel_range((size_t)C.S, [&](size_t sb, size_t se) {
       for (size_t s = sb; s < se; ++s) {
-        if (C.refId[s] < 0) continue;
-        const int base = h->stressIdx[C.refId[s]];
-        if (!(base >= 0 && base + (c == CLS_PML ? 21 : 12) <= h->sizeStress)) { badv[0] = 1; continue; }
-        for (int k = 0; k < C.nstress; ++k) sg[(size_t)k * C.S + s] = stressArr[base + k];
-        if (!qm.empty()) for (int k = 0; k < 6; ++k) qm[(size_t)k * C.S + s] = stressArr[base + 6 + k];
+        const int base = C.refId[s] < 0 ? -1 : h->stressIdx[C.refId[s]];
+        const bool ok = base >= 0 && base + (c == CLS_PML ? 21 : 12) <= h->sizeStress;
+        if (C.refId[s] >= 0 && !ok) badv[0] = 1;
+        for (int k = 0; k < C.nstress; ++k) sg[(size_t)k * C.S + s] = ok ? stressArr[base + k] : 0.0;
+        if (!qm.empty()) for (int k = 0; k < 6; ++k) qm[(size_t)k * C.S + s] = ok ? stressArr[base + 6 + k] : 0.0;
       }
     });
     need(!badv[0], "eqd_set_elem_ops: stress index out of range");
@@ -1252,7 +1257,10 @@ int eqd_set_nodal(eqd_handle* h, const double* nodalMassArr, const double* fnms,
       h->massH.assign(Nn, 1.0);
       h->massFromDevice = false;
     }
-    std::vector<double> vel(3 * NS, 0.0), disp(3 * NS, 0.0), v1p(12 * PS, 0.0), acc;
+    // first touched inside the parallel loops below (no serial zero fill of ~1 GB)
+    raw_vector<double> vel(3 * NS), disp(3 * NS), v1p(12 * PS);
+    std::vector<double> acc;
+    parallel_range(12 * PS, [&](size_t b, size_t e) { std::fill(v1p.begin() + b, v1p.begin() + e, 0.0); });
     bool anyAcc = false;
     if (nodalForceArr) {
       std::vector<char> any(1, 0);
@@ -1263,10 +1271,13 @@ int eqd_set_nodal(eqd_handle* h, const double* nodalMassArr, const double* fnms,
     }
     if (anyAcc) acc.assign(3 * NS + 12 * PS, 0.0);
     std::vector<char> badv(1, 0);
-    parallel_range((size_t)Nn, [&](size_t nb, size_t ne) {
+    parallel_range(NS, [&](size_t nb, size_t ne) {
       for (size_t n = nb; n < ne; ++n) {
-        const int kind = EQD_INFO_KIND(h->info[n]);
-        if (kind == KIND_FIXED) continue;
+        const int kind = n < (size_t)Nn ? EQD_INFO_KIND(h->info[n]) : KIND_FIXED;
+        if (kind == KIND_FIXED) {   // fixed nodes and the padding of the rows stay at rest
+          for (int j = 0; j < 3; ++j) { vel[j * NS + n] = 0.0; disp[j * NS + n] = 0.0; }
+          continue;
+        }
         const int st = h->eqStart[n], nd = h->ndof[n];
         if (!devMass) {
           const double m = nodalMassArr[h->eqIdx[st] - 1];
@@ -1553,10 +1564,31 @@ int eqd_fetch(eqd_handle* h, int32_t which, void* dst, int64_t dst_bytes) {
     switch (which) {
       case EQD_F_DISP: case EQD_F_VEL: {
         want(3 * (size_t)Nn);
-        std::vector<double> v = (which == EQD_F_DISP ? h->dDisp : h->dVel).download();
-        parallel_range((size_t)Nn, [&](size_t b, size_t e) {
-          for (size_t n = b; n < e; ++n) for (int j = 0; j < 3; ++j) out[j + 3 * n] = v[j * NS + n];
-        });
+        const double* dev = (which == EQD_F_DISP ? h->dDisp : h->dVel).p;
+        if ((size_t)Nn * 3 * sizeof(double) < (64u << 20)) {
+          std::vector<double> v = (which == EQD_F_DISP ? h->dDisp : h->dVel).download();
+          parallel_range((size_t)Nn, [&](size_t b, size_t e) {
+            for (size_t n = b; n < e; ++n) for (int j = 0; j < 3; ++j) out[j + 3 * n] = v[j * NS + n];
+          });
+          break;
+        }
+        // large sub-domains: chunks of the three SoA rows land in a pinned buffer (DMA at link
+        // speed, no pageable bounce, no serial first touch of a 0.5 GB temporary) and are
+        // interleaved into the caller's (3,Nn) array by all host threads
+        if (!h->stage) h->stage.reset(new StagedCopy());
+        void* pinv = nullptr;
+        CK(h->stage->pinned(0, &pinv));
+        double* pin = (double*)pinv;
+        const size_t cap = StagedCopy::kChunk / sizeof(double) / 3;   // nodes per chunk
+        for (size_t n0 = 0; n0 < (size_t)Nn; n0 += cap) {
+          const size_t m = std::min(cap, (size_t)Nn - n0);
+          for (int j = 0; j < 3; ++j)
+            CK(cudaMemcpyAsync(pin + j * m, dev + j * NS + n0, m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+          CK(cudaStreamSynchronize(h->stream));
+          parallel_range(m, [&](size_t b, size_t e) {
+            for (size_t i = b; i < e; ++i) for (int j = 0; j < 3; ++j) out[j + 3 * (n0 + i)] = pin[j * m + i];
+          });
+        }
         break;
       }
       case EQD_F_V1: case EQD_F_FORCE: case EQD_F_MASS: {

@@ -81,6 +81,15 @@ class StagedCopy {
     return cudaStreamSynchronize(s);
   }
 
+  // One of the two pinned buffers (kChunk bytes), for staged device -> host reads.  The caller
+  // must have drained the stream the uploads used (the buffers may still be DMA sources).
+  cudaError_t pinned(int i, void** out) {
+    cudaError_t e = init();
+    if (e != cudaSuccess) return e;
+    *out = buf_[i & 1];
+    return cudaSuccess;
+  }
+
  private:
   cudaError_t init() {
     for (int i = 0; i < 2; ++i) {

@@ -5,7 +5,10 @@
 #include "eqd_tiles.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 #include <stdexcept>
 #include <thread>
@@ -38,35 +41,84 @@ inline int balanced(int extent, int target, int& nblocks) {
   return std::max(1, (extent + nblocks - 1) / nblocks);
 }
 
+// EQD_VERBOSE=1: wall-clock laps of the planner's phases on stderr
+struct PlanLap {
+  bool on = std::getenv("EQD_VERBOSE") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void lap(const char* label, int n) {
+    if (!on || n < 100000) return;
+    auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[eqd]   plan_tiles(%d): %s %.3f s\n", n, label, std::chrono::duration<double>(now - t).count());
+    t = now;
+  }
+};
+
 struct Tile {
   int b, e;                 // range in the sorted element order
   std::vector<int> nodes;   // ascending unique node ids
 };
 
+// Small open-addressing table node id -> value, reused tile after tile by one thread: the
+// 8 x elements node ids of a tile are de-duplicated in O(ids) before the (much shorter) list of
+// unique nodes is sorted, and the tile-local index of a node is then one probe instead of a
+// binary search.
+class NodeTable {
+ public:
+  NodeTable() : key_(kSize, -1), val_(kSize, 0) {}
+  void clear() {
+    for (int s : used_) key_[s] = -1;
+    used_.clear();
+  }
+  // returns true when id was not in the table yet
+  bool insert(int id, int value) {
+    unsigned s = hash(id);
+    while (key_[s] >= 0) {
+      if (key_[s] == id) return false;
+      s = (s + 1) & (kSize - 1);
+    }
+    key_[s] = id; val_[s] = value; used_.push_back((int)s);
+    return true;
+  }
+  int find(int id) const {
+    unsigned s = hash(id);
+    while (key_[s] != id) {
+      if (key_[s] < 0) return -1;
+      s = (s + 1) & (kSize - 1);
+    }
+    return val_[s];
+  }
+  size_t size() const { return used_.size(); }
+
+ private:
+  static constexpr unsigned kSize = 1u << 14;   // > 4 x the ids of the largest tile (8 x capE = 5120 at most)
+  static unsigned hash(int id) { return ((unsigned)id * 2654435761u) >> 18; }
+  std::vector<int> key_, val_, used_;
+};
+
 void unique_nodes(const int* conn, const std::vector<int>& elems, const raw_vector<int>& order, int b, int e,
-                  std::vector<int>& out) {
+                  NodeTable& tab, std::vector<int>& out) {
   out.clear();
-  out.reserve(8 * (size_t)(e - b));
+  tab.clear();
   for (int k = b; k < e; ++k) {
     const int* c = conn + 8 * (size_t)elems[order[k]];
-    for (int j = 0; j < 8; ++j) out.push_back(c[j]);
+    for (int j = 0; j < 8; ++j)
+      if (tab.insert(c[j], 0)) out.push_back(c[j]);
   }
   std::sort(out.begin(), out.end());
-  out.erase(std::unique(out.begin(), out.end()), out.end());
 }
 
 void split_group(const int* conn, const std::vector<int>& elems, const raw_vector<int>& order, int b, int e,
-                 const TileShape& sh, std::vector<Tile>& out) {
+                 const TileShape& sh, NodeTable& tab, std::vector<Tile>& out) {
   if (b >= e) return;
   Tile t;
   t.b = b; t.e = e;
-  if (e - b <= sh.capE) {
-    unique_nodes(conn, elems, order, b, e, t.nodes);
+  if (e - b <= sh.capE && e - b <= 640) {   // 640: the table's capacity contract (8 x 640 ids)
+    unique_nodes(conn, elems, order, b, e, tab, t.nodes);
     if ((int)t.nodes.size() <= sh.capN || e - b == 1) { out.push_back(std::move(t)); return; }
   }
   const int m = b + (e - b) / 2;
-  split_group(conn, elems, order, b, m, sh, out);
-  split_group(conn, elems, order, m, e, sh, out);
+  split_group(conn, elems, order, b, m, sh, tab, out);
+  split_group(conn, elems, order, m, e, sh, tab, out);
 }
 
 }  // namespace
@@ -94,6 +146,7 @@ void plan_tiles(const int* conn, const std::vector<int>& elems, int Nn, int ny, 
   P.n = n;
   if (n == 0) { P.S = 32; P.PFS = 4; P.LS = 1; P.refId.assign(P.S, -1); P.tileNode.assign(1, 0); P.tnode.assign(P.PFS, -1); P.lconn.assign(8 * (size_t)P.S, 0); return; }
   if (sh.capN > (int)EQD_LN_MASK) throw std::runtime_error("tile node cap exceeds the 12-bit local index");
+  PlanLap lap;
   // ---- brick key per element
   raw_vector<int> key(n);
   int nKeys = 1;
@@ -138,6 +191,7 @@ void plan_tiles(const int* conn, const std::vector<int>& elems, int Nn, int ny, 
     nKeys = (n + per - 1) / per;
     for (int j = 0; j < n; ++j) key[j] = j / per;
   }
+  lap.lap("brick keys", n);
   // ---- stable counting sort by key (elements keep ascending reference order inside a brick)
   std::vector<int> start(nKeys + 1, 0);
   for (int j = 0; j < n; ++j) start[key[j] + 1]++;
@@ -147,14 +201,17 @@ void plan_tiles(const int* conn, const std::vector<int>& elems, int Nn, int ny, 
     std::vector<int> fill(start.begin(), start.end() - 1);
     for (int j = 0; j < n; ++j) order[fill[key[j]]++] = j;
   }
+  lap.lap("counting sort", n);
   // ---- non-empty groups -> tiles
   std::vector<int> groups;
   for (int k = 0; k < nKeys; ++k) if (start[k + 1] > start[k]) groups.push_back(k);
   const int nG = (int)groups.size();
   std::vector<std::vector<Tile>> gt(nG);
   parallel_for(nG, [&](int b, int e) {
-    for (int g = b; g < e; ++g) split_group(conn, elems, order, start[groups[g]], start[groups[g] + 1], sh, gt[g]);
+    NodeTable tab;
+    for (int g = b; g < e; ++g) split_group(conn, elems, order, start[groups[g]], start[groups[g] + 1], sh, tab, gt[g]);
   });
+  lap.lap("split into tiles (node lists)", n);
   std::vector<Tile*> tiles;
   for (auto& v : gt) for (auto& t : v) tiles.push_back(&t);
   const int nT = (int)tiles.size();
@@ -180,14 +237,18 @@ void plan_tiles(const int* conn, const std::vector<int>& elems, int Nn, int ny, 
   parallel_range((size_t)P.S, [&](size_t b, size_t e) { std::fill(P.refId.begin() + b, P.refId.begin() + e, -1); });
   parallel_range((size_t)P.PFS, [&](size_t b, size_t e) { std::fill(P.tnode.begin() + b, P.tnode.begin() + e, -1); });
   parallel_range(8 * (size_t)P.S, [&](size_t b, size_t e) { std::fill(P.lconn.begin() + b, P.lconn.begin() + e, (uint16_t)0); });
+  lap.lap("slots + fills", n);
   const size_t S = P.S;
   std::vector<int> bad(1, 0);
   parallel_for(nT, [&](int tb, int te) {
     std::vector<int> stamp, cnt;
+    NodeTable tab;
     for (int t = tb; t < te; ++t) {
       const Tile& T = *tiles[t];
       const int ln = (int)T.nodes.size();
       std::copy(T.nodes.begin(), T.nodes.end(), P.tnode.begin() + P.tileNode[t]);
+      tab.clear();
+      for (int i = 0; i < ln; ++i) tab.insert(T.nodes[i], i);   // node id -> tile-local index (ascending ids)
       stamp.assign(8 * (size_t)ln, -1); cnt.assign(8 * (size_t)ln, 0);
       int maxc = 1;
       for (int k = T.b; k < T.e; ++k) {
@@ -198,7 +259,7 @@ void plan_tiles(const int* conn, const std::vector<int>& elems, int Nn, int ny, 
         const int pass = le / NT;
         for (int i = 0; i < 8; ++i) {
           const int nd = conn[8 * (size_t)e + i];
-          const int li = (int)(std::lower_bound(T.nodes.begin(), T.nodes.end(), nd) - T.nodes.begin());
+          const int li = tab.find(nd);
           // colour = how many earlier elements of this (pass, phase) hit the same node
           const size_t q = 8 * (size_t)li + i;
           if (stamp[q] != pass) { stamp[q] = pass; cnt[q] = 0; }
@@ -211,6 +272,7 @@ void plan_tiles(const int* conn, const std::vector<int>& elems, int Nn, int ny, 
       P.tileColours[t] = (uint8_t)maxc;
     }
   });
+  lap.lap("local connectivity + colours", n);
   if (bad[0]) throw std::runtime_error("tile planner: more than 16 elements of one phase share a node");
   (void)Nn;
 }

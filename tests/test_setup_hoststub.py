@@ -1,0 +1,85 @@
+"""Host-side set-up and fetch logic of the step library, exercised WITHOUT a GPU by linking the
+library's objects against a stand-in for the CUDA runtime (tools/hoststub/cudart_stub.cpp:
+"device" memory is host memory, copies are memcpy, kernels do nothing).  What this can check is
+exactly the part of the C ABI that is host code: eqd_set_* conversions (AoS -> SoA, equation
+indirection, padding), the tile planner's uploads, and eqd_fetch's way back, including the
+staged path large sub-domains take.  It computes no physics -- nothing a kernel would produce
+exists in this mode -- and the product never loads the stub (see the header of the .cpp).
+Runs in a subprocess so that the stand-in never shares a process with the real library."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import parity
+
+ROOT = parity.ROOT
+
+SCRIPT = textwrap.dedent(r"""
+    import ctypes as C, os, sys
+    import numpy as np
+    sys.path.insert(0, %(root)r)
+    sys.path.insert(0, os.path.join(%(root)r, "tools", "hoststub"))
+    import setup_probe
+    lib, stub = setup_probe.build_stub()
+    from eqdyna_b200 import build, cases, device as dev
+    from eqdyna_b200.host import World
+    build.cuda_lib_path = lambda: lib
+    S = C.CDLL(stub)
+    S.stub_prefault()
+    case, nodes_min, device_ops = sys.argv[1], int(sys.argv[2]), bool(int(sys.argv[3]))
+    w = World(cases.materialize(case), np_xyz=(1, 1, 1), nstep=4)
+    w.build(0, sum_shared=False)
+    v = w.view(0)
+    assert v.Nn >= nodes_min, v.Nn
+    rng = np.random.default_rng(7)
+    v.dispArr[...] = rng.standard_normal(v.dispArr.shape)
+    v.velArr[...] = rng.standard_normal(v.velArr.shape)
+    v.v1[...] = rng.standard_normal(v.v1.shape)
+    fps = []
+    for rep in range(2):
+        d = dev.Domain(v, compute_ops=device_ops)
+        fp = (C.c_uint64 * 3)()
+        S.stub_fingerprint(fp)
+        fps.append((fp[0], fp[1], fp[2]))
+        disp = d.fetch(dev.F_DISP, (3, v.Nn))
+        vel = d.fetch(dev.F_VEL, (3, v.Nn))
+        v1 = d.fetch(dev.F_V1, (v.Neq,))
+        d.close()
+    assert fps[0] == fps[1], fps                      # the uploads are deterministic
+    st = v.eqNumStartIndexLoc
+    fixed = v.eqNumIndexArr[st] < 0
+    free3 = (~fixed) & (v.numOfDofPerNodeArr == 3)
+    pml = (~fixed) & (v.numOfDofPerNodeArr == 12)
+    # displacement: back as uploaded; fixed boundary nodes are held at rest
+    assert np.array_equal(disp[:, ~fixed], v.dispArr[:, ~fixed])
+    assert not disp[:, fixed].any() and not vel[:, fixed].any()
+    # velocity of a 3-dof node IS its v1 (driver.f90:102-103); a PML node keeps velArr next to its 12 split dofs
+    eq3 = v.eqNumIndexArr[st[free3][None, :] + np.arange(3)[:, None]] - 1
+    assert np.array_equal(vel[:, free3], v.v1[eq3])
+    assert np.array_equal(vel[:, pml], v.velArr[:, pml])
+    # v1 round trip through the SoA rows / the 12-row PML block
+    assert np.array_equal(v1, v.v1)
+    print("OK", case, v.Nn, int(free3.sum()), int(pml.sum()), int(fixed.sum()), "%%016x" %% fps[0][2])
+""")
+
+
+def _run(case, nodes_min, arena_gb, device_ops=0):
+    env = dict(os.environ, EQD_STUB_ARENA_GB=str(arena_gb))
+    env.pop("EQD_VERBOSE", None)
+    r = subprocess.run([sys.executable, "-c", SCRIPT % {"root": ROOT}, case, str(nodes_min), str(device_ops)], env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert r.stdout.strip().splitlines()[-1].startswith("OK " + case), r.stdout
+    return r.stdout
+
+
+def test_upload_and_fetch_round_trip_small():
+    """tpv8 (260 k nodes): the plain download path of eqd_fetch."""
+    _run("test.tpv8", 200000, 1.5)
+
+
+def test_upload_and_fetch_round_trip_staged():
+    """TPV104 at dx = 200 m (5.4 M nodes, 130 MB per field): eqd_fetch's staged path -- pinned
+    chunks, three SoA rows per chunk, interleaved by all host threads."""
+    _run("bench.tpv104_200m", 3000000, 10, device_ops=1)
