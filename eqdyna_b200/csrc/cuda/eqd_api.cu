@@ -1002,7 +1002,7 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
       std::vector<int> maxv(nth + 1, 2), badv(nth + 1, 0);
       const size_t NS = h->NnS;
       const size_t per = ((size_t)Nn + nth - 1) / nth;
-      auto scan = [&](std::vector<uint32_t>* tab) {
+      auto scan = [&](raw_vector<uint32_t>* tab) {
         std::vector<std::thread> th;
         for (int t = 0; t < nth; ++t)
           th.emplace_back([&, t] {
@@ -1030,7 +1030,8 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
       scan(nullptr);
       int maxCnt = 2;
       for (int t = 0; t < nth; ++t) { maxCnt = std::max(maxCnt, maxv[t]); need(!badv[t], "eqd_set_mesh: a node belongs to more than 255 tiles"); }
-      std::vector<uint32_t> tab((size_t)maxCnt * NS, 0);
+      raw_vector<uint32_t> tab((size_t)maxCnt * NS);   // first touched (zeroed) by all threads, not serially
+      parallel_range(tab.size(), [&](size_t b, size_t e) { std::fill(tab.begin() + b, tab.begin() + e, 0u); });
       parallel_range((size_t)Nn, [&](size_t b, size_t e) { std::fill(cnt.begin() + b, cnt.begin() + e, (uint8_t)0); });
       scan(&tab);
       for (int t = 0; t < nth; ++t) need(!badv[t], "internal: REG element on a 12-dof node");
