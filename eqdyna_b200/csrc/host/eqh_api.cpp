@@ -81,6 +81,7 @@ static void build_one(eqh_world* w, int r) {
   eqh::mesh4num(w->in, *s);
   eqh::meshgen(w->in, *s);
   eqh::load_on_fault(w->in, *s);
+  if (w->in.mode == 2) eqh::load_on_fault_restart(w->in, *s);   // eqdyna3d.f90:60
   eqh::find_surface_nodes(w->in, *s);
   eqh::alloc_after_meshgen(w->in, *s);
   eqh::assemble_global_mass(w->in, *s);

@@ -8,7 +8,9 @@
 //     int32    nfx, nfz, nvar(=24), 0
 //     float64  field[nvar][nfz][nfx]      (C order == Fortran (nfx,nfz,nvar))
 // in the order of var_id(1..24) in netcdf_io.f90:41-64.
-// (tools/nc_to_bin.py converts a real on_fault_vars_input.nc where netCDF4 exists.)
+// (tools/gen_case_fixtures.py writes it from the arrays scripts/case.setup hands to netCDF4.)
+// mode == 2 additionally reads `fault.r.bin`, the same container with the 12 fields of the
+// restart file fault.r.nc (netcdf_io.f90:116-185).
 //
 // Writers reproduce src/library_output.f90:16-205 (faultst*.txt, body*.txt,
 // frt.txt<me>) so that scripts/plotRuptureDynamics keeps working.
@@ -219,6 +221,30 @@ void read_case(const std::string& dir, CaseInput& in) {
     size_t n = (size_t)in.fnx * in.fnz * 24;
     in.on_fault_vars.resize(n);
     size_t got = std::fread(in.on_fault_vars.data(), 8, n, f);
+    std::fclose(f);
+    if (got != n) throw std::runtime_error(p + ": truncated");
+  }
+  if (in.mode == 2) {
+    // netcdf_read_on_fault_eqdyna_restart, netcdf_io.f90:116-150: fault.r.nc of the previous
+    // earthquake cycle, here its raw dump fault.r.bin (same container as above, 12 fields in the
+    // order shear_strike, shear_dip, effective_normal, slip_rate, state_variable, state_normal,
+    // vxm, vym, vzm, vxs, vys, vzs).  Required in this mode, as the reference's nf90_open is.
+    std::string p = dir + "/fault.r.bin";
+    FILE* f = std::fopen(p.c_str(), "rb");
+    if (!f) throw std::runtime_error(p + " is required for mode == 2 but missing");
+    char magic[8];
+    int32_t hdr[4];
+    if (std::fread(magic, 1, 8, f) != 8 || std::memcmp(magic, "EQDOFV1", 7) != 0 || std::fread(hdr, 4, 4, f) != 4) {
+      std::fclose(f);
+      throw std::runtime_error(p + ": bad header");
+    }
+    if (hdr[0] != in.fnx || hdr[1] != in.fnz || hdr[2] != 12) {
+      std::fclose(f);
+      throw std::runtime_error(p + ": dimensions do not match bFaultGeometry/dx,dz (12 fields expected)");
+    }
+    size_t n = (size_t)in.fnx * in.fnz * 12;
+    in.restart_vars.resize(n);
+    size_t got = std::fread(in.restart_vars.data(), 8, n, f);
     std::fclose(f);
     if (got != n) throw std::runtime_error(p + ": truncated");
   }

@@ -669,6 +669,29 @@ void load_on_fault(const CaseInput& in, RankState& s) {
     }
 }
 
+// netcdf_read_on_fault_eqdyna_restart, netcdf_io.f90:152-178 (mode == 2, eqdyna3d.f90:60): initial
+// tractions, slip rate, state variables and the split-node velocities of the previous cycle.
+// Unlike load_on_fault this one indexes fric by the fault it loops over (fric(k,i,ift)).
+void load_on_fault_restart(const CaseInput& in, RankState& s) {
+  const int fnx = in.fnx, fnz = in.fnz;
+  if (in.restart_vars.size() != (size_t)fnx * fnz * 12) throw std::runtime_error("load_on_fault_restart: no restart fields");
+  auto RV = [&](int ii, int jj, int v) {
+    return in.restart_vars[(size_t)(ii - 1) + (size_t)fnx * ((jj - 1) + (size_t)fnz * (v - 1))];
+  };
+  static const int slot[12] = {8, 49, 7, 47, 20, 23, 31, 32, 33, 34, 35, 36};
+  for (int ift = 0; ift < in.ntotft; ++ift)
+    for (int i = 1; i <= s.nftnd[ift]; ++i) {
+      const size_t pb = (size_t)(i - 1) + (size_t)s.nftmx * ift;
+      int slave = s.nsmp[0 + 2 * pb];
+      double xc = s.meshCoor[0 + 3 * (size_t)(slave - 1)], zc = s.meshCoor[2 + 3 * (size_t)(slave - 1)];
+      int ii = nint((xc - in.fxmin[ift]) / in.dx) + 1;
+      int jj = nint((zc - in.fzmin[ift]) / in.dz) + 1;
+      if (ii < 1 || ii > fnx || jj < 1 || jj > fnz) throw std::runtime_error("load_on_fault_restart: index out of range");
+      double* f = &s.fric[100 * pb];
+      for (int v = 1; v <= 12; ++v) f[slot[v - 1] - 1] = RV(ii, jj, v);
+    }
+}
+
 // find_surfaceNodeIdArr, library_output.f90:247-264
 void find_surface_nodes(const CaseInput& in, RankState& s) {
   s.surface_nnode = 0;

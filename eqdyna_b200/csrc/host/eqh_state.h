@@ -51,6 +51,9 @@ struct CaseInput {
   // on_fault_vars_input (24 fields, each (fnx,fnz) column-major = ix fastest)
   int fnx = 0, fnz = 0;
   std::vector<double> on_fault_vars;  // (fnx,fnz,24)
+  // mode == 2: the 12 fields of the restart file fault.r.nc spun off by EQquasi
+  // (netcdf_io.f90:116-185), from the raw dump fault.r.bin
+  std::vector<double> restart_vars;   // (fnx,fnz,12)
   // derived (readInputFiles.f90:182-186)
   double ccosphi = 0, sinphi = 0, tv = 0;
   int nstep = 0;
@@ -139,6 +142,7 @@ void mesh4num(const CaseInput& in, RankState& s);
 void meshgen(const CaseInput& in, RankState& s);
 void exchange_arn(const CaseInput& in, std::vector<RankState*>& world);
 void load_on_fault(const CaseInput& in, RankState& s);
+void load_on_fault_restart(const CaseInput& in, RankState& s);
 void find_surface_nodes(const CaseInput& in, RankState& s);
 void alloc_after_meshgen(const CaseInput& in, RankState& s);
 // eqh_mass.cpp
