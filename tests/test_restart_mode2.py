@@ -120,3 +120,72 @@ def test_mode2_without_restart_file_is_an_error(tmp_path):
     with pytest.raises(RuntimeError) as e:
         World(d, np_xyz=(1, 1, 1), nstep=2)
     assert "fault.r.bin" in str(e.value)
+
+
+def test_cycle_hand_off_frt_to_restart(tmp_path):
+    """One EQdyna run hands its final on-fault state to the next one: frt.txt<me> ->
+    tools/restart_from_frt.py (the mapping of scripts/plotRuptureDynamics:71-82) -> fault.r.bin ->
+    a mode == 2 world whose fric / v1 start from the first run's final tractions, slip rate,
+    state and split-node velocities (to the 7 digits frt.txt carries)."""
+    import subprocess
+    import sys
+    from eqdyna_b200.host import World
+    n = 60
+    w1 = parity.build_world("test.tpv104", (2, 2, 1), n)
+    parity.run_oracle(w1)
+    run_dir = str(tmp_path / "run1")
+    for r in range(w1.size):
+        w1.write_outputs(r, run_dir)
+    d, _ = _restart_case(tmp_path)
+    os.remove(os.path.join(d, "fault.r.bin"))
+    tool = os.path.join(parity.ROOT, "tools", "restart_from_frt.py")
+    r = subprocess.run([sys.executable, tool, run_dir, d], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "73 x 37" in r.stdout
+    w2 = World(d, np_xyz=(2, 2, 1), nstep=2).build()
+    checked = 0
+    for rk in range(w1.size):
+        a, b = w1.view(rk), w2.view(rk)
+        k = int(a.nftnd[0])
+        if not k:
+            continue
+        # final state of run 1 (fric slots as frt.txt prints them) == initial state of run 2
+        for src, dst in ((79, 8), (80, 49), (78, 7), (47, 47), (20, 20), (23, 23),
+                         (31, 31), (32, 32), (33, 33), (34, 34), (35, 35), (36, 36)):
+            x, y = a.fric[src - 1, :k, 0], b.fric[dst - 1, :k, 0]
+            np.testing.assert_allclose(y, x, rtol=6e-7, atol=1e-30)
+        st = b.eqNumStartIndexLoc
+        slave = b.nsmp[0, :k, 0] - 1
+        np.testing.assert_array_equal(b.v1[b.eqNumIndexArr[st[slave]] - 1], b.fric[33, :k, 0])
+        checked += k
+        assert float(np.abs(a.fric[46, :k, 0]).max()) > 1e-3          # the rupture was under way: not a trivial state
+    assert checked > 2701
+    w1.close(); w2.close()
+
+
+def test_nc_to_bin_with_a_stand_in_for_netcdf4(tmp_path, monkeypatch):
+    """tools/nc_to_bin.py converts the reference workflow's netCDF inputs where netCDF4 exists; here a
+    minimal stand-in for the module serves the arrays, and the output must equal the fixture that
+    tools/gen_case_fixtures.py captured from scripts/case.setup."""
+    import importlib.util
+    import sys
+    import types
+    from eqdyna_b200 import cases
+    src = cases.materialize("test.tpv8")
+    with open(os.path.join(src, "on_fault_vars_input.bin"), "rb") as f:
+        raw = f.read()
+    fnx, fnz, nvar, _ = struct.unpack("<4i", raw[8:24])
+    ofv = np.frombuffer(raw[24:], dtype="<f8").reshape(nvar, fnz, fnx)
+    spec = importlib.util.spec_from_file_location("nc_to_bin", os.path.join(parity.ROOT, "tools", "nc_to_bin.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+
+    class FakeDataset:
+        def __init__(self, path):
+            assert path.endswith("on_fault_vars_input.nc")
+            self.variables = {n: ofv[i] for i, n in enumerate(mod.ON_FAULT)}
+    monkeypatch.setitem(sys.modules, "netCDF4", types.SimpleNamespace(Dataset=FakeDataset))
+    d = str(tmp_path)
+    mod.main(["nc_to_bin.py", d])
+    assert open(os.path.join(d, "on_fault_vars_input.bin"), "rb").read() == raw
+    assert len(mod.RESTART) == 12 and mod.RESTART == list(FIELDS)
