@@ -59,6 +59,12 @@ subroutine driver
         c_loc(surfaceNodeIdArr), nSurf)
     call check('eqd_set_stations')
 
+    ! Optional fast path (DESIGN.md 3d): closed-form operators on tiles of axis-aligned hexahedra.  Off by
+    ! default, so that the stored eleshp / phi / ss are used for every element; results with it agree with
+    ! the default to ~1e-14 per step (parity tests: 1e-10 against the CPU oracle).
+    ! ierr = eqd_set_option(h, 'box'//c_null_char, 2_c_int32_t);          call check('eqd_set_option box')
+    ! ierr = eqd_set_option(h, 'box_compact'//c_null_char, 1_c_int32_t);  call check('eqd_set_option box_compact')
+
     if (npx*npy*npz > 1) then
         if (me == masterProcsId) ierr = eqd_get_unique_id(id128)
         call MPI_Bcast(id128, 128, MPI_CHARACTER, masterProcsId, MPI_COMM_WORLD, mpierr)
