@@ -1,0 +1,45 @@
+"""CPU prototype of the marching scheme planned for the box tiles (tools/proto_march):
+forces assembled by the emulated column-marching threads equal the element-by-element forces of the
+reference's stored operators.  Prototype only -- not a product path, no GPU."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import parity
+
+
+@pytest.fixture(scope="module")
+def proto(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("march") / "libmarch_proto.so")
+    src = os.path.join(parity.ROOT, "tools", "proto_march", "march_proto.cpp")
+    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-o", out, src], stderr=subprocess.DEVNULL)
+    L = C.CDLL(out)
+    L.march_proto.argtypes = [C.c_int32] * 5 + [C.c_void_p] * 11 + [C.c_double, C.c_double] + [C.c_void_p] * 3
+    return L
+
+
+@pytest.mark.parametrize("case,min_bundles", [("test.tpv104", 100), ("test.tpv8", 2)])
+def test_marching_forces_equal_element_by_element_forces(proto, case, min_bundles):
+    w = parity.build_world(case, (1, 1, 1), 2)
+    v = w.view(0)
+    r = v.raw
+    rng = np.random.default_rng(3)
+    vel = np.asfortranarray(rng.standard_normal((3, v.Nn)))
+    disp = np.asfortranarray(rng.standard_normal((3, v.Nn)) * 1e-2)
+    fm = np.zeros((3, v.Nn), order="F")
+    fr = np.zeros((3, v.Nn), order="F")
+    st = np.zeros(3, dtype=np.int64)
+    P = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+    rc = proto.march_proto(v.Nn, v.Ne, r.nx, r.ny, r.nz, P(v.meshCoor), P(v.nodeElemIdRelation), P(v.elemTypeArr),
+                           P(v.numOfDofPerNodeArr), P(v.eleshp), P(v.phi), P(v.ss), P(v.eledet), P(v.mat), P(vel), P(disp),
+                           v.params.rdampk, v.params.w, P(fm), P(fr), P(st))
+    assert rc == 0, "numbering assumption violated at march_proto.cpp:%d" % rc
+    assert st[0] >= min_bundles and st[1] == st[0] * 32 * 4 * 16
+    assert np.abs(fr).max() > 0
+    assert np.abs(fm - fr).max() <= 1e-12 * np.abs(fr).max()
+    # nodes outside every bundle receive nothing from either path
+    assert np.array_equal(np.abs(fm).sum(axis=0) > 0, np.abs(fr).sum(axis=0) > 0)
+    w.close()
