@@ -127,3 +127,46 @@ def test_launch_sequence_and_box_flags_under_the_stand_in():
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-3000:]
     assert r.stdout.strip().splitlines()[-1].startswith("OK"), r.stdout
+
+
+BENCH_SCRIPT = textwrap.dedent(r"""
+    import os, sys
+    sys.path.insert(0, %(root)r)
+    import torch
+    torch.cuda.is_available = lambda: True
+    torch.cuda.set_device = lambda *_: None
+    torch.cuda.synchronize = lambda *_: None
+    from eqdyna_b200 import build
+    build.cuda_lib_path = lambda: %(lib)r
+    import bench
+    bench.ClockSampler.run = lambda self: None            # no nvidia-smi here
+    sys.argv = ["bench.py", "--case", "test.tpv104", "--steps", "5", "--warmup", "3", "--no-cpu-baseline"]
+    bench.main()
+""")
+
+
+def test_bench_native_arm_call_sequence_under_the_stand_in():
+    """bench.py's native arm end to end against the real library's host code (kernels no-ops, event
+    times made up): every C-ABI call it makes, in its order, and the JSON line's keys.  The numbers
+    in the line mean nothing here; the point is that no call fails and no key is missing."""
+    import json
+    sys.path.insert(0, os.path.join(ROOT, "tools", "hoststub"))
+    import setup_probe
+    lib, stub = setup_probe.build_stub()
+    env = dict(os.environ, EQD_STUB_ARENA_GB="3", LD_PRELOAD=stub)   # torch brings the real libcudart into the global scope
+    env.pop("EQD_VERBOSE", None)
+    r = subprocess.run([sys.executable, "-c", BENCH_SCRIPT % {"root": ROOT, "lib": lib}], env=env,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "clocks"):
+        assert k in line, k
+    assert line["metric"] == "element-steps/s" and line["dtype"] == "f64" and line["vs_baseline"] is None
+    assert line["config"]["box"] == 2 and line["config"]["box_compact"] == 1 and "workload" in line["config"]
+    assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    rf = line["roofline"]
+    assert set(rf) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and rf["bound"] == "hbm"
+    assert rf["box_elements_per_launch"] == rf["elements_per_launch"] == 516096 and rf["alg_bytes_per_element"] == 272.0
+    assert line["gpu_launches"] > 0

@@ -80,7 +80,7 @@ cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = (void*)1; 
 cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
 cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
 cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
-cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return 0; }
+cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t, cudaEvent_t) { *ms = 1.0f; return 0; }   // a made-up millisecond: callers divide by it
 cudaError_t cudaFuncSetAttribute(const void*, int, int) { return 0; }
 cudaError_t cudaLaunchKernel(const void*, dim3, dim3, void**, size_t, cudaStream_t) { return 0; }   // kernels do not run
 unsigned __cudaPushCallConfiguration(dim3, dim3, size_t, void*) { return 0; }
