@@ -4,7 +4,7 @@
   python tools/hoststub/setup_probe.py [case] [--device-ops 0|1] [--box N] [--repeat R]
 
 Links the step library's objects (eqdyna_b200/lib/obj/*.o) against tools/hoststub/cudart_stub.cpp
-into /tmp/eqd_hoststub/ (kernels do nothing, "device" memory is host memory), runs the calls
+into a scratch directory (kernels do nothing, "device" memory is host memory), runs the calls
 bench.py's e2e leg makes before eqd_run -- eqd_create, eqd_set_mesh, eqd_compute_elem_ops |
 eqd_set_elem_ops, eqd_set_nodal, eqd_set_fault, eqd_set_halo, eqd_set_stations, finalize (through
 eqd_sum_shared's entry, which needs no communicator at 1x1x1) -- with EQD_VERBOSE=1 lap timers,
@@ -21,13 +21,19 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-OUT = "/tmp/eqd_hoststub"
+OUT = None   # per-process scratch directory, removed at exit
 
 
 def build_stub():
+    global OUT
     from eqdyna_b200 import build
     build.build_cuda()
-    os.makedirs(OUT, exist_ok=True)
+    if OUT is None:
+        import atexit
+        import shutil
+        import tempfile
+        OUT = tempfile.mkdtemp(prefix="eqd_hoststub_")
+        atexit.register(shutil.rmtree, OUT, ignore_errors=True)
     stub = os.path.join(OUT, "libcudart_stub.so")
     lib = os.path.join(OUT, "libeqdyna_b200_hoststub.so")
     src = os.path.join(ROOT, "tools", "hoststub", "cudart_stub.cpp")
