@@ -189,3 +189,31 @@ def test_nc_to_bin_with_a_stand_in_for_netcdf4(tmp_path, monkeypatch):
     mod.main(["nc_to_bin.py", d])
     assert open(os.path.join(d, "on_fault_vars_input.bin"), "rb").read() == raw
     assert len(mod.RESTART) == 12 and mod.RESTART == list(FIELDS)
+
+
+@pytest.mark.parametrize("case", ["test.tpv104", "test.meng2023a"])
+def test_restart_tool_reproduces_the_reference_restart_file(case, tmp_path):
+    """Golden vector: the reference ships, next to its golden frt.txt*, the fault.dyna.r.nc that
+    scripts/plotRuptureDynamics (generateNcRestart) derived from them.  The file is NETCDF4 (HDF5, no
+    reader in this image) but its twelve (dip, strike) float64 arrays are stored contiguously, in the
+    order netcdf_io.f90:139-150 reads them: tools/restart_from_frt.py, fed the golden frt.txt*, must
+    produce exactly those bytes."""
+    import gzip
+    import importlib.util
+    import golden_io
+    from eqdyna_b200 import cases
+    spec = importlib.util.spec_from_file_location("restart_from_frt", os.path.join(parity.ROOT, "tools", "restart_from_frt.py"))
+    rf = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rf)
+    run = str(tmp_path / "golden_run")
+    os.makedirs(run)
+    for f in ("frt.txt0", "frt.txt2"):
+        open(os.path.join(run, f), "w").write(golden_io.read_text(golden_io.golden_path(case, f)))
+    fields, fnx, fnz = rf.gather(run, cases.materialize(case))
+    mine = np.ascontiguousarray(fields).astype("<f8").tobytes()           # [12][fnz][fnx]
+    raw = gzip.open(golden_io.golden_path(case, "fault.dyna.r.nc"), "rb").read()
+    assert raw[:8] == b"\x89HDF\r\n\x1a\n"
+    first = raw.find(mine[:fnx * fnz * 8])
+    assert first > 0, "shear_strike of the tool is not in the reference's file"
+    assert raw[first:first + len(mine)] == mine, "the twelve restart arrays differ from the reference's"
+    assert np.abs(fields[0]).max() > 1.0e6                                # tractions in Pa, not a trivial block of zeros
