@@ -1,6 +1,9 @@
-"""CPU prototype of the marching scheme planned for the box tiles (tools/proto_march):
-forces assembled by the emulated column-marching threads equal the element-by-element forces of the
-reference's stored operators.  Prototype only -- not a product path, no GPU."""
+"""Prototype of the marching kernel planned for the box tiles (tools/proto_march).  The
+kernel is written once, as barrier-separated phases (march_kernel.cuh); here g++ compiles it and a
+driver runs every phase over all thread ids in turn, so the source the GPU will execute is checked on
+the CPU: partial forces and updated stresses equal the element-by-element evaluation from the
+reference's stored operators.  nvcc compiles the same header for sm_100a without spills.
+Prototype only -- not a product path, no GPU."""
 import ctypes as C
 import os
 import subprocess
@@ -31,7 +34,7 @@ def test_marching_forces_equal_element_by_element_forces(proto, case, min_bundle
     disp = np.asfortranarray(rng.standard_normal((3, v.Nn)) * 1e-2)
     fm = np.zeros((3, v.Nn), order="F")
     fr = np.zeros((3, v.Nn), order="F")
-    st = np.zeros(3, dtype=np.int64)
+    st = np.zeros(4, dtype=np.int64)
     P = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
     rc = proto.march_proto(v.Nn, v.Ne, r.nx, r.ny, r.nz, P(v.meshCoor), P(v.nodeElemIdRelation), P(v.elemTypeArr),
                            P(v.numOfDofPerNodeArr), P(v.eleshp), P(v.phi), P(v.ss), P(v.eledet), P(v.mat), P(vel), P(disp),
@@ -40,6 +43,19 @@ def test_marching_forces_equal_element_by_element_forces(proto, case, min_bundle
     assert st[0] >= min_bundles and st[1] == st[0] * 32 * 4 * 16
     assert np.abs(fr).max() > 0
     assert np.abs(fm - fr).max() <= 1e-12 * np.abs(fr).max()
+    assert st[3] * 1e-18 <= 1e-12                          # updated stresses, relative to the largest
     # nodes outside every bundle receive nothing from either path
     assert np.array_equal(np.abs(fm).sum(axis=0) > 0, np.abs(fr).sum(axis=0) > 0)
     w.close()
+
+
+def test_prototype_kernel_compiles_for_sm_100a_without_spills(tmp_path):
+    import shutil
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("no nvcc")
+    src = os.path.join(parity.ROOT, "tools", "proto_march", "march_kernel.cu")
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xptxas", "-v",
+                        "-c", src, "-o", str(tmp_path / "march_kernel.o")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
+    assert "k_march_reg" in r.stdout and "0 bytes spill stores, 0 bytes spill loads" in r.stdout
