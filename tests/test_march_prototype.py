@@ -59,3 +59,8 @@ def test_prototype_kernel_compiles_for_sm_100a_without_spills(tmp_path):
                         "-c", src, "-o", str(tmp_path / "march_kernel.o")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout
     assert "k_march_reg" in r.stdout and "0 bytes spill stores, 0 bytes spill loads" in r.stdout
+    # the stand-alone microbenchmark / GPU-vs-host check built on the same header links
+    bench = os.path.join(parity.ROOT, "tools", "proto_march", "march_bench.cu")
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
+                        "-o", str(tmp_path / "march_bench"), bench], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout
