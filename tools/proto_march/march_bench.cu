@@ -3,7 +3,8 @@
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o march_bench march_bench.cu
 //   ./march_bench --check                 # small block: GPU result against the host reading of the same source
-//   ./march_bench 512 160 256 20 [ctas_per_sm]   # cells in x, y, z (multiples of 32, 16, 4), timed launches
+//   ./march_bench 512 160 256 20 [ctas_per_sm] [prefetch 0|1]   # cells in x, y, z (multiples of 32, 16, 4), timed launches
+//   ./march_bench --check 1               # the same check for the prefetch variant of the schedule
 //
 // The block is cut into complete 32 x 4 x 16 bundles; node ids are the structured ones (ix*ny*nz + iz*ny + iy),
 // listed plane by plane as the kernel expects.  Operators and nodal fields are pseudo-random: the kernel's
@@ -119,11 +120,13 @@ int main(int argc, char** argv) {
   const bool check = argc > 1 && !std::strcmp(argv[1], "--check");
   Problem P;
   int iters = 20, ctasPerSm = 4;
-  if (check) { P.ncx = 64; P.ncy = 32; P.ncz = 8; iters = 1; }
+  bool prefetch = false;
+  if (check) { P.ncx = 64; P.ncy = 32; P.ncz = 8; iters = 1; prefetch = argc > 2 && std::atoi(argv[2]) != 0; }
   else {
     P.ncx = argc > 1 ? std::atoi(argv[1]) : 512; P.ncy = argc > 2 ? std::atoi(argv[2]) : 160; P.ncz = argc > 3 ? std::atoi(argv[3]) : 256;
     iters = argc > 4 ? std::atoi(argv[4]) : 20;
     ctasPerSm = argc > 5 ? std::atoi(argv[5]) : 4;
+    prefetch = argc > 6 && std::atoi(argv[6]) != 0;
   }
   if (P.ncx % 32 || P.ncy % BY || P.ncz % BZ || P.ncx <= 0) { std::fprintf(stderr, "cells must be multiples of 32, %d, %d\n", BY, BZ); return 4; }
   build(P);
@@ -137,7 +140,12 @@ int main(int argc, char** argv) {
               P.ncx, P.ncy, P.ncz, P.S, A.nBundles, P.PFS, (double)P.PFS / P.S, grid, NT);
   cudaStream_t s;
   CK(cudaStreamCreate(&s));
-  k_march_reg<<<grid, NT, 0, s>>>(A);   // warm-up (also the checked launch)
+  auto launch = [&] {
+    if (prefetch) k_march_reg_pf<<<grid, NT, 0, s>>>(A);
+    else k_march_reg<<<grid, NT, 0, s>>>(A);
+  };
+  std::printf("schedule: %s\n", prefetch ? "node planes prefetched through registers" : "node planes loaded synchronously");
+  launch();   // warm-up (also the checked launch)
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(s));
   if (check) {
@@ -154,7 +162,7 @@ int main(int argc, char** argv) {
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   CK(cudaEventRecord(e0, s));
-  for (int it = 0; it < iters; ++it) k_march_reg<<<grid, NT, 0, s>>>(A);
+  for (int it = 0; it < iters; ++it) launch();
   CK(cudaEventRecord(e1, s));
   CK(cudaEventSynchronize(e1));
   float ms = 0;

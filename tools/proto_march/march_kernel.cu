@@ -3,5 +3,8 @@
 #include "march_kernel.cuh"
 
 namespace march {
-void launch_march(const Args& A, int grid, cudaStream_t s) { k_march_reg<<<grid, NT, 0, s>>>(A); }
+void launch_march(const Args& A, int grid, bool prefetch, cudaStream_t s) {
+  if (prefetch) k_march_reg_pf<<<grid, NT, 0, s>>>(A);
+  else k_march_reg<<<grid, NT, 0, s>>>(A);
+}
 }  // namespace march

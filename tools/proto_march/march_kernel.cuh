@@ -46,11 +46,12 @@ struct Regs {
   double um[4][3];    // values at the element's x- corners (0,3,4,7): v (role 0) or d + rdampk v (role 1)
   double fc[4][3];    // forces on the x+ corners of the previous element, waiting for this element's share
   double fx[4][3];    // completed x- corner forces of this step, consumed by the four assembly phases
+  double pre[2][3];   // prefetch variant: v and d of the one node of plane p+2 this thread fetches (PN <= NT)
 };
 
 // shared memory of one CTA
 struct Shared {
-  double val[2][2][3][PN];   // [plane parity][v | d + rdampk v][component][node]: planes p and p+1
+  double val[3][2][3][PN];   // [plane mod 3][v | d + rdampk v][component][node]: a ring of node planes
   double frc[2][3][PN];      // [role][component][node]: force plane being assembled
 };
 
@@ -60,14 +61,14 @@ EQD_HD constexpr int xp(int q) { return q == 0 ? 1 : q == 1 ? 2 : q == 2 ? 5 : 6
 EQD_HD constexpr int dy(int q) { return q & 1; }
 EQD_HD constexpr int dz(int q) { return q >> 1; }
 
-// ---- phase: all threads load node plane `p` of the bundle into val[p & 1] (v and d + rdampk v)
+// ---- phase: all threads load node plane `p` of the bundle into val[p % 3] (v and d + rdampk v)
 EQD_HD void phase_load_plane(const Args& A, const Bundle& B, Shared& sm, int tid, int p) {
   for (int i = tid; i < PN; i += NT) {
     const int n = A.tnode[(size_t)B.n0 + (size_t)p * PN + i];
     for (int c = 0; c < 3; ++c) {
       const double v = A.vel[c * A.NnS + n], d = A.disp[c * A.NnS + n];
-      sm.val[p & 1][0][c][i] = v;
-      sm.val[p & 1][1][c][i] = d + A.rdampk * v;     // hrglss.f90:20-27
+      sm.val[p % 3][0][c][i] = v;
+      sm.val[p % 3][1][c][i] = d + A.rdampk * v;     // hrglss.f90:20-27
     }
   }
 }
@@ -96,7 +97,7 @@ EQD_HD void phase_element(const Args& A, const Bundle& B, Shared& sm, Regs& R, i
     const int li = (cz + dz(q)) * (BY + 1) + cy + dy(q);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      up[q][c] = sm.val[(p + 1) & 1][role][c][li];
+      up[q][c] = sm.val[(p + 1) % 3][role][c][li];
       u[xm(q)][c] = R.um[q][c];
       u[xp(q)][c] = up[q][c];
     }
@@ -129,6 +130,28 @@ EQD_HD void phase_element(const Args& A, const Bundle& B, Shared& sm, Regs& R, i
       R.fc[q][c] = f[xp(q)][c];
       R.um[q][c] = up[q][c];
     }
+}
+
+// ---- prefetch variant: the loads of node plane `p` are issued into registers (before the element work of
+// the step, so that their latency hides behind it) ...
+EQD_HD void phase_prefetch_issue(const Args& A, const Bundle& B, Regs& R, int tid, int p) {
+  static_assert(PN <= NT, "one node of a plane per thread");
+  if (tid < PN && p <= B.Lx) {
+    const int n = A.tnode[(size_t)B.n0 + (size_t)p * PN + tid];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { R.pre[0][c] = A.vel[c * A.NnS + n]; R.pre[1][c] = A.disp[c * A.NnS + n]; }
+  }
+}
+// ... and committed to the ring slot of plane p once the step's assembly is over (the slot's previous plane,
+// p - 3, was last read two steps ago)
+EQD_HD void phase_prefetch_commit(const Args& A, const Bundle& B, Shared& sm, const Regs& R, int tid, int p) {
+  if (tid < PN && p <= B.Lx) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      sm.val[p % 3][0][c][tid] = R.pre[0][c];
+      sm.val[p % 3][1][c][tid] = R.pre[1][c] + A.rdampk * R.pre[0][c];
+    }
+  }
 }
 
 // ---- phases q = 0..3: every column adds its completed forces to its (dy(q), dz(q)) node of the plane;
@@ -165,6 +188,20 @@ EQD_HD void phase_flush(const Args& A, const Bundle& B, Shared& sm, int tid, int
     RUN(phase_flush(A, B, sm, tid, (B).Lx));                                              \
   } while (0)
 
+// Prefetch variant of the schedule: one barrier less per step and no exposed load of the next node plane.
+#define MARCH_BUNDLE_PF(RUN, A, B, sm, REGS)                                                                   \
+  do {                                                                                                        \
+    RUN(phase_load_plane(A, B, sm, tid, 0); phase_load_plane(A, B, sm, tid, 1));                              \
+    RUN(phase_begin(sm, REGS, tid));                                                                          \
+    for (int p = 0; p < (B).Lx; ++p) {                                                                        \
+      RUN(phase_prefetch_issue(A, B, REGS, tid, p + 2); phase_element(A, B, sm, REGS, tid, p));               \
+      for (int q = 0; q < 4; ++q) RUN(phase_assemble(sm, REGS, tid, q, false));                               \
+      RUN(phase_flush(A, B, sm, tid, p); phase_prefetch_commit(A, B, sm, REGS, tid, p + 2));                  \
+    }                                                                                                         \
+    for (int q = 0; q < 4; ++q) RUN(phase_assemble(sm, REGS, tid, q, true));                                  \
+    RUN(phase_flush(A, B, sm, tid, (B).Lx));                                                                  \
+  } while (0)
+
 #ifdef __CUDACC__
 // One CTA per bundle at a time, persistent over the bundle list.  (No software pipelining yet: the next
 // plane is loaded synchronously; with < 8 KB of shared memory per CTA occupancy is set by registers.)
@@ -176,6 +213,17 @@ __global__ void __launch_bounds__(NT, 4) k_march_reg(Args A) {
     const Bundle B = A.rec[b];
 #define MK_RUN(body) do { body; __syncthreads(); } while (0)
     MARCH_BUNDLE(MK_RUN, A, B, sm, regs);
+#undef MK_RUN
+  }
+}
+__global__ void __launch_bounds__(NT, 4) k_march_reg_pf(Args A) {
+  __shared__ Shared sm;
+  Regs regs;
+  const int tid = threadIdx.x;
+  for (int b = blockIdx.x; b < A.nBundles; b += gridDim.x) {
+    const Bundle B = A.rec[b];
+#define MK_RUN(body) do { body; __syncthreads(); } while (0)
+    MARCH_BUNDLE_PF(MK_RUN, A, B, sm, regs);
 #undef MK_RUN
   }
 }

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "march_kernel.cuh"
@@ -91,7 +92,8 @@ extern "C" int march_proto(int32_t Nn, int32_t Ne, int32_t nx, int32_t ny, int32
     for (int b = 0; b < A.nBundles; ++b) {
       const Bundle B = A.rec[b];
 #define MK_RUN(body) do { for (int tid = 0; tid < NT; ++tid) { body; } } while (0)
-      MARCH_BUNDLE(MK_RUN, A, B, sm, R[tid]);
+      if (std::getenv("MARCH_PREFETCH")) MARCH_BUNDLE_PF(MK_RUN, A, B, sm, R[tid]);   // the prefetch variant of the schedule
+      else MARCH_BUNDLE(MK_RUN, A, B, sm, R[tid]);
 #undef MK_RUN
     }
   }
