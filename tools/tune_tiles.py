@@ -24,6 +24,9 @@ CONFIGS = [
 for reg, pml in CONFIGS:
     opts = dict(zip(("reg_bx", "reg_bz", "reg_by", "pml_bx", "pml_bz", "pml_by"), reg + pml))
     d = dev.Domain(w.view(0), device=0, compute_ops=True, options=opts)
+    box = int(os.environ.get("EQD_TUNE_BOX", "2"))     # the bench default; 0 = every operator row streamed
+    d.set_option("box", box)
+    d.set_option("box_compact", 1 if box else 0)
     d.set_option("timing", 1)
     d.run(1, 10)
     d.set_option("timing", 2)
