@@ -13,6 +13,9 @@ case = sys.argv[1] if len(sys.argv) > 1 else "bench.tpv104_100m"
 w = World(cases.materialize(case), np_xyz=(1, 1, 1), nstep=600)
 w.build(rank=0, sum_shared=False)
 d = dev.Domain(w.view(0), device=0, compute_ops=True)
+box = int(os.environ.get("EQD_TUNE_BOX", "2"))     # the bench default; 0 = every operator row streamed
+d.set_option("box", box)
+d.set_option("box_compact", 1 if box else 0)
 d.set_option("timing", 1)
 d.run(1, 10)
 nt = 10
