@@ -182,7 +182,9 @@ int eqd_get_timing(const eqd_handle* h, double* ms_slots /*[EQD_T_NSLOTS]*/);
  * "box" (before the first eqd_run / eqd_sum_shared) 0 off (default) / 1 regular
  * classes / 2 also PML: tiles whose elements are all axis-aligned hexahedra
  * (exact test on meshCoor) use eleshp = sign*a_d, phi = ha, ss = diag in closed
- * form and stream 15 instead of 71 (PML: 33 instead of 89) operator rows.
+ * form and stream 15 instead of 71 (PML: 33 instead of 89) operator rows;
+ * "box_compact" 1 = a regular class whose tiles are ALL box tiles uses the kernel
+ * variant whose stage buffer holds only those 15 rows (three CTAs per SM).
  * Unknown keys return 4.  See DESIGN.md sections 3-4.                          */
 int eqd_set_option(eqd_handle* h, const char* key, int32_t value);
 
