@@ -25,7 +25,7 @@ def proto(tmp_path_factory):
 
 
 @pytest.mark.parametrize("prefetch", [0, 1], ids=["sync-planes", "prefetched-planes"])
-@pytest.mark.parametrize("case,min_bundles", [("test.tpv104", 100), ("test.tpv8", 2)])
+@pytest.mark.parametrize("case,min_bundles", [("test.tpv104", 150), ("test.tpv8", 40)])
 def test_marching_forces_equal_element_by_element_forces(proto, case, min_bundles, prefetch, monkeypatch):
     if prefetch:
         monkeypatch.setenv("MARCH_PREFETCH", "1")          # the other schedule of march_kernel.cuh
@@ -39,13 +39,14 @@ def test_marching_forces_equal_element_by_element_forces(proto, case, min_bundle
     disp = np.asfortranarray(rng.standard_normal((3, v.Nn)) * 1e-2)
     fm = np.zeros((3, v.Nn), order="F")
     fr = np.zeros((3, v.Nn), order="F")
-    st = np.zeros(4, dtype=np.int64)
+    st = np.zeros(5, dtype=np.int64)
     P = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
     rc = proto.march_proto(v.Nn, v.Ne, r.nx, r.ny, r.nz, P(v.meshCoor), P(v.nodeElemIdRelation), P(v.elemTypeArr),
                            P(v.numOfDofPerNodeArr), P(v.eleshp), P(v.phi), P(v.ss), P(v.eledet), P(v.mat), P(vel), P(disp),
                            v.params.rdampk, v.params.w, P(fm), P(fr), P(st))
     assert rc == 0, "numbering assumption violated at march_proto.cpp:%d" % rc
-    assert st[0] >= min_bundles and st[1] == st[0] * 32 * 4 * 16
+    assert st[0] >= min_bundles and st[1] % (4 * 16) == 0
+    assert st[1] >= 0.7 * st[4]                            # share of the mesh's regular box elements inside bundles
     assert np.abs(fr).max() > 0
     assert np.abs(fm - fr).max() <= 1e-12 * np.abs(fr).max()
     assert st[3] * 1e-18 <= 1e-12                          # updated stresses, relative to the largest

@@ -16,7 +16,8 @@ using namespace march;
 
 // fm / fr: (3,Nn) nodal forces of the bundle elements by the marching kernel / element by element.
 // dev[0] = largest |stress_march - stress_ref| / largest |stress_ref| after one step with dt.
-// stats: bundles, elements in bundles, rejected lattice positions.  Returns 0 or a line number.
+// stats: bundles, elements in bundles, rejected lattice positions, stress deviation (1e-18 units), regular box
+// elements of the mesh (the most bundles could cover).  Returns 0 or a line number.
 extern "C" int march_proto(int32_t Nn, int32_t Ne, int32_t nx, int32_t ny, int32_t nz, const double* coor, const int32_t* conn,
                            const int32_t* etype, const int32_t* ndof, const double* shp, const double* phi, const double* ss,
                            const double* det, const double* mat, const double* v, const double* d, double rdampk, double w,
@@ -34,17 +35,46 @@ extern "C" int march_proto(int32_t Nn, int32_t Ne, int32_t nx, int32_t ny, int32
     // corner 1 is the cell's (x-,y-,z-) node, unless the fault replaced it by a split-node master (id beyond the grid)
     if (c[0] - 1 != node_id(cx, cy, cz) && c[0] - 1 < grid) return __LINE__;
   }
-  // ---- bundles on a fixed lattice; a bundle qualifies when all its elements are boxes of type 1 on 3-dof
-  // nodes.  Node ids are taken from the connectivity, so split-node masters are welcome.
+  // ---- bundles: the lattice starts at the first regular cell of every axis (behind the PML), restarts in y at
+  // the fault plane (cells on its + side reference split-node masters), and its last bundle in x is shortened
+  // to what is left (>= 8 elements).  A bundle qualifies when all its elements are boxes of type 1 on 3-dof
+  // nodes and agree on their shared corners.  Node ids are taken from the connectivity, so masters are welcome.
+  auto regular_cell = [&](int cx, int cy, int cz) {
+    const int e = elem_of(cx, cy, cz);
+    if (etype[e] != 1) return false;
+    for (int j = 0; j < 8; ++j) if (ndof[conn[8 * (size_t)e + j] - 1] != 3) return false;
+    return true;
+  };
+  auto span = [&](int n, auto&& ok, int& lo, int& hi) {
+    lo = 0; hi = n - 1;
+    while (lo < n && !ok(lo)) ++lo;
+    while (hi > lo && !ok(hi)) --hi;
+  };
+  int xlo, xhi, ylo, yhi, zlo, zhi;
+  span(ncx, [&](int c) { return regular_cell(c, ncy / 4, ncz / 2); }, xlo, xhi);
+  span(ncy, [&](int c) { return regular_cell(ncx / 2, c, ncz / 2); }, ylo, yhi);
+  span(ncz, [&](int c) { return regular_cell(ncx / 2, ncy / 4, c); }, zlo, zhi);
+  int yfault = -1;   // first cell row on the + side of the fault: one of its nodes is a master (id beyond the grid)
+  for (int cy = ylo; cy <= yhi && yfault < 0; ++cy) {
+    const int e = elem_of(ncx / 2, cy, ncz / 2);
+    for (int j = 0; j < 8; ++j) if (conn[8 * (size_t)e + j] - 1 >= grid) yfault = cy;
+  }
+  std::vector<int> ystarts;
+  for (int seg = 0; seg < 2; ++seg) {
+    const int a = seg == 0 ? ylo : (yfault > ylo ? yfault : yhi + 1), b = seg == 0 ? (yfault > ylo ? yfault - 1 : yhi) : yhi;
+    for (int by0 = a; by0 + BY <= b + 1; by0 += BY) ystarts.push_back(by0);
+  }
   std::vector<Bundle> rec;
   std::vector<int> tnode, elemOf;      // plane-ordered node ids; reference element of every bundle element slot
   int64_t nrej = 0;
-  for (int bx0 = 0; bx0 + LX <= ncx; bx0 += LX)
-    for (int bz0 = 0; bz0 + BZ <= ncz; bz0 += BZ)
-      for (int by0 = 0; by0 + BY <= ncy; by0 += BY) {
+  for (int bx0 = xlo; bx0 <= xhi;) {
+    const int LXb = std::min(LX, xhi - bx0 + 1);
+    if (LXb < 8) break;
+    for (int bz0 = zlo; bz0 + BZ <= zhi + 1; bz0 += BZ)
+      for (int by0 : ystarts) {
         bool ok = true;
-        std::vector<int> nodes((size_t)(LX + 1) * PN, -1), elems;
-        for (int p = 0; p < LX && ok; ++p)
+        std::vector<int> nodes((size_t)(LXb + 1) * PN, -1), elems;
+        for (int p = 0; p < LXb && ok; ++p)
           for (int cz = 0; cz < BZ && ok; ++cz)
             for (int cy = 0; cy < BY && ok; ++cy) {
               const int e = elem_of(bx0 + p, by0 + cy, bz0 + cz);
@@ -61,10 +91,12 @@ extern "C" int march_proto(int32_t Nn, int32_t Ne, int32_t nx, int32_t ny, int32
               elems.push_back(e);
             }
         if (!ok) { ++nrej; continue; }
-        rec.push_back(Bundle{(int)elemOf.size(), (int)tnode.size(), LX, 0});
+        rec.push_back(Bundle{(int)elemOf.size(), (int)tnode.size(), LXb, 0});
         elemOf.insert(elemOf.end(), elems.begin(), elems.end());
         tnode.insert(tnode.end(), nodes.begin(), nodes.end());
       }
+    bx0 += LXb;
+  }
   const size_t S = std::max<size_t>(elemOf.size(), 1), NnS = Nn, PFS = std::max<size_t>(tnode.size(), 1);
   // ---- class SoA of the bundle elements (what eqd_compute_elem_ops / eqd_set_elem_ops would fill)
   std::vector<double> ax(S), ay(S), az(S), s0(S), s3(S), s5(S), lam(S), mu(S), dt_(S), stress(6 * S), stressRef;
@@ -148,7 +180,15 @@ extern "C" int march_proto(int32_t Nn, int32_t Ne, int32_t nx, int32_t ny, int32
   }
   double smax = 0, sdev = 0;
   for (size_t k = 0; k < 6 * S && !elemOf.empty(); ++k) { smax = std::max(smax, std::fabs(stressRef[k])); sdev = std::max(sdev, std::fabs(stress[k] - stressRef[k])); }
-  stats[0] = (int64_t)rec.size(); stats[1] = (int64_t)elemOf.size(); stats[2] = nrej;
+  int64_t nRegBox = 0;   // what the bundles could cover at best: type-1 boxes on 3-dof nodes
+  for (int e = 0; e < Ne; ++e) {
+    if (etype[e] != 1) continue;
+    int c0[8];
+    bool three = true;
+    for (int j = 0; j < 8; ++j) { c0[j] = conn[8 * (size_t)e + j] - 1; three = three && ndof[c0[j]] == 3; }
+    if (three && box_element(c0, coor)) ++nRegBox;
+  }
+  stats[0] = (int64_t)rec.size(); stats[1] = (int64_t)elemOf.size(); stats[2] = nrej; stats[4] = nRegBox;
   stats[3] = smax > 0 ? (int64_t)std::llround(1e18 * std::min(sdev / smax, 1.0)) : 0;   // stress deviation in units of 1e-18
   return 0;
 }
