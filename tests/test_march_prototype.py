@@ -24,11 +24,11 @@ def proto(tmp_path_factory):
     return L
 
 
-@pytest.mark.parametrize("prefetch", [0, 1], ids=["sync-planes", "prefetched-planes"])
+@pytest.mark.parametrize("prefetch", [0, 1, 2], ids=["sync-planes", "prefetched-planes", "prefetched-planes-and-operators"])
 @pytest.mark.parametrize("case,min_bundles", [("test.tpv104", 150), ("test.tpv8", 40)])
 def test_marching_forces_equal_element_by_element_forces(proto, case, min_bundles, prefetch, monkeypatch):
     if prefetch:
-        monkeypatch.setenv("MARCH_PREFETCH", "1")          # the other schedule of march_kernel.cuh
+        monkeypatch.setenv("MARCH_PREFETCH", str(prefetch))   # the other schedules of march_kernel.cuh
     else:
         monkeypatch.delenv("MARCH_PREFETCH", raising=False)
     w = parity.build_world(case, (1, 1, 1), 2)
@@ -64,8 +64,8 @@ def test_prototype_kernel_compiles_for_sm_100a_without_spills(tmp_path):
     r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xptxas", "-v",
                         "-c", src, "-o", str(tmp_path / "march_kernel.o")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout
-    assert "k_march_reg" in r.stdout and "k_march_reg_pf" in r.stdout
-    assert r.stdout.count("0 bytes spill stores, 0 bytes spill loads") == 2
+    assert "k_march_reg" in r.stdout and "k_march_reg_pf" in r.stdout and "k_march_reg_pf2" in r.stdout
+    assert r.stdout.count("0 bytes spill stores, 0 bytes spill loads") == 3
     # the stand-alone microbenchmark / GPU-vs-host check built on the same header links
     bench = os.path.join(parity.ROOT, "tools", "proto_march", "march_bench.cu")
     r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

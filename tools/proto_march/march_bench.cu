@@ -3,8 +3,10 @@
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -o march_bench march_bench.cu
 //   ./march_bench --check                 # small block: GPU result against the host reading of the same source
-//   ./march_bench 512 160 256 20 [ctas_per_sm] [prefetch 0|1]   # cells in x, y, z (multiples of 32, 16, 4), timed launches
-//   ./march_bench --check 1               # the same check for the prefetch variant of the schedule
+//   ./march_bench 512 160 256 20 [ctas_per_sm] [variant 0|1|2]  # cells in x, y, z (multiples of 32, 16, 4), timed launches
+//   ./march_bench --check 1 ; ./march_bench --check 2           # the same check for the other schedules
+// variant 0: node planes loaded synchronously; 1: next-but-one plane prefetched through registers; 2: also the next
+// element's operator values (3 CTAs per SM by launch bounds: pass ctas_per_sm = 3).
 //
 // The block is cut into complete 32 x 4 x 16 bundles; node ids are the structured ones (ix*ny*nz + iz*ny + iy),
 // listed plane by plane as the kernel expects.  Operators and nodal fields are pseudo-random: the kernel's
@@ -120,13 +122,13 @@ int main(int argc, char** argv) {
   const bool check = argc > 1 && !std::strcmp(argv[1], "--check");
   Problem P;
   int iters = 20, ctasPerSm = 4;
-  bool prefetch = false;
-  if (check) { P.ncx = 64; P.ncy = 32; P.ncz = 8; iters = 1; prefetch = argc > 2 && std::atoi(argv[2]) != 0; }
+  int variant = 0;
+  if (check) { P.ncx = 64; P.ncy = 32; P.ncz = 8; iters = 1; variant = argc > 2 ? std::atoi(argv[2]) : 0; }
   else {
     P.ncx = argc > 1 ? std::atoi(argv[1]) : 512; P.ncy = argc > 2 ? std::atoi(argv[2]) : 160; P.ncz = argc > 3 ? std::atoi(argv[3]) : 256;
     iters = argc > 4 ? std::atoi(argv[4]) : 20;
     ctasPerSm = argc > 5 ? std::atoi(argv[5]) : 4;
-    prefetch = argc > 6 && std::atoi(argv[6]) != 0;
+    variant = argc > 6 ? std::atoi(argv[6]) : 0;
   }
   if (P.ncx % 32 || P.ncy % BY || P.ncz % BZ || P.ncx <= 0) { std::fprintf(stderr, "cells must be multiples of 32, %d, %d\n", BY, BZ); return 4; }
   build(P);
@@ -141,10 +143,12 @@ int main(int argc, char** argv) {
   cudaStream_t s;
   CK(cudaStreamCreate(&s));
   auto launch = [&] {
-    if (prefetch) k_march_reg_pf<<<grid, NT, 0, s>>>(A);
+    if (variant == 2) k_march_reg_pf2<<<grid, NT, 0, s>>>(A);
+    else if (variant == 1) k_march_reg_pf<<<grid, NT, 0, s>>>(A);
     else k_march_reg<<<grid, NT, 0, s>>>(A);
   };
-  std::printf("schedule: %s\n", prefetch ? "node planes prefetched through registers" : "node planes loaded synchronously");
+  std::printf("schedule %d: %s\n", variant, variant == 2 ? "node planes and operator values prefetched through registers"
+                                              : variant == 1 ? "node planes prefetched through registers" : "node planes loaded synchronously");
   launch();   // warm-up (also the checked launch)
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(s));

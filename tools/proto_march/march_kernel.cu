@@ -3,8 +3,9 @@
 #include "march_kernel.cuh"
 
 namespace march {
-void launch_march(const Args& A, int grid, bool prefetch, cudaStream_t s) {
-  if (prefetch) k_march_reg_pf<<<grid, NT, 0, s>>>(A);
+void launch_march(const Args& A, int grid, int variant, cudaStream_t s) {
+  if (variant == 2) k_march_reg_pf2<<<grid, NT, 0, s>>>(A);
+  else if (variant == 1) k_march_reg_pf<<<grid, NT, 0, s>>>(A);
   else k_march_reg<<<grid, NT, 0, s>>>(A);
 }
 }  // namespace march

@@ -47,6 +47,7 @@ struct Regs {
   double fc[4][3];    // forces on the x+ corners of the previous element, waiting for this element's share
   double fx[4][3];    // completed x- corner forces of this step, consumed by the four assembly phases
   double pre[2][3];   // prefetch variant: v and d of the one node of plane p+2 this thread fetches (PN <= NT)
+  double op[12];      // operator-prefetch variant: the next element's a_d, lam, mu, det, stress (role 0) or ss (role 1)
 };
 
 // shared memory of one CTA
@@ -88,10 +89,40 @@ EQD_HD void phase_begin(Shared& sm, Regs& R, int tid) {
 }
 
 // ---- phase: element (step p, this thread's column): forces from the carried x- values and plane p+1
-EQD_HD void phase_element(const Args& A, const Bundle& B, Shared& sm, Regs& R, int tid, int p) {
+// operator value k of element slot e: role 0: a_x, a_y, a_z, lam, mu, det, stress 1..6; role 1: ss1, ss4, ss6
+EQD_HD double op_value(const Args& A, size_t e, int role, int k) {
+  if (role == 0) {
+    switch (k) {
+      case 0: return A.ax[e];
+      case 1: return A.ay[e];
+      case 2: return A.az[e];
+      case 3: return A.lam[e];
+      case 4: return A.mu[e];
+      case 5: return A.det[e];
+      default: return A.stress[(size_t)(k - 6) * A.S + e];
+    }
+  }
+  return k == 0 ? A.ss0[e] : k == 1 ? A.ss3[e] : A.ss5[e];
+}
+EQD_HD void fetch_ops(const Args& A, const Bundle& B, int tid, int p, double op[12]) {
+  const int role = tid / NCOL, col = tid - role * NCOL;
+  const size_t e = (size_t)B.e0 + (size_t)p * NCOL + col;
+#pragma unroll
+  for (int k = 0; k < 12; ++k)
+    if (role == 0 || k < 3) op[k] = op_value(A, e, role, k);
+}
+// operator-prefetch variant: issue the loads of step p (p < Lx) into R.op
+EQD_HD void phase_ops_issue(const Args& A, const Bundle& B, Regs& R, int tid, int p) {
+  if (p < B.Lx) fetch_ops(A, B, tid, p, R.op);
+}
+
+template <bool OPS_IN_REGS>
+EQD_HD void phase_element_t(const Args& A, const Bundle& B, Shared& sm, Regs& R, int tid, int p) {
   const int role = tid / NCOL, col = tid - role * NCOL, cz = col / BY, cy = col - cz * BY;
   const size_t e = (size_t)B.e0 + (size_t)p * NCOL + col;
   double u[8][3], f[8][3], up[4][3];
+  // fetched during the previous step (operator-prefetch schedule) or read where it is needed
+#define MK_OP(k) (OPS_IN_REGS ? R.op[k] : op_value(A, e, role, k))
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int li = (cz + dz(q)) * (BY + 1) + cy + dy(q);
@@ -103,25 +134,26 @@ EQD_HD void phase_element(const Args& A, const Bundle& B, Shared& sm, Regs& R, i
     }
   }
   if (role == 0) {
-    const double ax = A.ax[e], ay = A.ay[e], az = A.az[e];
+    const double ax = MK_OP(0), ay = MK_OP(1), az = MK_OP(2);
     double g[3][3], sr[6], t[6];
     box_grad(u, g);
     box_strain(g, ax, ay, az, sr);
-    const double lam = A.lam[e], mu = A.mu[e], l2m = lam + 2 * mu;
+    const double lam = MK_OP(3), mu = MK_OP(4), l2m = lam + 2 * mu;
     // calcElemKU.f90:63-76
     const double rate[6] = {0.0 + l2m * sr[0] + lam * sr[1] + lam * sr[2], 0.0 + lam * sr[0] + l2m * sr[1] + lam * sr[2],
                             0.0 + lam * sr[0] + lam * sr[1] + l2m * sr[2], mu * sr[3], mu * sr[4], mu * sr[5]};
-    const double temp = (-A.det[e]) * A.w;     // calcElemKU.f90:169-173, constk = -eledet
+    const double temp = (-MK_OP(5)) * A.w;     // calcElemKU.f90:169-173, constk = -eledet
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-      const double sg = A.stress[k * A.S + e] + rate[k] * A.dt;
+      const double sg = MK_OP(6 + k) + rate[k] * A.dt;
       A.stress[k * A.S + e] = sg;
       t[k] = temp * (sg + A.rdampk * rate[k]);
     }
     box_force(t, ax, ay, az, f);
   } else {
-    box_hourglass(u, A.ss0[e], A.ss3[e], A.ss5[e], f);
+    box_hourglass(u, MK_OP(0), MK_OP(1), MK_OP(2), f);
   }
+#undef MK_OP
 #pragma unroll
   for (int q = 0; q < 4; ++q)
 #pragma unroll
@@ -130,6 +162,10 @@ EQD_HD void phase_element(const Args& A, const Bundle& B, Shared& sm, Regs& R, i
       R.fc[q][c] = f[xp(q)][c];
       R.um[q][c] = up[q][c];
     }
+}
+
+EQD_HD void phase_element(const Args& A, const Bundle& B, Shared& sm, Regs& R, int tid, int p) {
+  phase_element_t<false>(A, B, sm, R, tid, p);
 }
 
 // ---- prefetch variant: the loads of node plane `p` are issued into registers (before the element work of
@@ -202,6 +238,22 @@ EQD_HD void phase_flush(const Args& A, const Bundle& B, Shared& sm, int tid, int
     RUN(phase_flush(A, B, sm, tid, (B).Lx));                                                                  \
   } while (0)
 
+// Third schedule: additionally the next element's operator values travel through registers, so that no global
+// load is waited for inside a step (12 more doubles of state per thread: wants 3 CTAs per SM instead of 4).
+#define MARCH_BUNDLE_PF2(RUN, A, B, sm, REGS)                                                                  \
+  do {                                                                                                        \
+    RUN(phase_load_plane(A, B, sm, tid, 0); phase_load_plane(A, B, sm, tid, 1); phase_ops_issue(A, B, REGS, tid, 0)); \
+    RUN(phase_begin(sm, REGS, tid));                                                                          \
+    for (int p = 0; p < (B).Lx; ++p) {                                                                        \
+      RUN(phase_prefetch_issue(A, B, REGS, tid, p + 2); phase_element_t<true>(A, B, sm, REGS, tid, p);        \
+          phase_ops_issue(A, B, REGS, tid, p + 1));                                                           \
+      for (int q = 0; q < 4; ++q) RUN(phase_assemble(sm, REGS, tid, q, false));                               \
+      RUN(phase_flush(A, B, sm, tid, p); phase_prefetch_commit(A, B, sm, REGS, tid, p + 2));                  \
+    }                                                                                                         \
+    for (int q = 0; q < 4; ++q) RUN(phase_assemble(sm, REGS, tid, q, true));                                  \
+    RUN(phase_flush(A, B, sm, tid, (B).Lx));                                                                  \
+  } while (0)
+
 #ifdef __CUDACC__
 // One CTA per bundle at a time, persistent over the bundle list.  (No software pipelining yet: the next
 // plane is loaded synchronously; with < 8 KB of shared memory per CTA occupancy is set by registers.)
@@ -224,6 +276,17 @@ __global__ void __launch_bounds__(NT, 4) k_march_reg_pf(Args A) {
     const Bundle B = A.rec[b];
 #define MK_RUN(body) do { body; __syncthreads(); } while (0)
     MARCH_BUNDLE_PF(MK_RUN, A, B, sm, regs);
+#undef MK_RUN
+  }
+}
+__global__ void __launch_bounds__(NT, 3) k_march_reg_pf2(Args A) {
+  __shared__ Shared sm;
+  Regs regs;
+  const int tid = threadIdx.x;
+  for (int b = blockIdx.x; b < A.nBundles; b += gridDim.x) {
+    const Bundle B = A.rec[b];
+#define MK_RUN(body) do { body; __syncthreads(); } while (0)
+    MARCH_BUNDLE_PF2(MK_RUN, A, B, sm, regs);
 #undef MK_RUN
   }
 }

@@ -124,7 +124,9 @@ extern "C" int march_proto(int32_t Nn, int32_t Ne, int32_t nx, int32_t ny, int32
     for (int b = 0; b < A.nBundles; ++b) {
       const Bundle B = A.rec[b];
 #define MK_RUN(body) do { for (int tid = 0; tid < NT; ++tid) { body; } } while (0)
-      if (std::getenv("MARCH_PREFETCH")) MARCH_BUNDLE_PF(MK_RUN, A, B, sm, R[tid]);   // the prefetch variant of the schedule
+      const char* variant = std::getenv("MARCH_PREFETCH");        // which schedule of march_kernel.cuh
+      if (variant && variant[0] == '2') MARCH_BUNDLE_PF2(MK_RUN, A, B, sm, R[tid]);
+      else if (variant && variant[0] == '1') MARCH_BUNDLE_PF(MK_RUN, A, B, sm, R[tid]);
       else MARCH_BUNDLE(MK_RUN, A, B, sm, R[tid]);
 #undef MK_RUN
     }
