@@ -225,6 +225,7 @@ struct eqd_handle {
   long launches = 0;
   bool timing = false;
   int optNodeVariant = 4;
+  int optBankOrder = 0;    // 1: bank-aware element order inside the tiles (eqd_tiles.h: TileShape::bankOrder); before eqd_set_mesh
   int optBoxCompact = 0;   // 1: classes whose tiles are ALL box tiles use the compact stage buffer (three CTAs per SM)
   int optBox = 0;   // closed-form operators on all-box tiles (eqd_box.h): 1 = regular classes, 2 = also PML; set before the first eqd_run
   int optTile[2][3] = {{kRegBrick[0], kRegBrick[1], kRegBrick[2]}, {kPmlBrick[0], kPmlBrick[1], kPmlBrick[2]}};  // brick of a regular / PML tile in elements along x, z, y (before eqd_set_mesh)
@@ -934,6 +935,7 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
       sh.bx = ts[0]; sh.bz = ts[1]; sh.by = ts[2];
       if (c == CLS_PML) { sh.capE = 320; sh.capN = EQD_PML_LS; }
       else { sh.capE = 384; sh.capN = EQD_REG_LS; }  // two CTAs per SM
+      sh.bankOrder = h->optBankOrder;
       TilePlan T;
       plan_tiles(h->conn.data(), members[c], Nn, gny, gnz, gridOk, sh, c == CLS_PML ? EQD_STAGE_PML : EQD_STAGE, T);
       C.n = T.n; C.S = T.S; C.nf = nf[c]; C.nstress = nstr[c];
@@ -1734,6 +1736,11 @@ int eqd_set_option(eqd_handle* h, const char* key, int32_t value) {
       }
   }
   if (!strcmp(key, "node_variant")) { h->optNodeVariant = value; return EQD_OK; }
+  if (!strcmp(key, "bank_order")) {
+    if (h->meshSet) { h->err = "eqd_set_option: bank_order must be set before eqd_set_mesh"; return EQD_ERR_ARG; }
+    h->optBankOrder = value != 0;
+    return EQD_OK;
+  }
   if (!strcmp(key, "box_compact")) { h->optBoxCompact = value != 0; return EQD_OK; }
   if (!strcmp(key, "box")) {
     if (h->finalized) { h->err = "eqd_set_option: box must be set before the first eqd_run / eqd_sum_shared"; return EQD_ERR_ARG; }

@@ -149,10 +149,11 @@ void plan_tiles(const int* conn, const std::vector<int>& elems, int Nn, int ny, 
   PlanLap lap;
   // ---- brick key per element
   raw_vector<int> key(n);
+  raw_vector<int> cx, cy, cz;   // grid cell of every element (structured part of the mesh)
   int nKeys = 1;
   if (gridOk) {
     const long nynz = (long)ny * nz;
-    raw_vector<int> cx(n), cy(n), cz(n);
+    cx.resize(n); cy.resize(n); cz.resize(n);
     parallel_for(n, [&](int b, int e) {
       for (int j = b; j < e; ++j) {
         const int* c = conn + 8 * (size_t)elems[j];
@@ -214,6 +215,75 @@ void plan_tiles(const int* conn, const std::vector<int>& elems, int Nn, int ny, 
   lap.lap("split into tiles (node lists)", n);
   std::vector<Tile*> tiles;
   for (auto& v : gt) for (auto& t : v) tiles.push_back(&t);
+  // ---- shared-memory bank model of a tile's element order, and (option) the order that minimises it.
+  // A warp's 8-byte shared-memory access is served half-warp by half-warp; lanes whose words lie in the same
+  // bank pair (local node index mod 16) but at different addresses need one wavefront each.  The kernels read
+  // and update the tile's node rows at index lconn(corner, element), lanes = consecutive elements of a stage.
+  if (sh.bankOrder || std::getenv("EQD_VERBOSE")) {   // the model costs a pass over the elements: not on the default path
+    static_assert(EQD_STAGE % 16 == 0 && EQD_STAGE_PML % 16 == 0, "half-warps must not straddle stages");
+    std::vector<long> ideal(tiles.size(), 0), asc(tiles.size(), 0), chosen(tiles.size(), 0);
+    parallel_for((int)tiles.size(), [&](int tb, int te) {
+      NodeTable tab;
+      std::vector<int> li, perm, best, idx;
+      auto cost = [&](const std::vector<int>& ord, const Tile& T) {
+        long w = 0;
+        const int ne = T.e - T.b;
+        for (int base = 0; base < ne; base += 16) {
+          const int m = std::min(16, ne - base);
+          for (int i = 0; i < 8; ++i) {
+            int mult[16] = {0}, seen[16][16];
+            int wf = 1;
+            for (int l = 0; l < m; ++l) {
+              const int v = li[8 * (size_t)ord[base + l] + i], bk = v & 15;
+              bool dup = false;
+              for (int q = 0; q < mult[bk]; ++q) dup = dup || seen[bk][q] == v;
+              if (!dup) { seen[bk][mult[bk]] = v; wf = std::max(wf, ++mult[bk]); }
+            }
+            w += wf;
+          }
+        }
+        return w;
+      };
+      for (int t = tb; t < te; ++t) {
+        Tile& T = *tiles[t];
+        const int ne = T.e - T.b;
+        tab.clear();
+        for (int i = 0; i < (int)T.nodes.size(); ++i) tab.insert(T.nodes[i], i);
+        li.resize(8 * (size_t)ne);
+        for (int k = 0; k < ne; ++k)
+          for (int i = 0; i < 8; ++i) li[8 * (size_t)k + i] = tab.find(conn[8 * (size_t)elems[order[T.b + k]] + i]);
+        idx.resize(ne);
+        for (int k = 0; k < ne; ++k) idx[k] = k;
+        ideal[t] = 8L * ((ne + 15) / 16);
+        asc[t] = cost(idx, T);
+        chosen[t] = asc[t];
+        if (!sh.bankOrder || !gridOk || asc[t] == ideal[t]) continue;
+        best = idx;
+        // the six orders of the grid axes (slowest .. fastest); ties keep the earlier candidate, ascending id first
+        static const int axes[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};   // 0 = x, 1 = z, 2 = y
+        for (int c = 1; c < 6; ++c) {
+          perm = idx;
+          auto coord = [&](int k, int a) { const int j = order[T.b + k]; return a == 0 ? cx[j] : a == 1 ? cz[j] : cy[j]; };
+          std::stable_sort(perm.begin(), perm.end(), [&](int p, int q) {
+            for (int a = 0; a < 3; ++a) { const int u = coord(p, axes[c][a]), v = coord(q, axes[c][a]); if (u != v) return u < v; }
+            return false;
+          });
+          const long w = cost(perm, T);
+          if (w < chosen[t]) { chosen[t] = w; best = perm; }
+        }
+        if (chosen[t] < asc[t]) {
+          std::vector<int> moved(ne);
+          for (int k = 0; k < ne; ++k) moved[k] = order[T.b + best[k]];
+          for (int k = 0; k < ne; ++k) order[T.b + k] = moved[k];
+        }
+      }
+    });
+    for (size_t t = 0; t < tiles.size(); ++t) { P.bankIdeal += ideal[t]; P.bankAscending += asc[t]; P.bankChosen += chosen[t]; }
+    if (lap.on && n >= 100000)
+      std::fprintf(stderr, "[eqd]   plan_tiles(%d): modelled corner wavefronts ideal %ld, ascending order %ld, chosen order %ld\n", n,
+                   P.bankIdeal, P.bankAscending, P.bankChosen);
+    lap.lap("bank model / element order", n);
+  }
   const int nT = (int)tiles.size();
   P.nTiles = nT;
   P.tileElem.resize(nT); P.tileCnt.resize(nT); P.tileNode.resize(nT + 1); P.tileColours.assign(nT, 1);
@@ -353,6 +423,77 @@ extern "C" int eqd_plan_check(int32_t Nn, int32_t Ne, const int32_t* nodeElemIdR
       }
     }
     for (int e = 0; e < Ne; ++e) if (!seen[e]) return __LINE__;
+  } catch (const std::exception&) {
+    return __LINE__;
+  }
+  return 0;
+}
+
+// ----------------------------------------------------------------------------
+// Host-only model of the tile kernels' shared-memory bank behaviour (no GPU): plans the tiles of the three
+// classes as eqd_set_mesh would, with the element order inside a tile ascending (bank_order = 0) or chosen to
+// minimise conflicts (bank_order = 1, eqd_set_option "bank_order"), and returns per class the modelled
+// wavefronts of the corner accesses: out[3*c + 0..2] = conflict-free, ascending order, chosen order.
+// Also re-checks the planner's invariants for the chosen order.  Returns 0 or a line number.
+extern "C" int eqd_plan_bank_model(int32_t Nn, int32_t Ne, const int32_t* nodeElemIdRelation, const int32_t* elemTypeArr,
+                                   const int32_t* numOfDofPerNodeArr, int32_t bank_order, int64_t* out) {
+  using namespace eqd;
+  if (Nn <= 0 || Ne <= 0 || !nodeElemIdRelation || !elemTypeArr || !numOfDofPerNodeArr || !out) return __LINE__;
+  try {
+    std::vector<int> conn(8 * (size_t)Ne);
+    for (size_t k = 0; k < conn.size(); ++k) {
+      conn[k] = nodeElemIdRelation[k] - 1;
+      if (conn[k] < 0 || conn[k] >= Nn) return __LINE__;
+    }
+    std::vector<int> members[3];
+    for (int e = 0; e < Ne; ++e) {
+      int c = CLS_PML;
+      if (elemTypeArr[e] != 2) {
+        c = CLS_REG;
+        for (int k = 0; k < 8; ++k) if (numOfDofPerNodeArr[conn[8 * (size_t)e + k]] == 12) c = CLS_REGX;
+      }
+      members[c].push_back(e);
+    }
+    int ny = 0, nz = 0;
+    const bool ok = infer_grid(conn.data(), elemTypeArr, Ne, Nn, ny, nz);
+    for (int c = 0; c < 3; ++c) {
+      TileShape sh;
+      if (c == CLS_PML) { sh.bx = kPmlBrick[0]; sh.bz = kPmlBrick[1]; sh.by = kPmlBrick[2]; sh.capE = 320; sh.capN = EQD_PML_LS; }
+      else { sh.bx = kRegBrick[0]; sh.bz = kRegBrick[1]; sh.by = kRegBrick[2]; sh.capE = 384; sh.capN = EQD_REG_LS; }
+      sh.bankOrder = 1;                      // always run the model ...
+      TilePlan P;
+      plan_tiles(conn.data(), members[c], Nn, ny, nz, ok, sh, c == CLS_PML ? EQD_STAGE_PML : EQD_STAGE, P);
+      out[3 * c] = P.bankIdeal; out[3 * c + 1] = P.bankAscending; out[3 * c + 2] = bank_order ? P.bankChosen : P.bankAscending;
+      if (!bank_order || P.n == 0) continue; // ... the chosen order is only checked when asked for
+      // every element exactly once, local connectivity consistent, assembly schedule conflict free
+      std::vector<char> seen(Ne, 0);
+      const int NTP = c == CLS_PML ? EQD_STAGE_PML : EQD_STAGE;
+      for (int t = 0; t < P.nTiles; ++t) {
+        const int nb = P.tileNode[t], ln = P.tileNode[t + 1] - nb;
+        std::vector<int> owner(ln);
+        for (int base = 0; base < P.tileCnt[t]; base += NTP)
+          for (int i = 0; i < 8; ++i)
+            for (int col = 0; col < P.tileColours[t]; ++col) {
+              std::fill(owner.begin(), owner.end(), -1);
+              for (int le = base; le < std::min(P.tileCnt[t], base + NTP); ++le) {
+                const unsigned u = P.lconn[(size_t)i * P.S + (size_t)P.tileElem[t] + le];
+                if ((int)(u >> EQD_LN_BITS) != col) continue;
+                const int li = u & EQD_LN_MASK;
+                if (li >= ln || owner[li] >= 0) return __LINE__;
+                owner[li] = le;
+              }
+            }
+        for (int le = 0; le < P.tileCnt[t]; ++le) {
+          const size_t s = (size_t)P.tileElem[t] + le;
+          const int e = P.refId[s];
+          if (e < 0 || e >= Ne || seen[e]) return __LINE__;
+          seen[e] = 1;
+          for (int i = 0; i < 8; ++i)
+            if (P.tnode[nb + (P.lconn[(size_t)i * P.S + s] & EQD_LN_MASK)] != conn[8 * (size_t)e + i]) return __LINE__;
+        }
+      }
+      for (int e : members[c]) if (!seen[e]) return __LINE__;
+    }
   } catch (const std::exception&) {
     return __LINE__;
   }

@@ -24,6 +24,9 @@ struct TilePlan {
   std::vector<uint8_t> tileColours;  // [nTiles] colours per assembly phase (1 = conflict free)
   raw_vector<int> tnode;          // [PFS] node id per tile-node slot, ascending inside a tile, -1 = padding
   raw_vector<uint16_t> lconn;     // [8][S] tile-local node | colour << 12
+  // modelled shared-memory wavefronts of the 8 corner accesses of every half-warp (16 lanes, 8-byte words: a
+  // wavefront serves one word per bank pair): conflict-free, with ascending element order, with the chosen order
+  long bankIdeal = 0, bankAscending = 0, bankChosen = 0;
 };
 
 // default bricks (elements along x, z, y), measured on TPV104 @ 100 m (tools/tune_tiles.py): a regular
@@ -37,6 +40,9 @@ struct TileShape {
   int bx = 4, bz = 4, by = 32;  // target brick, in elements, along the x / z / y grid axes
   int capE = 640;               // hard cap on elements per tile
   int capN = 1280;              // hard cap on nodes per tile (< 4096: 12-bit local ids)
+  int bankOrder = 0;            // 1: order the elements inside a tile so that a half-warp's 16 gathers / updates of
+                                //    one corner fall into 16 different shared-memory bank pairs where a permutation of
+                                //    the grid axes allows it (0 = ascending reference id: y fastest, then z, then x)
 };
 
 // Node-grid strides of the structured part of the mesh, inferred from a plain

@@ -148,6 +148,13 @@ module eqdyna_cuda_iface
             integer(c_int32_t) :: nodeElemIdRelation(8,*), elemTypeArr(*), numOfDofPerNodeArr(*)
             integer(c_int64_t), intent(out) :: stats(24)
         end function
+        integer(c_int) function eqd_plan_bank_model(Nn, Ne, nodeElemIdRelation, elemTypeArr, numOfDofPerNodeArr, bank_order, wavefronts) &
+                bind(C, name='eqd_plan_bank_model')
+            import :: c_int, c_int32_t, c_int64_t
+            integer(c_int32_t), value :: Nn, Ne, bank_order
+            integer(c_int32_t) :: nodeElemIdRelation(8,*), elemTypeArr(*), numOfDofPerNodeArr(*)
+            integer(c_int64_t), intent(out) :: wavefronts(9)
+        end function
         integer(c_int) function eqd_box_check(Nn, Ne, meshCoor, nodeElemIdRelation, elemTypeArr, eleshp, phi, ss, nBox, dev) &
                 bind(C, name='eqd_box_check')
             import :: c_int, c_int32_t, c_int64_t, c_double

@@ -23,7 +23,7 @@ EXPORTS = [
     "eqd_create", "eqd_destroy", "eqd_last_error", "eqd_set_mesh", "eqd_set_elem_ops", "eqd_compute_elem_ops", "eqd_set_nodal",
     "eqd_set_fault", "eqd_set_halo", "eqd_set_stations", "eqd_get_unique_id", "eqd_set_comm", "eqd_sum_shared",
     "eqd_run", "eqd_run_group", "eqd_fetch", "eqd_get_counts", "eqd_get_timing", "eqd_set_option", "eqd_plan_check",
-    "eqd_box_check", "eqd_get_box_counts",
+    "eqd_box_check", "eqd_get_box_counts", "eqd_plan_bank_model",
 ]
 
 _lib = None
@@ -67,6 +67,7 @@ def lib():
         L.eqd_set_option.argtypes = [vp, cp, i32]
         L.eqd_plan_check.argtypes = [i32, i32, vp, vp, vp, vp]
         L.eqd_box_check.argtypes = [i32, i32] + [vp] * 8
+        L.eqd_plan_bank_model.argtypes = [i32, i32, vp, vp, vp, i32, vp]
         _lib = L
     return _lib
 
@@ -96,6 +97,18 @@ def plan_check(view):
         raise StepError(EQD_ERR_ARG, "tile planner invariant violated (eqd_tiles.cu:%d)" % rc)
     keys = ("tiles", "elements", "slots", "node_slots", "max_tile_nodes", "max_colours", "multi_colour_tiles", "grid")
     return {name: dict(zip(keys, (int(x) for x in st[8 * c:8 * c + 8]))) for c, name in enumerate(("reg", "regx", "pml"))}
+
+
+def plan_bank_model(view, bank_order=0):
+    """Modelled shared-memory wavefronts of the tile kernels' corner accesses on this sub-domain (host only):
+    {class: (conflict-free, ascending element order, order chosen under bank_order)}."""
+    r = view.raw
+    out = np.zeros(9, dtype=np.int64)
+    rc = lib().eqd_plan_bank_model(r.Nn, r.Ne, _ptr(view.nodeElemIdRelation), _ptr(view.elemTypeArr),
+                                   _ptr(view.numOfDofPerNodeArr), int(bank_order), _ptr(out))
+    if rc:
+        raise StepError(EQD_ERR_ARG, "eqd_plan_bank_model: planner invariant violated (eqd_tiles.cu:%d)" % rc)
+    return {name: tuple(int(x) for x in out[3 * c:3 * c + 3]) for c, name in enumerate(("reg", "regx", "pml"))}
 
 
 def box_check(view):

@@ -185,6 +185,8 @@ int eqd_get_timing(const eqd_handle* h, double* ms_slots /*[EQD_T_NSLOTS]*/);
  * form and stream 15 instead of 71 (PML: 33 instead of 89) operator rows;
  * "box_compact" 1 = a regular class whose tiles are ALL box tiles uses the kernel
  * variant whose stage buffer holds only those 15 rows (three CTAs per SM).
+ * "bank_order" (before eqd_set_mesh) 1 = bank-aware element order inside the tiles
+ * (see eqd_plan_bank_model; default 0 = ascending reference id).
  * Unknown keys return 4.  See DESIGN.md sections 3-4.                          */
 int eqd_set_option(eqd_handle* h, const char* key, int32_t value);
 
@@ -197,6 +199,17 @@ int eqd_set_option(eqd_handle* h, const char* key, int32_t value);
 int eqd_plan_check(int32_t Nn, int32_t Ne, const int32_t* nodeElemIdRelation,
                    const int32_t* elemTypeArr, const int32_t* numOfDofPerNodeArr,
                    int64_t* stats);
+
+/* Host-only model of the tile kernels' shared-memory bank conflicts (no GPU needed): plans
+ * the tiles as eqd_set_mesh would and counts, per class, the wavefronts of the half-warps'
+ * 8-byte corner accesses (gathers and force updates index the tile's node rows by local
+ * node): out[9] = {conflict-free, ascending element order, order chosen under bank_order}
+ * x {regular, regular-on-PML-node, PML}.  With bank_order = 1 (eqd_set_option
+ * "bank_order", before eqd_set_mesh) the elements inside a tile are ordered along the grid
+ * axis permutation that minimises the count; the planner's invariants are re-checked.  */
+int eqd_plan_bank_model(int32_t Nn, int32_t Ne, const int32_t* nodeElemIdRelation,
+                        const int32_t* elemTypeArr, const int32_t* numOfDofPerNodeArr,
+                        int32_t bank_order, int64_t* out);
 
 /* Host-only check of the closed-form operators the regular tile kernel uses on
  * axis-aligned hexahedra under eqd_set_option("box", 1) (no GPU needed): for every

@@ -198,3 +198,23 @@ def test_standalone_driver_fails_loudly_without_a_gpu(tmp_path):
     assert not any(f.startswith("frt") for f in os.listdir(str(tmp_path / "out")))
     r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 4 and "usage" in r.stderr
+
+
+@pytest.mark.parametrize("case", ["test.tpv104", "test.tpv36"])
+def test_bank_model_and_bank_aware_element_order(case):
+    """Modelled shared-memory wavefronts of the tile kernels' corner accesses (eqd_plan_bank_model): an
+    ascending element order already is close to conflict-free on the regular class (16-element y runs);
+    the PML bricks (6 x 7 x 6) need about two wavefronts per access, and the bank-aware order
+    (eqd_set_option "bank_order") lowers that without breaking any planner invariant."""
+    from eqdyna_b200 import device
+    w = parity.build_world(case, (1, 1, 1), 2)
+    v = w.view(0)
+    a = device.plan_bank_model(v, 0)
+    b = device.plan_bank_model(v, 1)          # raises if the reordered plan violates an invariant
+    for cls in ("reg", "pml"):
+        ideal, asc, _ = a[cls]
+        assert ideal > 0 and asc >= ideal
+        assert b[cls][0] == ideal and b[cls][1] == asc and ideal <= b[cls][2] <= asc
+    assert a["reg"][1] < 1.35 * a["reg"][0]
+    assert a["pml"][1] > 1.8 * a["pml"][0] and b["pml"][2] < 0.9 * a["pml"][1]
+    w.close()
