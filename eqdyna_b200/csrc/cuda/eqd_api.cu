@@ -1738,7 +1738,7 @@ int eqd_set_option(eqd_handle* h, const char* key, int32_t value) {
   if (!strcmp(key, "node_variant")) { h->optNodeVariant = value; return EQD_OK; }
   if (!strcmp(key, "bank_order")) {
     if (h->meshSet) { h->err = "eqd_set_option: bank_order must be set before eqd_set_mesh"; return EQD_ERR_ARG; }
-    h->optBankOrder = value != 0;
+    h->optBankOrder = value < 0 ? 0 : value > 2 ? 2 : value;
     return EQD_OK;
   }
   if (!strcmp(key, "box_compact")) { h->optBoxCompact = value != 0; return EQD_OK; }

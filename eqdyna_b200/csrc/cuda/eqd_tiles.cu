@@ -215,6 +215,58 @@ void plan_tiles(const int* conn, const std::vector<int>& elems, int Nn, int ny, 
   lap.lap("split into tiles (node lists)", n);
   std::vector<Tile*> tiles;
   for (auto& v : gt) for (auto& t : v) tiles.push_back(&t);
+  // ---- option bankOrder == 2: residue numbering of the tile-local nodes.  For a tile that is a complete brick of
+  // ex x ez x ey grid cells (elements in ascending id = x, z, y order; every node a regular grid node) the local
+  // index of node (ix, iz, iy) is chosen with  index mod 16 == (iy + ey*iz + ey*ez*ix) mod 16 : the corner-c nodes
+  // of 16 consecutive elements then have 16 consecutive residues, i.e. every half-warp access is conflict free.
+  // Nodes of one residue class are numbered 16 apart; classes are not equally large, the gaps stay empty (-1).
+  if (sh.bankOrder == 2 && gridOk) {
+    const long nynz = (long)ny * nz;
+    parallel_for((int)tiles.size(), [&](int tb, int te) {
+      std::vector<int> layout;
+      for (int t = tb; t < te; ++t) {
+        Tile& T = *tiles[t];
+        const int ne = T.e - T.b;
+        int lo[3] = {1 << 30, 1 << 30, 1 << 30}, hi[3] = {-1, -1, -1};
+        for (int k = T.b; k < T.e; ++k) {
+          const int j = order[k];
+          const int c3[3] = {cx[j], cz[j], cy[j]};
+          for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], c3[a]); hi[a] = std::max(hi[a], c3[a]); }
+        }
+        const int ex = hi[0] - lo[0] + 1, ez = hi[1] - lo[1] + 1, ey = hi[2] - lo[2] + 1;
+        if ((long)ex * ez * ey != ne || (long)(ex + 1) * (ez + 1) * (ey + 1) != (long)T.nodes.size()) continue;
+        // every corner must be the regular grid node of its cell corner (no split-node masters, no wedges),
+        // and the elements must come in x, z, y order
+        bool ok = true;
+        for (int k = 0; k < ne && ok; ++k) {
+          const int j = order[T.b + k];
+          const int px = cx[j] - lo[0], pz = cz[j] - lo[1], py = cy[j] - lo[2];
+          if (k != (px * ez + pz) * ey + py) { ok = false; break; }
+          const int* c = conn + 8 * (size_t)elems[j];
+          for (int i = 0; i < 8; ++i) {
+            const long want = (long)(cx[j] + (box_px(i) ? 1 : 0)) * nynz + (long)(cz[j] + (box_pz(i) ? 1 : 0)) * ny + cy[j] + (box_py(i) ? 1 : 0);
+            if (c[i] != want) { ok = false; break; }
+          }
+        }
+        if (!ok) continue;
+        int cnt[16] = {0};
+        auto cls = [&](int ix, int iz, int iy) { return (iy + ey * iz + ey * ez * ix) & 15; };
+        for (int ix = 0; ix <= ex; ++ix) for (int iz = 0; iz <= ez; ++iz) for (int iy = 0; iy <= ey; ++iy) cnt[cls(ix, iz, iy)]++;
+        int mx = 0;
+        for (int q = 0; q < 16; ++q) mx = std::max(mx, cnt[q]);
+        if (16 * mx > sh.capN) continue;                       // does not fit the shared-memory rows: keep ascending ids
+        layout.assign(16 * (size_t)mx, -1);
+        int fill[16] = {0};
+        for (int ix = 0; ix <= ex; ++ix) for (int iz = 0; iz <= ez; ++iz) for (int iy = 0; iy <= ey; ++iy) {
+          const int q = cls(ix, iz, iy);
+          layout[16 * (size_t)fill[q]++ + q] = (int)((long)(lo[0] + ix) * nynz + (long)(lo[1] + iz) * ny + lo[2] + iy);
+        }
+        while (!layout.empty() && layout.back() < 0) layout.pop_back();
+        T.nodes = layout;                                      // position = tile-local index; -1 = unused slot
+      }
+    });
+    lap.lap("residue numbering", n);
+  }
   // ---- shared-memory bank model of a tile's element order, and (option) the order that minimises it.
   // A warp's 8-byte shared-memory access is served half-warp by half-warp; lanes whose words lie in the same
   // bank pair (local node index mod 16) but at different addresses need one wavefront each.  The kernels read
@@ -248,7 +300,7 @@ void plan_tiles(const int* conn, const std::vector<int>& elems, int Nn, int ny, 
         Tile& T = *tiles[t];
         const int ne = T.e - T.b;
         tab.clear();
-        for (int i = 0; i < (int)T.nodes.size(); ++i) tab.insert(T.nodes[i], i);
+        for (int i = 0; i < (int)T.nodes.size(); ++i) if (T.nodes[i] >= 0) tab.insert(T.nodes[i], i);
         li.resize(8 * (size_t)ne);
         for (int k = 0; k < ne; ++k)
           for (int i = 0; i < 8; ++i) li[8 * (size_t)k + i] = tab.find(conn[8 * (size_t)elems[order[T.b + k]] + i]);
@@ -257,7 +309,7 @@ void plan_tiles(const int* conn, const std::vector<int>& elems, int Nn, int ny, 
         ideal[t] = 8L * ((ne + 15) / 16);
         asc[t] = cost(idx, T);
         chosen[t] = asc[t];
-        if (!sh.bankOrder || !gridOk || asc[t] == ideal[t]) continue;
+        if (sh.bankOrder != 1 || !gridOk || asc[t] == ideal[t]) continue;
         best = idx;
         // the six orders of the grid axes (slowest .. fastest); ties keep the earlier candidate, ascending id first
         static const int axes[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};   // 0 = x, 1 = z, 2 = y
@@ -318,7 +370,7 @@ void plan_tiles(const int* conn, const std::vector<int>& elems, int Nn, int ny, 
       const int ln = (int)T.nodes.size();
       std::copy(T.nodes.begin(), T.nodes.end(), P.tnode.begin() + P.tileNode[t]);
       tab.clear();
-      for (int i = 0; i < ln; ++i) tab.insert(T.nodes[i], i);   // node id -> tile-local index (ascending ids)
+      for (int i = 0; i < ln; ++i) if (T.nodes[i] >= 0) tab.insert(T.nodes[i], i);   // node id -> tile-local index
       stamp.assign(8 * (size_t)ln, -1); cnt.assign(8 * (size_t)ln, 0);
       int maxc = 1;
       for (int k = T.b; k < T.e; ++k) {
@@ -460,10 +512,11 @@ extern "C" int eqd_plan_bank_model(int32_t Nn, int32_t Ne, const int32_t* nodeEl
       TileShape sh;
       if (c == CLS_PML) { sh.bx = kPmlBrick[0]; sh.bz = kPmlBrick[1]; sh.by = kPmlBrick[2]; sh.capE = 320; sh.capN = EQD_PML_LS; }
       else { sh.bx = kRegBrick[0]; sh.bz = kRegBrick[1]; sh.by = kRegBrick[2]; sh.capE = 384; sh.capN = EQD_REG_LS; }
-      sh.bankOrder = 1;                      // always run the model ...
+      sh.bankOrder = bank_order == 2 ? 2 : 1;   // always run the model ...
       TilePlan P;
       plan_tiles(conn.data(), members[c], Nn, ny, nz, ok, sh, c == CLS_PML ? EQD_STAGE_PML : EQD_STAGE, P);
-      out[3 * c] = P.bankIdeal; out[3 * c + 1] = P.bankAscending; out[3 * c + 2] = bank_order ? P.bankChosen : P.bankAscending;
+      // bank_order 2: "ascending" already is the count under the residue numbering (the element order is kept)
+      out[3 * c] = P.bankIdeal; out[3 * c + 1] = P.bankAscending; out[3 * c + 2] = bank_order == 1 ? P.bankChosen : P.bankAscending;
       if (!bank_order || P.n == 0) continue; // ... the chosen order is only checked when asked for
       // every element exactly once, local connectivity consistent, assembly schedule conflict free
       std::vector<char> seen(Ne, 0);

@@ -43,6 +43,8 @@ struct TileShape {
   int bankOrder = 0;            // 1: order the elements inside a tile so that a half-warp's 16 gathers / updates of
                                 //    one corner fall into 16 different shared-memory bank pairs where a permutation of
                                 //    the grid axes allows it (0 = ascending reference id: y fastest, then z, then x)
+                                // 2: keep the element order, number the tile-local NODES of complete bricks by residue
+                                //    (index mod 16 == (iy + ey*iz + ey*ez*ix) mod 16): conflict free by construction
 };
 
 // Node-grid strides of the structured part of the mesh, inferred from a plain

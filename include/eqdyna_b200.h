@@ -185,8 +185,9 @@ int eqd_get_timing(const eqd_handle* h, double* ms_slots /*[EQD_T_NSLOTS]*/);
  * form and stream 15 instead of 71 (PML: 33 instead of 89) operator rows;
  * "box_compact" 1 = a regular class whose tiles are ALL box tiles uses the kernel
  * variant whose stage buffer holds only those 15 rows (three CTAs per SM).
- * "bank_order" (before eqd_set_mesh) 1 = bank-aware element order inside the tiles
- * (see eqd_plan_bank_model; default 0 = ascending reference id).
+ * "bank_order" (before eqd_set_mesh) 1 = bank-aware element order inside the tiles,
+ * 2 = residue numbering of the tile-local nodes of complete bricks (conflict free by
+ * construction; see eqd_plan_bank_model; default 0 = ascending ids).
  * Unknown keys return 4.  See DESIGN.md sections 3-4.                          */
 int eqd_set_option(eqd_handle* h, const char* key, int32_t value);
 
@@ -206,7 +207,9 @@ int eqd_plan_check(int32_t Nn, int32_t Ne, const int32_t* nodeElemIdRelation,
  * node): out[9] = {conflict-free, ascending element order, order chosen under bank_order}
  * x {regular, regular-on-PML-node, PML}.  With bank_order = 1 (eqd_set_option
  * "bank_order", before eqd_set_mesh) the elements inside a tile are ordered along the grid
- * axis permutation that minimises the count; the planner's invariants are re-checked.  */
+ * axis permutation that minimises the count; with bank_order = 2 the element order is kept and
+ * the tile-local nodes of complete bricks are numbered by residue instead (out[.+2] is then
+ * the count under that numbering).  The planner's invariants are re-checked.            */
 int eqd_plan_bank_model(int32_t Nn, int32_t Ne, const int32_t* nodeElemIdRelation,
                         const int32_t* elemTypeArr, const int32_t* numOfDofPerNodeArr,
                         int32_t bank_order, int64_t* out);

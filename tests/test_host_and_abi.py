@@ -217,4 +217,10 @@ def test_bank_model_and_bank_aware_element_order(case):
         assert b[cls][0] == ideal and b[cls][1] == asc and ideal <= b[cls][2] <= asc
     assert a["reg"][1] < 1.35 * a["reg"][0]
     assert a["pml"][1] > 1.8 * a["pml"][0] and b["pml"][2] < 0.9 * a["pml"][1]
+    # bank_order = 2: residue numbering of the tile-local nodes of complete bricks (element order kept):
+    # the regular class becomes all but conflict free; PML bricks of 6 x 7 x 6 do not fit the 400-node rows
+    # (448 needed) and keep ascending ids, smaller ones are renumbered
+    c = device.plan_bank_model(v, 2)
+    assert c["reg"][2] < 1.12 * c["reg"][0] and c["reg"][2] < a["reg"][1]
+    assert c["pml"][2] < a["pml"][1]
     w.close()

@@ -102,11 +102,12 @@ RUN_SCRIPT = textwrap.dedent(r"""
         w = parity.build_world(case, npx, 6)
         if case == "test.tpv36":
             # options that shape the upload go in before eqd_set_mesh: bank-aware element order inside the tiles
-            d0 = dev.Domain(w.view(0), options={"bank_order": 1})
-            d0.set_option("box", 2)
-            d0.run(1, 3)
-            assert d0.counts()["launches"] > 0 and d0.box_counts()["regular"] > 0
-            d0.close()
+            for bo in (1, 2):
+                d0 = dev.Domain(w.view(0), options={"bank_order": bo})
+                d0.set_option("box", 2)
+                d0.run(1, 3)
+                assert d0.counts()["launches"] > 0 and d0.box_counts()["regular"] > 0
+                d0.close()
         doms = parity.run_gpu(w, options=opts)          # kernels are no-ops here: launch sequence, halo plumbing, fetches
         nbox = sum(d.box_counts()["regular"] for d in doms)
         nreg = sum(d.counts()["regular"] for d in doms)
