@@ -20,9 +20,13 @@ CONFIGS = [
     ((4, 4, 16), (6, 8, 5)),
     ((2, 4, 21), (6, 7, 6)),
     ((3, 3, 14), (6, 7, 6)),
+    # worth re-timing with EQD_TUNE_BANK_ORDER=2 (conflict free under the residue numbering, fewer node slots per element):
+    ((4, 4, 14), (6, 5, 6)),
+    ((5, 4, 12), (4, 7, 6)),
 ]
 for reg, pml in CONFIGS:
     opts = dict(zip(("reg_bx", "reg_bz", "reg_by", "pml_bx", "pml_bz", "pml_by"), reg + pml))
+    opts["bank_order"] = int(os.environ.get("EQD_TUNE_BANK_ORDER", "0"))   # 1: element order, 2: residue node numbering
     d = dev.Domain(w.view(0), device=0, compute_ops=True, options=opts)
     box = int(os.environ.get("EQD_TUNE_BOX", "2"))     # the bench default; 0 = every operator row streamed
     d.set_option("box", box)
