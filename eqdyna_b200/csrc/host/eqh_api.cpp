@@ -62,6 +62,18 @@ int eqh_world_set_switch(eqh_world* w, const char* name, double value) {
     else if (n == "outputGroundMotion") w->in.outputGroundMotion = (int)value;   // before eqh_world_build: it sizes the sample arrays
     else if (n == "outputFinalSurfDisp") w->in.outputFinalSurfDisp = (int)value;
     else if (n == "output_plastic") w->in.output_plastic = (int)value;
+    // run-time parameters of bGlobal.txt (readInputFiles.f90:28-58,182-186): tests use them to reach the
+    // branches no shipped case takes (friclaw 3, TPV 2802 / 201 / 202, Drucker-Prager yielding)
+    else if (n == "friclaw") w->in.friclaw = (int)value;
+    else if (n == "TPV") w->in.TPV = (int)value;
+    else if (n == "C_nuclea") w->in.C_nuclea = (int)value;
+    else if (n == "ccosphi") w->in.ccosphi = value;
+    else if (n == "sinphi") w->in.sinphi = value;
+    else if (n == "tv") w->in.tv = value;
+    else if (n == "nucR") w->in.nucR = value;
+    else if (n == "nucT") w->in.nucT = value;
+    else if (n == "nucRuptVel") w->in.nucRuptVel = value;
+    else if (n == "nucdtau0") w->in.nucdtau0 = value;
     else throw std::runtime_error("eqh_world_set_switch: unknown switch " + n);
     if (w->in.C_elastic == 0 && w->in.C_Q == 1) throw std::runtime_error("Q model can only work with elastic code (stop 1001)");
   });

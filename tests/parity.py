@@ -57,10 +57,15 @@ def series_err(G, O, floor_rel=1.0e-6, unit=0.0):
     return worst
 
 
-def build_world(case, np_xyz=None, nstep=0, switches=None):
+def build_world(case, np_xyz=None, nstep=0, switches=None, pre_switches=None):
+    """switches are applied after the build (run-time parameters), pre_switches before it
+    (those that size arrays: outputGroundMotion, ...)."""
     from eqdyna_b200 import cases
     from eqdyna_b200.host import World
-    w = World(cases.materialize(case), np_xyz=np_xyz, nstep=nstep).build()
+    w = World(cases.materialize(case), np_xyz=np_xyz, nstep=nstep)
+    for k, v in (pre_switches or {}).items():
+        w.set_switch(k, v)
+    w.build()
     for k, v in (switches or {}).items():
         w.set_switch(k, v)
     return w

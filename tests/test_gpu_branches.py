@@ -1,0 +1,101 @@
+"""Parity tests (-m gpu) of the branches no shipped case takes: the Drucker-Prager return mapping
+(calcElemKU.f90:133-167), the rate-and-state ageing law (fric.f90:39-61), the TPV 2802 / 201 / 202
+nucleation variants (faulting.f90:367-443) and the every-10th-step output samples
+(driver.f90:30-33, library_output.f90:267-312).  Same protocol as test_gpu_parity.py: the CUDA step
+library through its C ABI against the CPU oracle on the same inputs, BASELINE.json tolerances
+(1e-6 relative L2, rupture time within one step).  The inputs are the shipped cases with one
+run-time parameter of bGlobal.txt changed (World.set_switch), applied to both sides."""
+import numpy as np
+import pytest
+
+import parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _both(case, np_xyz, nstep, switches=None, pre_switches=None, prepare=None, options=None):
+    wg = parity.build_world(case, np_xyz, nstep, switches, pre_switches)
+    wo = parity.build_world(case, np_xyz, nstep, switches, pre_switches)
+    if prepare:
+        prepare(wg)
+        prepare(wo)
+    doms = parity.run_gpu(wg, options=options)
+    parity.run_oracle(wo)
+    return wg, wo, doms, parity.compare_worlds(wg, wo)
+
+
+@pytest.mark.parametrize("sinphi,min_frac", [(0.33, 0.30), (0.34, 0.005)], ids=["half-yield", "one-percent-yield"])
+def test_drucker_prager_return_mapping(sinphi, min_frac):
+    """test.drv.a6 with the off-fault strength lowered (cohesion 0, sin(phi) 0.33 / 0.34 instead of 0.6):
+    54 % / 1 % of the elements sit on the yield surface from the first step, so `taomax > yield`, the
+    radial return `rjust`, the plastic-strain increment and the viscoplastic relaxation exp(-dt/tv)
+    all execute (at the shipped strength nothing ever yields)."""
+    wg, wo, doms, res = _both("test.drv.a6", (2, 2, 1), 12, switches={"ccosphi": 0.0, "sinphi": sinphi})
+    ne = sum(wo.view(r).Ne for r in range(wo.size))
+    yo = sum(int((wo.view(r).pstrain > 0).sum()) for r in range(wo.size))
+    yg = sum(int((wg.view(r).pstrain > 0).sum()) for r in range(wg.size))
+    assert yo >= min_frac * ne, "only %d of %d elements yielded in the oracle" % (yo, ne)
+    assert abs(yg - yo) <= 1e-4 * ne, (yg, yo)       # elements grazing the yield surface may differ by rounding
+    for k in ("disp", "vel", "v1", "accel", "stress", "pstrain", "station.vel", "station.disp"):
+        assert res.get(k, 0.0) <= 1e-6, (k, res[k])
+    assert res["rupt_mismatch"] == 0
+
+
+def _ageing_state(w):
+    """initial state of the ageing law equivalent to the case's slip-law psi:
+    psi = f0 + b ln(V0 theta / L)  (fric.f90:50 vs :76)"""
+    for r in range(w.size):
+        v = w.view(r)
+        k = int(v.nftnd[0])
+        if k:
+            f = v.fric
+            f[19, :k, 0] = f[10, :k, 0] / f[11, :k, 0] * np.exp((f[19, :k, 0] - f[12, :k, 0]) / f[9, :k, 0])
+
+
+def test_rate_state_ageing_law():
+    """friclaw = 3 (rate_state_ageing_law, fric.f90:39-61) on TPV104's fault, nucleated as TPV104."""
+    wg, wo, doms, res = _both("test.tpv104", (2, 2, 1), 60, switches={"friclaw": 3}, prepare=_ageing_state)
+    parity.assert_parity(res)
+    v = wo.view(0)
+    assert int((v.fnft[:int(v.nftnd[0]), 0] < 5000.0).sum()) > 0, "nothing ruptured: the solve was never exercised"
+
+
+def test_tpv2802_nucleation():
+    """TPV = 2802 (rsfNucleation, faulting.f90:381-392): the state variable and theta_pc are re-derived from
+    the stress ratio at nt = 1 and the perturbation amplitude is carried in fric(81)."""
+    wg, wo, doms, res = _both("test.tpv104", (2, 2, 1), 60, switches={"TPV": 2802})
+    parity.assert_parity(res)
+    v = wo.view(0)
+    k = int(v.nftnd[0])
+    assert float(v.fric[80, :k, 0].max()) == v.params.nucdtau0 and int((v.fnft[:k, 0] < 5000.0).sum()) > 50
+
+
+@pytest.mark.parametrize("tpv,extra", [(201, {}), (202, {"nucRuptVel": 2000.0})], ids=["tpv201", "tpv202"])
+def test_forced_rupture_front_variants(tpv, extra):
+    """swtwNucleation (faulting.f90:416-443) with TPV = 201 (same front as 36 / 37) and 202 (constant
+    nucRuptVel), on the shallow-thrust mesh of test.tpv37."""
+    sw = {"TPV": tpv}
+    sw.update(extra)
+    wg, wo, doms, res = _both("test.tpv37", (2, 2, 1), 70, switches=sw)
+    parity.assert_parity(res)
+    ruptured = sum(int((wo.view(r).fnft[:int(wo.view(r).nftnd[0]), 0] < 5000.0).sum()) for r in range(wo.size))
+    assert ruptured > 0
+
+
+def test_ground_motion_and_source_evolution_samples():
+    """outputGroundMotion = 1: k_sample_gm / k_sample_src take the samples output_gm / output_src_evol append
+    at every step with mod(nt,10) == 1 (driver.f90:30-33); fetched as EQD_F_GM / EQD_F_SRC_EVOL."""
+    nstep = 45
+    wg, wo, doms, res = _both("test.tpv8", (2, 2, 1), nstep, pre_switches={"outputGroundMotion": 1})
+    parity.assert_parity(res)
+    moved = False
+    for r in range(wo.size):
+        g, o = wg.view(r), wo.view(r)
+        assert int(g.nGmSamples[0]) == int(o.nGmSamples[0]) == 5
+        if o.gmHist is not None:
+            assert parity.rel_l2(g.gmHist[:, :, :5], o.gmHist[:, :, :5], unit=1.0e-3) <= 1e-6
+            # the sampled steps are velArr of steps 1, 11, 21, 31, 41: the last one equals no later state
+            moved = moved or float(np.abs(o.gmHist[:, :, :5]).max()) > 0
+        if o.srcEvolHist is not None:
+            assert parity.rel_l2(g.srcEvolHist[:, :5], o.srcEvolHist[:, :5], unit=1.0) <= 1e-6
+    assert moved, "no ground motion reached the surface: the samples would be trivially equal"

@@ -81,8 +81,11 @@ def test_plastic_path_short_horizon():
     for k in ("disp", "vel", "v1", "stress", "pstrain", "station.vel", "station.disp"):
         assert res.get(k, 0.0) <= 1e-6, (k, res[k])
     assert res["fric.traction"] <= 1e-6 and res["rupt_mismatch"] == 0
-    # yielding actually happened in the window that was compared
-    assert any(float(wo.view(r).pstrain.max()) > 0 for r in range(wo.size)) or True
+    # At the shipped strength (cohesion 4 MPa, sin(phi) = 0.6) no element of this case ever yields
+    # (the oracle's pstrain stays 0 over all 120 steps): this test covers gravity, pore pressure and the
+    # yield function only.  The return mapping itself (calcElemKU.f90:133-167) is exercised by
+    # tests/test_gpu_branches.py::test_drucker_prager_return_mapping, where half of the elements yield.
+    assert all(float(wo.view(r).pstrain.max()) == 0.0 for r in range(wo.size))
 
 
 def test_chunked_runs_and_determinism():

@@ -24,6 +24,8 @@ CONFIGS = [
     ((4, 4, 14), (6, 5, 6)),
     ((5, 4, 12), (4, 7, 6)),
 ]
+if len(sys.argv) > 2:            # tune_tiles.py CASE N: only the first N configurations
+    CONFIGS = CONFIGS[:int(sys.argv[2])]
 for reg, pml in CONFIGS:
     opts = dict(zip(("reg_bx", "reg_bz", "reg_by", "pml_bx", "pml_bz", "pml_by"), reg + pml))
     opts["bank_order"] = int(os.environ.get("EQD_TUNE_BANK_ORDER", "0"))   # 1: element order, 2: residue node numbering
