@@ -29,7 +29,11 @@ if len(sys.argv) > 2:            # tune_tiles.py CASE N: only the first N config
 for reg, pml in CONFIGS:
     opts = dict(zip(("reg_bx", "reg_bz", "reg_by", "pml_bx", "pml_bz", "pml_by"), reg + pml))
     opts["bank_order"] = int(os.environ.get("EQD_TUNE_BANK_ORDER", "0"))   # 1: element order, 2: residue node numbering
-    d = dev.Domain(w.view(0), device=0, compute_ops=True, options=opts)
+    try:
+        d = dev.Domain(w.view(0), device=0, compute_ops=True, options=opts)
+    except Exception as e:  # noqa: BLE001 -- a brick that does not fit the node cap: report and go on
+        print("reg %s pml %s: rejected (%s)" % (reg, pml, str(e)[:120]), flush=True)
+        continue
     box = int(os.environ.get("EQD_TUNE_BOX", "2"))     # the bench default; 0 = every operator row streamed
     d.set_option("box", box)
     d.set_option("box_compact", 1 if box else 0)
