@@ -35,7 +35,10 @@ def test_drucker_prager_return_mapping(sinphi, min_frac):
     yo = sum(int((wo.view(r).pstrain > 0).sum()) for r in range(wo.size))
     yg = sum(int((wg.view(r).pstrain > 0).sum()) for r in range(wg.size))
     assert yo >= min_frac * ne, "only %d of %d elements yielded in the oracle" % (yo, ne)
-    assert abs(yg - yo) <= 1e-4 * ne, (yg, yo)       # elements grazing the yield surface may differ by rounding
+    # the uniform prestress puts whole depth ranges within rounding of the yield surface (taomax == yield to
+    # ~1e-16): whether such an element counts as yielded differs between the two roundings (897 of 1.07 M
+    # elements on the B200), its plastic strain increment is zero to the same precision either way
+    assert abs(yg - yo) <= 2e-3 * ne, (yg, yo)
     for k in ("disp", "vel", "v1", "accel", "stress", "pstrain", "station.vel", "station.disp"):
         assert res.get(k, 0.0) <= 1e-6, (k, res[k])
     assert res["rupt_mismatch"] == 0
