@@ -21,7 +21,7 @@ LIBDIR = os.path.join(PKG, "lib")
 ORACLE = os.path.join(ROOT, "oracle")
 
 HOST_SRCS = ["eqh_io.cpp", "eqh_mesh.cpp", "eqh_mass.cpp", "eqh_api.cpp"]
-CUDA_SRCS = ["eqd_api.cu", "eqd_kernels.cu", "eqd_tiles.cu", "eqd_ops.cu"]
+CUDA_SRCS = ["eqd_api.cu", "eqd_kernels.cu", "eqd_tiles.cu", "eqd_ops.cu", "eqd_march.cu"]
 # the operator precompute must round like the reference build (no FMA contraction)
 CUDA_FILE_FLAGS = {"eqd_ops.cu": ["--fmad=false"]}
 

@@ -20,6 +20,7 @@
 #include "eqd_box.h"
 #include "eqd_dev.cuh"
 #include "eqd_kernels.h"
+#include "eqd_march_plan.h"
 #include "eqd_par.h"
 #include "eqd_tiles.h"
 #include "eqdyna_b200.h"
@@ -182,7 +183,17 @@ struct eqd_handle {
   int NnS = 0, Np = 0, NpS = 0;
   bool body = false, plastic = false, qmode = false;
   // ---- device
-  ElemClass cls[3];
+  ElemClass cls[NCLS];
+  // marching class (CLS_MARCH, eqd_march.h): bundles of box elements; cls[CLS_MARCH] holds its SoA rows
+  // (shp = [3][S] a_x a_y a_z, ss = [3][S] the diagonal, no phi), refId, partial buffer and node ids
+  DevBuf<MarchBundle> mRec;
+  DevBuf<int> mCtaFirst, mCode, mSlotBundle;
+  int mGrid = 0, mBundles = 0;
+  long mFused = 0;
+  int optMarch = 0;         // option "march" (before eqd_set_mesh)
+  bool sweepFused = false;  // the last element sweep updated the fused nodes itself
+  DevBuf<int> dNodeList;    // free 3-dof nodes no bundle updates, ascending (list variant of the node update)
+  int nNodeList = 0;
   DevBuf<int> dInfo, dPmlNode, dSpecial;
   DevBuf<uint8_t> dSlotCnt;
   DevBuf<uint32_t> dSlotTab;
@@ -234,6 +245,7 @@ struct eqd_handle {
 
   NodeArgs nodeArgs() const;
   ElemArgs elemArgs(int c) const;
+  MarchArgs marchArgs(bool update) const;
   FaultArgs faultArgs() const;
 };
 
@@ -342,6 +354,8 @@ NodeArgs eqd_handle::nodeArgs() const {
   A.pfR = cls[CLS_REG].pf.p; A.SR = cls[CLS_REG].PFS;
   A.pfX = cls[CLS_REGX].pf.p; A.SX = cls[CLS_REGX].PFS;
   A.pfP = cls[CLS_PML].pf.p; A.SP = cls[CLS_PML].PFS;
+  A.pfM = cls[CLS_MARCH].pf.p; A.SM = cls[CLS_MARCH].PFS;
+  A.list = nullptr; A.nList = 0; A.fusedMode = 1;
   A.accel0 = nullptr; A.skipSpecial = 0; A.variant = optNodeVariant;
   A.dt = p.dt;
   A.st = dState.p;
@@ -367,6 +381,17 @@ ElemArgs eqd_handle::elemArgs(int c) const {
   A.kapa_hg = p.kapa_hg;
   A.tileBox = C.tileBox.n ? C.tileBox.p : nullptr;
   A.allBox = (optBoxCompact && C.tileBox.n && C.nBoxElems == C.n) ? 1 : 0;
+  return A;
+}
+
+MarchArgs eqd_handle::marchArgs(bool update) const {
+  const ElemClass& C = cls[CLS_MARCH];
+  MarchArgs A{};
+  A.rec = mRec.p; A.ctaFirst = mCtaFirst.p; A.code = mCode.p;
+  A.S = (size_t)C.S; A.NnS = (size_t)NnS; A.PFS = (size_t)C.PFS;
+  A.a = C.shp.p; A.ss = C.ss.p; A.lam = C.lam.p; A.mu = C.mu.p; A.det = C.det.p; A.stress = C.stress.p;
+  A.vel = dVel.p; A.disp = dDisp.p; A.mass = dMass.p; A.pf = C.pf.p; A.force = dForce.p;
+  A.dt = p.dt; A.rdampk = p.rdampk; A.w = p.w; A.update = update ? 1 : 0; A.st = dState.p;
   return A;
 }
 
@@ -528,6 +553,18 @@ void finalize(eqd_handle* h) {
       list.push_back(n);
       (onFace[n] ? listA : listB).push_back(n);
     }
+  if (h->cls[CLS_MARCH].n) {
+    // a node a bundle updates itself is interior to the bundle: no split node (the planner cuts where elements stop
+    // sharing nodes), no rank-face node (a face bounds the sub-domain's elements)
+    for (int n : list)
+      if (EQD_INFO_KIND(h->info[n]) == KIND_FREE3 && EQD_INFO_FUSED(h->info[n])) throw ArgError("internal: node " + std::to_string(n + 1) + " is both fused and special");
+    std::vector<int> rest;
+    rest.reserve((size_t)Nn - (size_t)h->mFused);
+    for (int n = 0; n < Nn; ++n)
+      if (EQD_INFO_KIND(h->info[n]) == KIND_FREE3 && !EQD_INFO_FUSED(h->info[n])) rest.push_back(n);
+    h->nNodeList = (int)rest.size();
+    h->dNodeList.upload(rest);
+  }
   h->nSpecial = (int)list.size();
   h->dSpecial.upload(list);
   h->nSpecialA = (int)listA.size(); h->nSpecialB = (int)listB.size();
@@ -667,14 +704,19 @@ void launch_fault_phase(eqd_handle* h, cudaStream_t st) {
 //            node (those are updated by k_node_update_special after the join).
 //   ov == 2  additionally the tiles touching a rank face are swept first and the
 //            halo starts while the interior tiles are still being swept.
-void step_pre(eqd_handle* h, int ov, bool multi) {
+//   last     the last step of this eqd_run call: the marching kernel then leaves the complete force of the
+//            nodes it would update itself in force[] instead, so that the caller sees v(nt), d(nt) and
+//            f/m as the reference leaves them; the next call's first node update picks them up there.
+void step_pre(eqd_handle* h, int ov, bool multi, bool last) {
   const eqd_params& P = h->p;
   cudaStream_t s = h->stream, c = h->commStream;
+  const bool marching = h->cls[CLS_MARCH].n > 0;
   {
     Timer t(h, EQD_T_NODE);
     NodeArgs A = h->nodeArgs();
     if (h->dAccel0.p) A.accel0 = h->dAccel0.p;
     A.skipSpecial = ov ? 1 : 0;
+    if (marching && h->sweepFused) { A.list = h->dNodeList.p; A.nList = h->nNodeList; A.fusedMode = 2; }
     launch_node_update(A, s); h->launches += h->Np > 0 ? 2 : 1;
     t.stop();
     if (ov) {
@@ -688,10 +730,19 @@ void step_pre(eqd_handle* h, int ov, bool multi) {
       launch_store_offfault(h->dIdhist.p, 6 * h->nOff, h->dOffHist.p, h->dVel.p, h->dDisp.p, h->NnS, h->dState.p, s);
       h->launches++;
     }
+    if (P.outputGroundMotion && (h->hostNt + 1) % 10 == 1 && h->dGm.p) {
+      // output_gm (driver.f90:30-33): velArr of this step, before the element sweep moves the fused nodes on
+      launch_sample_gm(h->dSurf.p, h->nSurf, h->dVel.p, h->NnS, h->dGm.p + 3 * (size_t)h->nSurf * h->nGm, s); h->launches++;
+    }
     t2.stop();
   }
   if (h->dAccel0.p) { CK(cudaStreamSynchronize(s)); h->dAccel0.release(); }
   auto sweep = [&](int part) {   // 0: all tiles, 1: rank-face tiles, 2: interior tiles
+    if (marching && part != 1) {
+      Timer t(h, EQD_T_MARCH);
+      launch_march(h->marchArgs(!last), h->mGrid, s); h->launches++;
+      t.stop();
+    }
     for (int k = 0; k < 3; ++k) {
       ElemClass& C = h->cls[k];
       if (!C.n) continue;
@@ -711,7 +762,8 @@ void step_pre(eqd_handle* h, int ov, bool multi) {
     if (n) { launch_assemble_special(h->nodeArgs(), list.p, n, s); h->launches++; }
     t.stop();
   };
-  const bool split = ov == 2 && multi && h->anyFace;
+  // (the bundles' rank-face nodes leave partials like any tile node: with bundles the face tiles cannot go first)
+  const bool split = ov == 2 && multi && h->anyFace && !marching;
   if (!split) {
     sweep(0);
     assemble(h->dSpecial, h->nSpecial);
@@ -724,6 +776,7 @@ void step_pre(eqd_handle* h, int ov, bool multi) {
     sweep(2);
     assemble(h->dSpecialB, h->nSpecialB);
   }
+  h->sweepFused = marching && !last;
   if (ov) {
     CK(cudaEventRecord(h->evElem, s));
     CK(cudaStreamWaitEvent(c, h->evElem, 0));
@@ -738,11 +791,7 @@ void step_post(eqd_handle* h, int ov) {
   if (ov) CK(cudaEventRecord(h->evComm, h->commStream));
   h->hostNt++;
   h->hostTime = h->hostTime + P.dt;
-  if (P.outputGroundMotion && h->hostNt % 10 == 1) {
-    // velArr of this step: written by the node updates on the main stream
-    if (h->dGm.p) { launch_sample_gm(h->dSurf.p, h->nSurf, h->dVel.p, h->NnS, h->dGm.p + 3 * (size_t)h->nSurf * h->nGm, s); h->launches++; }
-    h->nGm++;
-  }
+  if (P.outputGroundMotion && h->hostNt % 10 == 1) h->nGm++;   // the samples of this step: step_pre (gm), launch_fault_phase (src_evol)
 }
 
 void prepare_run(eqd_handle* h, int nt_begin) {
@@ -927,6 +976,46 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
     int gny = 0, gnz = 0;
     const bool gridOk = infer_grid(h->conn.data(), h->etype.data(), Ne, Nn, gny, gnz);
     h->elemCode.assign(Ne, 0);
+    // ---- marching class: the box elements of the structured lattice leave the regular tile class (option "march";
+    // the kernel covers the elastic path with Kosloff-Frazier hourglass control and no body force)
+    {
+      ElemClass& M = h->cls[CLS_MARCH];
+      M.n = 0; M.S = 32; M.PFS = 4; M.nTiles = 0; M.nf = 3; M.nstress = 6;
+      h->mGrid = 0; h->mBundles = 0; h->mFused = 0;
+      const bool eligible = h->optMarch && gridOk && !h->plastic && !h->qmode && !h->body && P.C_hg == 1;
+      if (eligible && !members[CLS_REG].empty()) {
+        int dev = 0, sms = 148;
+        CK(cudaGetDevice(&dev));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const int perSm = march_ctas_per_sm();
+        need(perSm > 0, "option march: the marching kernel does not fit this device");
+        MarchPlan MP;
+        plan_march(h->conn.data(), h->etype.data(), h->coor.data(), h->info.data(), members[CLS_REG], Nn, gny, gnz, perSm * sms, MP);
+        if (MP.n > 0) {
+          M.n = MP.n; M.S = MP.S; M.PFS = MP.PFS;
+          h->mGrid = MP.grid; h->mBundles = (int)MP.rec.size(); h->mFused = MP.nFused;
+          h->mRec.upload(MP.rec); h->mCtaFirst.upload(MP.ctaFirst); h->mCode.upload(MP.code); h->mSlotBundle.upload(MP.slotBundle);
+          // host copy of the node slots for the slot table: only the nodes that emit a partial
+          M.tnodeH.resize(MP.code.size());
+          parallel_range(MP.code.size(), [&](size_t b, size_t e) {
+            for (size_t k = b; k < e; ++k) {
+              const int c = MP.code[k];
+              M.tnodeH[k] = (c < 0 || (c & MK_FUSED)) ? -1 : (c & MK_IDMASK);
+              if (c >= 0 && (c & MK_FUSED)) h->info[c & MK_IDMASK] |= EQD_INFO_FUSED_BIT;   // one bundle per fused node: no race
+            }
+          });
+          M.refId = std::move(MP.refId);
+          parallel_range((size_t)M.S, [&](size_t sb, size_t se) {
+            for (size_t sl = sb; sl < se; ++sl) if (M.refId[sl] >= 0) h->elemCode[M.refId[sl]] = CLS_MARCH | ((int)sl << 2);
+          });
+          M.pf.alloc((size_t)3 * M.PFS);
+          M.stress.alloc((size_t)6 * M.S);
+          M.nBoxElems = M.n;
+          members[CLS_REG] = std::move(MP.leftover);
+        }
+      }
+      lap.lap("march plan");
+    }
     const int nf[3] = {3, 6, 12}, nstr[3] = {6, 6, 21};
     for (int c = 0; c < 3; ++c) {
       ElemClass& C = h->cls[c];
@@ -1010,7 +1099,7 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
           th.emplace_back([&, t] {
             const int lo = (int)std::min((size_t)Nn, t * per), hi = (int)std::min((size_t)Nn, (t + 1) * per);
             if (lo >= hi) return;
-            for (int c = 0; c < 3; ++c) {
+            for (int c = 0; c < NCLS; ++c) {
               const raw_vector<int>& tn = h->cls[c].tnodeH;
               for (size_t sl = 0; sl < tn.size(); ++sl) {
                 const int nd = tn[sl];
@@ -1021,7 +1110,7 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
                   if (cnt[nd] == 255) { badv[t] = 1; continue; }
                   maxv[t] = std::max(maxv[t], (int)++cnt[nd]);
                 } else {
-                  if (c == CLS_REG && kind == KIND_PML12) { badv[t] = 2; continue; }
+                  if ((c == CLS_REG || c == CLS_MARCH) && kind == KIND_PML12) { badv[t] = 2; continue; }
                   (*tab)[(size_t)cnt[nd]++ * NS + nd] = EQD_SLOT(c, sl);
                 }
               }
@@ -1090,7 +1179,7 @@ void upload_elem_state(eqd_handle* h, DevBuf<int>& dCode, const double* eleporep
   }
   tmp.release();
   // stresses: stressArr(stressCompIndexArr(e) + k)
-  for (int c = 0; c < 3; ++c) {
+  for (int c = 0; c < NCLS; ++c) {
     ElemClass& C = h->cls[c];
     if (!C.n) continue;
     // first touched inside the parallel loop (no serial zero fill of ~1 GB); padding slots get zeros there
@@ -1121,6 +1210,8 @@ void alloc_elem_ops(eqd_handle* h) {
     if (h->body) C.emass.alloc(8 * (size_t)C.S);
     if (h->plastic && c != CLS_PML) { C.porep.alloc(C.S); C.pstrain.alloc(C.S); }
   }
+  ElemClass& M = h->cls[CLS_MARCH];
+  if (M.n) { M.shp.alloc(3 * (size_t)M.S); M.ss.alloc(3 * (size_t)M.S); M.lam.alloc(M.S); M.mu.alloc(M.S); M.det.alloc(M.S); }
 }
 }  // namespace
 
@@ -1166,14 +1257,39 @@ int eqd_compute_elem_ops(eqd_handle* h, const double* mat, const double* elepore
       launch_tile_mass(T, C.nTiles, h->stream);
       CK(cudaStreamSynchronize(h->stream));
     }
+    DevBuf<double> emM, pmM;
+    {
+      ElemClass& M = h->cls[CLS_MARCH];
+      if (M.n) {
+        DevBuf<int> dRef; dRef.upload(M.refId);
+        emM.alloc(8 * (size_t)M.S);
+        OpsArgs A{};
+        A.S = M.S; A.Ne = Ne; A.refId = dRef.p; A.conn = dConn.p; A.etype = dEtype.p; A.coor = dCoor.p; A.mat = dMat.p;
+        A.w = h->p.w;
+        A.shp = M.shp.p; A.phi = nullptr; A.ss = M.ss.p; A.det = M.det.p; A.lam = M.lam.p; A.mu = M.mu.p;
+        A.rho = nullptr; A.vp = nullptr; A.em = emM.p; A.badElem = dBad.p; A.compact = 1;
+        launch_elem_ops(A, h->stream);
+        pmM.alloc(M.PFS);
+        CK(cudaStreamSynchronize(h->stream));
+      }
+    }
     CK(cudaGetLastError());
     const int bad = dBad.download()[0];
     if (bad != 0x7fffffff) throw ArgError("Non-positive determinant; element " + std::to_string(bad + 1) + " (calcGlobalShapeFunc.f90:57-61)");
     NodeMassArgs M{};
     M.Nn = Nn; M.NnS = h->NnS; M.slotCnt = h->dSlotCnt.p; M.slotTab = h->dSlotTab.p;
     for (int c = 0; c < 3; ++c) M.pm[c] = pm[c].p;
+    M.pm[CLS_MARCH] = pmM.p;
     M.mass = h->dMass.p;
+    if (h->cls[CLS_MARCH].n) {   // partials of the bundle surfaces first (k_node_mass sums them) ...
+      const ElemClass& MC = h->cls[CLS_MARCH];
+      launch_march_mass(h->mRec.p, h->mBundles, h->mSlotBundle.p, h->mCode.p, emM.p, (size_t)MC.S, MC.PFS, pmM.p, nullptr, h->stream);
+    }
     launch_node_mass(M, h->stream);
+    if (h->cls[CLS_MARCH].n) {   // ... then the complete masses of the fused nodes, which have no slot-table entry
+      const ElemClass& MC = h->cls[CLS_MARCH];
+      launch_march_mass(h->mRec.p, h->mBundles, h->mSlotBundle.p, h->mCode.p, emM.p, (size_t)MC.S, MC.PFS, pmM.p, h->dMass.p, h->stream);
+    }
     CK(cudaStreamSynchronize(h->stream));
     h->massH = h->dMass.download();
     h->fnmsH = h->massH;                       // fnms adds the same element masses (assembleGlobalMass.f90:322)
@@ -1215,12 +1331,26 @@ int eqd_set_elem_ops(eqd_handle* h, const double* eleshp, const double* eledet, 
       }
       CK(cudaStreamSynchronize(h->stream));
     };
+    // marching class: of eleshp only rows 3, 7, 14 (a_x, a_y, a_z), of ss the diagonal, no phi (eqd_box.h)
+    ElemClass& M = h->cls[CLS_MARCH];
+    auto march_rows = [&](DevBuf<double>& dst, int K, const int* rows, int nrows) {
+      if (!M.n) return;
+      for (int k = 0; k < nrows; ++k)
+        launch_aos_to_soa(tmp.p, K, Ne, dCode.p, CLS_MARCH, dst.p + (size_t)k * M.S, M.S, rows[k], 1, h->stream);
+      CK(cudaStreamSynchronize(h->stream));
+    };
+    const int shpRows[3] = {BOX_AX, BOX_AY, BOX_AZ}, ssRows[3] = {0, 3, 5}, row0[1] = {0};
     spread(eleshp, 24, &ElemClass::shp, 0, 24, 0);
+    march_rows(M.shp, 24, shpRows, 3);
     spread(phi, 32, &ElemClass::phi, 0, 32, 0);
     spread(ss, 6, &ElemClass::ss, 0, 6, 0);
+    march_rows(M.ss, 6, ssRows, 3);
     spread(eledet, 1, &ElemClass::det, 0, 1, 0);
+    march_rows(M.det, 1, row0, 1);
     spread(mat + 3 * (size_t)Ne, 1, &ElemClass::lam, 0, 1, 0);  // mat(Ne,5): element index fastest
+    march_rows(M.lam, 1, row0, 1);
     spread(mat + 4 * (size_t)Ne, 1, &ElemClass::mu, 0, 1, 0);
+    march_rows(M.mu, 1, row0, 1);
     if (h->p.C_hg == 2) {
       spread(mat + 2 * (size_t)Ne, 1, &ElemClass::rho, 0, 1, 0);
       spread(mat, 1, &ElemClass::vp, 0, 1, 0);
@@ -1480,7 +1610,7 @@ int eqd_run(eqd_handle* h, int32_t nt_begin, int32_t nt_end) {
     if (h->timing) { CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1)); CK(cudaEventRecord(t0, h->stream)); }
     for (int nt = nt_begin; nt <= nt_end; ++nt) {
       const int ov = !h->commStream ? 0 : h->optOverlap < 0 ? (multi ? 1 : 0) : h->optOverlap;
-      step_pre(h, ov, multi);
+      step_pre(h, ov, multi, nt == nt_end);
       if (multi && !ov) halo_all_nccl(h, h->stream);
       step_post(h, ov);
     }
@@ -1512,7 +1642,7 @@ int eqd_run_group(eqd_handle** hs, int32_t n, int32_t nt_begin, int32_t nt_end) 
       prepare_run(hs[r], nt_begin);
     }
     for (int nt = nt_begin; nt <= nt_end; ++nt) {
-      for (int r = 0; r < n; ++r) { CK(cudaSetDevice(hs[r]->device)); step_pre(hs[r], 0, false); }
+      for (int r = 0; r < n; ++r) { CK(cudaSetDevice(hs[r]->device)); step_pre(hs[r], 0, false, nt == nt_end); }
       for (int a = 0; a < 3; ++a) {
         for (int r = 0; r < n; ++r) {
           eqd_handle* h = hs[r];
@@ -1623,6 +1753,28 @@ int eqd_fetch(eqd_handle* h, int32_t which, void* dst, int64_t dst_bytes) {
         need(h->opsSet, "eqd_fetch: no element operators yet");
         const int K = which == EQD_F_ELEDET ? 1 : which == EQD_F_ELESHP ? 24 : which == EQD_F_SS ? 6 : 32;
         want((size_t)K * h->Ne);
+        if (h->cls[CLS_MARCH].n) {
+          // the marching class keeps a_x, a_y, a_z and the diagonal of ss only; the rest is the closed form of eqd_box.h
+          ElemClass& C = h->cls[CLS_MARCH];
+          std::vector<double> a = (which == EQD_F_ELESHP ? C.shp : which == EQD_F_SS ? C.ss : C.det).download();
+          parallel_range((size_t)C.S, [&](size_t sb, size_t se) {
+            for (size_t s = sb; s < se; ++s) {
+              const int e = C.refId[s];
+              if (e < 0) continue;
+              double* o = out + (size_t)K * e;
+              if (which == EQD_F_ELEDET) o[0] = a[s];
+              else if (which == EQD_F_ELESHP)
+                for (int i = 0; i < 8; ++i) {
+                  o[3 * i] = box_px(i) ? a[s] : -a[s];
+                  o[3 * i + 1] = box_py(i) ? a[C.S + s] : -a[C.S + s];
+                  o[3 * i + 2] = box_pz(i) ? a[2 * (size_t)C.S + s] : -a[2 * (size_t)C.S + s];
+                }
+              else if (which == EQD_F_SS) { o[0] = a[s]; o[1] = 0; o[2] = 0; o[3] = a[C.S + s]; o[4] = 0; o[5] = a[2 * (size_t)C.S + s]; }
+              else
+                for (int m = 0; m < 4; ++m) for (int i = 0; i < 8; ++i) o[8 * m + i] = box_hp(m, i) ? 1.0 : -1.0;
+            }
+          });
+        }
         for (int c = 0; c < 3; ++c) {
           ElemClass& C = h->cls[c];
           if (!C.n) continue;
@@ -1664,7 +1816,7 @@ int eqd_fetch(eqd_handle* h, int32_t which, void* dst, int64_t dst_bytes) {
       }
       case EQD_F_STRESS: {
         want(h->sizeStress);
-        for (int c = 0; c < 3; ++c) {
+        for (int c = 0; c < NCLS; ++c) {
           ElemClass& C = h->cls[c];
           if (!C.n) continue;
           std::vector<double> sg = C.stress.download(), qm;
@@ -1702,7 +1854,7 @@ int eqd_fetch(eqd_handle* h, int32_t which, void* dst, int64_t dst_bytes) {
 
 int eqd_get_counts(const eqd_handle* h, int64_t* n_regular, int64_t* n_pml, int64_t* n_pairs, int64_t* launches) {
   if (!h) return EQD_ERR_ARG;
-  if (n_regular) *n_regular = h->cls[CLS_REG].n + h->cls[CLS_REGX].n;
+  if (n_regular) *n_regular = h->cls[CLS_REG].n + h->cls[CLS_REGX].n + h->cls[CLS_MARCH].n;
   if (n_pml) *n_pml = h->cls[CLS_PML].n;
   if (n_pairs) *n_pairs = h->nPairs;
   if (launches) *launches = h->launches;
@@ -1711,7 +1863,7 @@ int eqd_get_counts(const eqd_handle* h, int64_t* n_regular, int64_t* n_pml, int6
 
 int eqd_get_box_counts(const eqd_handle* h, int64_t* n_regular_box, int64_t* n_pml_box) {
   if (!h) return EQD_ERR_ARG;
-  if (n_regular_box) *n_regular_box = h->cls[CLS_REG].nBoxElems + h->cls[CLS_REGX].nBoxElems;
+  if (n_regular_box) *n_regular_box = h->cls[CLS_REG].nBoxElems + h->cls[CLS_REGX].nBoxElems + h->cls[CLS_MARCH].nBoxElems;
   if (n_pml_box) *n_pml_box = h->cls[CLS_PML].nBoxElems;
   return EQD_OK;
 }
@@ -1742,6 +1894,11 @@ int eqd_set_option(eqd_handle* h, const char* key, int32_t value) {
     return EQD_OK;
   }
   if (!strcmp(key, "box_compact")) { h->optBoxCompact = value != 0; return EQD_OK; }
+  if (!strcmp(key, "march")) {
+    if (h->meshSet) { h->err = "eqd_set_option: march must be set before eqd_set_mesh"; return EQD_ERR_ARG; }
+    h->optMarch = value != 0;
+    return EQD_OK;
+  }
   if (!strcmp(key, "box")) {
     if (h->finalized) { h->err = "eqd_set_option: box must be set before the first eqd_run / eqd_sum_shared"; return EQD_ERR_ARG; }
     h->optBox = value < 0 ? 0 : value > 2 ? 2 : value;

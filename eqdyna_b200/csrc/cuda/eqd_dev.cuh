@@ -31,10 +31,13 @@
 namespace eqd {
 
 enum { KIND_FREE3 = 0, KIND_PML12 = 1, KIND_FIXED = 2 };
-enum { CLS_REG = 0, CLS_REGX = 1, CLS_PML = 2 };
+enum { CLS_REG = 0, CLS_REGX = 1, CLS_PML = 2, CLS_MARCH = 3, NCLS = 4 };   // CLS_MARCH: bundles of box elements (eqd_march.h)
 #define EQD_INFO_KIND(i) ((i) & 3)
 #define EQD_INFO_SPECIAL(i) (((i) >> 2) & 1)
 #define EQD_INFO_SLOT(i) ((i) >> 3)
+// free 3-dof nodes only (they have no PML slot): the node is updated by its marching bundle (eqd_march.h)
+#define EQD_INFO_FUSED_BIT 8
+#define EQD_INFO_FUSED(i) (((i) >> 3) & 1)
 // node -> tile-node slot entry: class (2 bits) | slot in the class's partial buffer (30 bits)
 #define EQD_SLOT(cls, slot) ((uint32_t)(cls) | ((uint32_t)(slot) << 2))
 // local connectivity entry: tile-local node index (12 bits) | colour of the phase (4 bits)
@@ -68,6 +71,10 @@ struct NodeArgs {
   const double* pfR; int SR;   // [3][SR]  tile partials, REG
   const double* pfX; int SX;   // [6][SX]  REGX: KU | hourglass
   const double* pfP; int SP;   // [12][SP] PML
+  const double* pfM; int SM;   // [3][SM]  marching bundles (non-fused node slots)
+  const int* list; int nList;  // list variant of k_node_update3: the free 3-dof nodes no bundle updates, ascending
+  int fusedMode;               // nodes flagged EQD_INFO_FUSED: 1 = take their force from force[] (the last sweep did not
+                               // update them), 2 = skip them (it did)
   const double* accel0;  // optional uploaded acceleration, same layout as force; first step only
   int variant;           // launch-bounds variant of k_node_update3 (tuning)
   int skipSpecial;       // 1: k_node_update3/12 leave the special nodes to k_node_update_special
@@ -137,6 +144,7 @@ struct OpsArgs {
   double* rho; double* vp;   // optional (C_hg == 2)
   double* em;            // [8][S] lumped element mass per local node
   int* badElem;          // smallest element id with a non-positive determinant
+  int compact;           // 1 (marching class): shp = [3][S] a_x a_y a_z (eleshp rows 3, 7, 14), ss = [3][S] ss1 ss4 ss6, no phi
 };
 struct TileMassArgs {
   const int4* tileRec; const double* em; const uint16_t* lconn; int S, capE;
@@ -145,7 +153,7 @@ struct TileMassArgs {
 struct NodeMassArgs {
   int Nn, NnS;
   const uint8_t* slotCnt; const uint32_t* slotTab;
-  const double* pm[3];
+  const double* pm[NCLS];
   double* mass;
 };
 

@@ -51,6 +51,9 @@ __device__ __forceinline__ void add3(const NodeArgs& A, uint32_t u, double f[3])
   if (cls == CLS_REG) {
     const double* p = A.pfR + idx;
     f[0] += p[0]; f[1] += p[A.SR]; f[2] += p[2 * (size_t)A.SR];
+  } else if (cls == CLS_MARCH) {
+    const double* p = A.pfM + idx;
+    f[0] += p[0]; f[1] += p[A.SM]; f[2] += p[2 * (size_t)A.SM];
   } else if (cls == CLS_PML) {
     // 3-dof node of a PML element: assembleGlobalKU.f90:55-61
     const double* p = A.pfP + idx;
@@ -107,10 +110,13 @@ __device__ __forceinline__ void gather12(const NodeArgs& A, int n, int cnt, doub
 // previous step's `nodalForceArr/nodalMassArr` (driver.f90:29).  Two kernels so
 // that the 3-dof one (almost every node) stays light enough for full occupancy:
 // its gather is a chain of dependent loads that only parallelism hides.
-template <bool SKIP, int NT, int MINB>
+// LIST: one thread per entry of A.list (the free 3-dof nodes that no marching bundle updates itself) instead of
+// one per node; used after a sweep that updated the fused nodes (eqd_march.h).
+template <bool SKIP, bool LIST, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_node_update3(NodeArgs A) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= A.Nn) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (LIST ? A.nList : A.Nn)) return;
+  const int n = LIST ? ldc_now(A.list + i) : i;
   const size_t NS = A.NnS;
   // every independent load first: the stores below may alias them for the compiler,
   // which would otherwise serialise six DRAM round trips per node
@@ -123,7 +129,8 @@ __global__ void __launch_bounds__(NT, MINB) k_node_update3(NodeArgs A) {
   for (int j = 0; j < 3; ++j) { v[j] = ld_now(A.vel + j * NS + n); d[j] = ld_now(A.disp + j * NS + n); }
   // no early exit: fixed and PML nodes run through with an empty gather and skip the
   // stores (vel = disp = 0 for ever for fixed nodes, driver.f90:142-145)
-  const bool mine = EQD_INFO_KIND(info) == KIND_FREE3 && !(SKIP && EQD_INFO_SPECIAL(info));
+  const bool fused = !LIST && EQD_INFO_KIND(info) == KIND_FREE3 && EQD_INFO_FUSED(info);
+  const bool mine = EQD_INFO_KIND(info) == KIND_FREE3 && !(SKIP && EQD_INFO_SPECIAL(info)) && !(fused && A.fusedMode == 2);
   const int cnt = mine ? cnt0 : 0;
   const double dt = A.dt;
   double a[3] = {0.0, 0.0, 0.0};
@@ -131,7 +138,7 @@ __global__ void __launch_bounds__(NT, MINB) k_node_update3(NodeArgs A) {
     if (mine) { a[0] = A.accel0[n]; a[1] = A.accel0[NS + n]; a[2] = A.accel0[2 * NS + n]; }
   } else {
     double f[3];
-    if (!SKIP && mine && EQD_INFO_SPECIAL(info)) {
+    if (mine && (fused || (!SKIP && EQD_INFO_SPECIAL(info)))) {
       f[0] = A.force[n]; f[1] = A.force[NS + n]; f[2] = A.force[2 * NS + n];
     } else {
       gather3(A, n, cnt, u0, u1, f);
@@ -308,7 +315,7 @@ __global__ void k_materialize_accel(NodeArgs A, double* __restrict__ out) {
   if (kind == KIND_FREE3) {
     double f[3];
     if (A.accel0) { out[n] = A.accel0[n]; out[NS + n] = A.accel0[NS + n]; out[2 * NS + n] = A.accel0[2 * NS + n]; return; }
-    if (EQD_INFO_SPECIAL(info)) { f[0] = A.force[n]; f[1] = A.force[NS + n]; f[2] = A.force[2 * NS + n]; }
+    if (EQD_INFO_SPECIAL(info) || EQD_INFO_FUSED(info)) { f[0] = A.force[n]; f[1] = A.force[NS + n]; f[2] = A.force[2 * NS + n]; }
     else gather3(A, n, LDG(A.slotCnt + n), f);
     out[n] = f[0] / m; out[NS + n] = f[1] / m; out[2 * NS + n] = f[2] / m;
   } else if (kind == KIND_PML12) {
@@ -1557,14 +1564,18 @@ void launch_advance(StepState* st, double dt, cudaStream_t s) { k_advance<<<1, 1
 
 template <bool SKIP>
 static void launch_node3(const NodeArgs& A, cudaStream_t s) {
+  if (A.list) {   // the nodes no marching bundle updates (the last sweep updated the others)
+    if (A.nList > 0) k_node_update3<SKIP, true, 128, 10><<<nblk(A.nList, 128), 128, 0, s>>>(A);
+    return;
+  }
   // occupancy variants of the same kernel (eqd_set_option "node_variant"); the gather is latency bound
   switch (A.variant % 10) {
-    case 1: k_node_update3<SKIP, 256, 5><<<nblk(A.Nn, 256), 256, 0, s>>>(A); break;
-    case 2: k_node_update3<SKIP, 256, 6><<<nblk(A.Nn, 256), 256, 0, s>>>(A); break;
-    case 3: k_node_update3<SKIP, 128, 8><<<nblk(A.Nn, 128), 128, 0, s>>>(A); break;
-    case 4: k_node_update3<SKIP, 128, 10><<<nblk(A.Nn, 128), 128, 0, s>>>(A); break;
-    case 5: k_node_update3<SKIP, 128, 12><<<nblk(A.Nn, 128), 128, 0, s>>>(A); break;
-    default: k_node_update3<SKIP, 256, 4><<<nblk(A.Nn, 256), 256, 0, s>>>(A); break;
+    case 1: k_node_update3<SKIP, false, 256, 5><<<nblk(A.Nn, 256), 256, 0, s>>>(A); break;
+    case 2: k_node_update3<SKIP, false, 256, 6><<<nblk(A.Nn, 256), 256, 0, s>>>(A); break;
+    case 3: k_node_update3<SKIP, false, 128, 8><<<nblk(A.Nn, 128), 128, 0, s>>>(A); break;
+    case 4: k_node_update3<SKIP, false, 128, 10><<<nblk(A.Nn, 128), 128, 0, s>>>(A); break;
+    case 5: k_node_update3<SKIP, false, 128, 12><<<nblk(A.Nn, 128), 128, 0, s>>>(A); break;
+    default: k_node_update3<SKIP, false, 256, 4><<<nblk(A.Nn, 256), 256, 0, s>>>(A); break;
   }
 }
 template <bool SKIP>

@@ -88,7 +88,6 @@ struct MarchRegs {
   double wv[3][3];   // [S0 | Sy | Sz][component] of the x- face velocities
   double wl[3][3];   // [Sy | Sz | Syz][component] of the x- face l = d + rdampk v
   double cf[4][3];   // x+ face forces of the previous element, transformed: [1 | sy | sz | sy sz][component]
-  unsigned par[2];   // mbarrier phase parity of the two operator stages
 };
 
 // ---- asynchronous copies: real on the device, immediate in the host reading
@@ -130,17 +129,17 @@ __device__ __forceinline__ void mk_nan(StepState* st, int node) {
   if (atomicExch(&st->nanFlag, 1) == 0) st->nanNode = node + 1;
 }
 #else
-inline void mk_async8(void* dst, const void* src) { *(double*)dst = *(const double*)src; }
-inline void mk_async4(void* dst, const void* src) { *(int*)dst = *(const int*)src; }
-inline void mk_commit() {}
-inline void mk_wait_all() {}
-inline void mk_bar_init(unsigned long long*) {}
-inline void mk_bar_expect(unsigned long long*, unsigned) {}
-inline void mk_bar_wait(unsigned long long*, unsigned) {}
-inline void mk_bulk(void* dst, const void* src, unsigned bytes, unsigned long long*) {
+EQD_HD void mk_async8(void* dst, const void* src) { *(double*)dst = *(const double*)src; }
+EQD_HD void mk_async4(void* dst, const void* src) { *(int*)dst = *(const int*)src; }
+EQD_HD void mk_commit() {}
+EQD_HD void mk_wait_all() {}
+EQD_HD void mk_bar_init(unsigned long long*) {}
+EQD_HD void mk_bar_expect(unsigned long long*, unsigned) {}
+EQD_HD void mk_bar_wait(unsigned long long*, unsigned) {}
+EQD_HD void mk_bulk(void* dst, const void* src, unsigned bytes, unsigned long long*) {
   for (unsigned k = 0; k < bytes / 8; ++k) ((double*)dst)[k] = ((const double*)src)[k];
 }
-inline void mk_nan(StepState* st, int node) {
+EQD_HD void mk_nan(StepState* st, int node) {
   if (!st->nanFlag) { st->nanFlag = 1; st->nanNode = node + 1; }
 }
 #endif
@@ -352,14 +351,15 @@ EQD_HD void mk_phase_flush(const MarchArgs& A, const MarchBundle& B, MarchShared
 }
 
 // The schedule.  RUN(body) executes `body` for every thread of the CTA and then synchronises: a statement +
-// __syncthreads() on the device, a loop over the thread ids on the host.  WAIT_NODES / WAIT_OPS(p) are the
-// cp.async / mbarrier waits (nothing on the host, where copies complete at issue).
+// __syncthreads() on the device, a loop over the thread ids on the host; RUNNS(body) does the same without
+// the barrier.  WAIT_NODES / WAIT_OPS(p) are the cp.async / mbarrier waits (nothing on the host, where copies
+// complete at issue).
 //   step p:  [plane p+1 and operator stage p have landed] barrier
 //            issue plane p+2 values, plane p+3 codes, operator stage p+1 ; element p -> force buffers ; barrier
 //            flush node plane p (update or partial)
 // Ring slot (p+2)%3 was last read by the flush of plane p-1, the code slot (p+3)&3 by that flush too, the
 // operator stage (p+1)&1 by element p-1: all before the barrier that opens step p.
-#define MARCH_BUNDLE(RUN, WAIT_NODES, WAIT_OPS, A, B, sm, R)                                                            \
+#define MARCH_BUNDLE(RUN, RUNNS, WAIT_NODES, WAIT_OPS, A, B, sm, R)                                                           \
   do {                                                                                                                 \
     RUN(mk_issue_ids(A, B, sm, tid, 0); mk_issue_ids(A, B, sm, tid, 1); mk_issue_ids(A, B, sm, tid, 2); mk_commit(); WAIT_NODES); \
     RUN(mk_issue_values(A, B, sm, tid, 0); mk_issue_values(A, B, sm, tid, 1); mk_issue_ops(A, B, sm, tid, 0);           \
@@ -369,17 +369,11 @@ EQD_HD void mk_phase_flush(const MarchArgs& A, const MarchBundle& B, MarchShared
       RUN(WAIT_NODES; WAIT_OPS(p));                                                                                    \
       RUN(mk_issue_values(A, B, sm, tid, p + 2); mk_issue_ids(A, B, sm, tid, p + 3); mk_issue_ops(A, B, sm, tid, p + 1); \
           mk_commit(); mk_phase_element(A, B, sm, R, tid, p));                                                         \
-      mk_phase_flush(A, B, sm, tid, p);                                                                                \
+      RUNNS(mk_phase_flush(A, B, sm, tid, p));                                                                         \
     }                                                                                                                  \
     RUN(WAIT_NODES);                                                                                                   \
     RUN(mk_phase_last(B, sm, R, tid));                                                                                 \
     RUN(mk_phase_flush(A, B, sm, tid, (B).Lx));                                                                        \
   } while (0)
-
-// ---- host side (eqd_march.cu)
-struct MarchPlan;
-size_t march_smem_bytes();
-int march_ctas_per_sm();                       // occupancy of the kernel on the current device (0: not launchable)
-void launch_march(const MarchArgs& A, int grid, cudaStream_t s);
 
 }  // namespace eqd

@@ -113,10 +113,15 @@ __global__ void __launch_bounds__(128) k_elem_ops(OpsArgs A) {
     shg[i][2] = (t0 * cof31 + t1 * cof32 + t2 * cof33) / det;
   }
   A.det[s] = det;
+  if (A.compact) {
+    // eleshp(1,2), eleshp(2,3), eleshp(3,5): the three numbers a box element's 24 derivatives consist of (eqd_box.h)
+    A.shp[s] = shg[1][0]; A.shp[S + s] = shg[2][1]; A.shp[2 * S + s] = shg[4][2];
+  } else {
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 3; ++j) A.shp[(size_t)(3 * i + j) * S + s] = shg[i][j];
+      for (int j = 0; j < 3; ++j) A.shp[(size_t)(3 * i + j) * S + s] = shg[i][j];
+  }
   // material: mat(Ne,5) = vp, vs, rho, lam, mu with the element index fastest
   const double rho = A.mat[(size_t)e + (size_t)A.Ne * 2];
   const double lam = A.mat[(size_t)e + (size_t)A.Ne * 3], miu = A.mat[(size_t)e + (size_t)A.Ne * 4];
@@ -147,6 +152,12 @@ __global__ void __launch_bounds__(128) k_elem_ops(OpsArgs A) {
     x[0][0] = cof11 / det; x[1][0] = cof12 / det; x[2][0] = cof13 / det;
     x[0][1] = cof21 / det; x[1][1] = cof22 / det; x[2][1] = cof23 / det;
     x[0][2] = cof31 / det; x[1][2] = cof32 / det; x[2][2] = cof33 / det;
+    if (A.compact) {
+      A.ss[0 * S + s] = co * (x[0][0] * x[0][0] + x[1][0] * x[1][0] + x[2][0] * x[2][0]);
+      A.ss[1 * S + s] = co * (x[0][1] * x[0][1] + x[1][1] * x[1][1] + x[2][1] * x[2][1]);
+      A.ss[2 * S + s] = co * (x[0][2] * x[0][2] + x[1][2] * x[1][2] + x[2][2] * x[2][2]);
+      return;
+    }
     A.ss[0 * S + s] = co * (x[0][0] * x[0][0] + x[1][0] * x[1][0] + x[2][0] * x[2][0]);
     A.ss[1 * S + s] = co * (x[0][0] * x[0][1] + x[1][0] * x[1][1] + x[2][0] * x[2][1]);
     A.ss[2 * S + s] = co * (x[0][0] * x[0][2] + x[1][0] * x[1][2] + x[2][0] * x[2][2]);

@@ -17,13 +17,13 @@ from .host import EqdParams
 F_DISP, F_VEL, F_V1, F_FORCE, F_FRIC, F_FNFT, F_PSTRAIN, F_STRESS = 1, 2, 3, 4, 5, 6, 7, 8
 F_ONFAULT_HIST, F_OFFFAULT_HIST, F_HYPO_LOG, F_GM, F_SRC_EVOL, F_TPHIST, F_MASS, F_FNMS, F_ARN = 9, 10, 11, 12, 13, 14, 15, 16, 17
 F_ELEDET, F_ELESHP, F_SS, F_PHI = 18, 19, 20, 21
-T_TOTAL, T_NODE, T_ELEM, T_ASSEMBLE, T_HALO, T_FAULT, T_ELEM_PML, T_ELEM_REGX, T_NSLOTS = 0, 1, 2, 3, 4, 5, 6, 7, 8
+T_TOTAL, T_NODE, T_ELEM, T_ASSEMBLE, T_HALO, T_FAULT, T_ELEM_PML, T_ELEM_REGX, T_MARCH, T_NSLOTS = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
 
 EXPORTS = [
     "eqd_create", "eqd_destroy", "eqd_last_error", "eqd_set_mesh", "eqd_set_elem_ops", "eqd_compute_elem_ops", "eqd_set_nodal",
     "eqd_set_fault", "eqd_set_halo", "eqd_set_stations", "eqd_get_unique_id", "eqd_set_comm", "eqd_sum_shared",
     "eqd_run", "eqd_run_group", "eqd_fetch", "eqd_get_counts", "eqd_get_timing", "eqd_set_option", "eqd_plan_check",
-    "eqd_box_check", "eqd_get_box_counts", "eqd_plan_bank_model",
+    "eqd_box_check", "eqd_get_box_counts", "eqd_plan_bank_model", "eqd_march_emulate",
 ]
 
 _lib = None
@@ -202,7 +202,7 @@ class Domain:
         t = (C.c_double * T_NSLOTS)()
         lib().eqd_get_timing(self._h, t)
         return {"total": t[T_TOTAL], "node": t[T_NODE], "elem": t[T_ELEM], "assemble": t[T_ASSEMBLE],
-                "halo": t[T_HALO], "fault": t[T_FAULT], "elem_pml": t[T_ELEM_PML], "elem_regx": t[T_ELEM_REGX]}
+                "halo": t[T_HALO], "fault": t[T_FAULT], "elem_pml": t[T_ELEM_PML], "elem_regx": t[T_ELEM_REGX], "march": t[T_MARCH]}
 
     def fetch(self, which, shape, dtype=np.float64):
         out = np.zeros(shape, dtype=dtype, order="F")

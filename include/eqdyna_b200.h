@@ -95,7 +95,8 @@ enum {
  * compTimeInSeconds(3..6)+MPICommTimeInSeconds (library_output.f90:208-218) */
 enum {
   EQD_T_TOTAL = 0, EQD_T_NODE = 1, EQD_T_ELEM = 2 /* regular hex/wedge kernel */, EQD_T_ASSEMBLE = 3,
-  EQD_T_HALO = 4, EQD_T_FAULT = 5, EQD_T_ELEM_PML = 6, EQD_T_ELEM_REGX = 7, EQD_T_NSLOTS = 8
+  EQD_T_HALO = 4, EQD_T_FAULT = 5, EQD_T_ELEM_PML = 6, EQD_T_ELEM_REGX = 7,
+  EQD_T_MARCH = 8 /* marching kernel: box bundles, element sweep + assembly + update of their inner nodes */, EQD_T_NSLOTS = 9
 };
 
 /* -- lifecycle ------------------------------------------------------------- */
@@ -188,6 +189,9 @@ int eqd_get_timing(const eqd_handle* h, double* ms_slots /*[EQD_T_NSLOTS]*/);
  * "bank_order" (before eqd_set_mesh) 1 = bank-aware element order inside the tiles,
  * 2 = residue numbering of the tile-local nodes of complete bricks (conflict free by
  * construction; see eqd_plan_bank_model; default 0 = ascending ids).
+ * "march" (before eqd_set_mesh) 1 = elastic runs (C_elastic = 1, C_Q = 0, C_hg = 1, rdampm = 0) sweep the
+ * axis-aligned hexahedra of the structured grid with the marching kernel (eqd_march.h): bundles of element
+ * columns whose inner nodes are updated by the element sweep itself, connectivity implicit (default 0).
  * Unknown keys return 4.  See DESIGN.md sections 3-4.                          */
 int eqd_set_option(eqd_handle* h, const char* key, int32_t value);
 
@@ -223,6 +227,19 @@ int eqd_plan_bank_model(int32_t Nn, int32_t Ne, const int32_t* nodeElemIdRelatio
 int eqd_box_check(int32_t Nn, int32_t Ne, const double* meshCoor, const int32_t* nodeElemIdRelation,
                   const int32_t* elemTypeArr, const double* eleshp, const double* phi, const double* ss,
                   int64_t* nBox, double* dev);
+
+/* Host-only self-check of the marching kernel (option "march", eqd_march.h) -- no GPU needed.  Plans the bundles of
+ * a sub-domain from its connectivity as eqd_set_mesh would for a launch of `grid` CTAs, then runs the kernel's phases
+ * over all thread ids, CTA after CTA, for ONE step on the given nodal fields (asynchronous copies complete at issue).
+ * In/out: stress6(6,Ne) (slots 1..6 of every element's stresses), vel / disp (3,Nn): updated where the device would
+ * update them.  Out: fsum(3,Nn) = the partial forces summed per node (+ the complete force of the fused nodes when
+ * update = 0), fusedFlag(Nn), inBundle(Ne), stats[8] = elements in bundles, bundles, node slots, fused nodes, regular
+ * elements left to the tile kernels, grid, element slots, 0.  Returns 0 or a line number of eqd_march.cu.          */
+int eqd_march_emulate(int32_t Nn, int32_t Ne, const double* meshCoor, const int32_t* nodeElemIdRelation,
+                      const int32_t* elemTypeArr, const int32_t* numOfDofPerNodeArr, int32_t grid, const double* eleshp,
+                      const double* ss, const double* eledet, const double* mat, double* stress6, double* vel, double* disp,
+                      const double* mass, double dt, double rdampk, double w, int32_t update, double* fsum,
+                      int32_t* fusedFlag, int32_t* inBundle, int64_t* stats);
 
 #ifdef __cplusplus
 }

@@ -78,12 +78,13 @@ def run_oracle(world, nstep=None, threads=None):
     return world
 
 
-def run_gpu(world, nstep=None, device=0, chunks=1, options=None, compute_ops=False):
+def run_gpu(world, nstep=None, device=0, chunks=1, options=None, compute_ops=False, pre_options=None):
     """Step every sub-domain of `world` on the GPU and copy the results back into
-    the world's host arrays.  Returns the Domain list (caller may read timing)."""
+    the world's host arrays.  Returns the Domain list (caller may read timing).
+    pre_options are set before the upload (those that shape it: "march", tile bricks), options after it."""
     from eqdyna_b200 import device as dev
     n = world.view(0).nstep if nstep is None else nstep
-    doms = [dev.Domain(world.view(r), device=device, compute_ops=compute_ops) for r in range(world.size)]
+    doms = [dev.Domain(world.view(r), device=device, compute_ops=compute_ops, options=pre_options) for r in range(world.size)]
     for d in doms:
         for k, v in (options or {}).items():
             d.set_option(k, v)

@@ -22,7 +22,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world_size, port, case, decomp, nstep, overlap, own_rank_only, out):
+def _worker(rank, world_size, port, case, decomp, nstep, overlap, own_rank_only, out, march=0):
     sys.path.insert(0, parity.ROOT)
     sys.path.insert(0, os.path.join(parity.ROOT, "tests"))
     import torch
@@ -41,7 +41,11 @@ def _worker(rank, world_size, port, case, decomp, nstep, overlap, own_rank_only,
     else:
         w = parity.build_world(case, decomp, nstep)   # whole world on the host: init-time shared sums done
     v = w.view(rank)
-    d = dev.Domain(v, device=rank % torch.cuda.device_count(), compute_ops=bool(own_rank_only))
+    d = dev.Domain(v, device=rank % torch.cuda.device_count(), compute_ops=bool(own_rank_only),
+                   options={"march": 1} if march else None)
+    if march:
+        d.set_option("box", 2)
+        d.set_option("box_compact", 1)
     ids = [dev.unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     d.set_comm(ids[0], world_size, rank)
@@ -59,19 +63,21 @@ def _worker(rank, world_size, port, case, decomp, nstep, overlap, own_rank_only,
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("case,decomp,nstep,overlap,own_rank_only",
-                         [("test.tpv8", (2, 1, 1), 0, 1, 0), ("test.tpv104", (1, 2, 1), 60, 1, 0), ("test.tpv8", (2, 1, 1), 40, 0, 0),
-                          ("test.tpv104", (1, 2, 1), 60, 1, 1), ("test.tpv10", (2, 1, 2), 60, 2, 0)],
+@pytest.mark.parametrize("case,decomp,nstep,overlap,own_rank_only,march",
+                         [("test.tpv8", (2, 1, 1), 0, 1, 0, 0), ("test.tpv104", (1, 2, 1), 60, 1, 0, 0), ("test.tpv8", (2, 1, 1), 40, 0, 0, 0),
+                          ("test.tpv104", (1, 2, 1), 60, 1, 1, 0), ("test.tpv10", (2, 1, 2), 60, 2, 0, 0),
+                          ("test.tpv104", (2, 1, 1), 60, 1, 1, 1), ("test.tpv104", (1, 2, 1), 60, 0, 0, 1)],
                          ids=["tpv8-2x1x1", "tpv104-1x2x1-fault-on-rank-face", "tpv8-2x1x1-no-overlap",
-                              "tpv104-1x2x1-own-rank-device-ops-sum-shared", "tpv10-2x1x2-face-tiles-first"])
-def test_nccl_processes_match_oracle(tmp_path, case, decomp, nstep, overlap, own_rank_only):
+                              "tpv104-1x2x1-own-rank-device-ops-sum-shared", "tpv10-2x1x2-face-tiles-first",
+                              "tpv104-2x1x1-march-own-rank-device-ops", "tpv104-1x2x1-march-no-overlap"])
+def test_nccl_processes_match_oracle(tmp_path, case, decomp, nstep, overlap, own_rank_only, march):
     import torch
     import torch.multiprocessing as mp
     n = decomp[0] * decomp[1] * decomp[2]
     if torch.cuda.device_count() < n:
         pytest.skip("needs %d GPUs" % n)
     port = _free_port()
-    mp.spawn(_worker, args=(n, port, case, decomp, nstep, overlap, own_rank_only, str(tmp_path)), nprocs=n, join=True)
+    mp.spawn(_worker, args=(n, port, case, decomp, nstep, overlap, own_rank_only, str(tmp_path), march), nprocs=n, join=True)
     wo = parity.build_world(case, decomp, nstep)
     parity.run_oracle(wo)
     for r in range(n):
