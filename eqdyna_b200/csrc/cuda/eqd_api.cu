@@ -1868,6 +1868,13 @@ int eqd_get_box_counts(const eqd_handle* h, int64_t* n_regular_box, int64_t* n_p
   return EQD_OK;
 }
 
+int eqd_get_march_counts(const eqd_handle* h, int64_t* out5) {
+  if (!h || !out5) return EQD_ERR_ARG;
+  out5[0] = h->cls[CLS_MARCH].n; out5[1] = h->mBundles; out5[2] = h->cls[CLS_MARCH].n ? h->cls[CLS_MARCH].PFS : 0;
+  out5[3] = h->mFused; out5[4] = h->mGrid;
+  return EQD_OK;
+}
+
 int eqd_get_timing(const eqd_handle* h, double* ms_slots) {
   if (!h || !ms_slots) return EQD_ERR_ARG;
   for (int k = 0; k < EQD_T_NSLOTS; ++k) ms_slots[k] = h->tms[k];

@@ -23,7 +23,7 @@ EXPORTS = [
     "eqd_create", "eqd_destroy", "eqd_last_error", "eqd_set_mesh", "eqd_set_elem_ops", "eqd_compute_elem_ops", "eqd_set_nodal",
     "eqd_set_fault", "eqd_set_halo", "eqd_set_stations", "eqd_get_unique_id", "eqd_set_comm", "eqd_sum_shared",
     "eqd_run", "eqd_run_group", "eqd_fetch", "eqd_get_counts", "eqd_get_timing", "eqd_set_option", "eqd_plan_check",
-    "eqd_box_check", "eqd_get_box_counts", "eqd_plan_bank_model", "eqd_march_emulate",
+    "eqd_box_check", "eqd_get_box_counts", "eqd_plan_bank_model", "eqd_march_emulate", "eqd_get_march_counts",
 ]
 
 _lib = None
@@ -64,6 +64,7 @@ def lib():
         L.eqd_get_counts.argtypes = [vp] + [C.POINTER(i64)] * 4
         L.eqd_get_timing.argtypes = [vp, C.POINTER(C.c_double)]
         L.eqd_get_box_counts.argtypes = [vp] + [C.POINTER(i64)] * 2
+        L.eqd_get_march_counts.argtypes = [vp, C.POINTER(i64)]
         L.eqd_set_option.argtypes = [vp, cp, i32]
         L.eqd_plan_check.argtypes = [i32, i32, vp, vp, vp, vp]
         L.eqd_box_check.argtypes = [i32, i32] + [vp] * 8
@@ -197,6 +198,12 @@ class Domain:
         a, b = C.c_int64(), C.c_int64()
         lib().eqd_get_box_counts(self._h, C.byref(a), C.byref(b))
         return {"regular": a.value, "pml": b.value}
+
+    def march_counts(self):
+        """Marching class (option "march"): elements in bundles, bundles, node slots, fused nodes, CTAs."""
+        a = (C.c_int64 * 5)()
+        lib().eqd_get_march_counts(self._h, a)
+        return {"elements": a[0], "bundles": a[1], "node_slots": a[2], "fused_nodes": a[3], "grid": a[4]}
 
     def timing(self):
         t = (C.c_double * T_NSLOTS)()

@@ -173,6 +173,9 @@ int eqd_get_counts(const eqd_handle* h, int64_t* n_regular, int64_t* n_pml,
                    int64_t* n_pairs, int64_t* launches);
 /* elements swept with closed-form box operators (option "box"); valid after the first run */
 int eqd_get_box_counts(const eqd_handle* h, int64_t* n_regular_box, int64_t* n_pml_box);
+/* marching class (option "march"): out5 = elements in bundles, bundles, node slots, nodes the bundles update
+ * themselves, CTAs of the persistent launch */
+int eqd_get_march_counts(const eqd_handle* h, int64_t* out5);
 int eqd_get_timing(const eqd_handle* h, double* ms_slots /*[EQD_T_NSLOTS]*/);
 /* options: "timing" 1 = CUDA-event timing of every phase (2 = also reset the
  * accumulated slots and the launch counter); "overlap" -1 auto (default) / 0 serial

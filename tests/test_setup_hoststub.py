@@ -119,6 +119,18 @@ RUN_SCRIPT = textwrap.dedent(r"""
         for d in doms:
             d.close()
         w.close()
+    # marching class: planner, slot table with the bundles' partial slots, node list, launch sequence with chunked runs
+    for case, npx, cops in (("test.tpv104", (2, 2, 1), True), ("test.tpv36", (2, 2, 2), False)):
+        w = parity.build_world(case, npx, 6)
+        doms = parity.run_gpu(w, options={"box": 2, "box_compact": 1}, pre_options={"march": 1}, chunks=2, compute_ops=cops)
+        mc = [d.march_counts() for d in doms]
+        assert all(m["elements"] > 0 and m["fused_nodes"] > 0.4 * m["elements"] and m["grid"] == 3 * 148 for m in mc), mc
+        assert all(d.box_counts()["regular"] >= m["elements"] for d, m in zip(doms, mc))
+        if case == "test.tpv104":
+            assert all(m["elements"] == d.counts()["regular"] for d, m in zip(doms, mc))      # rectilinear: all of the regular class
+        for d in doms:
+            d.close()
+        w.close()
     assert out[0][1] == out[0][2] and out[0][3] > 0        # tpv8: rectilinear mesh, every tile of both classes
     assert 0 < out[1][1] < out[1][2]                       # tpv10: box and warped tiles mixed
     assert 0 < out[2][1] < out[2][2] and out[2][3] == 0    # tpv36: wedges excluded; box = 1 leaves the PML class alone
@@ -171,10 +183,14 @@ def test_bench_native_arm_call_sequence_under_the_stand_in():
               "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "clocks"):
         assert k in line, k
     assert line["metric"] == "element-steps/s" and line["dtype"] == "f64" and line["vs_baseline"] is None
-    assert line["config"]["box"] == 2 and line["config"]["box_compact"] == 1 and "workload" in line["config"]
+    assert "workload" in line["config"] and line["config"]["case"] == "test.tpv104"
+    tn = line["tuning"]
+    assert tn["box"] == 2 and tn["box_compact"] == 1 and tn["march"] == 1 and tn["march_elements"] == 516096
     assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
     rf = line["roofline"]
-    assert set(rf) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and rf["bound"] == "hbm"
-    assert rf["box_elements_per_launch"] == rf["elements_per_launch"] == 516096 and rf["alg_bytes_per_element"] == 272.0
+    assert set(rf) >= {"bound", "achieved", "peak", "unit", "frac", "traffic", "kernel"} and rf["bound"] == "hbm"
+    kernels = {r["kernel"]: r for r in line["rooflines"]}
+    assert set(kernels) >= {"k_march", "k_tile_pml", "k_node_update"} and "k_tile_reg" not in kernels   # every regular element marches
+    assert kernels["k_march"]["units_per_launch"] == 516096
     assert line["gpu_launches"] > 0
