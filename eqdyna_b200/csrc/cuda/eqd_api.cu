@@ -209,6 +209,7 @@ struct eqd_handle {
   // stations / histories
   int nOff = 0, nOn = 0, nOnAlloc = 1, nSurf = 0, nGm = 0;
   std::vector<int> idhistH, anonfsH, surfH;
+  std::vector<int> stationAlias;  // on-fault station -> the station whose device row holds its pair's record
   DevBuf<int> dIdhist, dSurf;
   DevBuf<double> dOnHist, dOffHist, dHypo, dTpHist, dGm, dSrc;
   // halo
@@ -241,7 +242,9 @@ struct eqd_handle {
   int optBox = 0;   // closed-form operators on all-box tiles (eqd_box.h): 1 = regular classes, 2 = also PML; set before the first eqd_run
   int optTile[2][3] = {{kRegBrick[0], kRegBrick[1], kRegBrick[2]}, {kPmlBrick[0], kPmlBrick[1], kPmlBrick[2]}};  // brick of a regular / PML tile in elements along x, z, y (before eqd_set_mesh)
   double tms[EQD_T_NSLOTS] = {0};
-  std::vector<cudaEvent_t> evs;  // timing events
+  std::vector<cudaEvent_t> evs;  // timing events in flight: (start, stop, slot) triples
+  std::vector<cudaEvent_t> evPool;  // timing events, created once and reused run after run (no create / destroy inside the step loop)
+  size_t evPoolUsed = 0;
 
   NodeArgs nodeArgs() const;
   ElemArgs elemArgs(int c) const;
@@ -576,7 +579,16 @@ void finalize(eqd_handle* h) {
     const int i = h->anonfsH[3 * j], ift = h->anonfsH[3 * j + 2];
     const int ref = (i - 1) + h->nftmx * (ift - 1);
     for (int q = 0; q < h->nPairs; ++q)
-      if (h->pairRef[q] == ref) pairStation[q] = j;  // last matching station wins, as the reference's loop
+      if (h->pairRef[q] == ref) pairStation[q] = j;  // the device records one row per pair: the last matching station's
+  }
+  // storeOnFaultStationQuantSCEC (faulting.f90:524-539) writes the record of a pair into the slot of EVERY station
+  // that snapped to it; stations sharing a pair get a copy of the recorded row when the history is fetched
+  h->stationAlias.assign(std::max(h->nOn, 1), 0);
+  for (int j = 0; j < h->nOn; ++j) {
+    const int ref = (h->anonfsH[3 * j] - 1) + h->nftmx * (h->anonfsH[3 * j + 2] - 1);
+    h->stationAlias[j] = j;
+    for (int q = 0; q < h->nPairs; ++q)
+      if (h->pairRef[q] == ref && pairStation[q] >= 0) h->stationAlias[j] = pairStation[q];
   }
   h->dPairStation.upload(pairStation);
   h->nOnAlloc = std::max(h->nOn, 1);
@@ -630,7 +642,11 @@ struct Timer {
   eqd_handle* h; int slot; cudaEvent_t a = nullptr, b = nullptr; cudaStream_t s;
   Timer(eqd_handle* h_, int slot_, cudaStream_t s_ = nullptr) : h(h_), slot(slot_), s(s_ ? s_ : h_->stream) {
     if (!h->timing) return;
-    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    if (h->evPoolUsed + 2 > h->evPool.size()) {
+      const size_t grow = std::max<size_t>(64, h->evPool.size());
+      for (size_t k = 0; k < grow; ++k) { cudaEvent_t e; CK(cudaEventCreate(&e)); h->evPool.push_back(e); }
+    }
+    a = h->evPool[h->evPoolUsed++]; b = h->evPool[h->evPoolUsed++];
     CK(cudaEventRecord(a, s));
   }
   void stop() {
@@ -645,9 +661,9 @@ void collect_timing(eqd_handle* h) {
     float ms = 0;
     cudaEventElapsedTime(&ms, h->evs[i], h->evs[i + 1]);
     h->tms[(int)(intptr_t)h->evs[i + 2]] += ms;
-    cudaEventDestroy(h->evs[i]); cudaEventDestroy(h->evs[i + 1]);
   }
   h->evs.clear();
+  h->evPoolUsed = 0;
 }
 
 void halo_pack(eqd_handle* h, int a, cudaStream_t st = nullptr) {
@@ -878,6 +894,7 @@ int eqd_destroy(eqd_handle* h) {
   if (h->comm && g_nccl.lib) g_nccl.CommDestroy(h->comm);
   for (int a = 0; a < 3; ++a) if (h->evPacked[a]) cudaEventDestroy(h->evPacked[a]);
   for (cudaEvent_t e : {h->evFace, h->evElem, h->evComm}) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->evPool) cudaEventDestroy(e);
   if (h->commStream) cudaStreamDestroy(h->commStream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -1830,7 +1847,14 @@ int eqd_fetch(eqd_handle* h, int32_t which, void* dst, int64_t dst_bytes) {
         }
         break;
       }
-      case EQD_F_ONFAULT_HIST: finalize(h); want(h->dOnHist.n); CK(cudaMemcpy(out, h->dOnHist.p, sizeof(double) * h->dOnHist.n, cudaMemcpyDeviceToHost)); break;
+      case EQD_F_ONFAULT_HIST: {
+        finalize(h); want(h->dOnHist.n);
+        CK(cudaMemcpy(out, h->dOnHist.p, sizeof(double) * h->dOnHist.n, cudaMemcpyDeviceToHost));
+        const size_t row = 12 * (size_t)std::max(h->p.nstep, 1);
+        for (int j = 0; j < h->nOn; ++j)
+          if (h->stationAlias[j] != j) memcpy(out + row * j, out + row * h->stationAlias[j], sizeof(double) * row);
+        break;
+      }
       case EQD_F_OFFFAULT_HIST: finalize(h); want(h->dOffHist.n); if (h->dOffHist.n) CK(cudaMemcpy(out, h->dOffHist.p, sizeof(double) * h->dOffHist.n, cudaMemcpyDeviceToHost)); break;
       case EQD_F_HYPO_LOG: finalize(h); want(h->dHypo.n); CK(cudaMemcpy(out, h->dHypo.p, sizeof(double) * h->dHypo.n, cudaMemcpyDeviceToHost)); break;
       case EQD_F_GM: finalize(h); want(3 * (size_t)h->nSurf * h->nGm); if (h->dGm.p && h->nGm) CK(cudaMemcpy(out, h->dGm.p, sizeof(double) * 3 * (size_t)h->nSurf * h->nGm, cudaMemcpyDeviceToHost)); break;

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(128) k_march_mass(const MarchBundle* __restric
   const int b = slotBundle[slot / MK_PN];   // node planes never straddle bundles: one entry per plane
   if (b < 0) return;
   const MarchBundle B = rec[b];
-  const int k = slot - B.n0, pl = k / MK_PN, i = k - pl * MK_PN, iz = i / (MK_BY + 1), iy = i - iz * (MK_BY + 1);
+  const int k = slot - B.n0, pl = k / MK_PN, i = k - pl * MK_PN, iz = i / MK_NY, iy = i - iz * MK_NY;
   const int c = code[slot];
   if (c < 0) { pm[slot] = 0.0; return; }
   const int bz = B.shape & 0xff, by = (B.shape >> 8) & 0xff;
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(128) k_march_mass(const MarchBundle* __restric
       for (int dy = 1; dy >= 0; --dy) {
         const int p = pl - dx, cz = iz - dz, cy = iy - dy;
         if (p < 0 || p >= B.Lx || cz < 0 || cz >= bz || cy < 0 || cy >= by) continue;
-        const size_t e = (size_t)B.e0 + (size_t)p * MK_NCOL + cz * MK_BY + cy;
+        const size_t e = (size_t)B.e0 + (size_t)p * MK_ES + cz * MK_NY + cy;
         sum = sum + em[(size_t)corner[dx][dy][dz] * S + e];
       }
   pm[slot] = sum;
@@ -303,7 +303,7 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
   for (int b = 0; b < nB; ++b) {
     stripOf[b] = P.rec[b].n0; xOf[b] = P.rec[b].e0;
     P.rec[b].e0 = (int)eslot; P.rec[b].n0 = (int)nslot;
-    eslot += (long)P.rec[b].Lx * MK_NCOL;
+    eslot += (long)P.rec[b].Lx * MK_ES;
     nslot += (long)(P.rec[b].Lx + 1) * MK_PN;
     if (eslot > (1L << 29) || nslot > (1L << 30)) throw std::runtime_error("march planner: class too large for 32-bit slots");
   }
@@ -330,7 +330,7 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
             for (int z = 0; z < bz; ++z)
               for (int y = 0; y < by; ++y) {
                 const int j = at(x0 + p, s.z0 + z, s.y0 + y);
-                P.refId[(size_t)B.e0 + (size_t)p * MK_NCOL + z * MK_BY + y] = elems[j];
+                P.refId[(size_t)B.e0 + (size_t)p * MK_ES + z * MK_NY + y] = elems[j];
                 taken[j] = 1;
                 elemsT[t]++;
               }
@@ -352,7 +352,7 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
                 const bool interior = pl > 0 && pl < B.Lx && iz > 0 && iz < bz && iy > 0 && iy < by;
                 const bool fused = interior && EQD_INFO_KIND(info[id]) == KIND_FREE3;
                 if (fused) fusedT[t]++;
-                P.code[(size_t)B.n0 + (size_t)pl * MK_PN + iz * (MK_BY + 1) + iy] = id | (fused ? MK_FUSED : 0);
+                P.code[(size_t)B.n0 + (size_t)pl * MK_PN + iz * MK_NY + iy] = id | (fused ? MK_FUSED : 0);
               }
           }
         }

@@ -40,21 +40,21 @@
 
 namespace eqd {
 
-constexpr int MK_BZ = 8, MK_BY = 16;                 // columns of a full bundle cross-section (z, y)
-constexpr int MK_NCOL = MK_BZ * MK_BY;               // = threads per CTA = element slots per plane
-constexpr int MK_NT = MK_NCOL;
-constexpr int MK_PN = (MK_BZ + 1) * (MK_BY + 1);     // nodes of a plane
-constexpr int MK_PNP = (MK_PN + 1) & ~1;             // padded to an even count (16-byte rows)
+constexpr int MK_NZ = 8, MK_NY = 16;                 // nodes of a bundle cross-section (z, y)
+constexpr int MK_BZ = MK_NZ - 1, MK_BY = MK_NY - 1;  // element columns of a full bundle cross-section: 7 x 15
+constexpr int MK_PN = MK_NZ * MK_NY;                 // nodes of a plane = threads of the CTA: thread t owns node t of every plane
+constexpr int MK_NT = MK_PN;                         //   and the element column whose (y-, z-) corner is node t
+constexpr int MK_ES = MK_BZ * MK_NY;                 // element slots per plane (the y = MK_BY column of every row stays empty)
 constexpr int MK_OPROWS = 15;                        // a_x a_y a_z ss1 ss4 ss6 lam mu det stress(6)
 constexpr int MK_FUSED = 0x40000000;                 // node code: updated by the bundle itself
 constexpr int MK_IDMASK = 0x3fffffff;
 constexpr int MK_MINLX = 4;                          // shortest bundle the planner makes
 
 struct MarchBundle {
-  int e0;      // first element slot of the class SoA (multiple of MK_NCOL): slot = e0 + p*MK_NCOL + cz*MK_BY + cy
-  int n0;      // first node slot: slot = n0 + p*MK_PN + iz*(MK_BY+1) + iy
+  int e0;      // first element slot of the class SoA (multiple of MK_ES): slot = e0 + p*MK_ES + cz*MK_NY + cy
+  int n0;      // first node slot: slot = n0 + p*MK_PN + iz*MK_NY + iy
   int Lx;      // elements along x (node planes 0..Lx)
-  int shape;   // bz | by << 8: active columns cz < bz, cy < by
+  int shape;   // bz | by << 8: active columns cz < bz <= MK_BZ, cy < by <= MK_BY
 };
 
 struct MarchArgs {
@@ -76,10 +76,9 @@ struct MarchArgs {
 };
 
 struct MarchShared {
-  double ops[2][MK_OPROWS][MK_NCOL];   // operator stage of element plane p in ops[p & 1]
-  double ring[3][7][MK_PNP];           // node plane pl in ring[pl % 3]: v(3) d(3) m
-  double frc[4][3][MK_PNP];            // force plane, one buffer per (dy,dz) corner
-  int ids[4][MK_PNP];                  // node codes of plane pl in ids[pl & 3]
+  double ops[2][MK_OPROWS][MK_ES];     // operator stage of element plane p in ops[p & 1]
+  double ring[3][6][MK_PN];            // node plane pl in ring[pl % 3]: v(3) d(3)
+  double frc[4][3][MK_PN];             // force plane, one buffer per (dy,dz) corner
   unsigned long long bar[2];           // mbarrier of each operator stage
 };
 
@@ -88,6 +87,8 @@ struct MarchRegs {
   double wv[3][3];   // [S0 | Sy | Sz][component] of the x- face velocities
   double wl[3][3];   // [Sy | Sz | Syz][component] of the x- face l = d + rdampk v
   double cf[4][3];   // x+ face forces of the previous element, transformed: [1 | sy | sz | sy sz][component]
+  int c0, c1, c2, c3;   // codes of this thread's node in planes p, p+1, p+2, p+3
+  double m;          // lumped mass of its node in plane p
 };
 
 // ---- asynchronous copies: real on the device, immediate in the host reading
@@ -95,9 +96,6 @@ struct MarchRegs {
 __device__ __forceinline__ unsigned mk_s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mk_async8(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(mk_s32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void mk_async4(void* dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(mk_s32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void mk_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void mk_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -130,7 +128,6 @@ __device__ __forceinline__ void mk_nan(StepState* st, int node) {
 }
 #else
 EQD_HD void mk_async8(void* dst, const void* src) { *(double*)dst = *(const double*)src; }
-EQD_HD void mk_async4(void* dst, const void* src) { *(int*)dst = *(const int*)src; }
 EQD_HD void mk_commit() {}
 EQD_HD void mk_wait_all() {}
 EQD_HD void mk_bar_init(unsigned long long*) {}
@@ -155,69 +152,61 @@ EQD_HD const double* mk_op_row(const MarchArgs& A, int r) {
   return A.stress + (size_t)(r - 9) * A.S;
 }
 
-// ---- issue: node codes of plane pl -> ids[pl & 3]
-EQD_HD void mk_issue_ids(const MarchArgs& A, const MarchBundle& B, MarchShared& sm, int tid, int pl) {
-  if (pl > B.Lx) return;
-  const int* src = A.code + (size_t)B.n0 + (size_t)pl * MK_PN;
-  for (int i = tid; i < MK_PN; i += MK_NT) mk_async4(&sm.ids[pl & 3][i], src + i);
+// code of this thread's node in plane pl (-1 beyond the bundle)
+EQD_HD int mk_code(const MarchArgs& A, const MarchBundle& B, int tid, int pl) {
+  return pl <= B.Lx ? A.code[(size_t)B.n0 + (size_t)pl * MK_PN + tid] : -1;
 }
-// ---- issue: v, d, m of plane pl -> ring[pl % 3] (its codes must have landed)
-EQD_HD void mk_issue_values(const MarchArgs& A, const MarchBundle& B, MarchShared& sm, int tid, int pl) {
-  if (pl > B.Lx) return;
-  double(*dst)[MK_PNP] = sm.ring[pl % 3];
-  for (int i = tid; i < MK_PN; i += MK_NT) {
-    const int code = sm.ids[pl & 3][i];
-    if (code >= 0) {
-      const size_t n = (size_t)(code & MK_IDMASK);
+// ---- issue: v, d of this thread's node (code) -> ring slot rs
+EQD_HD void mk_issue_values(const MarchArgs& A, MarchShared& sm, int tid, int rs, int code) {
+  double(*dst)[MK_PN] = sm.ring[rs];
+  if (code >= 0) {
+    const double* v = A.vel + (size_t)(code & MK_IDMASK);
+    const double* d = A.disp + (size_t)(code & MK_IDMASK);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        mk_async8(&dst[c][i], A.vel + c * A.NnS + n);
-        mk_async8(&dst[3 + c][i], A.disp + c * A.NnS + n);
-      }
-      mk_async8(&dst[6][i], A.mass + n);
-    } else {
-#pragma unroll
-      for (int c = 0; c < 6; ++c) dst[c][i] = 0.0;
-      dst[6][i] = 1.0;
+    for (int c = 0; c < 3; ++c) {
+      mk_async8(&dst[c][tid], v + c * A.NnS);
+      mk_async8(&dst[3 + c][tid], d + c * A.NnS);
     }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) dst[c][tid] = 0.0;
   }
 }
 // ---- issue: operator rows of element plane p -> ops[p & 1]
 EQD_HD void mk_issue_ops(const MarchArgs& A, const MarchBundle& B, MarchShared& sm, int tid, int p) {
   if (p >= B.Lx) return;
   unsigned long long* bar = &sm.bar[p & 1];
-  if (tid == 0) mk_bar_expect(bar, (unsigned)(MK_OPROWS * MK_NCOL * sizeof(double)));
+  if (tid == 0) mk_bar_expect(bar, (unsigned)(MK_OPROWS * MK_ES * sizeof(double)));
 #if defined(__CUDA_ARCH__)
   __syncwarp();
 #endif
   if (tid < MK_OPROWS)
-    mk_bulk(sm.ops[p & 1][tid], mk_op_row(A, tid) + (size_t)B.e0 + (size_t)p * MK_NCOL, (unsigned)(MK_NCOL * sizeof(double)), bar);
+    mk_bulk(sm.ops[p & 1][tid], mk_op_row(A, tid) + (size_t)B.e0 + (size_t)p * MK_ES, (unsigned)(MK_ES * sizeof(double)), bar);
 }
 
 // 4-point transform of a face: a[q], q = dy + 2 dz
 #define MK_FACE_SUMS(a0, a1, a2, a3)          \
   const double s0_ = (a0) + (a1), s1_ = (a2) + (a3), d0_ = (a1) - (a0), d1_ = (a3) - (a2);
 
+EQD_HD bool mk_active(const MarchBundle& B, int tid) { return (tid / MK_NY) < mk_bz(B) && (tid % MK_NY) < mk_by(B); }
+
 // ---- phase: bundle start.  Clears the force buffers and takes the transformed x- face of the first element.
 EQD_HD void mk_phase_begin(const MarchArgs& A, const MarchBundle& B, MarchShared& sm, MarchRegs& R, int tid) {
-  for (int i = tid; i < MK_PNP; i += MK_NT)
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
+  for (int q = 0; q < 4; ++q)
 #pragma unroll
-      for (int c = 0; c < 3; ++c) sm.frc[q][c][i] = 0.0;
-  const int cz = tid / MK_BY, cy = tid - cz * MK_BY;
-  if (cz >= mk_bz(B) || cy >= mk_by(B)) return;
-  const int l0 = cz * (MK_BY + 1) + cy;
-  double(*pl)[MK_PNP] = sm.ring[0];
+    for (int c = 0; c < 3; ++c) sm.frc[q][c][tid] = 0.0;
+  if (!mk_active(B, tid)) return;
+  double(*pl)[MK_PN] = sm.ring[0];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const double v0 = pl[c][l0], v1 = pl[c][l0 + 1], v2 = pl[c][l0 + MK_BY + 1], v3 = pl[c][l0 + MK_BY + 2];
+    const double v0 = pl[c][tid], v1 = pl[c][tid + 1], v2 = pl[c][tid + MK_NY], v3 = pl[c][tid + MK_NY + 1];
     {
       MK_FACE_SUMS(v0, v1, v2, v3)
       R.wv[0][c] = s0_ + s1_; R.wv[1][c] = d0_ + d1_; R.wv[2][c] = s1_ - s0_;
     }
-    const double m0 = pl[3 + c][l0] + A.rdampk * v0, m1 = pl[3 + c][l0 + 1] + A.rdampk * v1;
-    const double m2 = pl[3 + c][l0 + MK_BY + 1] + A.rdampk * v2, m3 = pl[3 + c][l0 + MK_BY + 2] + A.rdampk * v3;
+    const double m0 = pl[3 + c][tid] + A.rdampk * v0, m1 = pl[3 + c][tid + 1] + A.rdampk * v1;
+    const double m2 = pl[3 + c][tid + MK_NY] + A.rdampk * v2, m3 = pl[3 + c][tid + MK_NY + 1] + A.rdampk * v3;
     {
       MK_FACE_SUMS(m0, m1, m2, m3)
       R.wl[0][c] = d0_ + d1_; R.wl[1][c] = s1_ - s0_; R.wl[2][c] = d1_ - d0_;
@@ -228,25 +217,23 @@ EQD_HD void mk_phase_begin(const MarchArgs& A, const MarchBundle& B, MarchShared
 }
 
 // inverse face transform of G[k], k = 1 | sy | sz | sy sz, stored to the four corner buffers
-EQD_HD void mk_store_face(MarchShared& sm, int c, int l0, double G0, double G1, double G2, double G3) {
+EQD_HD void mk_store_face(MarchShared& sm, int c, int tid, double G0, double G1, double G2, double G3) {
   const double um = G0 - G1, up = G0 + G1, wm = G2 - G3, wp = G2 + G3;
-  sm.frc[0][c][l0] = um - wm;                       // (y-, z-)
-  sm.frc[1][c][l0 + 1] = up - wp;                   // (y+, z-)
-  sm.frc[2][c][l0 + MK_BY + 1] = um + wm;           // (y-, z+)
-  sm.frc[3][c][l0 + MK_BY + 2] = up + wp;           // (y+, z+)
+  sm.frc[0][c][tid] = um - wm;                      // (y-, z-)
+  sm.frc[1][c][tid + 1] = up - wp;                  // (y+, z-)
+  sm.frc[2][c][tid + MK_NY] = um + wm;              // (y-, z+)
+  sm.frc[3][c][tid + MK_NY + 1] = up + wp;          // (y+, z+)
 }
 
-// ---- phase: element p of this thread's column
-EQD_HD void mk_phase_element(const MarchArgs& A, const MarchBundle& B, MarchShared& sm, MarchRegs& R, int tid, int p) {
-  const int cz = tid / MK_BY, cy = tid - cz * MK_BY;
-  if (cz >= mk_bz(B) || cy >= mk_by(B)) return;
-  const int l0 = cz * (MK_BY + 1) + cy;
-  double(*pl)[MK_PNP] = sm.ring[(p + 1) % 3];
-  const double(*op)[MK_NCOL] = sm.ops[p & 1];
+// ---- phase: element p of this thread's column; rs1 = ring slot of node plane p+1
+EQD_HD void mk_phase_element(const MarchArgs& A, const MarchBundle& B, MarchShared& sm, MarchRegs& R, int tid, int p, int rs1) {
+  if (!mk_active(B, tid)) return;
+  double(*pl)[MK_PN] = sm.ring[rs1];
+  const double(*op)[MK_ES] = sm.ops[p & 1];
   double gx[3], gy[3], gz[3], P[4][3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const double v0 = pl[c][l0], v1 = pl[c][l0 + 1], v2 = pl[c][l0 + MK_BY + 1], v3 = pl[c][l0 + MK_BY + 2];
+    const double v0 = pl[c][tid], v1 = pl[c][tid + 1], v2 = pl[c][tid + MK_NY], v3 = pl[c][tid + MK_NY + 1];
     {
       MK_FACE_SUMS(v0, v1, v2, v3)
       const double n0 = s0_ + s1_, ny = d0_ + d1_, nz = s1_ - s0_;
@@ -255,8 +242,8 @@ EQD_HD void mk_phase_element(const MarchArgs& A, const MarchBundle& B, MarchShar
       R.wv[0][c] = n0; R.wv[1][c] = ny; R.wv[2][c] = nz;
     }
     // hrglss.f90:20-27: l = d + rdampk v
-    const double m0 = pl[3 + c][l0] + A.rdampk * v0, m1 = pl[3 + c][l0 + 1] + A.rdampk * v1;
-    const double m2 = pl[3 + c][l0 + MK_BY + 1] + A.rdampk * v2, m3 = pl[3 + c][l0 + MK_BY + 2] + A.rdampk * v3;
+    const double m0 = pl[3 + c][tid] + A.rdampk * v0, m1 = pl[3 + c][tid + 1] + A.rdampk * v1;
+    const double m2 = pl[3 + c][tid + MK_NY] + A.rdampk * v2, m3 = pl[3 + c][tid + MK_NY + 1] + A.rdampk * v3;
     {
       MK_FACE_SUMS(m0, m1, m2, m3)
       const double ny = d0_ + d1_, nz = s1_ - s0_, nyz = d1_ - d0_;
@@ -265,7 +252,8 @@ EQD_HD void mk_phase_element(const MarchArgs& A, const MarchBundle& B, MarchShar
       R.wl[0][c] = ny; R.wl[1][c] = nz; R.wl[2][c] = nyz;
     }
   }
-  const double ax = op[0][tid], ay = op[1][tid], az = op[2][tid];
+  const int es = tid;   // element slot inside the plane = cz*MK_NY + cy
+  const double ax = op[0][es], ay = op[1][es], az = op[2][es];
   // calcElemKU.f90:44-60 with eleshp(d,i) = sign_d(i) a_d
   double sr[6];
   sr[0] = ax * gx[0];
@@ -274,7 +262,7 @@ EQD_HD void mk_phase_element(const MarchArgs& A, const MarchBundle& B, MarchShar
   sr[3] = az * gz[1] + ay * gy[2];
   sr[4] = az * gz[0] + ax * gx[2];
   sr[5] = ay * gy[0] + ax * gx[1];
-  const double lam = op[6][tid], mu = op[7][tid], l2m = lam + 2 * mu;
+  const double lam = op[6][es], mu = op[7][es], l2m = lam + 2 * mu;
   double rate[6];   // calcElemKU.f90:63-70
   rate[0] = 0.0 + l2m * sr[0] + lam * sr[1] + lam * sr[2];
   rate[1] = 0.0 + lam * sr[0] + l2m * sr[1] + lam * sr[2];
@@ -282,16 +270,16 @@ EQD_HD void mk_phase_element(const MarchArgs& A, const MarchBundle& B, MarchShar
   rate[3] = mu * sr[3];
   rate[4] = mu * sr[4];
   rate[5] = mu * sr[5];
-  const double temp = (-op[8][tid]) * A.w;   // calcElemKU.f90:169-173, constk = -eledet
-  const size_t e = (size_t)B.e0 + (size_t)p * MK_NCOL + tid;
+  const double temp = (-op[8][es]) * A.w;   // calcElemKU.f90:169-173, constk = -eledet
+  double* sp = A.stress + (size_t)B.e0 + (size_t)p * MK_ES + es;
   double t[6];
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
-    const double sg = op[9 + k][tid] + rate[k] * A.dt;   // :72-76
-    A.stress[(size_t)k * A.S + e] = sg;
+    const double sg = op[9 + k][es] + rate[k] * A.dt;   // :72-76
+    sp[(size_t)k * A.S] = sg;
     t[k] = temp * (sg + A.rdampk * rate[k]);
   }
-  const double ssd[3] = {op[3][tid], op[4][tid], op[5][tid]};
+  const double ssd[3] = {op[3][es], op[4][es], op[5][es]};
   // B^T t (calcElemKU.f90:175-189): f_c = sx X + sy Y + sz Z ; hourglass (hrglss.f90:35-54): - sum_m ha(m) ss_c P_m
   const double X[3] = {ax * t[0], ax * t[5], ax * t[4]};
   const double Y[3] = {ay * t[5], ay * t[1], ay * t[3]};
@@ -301,79 +289,78 @@ EQD_HD void mk_phase_element(const MarchArgs& A, const MarchBundle& B, MarchShar
     const double H0 = ssd[c] * P[0][c], H1 = ssd[c] * P[1][c], H2 = ssd[c] * P[2][c], H3 = ssd[c] * P[3][c];
     // x- face of this element (sx = -1) + the carried x+ face of the previous one
     const double G0 = R.cf[0][c] - X[c], G1 = R.cf[1][c] + (Y[c] + H2), G2 = R.cf[2][c] + (Z[c] + H1), G3 = R.cf[3][c] + (H3 - H0);
-    mk_store_face(sm, c, l0, G0, G1, G2, G3);
+    mk_store_face(sm, c, tid, G0, G1, G2, G3);
     R.cf[0][c] = X[c]; R.cf[1][c] = Y[c] - H2; R.cf[2][c] = Z[c] - H1; R.cf[3][c] = 0.0 - H0 - H3;
   }
 }
 
 // ---- phase: the last node plane receives the carried x+ faces only
 EQD_HD void mk_phase_last(const MarchBundle& B, MarchShared& sm, MarchRegs& R, int tid) {
-  const int cz = tid / MK_BY, cy = tid - cz * MK_BY;
-  if (cz >= mk_bz(B) || cy >= mk_by(B)) return;
-  const int l0 = cz * (MK_BY + 1) + cy;
+  if (!mk_active(B, tid)) return;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) mk_store_face(sm, c, l0, R.cf[0][c], R.cf[1][c], R.cf[2][c], R.cf[3][c]);
+  for (int c = 0; c < 3; ++c) mk_store_face(sm, c, tid, R.cf[0][c], R.cf[1][c], R.cf[2][c], R.cf[3][c]);
 }
 
-// ---- phase: node plane pl is complete
-EQD_HD void mk_phase_flush(const MarchArgs& A, const MarchBundle& B, MarchShared& sm, int tid, int pl) {
-  double(*rg)[MK_PNP] = sm.ring[pl % 3];
-  for (int i = tid; i < MK_PN; i += MK_NT) {
-    const int code = sm.ids[pl & 3][i];
-    if (code < 0) continue;
-    double F[3];
+// ---- phase: node plane pl is complete; rs = its ring slot, code / m = this thread's node
+EQD_HD void mk_phase_flush(const MarchArgs& A, const MarchBundle& B, MarchShared& sm, int tid, int pl, int rs, int code, double m) {
+  if (code < 0) return;
+  double F[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) F[c] = ((sm.frc[0][c][i] + sm.frc[1][c][i]) + sm.frc[2][c][i]) + sm.frc[3][c][i];
-    const size_t n = (size_t)(code & MK_IDMASK);
-    if (code & MK_FUSED) {
-      if (A.update) {
-        const double m = rg[6][i];
-        bool bad = false;
+  for (int c = 0; c < 3; ++c) F[c] = ((sm.frc[0][c][tid] + sm.frc[1][c][tid]) + sm.frc[2][c][tid]) + sm.frc[3][c][tid];
+  const size_t n = (size_t)(code & MK_IDMASK);
+  if (code & MK_FUSED) {
+    if (A.update) {
+      double(*rg)[MK_PN] = sm.ring[rs];
+      bool bad = false;
+      const double rm = 1.0 / m;              // one reciprocal instead of three divisions: f/m within one rounding
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          double v = rg[c][i], d = rg[3 + c][i];
-          v = v + (F[c] / m) * A.dt;            // driver.f90:29,102
-          d = d + v * A.dt;                     // :104
-          bad |= (v != v);
-          A.vel[c * A.NnS + n] = v; A.disp[c * A.NnS + n] = d;
-        }
-        if (bad) mk_nan(A.st, (int)n);
-      } else {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) A.force[c * A.NnS + n] = F[c];
+      for (int c = 0; c < 3; ++c) {
+        double v = rg[c][tid], d = rg[3 + c][tid];
+        v = v + (F[c] * rm) * A.dt;           // driver.f90:29,102
+        d = d + v * A.dt;                     // :104
+        bad |= (v != v);
+        A.vel[c * A.NnS + n] = v; A.disp[c * A.NnS + n] = d;
       }
+      if (bad) mk_nan(A.st, (int)n);
     } else {
-      const size_t slot = (size_t)B.n0 + (size_t)pl * MK_PN + i;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) A.pf[c * A.PFS + slot] = F[c];
+      for (int c = 0; c < 3; ++c) A.force[c * A.NnS + n] = F[c];
     }
+  } else {
+    const size_t slot = (size_t)B.n0 + (size_t)pl * MK_PN + tid;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) A.pf[c * A.PFS + slot] = F[c];
   }
 }
 
 // The schedule.  RUN(body) executes `body` for every thread of the CTA and then synchronises: a statement +
 // __syncthreads() on the device, a loop over the thread ids on the host; RUNNS(body) does the same without
 // the barrier.  WAIT_NODES / WAIT_OPS(p) are the cp.async / mbarrier waits (nothing on the host, where copies
-// complete at issue).
+// complete at issue).  Thread t owns node t of every plane: it fetches the node's code (three planes ahead,
+// into a register), issues the copies of its v, d (two planes ahead, into the shared ring), loads its mass
+// (during the element work of the step that completes it) and finally flushes it.
 //   step p:  [plane p+1 and operator stage p have landed] barrier
-//            issue plane p+2 values, plane p+3 codes, operator stage p+1 ; element p -> force buffers ; barrier
-//            flush node plane p (update or partial)
-// Ring slot (p+2)%3 was last read by the flush of plane p-1, the code slot (p+3)&3 by that flush too, the
-// operator stage (p+1)&1 by element p-1: all before the barrier that opens step p.
-#define MARCH_BUNDLE(RUN, RUNNS, WAIT_NODES, WAIT_OPS, A, B, sm, R)                                                           \
+//            issue plane p+2 values and operator stage p+1, load the mass of plane p ; element p -> force buffers ; barrier
+//            flush node plane p (update or partial) ; fetch the code of plane p+4
+// Ring slot (p+2)%3 was last read by the flush of plane p-1, the operator stage (p+1)&1 by element p-1, the
+// force buffers by that flush: all before the barrier that opens step p.
+#define MARCH_BUNDLE(RUN, RUNNS, WAIT_NODES, WAIT_OPS, A, B, sm, R)                                                     \
   do {                                                                                                                 \
-    RUN(mk_issue_ids(A, B, sm, tid, 0); mk_issue_ids(A, B, sm, tid, 1); mk_issue_ids(A, B, sm, tid, 2); mk_commit(); WAIT_NODES); \
-    RUN(mk_issue_values(A, B, sm, tid, 0); mk_issue_values(A, B, sm, tid, 1); mk_issue_ops(A, B, sm, tid, 0);           \
+    RUN(R.c0 = mk_code(A, B, tid, 0); R.c1 = mk_code(A, B, tid, 1); R.c2 = mk_code(A, B, tid, 2); R.c3 = mk_code(A, B, tid, 3); \
+        mk_issue_values(A, sm, tid, 0, R.c0); mk_issue_values(A, sm, tid, 1, R.c1); mk_issue_ops(A, B, sm, tid, 0);     \
         mk_commit(); WAIT_NODES);                                                                                      \
     RUN(mk_phase_begin(A, B, sm, R, tid));                                                                             \
-    for (int p = 0; p < (B).Lx; ++p) {                                                                                 \
+    for (int p = 0, rs0 = 0, rs1 = 1, rs2 = 2; p < (B).Lx; ++p) {                                                      \
       RUN(WAIT_NODES; WAIT_OPS(p));                                                                                    \
-      RUN(mk_issue_values(A, B, sm, tid, p + 2); mk_issue_ids(A, B, sm, tid, p + 3); mk_issue_ops(A, B, sm, tid, p + 1); \
-          mk_commit(); mk_phase_element(A, B, sm, R, tid, p));                                                         \
-      RUNNS(mk_phase_flush(A, B, sm, tid, p));                                                                         \
+      RUN(mk_issue_values(A, sm, tid, rs2, R.c2); mk_issue_ops(A, B, sm, tid, p + 1); mk_commit();                     \
+          R.m = R.c0 >= 0 ? A.mass[R.c0 & MK_IDMASK] : 1.0; mk_phase_element(A, B, sm, R, tid, p, rs1));               \
+      RUNNS(mk_phase_flush(A, B, sm, tid, p, rs0, R.c0, R.m);                                                          \
+            R.c0 = R.c1; R.c1 = R.c2; R.c2 = R.c3; R.c3 = mk_code(A, B, tid, p + 4));                                  \
+      { const int t_ = rs0; rs0 = rs1; rs1 = rs2; rs2 = t_; }                                                          \
     }                                                                                                                  \
     RUN(WAIT_NODES);                                                                                                   \
     RUN(mk_phase_last(B, sm, R, tid));                                                                                 \
-    RUN(mk_phase_flush(A, B, sm, tid, (B).Lx));                                                                        \
+    RUN(mk_phase_flush(A, B, sm, tid, (B).Lx, (B).Lx % 3, R.c0, 1.0));                                                 \
   } while (0)
 
 }  // namespace eqd

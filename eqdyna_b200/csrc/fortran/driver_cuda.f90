@@ -15,9 +15,10 @@ subroutine driver
     type(eqd_params) :: p
     type(c_ptr) :: h
     integer(c_int) :: ierr
-    integer :: mpierr, nSurf, chunk, nt0, nt1
+    integer :: mpierr, nSurf, chunk, nt0, nt1, k, i, nGmDone, nGmNow, hypoPair
     character(kind=c_char) :: id128(128), msg(512)
     integer(c_int32_t), target :: fltMPIint(6)
+    real(c_double), allocatable, target :: hypoLog(:,:), gmBuf(:,:,:), srcBuf(:,:)
 
     ! ---- scalars of module globalvar (readInputFiles.f90:182-186 already applied rdampk = rdampk*dt)
     p%dt = dt; p%nstep = nstep; p%me = me; p%npx = npx; p%npy = npy; p%npz = npz
@@ -64,6 +65,8 @@ subroutine driver
     ! the default to ~1e-14 per step (parity tests: 1e-10 against the CPU oracle).
     ! ierr = eqd_set_option(h, 'box'//c_null_char, 2_c_int32_t);          call check('eqd_set_option box')
     ! ierr = eqd_set_option(h, 'box_compact'//c_null_char, 1_c_int32_t);  call check('eqd_set_option box_compact')
+    ! The marching kernel (DESIGN.md 3e; elastic runs) is chosen BEFORE eqd_set_mesh:
+    ! ierr = eqd_set_option(h, 'march'//c_null_char, 1_c_int32_t)
 
     if (npx*npy*npz > 1) then
         if (me == masterProcsId) ierr = eqd_get_unique_id(id128)
@@ -72,21 +75,77 @@ subroutine driver
         call check('eqd_set_comm')
     endif
 
-    ! ---- the loop of driver.f90:9-34, in chunks of 100 steps so that the banner keeps appearing
+    ! ---- the loop of driver.f90:9-34, in chunks of 100 steps: the banner of driver.f90:13-17 appears at
+    ! nt = 1, 101, ... with the accumulated timeElapsed, and after every chunk the samples output_gm /
+    ! output_src_evol would have appended inside it (driver.f90:30-33: every step with mod(nt,10) == 1) are
+    ! fetched and appended to gm<me> / src_evol<me>, and the hypocentre block of showSourceDynamics
+    ! (faulting.f90:343-365) is printed from the recorded log -- one block per step, as the reference does.
+    allocate(hypoLog(13, nstep))
+    hypoPair = 0
+    if (nftnd(1) > 0) then
+        do i = 1, nftnd(1)
+            if (abs(meshCoor(1,nsmp(1,i,1))-xsource) < tol .and. abs(meshCoor(3,nsmp(1,i,1))-zsource) < tol) hypoPair = i
+        enddo
+    endif
     chunk = 100
     nt0 = 1
+    nGmDone = 0
     do while (nt0 <= nstep)
         nt1 = min(nt0 + chunk - 1, nstep)
         if (me == masterProcsId) then
+            write(*,*) '=                                                                   ='
             write(*,*) '=     Current time in dynamic rupture                               ='
-            write(*,'(X,A,40X,f7.3,4X,A)') '=',  (nt0-1)*dt + dt , 's'
+            write(*,'(X,A,40X,f7.3,4X,A)') '=',  timeElapsed + dt , 's'
         endif
         ierr = eqd_run(h, nt0, nt1)
         call check('eqd_run')
+        do k = nt0, nt1
+            timeElapsed = timeElapsed + dt           ! the same accumulated sum as driver.f90:11
+        enddo
+        nt = nt1
+        if (hypoPair > 0) then
+            ierr = eqd_fetch(h, EQD_F_HYPO_LOG, c_loc(hypoLog), int(8*size(hypoLog), c_int64_t)); call check('fetch hypocentre log')
+            do k = nt0, nt1
+                write(*,*) 'Hypocenter dynamics'
+                write(*,'(X,A,3E15.7)') 'X, Y, Z      (m)   ', meshCoor(1,nsmp(1,hypoPair,1)), meshCoor(2,nsmp(1,hypoPair,1)), meshCoor(3,nsmp(1,hypoPair,1))
+                write(*,'(X,A,E15.7)') 'TimeElapsed  (s)   ', hypoLog(1,k)
+                write(*,'(X,A,3E15.7)') 'n,s,d tract  (MPa) ', hypoLog(2,k)/1.d6, hypoLog(3,k)/1.d6, hypoLog(4,k)/1.d6
+                write(*,'(X,A,E15.7)') 'state_normal (MPa) ', hypoLog(5,k)/1.d6
+                write(*,'(X,A,3E15.7)') 'n,s,d slip   (m)   ', hypoLog(6,k), hypoLog(7,k), hypoLog(8,k)
+                write(*,'(X,A,3E15.7)') 's,d, peak sr (m/s) ', hypoLog(9,k), hypoLog(10,k), hypoLog(11,k)
+                write(*,'(X,A,E15.7)') 'cummul slip  (m)   ', hypoLog(12,k)
+                write(*,'(X,A,3E15.7)') 'sw_fs, sw_fd, sw_D0', fric(1,hypoPair,1), fric(2,hypoPair,1), fric(3,hypoPair,1)
+                write(*,'(X,A,2E15.7)') 'rsf_a, rsf_b       ', fric(9,hypoPair,1), fric(10,hypoPair,1)
+                write(*,'(X,A,E15.7)') 'rsf_state          ', hypoLog(13,k)
+                write(*,'(X,A,E15.7)') 'Nuc add tau0 (MPa) ', fric(81,hypoPair,1)/1.d6
+            enddo
+        endif
+        if (outputGroundMotion == 1) then
+            nGmNow = (nt1 - 1)/10 + 1                 ! samples taken so far: steps 1, 11, 21, ... <= nt1
+            if (nGmNow > nGmDone) then
+                if (surface_nnode > 0) then            ! output_gm, library_output.f90:267-279
+                    allocate(gmBuf(3, surface_nnode, nGmNow))
+                    ierr = eqd_fetch(h, EQD_F_GM, c_loc(gmBuf), int(8*size(gmBuf), c_int64_t)); call check('fetch gm')
+                    open(unit=10009+me, file='gm'//mm, status='unknown', position='append', access='stream')
+                    write(10009+me) gmBuf(:, :, nGmDone+1:nGmNow)
+                    close(10009+me)
+                    deallocate(gmBuf)
+                endif
+                if (nftnd(1) > 0) then                 ! output_src_evol, library_output.f90:297-312
+                    allocate(srcBuf(nftnd(1), nGmNow))
+                    ierr = eqd_fetch(h, EQD_F_SRC_EVOL, c_loc(srcBuf), int(8*size(srcBuf), c_int64_t)); call check('fetch src_evol')
+                    open(unit=30009+me, file='src_evol'//mm, position='append', access='stream')
+                    write(30009+me) srcBuf(:, nGmDone+1:nGmNow)
+                    close(30009+me)
+                    deallocate(srcBuf)
+                endif
+                nGmDone = nGmNow
+            endif
+        endif
         nt0 = nt1 + 1
     enddo
     nt = nstep
-    timeElapsed = nstep*dt
+    deallocate(hypoLog)
 
     ! ---- post-state for output_onfault_st / output_offfault_st / output_frt / output_plastic_strain
     ierr = eqd_fetch(h, EQD_F_FRIC, c_loc(fric), int(8*size(fric), c_int64_t));                 call check('fetch fric')
@@ -102,6 +161,11 @@ subroutine driver
     if (C_elastic == 0) then
         ierr = eqd_fetch(h, EQD_F_PSTRAIN, c_loc(pstrain), int(8*size(pstrain), c_int64_t));    call check('fetch pstrain')
     endif
+    ! output_plastic_strain (library_output.f90:221-244) prints stressArr next to pstrain: the final stresses
+    ierr = eqd_fetch(h, EQD_F_STRESS, c_loc(stressArr), int(8*size(stressArr), c_int64_t));     call check('fetch stress')
+    ! v1 and the accelerations the reference leaves in nodalForceArr (driver.f90:29): needed by a host that goes on
+    ierr = eqd_fetch(h, EQD_F_V1, c_loc(v1), int(8*size(v1), c_int64_t));                       call check('fetch v1')
+    ierr = eqd_fetch(h, EQD_F_FORCE, c_loc(nodalForceArr), int(8*size(nodalForceArr), c_int64_t)); call check('fetch accel')
     ierr = eqd_destroy(h)
 
 contains

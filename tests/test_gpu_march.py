@@ -16,7 +16,8 @@ OPTS = {"box": 2, "box_compact": 1}
 CASES = [
     ("test.tpv8", (1, 1, 1), 0, 1, False, "slip weakening + PML, full 114 steps, host operators"),
     ("test.tpv8", (1, 1, 1), 40, 4, True, "four eqd_run calls (the last step of each leaves forces instead of updating), device operators + mass"),
-    ("test.tpv104", (2, 2, 1), 0, 1, True, "RSF, the reference's decomposition, full 120 steps"),
+    ("test.tpv104", (2, 2, 1), 0, 1, False, "RSF, the reference's decomposition, full 120 steps"),
+    ("test.tpv104", (1, 1, 1), 60, 1, True, "device operators + lumped mass of the bundles (k_march_mass)"),
     ("test.tpv104", (4, 1, 2), 60, 2, False, "the benchmark's 8-GPU decomposition"),
     ("test.tpv36", (2, 2, 2), 60, 1, False, "dipping fault: bundles only away from it, wedges and type-13 bricks on the tile kernels"),
     ("test.tpv10", (1, 1, 1), 40, 1, False, "warped mesh below the fault: box region marches, the rest does not"),
