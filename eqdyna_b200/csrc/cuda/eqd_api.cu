@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -187,17 +188,30 @@ struct eqd_handle {
   // marching class (CLS_MARCH, eqd_march.h): bundles of box elements; cls[CLS_MARCH] holds its SoA rows
   // (shp = [3][S] a_x a_y a_z, ss = [3][S] the diagonal, no phi), refId, partial buffer and node ids
   DevBuf<MarchBundle> mRec;
-  DevBuf<int> mCtaFirst, mCode, mSlotBundle;
+  DevBuf<int> mCtaFirstA, mCtaFirstB, mCode, mSlotBundle;   // work lists: A = bundles that may touch a rank face, B = the rest
   int mGrid = 0, mBundles = 0;
   long mFused = 0;
   int optMarch = 0;         // option "march" (before eqd_set_mesh)
   bool sweepFused = false;  // the last element sweep updated the fused nodes itself
+  raw_vector<unsigned char> mOwner;   // [S] 1: the slot is its element's own copy (0: padding / ghost copy of a neighbouring strip's element)
   DevBuf<int> dNodeList;    // free 3-dof nodes no bundle updates, ascending (list variant of the node update)
   int nNodeList = 0;
   DevBuf<int> dInfo, dPmlNode, dSpecial;
   DevBuf<uint8_t> dSlotCnt;
   DevBuf<uint32_t> dSlotTab;
-  DevBuf<double> dVel, dDisp, dMass, dV1p, dDampp, dForce, dAccel0;
+  // velArr / dispArr.  With ghost sharing between marching strips (option march = 2) a node is read, in the sweep
+  // that updates it, by strips other than the one updating it: v and d are then double-buffered -- every kernel that
+  // advances nodes reads buffer `cur` and writes the other one, and the two swap after the node-update phase.
+  DevBuf<double> dVelB[2], dDispB[2];
+  int cur = 0;
+  bool pingpong = false;
+  DevBuf<double>& velCur() { return dVelB[cur]; }
+  DevBuf<double>& dispCur() { return dDispB[cur]; }
+  const DevBuf<double>& velCur() const { return dVelB[cur]; }
+  const DevBuf<double>& dispCur() const { return dDispB[cur]; }
+  const DevBuf<double>& velNext() const { return dVelB[pingpong ? cur ^ 1 : cur]; }
+  const DevBuf<double>& dispNext() const { return dDispB[pingpong ? cur ^ 1 : cur]; }
+  DevBuf<double> dMass, dV1p, dDampp, dForce, dAccel0;
   int nSpecial = 0;
   DevBuf<StepState> dState;
   // fault
@@ -248,7 +262,7 @@ struct eqd_handle {
 
   NodeArgs nodeArgs() const;
   ElemArgs elemArgs(int c) const;
-  MarchArgs marchArgs(bool update) const;
+  MarchArgs marchArgs(bool update, int part) const;
   FaultArgs faultArgs() const;
 };
 
@@ -351,7 +365,8 @@ void need(bool ok, const char* msg) { if (!ok) throw ArgError(msg); }
 NodeArgs eqd_handle::nodeArgs() const {
   NodeArgs A{};
   A.Nn = Nn; A.NnS = NnS; A.Np = Np; A.NpS = NpS;
-  A.info = dInfo.p; A.pmlNode = dPmlNode.p; A.vel = dVel.p; A.disp = dDisp.p; A.mass = dMass.p;
+  A.info = dInfo.p; A.pmlNode = dPmlNode.p; A.vel = velCur().p; A.disp = dispCur().p; A.mass = dMass.p;
+  A.velOut = velNext().p; A.dispOut = dispNext().p;
   A.v1p = dV1p.p; A.dampp = dDampp.p; A.force = dForce.p;
   A.slotCnt = dSlotCnt.p; A.slotTab = dSlotTab.p;
   A.pfR = cls[CLS_REG].pf.p; A.SR = cls[CLS_REG].PFS;
@@ -375,7 +390,7 @@ ElemArgs eqd_handle::elemArgs(int c) const {
   A.lam = C.lam.p; A.mu = C.mu.p; A.det = C.det.p; A.rho = C.rho.p; A.vp = C.vp.p;
   A.stress = C.stress.p; A.qmem = C.qmem.p; A.qcls = C.qcls.p;
   A.porep = C.porep.p; A.pstrain = C.pstrain.p; A.emass = C.emass.p; A.damps = C.damps.p;
-  A.vel = dVel.p; A.disp = dDisp.p; A.NnS = NnS;
+  A.vel = velCur().p; A.disp = dispCur().p; A.NnS = NnS;
   A.dt = p.dt; A.rdampk = p.rdampk; A.rdampm = p.rdampm; A.w = p.w;
   // assembleGlobalKU.f90:16
   A.bodyz = (1.0 - p.C_elastic) * p.grav * (p.roumax - (p.gamar + 1.0) * p.rhow) / p.roumax;
@@ -387,13 +402,16 @@ ElemArgs eqd_handle::elemArgs(int c) const {
   return A;
 }
 
-MarchArgs eqd_handle::marchArgs(bool update) const {
+MarchArgs eqd_handle::marchArgs(bool update, int part) const {   // part 0: both work lists, 1: boundary list, 2: interior list
   const ElemClass& C = cls[CLS_MARCH];
   MarchArgs A{};
-  A.rec = mRec.p; A.ctaFirst = mCtaFirst.p; A.code = mCode.p;
+  A.rec = mRec.p; A.code = mCode.p;
+  A.ctaFirstA = part != 2 ? mCtaFirstA.p : nullptr;
+  A.ctaFirstB = part != 1 ? mCtaFirstB.p : nullptr;
   A.S = (size_t)C.S; A.NnS = (size_t)NnS; A.PFS = (size_t)C.PFS;
   A.a = C.shp.p; A.ss = C.ss.p; A.lam = C.lam.p; A.mu = C.mu.p; A.det = C.det.p; A.stress = C.stress.p;
-  A.vel = dVel.p; A.disp = dDisp.p; A.mass = dMass.p; A.pf = C.pf.p; A.force = dForce.p;
+  A.vel = velCur().p; A.disp = dispCur().p; A.velOut = velNext().p; A.dispOut = dispNext().p;
+  A.mass = dMass.p; A.pf = C.pf.p; A.force = dForce.p;
   A.dt = p.dt; A.rdampk = p.rdampk; A.w = p.w; A.update = update ? 1 : 0; A.st = dState.p;
   return A;
 }
@@ -404,7 +422,7 @@ FaultArgs eqd_handle::faultArgs() const {
   A.nodeS = dNodeS.p; A.nodeM = dNodeM.p; A.ift = dIft.p;
   A.un = dUn.p; A.us = dUs.p; A.ud = dUd.p; A.arn = dArn.p; A.massS = dMassS.p; A.massM = dMassM.p;
   A.xs = dXs.p; A.fric = dFric.p; A.fnft = dFnft.p;
-  A.vel = dVel.p; A.disp = dDisp.p; A.force = dForce.p;
+  A.vel = velCur().p; A.disp = dispCur().p; A.force = dForce.p;
   A.pairStation = dPairStation.p; A.onHist = dOnHist.p; A.nstep = p.nstep;
   A.hypoLog = dHypo.p; A.tphist = dTpHist.p;
   A.st = dState.p;
@@ -742,21 +760,22 @@ void step_pre(eqd_handle* h, int ov, bool multi, bool last) {
     launch_advance(h->dState.p, P.dt, s); h->launches++;
     Timer t2(h, EQD_T_NODE);
     if (ov && h->nSpecial) { launch_node_update_special(A, h->dSpecial.p, h->nSpecial, s); h->launches++; }
+    if (h->pingpong) h->cur ^= 1;   // every node's v(nt), d(nt) now sits in the other buffer: the sweep reads that one
     if (h->nOff > 0) {
-      launch_store_offfault(h->dIdhist.p, 6 * h->nOff, h->dOffHist.p, h->dVel.p, h->dDisp.p, h->NnS, h->dState.p, s);
+      launch_store_offfault(h->dIdhist.p, 6 * h->nOff, h->dOffHist.p, h->velCur().p, h->dispCur().p, h->NnS, h->dState.p, s);
       h->launches++;
     }
     if (P.outputGroundMotion && (h->hostNt + 1) % 10 == 1 && h->dGm.p) {
       // output_gm (driver.f90:30-33): velArr of this step, before the element sweep moves the fused nodes on
-      launch_sample_gm(h->dSurf.p, h->nSurf, h->dVel.p, h->NnS, h->dGm.p + 3 * (size_t)h->nSurf * h->nGm, s); h->launches++;
+      launch_sample_gm(h->dSurf.p, h->nSurf, h->velCur().p, h->NnS, h->dGm.p + 3 * (size_t)h->nSurf * h->nGm, s); h->launches++;
     }
     t2.stop();
   }
   if (h->dAccel0.p) { CK(cudaStreamSynchronize(s)); h->dAccel0.release(); }
   auto sweep = [&](int part) {   // 0: all tiles, 1: rank-face tiles, 2: interior tiles
-    if (marching && part != 1) {
+    if (marching) {
       Timer t(h, EQD_T_MARCH);
-      launch_march(h->marchArgs(!last), h->mGrid, s); h->launches++;
+      launch_march(h->marchArgs(!last, part), h->mGrid, s); h->launches++;
       t.stop();
     }
     for (int k = 0; k < 3; ++k) {
@@ -778,8 +797,7 @@ void step_pre(eqd_handle* h, int ov, bool multi, bool last) {
     if (n) { launch_assemble_special(h->nodeArgs(), list.p, n, s); h->launches++; }
     t.stop();
   };
-  // (the bundles' rank-face nodes leave partials like any tile node: with bundles the face tiles cannot go first)
-  const bool split = ov == 2 && multi && h->anyFace && !marching;
+  const bool split = ov == 2 && multi && h->anyFace;
   if (!split) {
     sweep(0);
     assemble(h->dSpecial, h->nSpecial);
@@ -1007,23 +1025,39 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
         const int perSm = march_ctas_per_sm();
         need(perSm > 0, "option march: the marching kernel does not fit this device");
         MarchPlan MP;
-        plan_march(h->conn.data(), h->etype.data(), h->coor.data(), h->info.data(), members[CLS_REG], Nn, gny, gnz, perSm * sms, MP);
+        int nxg = 0;   // node planes of the grid in x: the (+,+,+) corner of every element is a lattice node (meshgen.f90:702-741)
+        {
+          std::vector<int> mx(host_threads() + 1, 0);
+          const long nynz = (long)gny * gnz;
+          parallel_range((size_t)Ne, [&](size_t b, size_t e) {
+            int m = 0;
+            for (size_t el = b; el < e; ++el) m = std::max(m, (int)(h->conn[8 * el + 6] / nynz) + 1);
+            static std::mutex mu;
+            std::lock_guard<std::mutex> g(mu);
+            mx[0] = std::max(mx[0], m);
+          });
+          nxg = mx[0];
+        }
+        plan_march(h->conn.data(), h->etype.data(), h->coor.data(), h->info.data(), members[CLS_REG], Nn, gny, gnz, nxg, perSm * sms,
+                   h->optMarch >= 2 ? 1 : 0, MP);
         if (MP.n > 0) {
           M.n = MP.n; M.S = MP.S; M.PFS = MP.PFS;
           h->mGrid = MP.grid; h->mBundles = (int)MP.rec.size(); h->mFused = MP.nFused;
-          h->mRec.upload(MP.rec); h->mCtaFirst.upload(MP.ctaFirst); h->mCode.upload(MP.code); h->mSlotBundle.upload(MP.slotBundle);
+          h->mRec.upload(MP.rec); h->mCtaFirstA.upload(MP.ctaFirstA); h->mCtaFirstB.upload(MP.ctaFirstB);
+          h->mCode.upload(MP.code); h->mSlotBundle.upload(MP.slotBundle);
           // host copy of the node slots for the slot table: only the nodes that emit a partial
           M.tnodeH.resize(MP.code.size());
           parallel_range(MP.code.size(), [&](size_t b, size_t e) {
             for (size_t k = b; k < e; ++k) {
               const int c = MP.code[k];
-              M.tnodeH[k] = (c < 0 || (c & MK_FUSED)) ? -1 : (c & MK_IDMASK);
+              M.tnodeH[k] = (c < 0 || (c & (MK_FUSED | MK_GHOST))) ? -1 : (c & MK_IDMASK);
               if (c >= 0 && (c & MK_FUSED)) h->info[c & MK_IDMASK] |= EQD_INFO_FUSED_BIT;   // one bundle per fused node: no race
             }
           });
           M.refId = std::move(MP.refId);
+          h->mOwner = std::move(MP.owner);
           parallel_range((size_t)M.S, [&](size_t sb, size_t se) {
-            for (size_t sl = sb; sl < se; ++sl) if (M.refId[sl] >= 0) h->elemCode[M.refId[sl]] = CLS_MARCH | ((int)sl << 2);
+            for (size_t sl = sb; sl < se; ++sl) if (M.refId[sl] >= 0 && h->mOwner[sl]) h->elemCode[M.refId[sl]] = CLS_MARCH | ((int)sl << 2);
           });
           M.pf.alloc((size_t)3 * M.PFS);
           M.stress.alloc((size_t)6 * M.S);
@@ -1031,6 +1065,7 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
           members[CLS_REG] = std::move(MP.leftover);
         }
       }
+      h->pingpong = h->optMarch >= 2 && M.n > 0;
       lap.lap("march plan");
     }
     const int nf[3] = {3, 6, 12}, nstr[3] = {6, 6, 21};
@@ -1163,7 +1198,8 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
       if (neg[0]) throw ArgError("negative PML damping (comdampv.f90:114-118)");
     }
     h->dDampp.upload(dp);
-    h->dVel.alloc(3 * (size_t)h->NnS); h->dDisp.alloc(3 * (size_t)h->NnS);
+    for (int b = 0; b < (h->pingpong ? 2 : 1); ++b) { h->dVelB[b].alloc(3 * (size_t)h->NnS); h->dDispB[b].alloc(3 * (size_t)h->NnS); }
+    h->cur = 0;
     h->dV1p.alloc(12 * (size_t)h->NpS);
     h->dForce.alloc(3 * (size_t)h->NnS + 12 * (size_t)h->NpS);
     h->dMass.alloc(Nn);
@@ -1350,10 +1386,12 @@ int eqd_set_elem_ops(eqd_handle* h, const double* eleshp, const double* eledet, 
     };
     // marching class: of eleshp only rows 3, 7, 14 (a_x, a_y, a_z), of ss the diagonal, no phi (eqd_box.h)
     ElemClass& M = h->cls[CLS_MARCH];
+    DevBuf<int> dRefM;
+    if (M.n) dRefM.upload(M.refId);
     auto march_rows = [&](DevBuf<double>& dst, int K, const int* rows, int nrows) {
-      if (!M.n) return;
+      if (!M.n) return;   // by slot, not by element: the ghost copies of an element get its rows too
       for (int k = 0; k < nrows; ++k)
-        launch_aos_to_soa(tmp.p, K, Ne, dCode.p, CLS_MARCH, dst.p + (size_t)k * M.S, M.S, rows[k], 1, h->stream);
+        launch_gather_rows(tmp.p, K, dRefM.p, M.S, dst.p + (size_t)k * M.S, rows[k], h->stream);
       CK(cudaStreamSynchronize(h->stream));
     };
     const int shpRows[3] = {BOX_AX, BOX_AY, BOX_AZ}, ssRows[3] = {0, 3, 5}, row0[1] = {0};
@@ -1449,7 +1487,10 @@ int eqd_set_nodal(eqd_handle* h, const double* nodalMassArr, const double* fnms,
       }
     });
     need(!badv[0], "eqd_set_nodal: dofs of one node carry different lumped masses");
-    h->dVel.upload(vel); h->dDisp.upload(disp); h->dV1p.upload(v1p); h->dMass.upload(h->massH);
+    // (both buffers of a double-buffered pair: the nodes no kernel ever writes -- fixed ones -- must read the same in either)
+    for (int b = 0; b < (h->pingpong ? 2 : 1); ++b) { h->dVelB[b].upload(vel); h->dDispB[b].upload(disp); }
+    h->cur = 0;
+    h->dV1p.upload(v1p); h->dMass.upload(h->massH);
     if (anyAcc) h->dAccel0.upload(acc); else h->dAccel0.release();
     lap.lap("all");
     h->nodalSet = true;
@@ -1714,9 +1755,9 @@ int eqd_fetch(eqd_handle* h, int32_t which, void* dst, int64_t dst_bytes) {
     switch (which) {
       case EQD_F_DISP: case EQD_F_VEL: {
         want(3 * (size_t)Nn);
-        const double* dev = (which == EQD_F_DISP ? h->dDisp : h->dVel).p;
+        const double* dev = (which == EQD_F_DISP ? h->dispCur() : h->velCur()).p;
         if ((size_t)Nn * 3 * sizeof(double) < (64u << 20)) {
-          std::vector<double> v = (which == EQD_F_DISP ? h->dDisp : h->dVel).download();
+          std::vector<double> v = (which == EQD_F_DISP ? h->dispCur() : h->velCur()).download();
           parallel_range((size_t)Nn, [&](size_t b, size_t e) {
             for (size_t n = b; n < e; ++n) for (int j = 0; j < 3; ++j) out[j + 3 * n] = v[j * NS + n];
           });
@@ -1744,7 +1785,7 @@ int eqd_fetch(eqd_handle* h, int32_t which, void* dst, int64_t dst_bytes) {
       case EQD_F_V1: case EQD_F_FORCE: case EQD_F_MASS: {
         want(h->Neq);
         std::vector<double> a3, a12;
-        if (which == EQD_F_V1) { a3 = h->dVel.download(); a12 = h->dV1p.download(); }
+        if (which == EQD_F_V1) { a3 = h->velCur().download(); a12 = h->dV1p.download(); }
         else if (which == EQD_F_FORCE) {
           finalize(h);
           DevBuf<double> acc; acc.alloc(3 * NS + 12 * PSn);
@@ -1777,7 +1818,7 @@ int eqd_fetch(eqd_handle* h, int32_t which, void* dst, int64_t dst_bytes) {
           parallel_range((size_t)C.S, [&](size_t sb, size_t se) {
             for (size_t s = sb; s < se; ++s) {
               const int e = C.refId[s];
-              if (e < 0) continue;
+              if (e < 0 || !h->mOwner[s]) continue;
               double* o = out + (size_t)K * e;
               if (which == EQD_F_ELEDET) o[0] = a[s];
               else if (which == EQD_F_ELESHP)
@@ -1839,7 +1880,7 @@ int eqd_fetch(eqd_handle* h, int32_t which, void* dst, int64_t dst_bytes) {
           std::vector<double> sg = C.stress.download(), qm;
           if (C.qmem.p) qm = C.qmem.download();
           for (int s = 0; s < C.S; ++s) {
-            if (C.refId[s] < 0) continue;
+            if (C.refId[s] < 0 || (c == CLS_MARCH && !h->mOwner[s])) continue;
             const int base = h->stressIdx[C.refId[s]];
             for (int k = 0; k < C.nstress; ++k) out[base + k] = sg[(size_t)k * C.S + s];
             if (!qm.empty()) for (int k = 0; k < 6; ++k) out[base + 6 + k] = qm[(size_t)k * C.S + s];
@@ -1927,7 +1968,7 @@ int eqd_set_option(eqd_handle* h, const char* key, int32_t value) {
   if (!strcmp(key, "box_compact")) { h->optBoxCompact = value != 0; return EQD_OK; }
   if (!strcmp(key, "march")) {
     if (h->meshSet) { h->err = "eqd_set_option: march must be set before eqd_set_mesh"; return EQD_ERR_ARG; }
-    h->optMarch = value != 0;
+    h->optMarch = value < 0 ? 0 : value > 2 ? 2 : value;
     return EQD_OK;
   }
   if (!strcmp(key, "box")) {

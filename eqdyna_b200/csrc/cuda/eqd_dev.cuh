@@ -60,8 +60,10 @@ struct NodeArgs {
   int Nn, NnS, Np, NpS;
   const int* info;       // [Nn] kind | special<<2 | pmlSlot<<3
   const int* pmlNode;    // [Np] PML slot -> node
-  double* vel;           // [3][NnS]
-  double* disp;          // [3][NnS]
+  const double* vel;     // [3][NnS] v(nt-1), d(nt-1) as read ...
+  const double* disp;
+  double* velOut;        // ... and where v(nt), d(nt) go: the same arrays, or the other buffer of the pair (eqd_api.cu)
+  double* dispOut;
   const double* mass;    // [Nn]
   double* v1p;           // [12][NpS]
   const double* dampp;   // [3][NpS]

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(NT, MINB) k_node_update3(NodeArgs A) {
   }
   if (mine) {
 #pragma unroll
-    for (int j = 0; j < 3; ++j) { A.vel[j * NS + n] = v[j]; A.disp[j * NS + n] = d[j]; }  // :103
+    for (int j = 0; j < 3; ++j) { A.velOut[j * NS + n] = v[j]; A.dispOut[j * NS + n] = d[j]; }  // :103
     if (bad) {
       if (atomicExch(&A.st->nanFlag, 1) == 0) A.st->nanNode = n + 1;
     }
@@ -215,8 +215,8 @@ __global__ void __launch_bounds__(128, MINB) k_node_update12(NodeArgs A) {
   bool bad = false;
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    A.vel[j * NS + n] = vel[j];
-    A.disp[j * NS + n] = dis[j] + vel[j] * dt;
+    A.velOut[j * NS + n] = vel[j];
+    A.dispOut[j * NS + n] = dis[j] + vel[j] * dt;
     bad |= (vel[j] != vel[j]);
   }
   if (bad) {
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(128) k_node_update_special(NodeArgs A, const i
       v = v + a[j] * dt;                      // driver.f90:102
       d = d + v * dt;                         // :104
       bad |= (v != v);
-      A.vel[j * NS + n] = v; A.disp[j * NS + n] = d;
+      A.velOut[j * NS + n] = v; A.dispOut[j * NS + n] = d;
     }
   } else if (kind == KIND_PML12) {
     const int slot = EQD_INFO_SLOT(info);
@@ -272,8 +272,8 @@ __global__ void __launch_bounds__(128) k_node_update_special(NodeArgs A, const i
     vel[2] = v[6] + v[7] + v[8] + v[11];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      A.vel[j * NS + n] = vel[j];
-      A.disp[j * NS + n] = A.disp[j * NS + n] + vel[j] * dt;
+      A.velOut[j * NS + n] = vel[j];
+      A.dispOut[j * NS + n] = A.disp[j * NS + n] + vel[j] * dt;
       bad |= (vel[j] != vel[j]);
     }
   }
@@ -1556,6 +1556,14 @@ __global__ void k_aos_to_soa(const double* __restrict__ src, int K, int n, const
   for (int k = 0; k < nk; ++k) dst[(size_t)k * S + d] = src[(size_t)(k0 + k) + (size_t)K * e];
 }
 
+// one row of an AoS array by class slot: dst[s] = src(row, refId[s]) (the marching class: ghost copies included)
+__global__ void k_gather_rows(const double* __restrict__ src, int K, const int* __restrict__ refId, int S, double* __restrict__ dst, int row) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const int e = refId[s];
+  if (e >= 0) dst[s] = src[(size_t)row + (size_t)K * e];
+}
+
 // ----------------------------------------------------------------------------
 // launch wrappers
 static inline int nblk(long n, int b) { return (int)((n + b - 1) / b); }
@@ -1711,6 +1719,9 @@ void launch_thermop(const FaultArgs& A, cudaStream_t s) {
 void launch_fault(const FaultArgs& A, cudaStream_t s) {
   // 178 registers per thread: 64-thread CTAs pack five to an SM where 128-thread ones pack two
   if (A.nPairs > 0) k_fault<<<nblk(A.nPairs, 64), 64, 0, s>>>(A);
+}
+void launch_gather_rows(const double* src, int K, const int* refId, int S, double* dst, int row, cudaStream_t s) {
+  if (S > 0) k_gather_rows<<<nblk(S, 256), 256, 0, s>>>(src, K, refId, S, dst, row);
 }
 void launch_aos_to_soa(const double* src, int K, int n, const int* dstIdx, int cls, double* dst, int S, int k0, int nk,
                        cudaStream_t s) {

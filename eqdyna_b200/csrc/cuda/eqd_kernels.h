@@ -23,6 +23,7 @@ void launch_pack(const double* src, const uint32_t* idx, int n, double* buf, cud
 void launch_unpack_add(double* dst, const uint32_t* idx, int n, const double* buf, cudaStream_t s);
 void launch_thermop(const FaultArgs& A, cudaStream_t s);
 void launch_fault(const FaultArgs& A, cudaStream_t s);
+void launch_gather_rows(const double* src, int K, const int* refId, int S, double* dst, int row, cudaStream_t s);
 void launch_aos_to_soa(const double* src, int K, int n, const int* dstIdx, int cls, double* dst, int S, int k0, int nk,
                        cudaStream_t s);
 // eqd_ops.cu

@@ -34,7 +34,11 @@ __global__ void __launch_bounds__(MK_NT, 3) k_march(MarchArgs A) {
   unsigned par = 0;   // bit s = phase parity of operator stage s
   if (tid == 0) { mk_bar_init(&sm.bar[0]); mk_bar_init(&sm.bar[1]); }
   __syncthreads();
-  const int b0 = A.ctaFirst[blockIdx.x], b1 = A.ctaFirst[blockIdx.x + 1];
+  // this CTA's share of the boundary list, then of the interior list (either may be switched off by the launch)
+  for (int part = 0; part < 2; ++part) {
+  const int* first = part == 0 ? A.ctaFirstA : A.ctaFirstB;
+  if (!first) continue;
+  const int b0 = first[blockIdx.x], b1 = first[blockIdx.x + 1];
   for (int b = b0; b < b1; ++b) {
     const MarchBundle B = A.rec[b];
 #define MK_RUN(body) do { body; __syncthreads(); } while (0)
@@ -46,6 +50,7 @@ __global__ void __launch_bounds__(MK_NT, 3) k_march(MarchArgs A) {
 #undef MK_RUNNS
 #undef MK_WAITN
 #undef MK_WAITO
+  }
   }
 }
 
@@ -62,7 +67,7 @@ __global__ void __launch_bounds__(128) k_march_mass(const MarchBundle* __restric
   const MarchBundle B = rec[b];
   const int k = slot - B.n0, pl = k / MK_PN, i = k - pl * MK_PN, iz = i / MK_NY, iy = i - iz * MK_NY;
   const int c = code[slot];
-  if (c < 0) { pm[slot] = 0.0; return; }
+  if (c < 0 || (c & MK_GHOST)) { pm[slot] = 0.0; return; }
   const int bz = B.shape & 0xff, by = (B.shape >> 8) & 0xff;
   // corner of the element at (pl - dx, iz - dz, iy - dy) that is this node: signs (dx, dy, dz)
   const int corner[2][2][2] = {{{0, 4}, {3, 7}}, {{1, 5}, {2, 6}}};   // [sx][sy][sz]
@@ -102,7 +107,11 @@ void launch_march_mass(const MarchBundle* rec, int nBundles, const int* slotBund
 // planner
 namespace {
 
-struct Strip { int x0, len, z0, bz, y0, by; };   // cells [x0, x0+len) x [z0, z0+bz) x [y0, y0+by) of the lattice box
+// cells [x0, x0+len) x [z0, z0+bz) x [y0, y0+by) of the lattice box.  gz / gy: the first row / column of the
+// rectangle is a GHOST copy of the last row / column of the tile before (which owns those elements); hz / hy: the
+// tile after took such a copy of this strip's last row / column, so this strip leaves the nodes of its last node
+// row / column to it.  tz, ty: tile of the base (ghost-free) tiling.
+struct Strip { int x0, len, z0, bz, y0, by, tz, ty; unsigned char gz, gy, hz, hy; };
 
 // nearly equal parts of at most `cap` cells between consecutive seams of one lattice axis
 void cut_axis(int n, const std::vector<char>& seam, int cap, std::vector<std::pair<int, int>>& out) {
@@ -122,7 +131,7 @@ void cut_axis(int n, const std::vector<char>& seam, int cap, std::vector<std::pa
 }  // namespace
 
 void plan_march(const int* conn, const int* etype, const double* coor, const int* info, const std::vector<int>& elems, int Nn, int ny,
-                int nz, int grid, MarchPlan& P) {
+                int nz, int nxg, int grid, int share, MarchPlan& P) {
   P = MarchPlan();
   const int n = (int)elems.size();
   const long nynz = (long)ny * nz;
@@ -214,8 +223,9 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
   few(seamZ); few(seamY);
   // ---- column tiles and their strips: runs in x of complete cross-sections whose cells share all their nodes
   std::vector<std::pair<int, int>> zt, yt;
-  cut_axis(ez, seamZ, MK_BZ, zt);
-  cut_axis(ey, seamY, MK_BY, yt);
+  // base tiles are one cell short of the kernel's cross-section: room for the ghost row / column
+  cut_axis(ez, seamZ, share ? MK_BZ - 1 : MK_BZ, zt);
+  cut_axis(ey, seamY, share ? MK_BY - 1 : MK_BY, yt);
   std::vector<Strip> strips;
   {
     const int nT = (int)(zt.size() * yt.size());
@@ -237,65 +247,142 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
               if (x > 0 && (mis[((size_t)(x - 1) * ez + z) * ey + y] & 4)) joined = false;
             }
           if (run0 >= 0 && (!full || !joined)) {
-            if (x - run0 >= MK_MINLX) per[t].push_back({run0, x - run0, Z.first, Z.second, Y.first, Y.second});
+            if (x - run0 >= MK_MINLX)
+              per[t].push_back({run0, x - run0, Z.first, Z.second, Y.first, Y.second, (int)(t / yt.size()), (int)(t % yt.size()), 0, 0, 0, 0});
             run0 = -1;
           }
           if (full && run0 < 0) run0 = x;
         }
       }
     }, 1);
+    // ---- ghost sharing (option): a strip whose y- (then z-) neighbour tile has a strip over exactly the same x range
+    // takes a private copy of that strip's last element column (row): the node column (row) between the two tiles is
+    // then interior to this strip -- complete inside one CTA, updated by it -- instead of two partial sums that the node
+    // update has to gather.  Both copies of a shared element see the same nodal values and run the same instruction
+    // sequence, so their stresses stay bit-identical; only the owner's copy is ever fetched.
+    if (share) {
+      const int nty = (int)yt.size(), ntz = (int)zt.size();
+      // An interface between two tile columns (rows) is shared as a whole or not at all: every pair of tiles across it
+      // must hold strips over the same x ranges whose facing cells are joined.  That makes the choices around every tile
+      // corner agree (the corner element is then reported to the corner node by exactly one of the four tiles).
+      auto same_lists = [](const std::vector<Strip>& a, const std::vector<Strip>& b) {
+        if (a.size() != b.size() || a.empty()) return false;
+        for (size_t k = 0; k < a.size(); ++k) if (a[k].x0 != b[k].x0 || a[k].len != b[k].len) return false;
+        return true;
+      };
+      std::vector<char> yShared(nty + 1, 0), zShared(ntz + 1, 0);
+      for (int ty = 1; ty < nty; ++ty) {
+        bool ok = true;
+        for (int tz = 0; ok && tz < ntz; ++tz) {
+          const auto& a = per[tz * nty + ty - 1];
+          const auto& b = per[tz * nty + ty];
+          if (a.empty() && b.empty()) continue;
+          ok = same_lists(a, b);
+          for (size_t k = 0; ok && k < b.size(); ++k)
+            for (int x = b[k].x0; ok && x < b[k].x0 + b[k].len; ++x)
+              for (int z = b[k].z0; ok && z < b[k].z0 + b[k].bz; ++z) ok = !(mis[((size_t)x * ez + z) * ey + b[k].y0 - 1] & 1);
+        }
+        yShared[ty] = ok;
+      }
+      for (int tz = 1; tz < ntz; ++tz) {
+        bool ok = true;
+        for (int ty = 0; ok && ty < nty; ++ty) {
+          const auto& a = per[(tz - 1) * nty + ty];
+          const auto& b = per[tz * nty + ty];
+          if (a.empty() && b.empty()) continue;
+          ok = same_lists(a, b);
+          for (size_t k = 0; ok && k < b.size(); ++k)
+            for (int x = b[k].x0; ok && x < b[k].x0 + b[k].len; ++x)
+              for (int y = b[k].y0; ok && y < b[k].y0 + b[k].by; ++y) ok = !(mis[((size_t)x * ez + b[k].z0 - 1) * ey + y] & 2);
+        }
+        zShared[tz] = ok;
+      }
+      for (int t = 0; t < nT; ++t)
+        for (Strip& q : per[t]) { q.gy = yShared[q.ty]; q.gz = zShared[q.tz]; q.hy = yShared[q.ty + 1]; q.hz = zShared[q.tz + 1]; }
+      for (int t = 0; t < nT; ++t)
+        for (Strip& q : per[t]) { q.z0 -= q.gz; q.bz += q.gz; q.y0 -= q.gy; q.by += q.gy; }
+    }
     for (auto& v : per) strips.insert(strips.end(), v.begin(), v.end());
   }
   long total = 0;
   for (const Strip& s : strips) total += s.len;
   if (total == 0) { reject_all(); return; }
-  // ---- balanced static schedule: CTA b marches the element planes [b*total/grid, (b+1)*total/grid) of the
-  // strip sequence; a cut closer than MK_MINLX to a strip end moves to that end
-  P.grid = grid;
-  P.ctaFirst.assign(grid + 1, 0);
+  // ---- two work lists.  A: what may touch a rank face -- strips along the y / z boundary of the node grid, and
+  // short caps (MK_MINLX planes) where a strip reaches the grid's first or last node plane in x (the domain's outer
+  // boundary is PML, so in practice only rank faces and the free surface qualify).  B: the rest.  With rank
+  // neighbours the step sweeps A first and exchanges the face forces while B is swept (eqd_api.cu).
+  struct Piece { int strip, a, len; };
+  std::vector<Piece> listA, listB;
   {
-    std::vector<long> cutpos;   // snapped global plane positions where CTA b = 1 .. grid-1 starts (non-decreasing)
+    const int gx1 = nxg > 1 ? nxg - 2 : -1;   // last cell of the node grid in x
+    for (size_t k = 0; k < strips.size(); ++k) {
+      const Strip& s = strips[k];
+      const int z0 = lo[1] + s.z0, y0 = lo[2] + s.y0, x0 = lo[0] + s.x0;
+      const bool edge = z0 == 0 || y0 == 0 || z0 + s.bz == nz - 1 || y0 + s.by == ny - 1;
+      if (edge) { listA.push_back({(int)k, 0, s.len}); continue; }
+      int a = 0, b = s.len;
+      const bool capLo = x0 == 0 && s.len >= 3 * MK_MINLX, capHi = x0 + s.len - 1 == gx1 && s.len >= 3 * MK_MINLX;
+      if (x0 == 0 && !capLo) { listA.push_back({(int)k, 0, s.len}); continue; }          // too short to cap: all of it
+      if (x0 + s.len - 1 == gx1 && !capHi) { listA.push_back({(int)k, 0, s.len}); continue; }
+      if (capLo) { listA.push_back({(int)k, 0, MK_MINLX}); a = MK_MINLX; }
+      if (capHi) { listA.push_back({(int)k, s.len - MK_MINLX, MK_MINLX}); b = s.len - MK_MINLX; }
+      listB.push_back({(int)k, a, b - a});
+    }
+  }
+  // ---- balanced static schedule of one list: CTA c marches the element planes [c*total/grid, (c+1)*total/grid) of the
+  // piece sequence; a cut closer than MK_MINLX to a piece end moves to that end
+  P.grid = grid;
+  auto schedule = [&](const std::vector<Piece>& pieces, std::vector<int>& ctaFirst) {
+    const int first = (int)P.rec.size();
+    ctaFirst.assign(grid + 1, first);
+    long tot = 0;
+    for (const Piece& q : pieces) tot += q.len;
+    if (tot == 0) return;
+    std::vector<long> cutpos;   // snapped global plane positions where CTA c = 1 .. grid-1 starts (non-decreasing)
     long base = 0, prev = 0;
     size_t si = 0;
-    for (int b = 1; b < grid; ++b) {
-      const long g = total * b / grid;
-      while (si + 1 < strips.size() && g >= base + strips[si].len) { base += strips[si].len; ++si; }
-      long off = std::min<long>(g - base, strips[si].len);
+    for (int c = 1; c < grid; ++c) {
+      const long g = tot * c / grid;
+      while (si + 1 < pieces.size() && g >= base + pieces[si].len) { base += pieces[si].len; ++si; }
+      long off = std::min<long>(g - base, pieces[si].len);
       if (off < MK_MINLX) off = 0;
-      else if (strips[si].len - off < MK_MINLX) off = strips[si].len;
+      else if (pieces[si].len - off < MK_MINLX) off = pieces[si].len;
       long sgl = std::max(base + off, prev);
-      if (sgl > prev && sgl - prev < MK_MINLX && prev > base) sgl = prev;   // two cuts of one strip too close: the CTA stays empty
+      if (sgl > prev && sgl - prev < MK_MINLX && prev > base) sgl = prev;   // two cuts of one piece too close: the CTA stays empty
       cutpos.push_back(sgl);
       prev = sgl;
     }
     std::vector<int> ctaOf;
     size_t ci = 0;
     base = 0;
-    for (size_t k = 0; k < strips.size(); ++k) {
-      const Strip& s = strips[k];
+    for (const Piece& q : pieces) {
+      const Strip& st = strips[q.strip];
       int a = 0;
-      while (a < s.len) {
+      while (a < q.len) {
         while (ci < cutpos.size() && cutpos[ci] <= base + a) ++ci;
-        int end = s.len;
-        if (ci < cutpos.size() && cutpos[ci] < base + s.len) end = (int)(cutpos[ci] - base);
+        int end = q.len;
+        if (ci < cutpos.size() && cutpos[ci] < base + q.len) end = (int)(cutpos[ci] - base);
         MarchBundle B{};
         B.Lx = end - a;
-        B.shape = s.bz | (s.by << 8);
-        B.e0 = s.x0 + a;          // provisional: lattice x of the first plane (replaced by the slot below)
-        B.n0 = (int)k;            // provisional: strip
+        B.shape = st.bz | (st.by << 8);
+        B.e0 = st.x0 + q.a + a;   // provisional: lattice x of the first plane (replaced by the slot below)
+        B.n0 = q.strip;           // provisional: strip
         P.rec.push_back(B);
         ctaOf.push_back((int)ci);
         a = end;
       }
-      base += s.len;
+      base += q.len;
     }
     size_t bi = 0;
     for (int c = 0; c <= grid; ++c) {
       while (bi < ctaOf.size() && ctaOf[bi] < c) ++bi;
-      P.ctaFirst[c] = (int)bi;
+      ctaFirst[c] = first + (int)bi;
     }
-    P.ctaFirst[grid] = (int)P.rec.size();
-  }
+    ctaFirst[grid] = (int)P.rec.size();
+  };
+  schedule(listA, P.ctaFirstA);
+  P.nBundlesA = (int)P.rec.size();
+  schedule(listB, P.ctaFirstB);
   // ---- slots
   const int nB = (int)P.rec.size();
   std::vector<int> stripOf(nB), xOf(nB);
@@ -309,8 +396,8 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
   }
   P.S = (int)std::max(eslot, 32L);
   P.PFS = (int)std::max(nslot, 4L);
-  P.refId.resize(P.S); P.code.resize(P.PFS); P.slotBundle.assign((size_t)(P.PFS + MK_PN - 1) / MK_PN, -1);
-  parallel_range((size_t)P.S, [&](size_t b, size_t e) { std::fill(P.refId.begin() + b, P.refId.begin() + e, -1); });
+  P.refId.resize(P.S); P.owner.resize(P.S); P.code.resize(P.PFS); P.slotBundle.assign((size_t)(P.PFS + MK_PN - 1) / MK_PN, -1);
+  parallel_range((size_t)P.S, [&](size_t b, size_t e) { std::fill(P.refId.begin() + b, P.refId.begin() + e, -1); std::fill(P.owner.begin() + b, P.owner.begin() + e, (unsigned char)0); });
   parallel_range((size_t)P.PFS, [&](size_t b, size_t e) { std::fill(P.code.begin() + b, P.code.begin() + e, -1); });
   std::vector<char> taken(n, 0);
   std::vector<long> fusedT(host_threads() + 1, 0), elemsT(host_threads() + 1, 0);
@@ -330,9 +417,11 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
             for (int z = 0; z < bz; ++z)
               for (int y = 0; y < by; ++y) {
                 const int j = at(x0 + p, s.z0 + z, s.y0 + y);
-                P.refId[(size_t)B.e0 + (size_t)p * MK_ES + z * MK_NY + y] = elems[j];
-                taken[j] = 1;
-                elemsT[t]++;
+                const size_t slot = (size_t)B.e0 + (size_t)p * MK_ES + z * MK_NY + y;
+                P.refId[slot] = elems[j];
+                const bool ghost = (z == 0 && s.gz) || (y == 0 && s.gy);     // the tile before owns this element
+                P.owner[slot] = ghost ? 0 : 1;
+                if (!ghost) { taken[j] = 1; elemsT[t]++; }
               }
           for (int pl = 0; pl <= B.Lx; ++pl) {
             P.slotBundle[(size_t)B.n0 / MK_PN + pl] = b;
@@ -349,10 +438,12 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
                       id = nd;
                     }
                 if (id < 0 || id >= Nn || id > MK_IDMASK) { bad[0] = 1; continue; }
+                // a node of the first / last row or column is this strip's to report unless a neighbour tile shares it
+                const bool outZ = iz == 0 ? !s.gz : (iz == bz ? !s.hz : true), outY = iy == 0 ? !s.gy : (iy == by ? !s.hy : true);
                 const bool interior = pl > 0 && pl < B.Lx && iz > 0 && iz < bz && iy > 0 && iy < by;
                 const bool fused = interior && EQD_INFO_KIND(info[id]) == KIND_FREE3;
                 if (fused) fusedT[t]++;
-                P.code[(size_t)B.n0 + (size_t)pl * MK_PN + iz * MK_NY + iy] = id | (fused ? MK_FUSED : 0);
+                P.code[(size_t)B.n0 + (size_t)pl * MK_PN + iz * MK_NY + iy] = id | (fused ? MK_FUSED : 0) | (outZ && outY ? 0 : MK_GHOST);
               }
           }
         }
@@ -360,14 +451,56 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
     for (auto& x : th) x.join();
   }
   if (bad[0]) throw std::runtime_error("march planner: the elements of a bundle disagree on a lattice node (internal)");
+  if (share) {
+    // every (node, adjacent element) pair of the elements in bundles must be reported exactly once: count, per node,
+    // the corners the owned elements put on it, and the computed elements behind every slot that reports it
+    std::vector<int> want(Nn, 0), got(Nn, 0);
+    for (int b = 0; b < nB; ++b) {
+      const MarchBundle& B = P.rec[b];
+      const int bz = mk_bz(B), by = mk_by(B);
+      for (int p = 0; p < B.Lx; ++p)
+        for (int z = 0; z < bz; ++z)
+          for (int y = 0; y < by; ++y) {
+            const size_t slot = (size_t)B.e0 + (size_t)p * MK_ES + z * MK_NY + y;
+            if (P.owner[slot]) for (int k = 0; k < 8; ++k) want[conn[8 * (size_t)P.refId[slot] + k]]++;
+          }
+      for (int pl = 0; pl <= B.Lx; ++pl)
+        for (int iz = 0; iz <= bz; ++iz)
+          for (int iy = 0; iy <= by; ++iy) {
+            const int c = P.code[(size_t)B.n0 + (size_t)pl * MK_PN + iz * MK_NY + iy];
+            if (c < 0 || (c & MK_GHOST)) continue;
+            const int nx_ = (pl > 0) + (pl < B.Lx), nz_ = (iz > 0) + (iz < bz), ny_ = (iy > 0) + (iy < by);
+            got[c & MK_IDMASK] += nx_ * nz_ * ny_;
+          }
+    }
+    bool okc = true;
+    for (int nd = 0; nd < Nn && okc; ++nd) okc = want[nd] == got[nd];
+    if (!okc && std::getenv("EQD_MARCH_DEBUG")) {
+      int shown = 0;
+      for (int nd = 0; nd < Nn && shown < 12; ++nd)
+        if (want[nd] != got[nd]) {
+          std::fprintf(stderr, "  node %d (ix %ld iz %ld iy %ld; lattice x %ld z %ld y %ld): want %d got %d\n", nd, nd / nynz, (nd % nynz) / ny, (long)nd % ny,
+                       nd / nynz - lo[0], (nd % nynz) / ny - lo[1], (long)nd % ny - lo[2], want[nd], got[nd]);
+          ++shown;
+        }
+      for (size_t k = 0; k < strips.size() && k < 12; ++k)
+        std::fprintf(stderr, "  strip %zu: x %d+%d z %d+%d y %d+%d tile (%d,%d) g %d%d h %d%d\n", k, strips[k].x0, strips[k].len, strips[k].z0, strips[k].bz,
+                     strips[k].y0, strips[k].by, strips[k].tz, strips[k].ty, strips[k].gz, strips[k].gy, strips[k].hz, strips[k].hy);
+    }
+    if (!okc) {   // cannot happen on lattices the sharing rules were made for; stay correct on the others
+      if (std::getenv("EQD_VERBOSE")) std::fprintf(stderr, "[eqd]   plan_march: ghost sharing inconsistent on this mesh, planning without it\n");
+      plan_march(conn, etype, coor, info, elems, Nn, ny, nz, nxg, grid, 0, P);
+      return;
+    }
+  }
   for (long v : fusedT) P.nFused += v;
   for (long v : elemsT) P.n += (int)v;
   P.leftover.reserve(n - P.n);
   for (int j = 0; j < n; ++j) if (!taken[j]) P.leftover.push_back(elems[j]);
   if (std::getenv("EQD_VERBOSE"))
-    std::fprintf(stderr, "[eqd]   plan_march: %d of %d regular elements in %d bundles (%zu strips, lattice %dx%dx%d, %zu x %zu column tiles), "
-                         "%ld element planes over %d CTAs, %ld fused nodes of %ld node slots\n",
-                 P.n, n, nB, strips.size(), ex, ez, ey, zt.size(), yt.size(), total, grid, P.nFused, nslot);
+    std::fprintf(stderr, "[eqd]   plan_march: %d of %d regular elements in %d bundles (%d of them boundary work; %zu strips, lattice %dx%dx%d, "
+                         "%zu x %zu column tiles), %ld element planes over %d CTAs, %ld fused nodes of %ld node slots\n",
+                 P.n, n, nB, P.nBundlesA, strips.size(), ex, ez, ey, zt.size(), yt.size(), total, grid, P.nFused, nslot);
 }
 
 }  // namespace eqd
@@ -398,9 +531,11 @@ extern "C" int eqd_march_emulate(int32_t Nn, int32_t Ne, const double* meshCoor,
     int ny = 0, nz = 0;
     if (!infer_grid(conn.data(), elemTypeArr, Ne, Nn, ny, nz)) return __LINE__;
     MarchPlan P;
-    plan_march(conn.data(), elemTypeArr, meshCoor, info.data(), elems, Nn, ny, nz, grid, P);
+    int nxg = 0;
+    for (int e = 0; e < Ne; ++e) nxg = std::max(nxg, (int)(conn[8 * (size_t)e + 6] / ((long)ny * nz)) + 1);
+    plan_march(conn.data(), elemTypeArr, meshCoor, info.data(), elems, Nn, ny, nz, nxg, grid & 0xffff, (grid >> 16) & 1, P);
     stats[0] = P.n; stats[1] = (int64_t)P.rec.size(); stats[2] = P.PFS; stats[3] = P.nFused; stats[4] = (int64_t)P.leftover.size();
-    stats[5] = P.grid; stats[6] = P.S; stats[7] = 0;
+    stats[5] = P.grid; stats[6] = P.S; stats[7] = P.nBundlesA;
     for (int e = 0; e < Ne; ++e) inBundle[e] = 0;
     for (int nd = 0; nd < Nn; ++nd) fusedFlag[nd] = 0;
     if (P.n == 0) return 0;
@@ -410,7 +545,7 @@ extern "C" int eqd_march_emulate(int32_t Nn, int32_t Ne, const double* meshCoor,
     for (size_t s = 0; s < S; ++s) {
       const int e = P.refId[s];
       if (e < 0) continue;
-      inBundle[e] = 1;
+      if (P.owner[s]) inBundle[e] += 1;
       a[s] = eleshp[BOX_AX + 24 * (size_t)e]; a[S + s] = eleshp[BOX_AY + 24 * (size_t)e]; a[2 * S + s] = eleshp[BOX_AZ + 24 * (size_t)e];
       s3[s] = ss[0 + 6 * (size_t)e]; s3[S + s] = ss[3 + 6 * (size_t)e]; s3[2 * S + s] = ss[5 + 6 * (size_t)e];
       lam[s] = mat[(size_t)e + 3 * (size_t)Ne]; mu[s] = mat[(size_t)e + 4 * (size_t)Ne]; det[s] = eledet[e];
@@ -419,21 +554,22 @@ extern "C" int eqd_march_emulate(int32_t Nn, int32_t Ne, const double* meshCoor,
     std::vector<double> v(3 * NnS, 0.0), d(3 * NnS, 0.0), pf(3 * PFS, 0.0), force(3 * NnS, 0.0);
     for (int nd = 0; nd < Nn; ++nd)
       for (int c = 0; c < 3; ++c) { v[c * NnS + nd] = vel[c + 3 * (size_t)nd]; d[c * NnS + nd] = disp[c + 3 * (size_t)nd]; }
+    std::vector<double> vOut(v), dOut(d);   // the second buffer of the library's pair: updated nodes go here
     StepState st{};
     MarchArgs A{};
-    A.rec = P.rec.data(); A.ctaFirst = P.ctaFirst.data(); A.code = P.code.data();
+    A.rec = P.rec.data(); A.ctaFirstA = P.ctaFirstA.data(); A.ctaFirstB = P.ctaFirstB.data(); A.code = P.code.data();
     A.S = S; A.NnS = NnS; A.PFS = PFS;
     A.a = a.data(); A.ss = s3.data(); A.lam = lam.data(); A.mu = mu.data(); A.det = det.data(); A.stress = sg.data();
-    A.vel = v.data(); A.disp = d.data(); A.mass = mass; A.pf = pf.data(); A.force = force.data();
+    A.vel = v.data(); A.disp = d.data(); A.velOut = vOut.data(); A.dispOut = dOut.data(); A.mass = mass; A.pf = pf.data(); A.force = force.data();
     A.dt = dt; A.rdampk = rdampk; A.w = w; A.update = update; A.st = &st;
-    // the kernel reads v and d while neighbouring CTAs update fused nodes in place: legal because a fused
-    // node is read by its own bundle only.  The host reading runs the CTAs one after the other, which
-    // would expose any violation of that (a later CTA would see updated values).
+    // the kernel reads v and d of nodes that other CTAs update in the same launch (ghost sharing): the updates go to
+    // the second buffer.  The host reading runs the CTAs one after the other.
     std::vector<MarchShared> smv(1);
     MarchShared& sm = smv[0];
     std::vector<MarchRegs> regs(MK_NT);
     for (int cta = 0; cta < P.grid; ++cta)
-      for (int b = P.ctaFirst[cta]; b < P.ctaFirst[cta + 1]; ++b) {
+      for (int part = 0; part < 2; ++part)
+      for (int b = (part ? P.ctaFirstB : P.ctaFirstA)[cta]; b < (part ? P.ctaFirstB : P.ctaFirstA)[cta + 1]; ++b) {
         const MarchBundle B = P.rec[b];
 #define MK_RUN(body) do { for (int tid = 0; tid < MK_NT; ++tid) { MarchRegs& R = regs[tid]; (void)R; body; } } while (0)
 #define MK_WAITN ((void)0)
@@ -444,16 +580,22 @@ extern "C" int eqd_march_emulate(int32_t Nn, int32_t Ne, const double* meshCoor,
 #undef MK_WAITO
       }
     if (st.nanFlag) return __LINE__;
-    for (size_t s = 0; s < S; ++s) {
+    for (size_t s = 0; s < S; ++s) {      // the owner's copy is the element's stress ...
       const int e = P.refId[s];
-      if (e < 0) continue;
+      if (e < 0 || !P.owner[s]) continue;
       for (int k = 0; k < 6; ++k) stress6[k + 6 * (size_t)e] = sg[(size_t)k * S + s];
     }
+    for (size_t s = 0; s < S; ++s) {      // ... and every ghost copy carries the same bits
+      const int e = P.refId[s];
+      if (e < 0 || P.owner[s]) continue;
+      for (int k = 0; k < 6; ++k) if (stress6[k + 6 * (size_t)e] != sg[(size_t)k * S + s]) return __LINE__;
+    }
+    for (int e = 0; e < Ne; ++e) if (inBundle[e] > 1) return __LINE__;     // one owner per element
     for (int nd = 0; nd < Nn; ++nd)
-      for (int c = 0; c < 3; ++c) { vel[c + 3 * (size_t)nd] = v[c * NnS + nd]; disp[c + 3 * (size_t)nd] = d[c * NnS + nd]; fsum[c + 3 * (size_t)nd] = 0.0; }
+      for (int c = 0; c < 3; ++c) { vel[c + 3 * (size_t)nd] = vOut[c * NnS + nd]; disp[c + 3 * (size_t)nd] = dOut[c * NnS + nd]; fsum[c + 3 * (size_t)nd] = 0.0; }
     for (size_t slot = 0; slot < PFS; ++slot) {
       const int code = P.code[slot];
-      if (code < 0) continue;
+      if (code < 0 || (code & MK_GHOST)) continue;
       const int nd = code & MK_IDMASK;
       if (code & MK_FUSED) {
         if (fusedFlag[nd]) return __LINE__;          // a node is fused by one bundle only

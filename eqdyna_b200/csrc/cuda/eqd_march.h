@@ -47,7 +47,8 @@ constexpr int MK_NT = MK_PN;                         //   and the element column
 constexpr int MK_ES = MK_BZ * MK_NY;                 // element slots per plane (the y = MK_BY column of every row stays empty)
 constexpr int MK_OPROWS = 15;                        // a_x a_y a_z ss1 ss4 ss6 lam mu det stress(6)
 constexpr int MK_FUSED = 0x40000000;                 // node code: updated by the bundle itself
-constexpr int MK_IDMASK = 0x3fffffff;
+constexpr int MK_GHOST = 0x20000000;                 // node code: read only -- a neighbouring strip reports this node
+constexpr int MK_IDMASK = 0x1fffffff;
 constexpr int MK_MINLX = 4;                          // shortest bundle the planner makes
 
 struct MarchBundle {
@@ -59,14 +60,16 @@ struct MarchBundle {
 
 struct MarchArgs {
   const MarchBundle* rec;
-  const int* ctaFirst;      // [grid+1]: CTA b marches bundles rec[ctaFirst[b]] .. rec[ctaFirst[b+1]-1]
+  const int* ctaFirstA;     // [grid+1]: CTA b marches bundles rec[ctaFirstA[b]] .. rec[ctaFirstA[b+1]-1] (boundary work list)
+  const int* ctaFirstB;     // [grid+1]: ... then rec[ctaFirstB[b]] .. (interior work list); either may be null
   const int* code;          // [PFS] per node slot: -1 = no node, else node id | MK_FUSED
   size_t S, NnS, PFS;
   const double* a;          // [3][S] a_x, a_y, a_z  (eleshp rows 3, 7, 14)
   const double* ss;         // [3][S] ss1, ss4, ss6
   const double* lam; const double* mu; const double* det;
   double* stress;           // [6][S]
-  double* vel; double* disp;   // [3][NnS]
+  const double* vel; const double* disp;   // [3][NnS] v(nt), d(nt): read by every bundle that touches the node
+  double* velOut; double* dispOut;         // [3][NnS] where the updated nodes go (another buffer when strips share ghosts)
   const double* mass;       // [Nn]
   double* pf;               // [3][PFS] partial force of every non-fused node slot
   double* force;            // [3][NnS] complete force of the fused nodes when update == 0
@@ -303,7 +306,7 @@ EQD_HD void mk_phase_last(const MarchBundle& B, MarchShared& sm, MarchRegs& R, i
 
 // ---- phase: node plane pl is complete; rs = its ring slot, code / m = this thread's node
 EQD_HD void mk_phase_flush(const MarchArgs& A, const MarchBundle& B, MarchShared& sm, int tid, int pl, int rs, int code, double m) {
-  if (code < 0) return;
+  if (code < 0 || (code & MK_GHOST)) return;
   double F[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) F[c] = ((sm.frc[0][c][tid] + sm.frc[1][c][tid]) + sm.frc[2][c][tid]) + sm.frc[3][c][tid];
@@ -319,7 +322,7 @@ EQD_HD void mk_phase_flush(const MarchArgs& A, const MarchBundle& B, MarchShared
         v = v + (F[c] * rm) * A.dt;           // driver.f90:29,102
         d = d + v * A.dt;                     // :104
         bad |= (v != v);
-        A.vel[c * A.NnS + n] = v; A.disp[c * A.NnS + n] = d;
+        A.velOut[c * A.NnS + n] = v; A.dispOut[c * A.NnS + n] = d;
       }
       if (bad) mk_nan(A.st, (int)n);
     } else {

@@ -29,7 +29,7 @@ CASES = [
 def test_marching_kernel_matches_oracle(case, np_xyz, nstep, chunks, cops, what):
     wg = parity.build_world(case, np_xyz, nstep)
     wo = parity.build_world(case, np_xyz, nstep)
-    doms = parity.run_gpu(wg, options=OPTS, pre_options={"march": 1}, chunks=chunks, compute_ops=cops)
+    doms = parity.run_gpu(wg, options=OPTS, pre_options={"march": 2}, chunks=chunks, compute_ops=cops)
     parity.run_oracle(wo)
     res = parity.compare_worlds(wg, wo)
     parity.assert_parity(res)
@@ -45,7 +45,7 @@ def test_march_timing_slot_and_determinism():
     for chunks in (1, 1, 3):
         w = parity.build_world("test.tpv104", (1, 1, 1), n)
         from eqdyna_b200 import device as dev
-        d = dev.Domain(w.view(0), options={"march": 1})
+        d = dev.Domain(w.view(0), options={"march": 2})
         for k, v in OPTS.items():
             d.set_option(k, v)
         d.set_option("timing", 1)
@@ -62,8 +62,19 @@ def test_march_timing_slot_and_determinism():
 
 
 def test_march_and_tiles_agree_to_rounding():
+    """tile kernels only / bundles / bundles with shared ghost rows and columns: the same physics to rounding"""
     n = 20
     a = parity.build_world("test.tpv8", (1, 1, 1), n); parity.run_gpu(a, options=OPTS)
-    b = parity.build_world("test.tpv8", (1, 1, 1), n); parity.run_gpu(b, options=OPTS, pre_options={"march": 1})
-    for name in ("dispArr", "velArr", "stressArr", "nodalForceArr"):
-        assert parity.rel_l2(getattr(b.view(0), name), getattr(a.view(0), name)) < 1e-9, name
+    for march in (1, 2):
+        b = parity.build_world("test.tpv8", (1, 1, 1), n); parity.run_gpu(b, options=OPTS, pre_options={"march": march})
+        for name in ("dispArr", "velArr", "stressArr", "nodalForceArr"):
+            assert parity.rel_l2(getattr(b.view(0), name), getattr(a.view(0), name)) < 1e-9, (march, name)
+
+
+def test_march_without_ghost_sharing_matches_oracle():
+    """option march = 1 (strips do not overlap, v and d updated in place)"""
+    wg = parity.build_world("test.tpv104", (2, 2, 1), 60)
+    wo = parity.build_world("test.tpv104", (2, 2, 1), 60)
+    parity.run_gpu(wg, options=OPTS, pre_options={"march": 1}, chunks=2)
+    parity.run_oracle(wo)
+    parity.assert_parity(parity.compare_worlds(wg, wo))

@@ -42,7 +42,7 @@ def _worker(rank, world_size, port, case, decomp, nstep, overlap, own_rank_only,
         w = parity.build_world(case, decomp, nstep)   # whole world on the host: init-time shared sums done
     v = w.view(rank)
     d = dev.Domain(v, device=rank % torch.cuda.device_count(), compute_ops=bool(own_rank_only),
-                   options={"march": 1} if march else None)
+                   options={"march": 2} if march else None)
     if march:
         d.set_option("box", 2)
         d.set_option("box_compact", 1)

@@ -122,7 +122,7 @@ RUN_SCRIPT = textwrap.dedent(r"""
     # marching class: planner, slot table with the bundles' partial slots, node list, launch sequence with chunked runs
     for case, npx, cops in (("test.tpv104", (2, 2, 1), True), ("test.tpv36", (2, 2, 2), False)):
         w = parity.build_world(case, npx, 6)
-        doms = parity.run_gpu(w, options={"box": 2, "box_compact": 1}, pre_options={"march": 1}, chunks=2, compute_ops=cops)
+        doms = parity.run_gpu(w, options={"box": 2, "box_compact": 1}, pre_options={"march": 2}, chunks=2, compute_ops=cops)
         mc = [d.march_counts() for d in doms]
         assert all(m["elements"] > 0 and m["fused_nodes"] > 0.4 * m["elements"] and m["grid"] == 3 * 148 for m in mc), mc
         assert all(d.box_counts()["regular"] >= m["elements"] for d, m in zip(doms, mc))
@@ -185,7 +185,7 @@ def test_bench_native_arm_call_sequence_under_the_stand_in():
     assert line["metric"] == "element-steps/s" and line["dtype"] == "f64" and line["vs_baseline"] is None
     assert "workload" in line["config"] and line["config"]["case"] == "test.tpv104"
     tn = line["tuning"]
-    assert tn["box"] == 2 and tn["box_compact"] == 1 and tn["march"] == 1 and tn["march_elements"] == 516096
+    assert tn["box"] == 2 and tn["box_compact"] == 1 and tn["march"] == 2 and tn["march_elements"] == 516096
     assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
     rf = line["roofline"]

@@ -21,7 +21,7 @@ for n in (1, 2, 3, 10):
     v0 = wg.view(0)
     z = np.zeros((3, v0.Nn), order="F")
     _, fused, inb, st = T._emulate(v0, z.copy(order="F"), z.copy(order="F"), np.zeros((6, v0.Ne), order="F"), np.ones(v0.Nn), 1e-3, 0, 444)
-    doms = parity.run_gpu(wg, options={"box": 2, "box_compact": 1}, pre_options={"march": 1})
+    doms = parity.run_gpu(wg, options={"box": 2, "box_compact": 1}, pre_options={"march": 2})
     parity.run_oracle(wo)
     g, o = wg.view(0), wo.view(0)
 
