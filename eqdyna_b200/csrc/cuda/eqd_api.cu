@@ -975,14 +975,34 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
       });
       need(!badv[0], "eqd_set_mesh: bad dof table");
       need(!badv[1], "eqd_set_mesh: partially fixed node is not supported");
-      for (int n = 0; n < Nn; ++n)
-        if (h->info[n] == KIND_PML12) { h->info[n] = KIND_PML12 | (h->Np << 3); h->Np++; }
+      // PML slots in ascending node order: per-chunk counts, then an exclusive scan
+      const int nth = host_threads();
+      std::vector<int> cntT(nth + 1, 0);
+      const size_t per = ((size_t)Nn + nth - 1) / nth;
+      parallel_range((size_t)nth, [&](size_t tb, size_t te) {
+        for (size_t t = tb; t < te; ++t) {
+          int c = 0;
+          for (size_t n = std::min((size_t)Nn, t * per); n < std::min((size_t)Nn, (t + 1) * per); ++n) c += h->info[n] == KIND_PML12;
+          cntT[t + 1] = c;
+        }
+      }, 1);
+      for (int t = 0; t < nth; ++t) cntT[t + 1] += cntT[t];
+      h->Np = cntT[nth];
+      parallel_range((size_t)nth, [&](size_t tb, size_t te) {
+        for (size_t t = tb; t < te; ++t) {
+          int slot = cntT[t];
+          for (size_t n = std::min((size_t)Nn, t * per); n < std::min((size_t)Nn, (t + 1) * per); ++n)
+            if (h->info[n] == KIND_PML12) h->info[n] = KIND_PML12 | (slot++ << 3);
+        }
+      }, 1);
     }
     h->NnS = pad32(Nn);
     h->NpS = pad32(std::max(h->Np, 1));
     {
       std::vector<int> pn(std::max(h->Np, 1), 0);
-      for (int n = 0; n < Nn; ++n) if (EQD_INFO_KIND(h->info[n]) == KIND_PML12) pn[EQD_INFO_SLOT(h->info[n])] = n;
+      parallel_range((size_t)Nn, [&](size_t b, size_t e) {
+        for (size_t n = b; n < e; ++n) if (EQD_INFO_KIND(h->info[n]) == KIND_PML12) pn[EQD_INFO_SLOT(h->info[n])] = (int)n;
+      });
       h->dPmlNode.upload(pn);
     }
     need(3 * (double)h->NnS + 12 * (double)h->NpS < 4.0e9, "eqd_set_mesh: sub-domain too large for 32-bit halo offsets");
@@ -1002,10 +1022,27 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
           ccode[el] = (signed char)c;
         }
       });
-      size_t cntc[3] = {0, 0, 0};
-      for (int e = 0; e < Ne; ++e) { need(ccode[e] >= 0, "eqd_set_mesh: unknown element type"); cntc[ccode[e]]++; }
-      for (int c = 0; c < 3; ++c) members[c].reserve(cntc[c]);
-      for (int e = 0; e < Ne; ++e) members[ccode[e]].push_back(e);
+      // member lists in ascending element order: per-chunk counts per class, exclusive scan, parallel fill
+      const int nth = host_threads();
+      const size_t per = ((size_t)Ne + nth - 1) / nth;
+      std::vector<size_t> cnt3((size_t)(nth + 1) * 3, 0);
+      std::vector<char> unknown(1, 0);
+      parallel_range((size_t)nth, [&](size_t tb, size_t te) {
+        for (size_t t = tb; t < te; ++t)
+          for (size_t e = std::min((size_t)Ne, t * per); e < std::min((size_t)Ne, (t + 1) * per); ++e) {
+            if (ccode[e] < 0) { unknown[0] = 1; continue; }
+            cnt3[(t + 1) * 3 + ccode[e]]++;
+          }
+      }, 1);
+      need(!unknown[0], "eqd_set_mesh: unknown element type");
+      for (int t = 0; t < nth; ++t) for (int c = 0; c < 3; ++c) cnt3[(size_t)(t + 1) * 3 + c] += cnt3[(size_t)t * 3 + c];
+      for (int c = 0; c < 3; ++c) members[c].resize(cnt3[(size_t)nth * 3 + c]);
+      parallel_range((size_t)nth, [&](size_t tb, size_t te) {
+        for (size_t t = tb; t < te; ++t) {
+          size_t pos[3] = {cnt3[t * 3], cnt3[t * 3 + 1], cnt3[t * 3 + 2]};
+          for (size_t e = std::min((size_t)Ne, t * per); e < std::min((size_t)Ne, (t + 1) * per); ++e) members[ccode[e]][pos[ccode[e]]++] = (int)e;
+        }
+      }, 1);
     }
     lap.lap("node kinds + classes");
     int gny = 0, gnz = 0;
@@ -1138,35 +1175,48 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
     lap.lap("tile plan + uploads");
     // ---- node -> tile-node slots by rank, class then ascending tile id
     {
-      // every thread owns a contiguous range of nodes and scans all tile-node lists for them,
-      // so each node's slots are still visited in (class, ascending slot) order
+      // every thread owns a contiguous range of nodes.  The tile-node lists are first split, chunk by chunk, into one
+      // bucket per owner thread; an owner then walks its buckets in (class, chunk) order, so each node's slots are still
+      // visited in (class, ascending slot) order and every list entry is touched once, not once per thread
       std::vector<uint8_t> cnt(Nn, 0);
       const int nth = host_threads();
       std::vector<int> maxv(nth + 1, 2), badv(nth + 1, 0);
       const size_t NS = h->NnS;
       const size_t per = ((size_t)Nn + nth - 1) / nth;
+      struct Pair { int nd; uint32_t code; };
+      std::vector<std::vector<Pair>> bucket((size_t)NCLS * nth * nth);   // [class][chunk][owner]
+      {
+        std::vector<std::thread> th;
+        for (int w = 0; w < nth; ++w)
+          th.emplace_back([&, w] {
+            for (int c = 0; c < NCLS; ++c) {
+              const raw_vector<int>& tn = h->cls[c].tnodeH;
+              const size_t chunk = (tn.size() + nth - 1) / nth, b = std::min(tn.size(), w * chunk), e = std::min(tn.size(), (w + 1) * chunk);
+              for (size_t sl = b; sl < e; ++sl) {
+                const int nd = tn[sl];
+                if (nd < 0 || EQD_INFO_KIND(h->info[nd]) == KIND_FIXED) continue;
+                bucket[((size_t)c * nth + w) * nth + nd / per].push_back({nd, EQD_SLOT(c, sl)});
+              }
+            }
+          });
+        for (auto& x : th) x.join();
+      }
       auto scan = [&](raw_vector<uint32_t>* tab) {
         std::vector<std::thread> th;
         for (int t = 0; t < nth; ++t)
           th.emplace_back([&, t] {
-            const int lo = (int)std::min((size_t)Nn, t * per), hi = (int)std::min((size_t)Nn, (t + 1) * per);
-            if (lo >= hi) return;
-            for (int c = 0; c < NCLS; ++c) {
-              const raw_vector<int>& tn = h->cls[c].tnodeH;
-              for (size_t sl = 0; sl < tn.size(); ++sl) {
-                const int nd = tn[sl];
-                if (nd < lo || nd >= hi) continue;
-                const int kind = EQD_INFO_KIND(h->info[nd]);
-                if (kind == KIND_FIXED) continue;
-                if (!tab) {
-                  if (cnt[nd] == 255) { badv[t] = 1; continue; }
-                  maxv[t] = std::max(maxv[t], (int)++cnt[nd]);
-                } else {
-                  if ((c == CLS_REG || c == CLS_MARCH) && kind == KIND_PML12) { badv[t] = 2; continue; }
-                  (*tab)[(size_t)cnt[nd]++ * NS + nd] = EQD_SLOT(c, sl);
+            for (int c = 0; c < NCLS; ++c)
+              for (int w = 0; w < nth; ++w)
+                for (const Pair& q : bucket[((size_t)c * nth + w) * nth + t]) {
+                  const int nd = q.nd;
+                  if (!tab) {
+                    if (cnt[nd] == 255) { badv[t] = 1; continue; }
+                    maxv[t] = std::max(maxv[t], (int)++cnt[nd]);
+                  } else {
+                    if ((c == CLS_REG || c == CLS_MARCH) && EQD_INFO_KIND(h->info[nd]) == KIND_PML12) { badv[t] = 2; continue; }
+                    (*tab)[(size_t)cnt[nd]++ * NS + nd] = q.code;
+                  }
                 }
-              }
-            }
           });
         for (auto& x : th) x.join();
       };
@@ -1231,10 +1281,24 @@ void upload_elem_state(eqd_handle* h, DevBuf<int>& dCode, const double* eleporep
     spread(pstrain, 1, &ElemClass::pstrain, 0, 1, 0);
   }
   tmp.release();
-  // stresses: stressArr(stressCompIndexArr(e) + k)
+  // stresses: stressArr(stressCompIndexArr(e) + k).  Elastic runs start from rest (all zeros): then the device rows
+  // are simply cleared instead of being gathered on the host and uploaded
+  bool allZero = true;
+  {
+    std::vector<char> nz(1, 0);
+    parallel_range((size_t)h->sizeStress, [&](size_t b, size_t e) {
+      for (size_t k = b; k < e && !nz[0]; ++k) if (stressArr[k] != 0.0) nz[0] = 1;
+    });
+    allZero = !nz[0];
+  }
   for (int c = 0; c < NCLS; ++c) {
     ElemClass& C = h->cls[c];
     if (!C.n) continue;
+    if (allZero) {
+      CK(cudaMemsetAsync(C.stress.p, 0, sizeof(double) * (size_t)C.nstress * C.S, h->stream));
+      if (h->qmode && c != CLS_PML && C.qmem.p) CK(cudaMemsetAsync(C.qmem.p, 0, sizeof(double) * 6 * (size_t)C.S, h->stream));
+      continue;
+    }
     // first touched inside the parallel loop (no serial zero fill of ~1 GB); padding slots get zeros there
     raw_vector<double> sg((size_t)C.nstress * C.S), qm;
     if (h->qmode && c != CLS_PML) qm.resize(6 * (size_t)C.S);

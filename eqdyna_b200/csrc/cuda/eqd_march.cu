@@ -12,7 +12,10 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cstdio>
+#include <mutex>
 #include <cstdlib>
 #include <stdexcept>
 #include <string>
@@ -77,7 +80,7 @@ __global__ void __launch_bounds__(128) k_march_mass(const MarchBundle* __restric
       for (int dy = 1; dy >= 0; --dy) {
         const int p = pl - dx, cz = iz - dz, cy = iy - dy;
         if (p < 0 || p >= B.Lx || cz < 0 || cz >= bz || cy < 0 || cy >= by) continue;
-        const size_t e = (size_t)B.e0 + (size_t)p * MK_ES + cz * MK_NY + cy;
+        const size_t e = (size_t)B.e0 + (size_t)p * mk_es(B) + cz * by + cy;
         sum = sum + em[(size_t)corner[dx][dy][dz] * S + e];
       }
   pm[slot] = sum;
@@ -137,6 +140,16 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
   const long nynz = (long)ny * nz;
   auto reject_all = [&] { P.leftover = elems; };
   if (n == 0 || ny <= 1 || nz <= 1 || grid <= 0) { reject_all(); return; }
+  struct Lap {
+    bool on = std::getenv("EQD_VERBOSE") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char* label) {
+      if (!on) return;
+      auto now = std::chrono::steady_clock::now();
+      std::fprintf(stderr, "[eqd]   plan_march: %s %.3f s\n", label, std::chrono::duration<double>(now - t).count());
+      t = now;
+    }
+  } lap;
   // ---- lattice cell of every candidate: the grid position of corner 7 (+,+,+) minus one; the y+ face
   // (corners 3, 4, 7, 8) must be the lattice nodes of that cell (the y- face may hold split-node masters)
   raw_vector<int> cx(n), cy(n), cz(n);
@@ -157,12 +170,21 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
       cx[j] = ix - 1; cz[j] = iz - 1; cy[j] = iy - 1;
     }
   });
+  lap.lap("lattice cells + box test");
   int lo[3] = {1 << 30, 1 << 30, 1 << 30}, hi[3] = {-1, -1, -1};
-  for (int j = 0; j < n; ++j) {
-    if (cx[j] < 0) continue;
-    lo[0] = std::min(lo[0], cx[j]); hi[0] = std::max(hi[0], cx[j]);
-    lo[1] = std::min(lo[1], cz[j]); hi[1] = std::max(hi[1], cz[j]);
-    lo[2] = std::min(lo[2], cy[j]); hi[2] = std::max(hi[2], cy[j]);
+  {
+    std::mutex mu;
+    parallel_range((size_t)n, [&](size_t b, size_t e) {
+      int l[3] = {1 << 30, 1 << 30, 1 << 30}, h3[3] = {-1, -1, -1};
+      for (size_t j = b; j < e; ++j) {
+        if (cx[j] < 0) continue;
+        l[0] = std::min(l[0], cx[j]); h3[0] = std::max(h3[0], cx[j]);
+        l[1] = std::min(l[1], cz[j]); h3[1] = std::max(h3[1], cz[j]);
+        l[2] = std::min(l[2], cy[j]); h3[2] = std::max(h3[2], cy[j]);
+      }
+      std::lock_guard<std::mutex> g(mu);
+      for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], l[k]); hi[k] = std::max(hi[k], h3[k]); }
+    });
   }
   if (hi[0] < 0) { reject_all(); return; }
   const int ex = hi[0] - lo[0] + 1, ez = hi[1] - lo[1] + 1, ey = hi[2] - lo[2] + 1;
@@ -170,8 +192,11 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
   raw_vector<int> cell((size_t)ex * ez * ey);   // lattice cell -> index into elems, -1 = no candidate
   parallel_range(cell.size(), [&](size_t b, size_t e) { std::fill(cell.begin() + b, cell.begin() + e, -1); });
   auto at = [&](int x, int z, int y) -> int& { return cell[((size_t)x * ez + z) * ey + y]; };
-  for (int j = 0; j < n; ++j)
-    if (cx[j] >= 0) at(cx[j] - lo[0], cz[j] - lo[1], cy[j] - lo[2]) = j;
+  parallel_range((size_t)n, [&](size_t b, size_t e) {   // distinct cells: no two candidates share one
+    for (size_t j = b; j < e; ++j)
+      if (cx[j] >= 0) at(cx[j] - lo[0], cz[j] - lo[1], cy[j] - lo[2]) = (int)j;
+  });
+  lap.lap("cell map");
   // ---- where neighbouring candidates do not share their four nodes (the fault: its + side references the
   // split-node masters): per cell, bit 0 / 1 / 2 = mismatch with the y+ / z+ / x+ neighbour
   raw_vector<unsigned char> mis(cell.size());
@@ -212,6 +237,7 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
       for (int k = 0; k <= ey; ++k) seamY[k] |= sy[t][k];
     }
   }
+  lap.lap("neighbour joins");
   // A planar fault along a lattice plane (vertical strike-slip faults: y = 0) shows as ONE such plane: the column
   // tiles are then cut there.  A dipping fault crosses many planes; tiles then stay on the plain lattice and the
   // local checks below reject the stretches of a tile that the fault runs through (the tile kernels sweep those).
@@ -304,6 +330,7 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
     }
     for (auto& v : per) strips.insert(strips.end(), v.begin(), v.end());
   }
+  lap.lap("tiles + strips");
   long total = 0;
   for (const Strip& s : strips) total += s.len;
   if (total == 0) { reject_all(); return; }
@@ -383,6 +410,7 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
   schedule(listA, P.ctaFirstA);
   P.nBundlesA = (int)P.rec.size();
   schedule(listB, P.ctaFirstB);
+  lap.lap("schedule");
   // ---- slots
   const int nB = (int)P.rec.size();
   std::vector<int> stripOf(nB), xOf(nB);
@@ -390,7 +418,7 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
   for (int b = 0; b < nB; ++b) {
     stripOf[b] = P.rec[b].n0; xOf[b] = P.rec[b].e0;
     P.rec[b].e0 = (int)eslot; P.rec[b].n0 = (int)nslot;
-    eslot += (long)P.rec[b].Lx * MK_ES;
+    eslot += (long)P.rec[b].Lx * mk_es(P.rec[b]);
     nslot += (long)(P.rec[b].Lx + 1) * MK_PN;
     if (eslot > (1L << 29) || nslot > (1L << 30)) throw std::runtime_error("march planner: class too large for 32-bit slots");
   }
@@ -402,14 +430,15 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
   std::vector<char> taken(n, 0);
   std::vector<long> fusedT(host_threads() + 1, 0), elemsT(host_threads() + 1, 0);
   std::vector<int> bad(1, 0);
+  const bool fullCheck = std::getenv("EQD_MARCH_CHECK") != nullptr;
   {
     const int nth = host_threads();
     std::vector<std::thread> th;
-    const int per = (nB + nth - 1) / nth;
+    std::atomic<int> next(0);   // bundles differ in length: hand them out one by one
     for (int t = 0; t < nth; ++t)
       th.emplace_back([&, t] {
         const int corner[2][2][2] = {{{0, 4}, {3, 7}}, {{1, 5}, {2, 6}}};   // [sx][sy][sz]
-        for (int b = t * per; b < std::min(nB, (t + 1) * per); ++b) {
+        for (int b = next.fetch_add(1); b < nB; b = next.fetch_add(1)) {
           const MarchBundle& B = P.rec[b];
           const Strip& s = strips[stripOf[b]];
           const int bz = s.bz, by = s.by, x0 = xOf[b];
@@ -417,7 +446,7 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
             for (int z = 0; z < bz; ++z)
               for (int y = 0; y < by; ++y) {
                 const int j = at(x0 + p, s.z0 + z, s.y0 + y);
-                const size_t slot = (size_t)B.e0 + (size_t)p * MK_ES + z * MK_NY + y;
+                const size_t slot = (size_t)B.e0 + (size_t)p * mk_es(B) + z * by + y;
                 P.refId[slot] = elems[j];
                 const bool ghost = (z == 0 && s.gz) || (y == 0 && s.gy);     // the tile before owns this element
                 P.owner[slot] = ghost ? 0 : 1;
@@ -427,10 +456,12 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
             P.slotBundle[(size_t)B.n0 / MK_PN + pl] = b;
             for (int iz = 0; iz <= bz; ++iz)
               for (int iy = 0; iy <= by; ++iy) {
+                // the node id as any adjacent element of the strip has it (the joins between neighbouring cells were
+                // checked when the strips were made; EQD_MARCH_CHECK=1 compares all of them again)
                 int id = -1;
-                for (int dx = 0; dx < 2; ++dx)
-                  for (int dz = 0; dz < 2; ++dz)
-                    for (int dy = 0; dy < 2; ++dy) {
+                for (int dx = 0; dx < 2 && (id < 0 || fullCheck); ++dx)
+                  for (int dz = 0; dz < 2 && (id < 0 || fullCheck); ++dz)
+                    for (int dy = 0; dy < 2 && (id < 0 || fullCheck); ++dy) {
                       const int p = pl - dx, z = iz - dz, y = iy - dy;
                       if (p < 0 || p >= B.Lx || z < 0 || z >= bz || y < 0 || y >= by) continue;
                       const int nd = conn[8 * (size_t)elems[at(x0 + p, s.z0 + z, s.y0 + y)] + corner[dx][dy][dz]];
@@ -450,6 +481,7 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
       });
     for (auto& x : th) x.join();
   }
+  lap.lap("slots, codes");
   if (bad[0]) throw std::runtime_error("march planner: the elements of a bundle disagree on a lattice node (internal)");
   if (share) {
     // every (node, adjacent element) pair of the elements in bundles must be reported exactly once: count, per node,
@@ -461,7 +493,7 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
       for (int p = 0; p < B.Lx; ++p)
         for (int z = 0; z < bz; ++z)
           for (int y = 0; y < by; ++y) {
-            const size_t slot = (size_t)B.e0 + (size_t)p * MK_ES + z * MK_NY + y;
+            const size_t slot = (size_t)B.e0 + (size_t)p * mk_es(B) + z * by + y;
             if (P.owner[slot]) for (int k = 0; k < 8; ++k) want[conn[8 * (size_t)P.refId[slot] + k]]++;
           }
       for (int pl = 0; pl <= B.Lx; ++pl)
@@ -497,6 +529,7 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
   for (long v : elemsT) P.n += (int)v;
   P.leftover.reserve(n - P.n);
   for (int j = 0; j < n; ++j) if (!taken[j]) P.leftover.push_back(elems[j]);
+  lap.lap("check + leftover");
   if (std::getenv("EQD_VERBOSE"))
     std::fprintf(stderr, "[eqd]   plan_march: %d of %d regular elements in %d bundles (%d of them boundary work; %zu strips, lattice %dx%dx%d, "
                          "%zu x %zu column tiles), %ld element planes over %d CTAs, %ld fused nodes of %ld node slots\n",

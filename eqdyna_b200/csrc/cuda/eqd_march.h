@@ -44,7 +44,7 @@ constexpr int MK_NZ = 8, MK_NY = 16;                 // nodes of a bundle cross-
 constexpr int MK_BZ = MK_NZ - 1, MK_BY = MK_NY - 1;  // element columns of a full bundle cross-section: 7 x 15
 constexpr int MK_PN = MK_NZ * MK_NY;                 // nodes of a plane = threads of the CTA: thread t owns node t of every plane
 constexpr int MK_NT = MK_PN;                         //   and the element column whose (y-, z-) corner is node t
-constexpr int MK_ES = MK_BZ * MK_NY;                 // element slots per plane (the y = MK_BY column of every row stays empty)
+constexpr int MK_ES = MK_BZ * MK_NY;                 // room of one operator row in the stage buffer (>= bz*by of any bundle)
 constexpr int MK_OPROWS = 15;                        // a_x a_y a_z ss1 ss4 ss6 lam mu det stress(6)
 constexpr int MK_FUSED = 0x40000000;                 // node code: updated by the bundle itself
 constexpr int MK_GHOST = 0x20000000;                 // node code: read only -- a neighbouring strip reports this node
@@ -52,7 +52,8 @@ constexpr int MK_IDMASK = 0x1fffffff;
 constexpr int MK_MINLX = 4;                          // shortest bundle the planner makes
 
 struct MarchBundle {
-  int e0;      // first element slot of the class SoA (multiple of MK_ES): slot = e0 + p*MK_ES + cz*MK_NY + cy
+  int e0;      // first element slot of the class SoA (even): slot = e0 + p*mk_es(B) + cz*by + cy -- the planes of a bundle are
+               // packed (no slots for inactive columns), so an operator row of a plane is one contiguous, 16-byte aligned run
   int n0;      // first node slot: slot = n0 + p*MK_PN + iz*MK_NY + iy
   int Lx;      // elements along x (node planes 0..Lx)
   int shape;   // bz | by << 8: active columns cz < bz <= MK_BZ, cy < by <= MK_BY
@@ -146,6 +147,7 @@ EQD_HD void mk_nan(StepState* st, int node) {
 
 EQD_HD int mk_bz(const MarchBundle& B) { return B.shape & 0xff; }
 EQD_HD int mk_by(const MarchBundle& B) { return (B.shape >> 8) & 0xff; }
+EQD_HD int mk_es(const MarchBundle& B) { return (mk_bz(B) * mk_by(B) + 1) & ~1; }   // element slots per plane
 EQD_HD const double* mk_op_row(const MarchArgs& A, int r) {
   if (r < 3) return A.a + (size_t)r * A.S;
   if (r < 6) return A.ss + (size_t)(r - 3) * A.S;
@@ -179,12 +181,13 @@ EQD_HD void mk_issue_values(const MarchArgs& A, MarchShared& sm, int tid, int rs
 EQD_HD void mk_issue_ops(const MarchArgs& A, const MarchBundle& B, MarchShared& sm, int tid, int p) {
   if (p >= B.Lx) return;
   unsigned long long* bar = &sm.bar[p & 1];
-  if (tid == 0) mk_bar_expect(bar, (unsigned)(MK_OPROWS * MK_ES * sizeof(double)));
+  const int es = mk_es(B);
+  if (tid == 0) mk_bar_expect(bar, (unsigned)(MK_OPROWS * es * sizeof(double)));
 #if defined(__CUDA_ARCH__)
   __syncwarp();
 #endif
   if (tid < MK_OPROWS)
-    mk_bulk(sm.ops[p & 1][tid], mk_op_row(A, tid) + (size_t)B.e0 + (size_t)p * MK_ES, (unsigned)(MK_ES * sizeof(double)), bar);
+    mk_bulk(sm.ops[p & 1][tid], mk_op_row(A, tid) + (size_t)B.e0 + (size_t)p * es, (unsigned)(es * sizeof(double)), bar);
 }
 
 // 4-point transform of a face: a[q], q = dy + 2 dz
@@ -255,7 +258,7 @@ EQD_HD void mk_phase_element(const MarchArgs& A, const MarchBundle& B, MarchShar
       R.wl[0][c] = ny; R.wl[1][c] = nz; R.wl[2][c] = nyz;
     }
   }
-  const int es = tid;   // element slot inside the plane = cz*MK_NY + cy
+  const int es = (tid / MK_NY) * mk_by(B) + (tid % MK_NY);   // element slot inside the (packed) plane
   const double ax = op[0][es], ay = op[1][es], az = op[2][es];
   // calcElemKU.f90:44-60 with eleshp(d,i) = sign_d(i) a_d
   double sr[6];
@@ -274,7 +277,7 @@ EQD_HD void mk_phase_element(const MarchArgs& A, const MarchBundle& B, MarchShar
   rate[4] = mu * sr[4];
   rate[5] = mu * sr[5];
   const double temp = (-op[8][es]) * A.w;   // calcElemKU.f90:169-173, constk = -eledet
-  double* sp = A.stress + (size_t)B.e0 + (size_t)p * MK_ES + es;
+  double* sp = A.stress + (size_t)B.e0 + (size_t)p * mk_es(B) + es;
   double t[6];
 #pragma unroll
   for (int k = 0; k < 6; ++k) {

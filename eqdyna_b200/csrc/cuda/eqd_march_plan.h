@@ -11,7 +11,7 @@ namespace eqd {
 
 struct MarchPlan {
   int n = 0;        // elements placed in bundles
-  int S = 0;        // element slots of the class SoA (every element plane of a bundle holds MK_ES)
+  int S = 0;        // element slots of the class SoA (planes packed: (bz*by rounded up to even) slots each)
   int PFS = 0;      // node slots ((Lx + 1) * MK_PN per bundle)
   int grid = 0;     // CTAs of the persistent launch
   long nFused = 0;  // nodes the bundles update themselves

@@ -70,6 +70,7 @@ cudaError_t cudaMemcpy(void* d, const void* s, size_t n, int) { std::memcpy(d, s
 cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) { std::memcpy(d, s, n); return 0; }
 cudaError_t cudaMemcpyToSymbol(const void*, const void*, size_t, size_t, int) { return 0; }
 cudaError_t cudaMemset(void* d, int v, size_t n) { std::memset(d, v, n); return 0; }
+cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { std::memset(d, v, n); return 0; }
 cudaError_t cudaStreamCreate(cudaStream_t* s) { *s = (void*)1; return 0; }
 cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) { *s = (void*)2; return 0; }
 cudaError_t cudaStreamDestroy(cudaStream_t) { return 0; }
