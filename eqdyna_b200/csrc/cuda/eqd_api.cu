@@ -109,6 +109,7 @@ struct Nccl {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -124,7 +125,7 @@ struct Nccl {
     }
     if (!lib) return false;
 #define SYM(f) f = (decltype(f))dlsym(lib, "nccl" #f); if (!f) { why = "missing nccl" #f; lib = nullptr; return false; }
-    SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(Send) SYM(Recv) SYM(GroupStart) SYM(GroupEnd) SYM(GetErrorString)
+    SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(Send) SYM(Recv) SYM(AllGather) SYM(GroupStart) SYM(GroupEnd) SYM(GetErrorString)
 #undef SYM
     return true;
   }
@@ -190,6 +191,7 @@ struct eqd_handle {
   DevBuf<MarchBundle> mRec;
   DevBuf<int> mCtaFirstA, mCtaFirstB, mCode, mSlotBundle;   // work lists: A = bundles that may touch a rank face, B = the rest
   int mGrid = 0, mBundles = 0;
+  int mSlotB0 = 0;          // first node slot of the interior work list
   long mFused = 0;
   int optMarch = 0;         // option "march" (before eqd_set_mesh)
   bool sweepFused = false;  // the last element sweep updated the fused nodes itself
@@ -233,6 +235,25 @@ struct eqd_handle {
   Face face[3][2];
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;
+  // ncclCommInitRank runs on a helper thread from eqd_set_comm on, so that a host which calls eqd_set_comm right after
+  // eqd_create overlaps the communicator's start-up with its uploads; comm_ready() joins before the first use
+  std::thread commThread;
+  ncclResult_t commRc = ncclSuccess;
+  // Step-loop exchange over peer memory (option "halo", default on between processes of one box): every face has two
+  // receive buffers and two flag words in ONE allocation of this sub-domain, which the neighbours map through CUDA IPC;
+  // k_halo_send writes into the neighbour's copy, k_halo_recv polls the own one (eqd_kernels.cu).  NCCL is then used at
+  // set-up only (unique id, the all-gather of the IPC handles, eqd_sum_shared).
+  struct P2P {
+    bool on = false;
+    DevBuf<unsigned char> area;            // [face][parity] receive buffers | flag words | send counters
+    size_t recvOff[3][2][2] = {{{0}}};     // byte offsets inside `area`
+    size_t flagOff = 0, counterOff = 0;
+    std::vector<void*> peerBase;           // [rank] the neighbour's area as mapped here (nullptr: not a neighbour)
+    size_t peerRecvOff[3][2][2] = {{{0}}}; // [axis][my side][parity]: offset of the FACING face's buffer inside the neighbour's area
+    size_t peerFlagOff[3][2] = {{0}};      // flag words of the facing face (two parities, consecutive)
+    unsigned seq = 0;
+  } p2p;
+  int optHalo = -1;                        // -1 auto (peer memory when it can be set up), 0 ncclSend/ncclRecv, 1 peer memory or fail
   cudaEvent_t evPacked[3] = {nullptr, nullptr, nullptr};
   // overlap of the halo with the interior element sweep: tiles that
   // touch a rank-face node are swept first, their face sums are exchanged on
@@ -457,6 +478,15 @@ void face_nodes(const eqd_handle& h, int a, int side, std::vector<int>& out) {
     for (int k : h.fltface[2 * a + side]) out.push_back(nx * ny * nz + k - 1);
 }
 
+void p2p_setup(eqd_handle* h);
+
+void comm_ready(eqd_handle* h) {
+  if (h->commThread.joinable()) {
+    h->commThread.join();
+    if (h->commRc != ncclSuccess) { h->comm = nullptr; throw CudaError(std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(h->commRc)); }
+  }
+}
+
 void finalize(eqd_handle* h) {
   if (h->finalized) return;
   need(h->meshSet && h->opsSet && h->nodalSet, "eqd_run: eqd_set_mesh, eqd_set_elem_ops and eqd_set_nodal must be called first");
@@ -509,6 +539,7 @@ void finalize(eqd_handle* h) {
       }
     for (int a = 0; a < 3; ++a) CK(cudaEventCreateWithFlags(&h->evPacked[a], cudaEventDisableTiming));
   }
+  p2p_setup(h);
   // ---- launch order of the tiles: those touching an active rank face first
   std::vector<char> onFace(Nn, 0);
   bool& anyFace = h->anyFace;
@@ -579,6 +610,15 @@ void finalize(eqd_handle* h) {
     // sharing nodes), no rank-face node (a face bounds the sub-domain's elements)
     for (int n : list)
       if (EQD_INFO_KIND(h->info[n]) == KIND_FREE3 && EQD_INFO_FUSED(h->info[n])) throw ArgError("internal: node " + std::to_string(n + 1) + " is both fused and special");
+    // the interior work list is swept while the face forces travel: none of its strips may touch a rank-face node
+    {
+      const raw_vector<int>& tn = h->cls[CLS_MARCH].tnodeH;
+      std::vector<char> hit(1, 0);
+      parallel_range(tn.size() - std::min(tn.size(), (size_t)h->mSlotB0), [&](size_t b, size_t e) {
+        for (size_t k = b + h->mSlotB0; k < e + h->mSlotB0; ++k) if (tn[k] >= 0 && onFace[tn[k]]) hit[0] = 1;
+      });
+      if (hit[0]) throw ArgError("internal: a strip of the interior work list touches a rank face");
+    }
     std::vector<int> rest;
     rest.reserve((size_t)Nn - (size_t)h->mFused);
     for (int n = 0; n < Nn; ++n)
@@ -639,6 +679,7 @@ void finalize(eqd_handle* h) {
 
 // transport of one axis phase between processes (NCCL) -- pack/unpack by caller
 void halo_axis_nccl(eqd_handle* h, int a, cudaStream_t st) {
+  comm_ready(h);
   if (!h->comm) throw ArgError("eqd_run: sub-domain has neighbours but eqd_set_comm was not called");
   NK(g_nccl.GroupStart());
   for (int side = 0; side < 2; ++side) {
@@ -700,8 +741,103 @@ void halo_unpack(eqd_handle* h, int a, cudaStream_t st = nullptr) {
     launch_unpack_add(h->dForce.p, F.idx.p, F.n, F.recv.p, st); h->launches++;
   }
 }
+// Peer-memory set-up of the step-loop exchange (collective: every rank of the communicator calls it once, from
+// finalize).  Each rank lays its receive buffers, flag words and send counters out in one allocation, publishes the
+// allocation's IPC handle and the layout through one ncclAllGather, and maps its neighbours' allocations.
+struct P2PRecord { cudaIpcMemHandle_t handle; unsigned long long recvOff[3][2][2]; unsigned long long flagOff; unsigned long long pad[2]; };
+void p2p_setup(eqd_handle* h) {
+  auto& Q = h->p2p;
+  Q.on = false;
+  comm_ready(h);
+  if (!h->comm || h->optHalo == 0 || h->nranks < 2) return;
+  static_assert(sizeof(P2PRecord) % 8 == 0, "record is exchanged as 8-byte words");
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  for (int a = 0; a < 3; ++a)
+    for (int s = 0; s < 2; ++s)
+      for (int par = 0; par < 2; ++par) Q.recvOff[a][s][par] = take(sizeof(double) * (size_t)std::max(h->face[a][s].n, 1));
+  Q.flagOff = take(sizeof(unsigned) * 12);      // [axis][side][parity]
+  Q.counterOff = take(sizeof(unsigned) * 6);    // [axis][side]
+  Q.area.alloc(off);                            // zeroed: flags 0, counters 0
+  P2PRecord mine{};
+  bool ok = cudaIpcGetMemHandle(&mine.handle, Q.area.p) == cudaSuccess;
+  for (int a = 0; a < 3; ++a) for (int s = 0; s < 2; ++s) for (int par = 0; par < 2; ++par) mine.recvOff[a][s][par] = Q.recvOff[a][s][par];
+  mine.flagOff = Q.flagOff;
+  mine.pad[0] = ok ? 1 : 0;
+  // all-gather of the records through device memory
+  const size_t words = sizeof(P2PRecord) / 8;
+  DevBuf<unsigned long long> dMine, dAll;
+  dMine.alloc(words); dAll.alloc(words * h->nranks);
+  CK(cudaMemcpy(dMine.p, &mine, sizeof mine, cudaMemcpyHostToDevice));
+  NK(g_nccl.AllGather(dMine.p, dAll.p, words, ncclUint64, h->comm, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  std::vector<P2PRecord> all(h->nranks);
+  CK(cudaMemcpy(all.data(), dAll.p, sizeof(P2PRecord) * h->nranks, cudaMemcpyDeviceToHost));
+  for (const P2PRecord& r : all) ok = ok && r.pad[0] == 1;
+  Q.peerBase.assign(h->nranks, nullptr);
+  for (int a = 0; a < 3 && ok; ++a)
+    for (int s = 0; s < 2 && ok; ++s) {
+      const Face& F = h->face[a][s];
+      if (F.nb < 0) continue;
+      if (!Q.peerBase[F.nb]) {
+        void* base = nullptr;
+        if (cudaIpcOpenMemHandle(&base, all[F.nb].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+        Q.peerBase[F.nb] = base;
+      }
+      // my -side face talks to the neighbour's +side face of the same axis, and vice versa
+      for (int par = 0; par < 2; ++par) Q.peerRecvOff[a][s][par] = all[F.nb].recvOff[a][1 - s][par];
+      Q.peerFlagOff[a][s] = all[F.nb].flagOff + sizeof(unsigned) * (size_t)((a * 2 + (1 - s)) * 2);
+    }
+  // the choice must be the same on every rank: one more tiny all-gather of the outcome
+  unsigned long long okw = ok ? 1 : 0;
+  CK(cudaMemcpy(dMine.p, &okw, 8, cudaMemcpyHostToDevice));
+  NK(g_nccl.AllGather(dMine.p, dAll.p, 1, ncclUint64, h->comm, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  std::vector<unsigned long long> oks(h->nranks);
+  CK(cudaMemcpy(oks.data(), dAll.p, 8 * h->nranks, cudaMemcpyDeviceToHost));
+  for (unsigned long long v : oks) ok = ok && v == 1;
+  if (!ok) {
+    for (void*& b : Q.peerBase) if (b) { cudaIpcCloseMemHandle(b); b = nullptr; }
+    if (h->optHalo == 1) throw CudaError("option halo = 1: peer memory (CUDA IPC) between the ranks is not available");
+    if (getenv("EQD_VERBOSE")) fprintf(stderr, "[eqd] rank %d: peer memory not available, step-loop exchange over ncclSend/ncclRecv\n", h->rank);
+    return;
+  }
+  Q.on = true;
+  Q.seq = 0;
+  if (getenv("EQD_VERBOSE")) fprintf(stderr, "[eqd] rank %d: step-loop exchange over peer memory (CUDA IPC), %zu bytes of receive area\n", h->rank, off);
+}
+
+// the three axis phases over peer memory: pack into the neighbour's buffer + flag, wait for the own flag + add
+void halo_all_p2p(eqd_handle* h, cudaStream_t st) {
+  auto& Q = h->p2p;
+  Timer t(h, EQD_T_HALO, st);
+  const unsigned seq = ++Q.seq;
+  const int par = (int)(seq & 1u);
+  unsigned char* base = Q.area.p;
+  for (int a = 0; a < 3; ++a) {
+    if (h->face[a][0].nb < 0 && h->face[a][1].nb < 0) continue;
+    HaloAxisArgs A{};
+    for (int s = 0; s < 2; ++s) {
+      const Face& F = h->face[a][s];
+      A.n[s] = F.nb >= 0 ? F.n : 0;
+      if (F.nb < 0) continue;
+      A.idx[s] = F.idx.p;
+      unsigned char* peer = (unsigned char*)Q.peerBase[F.nb];
+      A.remoteRecv[s] = (double*)(peer + Q.peerRecvOff[a][s][par]);
+      A.remoteFlag[s] = (unsigned*)(peer + Q.peerFlagOff[a][s]) + par;
+      A.localRecv[s] = (const double*)(base + Q.recvOff[a][s][par]);
+      A.localFlag[s] = (const unsigned*)(base + Q.flagOff) + (a * 2 + s) * 2 + par;
+      A.counter[s] = (unsigned*)(base + Q.counterOff) + a * 2 + s;
+    }
+    A.force = h->dForce.p; A.seq = seq;
+    launch_halo_send(A, st); launch_halo_recv(A, st); h->launches += 2;
+  }
+  t.stop();
+}
+
 // the three axis phases of MPI4NodalQuant between processes, in order, on stream st
 void halo_all_nccl(eqd_handle* h, cudaStream_t st) {
+  if (h->p2p.on) { halo_all_p2p(h, st); return; }
   Timer t(h, EQD_T_HALO, st);
   for (int a = 0; a < 3; ++a) {
     if (h->face[a][0].nb < 0 && h->face[a][1].nb < 0) continue;
@@ -909,6 +1045,8 @@ int eqd_create(const eqd_params* p, int device, eqd_handle** out) {
 int eqd_destroy(eqd_handle* h) {
   if (!h) return EQD_OK;
   cudaSetDevice(h->device);
+  if (h->commThread.joinable()) h->commThread.join();
+  for (void* b : h->p2p.peerBase) if (b) cudaIpcCloseMemHandle(b);
   if (h->comm && g_nccl.lib) g_nccl.CommDestroy(h->comm);
   for (int a = 0; a < 3; ++a) if (h->evPacked[a]) cudaEventDestroy(h->evPacked[a]);
   for (cudaEvent_t e : {h->evFace, h->evElem, h->evComm}) if (e) cudaEventDestroy(e);
@@ -1080,6 +1218,7 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
         if (MP.n > 0) {
           M.n = MP.n; M.S = MP.S; M.PFS = MP.PFS;
           h->mGrid = MP.grid; h->mBundles = (int)MP.rec.size(); h->mFused = MP.nFused;
+          h->mSlotB0 = MP.nBundlesA < (int)MP.rec.size() ? MP.rec[MP.nBundlesA].n0 : MP.PFS;
           h->mRec.upload(MP.rec); h->mCtaFirstA.upload(MP.ctaFirstA); h->mCtaFirstB.upload(MP.ctaFirstB);
           h->mCode.upload(MP.code); h->mSlotBundle.upload(MP.slotBundle);
           // host copy of the node slots for the slot table: only the nodes that emit a partial
@@ -1663,8 +1802,13 @@ int eqd_set_comm(eqd_handle* h, const void* id128, int32_t nranks, int32_t rank)
     if (!g_nccl.load()) throw CudaError("cannot load NCCL: " + g_nccl.why);
     ncclUniqueId id;
     memcpy(&id, id128, 128);
-    NK(g_nccl.CommInitRank(&h->comm, nranks, id, rank));
+    comm_ready(h);
     h->nranks = nranks; h->rank = rank;
+    h->commRc = ncclSuccess;
+    h->commThread = std::thread([h, id, nranks, rank] {
+      cudaSetDevice(h->device);
+      h->commRc = g_nccl.CommInitRank(&h->comm, nranks, id, rank);
+    });
   });
 }
 
@@ -1677,6 +1821,7 @@ int eqd_sum_shared(eqd_handle* h) {
     need(h->nodalSet, "eqd_sum_shared: call after eqd_set_nodal / eqd_set_fault / eqd_set_halo");
     finalize(h);
     if (!has_neighbours(h)) return;
+    comm_ready(h);
     need(h->comm != nullptr, "eqd_sum_shared: eqd_set_comm first");
     // host-staged: these run once
     for (int a = 0; a < 3; ++a) {
@@ -1731,7 +1876,9 @@ int eqd_run(eqd_handle* h, int32_t nt_begin, int32_t nt_end) {
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     if (h->timing) { CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1)); CK(cudaEventRecord(t0, h->stream)); }
     for (int nt = nt_begin; nt <= nt_end; ++nt) {
-      const int ov = !h->commStream ? 0 : h->optOverlap < 0 ? (multi ? 1 : 0) : h->optOverlap;
+      // auto: with rank neighbours the exchange and the fault solver go to the second stream; with marching strips the
+      // boundary work list is swept first, so that the exchange also hides under the interior sweep
+      const int ov = !h->commStream ? 0 : h->optOverlap < 0 ? (multi ? (h->cls[CLS_MARCH].n ? 2 : 1) : 0) : h->optOverlap;
       step_pre(h, ov, multi, nt == nt_end);
       if (multi && !ov) halo_all_nccl(h, h->stream);
       step_post(h, ov);
@@ -2041,6 +2188,11 @@ int eqd_set_option(eqd_handle* h, const char* key, int32_t value) {
     return EQD_OK;
   }
   if (!strcmp(key, "reserve")) { h->optReserve = value; return EQD_OK; }
+  if (!strcmp(key, "halo")) {
+    if (h->finalized) { h->err = "eqd_set_option: halo must be set before the first eqd_run / eqd_sum_shared"; return EQD_ERR_ARG; }
+    h->optHalo = value;
+    return EQD_OK;
+  }
   h->err = std::string("eqd_set_option: unknown key ") + key;
   return EQD_ERR_ARG;
 }

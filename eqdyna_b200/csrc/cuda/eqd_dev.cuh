@@ -133,6 +133,19 @@ struct FaultArgs {
   int friclaw, C_nuclea, nucfault, TPV, insertFaultType, C_elastic;
 };
 
+// one axis phase of the nodal-force exchange over peer memory (k_halo_send / k_halo_recv), [side]
+struct HaloAxisArgs {
+  int n[2];                    // doubles exchanged with the -side / +side neighbour (0 = none)
+  const uint32_t* idx[2];      // dof positions in force[]
+  double* remoteRecv[2];       // the neighbour's receive buffer for this exchange (its memory, mapped through CUDA IPC)
+  unsigned* remoteFlag[2];     // ... and its flag word
+  const double* localRecv[2];  // this sub-domain's receive buffer for this exchange
+  const unsigned* localFlag[2];
+  unsigned* counter[2];        // blocks of k_halo_send that have finished
+  double* force;
+  unsigned seq;                // exchange number (1, 2, ...)
+};
+
 // operator precompute on the device (eqd_ops.cu)
 struct OpsArgs {
   int S, Ne;

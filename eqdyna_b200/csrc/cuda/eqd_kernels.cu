@@ -1239,6 +1239,51 @@ __global__ void k_unpack_add(double* __restrict__ dst, const uint32_t* __restric
 }
 
 // ----------------------------------------------------------------------------
+// The same exchange without a communication library in the step loop: the sub-domains of one box see each
+// other's memory over NVLink (CUDA IPC, set up once in eqd_api.cu).  k_halo_send packs the face dofs straight
+// into the NEIGHBOUR's receive buffer (remote stores) and, when the last block has done so, publishes the step
+// number in the neighbour's flag word; k_halo_recv waits for its own flag word to show this step and adds the
+// received values (processNodalQuantArr's "+", assembleGlobalMass.f90:190-236).  blockIdx.y = side of the axis.
+// Two receive buffers per face, used alternately: a sender can be at most one exchange ahead of its receiver
+// (it needs the receiver's data of exchange n+1 before it can send exchange n+2).
+__global__ void __launch_bounds__(256) k_halo_send(HaloAxisArgs A) {
+  const int side = blockIdx.y;
+  const int n = A.n[side];
+  if (n <= 0) return;
+  const int nblk = (n + 255) / 256;
+  if ((int)blockIdx.x >= nblk) return;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < n) A.remoteRecv[side][i] = A.force[A.idx[side][i]];
+  __threadfence_system();          // this thread's remote stores are visible system-wide ...
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned done = atomicAdd(A.counter[side], 1u) + 1u;
+    if (done == (unsigned)nblk) {  // ... so the block that arrives last may announce the whole message
+      *A.counter[side] = 0u;
+      __threadfence_system();
+      *(volatile unsigned*)A.remoteFlag[side] = A.seq;
+    }
+  }
+}
+__global__ void __launch_bounds__(256) k_halo_recv(HaloAxisArgs A) {
+  const int side = blockIdx.y;
+  const int n = A.n[side];
+  if (n <= 0) return;
+  if ((int)blockIdx.x >= (n + 255) / 256) return;
+  if (threadIdx.x == 0) {
+    const volatile unsigned* f = A.localFlag[side];
+    while (*f != A.seq) __nanosleep(100);
+    __threadfence_system();
+  }
+  __syncthreads();
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < n) {
+    const uint32_t k = A.idx[side][i];
+    A.force[k] = A.force[k] + __ldcg(A.localRecv[side] + i);   // written by the peer: never through this SM's L1
+  }
+}
+
+// ----------------------------------------------------------------------------
 // thermop.f90:1-40: one thread per pair, O(nt) history convolution
 __global__ void __launch_bounds__(128) k_thermop(FaultArgs A) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1712,6 +1757,14 @@ void launch_pack(const double* src, const uint32_t* idx, int n, double* buf, cud
 }
 void launch_unpack_add(double* dst, const uint32_t* idx, int n, const double* buf, cudaStream_t s) {
   if (n > 0) k_unpack_add<<<nblk(n, 256), 256, 0, s>>>(dst, idx, n, buf);
+}
+void launch_halo_send(const HaloAxisArgs& A, cudaStream_t s) {
+  const int n = std::max(A.n[0], A.n[1]);
+  if (n > 0) k_halo_send<<<dim3(nblk(n, 256), 2), 256, 0, s>>>(A);
+}
+void launch_halo_recv(const HaloAxisArgs& A, cudaStream_t s) {
+  const int n = std::max(A.n[0], A.n[1]);
+  if (n > 0) k_halo_recv<<<dim3(nblk(n, 256), 2), 256, 0, s>>>(A);
 }
 void launch_thermop(const FaultArgs& A, cudaStream_t s) {
   if (A.nPairs > 0) k_thermop<<<nblk(A.nPairs, 128), 128, 0, s>>>(A);

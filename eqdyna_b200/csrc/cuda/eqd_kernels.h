@@ -21,6 +21,8 @@ void launch_sample_gm(const int* surf, int nSurf, const double* vel, int NnS, do
 void launch_sample_src(const double* fric, int PS, int n, double* out, cudaStream_t s);
 void launch_pack(const double* src, const uint32_t* idx, int n, double* buf, cudaStream_t s);
 void launch_unpack_add(double* dst, const uint32_t* idx, int n, const double* buf, cudaStream_t s);
+void launch_halo_send(const HaloAxisArgs& A, cudaStream_t s);
+void launch_halo_recv(const HaloAxisArgs& A, cudaStream_t s);
 void launch_thermop(const FaultArgs& A, cudaStream_t s);
 void launch_fault(const FaultArgs& A, cudaStream_t s);
 void launch_gather_rows(const double* src, int K, const int* refId, int S, double* dst, int row, cudaStream_t s);

@@ -129,9 +129,11 @@ def box_check(view):
 class Domain:
     """One sub-domain of a case on one GPU."""
 
-    def __init__(self, view, device=0, compute_ops=False, options=None):
+    def __init__(self, view, device=0, compute_ops=False, options=None, comm=None):
         """compute_ops: let the device compute the element operators and the lumped mass from the
-        mesh (eqd_compute_elem_ops) instead of uploading the host's (eqd_set_elem_ops)."""
+        mesh (eqd_compute_elem_ops) instead of uploading the host's (eqd_set_elem_ops).
+        comm = (id128, nranks, rank): eqd_set_comm right after eqd_create, so that the communicator
+        starts up while the state is uploaded."""
         self.view = view
         self.compute_ops = compute_ops
         self._h = C.c_void_p()
@@ -143,6 +145,8 @@ class Domain:
         self._nt_done = 0
         for k, val in (options or {}).items():   # options that shape the upload (tile bricks)
             self.set_option(k, val)
+        if comm is not None:
+            self.set_comm(*comm)
         self._upload(view)
 
     def _check(self, rc):

@@ -42,10 +42,12 @@ def _worker(rank, world_size, port, case, decomp, nstep, overlap, own_rank_only,
         w = parity.build_world(case, decomp, nstep)   # whole world on the host: init-time shared sums done
     v = w.view(rank)
     d = dev.Domain(v, device=rank % torch.cuda.device_count(), compute_ops=bool(own_rank_only),
-                   options={"march": 2} if march else None)
+                   options={"march": 1} if march else None)
     if march:
         d.set_option("box", 2)
         d.set_option("box_compact", 1)
+    if march == 2:
+        d.set_option("halo", 0)      # the ncclSend / ncclRecv exchange instead of peer memory
     ids = [dev.unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     d.set_comm(ids[0], world_size, rank)
@@ -66,10 +68,12 @@ def _worker(rank, world_size, port, case, decomp, nstep, overlap, own_rank_only,
 @pytest.mark.parametrize("case,decomp,nstep,overlap,own_rank_only,march",
                          [("test.tpv8", (2, 1, 1), 0, 1, 0, 0), ("test.tpv104", (1, 2, 1), 60, 1, 0, 0), ("test.tpv8", (2, 1, 1), 40, 0, 0, 0),
                           ("test.tpv104", (1, 2, 1), 60, 1, 1, 0), ("test.tpv10", (2, 1, 2), 60, 2, 0, 0),
-                          ("test.tpv104", (2, 1, 1), 60, 1, 1, 1), ("test.tpv104", (1, 2, 1), 60, 0, 0, 1)],
+                          ("test.tpv104", (2, 1, 1), 60, 1, 1, 1), ("test.tpv104", (1, 2, 1), 60, 0, 0, 1), ("test.tpv104", (2, 1, 1), 60, -1, 1, 1),
+                          ("test.tpv8", (1, 1, 2), 40, -1, 0, 2)],
                          ids=["tpv8-2x1x1", "tpv104-1x2x1-fault-on-rank-face", "tpv8-2x1x1-no-overlap",
                               "tpv104-1x2x1-own-rank-device-ops-sum-shared", "tpv10-2x1x2-face-tiles-first",
-                              "tpv104-2x1x1-march-own-rank-device-ops", "tpv104-1x2x1-march-no-overlap"])
+                              "tpv104-2x1x1-march-own-rank-device-ops", "tpv104-1x2x1-march-no-overlap",
+                              "tpv104-2x1x1-march-auto-overlap-boundary-list-first", "tpv8-1x1x2-march-nccl-sendrecv-instead-of-peer-memory"])
 def test_nccl_processes_match_oracle(tmp_path, case, decomp, nstep, overlap, own_rank_only, march):
     import torch
     import torch.multiprocessing as mp
