@@ -191,10 +191,17 @@ struct eqd_handle {
   DevBuf<MarchBundle> mRec;
   DevBuf<int> mCtaFirstA, mCtaFirstB, mCode, mSlotBundle;   // work lists: A = bundles that may touch a rank face, B = the rest
   int mGrid = 0, mBundles = 0;
+  int mNxg = 0;             // node planes of the grid in x (for the planner's end caps)
   int mSlotB0 = 0;          // first node slot of the interior work list
+  bool mSplitOk = true;     // no strip of the interior work list touches a rank face (checked when the faces are known)
   long mFused = 0;
   int optMarch = 0;         // option "march" (before eqd_set_mesh)
   bool sweepFused = false;  // the last element sweep updated the fused nodes itself
+  // PML bundles (CLS_MARCHP, eqd_march_pml.h): cls[CLS_MARCHP] holds shp = [3][S], ss = [3][S], damps, 21 stress rows; their
+  // node slots follow the PML tile class's in cls[CLS_PML].pf (first one: pSlotBase)
+  DevBuf<MarchBundle> pRec;
+  DevBuf<int> pCtaFirstA, pCtaFirstB, pCode, pSlotBundle;
+  int pGrid = 0, pBundles = 0, pSlotBase = 0, pSlotB0 = 0;
   raw_vector<unsigned char> mOwner;   // [S] 1: the slot is its element's own copy (0: padding / ghost copy of a neighbouring strip's element)
   DevBuf<int> dNodeList;    // free 3-dof nodes no bundle updates, ascending (list variant of the node update)
   int nNodeList = 0;
@@ -284,6 +291,7 @@ struct eqd_handle {
   NodeArgs nodeArgs() const;
   ElemArgs elemArgs(int c) const;
   MarchArgs marchArgs(bool update, int part) const;
+  MarchPmlArgs marchPmlArgs(int part) const;
   FaultArgs faultArgs() const;
 };
 
@@ -434,6 +442,19 @@ MarchArgs eqd_handle::marchArgs(bool update, int part) const {   // part 0: both
   A.vel = velCur().p; A.disp = dispCur().p; A.velOut = velNext().p; A.dispOut = dispNext().p;
   A.mass = dMass.p; A.pf = C.pf.p; A.force = dForce.p;
   A.dt = p.dt; A.rdampk = p.rdampk; A.w = p.w; A.update = update ? 1 : 0; A.st = dState.p;
+  return A;
+}
+
+MarchPmlArgs eqd_handle::marchPmlArgs(int part) const {
+  const ElemClass& C = cls[CLS_MARCHP];
+  MarchPmlArgs A{};
+  A.rec = pRec.p; A.code = pCode.p;
+  A.ctaFirstA = part != 2 ? pCtaFirstA.p : nullptr;
+  A.ctaFirstB = part != 1 ? pCtaFirstB.p : nullptr;
+  A.S = (size_t)C.S; A.NnS = (size_t)NnS; A.PFS = (size_t)cls[CLS_PML].PFS; A.slotBase = (size_t)pSlotBase;
+  A.a = C.shp.p; A.ss = C.ss.p; A.lam = C.lam.p; A.mu = C.mu.p; A.det = C.det.p; A.damps = C.damps.p; A.stress = C.stress.p;
+  A.vel = velCur().p; A.disp = dispCur().p; A.pf = cls[CLS_PML].pf.p;
+  A.dt = p.dt; A.rdampk = p.rdampk; A.w = p.w;
   return A;
 }
 
@@ -605,7 +626,7 @@ void finalize(eqd_handle* h) {
       list.push_back(n);
       (onFace[n] ? listA : listB).push_back(n);
     }
-  if (h->cls[CLS_MARCH].n) {
+  if (h->cls[CLS_MARCH].n || h->cls[CLS_MARCHP].n) {
     // a node a bundle updates itself is interior to the bundle: no split node (the planner cuts where elements stop
     // sharing nodes), no rank-face node (a face bounds the sub-domain's elements)
     for (int n : list)
@@ -617,7 +638,12 @@ void finalize(eqd_handle* h) {
       parallel_range(tn.size() - std::min(tn.size(), (size_t)h->mSlotB0), [&](size_t b, size_t e) {
         for (size_t k = b + h->mSlotB0; k < e + h->mSlotB0; ++k) if (tn[k] >= 0 && onFace[tn[k]]) hit[0] = 1;
       });
-      if (hit[0]) throw ArgError("internal: a strip of the interior work list touches a rank face");
+      const raw_vector<int>& tp = h->cls[CLS_MARCHP].tnodeH;
+      if (h->cls[CLS_MARCHP].n)
+        parallel_range(tp.size() - std::min(tp.size(), (size_t)h->pSlotB0), [&](size_t b, size_t e) {
+          for (size_t k = b + h->pSlotB0; k < e + h->pSlotB0; ++k) if (tp[k] >= 0 && onFace[tp[k]]) hit[0] = 1;
+        });
+      h->mSplitOk = !hit[0];   // (a lattice the boundary criterion of the planner does not fit: sweep everything before the exchange)
     }
     std::vector<int> rest;
     rest.reserve((size_t)Nn - (size_t)h->mFused);
@@ -880,13 +906,13 @@ void launch_fault_phase(eqd_handle* h, cudaStream_t st) {
 void step_pre(eqd_handle* h, int ov, bool multi, bool last) {
   const eqd_params& P = h->p;
   cudaStream_t s = h->stream, c = h->commStream;
-  const bool marching = h->cls[CLS_MARCH].n > 0;
+  const bool marching = h->cls[CLS_MARCH].n > 0 || h->cls[CLS_MARCHP].n > 0;
   {
     Timer t(h, EQD_T_NODE);
     NodeArgs A = h->nodeArgs();
     if (h->dAccel0.p) A.accel0 = h->dAccel0.p;
     A.skipSpecial = ov ? 1 : 0;
-    if (marching && h->sweepFused) { A.list = h->dNodeList.p; A.nList = h->nNodeList; A.fusedMode = 2; }
+    if (h->cls[CLS_MARCH].n && h->sweepFused) { A.list = h->dNodeList.p; A.nList = h->nNodeList; A.fusedMode = 2; }
     launch_node_update(A, s); h->launches += h->Np > 0 ? 2 : 1;
     t.stop();
     if (ov) {
@@ -909,9 +935,14 @@ void step_pre(eqd_handle* h, int ov, bool multi, bool last) {
   }
   if (h->dAccel0.p) { CK(cudaStreamSynchronize(s)); h->dAccel0.release(); }
   auto sweep = [&](int part) {   // 0: all tiles, 1: rank-face tiles, 2: interior tiles
-    if (marching) {
+    if (h->cls[CLS_MARCH].n) {
       Timer t(h, EQD_T_MARCH);
       launch_march(h->marchArgs(!last, part), h->mGrid, s); h->launches++;
+      t.stop();
+    }
+    if (h->cls[CLS_MARCHP].n) {
+      Timer t(h, EQD_T_MARCH_PML);
+      launch_march_pml(h->marchPmlArgs(part), h->pGrid, s); h->launches++;
       t.stop();
     }
     for (int k = 0; k < 3; ++k) {
@@ -933,7 +964,7 @@ void step_pre(eqd_handle* h, int ov, bool multi, bool last) {
     if (n) { launch_assemble_special(h->nodeArgs(), list.p, n, s); h->launches++; }
     t.stop();
   };
-  const bool split = ov == 2 && multi && h->anyFace;
+  const bool split = ov == 2 && multi && h->anyFace && (!marching || h->mSplitOk);
   if (!split) {
     sweep(0);
     assemble(h->dSpecial, h->nSpecial);
@@ -946,7 +977,7 @@ void step_pre(eqd_handle* h, int ov, bool multi, bool last) {
     sweep(2);
     assemble(h->dSpecialB, h->nSpecialB);
   }
-  h->sweepFused = marching && !last;
+  h->sweepFused = h->cls[CLS_MARCH].n > 0 && !last;
   if (ov) {
     CK(cudaEventRecord(h->evElem, s));
     CK(cudaStreamWaitEvent(c, h->evElem, 0));
@@ -1193,6 +1224,31 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
       M.n = 0; M.S = 32; M.PFS = 4; M.nTiles = 0; M.nf = 3; M.nstress = 6;
       h->mGrid = 0; h->mBundles = 0; h->mFused = 0;
       const bool eligible = h->optMarch && gridOk && !h->plastic && !h->qmode && !h->body && P.C_hg == 1;
+      if (eligible) {
+        int nxg = 0;   // node planes of the grid in x: the (+,+,+) corner of every element is a lattice node (meshgen.f90:702-741)
+        {
+          std::vector<int> mx(host_threads() + 1, 0);
+          const long nynz = (long)gny * gnz;
+          parallel_range((size_t)Ne, [&](size_t b, size_t e) {
+            int m = 0;
+            for (size_t el = b; el < e; ++el) {
+              // only corners that sit on the lattice count (a split-node master has an id beyond the grid): the y+ face
+              // of the cell must be the four lattice nodes around corner 7
+              const int* c = &h->conn[8 * el];
+              const long id6 = c[6];
+              const long ix = id6 / nynz, iz = (id6 % nynz) / gny, iy = id6 % gny;
+              if (ix < 1 || iz < 1 || iy < 1) continue;
+              if (c[2] != id6 - gny || c[7] != id6 - nynz || c[3] != id6 - nynz - gny) continue;
+              m = std::max(m, (int)ix + 1);
+            }
+            static std::mutex mu;
+            std::lock_guard<std::mutex> g(mu);
+            mx[0] = std::max(mx[0], m);
+          });
+          nxg = mx[0];
+        }
+        h->mNxg = nxg;
+      }
       if (eligible && !members[CLS_REG].empty()) {
         int dev = 0, sms = 148;
         CK(cudaGetDevice(&dev));
@@ -1200,20 +1256,7 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
         const int perSm = march_ctas_per_sm();
         need(perSm > 0, "option march: the marching kernel does not fit this device");
         MarchPlan MP;
-        int nxg = 0;   // node planes of the grid in x: the (+,+,+) corner of every element is a lattice node (meshgen.f90:702-741)
-        {
-          std::vector<int> mx(host_threads() + 1, 0);
-          const long nynz = (long)gny * gnz;
-          parallel_range((size_t)Ne, [&](size_t b, size_t e) {
-            int m = 0;
-            for (size_t el = b; el < e; ++el) m = std::max(m, (int)(h->conn[8 * el + 6] / nynz) + 1);
-            static std::mutex mu;
-            std::lock_guard<std::mutex> g(mu);
-            mx[0] = std::max(mx[0], m);
-          });
-          nxg = mx[0];
-        }
-        plan_march(h->conn.data(), h->etype.data(), h->coor.data(), h->info.data(), members[CLS_REG], Nn, gny, gnz, nxg, perSm * sms,
+        plan_march(h->conn.data(), h->etype.data(), h->coor.data(), h->info.data(), members[CLS_REG], Nn, gny, gnz, h->mNxg, perSm * sms,
                    h->optMarch >= 2 ? 1 : 0, MP);
         if (MP.n > 0) {
           M.n = MP.n; M.S = MP.S; M.PFS = MP.PFS;
@@ -1243,6 +1286,54 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
       }
       h->pingpong = h->optMarch >= 2 && M.n > 0;
       lap.lap("march plan");
+      // ---- the same for the PML class (eqd_march_pml.h)
+      ElemClass& Q = h->cls[CLS_MARCHP];
+      Q.n = 0; Q.S = 32; Q.PFS = 0; Q.nTiles = 0; Q.nf = 12; Q.nstress = 21;
+      h->pGrid = 0; h->pBundles = 0;
+      if (eligible && !members[CLS_PML].empty()) {
+        int dev = 0, sms = 148;
+        CK(cudaGetDevice(&dev));
+        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const int perSm = march_pml_ctas_per_sm();
+        need(perSm > 0, "option march: the PML marching kernel does not fit this device");
+        MarchPlan MP;
+        plan_march(h->conn.data(), h->etype.data(), h->coor.data(), h->info.data(), members[CLS_PML], Nn, gny, gnz, h->mNxg, perSm * sms, 0, MP, true);
+        if (MP.n > 0) {
+          Q.n = MP.n; Q.S = MP.S; Q.PFS = MP.PFS;
+          h->pGrid = MP.grid; h->pBundles = (int)MP.rec.size();
+          h->pSlotB0 = MP.nBundlesA < (int)MP.rec.size() ? MP.rec[MP.nBundlesA].n0 : MP.PFS;
+          h->pRec.upload(MP.rec); h->pCtaFirstA.upload(MP.ctaFirstA); h->pCtaFirstB.upload(MP.ctaFirstB);
+          h->pCode.upload(MP.code); h->pSlotBundle.upload(MP.slotBundle);
+          Q.tnodeH.resize(MP.code.size());
+          parallel_range(MP.code.size(), [&](size_t b, size_t e) {
+            for (size_t k = b; k < e; ++k) Q.tnodeH[k] = MP.code[k] < 0 ? -1 : (MP.code[k] & MK_IDMASK);
+          });
+          Q.refId = std::move(MP.refId);
+          parallel_range((size_t)Q.S, [&](size_t sb, size_t se) {
+            for (size_t sl = sb; sl < se; ++sl) if (Q.refId[sl] >= 0) h->elemCode[Q.refId[sl]] = CLS_MARCH | ((int)sl << 2);   // (never matched by the scatter uploads)
+          });
+          Q.stress.alloc((size_t)21 * Q.S);
+          Q.nBoxElems = Q.n;
+          members[CLS_PML] = std::move(MP.leftover);
+          // damping profile at the centroids, as for the PML tile class
+          std::vector<double> dm(3 * (size_t)Q.S, 0.0);
+          parallel_range((size_t)Q.S, [&](size_t sb, size_t se) {
+            for (size_t sl = sb; sl < se; ++sl) {
+              const int e = Q.refId[sl];
+              if (e < 0) continue;
+              double xc[3] = {0, 0, 0};
+              for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 8; ++j) xc[i] = xc[i] + h->coor[i + 3 * (size_t)h->conn[8 * (size_t)e + j]];
+              for (int i = 0; i < 3; ++i) xc[i] = xc[i] / 8;
+              double d[3];
+              pml_elem_damps(P, xc, d);
+              for (int i = 0; i < 3; ++i) dm[(size_t)i * Q.S + sl] = d[i];
+            }
+          });
+          Q.damps.upload(dm);
+        }
+      }
+      lap.lap("PML march plan");
     }
     const int nf[3] = {3, 6, 12}, nstr[3] = {6, 6, 21};
     for (int c = 0; c < 3; ++c) {
@@ -1311,6 +1402,18 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
         C.qmem.alloc(6 * (size_t)C.S);
       }
     }
+    {
+      // the PML bundles' node slots follow the PML tiles' in one partial buffer (one class id for the node update's gather)
+      ElemClass& T = h->cls[CLS_PML];
+      ElemClass& Q = h->cls[CLS_MARCHP];
+      h->pSlotBase = 0;
+      if (Q.n) {
+        h->pSlotBase = T.n ? T.PFS : 0;
+        T.PFS = h->pSlotBase + Q.PFS;
+        T.nf = 12;
+        T.pf.alloc((size_t)12 * T.PFS);
+      }
+    }
     lap.lap("tile plan + uploads");
     // ---- node -> tile-node slots by rank, class then ascending tile id
     {
@@ -1334,7 +1437,7 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
               for (size_t sl = b; sl < e; ++sl) {
                 const int nd = tn[sl];
                 if (nd < 0 || EQD_INFO_KIND(h->info[nd]) == KIND_FIXED) continue;
-                bucket[((size_t)c * nth + w) * nth + nd / per].push_back({nd, EQD_SLOT(c, sl)});
+                bucket[((size_t)c * nth + w) * nth + nd / per].push_back({nd, c == CLS_MARCHP ? EQD_SLOT(CLS_PML, h->pSlotBase + sl) : EQD_SLOT(c, sl)});
               }
             }
           });
@@ -1440,12 +1543,12 @@ void upload_elem_state(eqd_handle* h, DevBuf<int>& dCode, const double* eleporep
     }
     // first touched inside the parallel loop (no serial zero fill of ~1 GB); padding slots get zeros there
     raw_vector<double> sg((size_t)C.nstress * C.S), qm;
-    if (h->qmode && c != CLS_PML) qm.resize(6 * (size_t)C.S);
+    if (h->qmode && c != CLS_PML && c != CLS_MARCHP) qm.resize(6 * (size_t)C.S);
     std::vector<char> badv(1, 0);
     parallel_range((size_t)C.S, [&](size_t sb, size_t se) {
       for (size_t s = sb; s < se; ++s) {
         const int base = C.refId[s] < 0 ? -1 : h->stressIdx[C.refId[s]];
-        const bool ok = base >= 0 && base + (c == CLS_PML ? 21 : 12) <= h->sizeStress;
+        const bool ok = base >= 0 && base + (c == CLS_PML || c == CLS_MARCHP ? 21 : 12) <= h->sizeStress;
         if (C.refId[s] >= 0 && !ok) badv[0] = 1;
         for (int k = 0; k < C.nstress; ++k) sg[(size_t)k * C.S + s] = ok ? stressArr[base + k] : 0.0;
         if (!qm.empty()) for (int k = 0; k < 6; ++k) qm[(size_t)k * C.S + s] = ok ? stressArr[base + 6 + k] : 0.0;
@@ -1466,8 +1569,10 @@ void alloc_elem_ops(eqd_handle* h) {
     if (h->body) C.emass.alloc(8 * (size_t)C.S);
     if (h->plastic && c != CLS_PML) { C.porep.alloc(C.S); C.pstrain.alloc(C.S); }
   }
-  ElemClass& M = h->cls[CLS_MARCH];
-  if (M.n) { M.shp.alloc(3 * (size_t)M.S); M.ss.alloc(3 * (size_t)M.S); M.lam.alloc(M.S); M.mu.alloc(M.S); M.det.alloc(M.S); }
+  for (int c : {CLS_MARCH, CLS_MARCHP}) {
+    ElemClass& M = h->cls[c];
+    if (M.n) { M.shp.alloc(3 * (size_t)M.S); M.ss.alloc(3 * (size_t)M.S); M.lam.alloc(M.S); M.mu.alloc(M.S); M.det.alloc(M.S); }
+  }
 }
 }  // namespace
 
@@ -1513,21 +1618,31 @@ int eqd_compute_elem_ops(eqd_handle* h, const double* mat, const double* elepore
       launch_tile_mass(T, C.nTiles, h->stream);
       CK(cudaStreamSynchronize(h->stream));
     }
-    DevBuf<double> emM, pmM;
-    {
-      ElemClass& M = h->cls[CLS_MARCH];
+    DevBuf<double> emM[2], pmM;
+    for (int k = 0; k < 2; ++k) {
+      ElemClass& M = h->cls[k == 0 ? CLS_MARCH : CLS_MARCHP];
       if (M.n) {
         DevBuf<int> dRef; dRef.upload(M.refId);
-        emM.alloc(8 * (size_t)M.S);
+        emM[k].alloc(8 * (size_t)M.S);
         OpsArgs A{};
         A.S = M.S; A.Ne = Ne; A.refId = dRef.p; A.conn = dConn.p; A.etype = dEtype.p; A.coor = dCoor.p; A.mat = dMat.p;
         A.w = h->p.w;
         A.shp = M.shp.p; A.phi = nullptr; A.ss = M.ss.p; A.det = M.det.p; A.lam = M.lam.p; A.mu = M.mu.p;
-        A.rho = nullptr; A.vp = nullptr; A.em = emM.p; A.badElem = dBad.p; A.compact = 1;
+        A.rho = nullptr; A.vp = nullptr; A.em = emM[k].p; A.badElem = dBad.p; A.compact = 1;
         launch_elem_ops(A, h->stream);
-        pmM.alloc(M.PFS);
         CK(cudaStreamSynchronize(h->stream));
       }
+    }
+    if (h->cls[CLS_MARCH].n) pmM.alloc(h->cls[CLS_MARCH].PFS);
+    if (h->cls[CLS_MARCHP].n) {
+      // mass partials of the PML bundles: behind the PML tiles' in one array, as their force partials are
+      DevBuf<double> both;
+      both.alloc(h->cls[CLS_PML].PFS);
+      if (pm[CLS_PML].p && h->pSlotBase) CK(cudaMemcpy(both.p, pm[CLS_PML].p, sizeof(double) * h->pSlotBase, cudaMemcpyDeviceToDevice));
+      const ElemClass& Q = h->cls[CLS_MARCHP];
+      launch_march_mass(h->pRec.p, h->pBundles, h->pSlotBundle.p, h->pCode.p, emM[1].p, (size_t)Q.S, Q.PFS, both.p + h->pSlotBase, nullptr, h->stream);
+      CK(cudaStreamSynchronize(h->stream));
+      std::swap(pm[CLS_PML].p, both.p); std::swap(pm[CLS_PML].n, both.n);
     }
     CK(cudaGetLastError());
     const int bad = dBad.download()[0];
@@ -1539,12 +1654,12 @@ int eqd_compute_elem_ops(eqd_handle* h, const double* mat, const double* elepore
     M.mass = h->dMass.p;
     if (h->cls[CLS_MARCH].n) {   // partials of the bundle surfaces first (k_node_mass sums them) ...
       const ElemClass& MC = h->cls[CLS_MARCH];
-      launch_march_mass(h->mRec.p, h->mBundles, h->mSlotBundle.p, h->mCode.p, emM.p, (size_t)MC.S, MC.PFS, pmM.p, nullptr, h->stream);
+      launch_march_mass(h->mRec.p, h->mBundles, h->mSlotBundle.p, h->mCode.p, emM[0].p, (size_t)MC.S, MC.PFS, pmM.p, nullptr, h->stream);
     }
     launch_node_mass(M, h->stream);
     if (h->cls[CLS_MARCH].n) {   // ... then the complete masses of the fused nodes, which have no slot-table entry
       const ElemClass& MC = h->cls[CLS_MARCH];
-      launch_march_mass(h->mRec.p, h->mBundles, h->mSlotBundle.p, h->mCode.p, emM.p, (size_t)MC.S, MC.PFS, pmM.p, h->dMass.p, h->stream);
+      launch_march_mass(h->mRec.p, h->mBundles, h->mSlotBundle.p, h->mCode.p, emM[0].p, (size_t)MC.S, MC.PFS, pmM.p, h->dMass.p, h->stream);
     }
     CK(cudaStreamSynchronize(h->stream));
     h->massH = h->dMass.download();
@@ -1588,27 +1703,30 @@ int eqd_set_elem_ops(eqd_handle* h, const double* eleshp, const double* eledet, 
       CK(cudaStreamSynchronize(h->stream));
     };
     // marching class: of eleshp only rows 3, 7, 14 (a_x, a_y, a_z), of ss the diagonal, no phi (eqd_box.h)
-    ElemClass& M = h->cls[CLS_MARCH];
-    DevBuf<int> dRefM;
-    if (M.n) dRefM.upload(M.refId);
-    auto march_rows = [&](DevBuf<double>& dst, int K, const int* rows, int nrows) {
-      if (!M.n) return;   // by slot, not by element: the ghost copies of an element get its rows too
-      for (int k = 0; k < nrows; ++k)
-        launch_gather_rows(tmp.p, K, dRefM.p, M.S, dst.p + (size_t)k * M.S, rows[k], h->stream);
+    DevBuf<int> dRefM[2];
+    for (int k = 0; k < 2; ++k) if (h->cls[CLS_MARCH + k].n) dRefM[k].upload(h->cls[CLS_MARCH + k].refId);
+    auto march_rows = [&](DevBuf<double> ElemClass::*member, int K, const int* rows, int nrows) {
+      for (int m = 0; m < 2; ++m) {   // by slot, not by element: the ghost copies of an element get its rows too
+        ElemClass& M = h->cls[CLS_MARCH + m];
+        if (!M.n) continue;
+        DevBuf<double>& dst = M.*member;
+        for (int k = 0; k < nrows; ++k)
+          launch_gather_rows(tmp.p, K, dRefM[m].p, M.S, dst.p + (size_t)k * M.S, rows[k], h->stream);
+      }
       CK(cudaStreamSynchronize(h->stream));
     };
     const int shpRows[3] = {BOX_AX, BOX_AY, BOX_AZ}, ssRows[3] = {0, 3, 5}, row0[1] = {0};
     spread(eleshp, 24, &ElemClass::shp, 0, 24, 0);
-    march_rows(M.shp, 24, shpRows, 3);
+    march_rows(&ElemClass::shp, 24, shpRows, 3);
     spread(phi, 32, &ElemClass::phi, 0, 32, 0);
     spread(ss, 6, &ElemClass::ss, 0, 6, 0);
-    march_rows(M.ss, 6, ssRows, 3);
+    march_rows(&ElemClass::ss, 6, ssRows, 3);
     spread(eledet, 1, &ElemClass::det, 0, 1, 0);
-    march_rows(M.det, 1, row0, 1);
+    march_rows(&ElemClass::det, 1, row0, 1);
     spread(mat + 3 * (size_t)Ne, 1, &ElemClass::lam, 0, 1, 0);  // mat(Ne,5): element index fastest
-    march_rows(M.lam, 1, row0, 1);
+    march_rows(&ElemClass::lam, 1, row0, 1);
     spread(mat + 4 * (size_t)Ne, 1, &ElemClass::mu, 0, 1, 0);
-    march_rows(M.mu, 1, row0, 1);
+    march_rows(&ElemClass::mu, 1, row0, 1);
     if (h->p.C_hg == 2) {
       spread(mat + 2 * (size_t)Ne, 1, &ElemClass::rho, 0, 1, 0);
       spread(mat, 1, &ElemClass::vp, 0, 1, 0);
@@ -1878,7 +1996,7 @@ int eqd_run(eqd_handle* h, int32_t nt_begin, int32_t nt_end) {
     for (int nt = nt_begin; nt <= nt_end; ++nt) {
       // auto: with rank neighbours the exchange and the fault solver go to the second stream; with marching strips the
       // boundary work list is swept first, so that the exchange also hides under the interior sweep
-      const int ov = !h->commStream ? 0 : h->optOverlap < 0 ? (multi ? (h->cls[CLS_MARCH].n ? 2 : 1) : 0) : h->optOverlap;
+      const int ov = !h->commStream ? 0 : h->optOverlap < 0 ? (multi ? (h->cls[CLS_MARCH].n || h->cls[CLS_MARCHP].n ? 2 : 1) : 0) : h->optOverlap;
       step_pre(h, ov, multi, nt == nt_end);
       if (multi && !ov) halo_all_nccl(h, h->stream);
       step_post(h, ov);
@@ -2022,14 +2140,15 @@ int eqd_fetch(eqd_handle* h, int32_t which, void* dst, int64_t dst_bytes) {
         need(h->opsSet, "eqd_fetch: no element operators yet");
         const int K = which == EQD_F_ELEDET ? 1 : which == EQD_F_ELESHP ? 24 : which == EQD_F_SS ? 6 : 32;
         want((size_t)K * h->Ne);
-        if (h->cls[CLS_MARCH].n) {
-          // the marching class keeps a_x, a_y, a_z and the diagonal of ss only; the rest is the closed form of eqd_box.h
-          ElemClass& C = h->cls[CLS_MARCH];
+        for (int mc : {CLS_MARCH, CLS_MARCHP}) {
+          // the marching classes keep a_x, a_y, a_z and the diagonal of ss only; the rest is the closed form of eqd_box.h
+          ElemClass& C = h->cls[mc];
+          if (!C.n) continue;
           std::vector<double> a = (which == EQD_F_ELESHP ? C.shp : which == EQD_F_SS ? C.ss : C.det).download();
           parallel_range((size_t)C.S, [&](size_t sb, size_t se) {
             for (size_t s = sb; s < se; ++s) {
               const int e = C.refId[s];
-              if (e < 0 || !h->mOwner[s]) continue;
+              if (e < 0 || (mc == CLS_MARCH && !h->mOwner[s])) continue;
               double* o = out + (size_t)K * e;
               if (which == EQD_F_ELEDET) o[0] = a[s];
               else if (which == EQD_F_ELESHP)
@@ -2131,7 +2250,7 @@ int eqd_fetch(eqd_handle* h, int32_t which, void* dst, int64_t dst_bytes) {
 int eqd_get_counts(const eqd_handle* h, int64_t* n_regular, int64_t* n_pml, int64_t* n_pairs, int64_t* launches) {
   if (!h) return EQD_ERR_ARG;
   if (n_regular) *n_regular = h->cls[CLS_REG].n + h->cls[CLS_REGX].n + h->cls[CLS_MARCH].n;
-  if (n_pml) *n_pml = h->cls[CLS_PML].n;
+  if (n_pml) *n_pml = h->cls[CLS_PML].n + h->cls[CLS_MARCHP].n;
   if (n_pairs) *n_pairs = h->nPairs;
   if (launches) *launches = h->launches;
   return EQD_OK;
@@ -2140,14 +2259,15 @@ int eqd_get_counts(const eqd_handle* h, int64_t* n_regular, int64_t* n_pml, int6
 int eqd_get_box_counts(const eqd_handle* h, int64_t* n_regular_box, int64_t* n_pml_box) {
   if (!h) return EQD_ERR_ARG;
   if (n_regular_box) *n_regular_box = h->cls[CLS_REG].nBoxElems + h->cls[CLS_REGX].nBoxElems + h->cls[CLS_MARCH].nBoxElems;
-  if (n_pml_box) *n_pml_box = h->cls[CLS_PML].nBoxElems;
+  if (n_pml_box) *n_pml_box = h->cls[CLS_PML].nBoxElems + h->cls[CLS_MARCHP].nBoxElems;
   return EQD_OK;
 }
 
-int eqd_get_march_counts(const eqd_handle* h, int64_t* out5) {
+int eqd_get_march_counts(const eqd_handle* h, int64_t* out5) {   // out5[0..7]
   if (!h || !out5) return EQD_ERR_ARG;
   out5[0] = h->cls[CLS_MARCH].n; out5[1] = h->mBundles; out5[2] = h->cls[CLS_MARCH].n ? h->cls[CLS_MARCH].PFS : 0;
   out5[3] = h->mFused; out5[4] = h->mGrid;
+  out5[5] = h->cls[CLS_MARCHP].n; out5[6] = h->pBundles; out5[7] = h->cls[CLS_MARCHP].n ? h->cls[CLS_MARCHP].PFS : 0;
   return EQD_OK;
 }
 

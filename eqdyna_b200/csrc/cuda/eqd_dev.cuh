@@ -31,7 +31,9 @@
 namespace eqd {
 
 enum { KIND_FREE3 = 0, KIND_PML12 = 1, KIND_FIXED = 2 };
-enum { CLS_REG = 0, CLS_REGX = 1, CLS_PML = 2, CLS_MARCH = 3, NCLS = 4 };   // CLS_MARCH: bundles of box elements (eqd_march.h)
+// CLS_MARCH: bundles of box elements (eqd_march.h); CLS_MARCHP: bundles of PML box elements (eqd_march_pml.h), whose
+// partial force rows live behind the PML tile class's in the same buffer (slot entries carry CLS_PML)
+enum { CLS_REG = 0, CLS_REGX = 1, CLS_PML = 2, CLS_MARCH = 3, CLS_MARCHP = 4, NCLS = 5 };
 #define EQD_INFO_KIND(i) ((i) & 3)
 #define EQD_INFO_SPECIAL(i) (((i) >> 2) & 1)
 #define EQD_INFO_SLOT(i) ((i) >> 3)

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "eqd_march.h"
+#include "eqd_march_pml.h"
 #include "eqd_march_plan.h"
 #include "eqd_par.h"
 #include "eqd_tiles.h"
@@ -49,6 +50,34 @@ __global__ void __launch_bounds__(MK_NT, 3) k_march(MarchArgs A) {
 #define MK_WAITN mk_wait_all()
 #define MK_WAITO(p) do { mk_bar_wait(&sm.bar[(p) & 1], (par >> ((p) & 1)) & 1u); par ^= 1u << ((p) & 1); } while (0)
     MARCH_BUNDLE(MK_RUN, MK_RUNNS, MK_WAITN, MK_WAITO, A, B, sm, R);
+#undef MK_RUN
+#undef MK_RUNNS
+#undef MK_WAITN
+#undef MK_WAITO
+  }
+  }
+}
+
+// PML bundles (eqd_march_pml.h): same driver
+__global__ void __launch_bounds__(MK_NT, 2) k_march_pml(MarchPmlArgs A) {
+  extern __shared__ __align__(128) unsigned char mk_smraw[];
+  MarchPmlShared& sm = *reinterpret_cast<MarchPmlShared*>(mk_smraw);
+  const int tid = threadIdx.x;
+  MarchPmlRegs R;
+  unsigned par = 0;
+  if (tid == 0) { mk_bar_init(&sm.bar[0]); mk_bar_init(&sm.bar[1]); }
+  __syncthreads();
+  for (int part = 0; part < 2; ++part) {
+  const int* first = part == 0 ? A.ctaFirstA : A.ctaFirstB;
+  if (!first) continue;
+  const int b0 = first[blockIdx.x], b1 = first[blockIdx.x + 1];
+  for (int b = b0; b < b1; ++b) {
+    const MarchBundle B = A.rec[b];
+#define MK_RUN(body) do { body; __syncthreads(); } while (0)
+#define MK_RUNNS(body) do { body; } while (0)
+#define MK_WAITN mk_wait_all()
+#define MK_WAITO(p) do { mk_bar_wait(&sm.bar[(p) & 1], (par >> ((p) & 1)) & 1u); par ^= 1u << ((p) & 1); } while (0)
+    MARCH_PML_BUNDLE(MK_RUN, MK_RUNNS, MK_WAITN, MK_WAITO, A, B, sm, R);
 #undef MK_RUN
 #undef MK_RUNNS
 #undef MK_WAITN
@@ -88,6 +117,17 @@ __global__ void __launch_bounds__(128) k_march_mass(const MarchBundle* __restric
 }
 
 size_t march_smem_bytes() { return sizeof(MarchShared) + 128; }
+size_t march_pml_smem_bytes() { return sizeof(MarchPmlShared) + 128; }
+int march_pml_ctas_per_sm() {
+  int n = 0;
+  if (cudaFuncSetAttribute(k_march_pml, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)march_pml_smem_bytes()) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_march_pml, MK_NT, march_pml_smem_bytes()) != cudaSuccess) return 0;
+  return n;
+}
+void launch_march_pml(const MarchPmlArgs& A, int grid, cudaStream_t s) {
+  if (grid <= 0) return;
+  k_march_pml<<<grid, MK_NT, march_pml_smem_bytes(), s>>>(A);
+}
 
 int march_ctas_per_sm() {
   int n = 0;
@@ -134,7 +174,7 @@ void cut_axis(int n, const std::vector<char>& seam, int cap, std::vector<std::pa
 }  // namespace
 
 void plan_march(const int* conn, const int* etype, const double* coor, const int* info, const std::vector<int>& elems, int Nn, int ny,
-                int nz, int nxg, int grid, int share, MarchPlan& P) {
+                int nz, int nxg, int grid, int share, MarchPlan& P, bool pml) {
   P = MarchPlan();
   const int n = (int)elems.size();
   const long nynz = (long)ny * nz;
@@ -164,8 +204,9 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
       if (ix < 1 || iz < 1 || iy < 1) continue;
       auto id = [&](int dx, int dz, int dy) { return (long)(ix - 1 + dx) * nynz + (long)(iz - 1 + dz) * ny + (iy - 1 + dy); };
       if (c[2] != id(1, 0, 1) || c[3] != id(0, 0, 1) || c[7] != id(0, 1, 1)) continue;
-      bool free3 = true;
-      for (int k = 0; k < 8; ++k) free3 = free3 && EQD_INFO_KIND(info[c[k]]) != KIND_PML12;
+      bool free3 = true;   // regular bundles: 3-dof nodes only; PML bundles: type-2 elements on any nodes
+      for (int k = 0; k < 8 && !pml; ++k) free3 = free3 && EQD_INFO_KIND(info[c[k]]) != KIND_PML12;
+      if (pml && etype[el] != 2) continue;
       if (!free3 || !box_element(c, coor)) continue;
       cx[j] = ix - 1; cz[j] = iz - 1; cy[j] = iy - 1;
     }
@@ -200,10 +241,11 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
   // ---- where neighbouring candidates do not share their four nodes (the fault: its + side references the
   // split-node masters): per cell, bit 0 / 1 / 2 = mismatch with the y+ / z+ / x+ neighbour
   raw_vector<unsigned char> mis(cell.size());
-  std::vector<char> seamZ(ez + 1, 0), seamY(ey + 1, 0);
+  std::vector<char> seamZ(ez + 1, 0), seamY(ey + 1, 0), edgeZ(ez + 1, 0), edgeY(ey + 1, 0);
   {
     const int nth = host_threads();
     std::vector<std::vector<char>> sz(nth, std::vector<char>(ez + 1, 0)), sy(nth, std::vector<char>(ey + 1, 0));
+    std::vector<std::vector<char>> bz2(nth, std::vector<char>(ez + 1, 0)), by2(nth, std::vector<char>(ey + 1, 0));
     std::vector<std::thread> th;
     const int per = (ex + nth - 1) / nth;
     for (int t = 0; t < nth; ++t)
@@ -215,6 +257,11 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
               unsigned char m = 0;
               if (j >= 0) {
                 const int* c = conn + 8 * (size_t)elems[j];
+                // lattice planes where the candidate set ends (a PML slab against the interior, say)
+                if (y + 1 < ey && at(x, z, y + 1) < 0) by2[t][y + 1] = 1;
+                if (y > 0 && at(x, z, y - 1) < 0) by2[t][y] = 1;
+                if (z + 1 < ez && at(x, z + 1, y) < 0) bz2[t][z + 1] = 1;
+                if (z > 0 && at(x, z - 1, y) < 0) bz2[t][z] = 1;
                 if (y + 1 < ey && at(x, z, y + 1) >= 0) {
                   const int* d = conn + 8 * (size_t)elems[at(x, z, y + 1)];
                   if (c[3] != d[0] || c[2] != d[1] || c[7] != d[4] || c[6] != d[5]) { m |= 1; sy[t][y + 1] = 1; }
@@ -233,8 +280,8 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
       });
     for (auto& x : th) x.join();
     for (int t = 0; t < nth; ++t) {
-      for (int k = 0; k <= ez; ++k) seamZ[k] |= sz[t][k];
-      for (int k = 0; k <= ey; ++k) seamY[k] |= sy[t][k];
+      for (int k = 0; k <= ez; ++k) { seamZ[k] |= sz[t][k]; edgeZ[k] |= bz2[t][k]; }
+      for (int k = 0; k <= ey; ++k) { seamY[k] |= sy[t][k]; edgeY[k] |= by2[t][k]; }
     }
   }
   lap.lap("neighbour joins");
@@ -247,6 +294,11 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
     if (cnt > 4) std::fill(seam.begin(), seam.end(), 0);
   };
   few(seamZ); few(seamY);
+  // the same for the planes where the candidate set ends: a PML slab is six cells thick, tiles that straddle its inner
+  // face would never be complete; an irregular outline (a dipping fault zone) gives many such planes and is left alone
+  few(edgeZ); few(edgeY);
+  for (int k = 0; k <= ez; ++k) seamZ[k] |= edgeZ[k];
+  for (int k = 0; k <= ey; ++k) seamY[k] |= edgeY[k];
   // ---- column tiles and their strips: runs in x of complete cross-sections whose cells share all their nodes
   std::vector<std::pair<int, int>> zt, yt;
   // base tiles are one cell short of the kernel's cross-section: room for the ghost row / column
@@ -472,7 +524,7 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
                 // a node of the first / last row or column is this strip's to report unless a neighbour tile shares it
                 const bool outZ = iz == 0 ? !s.gz : (iz == bz ? !s.hz : true), outY = iy == 0 ? !s.gy : (iy == by ? !s.hy : true);
                 const bool interior = pl > 0 && pl < B.Lx && iz > 0 && iz < bz && iy > 0 && iy < by;
-                const bool fused = interior && EQD_INFO_KIND(info[id]) == KIND_FREE3;
+                const bool fused = !pml && interior && EQD_INFO_KIND(info[id]) == KIND_FREE3;
                 if (fused) fusedT[t]++;
                 P.code[(size_t)B.n0 + (size_t)pl * MK_PN + iz * MK_NY + iy] = id | (fused ? MK_FUSED : 0) | (outZ && outY ? 0 : MK_GHOST);
               }
@@ -521,7 +573,7 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
     }
     if (!okc) {   // cannot happen on lattices the sharing rules were made for; stay correct on the others
       if (std::getenv("EQD_VERBOSE")) std::fprintf(stderr, "[eqd]   plan_march: ghost sharing inconsistent on this mesh, planning without it\n");
-      plan_march(conn, etype, coor, info, elems, Nn, ny, nz, nxg, grid, 0, P);
+      plan_march(conn, etype, coor, info, elems, Nn, ny, nz, nxg, grid, 0, P, pml);
       return;
     }
   }
@@ -566,7 +618,7 @@ extern "C" int eqd_march_emulate(int32_t Nn, int32_t Ne, const double* meshCoor,
     MarchPlan P;
     int nxg = 0;
     for (int e = 0; e < Ne; ++e) nxg = std::max(nxg, (int)(conn[8 * (size_t)e + 6] / ((long)ny * nz)) + 1);
-    plan_march(conn.data(), elemTypeArr, meshCoor, info.data(), elems, Nn, ny, nz, nxg, grid & 0xffff, (grid >> 16) & 1, P);
+    plan_march(conn.data(), elemTypeArr, meshCoor, info.data(), elems, Nn, ny, nz, nxg, grid & 0xffff, (grid >> 16) & 1, P, false);
     stats[0] = P.n; stats[1] = (int64_t)P.rec.size(); stats[2] = P.PFS; stats[3] = P.nFused; stats[4] = (int64_t)P.leftover.size();
     stats[5] = P.grid; stats[6] = P.S; stats[7] = P.nBundlesA;
     for (int e = 0; e < Ne; ++e) inBundle[e] = 0;
@@ -641,6 +693,89 @@ extern "C" int eqd_march_emulate(int32_t Nn, int32_t Ne, const double* meshCoor,
     return 0;
   } catch (const std::exception& e) {
     std::fprintf(stderr, "eqd_march_emulate: %s\n", e.what());
+    return __LINE__;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same self-check for the PML bundles (eqd_march_pml.h): plans the bundles of the type-2 elements and runs the
+// kernel's phases on the host for one step.  damps(3,Ne) is the damping profile at the element centroids,
+// stress21(21,Ne) the split stresses (slots 1..21 of every PML element, in/out); f12(12,Nn) receives the twelve
+// partial force rows summed per node.  stats[8] as eqd_march_emulate.
+extern "C" int eqd_march_pml_emulate(int32_t Nn, int32_t Ne, const double* meshCoor, const int32_t* nodeElemIdRelation,
+                                     const int32_t* elemTypeArr, const int32_t* numOfDofPerNodeArr, int32_t grid, const double* eleshp,
+                                     const double* ss, const double* eledet, const double* mat, const double* damps, double* stress21,
+                                     const double* vel, const double* disp, double dt, double rdampk, double w, double* f12,
+                                     int32_t* inBundle, int64_t* stats) {
+  using namespace eqd;
+  try {
+    std::vector<int> conn(8 * (size_t)Ne), info(Nn), elems;
+    for (size_t k = 0; k < conn.size(); ++k) conn[k] = nodeElemIdRelation[k] - 1;
+    for (int nd = 0; nd < Nn; ++nd) info[nd] = numOfDofPerNodeArr[nd] == 12 ? KIND_PML12 : KIND_FREE3;
+    for (int e = 0; e < Ne; ++e) if (elemTypeArr[e] == 2) elems.push_back(e);
+    int ny = 0, nz = 0;
+    if (!infer_grid(conn.data(), elemTypeArr, Ne, Nn, ny, nz)) return __LINE__;
+    int nxg = 0;
+    for (int e = 0; e < Ne; ++e) nxg = std::max(nxg, (int)(conn[8 * (size_t)e + 6] / ((long)ny * nz)) + 1);
+    MarchPlan P;
+    plan_march(conn.data(), elemTypeArr, meshCoor, info.data(), elems, Nn, ny, nz, nxg, grid, 0, P, true);
+    stats[0] = P.n; stats[1] = (int64_t)P.rec.size(); stats[2] = P.PFS; stats[3] = P.nFused; stats[4] = (int64_t)P.leftover.size();
+    stats[5] = P.grid; stats[6] = P.S; stats[7] = P.nBundlesA;
+    for (int e = 0; e < Ne; ++e) inBundle[e] = 0;
+    for (size_t k = 0; k < 12 * (size_t)Nn; ++k) f12[k] = 0.0;
+    if (P.n == 0) return 0;
+    if (P.nFused != 0) return __LINE__;
+    const size_t S = P.S, NnS = ((size_t)Nn + 31) / 32 * 32, PFS = P.PFS;
+    std::vector<double> a(3 * S, 0.0), s3(3 * S, 0.0), lam(S, 0.0), mu(S, 0.0), det(S, 1.0), dm(3 * S, 0.0), sg(21 * S, 0.0);
+    for (size_t s = 0; s < S; ++s) {
+      const int e = P.refId[s];
+      if (e < 0) continue;
+      inBundle[e] += 1;
+      a[s] = eleshp[BOX_AX + 24 * (size_t)e]; a[S + s] = eleshp[BOX_AY + 24 * (size_t)e]; a[2 * S + s] = eleshp[BOX_AZ + 24 * (size_t)e];
+      s3[s] = ss[0 + 6 * (size_t)e]; s3[S + s] = ss[3 + 6 * (size_t)e]; s3[2 * S + s] = ss[5 + 6 * (size_t)e];
+      lam[s] = mat[(size_t)e + 3 * (size_t)Ne]; mu[s] = mat[(size_t)e + 4 * (size_t)Ne]; det[s] = eledet[e];
+      for (int k = 0; k < 3; ++k) dm[(size_t)k * S + s] = damps[k + 3 * (size_t)e];
+      for (int k = 0; k < 21; ++k) sg[(size_t)k * S + s] = stress21[k + 21 * (size_t)e];
+    }
+    for (int e = 0; e < Ne; ++e) if (inBundle[e] > 1) return __LINE__;
+    std::vector<double> v(3 * NnS, 0.0), d(3 * NnS, 0.0), pf(12 * PFS, 0.0);
+    for (int nd = 0; nd < Nn; ++nd)
+      for (int c = 0; c < 3; ++c) { v[c * NnS + nd] = vel[c + 3 * (size_t)nd]; d[c * NnS + nd] = disp[c + 3 * (size_t)nd]; }
+    MarchPmlArgs A{};
+    A.rec = P.rec.data(); A.ctaFirstA = P.ctaFirstA.data(); A.ctaFirstB = P.ctaFirstB.data(); A.code = P.code.data();
+    A.S = S; A.NnS = NnS; A.PFS = PFS; A.slotBase = 0;
+    A.a = a.data(); A.ss = s3.data(); A.lam = lam.data(); A.mu = mu.data(); A.det = det.data(); A.damps = dm.data(); A.stress = sg.data();
+    A.vel = v.data(); A.disp = d.data(); A.pf = pf.data();
+    A.dt = dt; A.rdampk = rdampk; A.w = w;
+    std::vector<MarchPmlShared> smv(1);
+    MarchPmlShared& sm = smv[0];
+    std::vector<MarchPmlRegs> regs(MK_NT);
+    for (int cta = 0; cta < P.grid; ++cta)
+      for (int part = 0; part < 2; ++part)
+      for (int b = (part ? P.ctaFirstB : P.ctaFirstA)[cta]; b < (part ? P.ctaFirstB : P.ctaFirstA)[cta + 1]; ++b) {
+        const MarchBundle B = P.rec[b];
+#define MK_RUN(body) do { for (int tid = 0; tid < MK_NT; ++tid) { MarchPmlRegs& R = regs[tid]; (void)R; body; } } while (0)
+#define MK_WAITN ((void)0)
+#define MK_WAITO(p) ((void)0)
+        MARCH_PML_BUNDLE(MK_RUN, MK_RUN, MK_WAITN, MK_WAITO, A, B, sm, R);
+#undef MK_RUN
+#undef MK_WAITN
+#undef MK_WAITO
+      }
+    for (size_t s = 0; s < S; ++s) {
+      const int e = P.refId[s];
+      if (e < 0) continue;
+      for (int k = 0; k < 21; ++k) stress21[k + 21 * (size_t)e] = sg[(size_t)k * S + s];
+    }
+    for (size_t slot = 0; slot < PFS; ++slot) {
+      const int code = P.code[slot];
+      if (code < 0) continue;
+      const int nd = code & MK_IDMASK;
+      for (int r = 0; r < 12; ++r) f12[r + 12 * (size_t)nd] += pf[(size_t)r * PFS + slot];
+    }
+    return 0;
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "eqd_march_pml_emulate: %s\n", e.what());
     return __LINE__;
   }
 }

@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "eqd_march.h"
+#include "eqd_march_pml.h"
 #include "eqd_par.h"
 
 namespace eqd {
@@ -30,12 +31,16 @@ struct MarchPlan {
 // kinds (EQD_INFO_KIND); ny, nz from infer_grid; nxg = node planes of the grid in x (0 = unknown: no caps);
 // grid = CTAs the launch will have; share = 1: neighbouring strips share an element row / column as ghost copies so
 // that the nodes between them are interior to one of them (needs the caller to double-buffer v and d).
+// pml = true: elems are PML elements (type 2) on nodes of either kind; no node is updated by the bundles then.
 void plan_march(const int* conn, const int* etype, const double* coor, const int* info, const std::vector<int>& elems, int Nn, int ny,
-                int nz, int nxg, int grid, int share, MarchPlan& out);
+                int nz, int nxg, int grid, int share, MarchPlan& out, bool pml = false);
 
 size_t march_smem_bytes();
 int march_ctas_per_sm();   // occupancy of k_march on the current device (0: not launchable)
 void launch_march(const MarchArgs& A, int grid, cudaStream_t s);
+size_t march_pml_smem_bytes();
+int march_pml_ctas_per_sm();
+void launch_march_pml(const MarchPmlArgs& A, int grid, cudaStream_t s);
 void launch_march_mass(const MarchBundle* rec, int nBundles, const int* slotBundle, const int* code, const double* em, size_t S, int PFS,
                        double* pm, double* mass, cudaStream_t s);
 

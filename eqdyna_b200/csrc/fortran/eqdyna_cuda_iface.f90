@@ -128,12 +128,12 @@ module eqdyna_cuda_iface
         integer(c_int) function eqd_get_timing(handle, ms_slots) bind(C, name='eqd_get_timing')
             import :: c_int, c_ptr, c_double
             type(c_ptr), value :: handle
-            real(c_double), intent(out) :: ms_slots(9)
+            real(c_double), intent(out) :: ms_slots(10)
         end function
         integer(c_int) function eqd_get_march_counts(handle, out5) bind(C, name='eqd_get_march_counts')
             import :: c_int, c_ptr, c_int64_t
             type(c_ptr), value :: handle
-            integer(c_int64_t), intent(out) :: out5(5)
+            integer(c_int64_t), intent(out) :: out5(8)
         end function
         integer(c_int) function eqd_set_option(handle, key, val) bind(C, name='eqd_set_option')
             import :: c_int, c_ptr, c_char, c_int32_t
@@ -176,6 +176,16 @@ module eqdyna_cuda_iface
             integer(c_int32_t), value :: Nn, Ne, grid, update
             real(c_double) :: meshCoor(3,*), eleshp(3,8,*), ss(6,*), eledet(*), mat(*), stress6(6,*), vel(3,*), disp(3,*), mass(*), fsum(3,*)
             integer(c_int32_t) :: nodeElemIdRelation(8,*), elemTypeArr(*), numOfDofPerNodeArr(*), fusedFlag(*), inBundle(*)
+            real(c_double), value :: dt, rdampk, w
+            integer(c_int64_t), intent(out) :: stats(8)
+        end function
+        integer(c_int) function eqd_march_pml_emulate(Nn, Ne, meshCoor, nodeElemIdRelation, elemTypeArr, numOfDofPerNodeArr, grid, &
+                eleshp, ss, eledet, mat, damps, stress21, vel, disp, dt, rdampk, w, f12, inBundle, stats) &
+                bind(C, name='eqd_march_pml_emulate')
+            import :: c_int, c_int32_t, c_int64_t, c_double
+            integer(c_int32_t), value :: Nn, Ne, grid
+            real(c_double) :: meshCoor(3,*), eleshp(3,8,*), ss(6,*), eledet(*), mat(*), damps(3,*), stress21(21,*), vel(3,*), disp(3,*), f12(12,*)
+            integer(c_int32_t) :: nodeElemIdRelation(8,*), elemTypeArr(*), numOfDofPerNodeArr(*), inBundle(*)
             real(c_double), value :: dt, rdampk, w
             integer(c_int64_t), intent(out) :: stats(8)
         end function

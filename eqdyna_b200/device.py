@@ -17,13 +17,13 @@ from .host import EqdParams
 F_DISP, F_VEL, F_V1, F_FORCE, F_FRIC, F_FNFT, F_PSTRAIN, F_STRESS = 1, 2, 3, 4, 5, 6, 7, 8
 F_ONFAULT_HIST, F_OFFFAULT_HIST, F_HYPO_LOG, F_GM, F_SRC_EVOL, F_TPHIST, F_MASS, F_FNMS, F_ARN = 9, 10, 11, 12, 13, 14, 15, 16, 17
 F_ELEDET, F_ELESHP, F_SS, F_PHI = 18, 19, 20, 21
-T_TOTAL, T_NODE, T_ELEM, T_ASSEMBLE, T_HALO, T_FAULT, T_ELEM_PML, T_ELEM_REGX, T_MARCH, T_NSLOTS = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
+T_TOTAL, T_NODE, T_ELEM, T_ASSEMBLE, T_HALO, T_FAULT, T_ELEM_PML, T_ELEM_REGX, T_MARCH, T_MARCH_PML, T_NSLOTS = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 
 EXPORTS = [
     "eqd_create", "eqd_destroy", "eqd_last_error", "eqd_set_mesh", "eqd_set_elem_ops", "eqd_compute_elem_ops", "eqd_set_nodal",
     "eqd_set_fault", "eqd_set_halo", "eqd_set_stations", "eqd_get_unique_id", "eqd_set_comm", "eqd_sum_shared",
     "eqd_run", "eqd_run_group", "eqd_fetch", "eqd_get_counts", "eqd_get_timing", "eqd_set_option", "eqd_plan_check",
-    "eqd_box_check", "eqd_get_box_counts", "eqd_plan_bank_model", "eqd_march_emulate", "eqd_get_march_counts",
+    "eqd_box_check", "eqd_get_box_counts", "eqd_plan_bank_model", "eqd_march_emulate", "eqd_get_march_counts", "eqd_march_pml_emulate",
 ]
 
 _lib = None
@@ -205,15 +205,16 @@ class Domain:
 
     def march_counts(self):
         """Marching class (option "march"): elements in bundles, bundles, node slots, fused nodes, CTAs."""
-        a = (C.c_int64 * 5)()
+        a = (C.c_int64 * 8)()
         lib().eqd_get_march_counts(self._h, a)
-        return {"elements": a[0], "bundles": a[1], "node_slots": a[2], "fused_nodes": a[3], "grid": a[4]}
+        return {"elements": a[0], "bundles": a[1], "node_slots": a[2], "fused_nodes": a[3], "grid": a[4],
+                "pml_elements": a[5], "pml_bundles": a[6], "pml_node_slots": a[7]}
 
     def timing(self):
         t = (C.c_double * T_NSLOTS)()
         lib().eqd_get_timing(self._h, t)
         return {"total": t[T_TOTAL], "node": t[T_NODE], "elem": t[T_ELEM], "assemble": t[T_ASSEMBLE],
-                "halo": t[T_HALO], "fault": t[T_FAULT], "elem_pml": t[T_ELEM_PML], "elem_regx": t[T_ELEM_REGX], "march": t[T_MARCH]}
+                "halo": t[T_HALO], "fault": t[T_FAULT], "elem_pml": t[T_ELEM_PML], "elem_regx": t[T_ELEM_REGX], "march": t[T_MARCH], "march_pml": t[T_MARCH_PML]}
 
     def fetch(self, which, shape, dtype=np.float64):
         out = np.zeros(shape, dtype=dtype, order="F")

@@ -96,7 +96,8 @@ enum {
 enum {
   EQD_T_TOTAL = 0, EQD_T_NODE = 1, EQD_T_ELEM = 2 /* regular hex/wedge kernel */, EQD_T_ASSEMBLE = 3,
   EQD_T_HALO = 4, EQD_T_FAULT = 5, EQD_T_ELEM_PML = 6, EQD_T_ELEM_REGX = 7,
-  EQD_T_MARCH = 8 /* marching kernel: box bundles, element sweep + assembly + update of their inner nodes */, EQD_T_NSLOTS = 9
+  EQD_T_MARCH = 8 /* marching kernel: box bundles, element sweep + assembly + update of their inner nodes */,
+  EQD_T_MARCH_PML = 9 /* marching kernel of the PML bundles */, EQD_T_NSLOTS = 10
 };
 
 /* -- lifecycle ------------------------------------------------------------- */
@@ -173,9 +174,9 @@ int eqd_get_counts(const eqd_handle* h, int64_t* n_regular, int64_t* n_pml,
                    int64_t* n_pairs, int64_t* launches);
 /* elements swept with closed-form box operators (option "box"); valid after the first run */
 int eqd_get_box_counts(const eqd_handle* h, int64_t* n_regular_box, int64_t* n_pml_box);
-/* marching class (option "march"): out5 = elements in bundles, bundles, node slots, nodes the bundles update
- * themselves, CTAs of the persistent launch */
-int eqd_get_march_counts(const eqd_handle* h, int64_t* out5);
+/* marching classes (option "march"): out8 = elements in bundles, bundles, node slots, nodes the bundles update
+ * themselves, CTAs of the persistent launch; PML elements in bundles, PML bundles, PML node slots */
+int eqd_get_march_counts(const eqd_handle* h, int64_t* out8);
 int eqd_get_timing(const eqd_handle* h, double* ms_slots /*[EQD_T_NSLOTS]*/);
 /* options: "timing" 1 = CUDA-event timing of every phase (2 = also reset the
  * accumulated slots and the launch counter); "overlap" -1 auto (default) / 0 serial
@@ -243,6 +244,15 @@ int eqd_march_emulate(int32_t Nn, int32_t Ne, const double* meshCoor, const int3
                       const double* ss, const double* eledet, const double* mat, double* stress6, double* vel, double* disp,
                       const double* mass, double dt, double rdampk, double w, int32_t update, double* fsum,
                       int32_t* fusedFlag, int32_t* inBundle, int64_t* stats);
+
+/* The same for the PML bundles (eqd_march_pml.h): damps(3,Ne) = damping profile at the element centroids
+ * (assembleGlobalKU.f90:130-213), stress21(21,Ne) in/out = the 21 stresses of every PML element, f12(12,Nn) out = the
+ * twelve split-field force rows (assembleGlobalKU.f90:328-344) summed per node over the bundle elements.           */
+int eqd_march_pml_emulate(int32_t Nn, int32_t Ne, const double* meshCoor, const int32_t* nodeElemIdRelation,
+                          const int32_t* elemTypeArr, const int32_t* numOfDofPerNodeArr, int32_t grid, const double* eleshp,
+                          const double* ss, const double* eledet, const double* mat, const double* damps, double* stress21,
+                          const double* vel, const double* disp, double dt, double rdampk, double w, double* f12,
+                          int32_t* inBundle, int64_t* stats);
 
 #ifdef __cplusplus
 }

@@ -29,7 +29,7 @@ CASES = [
 def test_marching_kernel_matches_oracle(case, np_xyz, nstep, chunks, cops, what):
     wg = parity.build_world(case, np_xyz, nstep)
     wo = parity.build_world(case, np_xyz, nstep)
-    doms = parity.run_gpu(wg, options=OPTS, pre_options={"march": 2}, chunks=chunks, compute_ops=cops)
+    doms = parity.run_gpu(wg, options=OPTS, pre_options={"march": 1}, chunks=chunks, compute_ops=cops)
     parity.run_oracle(wo)
     res = parity.compare_worlds(wg, wo)
     parity.assert_parity(res)
@@ -45,14 +45,16 @@ def test_march_timing_slot_and_determinism():
     for chunks in (1, 1, 3):
         w = parity.build_world("test.tpv104", (1, 1, 1), n)
         from eqdyna_b200 import device as dev
-        d = dev.Domain(w.view(0), options={"march": 2})
+        d = dev.Domain(w.view(0), options={"march": 1})
         for k, v in OPTS.items():
             d.set_option(k, v)
         d.set_option("timing", 1)
         b = np.linspace(0, n, chunks + 1).astype(int)
         for a, e in zip(b[:-1], b[1:]):
             d.run(a + 1, e)
-        assert d.timing()["march"] > 0.0
+        assert d.timing()["march"] > 0.0 and d.timing()["march_pml"] > 0.0
+        mc = d.march_counts()
+        assert mc["elements"] > 0 and mc["pml_elements"] > 0.8 * d.counts()["pml"]
         d.fetch_into_view()
         runs.append(w)
     a, b, c = (w.view(0) for w in runs)
@@ -71,10 +73,11 @@ def test_march_and_tiles_agree_to_rounding():
             assert parity.rel_l2(getattr(b.view(0), name), getattr(a.view(0), name)) < 1e-9, (march, name)
 
 
-def test_march_without_ghost_sharing_matches_oracle():
-    """option march = 1 (strips do not overlap, v and d updated in place)"""
-    wg = parity.build_world("test.tpv104", (2, 2, 1), 60)
-    wo = parity.build_world("test.tpv104", (2, 2, 1), 60)
-    parity.run_gpu(wg, options=OPTS, pre_options={"march": 1}, chunks=2)
+@pytest.mark.parametrize("case,np_xyz,nstep", [("test.tpv104", (2, 2, 1), 60), ("test.tpv8", (1, 1, 1), 40), ("test.tpv36", (2, 2, 2), 40)])
+def test_march_with_ghost_sharing_matches_oracle(case, np_xyz, nstep):
+    """option march = 2: neighbouring strips share ghost rows / columns, v and d double-buffered"""
+    wg = parity.build_world(case, np_xyz, nstep)
+    wo = parity.build_world(case, np_xyz, nstep)
+    parity.run_gpu(wg, options=OPTS, pre_options={"march": 2}, chunks=2)
     parity.run_oracle(wo)
     parity.assert_parity(parity.compare_worlds(wg, wo))

@@ -118,3 +118,97 @@ def test_marching_kernel_phases_on_the_host(case, grid, min_cover, min_fused):
         else:
             assert np.array_equal(vel, vel0) and np.array_equal(disp, disp0)
     w.close()
+
+
+def _emulate_pml(v, vel, disp, stress21, damps, dt, grid):
+    from eqdyna_b200 import device
+    L = device.lib()
+    L.eqd_march_pml_emulate.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 4 + [C.c_int32] + [C.c_void_p] * 8 + [C.c_double] * 3 + \
+                                      [C.c_void_p] * 3
+    P = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+    f12 = np.zeros((12, v.Nn), order="F")
+    inb = np.zeros(v.Ne, dtype=np.int32)
+    st = np.zeros(8, dtype=np.int64)
+    rc = L.eqd_march_pml_emulate(v.Nn, v.Ne, P(v.meshCoor), P(v.nodeElemIdRelation), P(v.elemTypeArr), P(v.numOfDofPerNodeArr), grid,
+                                 P(v.eleshp), P(v.ss), P(v.eledet), P(v.mat), P(damps), P(stress21), P(vel), P(disp),
+                                 dt, v.params.rdampk, v.params.w, P(f12), P(inb), P(st))
+    assert rc == 0, "eqd_march_pml_emulate failed at eqd_march.cu:%d" % rc
+    return f12, inb.astype(bool), st
+
+
+def _reference_pml(v, E, vel, disp, stress21, damps, dt):
+    """calcPMLElemKU (assembleGlobalKU.f90:215-344) + hrglss.f90:20-54 of elements E, from the stored operators"""
+    conn = v.nodeElemIdRelation[:, E] - 1
+    shp = v.eleshp[:, :, E]
+    phi = v.phi[:, :, E]
+    ss = v.ss[:, E]
+    lam, mu, det = v.mat[E, 3], v.mat[E, 4], v.eledet[E]
+    rk, w = v.params.rdampk, v.params.w
+    ve = vel[:, conn]                                              # (3,8,nE)
+    le = disp[:, conn] + rk * ve
+    D = lambda d, c: np.einsum("ie,ie->e", shp[d], ve[c])        # noqa: E731  D_d v_c
+    l2m = lam + 2 * mu
+    s = stress21[:, E].copy()
+    rdt = 1.0 / dt
+    dm = damps[:, E]
+
+    def upd(k, cf, Dv, a):
+        s[k] = (cf * Dv + (rdt - dm[a] / 2) * s[k]) / (rdt + dm[a] / 2)
+    Dxx, Dyy, Dzz = D(0, 0), D(1, 1), D(2, 2)
+    upd(0, l2m, Dxx, 0); upd(1, lam, Dyy, 1); upd(2, lam, Dzz, 2)
+    upd(3, lam, Dxx, 0); upd(4, l2m, Dyy, 1); upd(5, lam, Dzz, 2)
+    upd(6, lam, Dxx, 0); upd(7, lam, Dyy, 1); upd(8, l2m, Dzz, 2)
+    upd(9, mu, D(0, 1), 0); upd(10, mu, D(1, 0), 1)
+    upd(11, mu, D(0, 2), 0); upd(12, mu, D(2, 0), 2)
+    upd(13, mu, D(1, 2), 1); upd(14, mu, D(2, 1), 2)
+    sxx, syy, szz = s[0] + s[1] + s[2], s[3] + s[4] + s[5], s[6] + s[7] + s[8]
+    sxy, sxz, syz = s[9] + s[10], s[11] + s[12], s[13] + s[14]
+    sr = np.stack([Dxx, Dyy, Dzz, D(2, 1) + D(1, 2), D(2, 0) + D(0, 2), D(1, 0) + D(0, 1)])
+    rate = np.stack([l2m * sr[0] + lam * sr[1] + lam * sr[2], lam * sr[0] + l2m * sr[1] + lam * sr[2],
+                     lam * sr[0] + lam * sr[1] + l2m * sr[2], mu * sr[3], mu * sr[4], mu * sr[5]])
+    s0 = s[15:21] + rk * rate
+    detw = det * w
+    phid = np.einsum("ime,cie->mce", phi, le)
+    S = np.array([[0, 1, 2], [1, 3, 4], [2, 4, 5]])
+    hv = np.stack([np.stack([sum(ss[S[c, k]] * phid[m, k] for k in range(3)) for c in range(3)]) for m in range(4)])
+    f = np.zeros((12, vel.shape[1]))
+    for i in range(8):
+        s1, s2, s3 = shp[0, i], shp[1, i], shp[2, i]
+        rows = [s1 * sxx, s2 * sxy, s3 * sxz, s1 * sxy, s2 * syy, s3 * syz, s1 * sxz, s2 * syz, s3 * szz,
+                s1 * s0[0] + s3 * s0[4] + s2 * s0[5], s2 * s0[1] + s3 * s0[3] + s1 * s0[5], s3 * s0[2] + s2 * s0[3] + s1 * s0[4]]
+        hg = np.einsum("me,mce->ce", phi[i], hv)
+        for r in range(12):
+            val = -detw * rows[r]
+            if r >= 9:
+                val = val - hg[r - 9]
+            np.add.at(f[r], conn[i], val)
+    return f, s
+
+
+@pytest.mark.parametrize("case,grid,min_cover", [("test.tpv104", 296, 0.9), ("test.tpv8", 17, 0.9)], ids=["tpv104-296ctas", "tpv8-17ctas"])
+def test_pml_marching_kernel_phases_on_the_host(case, grid, min_cover):
+    """eqd_march_pml.h on the CPU: the 15 split stresses, the twelve force rows in their one-number-per-column form and
+    the regular + hourglass rows, against calcPMLElemKU evaluated element by element from the stored operators."""
+    w = parity.build_world(case, (1, 1, 1), 2)
+    v = w.view(0)
+    rng = np.random.default_rng(11)
+    vel = np.asfortranarray(rng.standard_normal((3, v.Nn)))
+    disp = np.asfortranarray(rng.standard_normal((3, v.Nn)) * 1e-2)
+    stress0 = np.asfortranarray(rng.standard_normal((21, v.Ne)) * 1e6)
+    damps = np.asfortranarray(rng.uniform(0.0, 30.0, (3, v.Ne)))
+    dt = 0.004
+    stress = stress0.copy(order="F")
+    f12, inb, st = _emulate_pml(v, vel, disp, stress, damps, dt, grid)
+    E = np.nonzero(inb)[0]
+    npml = int((v.elemTypeArr == 2).sum())
+    assert st[0] == len(E) >= min_cover * npml and st[0] + st[4] == npml and st[3] == 0
+    assert np.all(v.elemTypeArr[E] == 2)
+    fref, sref = _reference_pml(v, E, vel, disp, stress0, damps, dt)
+    assert np.abs(fref).max() > 0
+    for r in range(12):
+        assert np.abs(f12[r] - fref[r]).max() <= 1e-12 * np.abs(fref).max(), r
+    assert np.abs(stress[:15, E] - sref[:15]).max() <= 1e-13 * np.abs(sref[:15]).max()
+    assert np.array_equal(stress[15:, E], stress0[15:, E])           # the regular slots are read, never written
+    out = np.ones(v.Ne, bool); out[E] = False
+    assert np.array_equal(stress[:, out], stress0[:, out])
+    w.close()
