@@ -4,7 +4,7 @@
 // driver_cuda.f90 for an image without a Fortran compiler:
 //
 //   eqdyna_host <case_dir> [-o out_dir] [-np npx npy npz] [-nstep n] [-device-ops]
-//               [-box 0|1|2] [-box-compact 0|1] [-chunk n] [-gm]
+//               [-box 0|1|2] [-box-compact 0|1] [-march 0|1|2] [-chunk n] [-gm]
 //
 //   1. libeqdyna_host.so  reads b*.txt + on_fault_vars_input.bin, builds every
 //      sub-domain (mesh4num, meshgen, on-fault load, assembleGlobalMass, init_vel)
@@ -38,13 +38,13 @@ double now() {
 struct Opts {
   std::string dir, out = ".";
   int np[3] = {0, 0, 0};
-  int nstep = 0, deviceOps = 0, box = 0, boxCompact = 0, chunk = 100, gm = 0;
+  int nstep = 0, deviceOps = 0, box = 0, boxCompact = 0, chunk = 100, gm = 0, march = 0;
 };
 
 int usage() {
   std::fprintf(stderr,
                "usage: eqdyna_host <case_dir> [-o out_dir] [-np npx npy npz] [-nstep n] [-device-ops]\n"
-               "                   [-box 0|1|2] [-box-compact 0|1] [-chunk n] [-gm]\n");
+               "                   [-box 0|1|2] [-box-compact 0|1] [-march 0|1|2] [-chunk n] [-gm]\n");
   return EQD_ERR_ARG;
 }
 
@@ -70,6 +70,7 @@ int fail(eqd_handle* h, const char* what, int rc) {
 
 // the eqd_set_* sequence of driver_cuda.f90 for one sub-domain
 int upload(eqd_handle* h, const eqh_view& v, const Opts& o) {
+  DEVCK(h, eqd_set_option(h, "march", o.march));   // shapes the element classes: before eqd_set_mesh
   DEVCK(h, eqd_set_mesh(h, v.Nn, v.Ne, v.Neq, v.sizeEq, v.meshCoor, v.nodeElemIdRelation, v.elemTypeArr, v.numOfDofPerNodeArr,
                         v.eqNumStartIndexLoc, v.eqNumIndexArr, v.stressCompIndexArr, v.sizeStress));
   if (o.deviceOps) {
@@ -133,6 +134,7 @@ int main(int argc, char** argv) {
     else if (a == "-device-ops") o.deviceOps = 1;
     else if (a == "-box" && need(1)) o.box = std::atoi(argv[++i]);
     else if (a == "-box-compact" && need(1)) o.boxCompact = std::atoi(argv[++i]);
+    else if (a == "-march" && need(1)) o.march = std::atoi(argv[++i]);
     else if (a == "-chunk" && need(1)) o.chunk = std::max(1, std::atoi(argv[++i]));
     else if (a == "-gm") o.gm = 1;
     else if (!a.empty() && a[0] != '-' && o.dir.empty()) o.dir = a;

@@ -177,6 +177,9 @@ VARIANTS = {
                                           ("par.dt = 0.5*par.dx/par.vp", "par.dt = 0.008")]),
     "bench.tpv104_200m": ("test.tpv104", [("par.term = 5.", "par.term = 15."), ("par.dx = 500.", "par.dx = 200."),
                                           ("par.dt = 0.5*par.dx/par.vp", "par.dt = 0.016")]),
+    # TPV36 (15-degree thrust, wedges) at finer resolutions than the shipped 500 m (README.md:5,86 quotes 50 m on 512 cores)
+    "bench.tpv36_100m": ("test.tpv36", [("par.dx   = 500.", "par.dx   = 100.")]),
+    "bench.tpv36_200m": ("test.tpv36", [("par.dx   = 500.", "par.dx   = 200.")]),
 }
 
 if __name__ == "__main__":

@@ -2,6 +2,7 @@
 """Turn ncu outputs into the tracked summaries under profiles/.
 
   summarize_profiles.py TAG LAUNCHES.csv FULL_RAW.csv [N_REGULAR N_PML N_NODES [N_PML_NODES]]
+  summarize_profiles.py TAG LAUNCHES.csv FULL_RAW.csv kernel=work_items ... [case=bench.tpv104_100m]
 
 LAUNCHES.csv: `ncu --metrics gpu__time_duration.sum --clock-control none --csv` launch list.
 FULL_RAW.csv: `ncu -i prof.ncu-rep --page raw --csv` of a `--set full` capture.
@@ -89,11 +90,20 @@ def full(path, counts):
 def main():
     tag, lpath, fpath = sys.argv[1:4]
     counts = {}
-    if len(sys.argv) >= 7:
-        counts = {"k_tile_reg": int(sys.argv[4]), "k_tile_pml": int(sys.argv[5]), "k_node_update3": int(sys.argv[6])}
-        if len(sys.argv) >= 8:
-            counts["k_node_update12"] = int(sys.argv[7])
-    s = {"tag": tag, "launch_list": launches(lpath), **full(fpath, counts)}
+    case = None
+    rest = sys.argv[4:]
+    if rest and all("=" in a for a in rest):       # kernel=work_items ... [case=NAME]
+        for a in rest:
+            k, v = a.split("=", 1)
+            if k == "case":
+                case = v
+            else:
+                counts[k] = int(v)
+    elif len(rest) >= 3:
+        counts = {"k_tile_reg": int(rest[0]), "k_tile_pml": int(rest[1]), "k_node_update3": int(rest[2])}
+        if len(rest) >= 4:
+            counts["k_node_update12"] = int(rest[3])
+    s = {"tag": tag, "case": case, "launch_list": launches(lpath), **full(fpath, counts)}
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     for name in ("ncu_summary_%s.json" % tag, "ncu_summary.json"):
         json.dump(s, open(os.path.join(ROOT, "profiles", name), "w"), indent=1)
