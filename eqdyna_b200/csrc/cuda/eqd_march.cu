@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(128) k_march_mass(const MarchBundle* __restric
   const int b = slotBundle[slot / MK_PN];   // node planes never straddle bundles: one entry per plane
   if (b < 0) return;
   const MarchBundle B = rec[b];
-  const int k = slot - B.n0, pl = k / MK_PN, i = k - pl * MK_PN, iz = i / MK_NY, iy = i - iz * MK_NY;
+  const int k = slot - B.n0, pl = k / MK_PN, i = k - pl * MK_PN, rowlen = mk_rowlen(B), iz = i / rowlen, iy = i - iz * rowlen;
   const int c = code[slot];
   if (c < 0 || (c & MK_GHOST)) { pm[slot] = 0.0; return; }
   const int bz = B.shape & 0xff, by = (B.shape >> 8) & 0xff;
@@ -154,7 +154,7 @@ namespace {
 // rectangle is a GHOST copy of the last row / column of the tile before (which owns those elements); hz / hy: the
 // tile after took such a copy of this strip's last row / column, so this strip leaves the nodes of its last node
 // row / column to it.  tz, ty: tile of the base (ghost-free) tiling.
-struct Strip { int x0, len, z0, bz, y0, by, tz, ty; unsigned char gz, gy, hz, hy; };
+struct Strip { int x0, len, z0, bz, y0, by, tz, ty; unsigned char gz, gy, hz, hy, orient; };
 
 // nearly equal parts of at most `cap` cells between consecutive seams of one lattice axis
 void cut_axis(int n, const std::vector<char>& seam, int cap, std::vector<std::pair<int, int>>& out) {
@@ -300,18 +300,34 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
   for (int k = 0; k <= ez; ++k) seamZ[k] |= edgeZ[k];
   for (int k = 0; k <= ey; ++k) seamY[k] |= edgeY[k];
   // ---- column tiles and their strips: runs in x of complete cross-sections whose cells share all their nodes
-  std::vector<std::pair<int, int>> zt, yt;
+  std::vector<std::pair<int, int>> zt, yt, ztB;
   // base tiles are one cell short of the kernel's cross-section: room for the ghost row / column
   cut_axis(ez, seamZ, share ? MK_BZ - 1 : MK_BZ, zt);
   cut_axis(ey, seamY, share ? MK_BY - 1 : MK_BY, yt);
+  // PML bundles: a y segment no wider than 7 cells (a slab) is swept with the node plane turned -- 16 rows of 8 nodes, up
+  // to 15 x 7 element columns -- so that the threads are filled along z instead
+  std::vector<char> turned(yt.size(), 0);
+  if (pml && !share) {
+    cut_axis(ez, seamZ, MK_BY, ztB);
+    for (size_t k = 0; k < yt.size(); ++k) turned[k] = yt[k].second <= MK_BZ && ztB.size() < zt.size();
+  }
+  struct TileRef { int zi, yi; };
+  std::vector<TileRef> tiles;
+  if (share || !pml) {
+    for (size_t zi = 0; zi < zt.size(); ++zi) for (size_t yi = 0; yi < yt.size(); ++yi) tiles.push_back({(int)zi, (int)yi});   // index = zi*nty + yi
+  } else {
+    for (size_t yi = 0; yi < yt.size(); ++yi)
+      for (size_t zi = 0; zi < (turned[yi] ? ztB.size() : zt.size()); ++zi) tiles.push_back({(int)zi, (int)yi});
+  }
   std::vector<Strip> strips;
   {
-    const int nT = (int)(zt.size() * yt.size());
+    const int nT = (int)tiles.size();
     std::vector<std::vector<Strip>> per(nT);
     parallel_range((size_t)nT, [&](size_t tb, size_t te) {
       for (size_t t = tb; t < te; ++t) {
-        const auto& Z = zt[t / yt.size()];
-        const auto& Y = yt[t % yt.size()];
+        const unsigned char orient = turned[tiles[t].yi];
+        const auto& Z = (orient ? ztB : zt)[tiles[t].zi];
+        const auto& Y = yt[tiles[t].yi];
         const int z1 = Z.first + Z.second, y1 = Y.first + Y.second;
         int run0 = -1;
         for (int x = 0; x <= ex; ++x) {
@@ -326,7 +342,7 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
             }
           if (run0 >= 0 && (!full || !joined)) {
             if (x - run0 >= MK_MINLX)
-              per[t].push_back({run0, x - run0, Z.first, Z.second, Y.first, Y.second, (int)(t / yt.size()), (int)(t % yt.size()), 0, 0, 0, 0});
+              per[t].push_back({run0, x - run0, Z.first, Z.second, Y.first, Y.second, tiles[t].zi, tiles[t].yi, 0, 0, 0, 0, orient});
             run0 = -1;
           }
           if (full && run0 < 0) run0 = x;
@@ -443,7 +459,7 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
         if (ci < cutpos.size() && cutpos[ci] < base + q.len) end = (int)(cutpos[ci] - base);
         MarchBundle B{};
         B.Lx = end - a;
-        B.shape = st.bz | (st.by << 8);
+        B.shape = st.bz | (st.by << 8) | ((int)st.orient << 16);
         B.e0 = st.x0 + q.a + a;   // provisional: lattice x of the first plane (replaced by the slot below)
         B.n0 = q.strip;           // provisional: strip
         P.rec.push_back(B);
@@ -493,7 +509,7 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
         for (int b = next.fetch_add(1); b < nB; b = next.fetch_add(1)) {
           const MarchBundle& B = P.rec[b];
           const Strip& s = strips[stripOf[b]];
-          const int bz = s.bz, by = s.by, x0 = xOf[b];
+          const int bz = s.bz, by = s.by, x0 = xOf[b], rowlen = mk_rowlen(B);
           for (int p = 0; p < B.Lx; ++p)
             for (int z = 0; z < bz; ++z)
               for (int y = 0; y < by; ++y) {
@@ -526,7 +542,7 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
                 const bool interior = pl > 0 && pl < B.Lx && iz > 0 && iz < bz && iy > 0 && iy < by;
                 const bool fused = !pml && interior && EQD_INFO_KIND(info[id]) == KIND_FREE3;
                 if (fused) fusedT[t]++;
-                P.code[(size_t)B.n0 + (size_t)pl * MK_PN + iz * MK_NY + iy] = id | (fused ? MK_FUSED : 0) | (outZ && outY ? 0 : MK_GHOST);
+                P.code[(size_t)B.n0 + (size_t)pl * MK_PN + iz * rowlen + iy] = id | (fused ? MK_FUSED : 0) | (outZ && outY ? 0 : MK_GHOST);
               }
           }
         }
@@ -551,7 +567,7 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
       for (int pl = 0; pl <= B.Lx; ++pl)
         for (int iz = 0; iz <= bz; ++iz)
           for (int iy = 0; iy <= by; ++iy) {
-            const int c = P.code[(size_t)B.n0 + (size_t)pl * MK_PN + iz * MK_NY + iy];
+            const int c = P.code[(size_t)B.n0 + (size_t)pl * MK_PN + iz * mk_rowlen(B) + iy];
             if (c < 0 || (c & MK_GHOST)) continue;
             const int nx_ = (pl > 0) + (pl < B.Lx), nz_ = (iz > 0) + (iz < bz), ny_ = (iy > 0) + (iy < by);
             got[c & MK_IDMASK] += nx_ * nz_ * ny_;

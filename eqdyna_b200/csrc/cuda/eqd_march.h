@@ -56,7 +56,9 @@ struct MarchBundle {
                // packed (no slots for inactive columns), so an operator row of a plane is one contiguous, 16-byte aligned run
   int n0;      // first node slot: slot = n0 + p*MK_PN + iz*MK_NY + iy
   int Lx;      // elements along x (node planes 0..Lx)
-  int shape;   // bz | by << 8: active columns cz < bz <= MK_BZ, cy < by <= MK_BY
+  int shape;   // bz | by << 8 | orient << 16: active columns cz < bz, cy < by.  orient 0: the node plane is MK_NZ rows of MK_NY
+               // nodes (bz <= 7, by <= 15); orient 1 (PML bundles only): MK_NY rows of MK_NZ nodes (bz <= 15, by <= 7), for slabs
+               // that are thin in y
 };
 
 struct MarchArgs {
@@ -148,6 +150,7 @@ EQD_HD void mk_nan(StepState* st, int node) {
 EQD_HD int mk_bz(const MarchBundle& B) { return B.shape & 0xff; }
 EQD_HD int mk_by(const MarchBundle& B) { return (B.shape >> 8) & 0xff; }
 EQD_HD int mk_es(const MarchBundle& B) { return (mk_bz(B) * mk_by(B) + 1) & ~1; }   // element slots per plane
+EQD_HD int mk_rowlen(const MarchBundle& B) { return ((B.shape >> 16) & 1) ? MK_NZ : MK_NY; }   // nodes per row of the node plane
 EQD_HD const double* mk_op_row(const MarchArgs& A, int r) {
   if (r < 3) return A.a + (size_t)r * A.S;
   if (r < 6) return A.ss + (size_t)(r - 3) * A.S;

@@ -93,8 +93,9 @@ EQD_HD void mp_issue_ops(const MarchPmlArgs& A, const MarchBundle& B, MarchPmlSh
   if (tid < MP_OPROWS)
     mk_bulk(sm.ops[p & 1][tid], mp_op_row(A, tid) + (size_t)B.e0 + (size_t)p * es, (unsigned)(es * sizeof(double)), bar);
 }
-// this thread's column in the bordered column array
-EQD_HD int mp_col(int tid) { return (tid / MK_NY + 1) * (MK_NY + 1) + (tid % MK_NY) + 1; }
+// this thread's column in the bordered column array (ny = nodes per row of the bundle's node plane: 16 or 8)
+EQD_HD int mp_col(int tid, int ny) { return (tid / ny + 1) * (ny + 1) + (tid % ny) + 1; }
+EQD_HD bool mp_active(const MarchBundle& B, int tid, int ny) { return (tid / ny) < mk_bz(B) && (tid % ny) < mk_by(B); }
 
 EQD_HD void mp_phase_begin(const MarchPmlArgs& A, const MarchBundle& B, MarchPmlShared& sm, MarchPmlRegs& R, int tid) {
 #pragma unroll
@@ -104,17 +105,18 @@ EQD_HD void mp_phase_begin(const MarchPmlArgs& A, const MarchBundle& B, MarchPml
   for (int i = tid; i < MP_COLN; i += MK_NT)
 #pragma unroll
     for (int r = 0; r < 9; ++r) sm.col[r][i] = 0.0;
-  if (!mk_active(B, tid)) return;
+  const int ny = mk_rowlen(B);
+  if (!mp_active(B, tid, ny)) return;
   double(*pl)[MK_PN] = sm.ring[0];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const double v0 = pl[c][tid], v1 = pl[c][tid + 1], v2 = pl[c][tid + MK_NY], v3 = pl[c][tid + MK_NY + 1];
+    const double v0 = pl[c][tid], v1 = pl[c][tid + 1], v2 = pl[c][tid + ny], v3 = pl[c][tid + ny + 1];
     {
       MK_FACE_SUMS(v0, v1, v2, v3)
       R.wv[0][c] = s0_ + s1_; R.wv[1][c] = d0_ + d1_; R.wv[2][c] = s1_ - s0_;
     }
     const double m0 = pl[3 + c][tid] + A.rdampk * v0, m1 = pl[3 + c][tid + 1] + A.rdampk * v1;
-    const double m2 = pl[3 + c][tid + MK_NY] + A.rdampk * v2, m3 = pl[3 + c][tid + MK_NY + 1] + A.rdampk * v3;
+    const double m2 = pl[3 + c][tid + ny] + A.rdampk * v2, m3 = pl[3 + c][tid + ny + 1] + A.rdampk * v3;
     {
       MK_FACE_SUMS(m0, m1, m2, m3)
       R.wl[0][c] = d0_ + d1_; R.wl[1][c] = s1_ - s0_; R.wl[2][c] = d1_ - d0_;
@@ -126,12 +128,12 @@ EQD_HD void mp_phase_begin(const MarchPmlArgs& A, const MarchBundle& B, MarchPml
   for (int r = 0; r < 9; ++r) R.cs[r] = 0.0;
 }
 
-EQD_HD void mp_store_face(MarchPmlShared& sm, int c, int tid, double G0, double G1, double G2, double G3) {
+EQD_HD void mp_store_face(MarchPmlShared& sm, int c, int tid, int ny, double G0, double G1, double G2, double G3) {
   const double um = G0 - G1, up = G0 + G1, wm = G2 - G3, wp = G2 + G3;
   sm.frc[0][c][tid] = um - wm;
   sm.frc[1][c][tid + 1] = up - wp;
-  sm.frc[2][c][tid + MK_NY] = um + wm;
-  sm.frc[3][c][tid + MK_NY + 1] = up + wp;
+  sm.frc[2][c][tid + ny] = um + wm;
+  sm.frc[3][c][tid + ny + 1] = up + wp;
 }
 
 // direction of the shape derivative in split row r (0-based dof): assembleGlobalKU.f90:328-344
@@ -139,29 +141,30 @@ EQD_HD void mp_store_face(MarchPmlShared& sm, int c, int tid, double G0, double 
 EQD_HD constexpr int mp_dir(int r) { return r == 0 || r == 3 || r == 6 ? 0 : (r == 1 || r == 4 || r == 7 ? 1 : 2); }
 
 EQD_HD void mp_phase_element(const MarchPmlArgs& A, const MarchBundle& B, MarchPmlShared& sm, MarchPmlRegs& R, int tid, int p, int rs1) {
-  if (!mk_active(B, tid)) return;
+  const int ny = mk_rowlen(B);
+  if (!mp_active(B, tid, ny)) return;
   double(*pl)[MK_PN] = sm.ring[rs1];
   const double(*op)[MK_ES] = sm.ops[p & 1];
   double gx[3], gy[3], gz[3], P[4][3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const double v0 = pl[c][tid], v1 = pl[c][tid + 1], v2 = pl[c][tid + MK_NY], v3 = pl[c][tid + MK_NY + 1];
+    const double v0 = pl[c][tid], v1 = pl[c][tid + 1], v2 = pl[c][tid + ny], v3 = pl[c][tid + ny + 1];
     {
       MK_FACE_SUMS(v0, v1, v2, v3)
-      const double n0 = s0_ + s1_, ny = d0_ + d1_, nz = s1_ - s0_;
-      gx[c] = n0 - R.wv[0][c]; gy[c] = ny + R.wv[1][c]; gz[c] = nz + R.wv[2][c];
-      R.wv[0][c] = n0; R.wv[1][c] = ny; R.wv[2][c] = nz;
+      const double n0 = s0_ + s1_, vy = d0_ + d1_, vz = s1_ - s0_;
+      gx[c] = n0 - R.wv[0][c]; gy[c] = vy + R.wv[1][c]; gz[c] = vz + R.wv[2][c];
+      R.wv[0][c] = n0; R.wv[1][c] = vy; R.wv[2][c] = vz;
     }
     const double m0 = pl[3 + c][tid] + A.rdampk * v0, m1 = pl[3 + c][tid + 1] + A.rdampk * v1;
-    const double m2 = pl[3 + c][tid + MK_NY] + A.rdampk * v2, m3 = pl[3 + c][tid + MK_NY + 1] + A.rdampk * v3;
+    const double m2 = pl[3 + c][tid + ny] + A.rdampk * v2, m3 = pl[3 + c][tid + ny + 1] + A.rdampk * v3;
     {
       MK_FACE_SUMS(m0, m1, m2, m3)
-      const double ny = d0_ + d1_, nz = s1_ - s0_, nyz = d1_ - d0_;
-      P[0][c] = nyz + R.wl[2][c]; P[1][c] = nz - R.wl[1][c]; P[2][c] = ny - R.wl[0][c]; P[3][c] = nyz - R.wl[2][c];
-      R.wl[0][c] = ny; R.wl[1][c] = nz; R.wl[2][c] = nyz;
+      const double ly = d0_ + d1_, lz = s1_ - s0_, lyz = d1_ - d0_;
+      P[0][c] = lyz + R.wl[2][c]; P[1][c] = lz - R.wl[1][c]; P[2][c] = ly - R.wl[0][c]; P[3][c] = lyz - R.wl[2][c];
+      R.wl[0][c] = ly; R.wl[1][c] = lz; R.wl[2][c] = lyz;
     }
   }
-  const int es = (tid / MK_NY) * mk_by(B) + (tid % MK_NY);
+  const int es = (tid / ny) * mk_by(B) + (tid % ny);
   const double ax = op[0][es], ay = op[1][es], az = op[2][es];
   const double lam = op[6][es], mu = op[7][es], l2m = lam + 2.0 * mu;
   const double detw = op[8][es] * A.w;
@@ -193,7 +196,7 @@ EQD_HD void mp_phase_element(const MarchPmlArgs& A, const MarchBundle& B, MarchP
   const double V[9] = {0.0 - detw * ax * sxx, 0.0 - detw * ay * sxy, 0.0 - detw * az * sxz,
                        0.0 - detw * ax * sxy, 0.0 - detw * ay * syy, 0.0 - detw * az * syz,
                        0.0 - detw * ax * sxz, 0.0 - detw * ay * syz, 0.0 - detw * az * szz};
-  const int cb = mp_col(tid);
+  const int cb = mp_col(tid, ny);
 #pragma unroll
   for (int r = 0; r < 9; ++r) {
     // x type: +V on the x+ face, -V on the x- face; y / z type: the same on both faces
@@ -226,26 +229,28 @@ EQD_HD void mp_phase_element(const MarchPmlArgs& A, const MarchBundle& B, MarchP
   for (int c = 0; c < 3; ++c) {
     const double H0 = ssd[c] * P[0][c], H1 = ssd[c] * P[1][c], H2 = ssd[c] * P[2][c], H3 = ssd[c] * P[3][c];
     const double G0 = R.cf[0][c] - X[c], G1 = R.cf[1][c] + (Y[c] + H2), G2 = R.cf[2][c] + (Z[c] + H1), G3 = R.cf[3][c] + (H3 - H0);
-    mp_store_face(sm, c, tid, G0, G1, G2, G3);
+    mp_store_face(sm, c, tid, ny, G0, G1, G2, G3);
     R.cf[0][c] = X[c]; R.cf[1][c] = Y[c] - H2; R.cf[2][c] = Z[c] - H1; R.cf[3][c] = 0.0 - H0 - H3;
   }
 }
 
 EQD_HD void mp_phase_last(const MarchBundle& B, MarchPmlShared& sm, MarchPmlRegs& R, int tid) {
-  if (!mk_active(B, tid)) return;
-  const int cb = mp_col(tid);
+  const int ny = mk_rowlen(B);
+  if (!mp_active(B, tid, ny)) return;
+  const int cb = mp_col(tid, ny);
 #pragma unroll
   for (int r = 0; r < 9; ++r) sm.col[r][cb] = R.cs[r];   // the x+ face of the last element: +V (x type) or V (y, z type)
 #pragma unroll
-  for (int c = 0; c < 3; ++c) mp_store_face(sm, c, tid, R.cf[0][c], R.cf[1][c], R.cf[2][c], R.cf[3][c]);
+  for (int c = 0; c < 3; ++c) mp_store_face(sm, c, tid, ny, R.cf[0][c], R.cf[1][c], R.cf[2][c], R.cf[3][c]);
 }
 
 EQD_HD void mp_phase_flush(const MarchPmlArgs& A, const MarchBundle& B, MarchPmlShared& sm, int tid, int pl, int code) {
   if (code < 0) return;
   const size_t slot = A.slotBase + (size_t)B.n0 + (size_t)pl * MK_PN + tid;
   // the four columns around node (iz, iy): c00 has it at its (y-, z-) corner, c01 at (y+, z-), c10 at (y-, z+), c11 at (y+, z+)
-  const int iz = tid / MK_NY, iy = tid % MK_NY;
-  const int c11 = iz * (MK_NY + 1) + iy, c10 = c11 + 1, c01 = c11 + (MK_NY + 1), c00 = c01 + 1;
+  const int ny = mk_rowlen(B);
+  const int iz = tid / ny, iy = tid % ny;
+  const int c11 = iz * (ny + 1) + iy, c10 = c11 + 1, c01 = c11 + (ny + 1), c00 = c01 + 1;
 #pragma unroll
   for (int r = 0; r < 9; ++r) {
     const double g00 = sm.col[r][c00], g01 = sm.col[r][c01], g10 = sm.col[r][c10], g11 = sm.col[r][c11];
