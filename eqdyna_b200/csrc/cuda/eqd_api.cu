@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
@@ -47,6 +48,17 @@ struct ArgError : std::runtime_error { using std::runtime_error::runtime_error; 
 // the calling handle's pinned staging buffers while a set-up call is running (else pageable copies)
 thread_local StagedCopy* t_stage = nullptr;
 thread_local cudaStream_t t_stageStream = nullptr;
+
+// the pinned double buffer of a device: allocated at its first use in the process, kept for every later handle (pinning
+// 256 MB costs 0.1-0.2 s, more than the uploads of a mid-sized sub-domain take)
+std::shared_ptr<StagedCopy> shared_stage(int device) {
+  static std::mutex mu;
+  static std::map<int, std::shared_ptr<StagedCopy>> pool;
+  std::lock_guard<std::mutex> g(mu);
+  auto& p = pool[device];
+  if (!p) p.reset(new StagedCopy());
+  return p;
+}
 
 inline void h2d(void* dst, const void* src, size_t bytes) {
   if (t_stage && bytes >= (8u << 20)) {
@@ -271,7 +283,7 @@ struct eqd_handle {
   DevBuf<int> dSpecialA, dSpecialB;  // special nodes on active rank faces | the others (split-node pairs)
   int nSpecialA = 0, nSpecialB = 0;
   int optOverlap = -1, optReserve = 8, smCount = 148;  // overlap -1 = auto: 1 with rank neighbours, else 0
-  std::unique_ptr<StagedCopy> stage;  // pinned staging of the set-up uploads (and of large eqd_fetch reads); small sub-domains drop it once the run starts
+  std::shared_ptr<StagedCopy> stage;  // (one per device and process, shared by the handles on it) pinned staging of the set-up uploads (and of large eqd_fetch reads); small sub-domains drop it once the run starts
   // run state
   bool meshSet = false, opsSet = false, nodalSet = false, faultSet = false, finalized = false;
   int hostNt = 0;
@@ -1049,7 +1061,7 @@ int eqd_create(const eqd_params* p, int device, eqd_handle** out) {
     // cudaMemset on the legacy stream (a pageable H2D copy may return before its
     // DMA has landed), and a blocking stream is ordered after those.
     CK(cudaStreamCreate(&h->stream));
-    h->stage.reset(new StagedCopy());
+    h->stage = shared_stage(h->device);
     h->body = (p->C_elastic == 0) || (p->rdampm != 0.0);
     h->plastic = p->C_elastic == 0;
     h->qmode = p->C_Q == 1;
@@ -2095,7 +2107,7 @@ int eqd_fetch(eqd_handle* h, int32_t which, void* dst, int64_t dst_bytes) {
         // large sub-domains: chunks of the three SoA rows land in a pinned buffer (DMA at link
         // speed, no pageable bounce, no serial first touch of a 0.5 GB temporary) and are
         // interleaved into the caller's (3,Nn) array by all host threads
-        if (!h->stage) h->stage.reset(new StagedCopy());
+        if (!h->stage) h->stage = shared_stage(h->device);
         void* pinv = nullptr;
         CK(h->stage->pinned(0, &pinv));
         double* pin = (double*)pinv;
