@@ -1269,7 +1269,7 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
         need(perSm > 0, "option march: the marching kernel does not fit this device");
         MarchPlan MP;
         plan_march(h->conn.data(), h->etype.data(), h->coor.data(), h->info.data(), members[CLS_REG], Nn, gny, gnz, h->mNxg, perSm * sms,
-                   h->optMarch >= 2 ? 1 : 0, MP);
+                   h->optMarch == 2 ? 3 : h->optMarch == 3 ? 1 : 0, MP);   // 2: ghost rows and columns, 3: ghost columns (y) only
         if (MP.n > 0) {
           M.n = MP.n; M.S = MP.S; M.PFS = MP.PFS;
           h->mGrid = MP.grid; h->mBundles = (int)MP.rec.size(); h->mFused = MP.nFused;
@@ -2311,7 +2311,7 @@ int eqd_set_option(eqd_handle* h, const char* key, int32_t value) {
   if (!strcmp(key, "box_compact")) { h->optBoxCompact = value != 0; return EQD_OK; }
   if (!strcmp(key, "march")) {
     if (h->meshSet) { h->err = "eqd_set_option: march must be set before eqd_set_mesh"; return EQD_ERR_ARG; }
-    h->optMarch = value < 0 ? 0 : value > 2 ? 2 : value;
+    h->optMarch = value < 0 ? 0 : value > 3 ? 3 : value;
     return EQD_OK;
   }
   if (!strcmp(key, "box")) {

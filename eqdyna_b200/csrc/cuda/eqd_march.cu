@@ -302,8 +302,8 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
   // ---- column tiles and their strips: runs in x of complete cross-sections whose cells share all their nodes
   std::vector<std::pair<int, int>> zt, yt, ztB;
   // base tiles are one cell short of the kernel's cross-section: room for the ghost row / column
-  cut_axis(ez, seamZ, share ? MK_BZ - 1 : MK_BZ, zt);
-  cut_axis(ey, seamY, share ? MK_BY - 1 : MK_BY, yt);
+  cut_axis(ez, seamZ, (share & 2) ? MK_BZ - 1 : MK_BZ, zt);   // share: bit 0 = ghost columns (y), bit 1 = ghost rows (z)
+  cut_axis(ey, seamY, (share & 1) ? MK_BY - 1 : MK_BY, yt);
   // PML bundles: a y segment no wider than 7 cells (a slab) is swept with the node plane turned -- 16 rows of 8 nodes, up
   // to 15 x 7 element columns -- so that the threads are filled along z instead
   std::vector<char> turned(yt.size(), 0);
@@ -366,7 +366,7 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
       };
       std::vector<char> yShared(nty + 1, 0), zShared(ntz + 1, 0);
       for (int ty = 1; ty < nty; ++ty) {
-        bool ok = true;
+        bool ok = (share & 1) != 0;
         for (int tz = 0; ok && tz < ntz; ++tz) {
           const auto& a = per[tz * nty + ty - 1];
           const auto& b = per[tz * nty + ty];
@@ -379,7 +379,7 @@ void plan_march(const int* conn, const int* etype, const double* coor, const int
         yShared[ty] = ok;
       }
       for (int tz = 1; tz < ntz; ++tz) {
-        bool ok = true;
+        bool ok = (share & 2) != 0;
         for (int ty = 0; ok && ty < nty; ++ty) {
           const auto& a = per[(tz - 1) * nty + ty];
           const auto& b = per[tz * nty + ty];
@@ -634,7 +634,7 @@ extern "C" int eqd_march_emulate(int32_t Nn, int32_t Ne, const double* meshCoor,
     MarchPlan P;
     int nxg = 0;
     for (int e = 0; e < Ne; ++e) nxg = std::max(nxg, (int)(conn[8 * (size_t)e + 6] / ((long)ny * nz)) + 1);
-    plan_march(conn.data(), elemTypeArr, meshCoor, info.data(), elems, Nn, ny, nz, nxg, grid & 0xffff, (grid >> 16) & 1, P, false);
+    plan_march(conn.data(), elemTypeArr, meshCoor, info.data(), elems, Nn, ny, nz, nxg, grid & 0xffff, (grid >> 16) & 3, P, false);
     stats[0] = P.n; stats[1] = (int64_t)P.rec.size(); stats[2] = P.PFS; stats[3] = P.nFused; stats[4] = (int64_t)P.leftover.size();
     stats[5] = P.grid; stats[6] = P.S; stats[7] = P.nBundlesA;
     for (int e = 0; e < Ne; ++e) inBundle[e] = 0;

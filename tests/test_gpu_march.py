@@ -73,11 +73,12 @@ def test_march_and_tiles_agree_to_rounding():
             assert parity.rel_l2(getattr(b.view(0), name), getattr(a.view(0), name)) < 1e-9, (march, name)
 
 
-@pytest.mark.parametrize("case,np_xyz,nstep", [("test.tpv104", (2, 2, 1), 60), ("test.tpv8", (1, 1, 1), 40), ("test.tpv36", (2, 2, 2), 40)])
-def test_march_with_ghost_sharing_matches_oracle(case, np_xyz, nstep):
-    """option march = 2: neighbouring strips share ghost rows / columns, v and d double-buffered"""
+@pytest.mark.parametrize("case,np_xyz,nstep,march", [("test.tpv104", (2, 2, 1), 60, 2), ("test.tpv8", (1, 1, 1), 40, 2), ("test.tpv36", (2, 2, 2), 40, 2),
+                                                     ("test.tpv104", (2, 2, 1), 60, 3)])
+def test_march_with_ghost_sharing_matches_oracle(case, np_xyz, nstep, march):
+    """option march = 2 / 3: neighbouring strips share ghost rows and columns / columns only, v and d double-buffered"""
     wg = parity.build_world(case, np_xyz, nstep)
     wo = parity.build_world(case, np_xyz, nstep)
-    parity.run_gpu(wg, options=OPTS, pre_options={"march": 2}, chunks=2)
+    parity.run_gpu(wg, options=OPTS, pre_options={"march": march}, chunks=2)
     parity.run_oracle(wo)
     parity.assert_parity(parity.compare_worlds(wg, wo))

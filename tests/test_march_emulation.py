@@ -66,13 +66,15 @@ def _reference(v, E, vel, disp, stress6, dt):
     return f, sg
 
 
-SHARE = 1 << 16   # flag in the grid argument of eqd_march_emulate: neighbouring strips share ghost rows / columns
+SHARE = 3 << 16   # flags in the grid argument of eqd_march_emulate: neighbouring strips share ghost columns (bit 16) / rows (bit 17)
+SHARE_Y = 1 << 16
 
 
 @pytest.mark.parametrize("case,grid,min_cover,min_fused", [("test.tpv104", 444, 0.95, 0.3), ("test.tpv8", 37, 0.95, 0.3), ("test.tpv104", 7, 0.95, 0.3),
                                                            ("test.tpv104", 444 | SHARE, 0.95, 0.75), ("test.tpv8", 37 | SHARE, 0.95, 0.7),
-                                                           ("test.tpv36", 100 | SHARE, 0.6, 0.5)],
-                         ids=["tpv104-444ctas", "tpv8-37ctas", "tpv104-7ctas", "tpv104-444ctas-ghosts", "tpv8-37ctas-ghosts", "tpv36-dipping-fault-ghosts"])
+                                                           ("test.tpv36", 100 | SHARE, 0.6, 0.5), ("test.tpv104", 444 | SHARE_Y, 0.95, 0.5)],
+                         ids=["tpv104-444ctas", "tpv8-37ctas", "tpv104-7ctas", "tpv104-444ctas-ghosts", "tpv8-37ctas-ghosts", "tpv36-dipping-fault-ghosts",
+                              "tpv104-444ctas-ghost-columns-only"])
 def test_marching_kernel_phases_on_the_host(case, grid, min_cover, min_fused):
     w = parity.build_world(case, (1, 1, 1), 2)
     v = w.view(0)
