@@ -1090,6 +1090,15 @@ int eqd_destroy(eqd_handle* h) {
   cudaSetDevice(h->device);
   if (h->commThread.joinable()) h->commThread.join();
   for (void* b : h->p2p.peerBase) if (b) cudaIpcCloseMemHandle(b);
+  if (h->p2p.area.p) {
+    // a neighbour may still have this allocation mapped (freeing an exported allocation before every importer has closed
+    // it is undefined): the few MB stay allocated until the process ends
+    static std::mutex mu;
+    static std::vector<void*> keep;
+    std::lock_guard<std::mutex> g(mu);
+    keep.push_back(h->p2p.area.p);
+    h->p2p.area.p = nullptr; h->p2p.area.n = 0;
+  }
   if (h->comm && g_nccl.lib) g_nccl.CommDestroy(h->comm);
   for (int a = 0; a < 3; ++a) if (h->evPacked[a]) cudaEventDestroy(h->evPacked[a]);
   for (cudaEvent_t e : {h->evFace, h->evElem, h->evComm}) if (e) cudaEventDestroy(e);
@@ -2281,6 +2290,11 @@ int eqd_get_march_counts(const eqd_handle* h, int64_t* out5) {   // out5[0..7]
   out5[3] = h->mFused; out5[4] = h->mGrid;
   out5[5] = h->cls[CLS_MARCHP].n; out5[6] = h->pBundles; out5[7] = h->cls[CLS_MARCHP].n ? h->cls[CLS_MARCHP].PFS : 0;
   return EQD_OK;
+}
+
+int eqd_get_halo_mode(const eqd_handle* h) {
+  if (!h || !h->finalized || !has_neighbours(h)) return 0;
+  return h->p2p.on ? 2 : 1;
 }
 
 int eqd_get_timing(const eqd_handle* h, double* ms_slots) {

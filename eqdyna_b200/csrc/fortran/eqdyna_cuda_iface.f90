@@ -130,6 +130,10 @@ module eqdyna_cuda_iface
             type(c_ptr), value :: handle
             real(c_double), intent(out) :: ms_slots(10)
         end function
+        integer(c_int) function eqd_get_halo_mode(handle) bind(C, name='eqd_get_halo_mode')
+            import :: c_int, c_ptr
+            type(c_ptr), value :: handle
+        end function
         integer(c_int) function eqd_get_march_counts(handle, out5) bind(C, name='eqd_get_march_counts')
             import :: c_int, c_ptr, c_int64_t
             type(c_ptr), value :: handle

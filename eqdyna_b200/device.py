@@ -23,7 +23,7 @@ EXPORTS = [
     "eqd_create", "eqd_destroy", "eqd_last_error", "eqd_set_mesh", "eqd_set_elem_ops", "eqd_compute_elem_ops", "eqd_set_nodal",
     "eqd_set_fault", "eqd_set_halo", "eqd_set_stations", "eqd_get_unique_id", "eqd_set_comm", "eqd_sum_shared",
     "eqd_run", "eqd_run_group", "eqd_fetch", "eqd_get_counts", "eqd_get_timing", "eqd_set_option", "eqd_plan_check",
-    "eqd_box_check", "eqd_get_box_counts", "eqd_plan_bank_model", "eqd_march_emulate", "eqd_get_march_counts", "eqd_march_pml_emulate",
+    "eqd_box_check", "eqd_get_box_counts", "eqd_plan_bank_model", "eqd_march_emulate", "eqd_get_march_counts", "eqd_march_pml_emulate", "eqd_get_halo_mode",
 ]
 
 _lib = None
@@ -202,6 +202,11 @@ class Domain:
         a, b = C.c_int64(), C.c_int64()
         lib().eqd_get_box_counts(self._h, C.byref(a), C.byref(b))
         return {"regular": a.value, "pml": b.value}
+
+    def halo_mode(self):
+        """0 = no rank neighbours, 1 = ncclSend / ncclRecv, 2 = peer memory (valid after the first run / sum_shared)."""
+        lib().eqd_get_halo_mode.argtypes = [C.c_void_p]
+        return int(lib().eqd_get_halo_mode(self._h))
 
     def march_counts(self):
         """Marching class (option "march"): elements in bundles, bundles, node slots, fused nodes, CTAs."""

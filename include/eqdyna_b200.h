@@ -177,6 +177,9 @@ int eqd_get_box_counts(const eqd_handle* h, int64_t* n_regular_box, int64_t* n_p
 /* marching classes (option "march"): out8 = elements in bundles, bundles, node slots, nodes the bundles update
  * themselves, CTAs of the persistent launch; PML elements in bundles, PML bundles, PML node slots */
 int eqd_get_march_counts(const eqd_handle* h, int64_t* out8);
+/* transport of the step-loop exchange once the first run / eqd_sum_shared has set it up: 0 = no rank neighbours,
+ * 1 = ncclSend / ncclRecv, 2 = peer memory (CUDA IPC, k_halo_send / k_halo_recv)                                */
+int eqd_get_halo_mode(const eqd_handle* h);
 int eqd_get_timing(const eqd_handle* h, double* ms_slots /*[EQD_T_NSLOTS]*/);
 /* options: "timing" 1 = CUDA-event timing of every phase (2 = also reset the
  * accumulated slots and the launch counter); "overlap" -1 auto (default) / 0 serial

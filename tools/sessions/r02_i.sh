@@ -12,8 +12,7 @@ run() {  # name, port, args...
 EQD_VERBOSE=1 run tpv104_n8 29601 --steps 20 --warmup 5
 run tpv104_n8_long 29602 --steps 200 --warmup 5 --no-cpu-baseline
 run tpv36_100m_n8 29603 --steps 50 --warmup 5 --case bench.tpv36_100m --decomp 2x2x2 --no-cpu-baseline
-run tpv36_200m_n8 29604 --steps 40 --warmup 5 --case bench.tpv36_200m --decomp 2x2x2
 run tpv10_n8 29605 --steps 40 --warmup 5 --case test.tpv10 --decomp 2x2x2
 run drva6_n8 29606 --steps 20 --warmup 5 --case test.drv.a6 --decomp 2x2x2
 cat gpurun_out/r02_i_status.txt
-for n in tpv104_n8 tpv104_n8_long tpv36_100m_n8 tpv36_200m_n8 tpv10_n8 drva6_n8; do echo "== $n"; grep "ms/step\|e2e leg\|parity over" gpurun_out/r02_i_${n}.log | head -3 | cut -c1-330; done
+for n in tpv104_n8 tpv104_n8_long tpv36_100m_n8 tpv10_n8 drva6_n8; do echo "== $n"; grep "ms/step\|e2e leg\|parity over" gpurun_out/r02_i_${n}.log | head -3 | cut -c1-330; done
