@@ -1149,13 +1149,14 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
     }
     lap.lap("host copies");
     // ---- node kinds
-    h->info.assign(Nn, 0);
+    h->info.resize(Nn);   // (every entry is written by the loop below)
     h->Np = 0;
     {
       std::vector<char> badv(2, 0);
       parallel_range((size_t)Nn, [&](size_t b, size_t e) {
         for (size_t n = b; n < e; ++n) {
           const int nd = h->ndof[n], st = h->eqStart[n];
+          h->info[n] = 0;
           if (!((nd == 3 || nd == 12) && st >= 0 && st + nd <= sizeEq)) { badv[0] = 1; continue; }
           int nfix = 0;
           for (int j = 0; j < nd; ++j) if (h->eqIdx[st + j] <= 0) nfix++;
@@ -1199,15 +1200,18 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
     // ---- element classes, cut into tiles (eqd_tiles.h)
     std::vector<int> members[3];
     {
-      std::vector<signed char> ccode(Ne);
+      raw_vector<signed char> ccode(Ne);
+      raw_vector<unsigned char> is12(Nn);   // one byte per node: the eight gathers per element stay in cache
+      parallel_range((size_t)Nn, [&](size_t b, size_t e) { for (size_t n = b; n < e; ++n) is12[n] = h->ndof[n] == 12; });
       parallel_range((size_t)Ne, [&](size_t b, size_t e) {
         for (size_t el = b; el < e; ++el) {
           const int t = h->etype[el];
           int c;
           if (t == 2) c = CLS_PML;
           else if (t == 1 || (t >= 11 && t <= 13)) {
-            c = CLS_REG;
-            for (int k = 0; k < 8; ++k) if (h->ndof[h->conn[8 * el + k]] == 12) c = CLS_REGX;
+            const int* cn = &h->conn[8 * el];
+            const int any = is12[cn[0]] | is12[cn[1]] | is12[cn[2]] | is12[cn[3]] | is12[cn[4]] | is12[cn[5]] | is12[cn[6]] | is12[cn[7]];
+            c = any ? CLS_REGX : CLS_REG;
           } else c = -1;
           ccode[el] = (signed char)c;
         }
