@@ -258,6 +258,9 @@ struct eqd_handle {
   // eqd_create overlaps the communicator's start-up with its uploads; comm_ready() joins before the first use
   std::thread commThread;
   ncclResult_t commRc = ncclSuccess;
+  // eqd_set_host_comm: the host's own all-gather (MPI_Allgather) carries the set-up exchanges; no NCCL communicator
+  eqd_allgather_fn hostAg = nullptr;
+  void* hostCtx = nullptr;
   // Step-loop exchange over peer memory (option "halo", default on between processes of one box): every face has two
   // receive buffers and two flag words in ONE allocation of this sub-domain, which the neighbours map through CUDA IPC;
   // k_halo_send writes into the neighbour's copy, k_halo_recv polls the own one (eqd_kernels.cu).  NCCL is then used at
@@ -718,7 +721,9 @@ void finalize(eqd_handle* h) {
 // transport of one axis phase between processes (NCCL) -- pack/unpack by caller
 void halo_axis_nccl(eqd_handle* h, int a, cudaStream_t st) {
   comm_ready(h);
-  if (!h->comm) throw ArgError("eqd_run: sub-domain has neighbours but eqd_set_comm was not called");
+  if (!h->comm)
+    throw ArgError(h->hostAg ? "eqd_run: peer memory (CUDA IPC) cannot be mapped between the ranks and no NCCL communicator was given (eqd_set_comm)"
+                             : "eqd_run: sub-domain has neighbours but eqd_set_comm was not called");
   NK(g_nccl.GroupStart());
   for (int side = 0; side < 2; ++side) {
     Face& F = h->face[a][side];
@@ -782,12 +787,27 @@ void halo_unpack(eqd_handle* h, int a, cudaStream_t st = nullptr) {
 // Peer-memory set-up of the step-loop exchange (collective: every rank of the communicator calls it once, from
 // finalize).  Each rank lays its receive buffers, flag words and send counters out in one allocation, publishes the
 // allocation's IPC handle and the layout through one ncclAllGather, and maps its neighbours' allocations.
+// set-up all-gather of `bytes` (a multiple of 8) per rank: the host's communicator when eqd_set_host_comm gave one,
+// else NCCL through device memory
+void setup_allgather(eqd_handle* h, const void* send, size_t bytes, void* recv) {
+  if (h->hostAg) {
+    if (h->hostAg(h->hostCtx, send, (int64_t)bytes, recv) != 0) throw CudaError("eqd_set_host_comm: the host's all-gather reported a failure");
+    return;
+  }
+  DevBuf<unsigned long long> dMine, dAll;
+  dMine.alloc(bytes / 8); dAll.alloc(bytes / 8 * h->nranks);
+  CK(cudaMemcpy(dMine.p, send, bytes, cudaMemcpyHostToDevice));
+  NK(g_nccl.AllGather(dMine.p, dAll.p, bytes / 8, ncclUint64, h->comm, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(recv, dAll.p, bytes * h->nranks, cudaMemcpyDeviceToHost));
+}
+
 struct P2PRecord { cudaIpcMemHandle_t handle; unsigned long long recvOff[3][2][2]; unsigned long long flagOff; unsigned long long pad[2]; };
 void p2p_setup(eqd_handle* h) {
   auto& Q = h->p2p;
   Q.on = false;
-  comm_ready(h);
-  if (!h->comm || h->optHalo == 0 || h->nranks < 2) return;
+  if (!h->hostAg) comm_ready(h);
+  if ((!h->comm && !h->hostAg) || h->optHalo == 0 || h->nranks < 2) return;
   static_assert(sizeof(P2PRecord) % 8 == 0, "record is exchanged as 8-byte words");
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
@@ -802,15 +822,8 @@ void p2p_setup(eqd_handle* h) {
   for (int a = 0; a < 3; ++a) for (int s = 0; s < 2; ++s) for (int par = 0; par < 2; ++par) mine.recvOff[a][s][par] = Q.recvOff[a][s][par];
   mine.flagOff = Q.flagOff;
   mine.pad[0] = ok ? 1 : 0;
-  // all-gather of the records through device memory
-  const size_t words = sizeof(P2PRecord) / 8;
-  DevBuf<unsigned long long> dMine, dAll;
-  dMine.alloc(words); dAll.alloc(words * h->nranks);
-  CK(cudaMemcpy(dMine.p, &mine, sizeof mine, cudaMemcpyHostToDevice));
-  NK(g_nccl.AllGather(dMine.p, dAll.p, words, ncclUint64, h->comm, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
   std::vector<P2PRecord> all(h->nranks);
-  CK(cudaMemcpy(all.data(), dAll.p, sizeof(P2PRecord) * h->nranks, cudaMemcpyDeviceToHost));
+  setup_allgather(h, &mine, sizeof mine, all.data());
   for (const P2PRecord& r : all) ok = ok && r.pad[0] == 1;
   Q.peerBase.assign(h->nranks, nullptr);
   for (int a = 0; a < 3 && ok; ++a)
@@ -828,11 +841,8 @@ void p2p_setup(eqd_handle* h) {
     }
   // the choice must be the same on every rank: one more tiny all-gather of the outcome
   unsigned long long okw = ok ? 1 : 0;
-  CK(cudaMemcpy(dMine.p, &okw, 8, cudaMemcpyHostToDevice));
-  NK(g_nccl.AllGather(dMine.p, dAll.p, 1, ncclUint64, h->comm, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
   std::vector<unsigned long long> oks(h->nranks);
-  CK(cudaMemcpy(oks.data(), dAll.p, 8 * h->nranks, cudaMemcpyDeviceToHost));
+  setup_allgather(h, &okw, 8, oks.data());
   for (unsigned long long v : oks) ok = ok && v == 1;
   if (!ok) {
     for (void*& b : Q.peerBase) if (b) { cudaIpcCloseMemHandle(b); b = nullptr; }
@@ -1955,6 +1965,17 @@ int eqd_set_comm(eqd_handle* h, const void* id128, int32_t nranks, int32_t rank)
   });
 }
 
+int eqd_set_host_comm(eqd_handle* h, int32_t nranks, int32_t rank, eqd_allgather_fn fn, void* ctx) {
+  if (!h) return EQD_ERR_ARG;
+  return guarded(h, [&] {
+    need(fn && nranks >= 1 && rank >= 0 && rank < nranks, "eqd_set_host_comm: bad arguments");
+    need(nranks == h->p.npx * h->p.npy * h->p.npz && rank == h->p.me, "eqd_set_host_comm: rank/nranks must match me and npx*npy*npz");
+    need(!h->finalized, "eqd_set_host_comm: call before the first eqd_run / eqd_sum_shared");
+    h->nranks = nranks; h->rank = rank;
+    h->hostAg = fn; h->hostCtx = ctx;
+  });
+}
+
 // The init-time sums of the reference (nodalMassArr and fnms through
 // MPI4NodalQuant, assembleGlobalMass.f90:40-41; arn through MPI4arn,
 // meshgen.f90:274-395), x then y then z, for a one-process-per-GPU host.
@@ -1964,33 +1985,55 @@ int eqd_sum_shared(eqd_handle* h) {
     need(h->nodalSet, "eqd_sum_shared: call after eqd_set_nodal / eqd_set_fault / eqd_set_halo");
     finalize(h);
     if (!has_neighbours(h)) return;
-    comm_ready(h);
-    need(h->comm != nullptr, "eqd_sum_shared: eqd_set_comm first");
+    if (!h->hostAg) comm_ready(h);
+    need(h->comm != nullptr || h->hostAg, "eqd_sum_shared: eqd_set_comm or eqd_set_host_comm first");
     // host-staged: these run once
     for (int a = 0; a < 3; ++a) {
       std::vector<double> sendv[2], recvv[2];
-      DevBuf<double> ds[2], dr[2];
       for (int side = 0; side < 2; ++side) {
         Face& F = h->face[a][side];
         if (F.nb < 0) continue;
         for (int n : F.nodes) { sendv[side].push_back(h->massH[n]); sendv[side].push_back(h->fnmsH[n]); }
         std::vector<double> arnH = h->dArn.download();
         for (int q : F.pairs) sendv[side].push_back(arnH[q]);
-        ds[side].upload(sendv[side]); dr[side].alloc(sendv[side].size());
       }
-      NK(g_nccl.GroupStart());
+      if (h->hostAg) {
+        // one all-gather of [len(-side), len(+side)] and one of the two vectors padded to the longest: a rank reads
+        // what the facing side of each neighbour sent (the two sides of a face hold the same nodes in the same order)
+        unsigned long long len[2] = {sendv[0].size(), sendv[1].size()};
+        std::vector<unsigned long long> lens(2 * (size_t)h->nranks);
+        setup_allgather(h, len, sizeof len, lens.data());
+        size_t L = 0;
+        for (unsigned long long v : lens) L = std::max(L, (size_t)v);
+        if (L) {
+          std::vector<double> mine(2 * L, 0.0), all(2 * L * (size_t)h->nranks);
+          for (int side = 0; side < 2; ++side) std::copy(sendv[side].begin(), sendv[side].end(), mine.begin() + side * L);
+          setup_allgather(h, mine.data(), sizeof(double) * 2 * L, all.data());
+          for (int side = 0; side < 2; ++side) {
+            const Face& F = h->face[a][side];
+            if (F.nb < 0 || sendv[side].empty()) continue;
+            need(lens[2 * (size_t)F.nb + (1 - side)] == sendv[side].size(), "eqd_sum_shared: the two sides of a rank face differ in length");
+            const double* src = all.data() + (2 * (size_t)F.nb + (1 - side)) * L;
+            recvv[side].assign(src, src + sendv[side].size());
+          }
+        }
+      } else {
+        DevBuf<double> ds[2], dr[2];
+        for (int side = 0; side < 2; ++side) if (h->face[a][side].nb >= 0) { ds[side].upload(sendv[side]); dr[side].alloc(sendv[side].size()); }
+        NK(g_nccl.GroupStart());
+        for (int side = 0; side < 2; ++side) {
+          Face& F = h->face[a][side];
+          if (F.nb < 0 || ds[side].n == 0) continue;
+          NK(g_nccl.Send(ds[side].p, ds[side].n, ncclDouble, F.nb, h->comm, h->stream));
+          NK(g_nccl.Recv(dr[side].p, dr[side].n, ncclDouble, F.nb, h->comm, h->stream));
+        }
+        NK(g_nccl.GroupEnd());
+        CK(cudaStreamSynchronize(h->stream));
+        for (int side = 0; side < 2; ++side) if (h->face[a][side].nb >= 0 && ds[side].n) recvv[side] = dr[side].download();
+      }
       for (int side = 0; side < 2; ++side) {
         Face& F = h->face[a][side];
-        if (F.nb < 0 || ds[side].n == 0) continue;
-        NK(g_nccl.Send(ds[side].p, ds[side].n, ncclDouble, F.nb, h->comm, h->stream));
-        NK(g_nccl.Recv(dr[side].p, dr[side].n, ncclDouble, F.nb, h->comm, h->stream));
-      }
-      NK(g_nccl.GroupEnd());
-      CK(cudaStreamSynchronize(h->stream));
-      for (int side = 0; side < 2; ++side) {
-        Face& F = h->face[a][side];
-        if (F.nb < 0 || ds[side].n == 0) continue;
-        recvv[side] = dr[side].download();
+        if (F.nb < 0 || sendv[side].empty()) continue;
         size_t k = 0;
         for (int n : F.nodes) {
           if (EQD_INFO_KIND(h->info[n]) != KIND_FIXED) h->massH[n] = h->massH[n] + recvv[side][k];

@@ -13,6 +13,10 @@
 #include <type_traits>
 #include <utility>
 #include <vector>
+#include <cstdlib>
+#ifdef __linux__
+#include <sched.h>
+#endif
 
 namespace eqd {
 
@@ -28,9 +32,19 @@ struct default_init_allocator : std::allocator<T> {
 };
 template <class T> using raw_vector = std::vector<T, default_init_allocator<T>>;
 
+// worker threads of the set-up loops: EQD_HOST_THREADS when the host sets it (several ranks sharing the cores of one
+// box should: cores / ranks), else the cores this process may run on, at most 16
 inline int host_threads() {
-  int nt = (int)std::thread::hardware_concurrency();
-  return std::max(1, std::min(nt, 16));
+  static const int nt = [] {
+    if (const char* e = getenv("EQD_HOST_THREADS")) { const int v = atoi(e); if (v >= 1) return std::min(v, 64); }
+    int n = (int)std::thread::hardware_concurrency();
+#ifdef __linux__
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) n = std::min(n, (int)CPU_COUNT(&set));
+#endif
+    return std::max(1, std::min(n, 16));
+  }();
+  return nt;
 }
 
 // fn(begin, end) over [0, n) split into contiguous chunks, one per thread

@@ -23,8 +23,7 @@ namespace {
 
 template <class F>
 void parallel_for(int n, F&& fn) {
-  int nt = (int)std::thread::hardware_concurrency();
-  nt = std::max(1, std::min(nt, 16));
+  const int nt = host_threads();
   if (n < 64 || nt == 1) { fn(0, n); return; }
   std::vector<std::thread> th;
   const int chunk = (n + nt - 1) / nt;

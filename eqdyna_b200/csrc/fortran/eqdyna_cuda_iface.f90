@@ -95,6 +95,15 @@ module eqdyna_cuda_iface
             character(kind=c_char) :: id128(128)
             integer(c_int32_t), value :: nranks, rank
         end function
+        ! fn is a bind(C) function  integer(c_int32_t) fn(ctx, send, bytes, recv)  that wraps
+        ! MPI_Allgather(send, bytes, MPI_BYTE, recv, bytes, MPI_BYTE, MPI_COMM_WORLD); pass it as c_funloc(fn)
+        integer(c_int) function eqd_set_host_comm(handle, nranks, rank, fn, ctx) bind(C, name='eqd_set_host_comm')
+            import :: c_int, c_ptr, c_funptr, c_int32_t
+            type(c_ptr), value :: handle
+            integer(c_int32_t), value :: nranks, rank
+            type(c_funptr), value :: fn
+            type(c_ptr), value :: ctx
+        end function
         integer(c_int) function eqd_sum_shared(handle) bind(C, name='eqd_sum_shared')
             import :: c_int, c_ptr
             type(c_ptr), value :: handle

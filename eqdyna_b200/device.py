@@ -21,13 +21,15 @@ T_TOTAL, T_NODE, T_ELEM, T_ASSEMBLE, T_HALO, T_FAULT, T_ELEM_PML, T_ELEM_REGX, T
 
 EXPORTS = [
     "eqd_create", "eqd_destroy", "eqd_last_error", "eqd_set_mesh", "eqd_set_elem_ops", "eqd_compute_elem_ops", "eqd_set_nodal",
-    "eqd_set_fault", "eqd_set_halo", "eqd_set_stations", "eqd_get_unique_id", "eqd_set_comm", "eqd_sum_shared",
+    "eqd_set_fault", "eqd_set_halo", "eqd_set_stations", "eqd_get_unique_id", "eqd_set_comm", "eqd_set_host_comm", "eqd_sum_shared",
     "eqd_run", "eqd_run_group", "eqd_fetch", "eqd_get_counts", "eqd_get_timing", "eqd_set_option", "eqd_plan_check",
     "eqd_box_check", "eqd_get_box_counts", "eqd_plan_bank_model", "eqd_march_emulate", "eqd_get_march_counts", "eqd_march_pml_emulate", "eqd_get_halo_mode",
 ]
 
 _lib = None
 EQD_ERR_ARG = 4
+# eqd_allgather_fn of include/eqdyna_b200.h: fn(ctx, send, bytes, recv) -> 0 on success
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
 
 
 class StepError(RuntimeError):
@@ -57,6 +59,7 @@ def lib():
         L.eqd_set_stations.argtypes = [vp, vp, i32, vp, i32, vp, i32]
         L.eqd_get_unique_id.argtypes = [vp]
         L.eqd_set_comm.argtypes = [vp, vp, i32, i32]
+        L.eqd_set_host_comm.argtypes = [vp, i32, i32, ALLGATHER_FN, vp]
         L.eqd_sum_shared.argtypes = [vp]
         L.eqd_run.argtypes = [vp, i32, i32]
         L.eqd_run_group.argtypes = [C.POINTER(vp), i32, i32, i32]
@@ -129,11 +132,14 @@ def box_check(view):
 class Domain:
     """One sub-domain of a case on one GPU."""
 
-    def __init__(self, view, device=0, compute_ops=False, options=None, comm=None):
+    def __init__(self, view, device=0, compute_ops=False, options=None, comm=None, host_comm=None):
         """compute_ops: let the device compute the element operators and the lumped mass from the
         mesh (eqd_compute_elem_ops) instead of uploading the host's (eqd_set_elem_ops).
         comm = (id128, nranks, rank): eqd_set_comm right after eqd_create, so that the communicator
-        starts up while the state is uploaded."""
+        starts up while the state is uploaded.
+        host_comm = (nranks, rank, allgather): eqd_set_host_comm -- allgather(send: bytes-like, nranks) -> bytes-like
+        of nranks * len(send) bytes in rank order is the host's own all-gather (MPI_Allgather / torch.distributed);
+        the library then creates no NCCL communicator."""
         self.view = view
         self.compute_ops = compute_ops
         self._h = C.c_void_p()
@@ -147,6 +153,8 @@ class Domain:
             self.set_option(k, val)
         if comm is not None:
             self.set_comm(*comm)
+        if host_comm is not None:
+            self.set_host_comm(*host_comm)
         self._upload(view)
 
     def _check(self, rc):
@@ -181,6 +189,19 @@ class Domain:
     # -- multi-process plumbing
     def set_comm(self, id128, nranks, rank):
         self._check(lib().eqd_set_comm(self._h, C.c_char_p(id128), nranks, rank))
+
+    def set_host_comm(self, nranks, rank, allgather):
+        def fn(ctx, send, nbytes, recv):
+            try:
+                out = allgather((C.c_char * nbytes).from_address(send), nranks)
+                C.memmove(recv, bytes(out) if not isinstance(out, (bytes, bytearray)) else out, nbytes * nranks)
+                return 0
+            except Exception:   # an exception must not unwind through the C frames
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._host_ag = ALLGATHER_FN(fn)   # keep the trampoline alive as long as the handle
+        self._check(lib().eqd_set_host_comm(self._h, int(nranks), int(rank), self._host_ag, None))
 
     def sum_shared(self):
         self._check(lib().eqd_sum_shared(self._h))

@@ -156,6 +156,15 @@ int eqd_set_stations(eqd_handle* h, const int32_t* idhist, int32_t nOff,
 /* 128-byte ncclUniqueId made by rank 0 and broadcast by the host (MPI_Bcast) */
 int eqd_get_unique_id(void* id128);
 int eqd_set_comm(eqd_handle* h, const void* id128, int32_t nranks, int32_t rank);
+/* Alternative to eqd_get_unique_id / eqd_set_comm for a host that already has a communicator over the same
+ * npx*npy*npz ranks (the reference's MPI_COMM_WORLD, eqdyna3d.f90:19-21): the library does its SET-UP exchanges
+ * (the CUDA-IPC handles of the peer-memory areas, the sums of eqd_sum_shared) through the host's all-gather
+ *     fn(ctx, send, bytes, recv)  ==  MPI_Allgather(send, bytes, MPI_BYTE, recv, bytes, MPI_BYTE, comm),  0 = ok,
+ * called collectively (every rank, same order, from the thread that calls eqd_sum_shared / the first eqd_run),
+ * and the step-loop exchange of MPI4NodalQuant runs over peer memory.  No NCCL communicator is created (its start-up
+ * costs seconds on an 8-GPU box); where peer memory cannot be mapped, also call eqd_set_comm.                       */
+typedef int32_t (*eqd_allgather_fn)(void* ctx, const void* send, int64_t bytes, void* recv);
+int eqd_set_host_comm(eqd_handle* h, int32_t nranks, int32_t rank, eqd_allgather_fn fn, void* ctx);
 /* init-time shared-node sums the reference does with MPI before the loop:
  * nodalMassArr, fnms (assembleGlobalMass.f90:40-41) and arn (meshgen.f90:154).
  * Call once after eqd_set_* if the host has NOT already summed them.         */

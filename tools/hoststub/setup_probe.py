@@ -49,7 +49,11 @@ def main():
     ap.add_argument("--device-ops", type=int, default=1)
     ap.add_argument("--box", type=int, default=2)
     ap.add_argument("--repeat", type=int, default=1)
+    ap.add_argument("--np", default="1x1x1", help="decomposition; the probe sets up sub-domain --rank of it (no exchange: eqd_sum_shared is skipped)")
+    ap.add_argument("--rank", type=int, default=0)
+    ap.add_argument("--march", type=int, default=1)
     args = ap.parse_args()
+    decomp = tuple(int(x) for x in args.np.split("x"))
     lib, stub = build_stub()
     os.environ["EQD_VERBOSE"] = "1"
     from eqdyna_b200 import build, cases, device as dev
@@ -58,17 +62,18 @@ def main():
     S = C.CDLL(stub)
     S.stub_prefault()                          # "device" arena faulted in before anything is timed
     t0 = time.time()
-    w = World(cases.materialize(args.case), np_xyz=(1, 1, 1), nstep=20)
-    w.build(0, sum_shared=False)
-    v = w.view(0)
+    w = World(cases.materialize(args.case), np_xyz=decomp, nstep=20)
+    w.build(args.rank, sum_shared=False)
+    v = w.view(args.rank)
     print("[probe] host state built in %.2f s: %d elements, %d nodes" % (time.time() - t0, v.Ne, v.Nn), flush=True)
     for rep in range(args.repeat):
         t0 = time.perf_counter()
-        d = dev.Domain(v, compute_ops=bool(args.device_ops))
+        d = dev.Domain(v, compute_ops=bool(args.device_ops), options={"march": args.march})
         t1 = time.perf_counter()
         d.set_option("box", args.box)
         d.set_option("box_compact", 1)
-        d.sum_shared()                         # runs finalize (no neighbours: no communicator needed)
+        if decomp == (1, 1, 1):
+            d.sum_shared()                     # runs finalize (no neighbours: no communicator needed)
         t2 = time.perf_counter()
         fp = (C.c_uint64 * 3)()
         S.stub_fingerprint(fp)
