@@ -68,11 +68,19 @@ subroutine driver
     ! The marching kernel (DESIGN.md 3e; elastic runs) is chosen BEFORE eqd_set_mesh:
     ! ierr = eqd_set_option(h, 'march'//c_null_char, 1_c_int32_t)
 
+    ! one box (<= 8 GPUs, peers mappable): the library's set-up exchanges go through MPI_Allgather and the steps over
+    ! peer memory.  Across boxes (or with EQD_USE_NCCL set) give it an NCCL communicator as well: the step exchange
+    ! then falls back to ncclSend / ncclRecv where a neighbour's memory cannot be mapped.
     if (npx*npy*npz > 1) then
-        if (me == masterProcsId) ierr = eqd_get_unique_id(id128)
-        call MPI_Bcast(id128, 128, MPI_CHARACTER, masterProcsId, MPI_COMM_WORLD, mpierr)
-        ierr = eqd_set_comm(h, id128, npx*npy*npz, me)
-        call check('eqd_set_comm')
+        ierr = eqd_set_host_comm(h, npx*npy*npz, me, c_funloc(eqd_mpi_allgather), c_null_ptr)
+        call check('eqd_set_host_comm')
+        call get_environment_variable('EQD_USE_NCCL', length=k)
+        if (k > 0) then
+            if (me == masterProcsId) ierr = eqd_get_unique_id(id128)
+            call MPI_Bcast(id128, 128, MPI_CHARACTER, masterProcsId, MPI_COMM_WORLD, mpierr)
+            ierr = eqd_set_comm(h, id128, npx*npy*npz, me)
+            call check('eqd_set_comm')
+        endif
     endif
 
     ! ---- the loop of driver.f90:9-34, in chunks of 100 steps: the banner of driver.f90:13-17 appears at

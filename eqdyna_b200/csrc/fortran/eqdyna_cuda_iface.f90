@@ -203,4 +203,20 @@ module eqdyna_cuda_iface
             integer(c_int64_t), intent(out) :: stats(8)
         end function
     end interface
+
+contains
+
+    ! the eqd_allgather_fn of eqd_set_host_comm over the reference's communicator (eqdyna3d.f90:19-21)
+    integer(c_int32_t) function eqd_mpi_allgather(ctx, send, nbytes, recv) bind(C)
+        include 'mpif.h'
+        type(c_ptr), value :: ctx, send, recv
+        integer(c_int64_t), value :: nbytes
+        character(kind=c_char), pointer :: s(:), r(:)
+        integer :: nranks, mpierr
+        call MPI_Comm_size(MPI_COMM_WORLD, nranks, mpierr)
+        call c_f_pointer(send, s, [nbytes])
+        call c_f_pointer(recv, r, [nbytes*nranks])
+        call MPI_Allgather(s, int(nbytes), MPI_BYTE, r, int(nbytes), MPI_BYTE, MPI_COMM_WORLD, mpierr)
+        eqd_mpi_allgather = mpierr
+    end function eqd_mpi_allgather
 end module eqdyna_cuda_iface
