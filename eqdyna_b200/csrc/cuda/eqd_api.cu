@@ -1071,6 +1071,19 @@ int eqd_create(const eqd_params* p, int device, eqd_handle** out) {
     // cudaMemset on the legacy stream (a pageable H2D copy may return before its
     // DMA has landed), and a blocking stream is ordered after those.
     CK(cudaStreamCreate(&h->stream));
+    // L2 -> DRAM fetch size.  The node kernels that follow a node list (perimeter nodes of the marching bundles, rank
+    // faces, split nodes) read single 8-byte values a row of the lattice apart; with the default of 64 B every such
+    // read pulls two sectors from DRAM (ncu, r02_j: 2.0 L2 sectors per L1 sector in k_node_update3's list variant,
+    // 1.2 in the streaming kernels).  EQD_L2_FETCH = 32 / 64 / 128 sets the device limit (a hint; per context).
+    if (const char* e = getenv("EQD_L2_FETCH")) {
+      const int v = atoi(e);
+      if (v == 32 || v == 64 || v == 128) {
+        if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v) != cudaSuccess) cudaGetLastError();
+      }
+      size_t now = 0;
+      if (cudaDeviceGetLimit(&now, cudaLimitMaxL2FetchGranularity) != cudaSuccess) cudaGetLastError();
+      if (getenv("EQD_VERBOSE")) fprintf(stderr, "[eqd] L2 fetch granularity: asked %d, device reports %zu\n", v, now);
+    }
     h->stage = shared_stage(h->device);
     h->body = (p->C_elastic == 0) || (p->rdampm != 0.0);
     h->plastic = p->C_elastic == 0;

@@ -83,7 +83,9 @@ enum {
   EQD_F_SRC_EVOL = 13,   /* (nftnd(1),nGmSamples) output_src_evol samples    */
   EQD_F_TPHIST = 14,     /* onFaultTPHist(2,nftmx,nstep,ntotft), friclaw 5   */
   EQD_F_MASS = 15,       /* nodalMassArr(Neq) (after eqd_sum_shared)         */
-  EQD_F_FNMS = 16,       /* fnms(Nn)                                         */
+  EQD_F_FNMS = 16,       /* fnms(Nn); after eqd_compute_elem_ops: 0 on nodes whose
+                          * dofs are all fixed (the loop never reads it there; the
+                          * reference accumulates it, assembleGlobalMass.f90:322)      */
   EQD_F_ARN = 17,        /* arn(nftmx,ntotft)                                */
   EQD_F_ELEDET = 18,     /* eledet(Ne)       | element operators as the device  */
   EQD_F_ELESHP = 19,     /* eleshp(3,8,Ne)   | holds them (uploaded by          */

@@ -1,6 +1,6 @@
 """Multi-process / multi-GPU parity (-m gpu, needs >= 2 devices; skipped on a
-single-GPU box): one process per sub-domain, nodal-force halos over
-ncclSend/ncclRecv exactly as `bench.py --gpus N` runs them, compared with the
+single-GPU box): one process per sub-domain, nodal-force halos over peer memory
+(or ncclSend/ncclRecv) exactly as `bench.py --gpus N` runs them, compared with the
 CPU oracle of the same decomposition at the contract tolerance."""
 import os
 import socket
@@ -48,14 +48,26 @@ def _worker(rank, world_size, port, case, decomp, nstep, overlap, own_rank_only,
         d.set_option("box_compact", 1)
     if march == 2:
         d.set_option("halo", 0)      # the ncclSend / ncclRecv exchange instead of peer memory
-    ids = [dev.unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(ids, src=0)
-    d.set_comm(ids[0], world_size, rank)
+    if march == 3:
+        # eqd_set_host_comm: the set-up exchanges go over the host's own all-gather (here gloo, MPI_Allgather in the
+        # Fortran host), the steps over peer memory; the library creates no NCCL communicator
+        def allgather(send, nr):
+            s = torch.frombuffer(send, dtype=torch.uint8)
+            out_t = torch.empty(nr * s.numel(), dtype=torch.uint8)
+            dist.all_gather_into_tensor(out_t, s)
+            return out_t.numpy()
+        d.set_host_comm(world_size, rank, allgather)
+    else:
+        ids = [dev.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        d.set_comm(ids[0], world_size, rank)
     if own_rank_only:
         d.sum_shared()
     d.set_option("overlap", overlap)   # 1: halo on the communication stream under the interior tiles
     n = v.nstep
     d.run(1, n // 2)          # two chunks: the halo state must survive a return to the host
+    if march == 3:
+        assert d.halo_mode() == 2, "peer memory carries the steps when only the host's communicator is given"
     d.run(n // 2 + 1, n)
     d.fetch_into_view()
     np.savez(os.path.join(out, "rank%d.npz" % rank), disp=v.dispArr, vel=v.velArr, fric=v.fric, fnft=v.fnft,
@@ -69,11 +81,12 @@ def _worker(rank, world_size, port, case, decomp, nstep, overlap, own_rank_only,
                          [("test.tpv8", (2, 1, 1), 0, 1, 0, 0), ("test.tpv104", (1, 2, 1), 60, 1, 0, 0), ("test.tpv8", (2, 1, 1), 40, 0, 0, 0),
                           ("test.tpv104", (1, 2, 1), 60, 1, 1, 0), ("test.tpv10", (2, 1, 2), 60, 2, 0, 0),
                           ("test.tpv104", (2, 1, 1), 60, 1, 1, 1), ("test.tpv104", (1, 2, 1), 60, 0, 0, 1), ("test.tpv104", (2, 1, 1), 60, -1, 1, 1),
-                          ("test.tpv8", (1, 1, 2), 40, -1, 0, 2)],
+                          ("test.tpv8", (1, 1, 2), 40, -1, 0, 2), ("test.tpv104", (2, 1, 1), 60, -1, 1, 3), ("test.tpv10", (1, 1, 2), 40, -1, 0, 3)],
                          ids=["tpv8-2x1x1", "tpv104-1x2x1-fault-on-rank-face", "tpv8-2x1x1-no-overlap",
                               "tpv104-1x2x1-own-rank-device-ops-sum-shared", "tpv10-2x1x2-face-tiles-first",
                               "tpv104-2x1x1-march-own-rank-device-ops", "tpv104-1x2x1-march-no-overlap",
-                              "tpv104-2x1x1-march-auto-overlap-boundary-list-first", "tpv8-1x1x2-march-nccl-sendrecv-instead-of-peer-memory"])
+                              "tpv104-2x1x1-march-auto-overlap-boundary-list-first", "tpv8-1x1x2-march-nccl-sendrecv-instead-of-peer-memory",
+                              "tpv104-2x1x1-march-host-communicator-own-rank-sum-shared", "tpv10-1x1x2-march-host-communicator"])
 def test_nccl_processes_match_oracle(tmp_path, case, decomp, nstep, overlap, own_rank_only, march):
     import torch
     import torch.multiprocessing as mp

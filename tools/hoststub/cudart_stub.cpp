@@ -87,6 +87,8 @@ struct cudaIpcMemHandle_st { char reserved[64]; };
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_st*, void*) { return 1; }   // no peers in the stand-in
 cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_st, unsigned) { return 1; }
 cudaError_t cudaIpcCloseMemHandle(void*) { return 0; }
+cudaError_t cudaDeviceSetLimit(int, size_t) { return 0; }
+cudaError_t cudaDeviceGetLimit(size_t* v, int) { *v = 0; return 0; }
 cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, const void*, int, size_t) { *n = 3; return 0; }
 cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessorWithFlags(int* n, const void*, int, size_t, unsigned) { *n = 3; return 0; }
 cudaError_t cudaLaunchKernel(const void*, dim3, dim3, void**, size_t, cudaStream_t) { return 0; }   // kernels do not run

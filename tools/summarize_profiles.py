@@ -67,10 +67,8 @@ def full(path, counts):
     hdr, units = rows[0], rows[1]
     out = {}
     for r in rows[2:]:
-        name = short(r[hdr.index("Kernel Name")])
-        if name in out:
-            continue
-        d = {}
+        name = short(r[hdr.index("Kernel Name")])   # a later launch of the same kernel replaces an earlier one: the steady-state step
+        d = {"template": r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "")}
         for k in KEEP:
             if k in hdr:
                 d[k] = (r[hdr.index(k)] + " " + units[hdr.index(k)]).strip()
