@@ -2075,9 +2075,11 @@ int eqd_run(eqd_handle* h, int32_t nt_begin, int32_t nt_end) {
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     if (h->timing) { CK(cudaEventCreate(&t0)); CK(cudaEventCreate(&t1)); CK(cudaEventRecord(t0, h->stream)); }
     for (int nt = nt_begin; nt <= nt_end; ++nt) {
-      // auto: with rank neighbours the exchange and the fault solver go to the second stream; with marching strips the
-      // boundary work list is swept first, so that the exchange also hides under the interior sweep
-      const int ov = !h->commStream ? 0 : h->optOverlap < 0 ? (multi ? (h->cls[CLS_MARCH].n || h->cls[CLS_MARCHP].n ? 2 : 1) : 0) : h->optOverlap;
+      // auto: with rank neighbours the exchange and the fault solver go to the second stream, under the next step's
+      // bulk node update.  Mode 2 (boundary work list first, exchange under the interior sweep) is an option only:
+      // measured slower on one box -- 1.619 against 1.577 ms at 2 GPUs, 0.534 against 0.495 ms at 8 (r02_k, r02_l) --
+      // because two half-filled persistent launches per class cost more than the exchange it hides
+      const int ov = !h->commStream ? 0 : h->optOverlap < 0 ? (multi ? 1 : 0) : h->optOverlap;
       step_pre(h, ov, multi, nt == nt_end);
       if (multi && !ov) halo_all_nccl(h, h->stream);
       step_post(h, ov);

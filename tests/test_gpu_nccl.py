@@ -80,12 +80,12 @@ def _worker(rank, world_size, port, case, decomp, nstep, overlap, own_rank_only,
 @pytest.mark.parametrize("case,decomp,nstep,overlap,own_rank_only,march",
                          [("test.tpv8", (2, 1, 1), 0, 1, 0, 0), ("test.tpv104", (1, 2, 1), 60, 1, 0, 0), ("test.tpv8", (2, 1, 1), 40, 0, 0, 0),
                           ("test.tpv104", (1, 2, 1), 60, 1, 1, 0), ("test.tpv10", (2, 1, 2), 60, 2, 0, 0),
-                          ("test.tpv104", (2, 1, 1), 60, 1, 1, 1), ("test.tpv104", (1, 2, 1), 60, 0, 0, 1), ("test.tpv104", (2, 1, 1), 60, -1, 1, 1),
+                          ("test.tpv104", (2, 1, 1), 60, 1, 1, 1), ("test.tpv104", (1, 2, 1), 60, 0, 0, 1), ("test.tpv104", (2, 1, 1), 60, 2, 1, 1),
                           ("test.tpv8", (1, 1, 2), 40, -1, 0, 2), ("test.tpv104", (2, 1, 1), 60, -1, 1, 3), ("test.tpv10", (1, 1, 2), 40, -1, 0, 3)],
                          ids=["tpv8-2x1x1", "tpv104-1x2x1-fault-on-rank-face", "tpv8-2x1x1-no-overlap",
                               "tpv104-1x2x1-own-rank-device-ops-sum-shared", "tpv10-2x1x2-face-tiles-first",
                               "tpv104-2x1x1-march-own-rank-device-ops", "tpv104-1x2x1-march-no-overlap",
-                              "tpv104-2x1x1-march-auto-overlap-boundary-list-first", "tpv8-1x1x2-march-nccl-sendrecv-instead-of-peer-memory",
+                              "tpv104-2x1x1-march-overlap-2-boundary-list-first", "tpv8-1x1x2-march-nccl-sendrecv-instead-of-peer-memory",
                               "tpv104-2x1x1-march-host-communicator-own-rank-sum-shared", "tpv10-1x1x2-march-host-communicator"])
 def test_nccl_processes_match_oracle(tmp_path, case, decomp, nstep, overlap, own_rank_only, march):
     import torch
