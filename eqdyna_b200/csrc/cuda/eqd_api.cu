@@ -99,14 +99,21 @@ struct DevBuf {
 
 // EQD_VERBOSE=1: wall-clock laps of the set-up phases on stderr
 struct Lap {
-  bool on; const char* what; std::chrono::steady_clock::time_point t;
-  explicit Lap(const char* w) : on(getenv("EQD_VERBOSE") != nullptr), what(w), t(std::chrono::steady_clock::now()) {}
+  bool on; const char* what; std::chrono::steady_clock::time_point t, ts;
+  explicit Lap(const char* w) : on(getenv("EQD_VERBOSE") != nullptr), what(w), t(std::chrono::steady_clock::now()), ts(t) {}
   void lap(const char* label) {
     if (!on) return;
     cudaDeviceSynchronize();
     auto n = std::chrono::steady_clock::now();
     fprintf(stderr, "[eqd] %s: %s %.3f s\n", what, label, std::chrono::duration<double>(n - t).count());
-    t = n;
+    t = ts = n;
+  }
+  void sub(const char* label) {   // a part of the lap that follows: printed, the lap's own clock runs on
+    if (!on) return;
+    cudaDeviceSynchronize();
+    auto n = std::chrono::steady_clock::now();
+    fprintf(stderr, "[eqd] %s:   . %s %.3f s\n", what, label, std::chrono::duration<double>(n - ts).count());
+    ts = n;
   }
 };
 
@@ -1265,6 +1272,7 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
     int gny = 0, gnz = 0;
     const bool gridOk = infer_grid(h->conn.data(), h->etype.data(), Ne, Nn, gny, gnz);
     h->elemCode.assign(Ne, 0);
+    lap.sub("lattice strides");
     // ---- marching class: the box elements of the structured lattice leave the regular tile class (option "march";
     // the kernel covers the elastic path with Kosloff-Frazier hourglass control and no body force)
     {
@@ -1297,6 +1305,7 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
         }
         h->mNxg = nxg;
       }
+      lap.sub("node planes in x");
       if (eligible && !members[CLS_REG].empty()) {
         int dev = 0, sms = 148;
         CK(cudaGetDevice(&dev));
@@ -1306,12 +1315,14 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
         MarchPlan MP;
         plan_march(h->conn.data(), h->etype.data(), h->coor.data(), h->info.data(), members[CLS_REG], Nn, gny, gnz, h->mNxg, perSm * sms,
                    h->optMarch == 2 ? 3 : h->optMarch == 3 ? 1 : 0, MP);   // 2: ghost rows and columns, 3: ghost columns (y) only
+        lap.sub("plan_march");
         if (MP.n > 0) {
           M.n = MP.n; M.S = MP.S; M.PFS = MP.PFS;
           h->mGrid = MP.grid; h->mBundles = (int)MP.rec.size(); h->mFused = MP.nFused;
           h->mSlotB0 = MP.nBundlesA < (int)MP.rec.size() ? MP.rec[MP.nBundlesA].n0 : MP.PFS;
           h->mRec.upload(MP.rec); h->mCtaFirstA.upload(MP.ctaFirstA); h->mCtaFirstB.upload(MP.ctaFirstB);
           h->mCode.upload(MP.code); h->mSlotBundle.upload(MP.slotBundle);
+          lap.sub("plan uploads");
           // host copy of the node slots for the slot table: only the nodes that emit a partial
           M.tnodeH.resize(MP.code.size());
           parallel_range(MP.code.size(), [&](size_t b, size_t e) {
@@ -1326,10 +1337,12 @@ int eqd_set_mesh(eqd_handle* h, int32_t Nn, int32_t Ne, int32_t Neq, int32_t siz
           parallel_range((size_t)M.S, [&](size_t sb, size_t se) {
             for (size_t sl = sb; sl < se; ++sl) if (M.refId[sl] >= 0 && h->mOwner[sl]) h->elemCode[M.refId[sl]] = CLS_MARCH | ((int)sl << 2);
           });
+          lap.sub("slot nodes + element codes");
           M.pf.alloc((size_t)3 * M.PFS);
           M.stress.alloc((size_t)6 * M.S);
           M.nBoxElems = M.n;
           members[CLS_REG] = std::move(MP.leftover);
+          lap.sub("partial + stress buffers");
         }
       }
       h->pingpong = h->optMarch >= 2 && M.n > 0;
