@@ -99,3 +99,61 @@ def test_sum_shared_over_the_hosts_allgather(tmp_path):
         outs.append(out)
     for r, (p, out) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and "HOSTCOMM_OK %d" % r in out, out[-3000:]
+
+
+ERRORS = textwrap.dedent(r"""
+    import ctypes as C, os, sys
+    import numpy as np
+    sys.path.insert(0, %(root)r)
+    sys.path.insert(0, os.path.join(%(root)r, "tools", "hoststub"))
+    import setup_probe
+    setup_probe.OUT = sys.argv[1]
+    lib = os.path.join(setup_probe.OUT, "libeqdyna_b200_hoststub.so")
+    from eqdyna_b200 import build, cases, device as dev
+    from eqdyna_b200.host import World
+    build.cuda_lib_path = lambda: lib
+    w = World(cases.materialize("test.tpv8"), np_xyz=(2, 1, 1), nstep=4)
+    w.build(rank=0, sum_shared=False)
+    v = w.view(0)
+    def broken(send, n):
+        raise RuntimeError("the host's communicator is down")
+    # rank / nranks must be the sub-domain's own (error 4, as eqd_set_comm)
+    for bad in ((3, 0), (2, 1), (2, -1)):
+        d = dev.Domain(v)
+        try:
+            d.set_host_comm(bad[0], bad[1], broken)
+            raise SystemExit("accepted nranks, rank = %%r" %% (bad,))
+        except dev.StepError as e:
+            assert e.code == 4, e
+        d.close()
+    # a failing all-gather surfaces as an error of the call that needed it, not as a crash
+    d = dev.Domain(v, host_comm=(2, 0, broken))
+    try:
+        d.sum_shared()
+        raise SystemExit("eqd_sum_shared went through a broken communicator")
+    except dev.StepError as e:
+        assert e.code == 3 and "all-gather" in str(e), e
+    d.close()
+    # after the first eqd_sum_shared / eqd_run the communicator is fixed
+    w1 = World(cases.materialize("test.tpv8"), np_xyz=(1, 1, 1), nstep=4)
+    w1.build(rank=0, sum_shared=False)
+    d = dev.Domain(w1.view(0))
+    d.sum_shared()
+    try:
+        d.set_host_comm(1, 0, broken)
+        raise SystemExit("eqd_set_host_comm accepted after finalize")
+    except dev.StepError as e:
+        assert e.code == 4, e
+    d.close()
+    print("HOSTCOMM_ERRORS_OK")
+""")
+
+
+def test_host_comm_argument_and_failure_paths(tmp_path):
+    sys.path.insert(0, os.path.join(ROOT, "tools", "hoststub"))
+    import setup_probe
+    setup_probe.OUT = str(tmp_path)
+    setup_probe.build_stub()
+    r = subprocess.run([sys.executable, "-c", ERRORS % {"root": ROOT}, str(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and "HOSTCOMM_ERRORS_OK" in r.stdout, r.stdout[-3000:]
